@@ -1,0 +1,134 @@
+"""ctypes binding of libsrm_physics.so (include/srm_physics.h).
+
+This is the reference-side stub a maintainer would add: plain pointers and
+sizes, no torch types in the signatures.  torch is used by the callers only to own device memory
+and streams.  There is no CPU fallback: if the shared library is missing or no CUDA device is
+usable, loading / handle creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrm_physics.so")
+
+SRM_ABI_VERSION = 1
+SRM_N_TERMS = 8
+TERM_NAMES = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
+SRM_FLUID_DG, SRM_FLUID_GC = 0, 1
+SRM_PVT_SPLINE, SRM_PVT_POLYNOMIAL = 0, 1
+SRM_NUMERICS_REFERENCE, SRM_NUMERICS_CLOSED_FORM = 0, 1
+SRM_FLAG_SAVE_FOR_BACKWARD = 1
+
+EXPORTS = (
+    "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
+    "srm_pvt_eval", "srm_denormalize_log", "srm_wells", "srm_forward", "srm_backward",
+)
+
+
+class SrmWell(C.Structure):
+    _fields_ = [("i", C.c_int32), ("j", C.c_int32), ("k", C.c_int32), ("q_target", C.c_float),
+                ("pwf_min", C.c_float), ("rw", C.c_float), ("hc", C.c_float),
+                ("shut_start", C.c_float), ("shut_stop", C.c_float)]
+
+
+class SrmConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("dx", C.c_float), ("dy", C.c_float), ("dz", C.c_float),
+        ("C", C.c_float), ("Dc", C.c_float),
+        ("phi", C.c_float), ("cf", C.c_float), ("Sgi", C.c_float), ("krg", C.c_float),
+        ("kx_ky", C.c_float), ("kv_kh", C.c_float),
+        ("fluid_type", C.c_int32),
+        ("pvt_method", C.c_int32), ("spline_order", C.c_int32), ("n_knots", C.c_int32), ("n_props", C.c_int32),
+        ("knots", C.POINTER(C.c_float)), ("spline_w", C.POINTER(C.c_float)), ("spline_v", C.POINTER(C.c_float)),
+        ("p_min", C.c_float), ("p_max", C.c_float),
+        ("n_wells", C.c_int32), ("wells", C.POINTER(SrmWell)),
+        ("use_blocking_factor", C.c_int32), ("n_intervals", C.c_int32),
+        ("numerics", C.c_int32), ("tde_in_dom", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the library and declare every prototype of include/srm_physics.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the physics-loss path.")
+    lib = C.CDLL(path)
+    vp, i32, i64, fp = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.srm_version.restype = C.c_int
+    lib.srm_version.argtypes = []
+    lib.srm_last_error.restype = C.c_char_p
+    lib.srm_last_error.argtypes = []
+    lib.srm_create.restype = C.c_int
+    lib.srm_create.argtypes = [C.POINTER(SrmConfig), C.POINTER(vp)]
+    lib.srm_destroy.restype = None
+    lib.srm_destroy.argtypes = [vp]
+    lib.srm_workspace_bytes.restype = C.c_size_t
+    lib.srm_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.srm_pvt_eval.restype = C.c_int
+    lib.srm_pvt_eval.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.srm_denormalize_log.restype = C.c_int
+    lib.srm_denormalize_log.argtypes = [i64, vp, fp, fp, fp, fp, vp, vp]
+    lib.srm_wells.restype = C.c_int
+    lib.srm_wells.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.srm_forward.restype = C.c_int
+    lib.srm_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.srm_backward.restype = C.c_int
+    lib.srm_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
+    if lib.srm_version() != SRM_ABI_VERSION:
+        raise RuntimeError(f"libsrm_physics ABI {lib.srm_version()} != binding {SRM_ABI_VERSION}")
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+class SrmError(RuntimeError):
+    pass
+
+
+def check(lib, rc: int, what: str):
+    if rc != 0:
+        msg = lib.srm_last_error()
+        raise SrmError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz: float, C_: float, Dc: float,
+                phi: float, cf: float, Sgi: float, krg: float, kx_ky: float, kv_kh: float,
+                knots: np.ndarray, spline_w: np.ndarray, spline_v: np.ndarray, spline_order: int,
+                p_min: float, p_max: float, wells: Sequence[dict], use_blocking_factor: bool, n_intervals: int,
+                numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG):
+    """Fill an SrmConfig; returns (cfg, keepalive) -- keepalive owns the host arrays cfg points into."""
+    knots = np.ascontiguousarray(knots, dtype=np.float32)
+    spline_w = np.ascontiguousarray(spline_w, dtype=np.float32)
+    spline_v = np.ascontiguousarray(spline_v, dtype=np.float32)
+    assert spline_w.shape == (spline_v.shape[0], knots.size) and spline_v.shape[1] == 2
+    warr = (SrmWell * max(1, len(wells)))()
+    for n, w in enumerate(wells):
+        warr[n] = SrmWell(int(w["i"]), int(w["j"]), int(w["k"]), float(w["q_target"]), float(w["pwf_min"]),
+                          float(w["rw"]), float(w["hc"]), float(w["shut_start"]), float(w["shut_stop"]))
+    cfg = SrmConfig(
+        abi_version=SRM_ABI_VERSION, device=device, D=D, H=H, W=W, dx=dx, dy=dy, dz=dz, C=C_, Dc=Dc,
+        phi=phi, cf=cf, Sgi=Sgi, krg=krg, kx_ky=kx_ky, kv_kh=kv_kh, fluid_type=fluid_type,
+        pvt_method=SRM_PVT_SPLINE, spline_order=spline_order, n_knots=knots.size, n_props=spline_w.shape[0],
+        knots=_fptr(knots), spline_w=_fptr(spline_w), spline_v=_fptr(spline_v), p_min=p_min, p_max=p_max,
+        n_wells=len(wells), wells=warr, use_blocking_factor=int(bool(use_blocking_factor)),
+        n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)))
+    return cfg, (knots, spline_w, spline_v, warr)

@@ -1,0 +1,270 @@
+// C ABI of libsrm_physics.so (see include/srm_physics.h).  Host-side validation, handle
+// construction and dispatch to the kernel launchers.  No CPU compute path exists here.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "srm_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void srm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int srm_launch_denorm_log(int64_t n, const float* x, float kmin, float kmax, float lo, float hi, float* out, cudaStream_t s);
+int srm_launch_scatter_wells(const SrmHandle* h, int32_t B, const float* sorted, float* dense, cudaStream_t s);
+int srm_launch_unsort_wells(const SrmHandle* h, int32_t B, const float* sorted, float* out, cudaStream_t s);
+int srm_build_closed_form(SrmHandle* h, const SrmConfig* cfg);
+int srm_launch_pvt_eval_cf(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s);
+int srm_forward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                   const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                   float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s);
+int srm_backward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                    const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                    const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                    const SrmWs& ws, cudaStream_t s);
+
+extern "C" {
+
+int srm_version(void) { return SRM_ABI_VERSION; }
+const char* srm_last_error(void) { return g_err; }
+
+int srm_create(const SrmConfig* cfg, SrmHandle** out) {
+  if (!cfg || !out) { srm_set_error("srm_create: null argument"); return SRM_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != SRM_ABI_VERSION) {
+    srm_set_error("srm_create: abi_version %d != %d", cfg->abi_version, SRM_ABI_VERSION);
+    return SRM_ERR_INVALID;
+  }
+  if (cfg->D < 1 || cfg->H < 1 || cfg->W < 1 || (int64_t)cfg->D * cfg->H * cfg->W > (int64_t)INT32_MAX / 2) {
+    srm_set_error("srm_create: bad grid %d x %d x %d", cfg->D, cfg->H, cfg->W);
+    return SRM_ERR_INVALID;
+  }
+  if (cfg->fluid_type != SRM_FLUID_DG) { srm_set_error("srm_create: only SRM_FLUID_DG is implemented"); return SRM_ERR_INVALID; }
+  if (cfg->pvt_method != SRM_PVT_SPLINE) { srm_set_error("srm_create: only SRM_PVT_SPLINE is implemented"); return SRM_ERR_INVALID; }
+  if (cfg->n_knots < 2 || cfg->n_knots > SRM_MAXK || cfg->n_props < 2 || cfg->n_props > SRM_MAXP ||
+      !cfg->knots || !cfg->spline_w || !cfg->spline_v) {
+    srm_set_error("srm_create: bad spline table (n_knots=%d, n_props=%d)", cfg->n_knots, cfg->n_props);
+    return SRM_ERR_INVALID;
+  }
+  if (cfg->spline_order != 1 && cfg->spline_order != 2) { srm_set_error("srm_create: spline_order must be 1 or 2"); return SRM_ERR_INVALID; }
+  for (int i = 1; i < cfg->n_knots; ++i)
+    if (!(cfg->knots[i] > cfg->knots[i - 1])) { srm_set_error("srm_create: knots must be strictly ascending"); return SRM_ERR_INVALID; }
+  if (cfg->n_wells < 0 || (cfg->n_wells > 0 && !cfg->wells)) { srm_set_error("srm_create: bad wells"); return SRM_ERR_INVALID; }
+  if (cfg->numerics != SRM_NUMERICS_REFERENCE && cfg->numerics != SRM_NUMERICS_CLOSED_FORM) {
+    srm_set_error("srm_create: unknown numerics %d", cfg->numerics);
+    return SRM_ERR_INVALID;
+  }
+  if (cfg->numerics == SRM_NUMERICS_CLOSED_FORM && cfg->spline_order != 1) {
+    srm_set_error("srm_create: SRM_NUMERICS_CLOSED_FORM needs spline_order 1 (order 2 is not piecewise polynomial)");
+    return SRM_ERR_INVALID;
+  }
+  if (cfg->use_blocking_factor && (cfg->n_intervals < 1 || cfg->n_intervals > 64)) {
+    srm_set_error("srm_create: n_intervals out of range");
+    return SRM_ERR_INVALID;
+  }
+  for (int w = 0; w < cfg->n_wells; ++w) {
+    const SrmWell& x = cfg->wells[w];
+    if (x.i < 0 || x.i >= cfg->W || x.j < 0 || x.j >= cfg->H || x.k < 0 || x.k >= cfg->D) {
+      srm_set_error("srm_create: well %d at (i=%d,j=%d,k=%d) outside the grid", w, x.i, x.j, x.k);
+      return SRM_ERR_INVALID;
+    }
+  }
+  int ndev = 0;
+  SRM_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) { srm_set_error("srm_create: device %d of %d", cfg->device, ndev); return SRM_ERR_CUDA; }
+  SRM_CUDA_CHECK(cudaSetDevice(cfg->device));
+
+  SrmHandle* h = new (std::nothrow) SrmHandle();
+  if (!h) { srm_set_error("srm_create: out of host memory"); return SRM_ERR_INVALID; }
+  std::memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->cfg.knots = h->cfg.spline_w = h->cfg.spline_v = nullptr;
+  h->cfg.wells = nullptr;
+  h->device = cfg->device;
+  SRM_CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
+
+  SrmDev& P = h->dev;
+  P.D = cfg->D; P.H = cfg->H; P.W = cfg->W; P.N = cfg->D * cfg->H * cfg->W;
+  P.dx = cfg->dx; P.dy = cfg->dy; P.dz = cfg->dz;
+  P.idx = 1.0f / cfg->dx; P.idy = 1.0f / cfg->dy; P.idz = 1.0f / cfg->dz;
+  P.dv = (cfg->dx * cfg->dy) * cfg->dz;
+  P.C = cfg->C; P.Dc = cfg->Dc; P.invDc = 1.0f / cfg->Dc;
+  P.dvDc = P.dv / cfg->Dc;
+  P.phi = cfg->phi; P.cf = cfg->cf; P.phicf = cfg->phi * cfg->cf;
+  P.Sgi = cfg->Sgi; P.krg = cfg->krg;
+  P.dvSgi_phi = (P.dv * cfg->Sgi) * cfg->phi;
+  P.kx_ky = cfg->kx_ky; P.kv_kh = cfg->kv_kh;
+  P.p_min = cfg->p_min; P.p_max = cfg->p_max;
+  P.tde_in_dom = cfg->tde_in_dom;
+  P.use_blk = cfg->use_blocking_factor; P.n_int = cfg->n_intervals;
+  P.n_knots = cfg->n_knots; P.order = cfg->spline_order; P.n_props = cfg->n_props;
+  for (int i = 0; i < cfg->n_knots; ++i) {
+    P.c[i] = cfg->knots[i];
+    P.c2[i] = cfg->knots[i] * cfg->knots[i];
+    for (int q = 0; q < cfg->n_props; ++q) P.w[q][i] = cfg->spline_w[q * cfg->n_knots + i];
+  }
+  for (int q = 0; q < cfg->n_props; ++q) { P.v[q][0] = cfg->spline_v[2 * q]; P.v[q][1] = cfg->spline_v[2 * q + 1]; }
+
+  // wells: [k,j,i] -> flat cell, sorted (stable) by cell; integer work, bit-exact
+  P.n_wells = cfg->n_wells;
+  if (cfg->n_wells > 0) {
+    std::vector<WellDev> wd(cfg->n_wells);
+    for (int w = 0; w < cfg->n_wells; ++w) {
+      const SrmWell& x = cfg->wells[w];
+      wd[w].cell = (x.k * cfg->H + x.j) * cfg->W + x.i;
+      wd[w].orig = w;
+      wd[w].q_target = x.q_target; wd[w].pwf_min = x.pwf_min; wd[w].rw = x.rw; wd[w].hc = x.hc;
+      wd[w].shut_start = x.shut_start; wd[w].shut_stop = x.shut_stop;
+    }
+    std::stable_sort(wd.begin(), wd.end(), [](const WellDev& a, const WellDev& b) { return a.cell < b.cell; });
+    cudaError_t e = cudaMalloc((void**)&h->d_wells, sizeof(WellDev) * cfg->n_wells);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_wells, wd.data(), sizeof(WellDev) * cfg->n_wells, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { srm_set_error("srm_create: wells upload: %s", cudaGetErrorString(e)); srm_destroy(h); return SRM_ERR_CUDA; }
+    P.wells = h->d_wells;
+  }
+  if (cfg->spline_order == 1) {
+    int rc = srm_build_closed_form(h, cfg);
+    if (rc) { srm_destroy(h); return rc; }
+  }
+  *out = h;
+  return SRM_OK;
+}
+
+void srm_destroy(SrmHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->d_wells) cudaFree(h->d_wells);
+  if (h->d_cf) cudaFree(h->d_cf);
+  delete h;
+}
+
+size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t flags) {
+  if (!h || B < 0) return 0;
+  (void)flags;
+  // the backward fields are always carved so that srm_backward can run on any forward workspace
+  return srm_carve(nullptr, B, h->dev.N, h->dev.n_wells, true).bytes;
+}
+
+int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, void* stream) {
+  if (!h || n < 0 || (n > 0 && !p)) { srm_set_error("srm_pvt_eval: bad argument"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM) return srm_launch_pvt_eval_cf(h, n, p, val, dval, (cudaStream_t)stream);
+  return srm_launch_pvt_eval_ref(h, n, p, val, dval, (cudaStream_t)stream);
+}
+
+int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi, float* out, void* stream) {
+  if (n < 0 || (n > 0 && (!x_norm || !out)) || !(kmin > 0.f) || !(kmax > kmin) || !(hi > lo)) {
+    srm_set_error("srm_denormalize_log: bad argument");
+    return SRM_ERR_INVALID;
+  }
+  return srm_launch_denorm_log(n, x_norm, kmin, kmax, lo, hi, out, (cudaStream_t)stream);
+}
+
+static int check_batch(const SrmHandle* h, int32_t B, int32_t R, const char* who) {
+  if (!h) { srm_set_error("%s: null handle", who); return SRM_ERR_INVALID; }
+  if (B < 1 || R < 1 || B > 65535) { srm_set_error("%s: B=%d (1..65535), R=%d", who, B, R); return SRM_ERR_INVALID; }
+  return SRM_OK;
+}
+
+int srm_wells(const SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+              const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp, float* q_dense,
+              float* pwf_dense, void* stream) {
+  int rc = check_batch(h, B, R, "srm_wells");
+  if (rc) return rc;
+  if (!kx || !p || !t_days) { srm_set_error("srm_wells: null input"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t N = h->dev.N;
+  if (q_dense) SRM_CUDA_CHECK(cudaMemsetAsync(q_dense, 0, sizeof(float) * B * N, s));
+  if (pwf_dense) SRM_CUDA_CHECK(cudaMemsetAsync(pwf_dense, 0, sizeof(float) * B * N, s));
+  const int nw = h->dev.n_wells;
+  if (nw == 0) return SRM_OK;
+  float* tmp = nullptr;
+  SRM_CUDA_CHECK(cudaMallocAsync((void**)&tmp, sizeof(float) * 3 * (size_t)B * nw, s));
+  float *tq = tmp, *tp = tmp + (size_t)B * nw, *td = tmp + 2 * (size_t)B * nw;
+  rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p, t_days, tq, tp, td, s);
+  if (!rc && qw) rc = srm_launch_unsort_wells(h, B, tq, qw, s);
+  if (!rc && pwfw) rc = srm_launch_unsort_wells(h, B, tp, pwfw, s);
+  if (!rc && dqdp) rc = srm_launch_unsort_wells(h, B, td, dqdp, s);
+  if (!rc && q_dense) rc = srm_launch_scatter_wells(h, B, tq, q_dense, s);
+  if (!rc && pwf_dense) rc = srm_launch_scatter_wells(h, B, tp, pwf_dense, s);
+  cudaFreeAsync(tmp, s);
+  return rc;
+}
+
+int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                float* terms_out, float* dom_out, float* qw_out, float* pwfw_out, void* workspace,
+                size_t workspace_bytes, int32_t flags, void* stream) {
+  int rc = check_batch(h, B, R, "srm_forward");
+  if (rc) return rc;
+  if (!kx || !p0 || !p1 || !dt1 || !dt2 || !t1 || !terms_out || !workspace) {
+    srm_set_error("srm_forward: null argument");
+    return SRM_ERR_INVALID;
+  }
+  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, true);
+  if (ws.bytes > workspace_bytes) {
+    srm_set_error("srm_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return SRM_ERR_WORKSPACE;
+  }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool save = (flags & SRM_FLAG_SAVE_FOR_BACKWARD) != 0;
+  h->st_valid = 0;
+  if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM)
+    rc = srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
+  else
+    rc = srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
+  if (rc) return rc;
+  if (qw_out && h->dev.n_wells) { rc = srm_launch_unsort_wells(h, B, ws.qw, qw_out, s); if (rc) return rc; }
+  if (pwfw_out && h->dev.n_wells) { rc = srm_launch_unsort_wells(h, B, ws.pwfw, pwfw_out, s); if (rc) return rc; }
+  if (save) {
+    h->st_ws = workspace; h->st_p0 = p0; h->st_p1 = p1; h->st_kx = kx; h->st_B = B; h->st_valid = 1;
+  }
+  return SRM_OK;
+}
+
+int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                 const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                 const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2, void* workspace,
+                 size_t workspace_bytes, int32_t flags, void* stream) {
+  int rc = check_batch(h, B, R, "srm_backward");
+  if (rc) return rc;
+  (void)flags;
+  if (!kx || !p0 || !p1 || !dt1 || !dt2 || !t1 || !dterms || !gp0 || !gp1 || !gdt1 || !gdt2 || !workspace) {
+    srm_set_error("srm_backward: null argument");
+    return SRM_ERR_INVALID;
+  }
+  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, true);
+  if (ws.bytes > workspace_bytes) {
+    srm_set_error("srm_backward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return SRM_ERR_WORKSPACE;
+  }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool have = h->st_valid && h->st_ws == workspace && h->st_p0 == p0 && h->st_p1 == p1 && h->st_kx == kx && h->st_B == B;
+  const bool cf = h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM;
+  if (!have) {
+    // recompute the forward state (PVT stage with derivatives, wells, residual field) into the workspace
+    float* terms_tmp = nullptr;
+    SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
+    rc = cf ? srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s)
+            : srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
+    cudaFreeAsync(terms_tmp, s);
+    if (rc) return rc;
+  }
+  rc = cf ? srm_backward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
+          : srm_backward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,591 @@
+// SRM_NUMERICS_REFERENCE kernels: the reference's fp32 arithmetic, op order preserved.
+//
+//   k_pvt_eval_ref    PVTLayer.call                                PVT_Layer_Subclassed.py:146-216
+//   k_stage_ref       PVT at p0 (invBg, d/dp[, d2/dp2]) and p1     physics_loss.py:88-95,111-117,137
+//   k_wells_ref       WellRatesPressure.compute_rates_and_bhp      well_rate_bhp_Subclassed.py:727-1007
+//   k_resid_fwd_ref   physics_error_gas residual + SSE partials    physics_loss.py:143-193,787-807
+//   k_finalize_fwd    mbc per sample, terms/counts                 physics_loss.py:193,800-832
+//   k_resid_adj_ref   hand-derived adjoint (what tape.gradient delivers, physics_loss.py:849-859)
+//   k_ibc_adj_ref     inner-boundary (well-cell) part of the adjoint
+//
+// These kernels are compute bound by construction (37 sqrt + up to 111 IEEE divisions per cell),
+// so they stage PVT results through the workspace instead of tiling: one thread per cell,
+// neighbour values re-read through L1/L2.
+#include <math_constants.h>
+#include "pvt_ref.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// block reduction of NV doubles; result valid in thread 0
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* smem /* [NV*32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) smem[q * 32 + warp] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double x = (lane < nw) ? smem[q * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      v[q] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PVT eval
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(kThreads) k_pvt_eval_ref(const __grid_constant__ SrmDev P, int64_t n,
+                                                           const float* __restrict__ p,
+                                                           float* __restrict__ val, float* __restrict__ dval) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  float pass;
+  const float x = srm_clamp(P, p[g], pass);
+  float v[NP], d[NP], d2[NP];
+  srm_spline_ref<NP, true, false>(P, 0, x, v, d, d2);
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    if (val) val[(int64_t)q * n + g] = v[q];
+    if (dval) dval[(int64_t)q * n + g] = d[q];   // derivative w.r.t. the clamped input (:196-201)
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage: PVT of every cell at both time levels -> workspace
+// ------------------------------------------------------------------------------------------
+template <bool SAVE>
+__global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ SrmDev P, int64_t total,
+                                                        const float* __restrict__ p0, const float* __restrict__ p1,
+                                                        float* __restrict__ A0, float* __restrict__ A0p,
+                                                        float* __restrict__ A1, float* __restrict__ G1,
+                                                        float* __restrict__ A0pp, float* __restrict__ G1p,
+                                                        float* __restrict__ A1p) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  float m0, m1;
+  const float x0 = srm_clamp(P, p0[g], m0);
+  const float x1 = srm_clamp(P, p1[g], m1);
+  {
+    float v[1], d[1], d2[1];
+    srm_spline_ref<1, true, SAVE>(P, 0, x0, v, d, d2);
+    A0[g] = v[0];
+    A0p[g] = d[0];                 // w.r.t. clamped input: enters cp unmasked (physics_loss.py:150)
+    if (SAVE) A0pp[g] = d2[0] * m0;
+  }
+  {
+    float v[2], d[2], d2[2];
+    srm_spline_ref<2, SAVE, false>(P, 0, x1, v, d, d2);
+    A1[g] = v[0];
+    G1[g] = __fmul_rn(v[0], v[1]);   // invBgug_n1 = invBg*invug   physics_loss.py:137
+    if (SAVE) {
+      A1p[g] = d[0] * m1;
+      G1p[g] = (d[0] * v[1] + v[0] * d[1]) * m1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wells: forward-mode dual numbers carry d/dp of the connection-cell pressure through the
+// min/max/clip/divide_no_nan chain with TensorFlow's gradient conventions.
+// ------------------------------------------------------------------------------------------
+struct Dual { float v, d; };
+__device__ __forceinline__ Dual dmk(float v, float d = 0.f) { Dual r; r.v = v; r.d = d; return r; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return dmk(__fadd_rn(a.v, b.v), a.d + b.d); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return dmk(__fsub_rn(a.v, b.v), a.d - b.d); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return dmk(__fmul_rn(a.v, b.v), a.d * b.v + a.v * b.d); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  const float q = __fdiv_rn(a.v, b.v);
+  return dmk(q, (a.d - q * b.d) / b.v);
+}
+// tf.math.divide_no_nan
+__device__ __forceinline__ Dual ddnn(Dual a, Dual b) { return (b.v == 0.f) ? dmk(0.f, 0.f) : a / b; }
+// tf.minimum / tf.maximum: ties route the gradient to the first argument
+__device__ __forceinline__ Dual dmin(Dual a, Dual b) { return (a.v <= b.v) ? a : b; }
+__device__ __forceinline__ Dual dmax(Dual a, Dual b) { return (a.v >= b.v) ? a : b; }
+// tf.clip_by_value(t, lo, hi)
+// value = max(min(t,hi),lo) (the kernel's cwiseMin/cwiseMax); gradient per _ClipByValueGrad:
+// to t where lo <= t <= hi, to lo where t < lo, to hi where t > hi
+__device__ __forceinline__ Dual dclip(Dual t, Dual lo, Dual hi) {
+  const bool below = t.v < lo.v, above = t.v > hi.v;
+  return dmk(fmaxf(fminf(t.v, hi.v), lo.v), ((!below && !above) ? t.d : 0.f) + (below ? lo.d : 0.f) + (above ? hi.d : 0.f));
+}
+
+// mg = krg*invBg*invug at a (dual) pressure                       well_rate_bhp_Subclassed.py:799
+__device__ __forceinline__ Dual mobility_ref(const SrmDev& P, Dual p) {
+  float pass;
+  const float x = srm_clamp(P, p.v, pass);
+  float v[2], d[2], d2[2];
+  srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
+  const float kA = __fmul_rn(P.krg, v[0]);
+  const float mg = __fmul_rn(kA, v[1]);
+  const float dmg = P.krg * (d[0] * v[1] + v[0] * d[1]) * pass * p.d;
+  return dmk(mg, dmg);
+}
+
+// compute_blocking_integral_and_factor, DG branch             well_rate_bhp_Subclassed.py:840-960
+__device__ Dual blocking_integral_ref(const SrmDev& P, Dual p, Dual pwf, Dual mg_n1) {
+  const int n = P.n_int;
+  const Dual delta = (pwf - p) / dmk((float)n);          // tf.linspace: delta = (stop-start)/n
+  Dual sum = dmk(0.f), mg_prev = mg_n1, pa = p;
+  for (int i = 0; i < n; ++i) {
+    const Dual pb = (i + 1 < n) ? p + delta * dmk((float)(i + 1)) : pwf;   // ends are exact
+    const Dual mg1 = mobility_ref(P, pb);                  // Sg1 = Sg_max -> same krg (:912)
+    const Dual dp = pa - pb;
+    sum = sum + dmk(0.5f) * (mg_prev + mg1) * dp;          // :920
+    mg_prev = mg1;
+    pa = pb;
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(128) k_wells_ref(const __grid_constant__ SrmDev P, int32_t B, int32_t R,
+                                                   const float* __restrict__ kx, const int32_t* __restrict__ sample_real,
+                                                   const float* __restrict__ pfield, const float* __restrict__ t_days,
+                                                   float* __restrict__ qw, float* __restrict__ pwfw,
+                                                   float* __restrict__ dqdp) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = P.n_wells;
+  if (g >= (int64_t)B * nw) return;
+  const int b = (int)(g / nw), w = (int)(g % nw);
+  const WellDev wd = P.wells[w];
+  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const float k = kx[(int64_t)r * P.N + wd.cell];
+  const Dual p = dmk(pfield[(int64_t)b * P.N + wd.cell], 1.0f);
+  // shut-in mask: 1 unless shut_start <= t <= shut_stop          welldata_processor.py:349-354
+  const float t = t_days[b];
+  const float open = (t >= wd.shut_start && t <= wd.shut_stop) ? 0.f : 1.f;
+  // Peaceman                                                  well_rate_bhp_Subclassed.py:782-788
+  const float ky = __fmul_rn(P.kx_ky, k);
+  const float ryx = __fdiv_rn(ky, k), rxy = __fdiv_rn(k, ky);
+  const float num = sqrtf(__fadd_rn(__fmul_rn(sqrtf(ryx), __fmul_rn(P.dx, P.dx)),
+                                    __fmul_rn(sqrtf(rxy), __fmul_rn(P.dy, P.dy))));
+  const float den = __fadd_rn(powf(ryx, 0.25f), powf(rxy, 0.25f));
+  const float ro = __fdiv_rn(__fmul_rn(0.28f, num), den);
+  const float two_pi = 6.283185307179586f;
+  float ck = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(two_pi, wd.hc), k), P.dz), P.C);
+  ck = __fdiv_rn(ck, logf(__fdiv_rn(ro, wd.rw)));
+  const Dual Ck = dmk(__fmul_rn(open, ck));
+  const Dual mg = mobility_ref(P, p);
+  const Dual pmin = dmk(wd.pwf_min), qt = dmk(wd.q_target), zero = dmk(0.f), tiny = dmk(1e-12f);
+  // ---- _non_iterative_method                                 :614-724
+  Dual ig_max = dmk(1.f);
+  if (P.use_blk) ig_max = blocking_integral_ref(P, p, pmin, mg);
+  const Dual dp_max = (p - pmin) + tiny;                                       // :650
+  const Dual blk_max = P.use_blk ? ddnn(ig_max, mg * dp_max) : ig_max;         // :654-657
+  const Dual ckb = Ck * blk_max;                                               // well_id == 1
+  const Dual qg_max = ckb * mg * dp_max;                                       // :662
+  const Dual qg_opt = dmax(dmin(qt, qg_max), zero);                            // :666
+  const Dual lam = dclip(ddnn(qg_opt, ckb * mg), zero, blk_max);               // :699
+  const Dual dp_opt = lam * dp_max;                                            // :721
+  const Dual pwf = dclip(p - dp_opt, pmin, p);                                 // :723
+  // ---- _compute_phase_rates                                  :963-1007
+  Dual ig = dmk(1.f);
+  if (P.use_blk) ig = blocking_integral_ref(P, p, pwf, mg);
+  const Dual dp = (p - pwf) + tiny;                                            // :987
+  const Dual blk = P.use_blk ? ddnn(ig, mg * dp) : ig;                         // :991
+  const Dual qg_max2 = Ck * blk * mg * dp;                                     // :997
+  const Dual qg = dmax(dmin(qt, qg_max2), zero);                               // :1001
+  qw[g] = qg.v;
+  pwfw[g] = pwf.v;
+  dqdp[g] = qg.d;
+}
+
+// first well (sorted by cell) with cell >= c
+__device__ __forceinline__ int well_lower_bound(const SrmDev& P, int c) {
+  int lo = 0, hi = P.n_wells;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (P.wells[mid].cell < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward residual
+// ------------------------------------------------------------------------------------------
+struct CellIdx { int i, j, k; int cW, cE, cS, cN, cD, cU; };   // neighbour cell offsets with edge replication
+__device__ __forceinline__ CellIdx cell_index(const SrmDev& P, int c) {
+  CellIdx x;
+  x.i = c % P.W;
+  const int t = c / P.W;
+  x.j = t % P.H;
+  x.k = t / P.H;
+  const int HW = P.H * P.W;
+  x.cW = (x.i > 0) ? c - 1 : c;
+  x.cE = (x.i < P.W - 1) ? c + 1 : c;
+  x.cS = (x.j > 0) ? c - P.W : c;
+  x.cN = (x.j < P.H - 1) ? c + P.W : c;
+  x.cD = (x.k > 0) ? c - HW : c;
+  x.cU = (x.k < P.D - 1) ? c + HW : c;
+  return x;
+}
+
+// (2.*k1*k2)/(k1+k2)                                             physics_loss.py:59-60
+__device__ __forceinline__ float harm_ref(float kc, float kn) {
+  return __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, kc), kn), __fadd_rn(kc, kn));
+}
+// C*k_f*krg*G_f*(1/dl)*(1/dl)                                    physics_loss.py:152-155
+__device__ __forceinline__ float coef_ref(const SrmDev& P, float kf, float Gf, float idl) {
+  return __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(P.C, kf), P.krg), Gf), idl), idl);
+}
+
+struct PerSample { float dt1, dt2; };
+
+__global__ void __launch_bounds__(kThreads) k_resid_fwd_ref(
+    const __grid_constant__ SrmDev P, int32_t B, int32_t R, const float* __restrict__ kx,
+    const int32_t* __restrict__ sample_real, const float* __restrict__ p0f, const float* __restrict__ p1f,
+    const float* __restrict__ dt1v, const float* __restrict__ dt2v, const float* __restrict__ A0f,
+    const float* __restrict__ A0pf, const float* __restrict__ A1f, const float* __restrict__ G1f,
+    const float* __restrict__ qw, float* __restrict__ divqw, float* __restrict__ dom_ws,
+    float* __restrict__ dom_out, double* __restrict__ sse, double* __restrict__ mb_sum,
+    double* __restrict__ q_sum) {
+  __shared__ double red[4 * 32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  double acc4[4] = {0.0, 0.0, 0.0, 0.0};   // dom^2, ibc^2, tde^2, mb_cells
+  if (c < P.N) {
+    const int64_t base = (int64_t)b * P.N;
+    const float* kr = kx + (int64_t)r * P.N;
+    const CellIdx ix = cell_index(P, c);
+    const float d1 = dt1v[b], d2 = dt2v[b];
+    const float p0 = p0f[base + c], p1 = p1f[base + c];
+    const float pW = p1f[base + ix.cW], pE = p1f[base + ix.cE];
+    const float pS = p1f[base + ix.cS], pN = p1f[base + ix.cN];
+    const float pD = p1f[base + ix.cD], pU = p1f[base + ix.cU];
+    const float G = G1f[base + c];
+    const float GW = __fmul_rn(__fadd_rn(G, G1f[base + ix.cW]), 0.5f);   // (a+b)/2. == *0.5 exactly
+    const float GE = __fmul_rn(__fadd_rn(G1f[base + ix.cE], G), 0.5f);
+    const float GS = __fmul_rn(__fadd_rn(G, G1f[base + ix.cS]), 0.5f);
+    const float GN = __fmul_rn(__fadd_rn(G1f[base + ix.cN], G), 0.5f);
+    const float GD = __fmul_rn(__fadd_rn(G, G1f[base + ix.cD]), 0.5f);
+    const float GU = __fmul_rn(__fadd_rn(G1f[base + ix.cU], G), 0.5f);
+    // static face permeabilities                               physics_loss.py:56-60
+    const float kc = kr[c];
+    const float kyc = __fmul_rn(P.kx_ky, kc), kzc = __fmul_rn(P.kv_kh, kc);
+    const float kW = harm_ref(kc, kr[ix.cW]);
+    const float kE = harm_ref(kr[ix.cE], kc);
+    const float kS = harm_ref(kyc, __fmul_rn(P.kx_ky, kr[ix.cS]));
+    const float kN = harm_ref(__fmul_rn(P.kx_ky, kr[ix.cN]), kyc);
+    const float kD = harm_ref(kzc, __fmul_rn(P.kv_kh, kr[ix.cD]));
+    const float kU = harm_ref(__fmul_rn(P.kv_kh, kr[ix.cU]), kzc);
+    const float a1 = coef_ref(P, kW, GW, P.idx);
+    const float a2 = coef_ref(P, kS, GS, P.idy);
+    const float a3 = coef_ref(P, kE, GE, P.idx);
+    const float a4 = coef_ref(P, kN, GN, P.idy);
+    const float a5 = coef_ref(P, kD, GD, P.idz);
+    const float a6 = coef_ref(P, kU, GU, P.idz);
+    // accumulation coefficient                                 physics_loss.py:149-150,156
+    const float A0 = A0f[base + c], A0p = A0pf[base + c], A1 = A1f[base + c];
+    const float cr = __fmul_rn(P.phicf, A0);
+    const float cp = __fmul_rn(P.Sgi, __fadd_rn(__fmul_rn(P.phi, A0p), cr));
+    const float a5t = __fmul_rn(P.invDc, __fdiv_rn(cp, d1));
+    // wells in this cell (scatter_nd sums duplicates)          well_rate_bhp_Subclassed.py:128-132
+    float q = 0.f, mask = 0.f;
+    if (P.n_wells > 0) {
+      const int first = well_lower_bound(P, c);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) {
+        q = __fadd_rn(q, qw[(int64_t)b * P.n_wells + w]);
+        mask += 1.f;
+      }
+    }
+    // p2 by linear extrapolation                               physics_loss.py:126
+    const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
+    const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), __fadd_rn(1.0f, rho)), p0);
+    // truncation term                                          physics_loss.py:171
+    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+    const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(__fadd_rn(d1, d2), p1));
+    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), __fdiv_rn(numr, den));
+    const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
+    // flux divergence                                          physics_loss.py:174
+    float s = __fadd_rn(-__fmul_rn(a1, pW), -__fmul_rn(a2, pS));
+    const float asum = __fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4);
+    s = __fadd_rn(s, __fmul_rn(asum, p1));
+    s = __fadd_rn(s, -__fmul_rn(a3, pE));
+    s = __fadd_rn(s, -__fmul_rn(a4, pN));
+    const float zt = __fadd_rn(__fmul_rn(a5, __fsub_rn(p1, pD)), __fmul_rn(a6, __fsub_rn(p1, pU)));   // 3-D extension
+    s = __fadd_rn(s, zt);
+    s = __fadd_rn(s, __fdiv_rn(q, P.dv));
+    const float divq = __fmul_rn(P.dv, s);
+    const float acc = __fmul_rn(__fmul_rn(P.dv, a5t), __fsub_rn(p1, p0));       // physics_loss.py:175
+    const float dom = P.tde_in_dom ? __fadd_rn(divq, __fadd_rn(acc, tde)) : __fadd_rn(divq, acc);
+    const float ibc = __fmul_rn(mask, divq);                                    // physics_loss.py:189
+    // material balance summand                                 physics_loss.py:193
+    const float mb = __fmul_rn(__fmul_rn(P.dvSgi_phi, __fsub_rn(A1, A0)), __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1)));
+    dom_ws[base + c] = dom;
+    if (dom_out) dom_out[base + c] = dom;
+    if (mask != 0.f) {
+      const int first = well_lower_bound(P, c);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) divqw[(int64_t)b * P.n_wells + w] = divq;
+    }
+    acc4[0] = (double)dom * (double)dom;
+    acc4[1] = (double)ibc * (double)ibc;
+    acc4[2] = (double)tde * (double)tde;
+    acc4[3] = (double)mb;
+  }
+  block_reduce<4>(acc4, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sse[SRM_TERM_DOM], acc4[0]);
+    atomicAdd(&sse[SRM_TERM_IBC], acc4[1]);
+    atomicAdd(&sse[SRM_TERM_TDE], acc4[2]);
+    atomicAdd(&mb_sum[b], acc4[3]);
+  }
+  // sum of the sample's well rates (once per sample)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double qs = 0.0;
+    for (int w = 0; w < P.n_wells; ++w) qs += (double)qw[(int64_t)b * P.n_wells + w];
+    q_sum[b] = qs;
+  }
+}
+
+// mbc_b = (-sum q) - sum mb_cells ; SSE_mbc ; terms/counts        physics_loss.py:193,800-832
+__global__ void k_finalize_fwd(const __grid_constant__ SrmDev P, int32_t B, double* __restrict__ sse,
+                               const double* __restrict__ mb_sum, const double* __restrict__ q_sum,
+                               float* __restrict__ mbc, float* __restrict__ terms_out) {
+  __shared__ double red[32];
+  double v[1] = {0.0};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float m = __fsub_rn(-(float)q_sum[b], (float)mb_sum[b]);
+    mbc[b] = m;
+    v[0] += (double)m * (double)m;
+  }
+  block_reduce<1>(v, red);
+  if (threadIdx.x == 0) {
+    sse[SRM_TERM_MBC] = v[0];
+    const double n = (double)B * (double)P.N;
+    for (int t = 0; t < SRM_N_TERMS; ++t) {
+      terms_out[t] = (float)sse[t];
+      double cnt = 0.0;
+      if (t == SRM_TERM_DOM || t == SRM_TERM_IBC || t == SRM_TERM_TDE) cnt = n;
+      if (t == SRM_TERM_MBC) cnt = (double)B;
+      terms_out[SRM_N_TERMS + t] = (float)cnt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------
+// T_f = C*k_f*krg/dl^2 (coefficient without the mobility average)
+__device__ __forceinline__ float tcoef(const SrmDev& P, float kf, float idl) { return P.C * kf * P.krg * idl * idl; }
+
+__global__ void __launch_bounds__(kThreads) k_resid_adj_ref(
+    const __grid_constant__ SrmDev P, int32_t B, int32_t R, const float* __restrict__ kx,
+    const int32_t* __restrict__ sample_real, const float* __restrict__ p0f, const float* __restrict__ p1f,
+    const float* __restrict__ dt1v, const float* __restrict__ dt2v, const float* __restrict__ dterms,
+    const float* __restrict__ A0f, const float* __restrict__ A0pf, const float* __restrict__ A0ppf,
+    const float* __restrict__ A1f, const float* __restrict__ A1pf, const float* __restrict__ G1f,
+    const float* __restrict__ G1pf, const float* __restrict__ domf, const float* __restrict__ mbc,
+    const float* __restrict__ dqdp, float* __restrict__ gp0, float* __restrict__ gp1,
+    double* __restrict__ gdt1_acc, double* __restrict__ gdt2_acc) {
+  __shared__ double red[2 * 32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  double acc2[2] = {0.0, 0.0};
+  if (c < P.N) {
+    const int64_t base = (int64_t)b * P.N;
+    const float* kr = kx + (int64_t)r * P.N;
+    const CellIdx ix = cell_index(P, c);
+    const float w_dom = dterms[SRM_TERM_DOM], w_mbc = dterms[SRM_TERM_MBC], w_tde = dterms[SRM_TERM_TDE];
+    const float d1 = dt1v[b], d2 = dt2v[b];
+    const float p0 = p0f[base + c], p1 = p1f[base + c];
+    const float G = G1f[base + c], Gp = G1pf[base + c];
+    const float sc = 2.f * w_dom * domf[base + c];        // dL/d dom
+    const float smb = 2.f * w_mbc * mbc[b];               // dL/d mbc_b
+    const float kc = kr[c];
+    const float kyc = P.kx_ky * kc, kzc = P.kv_kh * kc;
+    float g1 = 0.f;
+    // stencil gather: dv * sum_f (s_c - s_n) * [a_f + 0.5*T_f*G'_c*(p_c - p_n)]; replicated faces drop out
+    auto face = [&](int cn, float kf, float idl) {
+      if (cn == c) return;
+      const float sn = 2.f * w_dom * domf[base + cn];
+      const float Tf = tcoef(P, kf, idl);
+      const float af = Tf * 0.5f * (G + G1f[base + cn]);
+      g1 += (sc - sn) * (af + 0.5f * Tf * Gp * (p1 - p1f[base + cn]));
+    };
+    face(ix.cW, harm_ref(kc, kr[ix.cW]), P.idx);
+    face(ix.cE, harm_ref(kr[ix.cE], kc), P.idx);
+    face(ix.cS, harm_ref(kyc, P.kx_ky * kr[ix.cS]), P.idy);
+    face(ix.cN, harm_ref(P.kx_ky * kr[ix.cN], kyc), P.idy);
+    face(ix.cD, harm_ref(kzc, P.kv_kh * kr[ix.cD]), P.idz);
+    face(ix.cU, harm_ref(P.kv_kh * kr[ix.cU], kzc), P.idz);
+    g1 *= P.dv;
+    // local terms
+    const float A0 = A0f[base + c], A0p = A0pf[base + c], A0pp = A0ppf[base + c];
+    const float A1 = A1f[base + c], A1p = A1pf[base + c];
+    float m0;
+    (void)srm_clamp(P, p0, m0);
+    const float cp = P.Sgi * (P.phi * A0p + P.phicf * A0);
+    const float cpp = P.Sgi * (P.phi * A0pp + P.phicf * A0p * m0);   // d cp / d p0
+    const float a5t = P.invDc * (cp / d1);
+    const float dp = p1 - p0;
+    const float acc = P.dv * a5t * dp;
+    // tde pieces recomputed in the forward's op order (E is dominated by the rounding of N)
+    const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
+    const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), __fadd_rn(1.0f, rho)), p0);
+    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+    const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(__fadd_rn(d1, d2), p1));
+    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), __fdiv_rn(numr, den));
+    const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
+    const float st = (P.tde_in_dom ? sc : 0.f) + 2.f * w_tde * tde;   // dL/d tde
+    // wells in this cell
+    float dq = 0.f;
+    if (P.n_wells > 0) {
+      const int first = well_lower_bound(P, c);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) dq += dqdp[(int64_t)b * P.n_wells + w];
+    }
+    const float mbk = P.dvSgi_phi / (P.Dc * d1);                      // d mb_cells / d(A1-A0)
+    g1 += sc * (dq + P.dv * a5t) + smb * (-dq - mbk * A1p);
+    const float g0 = sc * (-P.dv * a5t + P.dv * dp * P.invDc / d1 * cpp) + st * P.dvDc * cpp * E + smb * (mbk * A0p * m0);
+    gp0[base + c] = g0;
+    gp1[base + c] = g1;
+    // d/d dt1, d/d dt2 (the dN/d* pieces vanish identically; N itself is rounding noise)
+    const float dE1 = -2e-7f / (d1 * d1) - numr * d2 / (den * den);
+    const float dE2 = -numr * (d1 + 2.f * d2) / (den * den);
+    const float mb = mbk * (A1 - A0);
+    acc2[0] = (double)(sc * (-acc / d1) + st * P.dvDc * cp * dE1 + smb * (mb / d1));
+    acc2[1] = (double)(st * P.dvDc * cp * dE2);
+  }
+  block_reduce<2>(acc2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&gdt1_acc[b], acc2[0]);
+    atomicAdd(&gdt2_acc[b], acc2[1]);
+  }
+}
+
+// inner-boundary term: L_ibc = w_ibc * sum (mask*divq)^2 ; scatter d divq_c / d p1 to the cell and
+// its six neighbours (atomics: adjacent well cells may hit the same target).
+__global__ void __launch_bounds__(128) k_ibc_adj_ref(
+    const __grid_constant__ SrmDev P, int32_t B, int32_t R, const float* __restrict__ kx,
+    const int32_t* __restrict__ sample_real, const float* __restrict__ p1f, const float* __restrict__ dterms,
+    const float* __restrict__ G1f, const float* __restrict__ G1pf, const float* __restrict__ divqw,
+    const float* __restrict__ dqdp, float* __restrict__ gp1) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = P.n_wells;
+  if (g >= (int64_t)B * nw) return;
+  const int b = (int)(g / nw), w = (int)(g % nw);
+  const int c = P.wells[w].cell;
+  if (w > 0 && P.wells[w - 1].cell == c) return;   // one thread per distinct cell
+  float mask = 0.f, dq = 0.f;
+  for (int u = w; u < nw && P.wells[u].cell == c; ++u) { mask += 1.f; dq += dqdp[(int64_t)b * nw + u]; }
+  const float w_ibc = dterms[SRM_TERM_IBC];
+  const float s = 2.f * w_ibc * mask * mask * divqw[g];
+  if (s == 0.f) return;
+  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int64_t base = (int64_t)b * P.N;
+  const float* kr = kx + (int64_t)r * P.N;
+  const CellIdx ix = cell_index(P, c);
+  const float p1 = p1f[base + c], G = G1f[base + c], Gp = G1pf[base + c];
+  const float kc = kr[c], kyc = P.kx_ky * kc, kzc = P.kv_kh * kc;
+  float self = 0.f;
+  auto face = [&](int cn, float kf, float idl) {
+    if (cn == c) return;
+    const float Tf = tcoef(P, kf, idl);
+    const float pn = p1f[base + cn];
+    const float af = Tf * 0.5f * (G + G1f[base + cn]);
+    self += af + 0.5f * Tf * Gp * (p1 - pn);
+    atomicAdd(&gp1[base + cn], s * P.dv * (-af + 0.5f * Tf * G1pf[base + cn] * (p1 - pn)));
+  };
+  face(ix.cW, harm_ref(kc, kr[ix.cW]), P.idx);
+  face(ix.cE, harm_ref(kr[ix.cE], kc), P.idx);
+  face(ix.cS, harm_ref(kyc, P.kx_ky * kr[ix.cS]), P.idy);
+  face(ix.cN, harm_ref(P.kx_ky * kr[ix.cN], kyc), P.idy);
+  face(ix.cD, harm_ref(kzc, P.kv_kh * kr[ix.cD]), P.idz);
+  face(ix.cU, harm_ref(P.kv_kh * kr[ix.cU], kzc), P.idz);
+  atomicAdd(&gp1[base + c], s * (P.dv * self + dq));
+}
+
+__global__ void k_finalize_adj(int32_t B, const double* __restrict__ a1, const double* __restrict__ a2,
+                               float* __restrict__ gdt1, float* __restrict__ gdt2) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    gdt1[b] = (float)a1[b];
+    gdt2[b] = (float)a2[b];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int srm_launch_pvt_eval_ref(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s) {
+  if (n <= 0) return SRM_OK;
+  const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+  if (h->dev.n_props == 2) k_pvt_eval_ref<2><<<blocks, kThreads, 0, s>>>(h->dev, n, p, val, dval);
+  else if (h->dev.n_props == 7) k_pvt_eval_ref<7><<<blocks, kThreads, 0, s>>>(h->dev, n, p, val, dval);
+  else { srm_set_error("srm_pvt_eval: n_props must be 2 (DG) or 7 (GC), got %d", h->dev.n_props); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const int32_t* sample_real, int32_t R,
+                         const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp, cudaStream_t s) {
+  const int64_t n = (int64_t)B * h->dev.n_wells;
+  if (n <= 0) return SRM_OK;
+  k_wells_ref<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->dev, B, R, kx, sample_real, p, t_days, qw, pwfw, dqdp);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                    const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                    float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  const int64_t total = (int64_t)B * P.N;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
+  const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
+  if (save)
+    k_stage_ref<true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, ws.A0pp, ws.G1p, ws.A1p);
+  else
+    k_stage_ref<false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, nullptr, nullptr, nullptr);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  int rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p1, t1, ws.qw, ws.pwfw, ws.dqdp, s);
+  if (rc) return rc;
+  dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  k_resid_fwd_ref<<<grid, kThreads, 0, s>>>(P, B, R, kx, sample_real, p0, p1, dt1, dt2, ws.A0, ws.A0p, ws.A1, ws.G1,
+                                           ws.qw, ws.divqw, ws.dom, dom_out, ws.sse, ws.mb_sum, ws.q_sum);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  k_finalize_fwd<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.mbc, terms_out);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_backward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                     const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                     const SrmWs& ws, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
+  dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  k_resid_adj_ref<<<grid, kThreads, 0, s>>>(P, B, R, kx, sample_real, p0, p1, dt1, dt2, dterms, ws.A0, ws.A0p, ws.A0pp,
+                                           ws.A1, ws.A1p, ws.G1, ws.G1p, ws.dom, ws.mbc, ws.dqdp, gp0, gp1,
+                                           ws.gdt1_acc, ws.gdt2_acc);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  const int64_t n = (int64_t)B * P.n_wells;
+  if (n > 0) {
+    k_ibc_adj_ref<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, B, R, kx, sample_real, p1, dterms, ws.G1, ws.G1p,
+                                                             ws.divqw, ws.dqdp, gp1);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

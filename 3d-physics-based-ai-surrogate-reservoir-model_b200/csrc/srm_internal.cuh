@@ -1,0 +1,145 @@
+// Internal declarations shared by the kernels of libsrm_physics.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/srm_physics.h"
+
+#define SRM_MAXK 64   // knots
+#define SRM_MAXP 7    // PVT properties (GC)
+#define SRM_EPS 1e-10f  // polyhm_splines.py:6
+
+// One connection, sorted by flat cell index (so a block can binary-search its range).
+struct WellDev {
+  int32_t cell;   // (k*H + j)*W + i     welldata_processor.py:26-40 ([k,j,i] index rows)
+  int32_t orig;   // position in the caller's well list (output tables use that order)
+  float q_target, pwf_min, rw, hc, shut_start, shut_stop;
+};
+
+// Immutable parameters, passed to kernels by value (lands in the constant bank: the knot loop
+// reads c[i], w[i] with uniform addresses).
+struct SrmDev {
+  int32_t D, H, W, N;  // N = D*H*W cells per sample
+  float dx, dy, dz;
+  float idx, idy, idz;  // fl(1/dx) ...
+  float dv;             // (dx*dy)*dz          physics_loss.py:36
+  float C, Dc, invDc;   // invDc = fl(1/Dc)    physics_loss.py:156
+  float dvDc;           // fl(dv/Dc)           physics_loss.py:171
+  float phi, cf, phicf; // phicf = fl(phi*cf)  physics_loss.py:149
+  float Sgi, krg;
+  float dvSgi_phi;      // (dv*Sgi)*phi        physics_loss.py:193
+  float kx_ky, kv_kh;
+  float p_min, p_max;
+  int32_t tde_in_dom;
+  int32_t use_blk, n_int;
+  int32_t n_wells;
+  const WellDev* wells;  // device, sorted by cell
+  // spline
+  int32_t n_knots, order, n_props;
+  float c[SRM_MAXK];
+  float c2[SRM_MAXK];            // fl(c*c)
+  float w[SRM_MAXP][SRM_MAXK];
+  float v[SRM_MAXP][2];
+};
+
+// Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory.
+struct SrmClosedForm {
+  // interval k in [0, n_knots]: (-inf,c0), [c0,c1), ..., [c_{n-1}, inf)
+  // value(x) = f0[k] + slope[k] * (x - x0[k])
+  float x0[SRM_MAXK + 1];
+  float f0[SRM_MAXP][SRM_MAXK + 1];
+  float slope[SRM_MAXP][SRM_MAXK + 1];
+};
+
+struct SrmHandle {
+  SrmConfig cfg;       // host copy (pointers nulled)
+  SrmDev dev;          // device parameter block
+  WellDev* d_wells;    // device
+  SrmClosedForm* d_cf; // device (closed-form tables), may be null
+  int device;
+  int sm_count;
+  // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD)
+  const void* st_ws; const void* st_p0; const void* st_p1; const void* st_kx;
+  int32_t st_B; int32_t st_valid;
+};
+
+// ---- workspace carving ------------------------------------------------------------------
+struct SrmWs {
+  double* sse;        // [8]
+  double* mb_sum;     // [B]  sum over cells of mb_cells
+  double* q_sum;      // [B]  sum of well rates
+  double* gdt1_acc;   // [B]
+  double* gdt2_acc;   // [B]
+  float* mbc;         // [B]
+  float* qw;          // [B*nw] sorted-well order
+  float* pwfw;        // [B*nw]
+  float* dqdp;        // [B*nw]
+  float* divqw;       // [B*nw]
+  float* A0;          // fields [B*N]
+  float* A0p;
+  float* A1;
+  float* G1;
+  float* dom;
+  float* A0pp;        // backward-only fields
+  float* G1p;
+  float* A1p;
+  size_t bytes;
+};
+
+static inline size_t srm_align(size_t x) { return (x + 255) & ~size_t(255); }
+
+static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool with_bwd) {
+  SrmWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += srm_align(bytes); return r; };
+  w.sse = (double*)take(8 * sizeof(double));
+  w.mb_sum = (double*)take(B * sizeof(double));
+  w.q_sum = (double*)take(B * sizeof(double));
+  w.gdt1_acc = (double*)take(B * sizeof(double));
+  w.gdt2_acc = (double*)take(B * sizeof(double));
+  w.mbc = (float*)take(B * sizeof(float));
+  size_t wt = (size_t)(B * (nw > 0 ? nw : 1)) * sizeof(float);
+  w.qw = (float*)take(wt);
+  w.pwfw = (float*)take(wt);
+  w.dqdp = (float*)take(wt);
+  w.divqw = (float*)take(wt);
+  size_t fb = (size_t)(B * N) * sizeof(float);
+  w.A0 = (float*)take(fb);
+  w.A0p = (float*)take(fb);
+  w.A1 = (float*)take(fb);
+  w.G1 = (float*)take(fb);
+  w.dom = (float*)take(fb);
+  if (with_bwd) {
+    w.A0pp = (float*)take(fb);
+    w.G1p = (float*)take(fb);
+    w.A1p = (float*)take(fb);
+  } else {
+    w.A0pp = w.G1p = w.A1p = nullptr;
+  }
+  w.bytes = off;
+  return w;
+}
+
+// ---- error plumbing ---------------------------------------------------------------------
+void srm_set_error(const char* fmt, ...);
+#define SRM_CUDA_CHECK(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      srm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SRM_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+int srm_launch_pvt_eval_ref(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s);
+int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const int32_t* sample_real, int32_t R,
+                         const float* p, const float* t_days, float* qw_sorted, float* pwfw_sorted,
+                         float* dqdp_sorted, cudaStream_t s);
+int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                    const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                    float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s);
+int srm_backward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                     const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                     const SrmWs& ws, cudaStream_t s);

@@ -1,0 +1,154 @@
+"""SrmPhysics: a handle of libsrm_physics.so bound to one CUDA device, driven with torch tensors.
+
+torch is plumbing here (device memory, streams, autograd glue); every number comes out of the
+CUDA kernels behind the C ABI.  All methods raise if a tensor is not a contiguous fp32 CUDA tensor
+on the handle's device -- there is no host fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .config import PhysicsSpec
+from .pvt import SplineTables
+
+NUMERICS = {"reference": L.SRM_NUMERICS_REFERENCE, "closed_form": L.SRM_NUMERICS_CLOSED_FORM}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class SrmPhysics:
+    def __init__(self, spec: PhysicsSpec, tables: SplineTables, device: int = 0, numerics: str = "reference"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("SrmPhysics needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = L.load_library()
+        self.spec = spec
+        self.tables = tables
+        self.device = torch.device("cuda", device)
+        self.numerics = numerics
+        if spec.fluid_type != "DG":
+            raise NotImplementedError("only the dry-gas (DG) path is built")
+        cfg, self._keep = L.make_config(
+            device=device, D=spec.D, H=spec.H, W=spec.W, dx=spec.dx, dy=spec.dy, dz=spec.dz, C_=spec.C, Dc=spec.Dc,
+            phi=spec.phi, cf=spec.cf, Sgi=spec.Sgi, krg=spec.krg, kx_ky=spec.kx_ky, kv_kh=spec.kv_kh,
+            knots=tables.knots, spline_w=tables.w, spline_v=tables.v, spline_order=tables.order,
+            p_min=spec.p_min, p_max=spec.p_max, wells=[w.as_dict() for w in spec.wells],
+            use_blocking_factor=spec.use_blocking_factor, n_intervals=spec.n_intervals,
+            numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom)
+        h = C.c_void_p()
+        L.check(self.lib, self.lib.srm_create(C.byref(cfg), C.byref(h)), "srm_create")
+        self._h = h
+        self.n_wells = len(spec.wells)
+        self.n_props = tables.w.shape[0]
+        self._ws = None
+        self._ws_B = -1
+        self.launches = 0       # kernels launched through this handle (bench's gpu_launches claim)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.srm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------
+    def _check(self, t: torch.Tensor, name: str, dtype=torch.float32):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device and t.dtype == dtype
+                and t.is_contiguous()):
+            raise ValueError(f"{name}: need a contiguous {dtype} CUDA tensor on {self.device}, got "
+                             f"{getattr(t, 'dtype', type(t))} on {getattr(t, 'device', '?')}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, B: int) -> torch.Tensor:
+        if self._ws is None or self._ws_B != B:
+            n = self.lib.srm_workspace_bytes(self._h, B, L.SRM_FLAG_SAVE_FOR_BACKWARD)
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._ws_B = B
+        return self._ws
+
+    # ---------------------------------------------------------------------------------------
+    def pvt_eval(self, p: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """values, derivatives: each (n_props, n)."""
+        self._check(p, "p")
+        n = p.numel()
+        val = torch.empty((self.n_props, n), dtype=torch.float32, device=self.device)
+        der = torch.empty_like(val)
+        L.check(self.lib, self.lib.srm_pvt_eval(self._h, n, _ptr(p), _ptr(val), _ptr(der), self._stream()), "srm_pvt_eval")
+        self.launches += 1
+        return val, der
+
+    def denormalize_log(self, x_norm: torch.Tensor, kmin: float, kmax: float, lo: float = -1.0, hi: float = 1.0):
+        self._check(x_norm, "x_norm")
+        out = torch.empty_like(x_norm)
+        L.check(self.lib, self.lib.srm_denormalize_log(x_norm.numel(), _ptr(x_norm), kmin, kmax, lo, hi, _ptr(out),
+                                                       self._stream()), "srm_denormalize_log")
+        self.launches += 1
+        return out
+
+    def wells(self, kx, sample_real, p, t_days, dense: bool = False):
+        B = p.shape[0]
+        R = kx.shape[0]
+        self._check(kx, "kx"); self._check(p, "p"); self._check(t_days, "t_days")
+        if sample_real is not None:
+            self._check(sample_real, "sample_real", torch.int32)
+        nw = max(self.n_wells, 1)
+        qw = torch.zeros((B, nw), dtype=torch.float32, device=self.device)
+        pwfw = torch.zeros_like(qw)
+        dqdp = torch.zeros_like(qw)
+        qd = torch.empty_like(p) if dense else None
+        pd = torch.empty_like(p) if dense else None
+        L.check(self.lib, self.lib.srm_wells(self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p), _ptr(t_days),
+                                             _ptr(qw), _ptr(pwfw), _ptr(dqdp), _ptr(qd), _ptr(pd), self._stream()),
+                "srm_wells")
+        self.launches += 4 + (2 if dense else 0)
+        return dict(qw=qw, pwfw=pwfw, dqdp=dqdp, q=qd, pwf=pd)
+
+    def forward(self, kx, sample_real, p0, p1, dt1, dt2, t1, want_dom: bool = False, want_wells: bool = False,
+                save_for_backward: bool = True):
+        B = p0.shape[0]
+        R = kx.shape[0]
+        for t, nm in ((kx, "kx"), (p0, "p0"), (p1, "p1"), (dt1, "dt1"), (dt2, "dt2"), (t1, "t1")):
+            self._check(t, nm)
+        if sample_real is not None:
+            self._check(sample_real, "sample_real", torch.int32)
+        if p0.numel() != B * self.spec.n_cells or p1.shape != p0.shape or kx.numel() != R * self.spec.n_cells:
+            raise ValueError("field shapes do not match the handle's grid")
+        ws = self.workspace(B)
+        terms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32, device=self.device)
+        dom = torch.empty_like(p0) if want_dom else None
+        qw = torch.empty((B, max(self.n_wells, 1)), dtype=torch.float32, device=self.device) if want_wells else None
+        pwfw = torch.empty_like(qw) if want_wells else None
+        flags = L.SRM_FLAG_SAVE_FOR_BACKWARD if save_for_backward else 0
+        L.check(self.lib, self.lib.srm_forward(self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1),
+                                               _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(terms), _ptr(dom), _ptr(qw),
+                                               _ptr(pwfw), _ptr(ws), ws.numel(), flags, self._stream()), "srm_forward")
+        self.launches += 4 + (2 if want_wells else 0)
+        return dict(terms=terms, dom=dom, qw=qw, pwfw=pwfw)
+
+    def backward(self, kx, sample_real, p0, p1, dt1, dt2, t1, dterms):
+        B = p0.shape[0]
+        R = kx.shape[0]
+        self._check(dterms, "dterms")
+        ws = self.workspace(B)
+        gp0 = torch.empty_like(p0)
+        gp1 = torch.empty_like(p1)
+        gdt1 = torch.empty_like(dt1)
+        gdt2 = torch.empty_like(dt2)
+        L.check(self.lib, self.lib.srm_backward(self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1),
+                                                _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(dterms), _ptr(gp0), _ptr(gp1),
+                                                _ptr(gdt1), _ptr(gdt2), _ptr(ws), ws.numel(), 0, self._stream()),
+                "srm_backward")
+        self.launches += 3
+        return gp0, gp1, gdt1, gdt2

@@ -1,0 +1,176 @@
+/*
+ * srm_physics.h -- C ABI of the B200-native physics-loss library (libsrm_physics.so).
+ *
+ * The reference (molokwuvictor/3d-physics-based-ai-surrogate-reservoir-model) is pure
+ * Python/TensorFlow and has NO foreign-function interface; this header is the boundary a
+ * TensorFlow custom op (tf_op/srm_physics_op.cc) or any other host (ctypes, here) binds instead of
+ * the reference's op-by-op graph.  Each entry point names the reference code it replaces
+ * (file:line relative to the reference repo root).
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers on the handle's device unless marked "host".
+ *   - Fields are fp32, layout (B, D, H, W) with W (x, index i) contiguous; kx is (R, D, H, W).
+ *     "sample" b = one (realisation, time point) pair (training.py:187-204 flattens K x T into B).
+ *   - sample_real[b] in [0, R) maps a sample to its permeability realisation (device int32;
+ *     NULL means b * R / B, i.e. realisation-major equal-sized groups).
+ *   - The caller owns every buffer.  The library owns only the handle's immutable device tables.
+ *     No allocation happens inside forward/backward: scratch comes from the caller's workspace
+ *     (query srm_workspace_bytes once).
+ *   - Every call returns 0 on success or a negative SrmStatus; the message is in
+ *     srm_last_error() (thread-local).  Nothing throws across the ABI.  Launches are asynchronous
+ *     on `stream` (a cudaStream_t passed as void*); asynchronous CUDA errors surface at the
+ *     caller's next synchronisation.
+ *   - A handle is read-only after creation: concurrent calls on different streams with different
+ *     workspaces are safe.
+ *   - There is NO CPU fallback.  If no CUDA device is usable srm_create fails with SRM_ERR_CUDA.
+ */
+#ifndef SRM_PHYSICS_H_
+#define SRM_PHYSICS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRM_ABI_VERSION 1
+
+typedef enum SrmStatus {
+  SRM_OK = 0,
+  SRM_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  SRM_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  SRM_ERR_WORKSPACE = -3, /* workspace too small */
+  SRM_ERR_STATE = -4      /* backward without usable forward state and recompute disabled */
+} SrmStatus;
+
+/* loss-term slots of terms_out / dterms (default_configurations.py:63-83 key set) */
+enum { SRM_TERM_DOM = 0, SRM_TERM_IBC = 1, SRM_TERM_MBC = 2, SRM_TERM_TDE = 3,
+       SRM_TERM_OBC = 4, SRM_TERM_IC = 5, SRM_TERM_TD = 6, SRM_TERM_CMBC = 7, SRM_N_TERMS = 8 };
+
+enum { SRM_FLUID_DG = 0, SRM_FLUID_GC = 1 };
+enum { SRM_PVT_SPLINE = 0, SRM_PVT_POLYNOMIAL = 1 };
+
+/* Numerics of the PVT evaluation and the flux assembly.
+ *   SRM_NUMERICS_REFERENCE : the reference's fp32 op order reproduced op by op (all 37 RBF terms in
+ *       the x^2-2xc+c^2 form of polyhm_splines.py:91-96, a*p products of physics_loss.py:174, no FMA
+ *       contraction).  Forward fields are bit-faithful to the pinned-order oracle.  Compute bound.
+ *   SRM_NUMERICS_CLOSED_FORM : the same order-1 interpolant in its exact closed form (piecewise
+ *       linear between knots) and the flux in difference form.  Closer to exact arithmetic than the
+ *       fp32 reference itself, but not bit-faithful to its rounding noise.  HBM bound. */
+enum { SRM_NUMERICS_REFERENCE = 0, SRM_NUMERICS_CLOSED_FORM = 1 };
+
+/* forward/backward flags */
+enum { SRM_FLAG_SAVE_FOR_BACKWARD = 1 };
+
+/* One well connection (default_configurations.py:132-140; welldata_processor.py:39-107).
+ * (i,j,k) are 0-based cell indices along (W,H,D); the library scatters at [k,j,i]
+ * (welldata_processor.py:26-40).  q_target carries the sign rule (producer +, injector -). */
+typedef struct SrmWell {
+  int32_t i, j, k;
+  float q_target;
+  float pwf_min;
+  float rw;
+  float hc;          /* completion ratio */
+  float shut_start;  /* shut in while shut_start <= t <= shut_stop (welldata_processor.py:349-354) */
+  float shut_stop;
+} SrmWell;
+
+typedef struct SrmConfig {
+  int32_t abi_version;   /* = SRM_ABI_VERSION */
+  int32_t device;        /* CUDA device ordinal */
+  /* grid (default_configurations.py:92-104) */
+  int32_t D, H, W;
+  float dx, dy, dz;
+  /* unit constants (default_configurations.py:449-451) */
+  float C, Dc;
+  /* rock / SCAL scalars, host-computed in fp32 the way the reference does
+   * (physics_loss.py:64-65,129; relative_permeability.py:49-75) */
+  float phi, cf, Sgi, krg;
+  float kx_ky, kv_kh;
+  int32_t fluid_type;    /* SRM_FLUID_* */
+  /* PVT (PVT_Layer_Subclassed.py:23-216; polyhm_splines.py) -- host pointers, copied at create */
+  int32_t pvt_method;    /* SRM_PVT_* */
+  int32_t spline_order;  /* 1 (example) or 2 (default config) */
+  int32_t n_knots;       /* <= 64 */
+  int32_t n_props;       /* DG: 2 [invBg, invug] */
+  const float* knots;    /* host [n_knots], ascending */
+  const float* spline_w; /* host [n_props][n_knots]  RBF weights */
+  const float* spline_v; /* host [n_props][2]        linear term */
+  float p_min, p_max;    /* clamp (PVT_Layer_Subclassed.py:165-167) */
+  /* wells -- host pointer, copied at create */
+  int32_t n_wells;
+  const SrmWell* wells;
+  int32_t use_blocking_factor; /* well_rate_bhp_Subclassed.py:36 */
+  int32_t n_intervals;         /* well_rate_bhp_Subclassed.py:39 */
+  /* behaviour */
+  int32_t numerics;      /* SRM_NUMERICS_* */
+  int32_t tde_in_dom;    /* 1: legacy DG folds the truncation term into dom (physics_loss.py:175) */
+} SrmConfig;
+
+typedef struct SrmHandle SrmHandle;
+
+/* library / error plumbing (no reference counterpart) */
+int srm_version(void);
+const char* srm_last_error(void);
+
+/* Build the immutable device tables.  Replaces the per-call constant work of the reference:
+ * the 39x39 spline solve redone inside every call (polyhm_splines.py:180 -- here solved once by
+ * the host and passed in), scatter_nd of well scalars (well_rate_bhp_Subclassed.py:128-132),
+ * Peaceman/relperm constants (physics_loss.py:61-77). */
+int srm_create(const SrmConfig* cfg, SrmHandle** out);
+void srm_destroy(SrmHandle* h);
+
+/* Scratch needed by srm_forward/srm_backward for B samples (bytes). */
+size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t flags);
+
+/* PVTLayer.call (PVT_Layer_Subclassed.py:146-216) + PolyharmonicSplineInterpolationLayer.call
+ * (polyhm_splines.py:152-196): clamp, value and d/dp of every property at n pressures.
+ * val/dval are [n_props][n] (either may be NULL). */
+int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, void* stream);
+
+/* DataSummary.nonormalize, log branch used for permeability
+ * (data_processing/data_processing_utils.py:1098-1106): kx = exp(ln(kmax/kmin)*((x-lo)/(hi-lo)) + ln kmin). */
+int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi,
+                        float* out, void* stream);
+
+/* WellRatesPressure.compute_rates_and_bhp (well_rate_bhp_Subclassed.py:727-837) incl.
+ * _non_iterative_method (:614-724), _compute_phase_rates (:963-1007),
+ * compute_blocking_integral_and_factor (:840-960), and the integer bookkeeping of
+ * WellDataProcessor.scatter_y / conn_shutins_idx (welldata_processor.py:170-224,228-389),
+ * evaluated sparsely at the connection cells.
+ * p: (B,D,H,W) pressure; t_days: (B,) time used for the shut-in test.
+ * Outputs (any may be NULL): qw,pwfw,dqdp [B][n_wells] per-connection tables;
+ * q_dense,pwf_dense (B,D,H,W) zero off-well (scatter_nd semantics: duplicates sum). */
+int srm_wells(const SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+              const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp,
+              float* q_dense, float* pwf_dense, void* stream);
+
+/* physics_error_gas (physics_loss.py:79-208) + the SSE/count reduction of pinn_batch_sse_grad
+ * (physics_loss.py:787-846), given the networks' outputs.
+ *   p0,p1   (B,D,H,W) pressure at t_n and t_n+dt1         (physics_loss.py:88-95,111-115)
+ *   dt1,dt2 (B,)      per-sample mean of the dt field      (physics_loss.py:102,122)
+ *   t1      (B,)      time (days) at level n+1, for shut-ins
+ * Outputs:
+ *   terms_out [2][SRM_N_TERMS] fp32: row 0 = sum of squares per term, row 1 = element counts
+ *   dom_out   (B,D,H,W) residual field, nullable
+ *   qw_out, pwfw_out [B][n_wells], nullable
+ */
+int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                float* terms_out, float* dom_out, float* qw_out, float* pwfw_out,
+                void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
+
+/* The gradient TF's tape delivers to the networks' outputs (physics_loss.py:849-859) for the loss
+ * L = sum_k dterms[k] * SSE_k:  gp0,gp1 (B,D,H,W), gdt1,gdt2 (B,).  dterms is a DEVICE fp32[8].
+ * If the workspace still holds the state of an srm_forward call with SRM_FLAG_SAVE_FOR_BACKWARD on
+ * the same inputs it is reused; otherwise the forward state is recomputed first. */
+int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                 const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                 const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                 void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRM_PHYSICS_H_ */

@@ -1,0 +1,87 @@
+"""Shared helpers for the tests: build the oracle configuration and the product spec from ONE
+description, generate seeded synthetic inputs, compare fields."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import srm_b200 as srm  # noqa: E402
+import srm_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+WEIGHTS = [1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0]   # dom, ibc, mbc, tde (default_configurations.py:63-83)
+
+
+def make_case(W, H, D, T, K, seed, wells="default", all_layers=False, use_blocking_factor=False, n_intervals=8,
+              near_knots=True, order=1):
+    """returns (oracle_cfg, oracle_table, spec, tables, batch)"""
+    if wells == "default":
+        wl = srm.config.scaled_default_wells(W, H, D, all_layers=all_layers)
+    elif wells == "lattice":
+        wl = srm.config.lattice_wells(W, H, D)
+    elif wells == "none":
+        wl = []
+    else:
+        wl = wells
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=wl, use_blocking_factor=use_blocking_factor, n_intervals=n_intervals)
+    cols = O.load_pvt_table(os.path.join(GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.DG_PROPS, order=order, lam=0.001)
+    ptab = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES, order=order)
+    ocfg = O.OracleConfig(
+        D=D, H=H, W=W, use_blocking_factor=use_blocking_factor, n_intervals=n_intervals,
+        wells=[O.Well(i=w.i, j=w.j, k=w.k, value=abs(w.q_target), producer=(w.q_target >= 0 and not (w.q_target == 0 and np.signbit(w.q_target))),
+                      minimum_bhp=w.pwf_min, wellbore_radius=w.rw, completion_ratio=w.hc,
+                      shutin_days=(w.shut_start, w.shut_stop)) for w in wl])
+    batch = srm.synth.make_batch(W, H, D, T, K, [(w.i, w.j) for w in wl[:8]], seed=seed,
+                                 near_knots=torch.as_tensor(otab.c) if near_knots else None)
+    return ocfg, otab, spec, ptab, batch
+
+
+def oracle_run(ocfg, otab, batch, weights=WEIGHTS, dtype=torch.float32):
+    return O.dg_forward_backward(ocfg, otab, batch.kx.numpy(), batch.p0.numpy(), batch.p1.numpy(), batch.dt1.numpy(),
+                                 batch.dt2.numpy(), batch.t1.numpy(), batch.sample_real.numpy(), weights, dtype=dtype)
+
+
+def to_dev(batch, dev):
+    c = lambda t: t.to(dev).contiguous()
+    return dict(kx=c(batch.kx), sample_real=c(batch.sample_real), p0=c(batch.p0), p1=c(batch.p1), dt1=c(batch.dt1),
+                dt2=c(batch.dt2), t1=c(batch.t1))
+
+
+def cuda_run(spec, ptab, batch, weights=WEIGHTS, numerics="reference", want_dom=True):
+    dev = torch.device("cuda", 0)
+    eng = srm.SrmPhysics(spec, ptab, device=0, numerics=numerics)
+    d = to_dev(batch, dev)
+    fw = eng.forward(want_dom=want_dom, want_wells=True, **d)
+    dterms = torch.tensor(weights, dtype=torch.float32, device=dev)
+    gp0, gp1, gdt1, gdt2 = eng.backward(dterms=dterms, **d)
+    torch.cuda.synchronize()
+    out = dict(terms=fw["terms"][0].cpu().numpy(), counts=fw["terms"][1].cpu().numpy(),
+               dom=fw["dom"].cpu().numpy() if want_dom else None, qw=fw["qw"].cpu().numpy(),
+               pwfw=fw["pwfw"].cpu().numpy(), gp0=gp0.cpu().numpy(), gp1=gp1.cpu().numpy(),
+               gdt1=gdt1.cpu().numpy(), gdt2=gdt2.cpu().numpy())
+    eng.close()
+    return out
+
+
+def rel_to_max(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def ulp_diff(a, b):
+    """max distance in units of fp32 ulps (of b)"""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, np.int64(-2**31) - ai, ai)
+    bi = np.where(bi < 0, np.int64(-2**31) - bi, bi)
+    return int(np.abs(ai - bi).max())
