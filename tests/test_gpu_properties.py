@@ -1,0 +1,95 @@
+"""Size-independent properties at BASELINE.json's full single-GPU size (config 2: 64x64x16, T=32,
+K=16 -> 3.4e7 cell-timesteps), where the CPU oracle would take minutes."""
+import numpy as np
+import pytest
+import torch
+
+import util as U
+
+srm = U.srm
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    c = srm.synth.CONFIGS["cfg2"]
+    wells = srm.config.scaled_default_wells(c["W"], c["H"], c["D"])
+    spec = srm.PhysicsSpec(D=c["D"], H=c["H"], W=c["W"], wells=wells)
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    eng = srm.SrmPhysics(spec, tabs)
+    b = srm.synth.make_batch(c["W"], c["H"], c["D"], c["T"], c["K"], [(w.i, w.j) for w in wells], seed=2002, device="cuda")
+    d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
+    return eng, d
+
+
+def test_terms_are_the_sums_of_squares_of_the_fields(cfg2):
+    eng, d = cfg2
+    fw = eng.forward(want_dom=True, **d)
+    dom = fw["dom"].double()
+    assert abs(float((dom * dom).sum()) / float(fw["terms"][0, 0]) - 1.0) < 1e-5
+    B, N = d["p0"].shape[0], d["p0"][0].numel()
+    assert fw["terms"][1].tolist() == [B * N, B * N, B, B * N, 0, 0, 0, 0]
+    assert torch.isfinite(fw["dom"]).all()
+
+
+def test_uniform_pressure_has_zero_flux_and_zero_accumulation(cfg2):
+    """p0 == p1 == const and no wells: every flux difference, the accumulation and mbc vanish exactly
+    in the 3-D extension's z faces; the reference's a*p form leaves only its rounding residue."""
+    eng, d = cfg2
+    spec = srm.PhysicsSpec(D=eng.spec.D, H=eng.spec.H, W=eng.spec.W, wells=[])
+    e2 = srm.SrmPhysics(spec, eng.tables)
+    p = torch.full_like(d["p0"][:4], 4700.0)
+    fw = e2.forward(kx=d["kx"], sample_real=d["sample_real"][:4].contiguous(), p0=p, p1=p, dt1=d["dt1"][:4].contiguous(),
+                    dt2=d["dt2"][:4].contiguous(), t1=d["t1"][:4].contiguous(), want_dom=True)
+    dom = fw["dom"]
+    scale = 4700.0 * 4 * 1e-3 * e2.spec.dx * e2.spec.dy * e2.spec.dz      # |a*p| * dv, a ~ 1e-3
+    assert float(dom.abs().max()) < 1e-5 * scale
+    assert float(fw["terms"][0, 2]) == 0.0                                  # mbc: A1 - A0 == 0 exactly
+
+
+def test_loss_is_additive_over_sample_shards(cfg2):
+    """the batch shards across ranks with no data-path exchange: terms(all) == sum of terms(shards)"""
+    eng, d = cfg2
+    full = eng.forward(**d)["terms"][0].double().clone()
+    B = d["p0"].shape[0]
+    acc = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for lo in range(0, B, B // 4):
+        sl = slice(lo, lo + B // 4)
+        part = {k: (v[sl].contiguous() if k != "kx" else v) for k, v in d.items()}
+        acc += eng.forward(**part)["terms"][0].double()
+    assert torch.allclose(acc, full, rtol=1e-6, atol=0)
+
+
+def test_gradient_is_linear_in_the_upstream_weights(cfg2):
+    eng, d = cfg2
+    sub = {k: (v[:32].contiguous() if k != "kx" else v) for k, v in d.items()}
+    eng.forward(**sub)
+    w1 = torch.tensor([1.0, 0, 0, 0, 0, 0, 0, 0], device="cuda")
+    w2 = torch.tensor([0, 0.5, 2.0, 0.25, 0, 0, 0, 0], device="cuda")
+    g1 = [t.clone() for t in eng.backward(dterms=w1, **sub)]
+    g2 = [t.clone() for t in eng.backward(dterms=w2, **sub)]
+    g12 = eng.backward(dterms=w1 + w2, **sub)
+    for a, b, c in zip(g1, g2, g12):
+        ref = a.double() + b.double()
+        assert float((c.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_directional_derivative_of_the_loss(cfg2):
+    """<grad, v> matches a central difference of the fp32 loss along a smooth direction v.  The
+    direction avoids PVT-knot crossings by being small; tolerance reflects fp32 loss rounding."""
+    eng, d = cfg2
+    sub = {k: (v[:8].contiguous() if k != "kx" else v) for k, v in d.items()}
+    w = torch.tensor([0.0, 0.0, 1.0, 0.0, 0, 0, 0, 0], device="cuda")        # mbc: smooth, well conditioned
+    eng.forward(**sub)
+    gp0, gp1, gdt1, gdt2 = eng.backward(dterms=w, **sub)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    v = torch.randn(sub["dt1"].shape, generator=gen, device="cuda")
+    h = 1e-3
+
+    def loss(dt1):
+        t = eng.forward(**{**sub, "dt1": dt1.contiguous()})["terms"][0].double()
+        return float((t * w.double()).sum())
+
+    fd = (loss(sub["dt1"] + h * v) - loss(sub["dt1"] - h * v)) / (2 * h)
+    an = float((gdt1.double() * v.double()).sum())
+    assert abs(fd - an) <= 2e-3 * abs(an)

@@ -1,0 +1,136 @@
+"""CPU tests of the host-side logic of the product package (no GPU, no compute through the .so)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util as U
+
+srm, O = U.srm, U.O
+
+
+def test_product_spline_solve_is_bitwise_the_oracles():
+    ptab = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES, order=1)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    assert np.array_equal(ptab.knots, otab.c)
+    assert np.array_equal(ptab.w, otab.w) and np.array_equal(ptab.v, otab.v)
+
+
+def test_pvt_table_lookup_is_case_insensitive():
+    t = srm.load_default_pvt_table()
+    assert np.array_equal(t.lookup("invBg"), t.lookup("InvBg"))
+    assert np.array_equal(t.lookup("pre"), t.lookup("Pre"))
+    with pytest.raises(KeyError):
+        t.lookup("nope")
+
+
+def test_spec_scalars_match_oracle():
+    spec = srm.PhysicsSpec()
+    assert np.float32(spec.cf) == O.rock_compressibility(0.2)
+    _, krg = O.corey_krog_krgo_np(1.0 - 0.22, O.OracleConfig(), np.float32)
+    assert np.float32(spec.krg) == np.float32(krg) == np.float32(0.9)
+    assert np.float32(spec.Sgi) == np.float32(0.78)
+    assert abs(spec.dx - 2900.0 / 39) < 1e-12 and spec.dz == 80.0
+
+
+def test_wells_from_connections_sign_rule_and_shutins():
+    conns = [
+        {"i": 1, "j": 2, "k": 0, "type": "producer", "control": "ORAT", "value": 500.0, "minimum_bhp": 4100.0,
+         "wellbore_radius": 0.1, "completion_ratio": 0.5, "shutin_days": [[10.0, 20.0]]},
+        {"i": 3, "j": 4, "k": 1, "type": "Injector", "control": "orat", "value": 250.0},
+        {"i": 0, "j": 0, "k": 0, "type": "injector", "control": "BHP", "value": 3000.0, "shutin_days": [[1, 2], [3, 4]]},
+    ]
+    w = srm.config.wells_from_connections(conns)
+    assert w[0].q_target == 500.0 and (w[0].shut_start, w[0].shut_stop) == (10.0, 20.0)
+    assert w[1].q_target == -250.0 and (w[1].shut_start, w[1].shut_stop) == (0.0, 0.0)   # default [[0,0]]
+    assert w[2].q_target == 3000.0                                                      # BHP stays positive
+    assert (w[2].shut_start, w[2].shut_stop) == (0.0, 0.0)                              # malformed list -> default
+
+
+def test_reference_shaped_config_dicts_are_accepted():
+    spec = srm.spec_from_reference_configs()
+    assert (spec.W, spec.H, spec.D) == (39, 39, 1) and len(spec.wells) == 5
+    assert [(w.i, w.j, w.k) for w in spec.wells] == [(29, 29, 0), (29, 9, 0), (9, 9, 0), (9, 29, 0), (19, 19, 0)]
+    assert spec.wells[4].q_target == 0.0 and np.signbit(spec.wells[4].q_target)         # injector: -0.0
+    spec2 = srm.spec_from_reference_configs(reservoir={"Nx": 64, "Ny": 32, "Nz": 4, "porosity": 0.25})
+    assert (spec2.W, spec2.H, spec2.D, spec2.phi) == (64, 32, 4, 0.25)
+
+
+def test_header_symbols_are_all_exported():
+    """the C-ABI library loads and exports every function include/srm_physics.h declares."""
+    hdr = open(os.path.join(U.ROOT, "include", "srm_physics.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(srm_[a-z_]+)\s*\(", hdr))
+    assert names == set(srm._lib.EXPORTS), names ^ set(srm._lib.EXPORTS)
+    lib = srm._lib.load_library()
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.srm_version() == srm._lib.SRM_ABI_VERSION
+
+
+def test_struct_layout_matches_header_field_order():
+    hdr = open(os.path.join(U.ROOT, "include", "srm_physics.h")).read()
+    body = hdr[hdr.index("typedef struct SrmConfig {"):hdr.index("} SrmConfig;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        m = re.match(r"(?:const\s+)?(?:int32_t|float|SrmWell\*|float\*)\s*\*?\s*(.*)", decl.replace("typedef struct SrmConfig {", "").strip())
+        if not m or not decl:
+            continue
+        for nm in m.group(1).split(","):
+            nm = nm.strip().lstrip("*").strip()
+            if nm:
+                fields.append(nm)
+    assert fields == [f[0] for f in srm._lib.SrmConfig._fields_], fields
+
+
+def test_create_rejects_bad_configs_without_touching_a_gpu():
+    """argument validation happens before any CUDA call, so it is testable on the CPU box"""
+    lib = srm._lib.load_library()
+    L = srm._lib
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    base = dict(device=0, D=1, H=4, W=4, dx=1.0, dy=1.0, dz=1.0, C_=0.001127, Dc=5.6145833334, phi=0.2, cf=1e-5,
+                Sgi=0.78, krg=0.9, kx_ky=1.0, kv_kh=1.0, knots=tabs.knots, spline_w=tabs.w, spline_v=tabs.v,
+                spline_order=1, p_min=14.7, p_max=1e4, wells=[], use_blocking_factor=False, n_intervals=8,
+                numerics=0, tde_in_dom=True)
+
+    def rc(**kw):
+        cfg, keep = L.make_config(**{**base, **kw})
+        h = ctypes.c_void_p()
+        r = lib.srm_create(ctypes.byref(cfg), ctypes.byref(h))
+        return r, lib.srm_last_error().decode()
+
+    r, msg = rc(W=0)
+    assert r == -1 and "grid" in msg
+    r, msg = rc(spline_order=3)
+    assert r == -1 and "spline_order" in msg
+    r, msg = rc(numerics=7)
+    assert r == -1 and "numerics" in msg
+    r, msg = rc(wells=[dict(i=9, j=0, k=0, q_target=1.0, pwf_min=1.0, rw=0.1, hc=0.5, shut_start=0, shut_stop=0)])
+    assert r == -1 and "outside the grid" in msg
+    r, msg = rc(knots=tabs.knots[::-1].copy())
+    assert r == -1 and "ascending" in msg
+    r, msg = rc(fluid_type=1)
+    assert r == -1
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        srm.SrmPhysics(srm.PhysicsSpec(), tabs)
+
+
+def test_synthetic_batch_ranges():
+    b = srm.synth.make_batch(16, 12, 3, 4, 2, [(4, 4)], seed=1)
+    assert b.p0.shape == (8, 3, 12, 16) and b.kx.shape == (2, 3, 12, 16)
+    assert float(b.kx.min()) >= 0.2599 and float(b.kx.max()) <= 24.001
+    assert float(b.p0.min()) > 4100 and float(b.p0.max()) <= 5000 and float((b.p0 - b.p1).max()) <= 31
+    assert float(b.dt1.min()) >= 0.1 and float(b.dt1.max()) <= 10.0
+    assert b.sample_real.tolist() == [0, 0, 0, 0, 1, 1, 1, 1]

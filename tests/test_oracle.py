@@ -1,0 +1,175 @@
+"""CPU tests of the oracle itself: goldens, internal consistency, derivative checks.
+
+The reference has no assertions or golden vectors on this path, so the oracle is
+checked (a) against its own committed goldens (regression pin), (b) against independent
+formulations of the same mathematics: fp64 finite differences for every hand-pinned derivative,
+the closed form of the order-1 spline, and interpolation of the knot data at lambda = 0.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util as U
+
+O = U.O
+GOLD = U.GOLDEN
+
+
+def _tab(order=1, lam=0.001):
+    cols = O.load_pvt_table(os.path.join(GOLD, "pvt_table.npz"))
+    return O.build_spline_table(cols, O.DG_PROPS, order=order, lam=lam)
+
+
+def test_pvt_table_fixture_matches_reference_shape():
+    cols = O.load_pvt_table(os.path.join(GOLD, "pvt_table.npz"))
+    assert set(cols) == {"Pre", "InvBg", "InvBo", "Invug", "Invuo", "Rs", "Rv", "InvBgd", "Invugd", "Vro"}
+    assert cols["Pre"].shape == (37,) and cols["Pre"].dtype == np.float32
+    assert np.all(np.diff(cols["Pre"]) > 0)
+    assert cols["Pre"][0] == 10.0 and cols["Pre"][-1] == 20000.0
+    assert abs(float(cols["Pre"][20]) - 4048.485352) < 1e-3          # dew-point row
+
+
+def test_spline_solve_probe_numbers():
+    """SURVEY 8(c) probe: max|w| = 1.44e-4 (InvBg) / 2.17e-2 (Invug)."""
+    tab = _tab()
+    assert abs(np.abs(tab.w[0]).max() - 1.44e-4) < 1e-6
+    assert abs(np.abs(tab.w[1]).max() - 2.17e-2) < 1e-4
+
+
+def test_spline_interpolates_knots_without_regularisation():
+    tab = _tab(lam=0.0)
+    cfg = O.OracleConfig(p_min=0.0, p_max=1e9)
+    for q in range(2):
+        val, _, _ = O.spline_eval_np(tab.c.astype(np.float64), tab, q, np.float64, need=0)
+        assert np.allclose(val, tab.f[q], rtol=2e-3, atol=2e-4)     # fp32 solve, cond ~ 4e6
+
+
+def test_spline_pvt_golden_regression():
+    g = np.load(os.path.join(GOLD, "pvt_golden.npz"))
+    tab = _tab()
+    assert np.array_equal(tab.w, g["w"]) and np.array_equal(tab.v, g["v"]), "fp32 LAPACK solve changed"
+    cfg = O.OracleConfig()
+    ph = O.pvt_clamp(torch.from_numpy(g["p"]), cfg).numpy()
+    for q, name in enumerate(tab.names):
+        val, d1, d2 = O.spline_eval_np(ph, tab, q, np.float32, need=2)
+        assert np.array_equal(val, g[f"val_{name}"])
+        assert np.array_equal(d1, g[f"d1_{name}"])
+        assert np.array_equal(d2, g[f"d2_{name}"])
+
+
+def test_spline_fp64_matches_closed_form_and_fd():
+    """In fp64 the RBF form, its pinned derivatives and the piecewise-linear closed form agree."""
+    tab = _tab()
+    cfg = O.OracleConfig()
+    rng = np.random.default_rng(1)
+    x = rng.uniform(3000.0, 6000.0, 4000)
+    x = x[np.abs(x[:, None] - tab.c[None, :].astype(np.float64)).min(1) > 1.0]   # r = x^2-2xc+c^2 is noisy near knots even in fp64
+    for q in range(2):
+        val, d1, d2 = O.spline_eval_np(x, tab, q, np.float64, need=2)
+        cv, cs = O.spline_closed_form_fp64(x, tab, cfg, q)
+        assert np.allclose(val, cv, rtol=1e-12, atol=1e-12)
+        assert np.allclose(d1, cs, rtol=1e-7, atol=1e-12)
+        h = 0.05
+        vp, _, _ = O.spline_eval_np(x + h, tab, q, np.float64, need=0)
+        vm, _, _ = O.spline_eval_np(x - h, tab, q, np.float64, need=0)
+        assert np.allclose((vp - vm) / (2 * h), d1, rtol=1e-6, atol=1e-9)
+        assert np.abs(d2).max() < 1e-5 * np.abs(d1).max()            # exactly piecewise linear
+
+
+def test_spline_fp32_noise_band_matches_survey_probe():
+    """TF-order fp32 derivative is off by up to 4.6 % of max in [4100, 5000]."""
+    tab = _tab()
+    cfg = O.OracleConfig()
+    x = np.linspace(4100, 5000, 20001).astype(np.float32)
+    for q in range(2):
+        val, d1, _ = O.spline_eval_np(x, tab, q, np.float32, need=1)
+        cv, cs = O.spline_closed_form_fp64(x, tab, cfg, q)
+        assert np.max(np.abs(val - cv) / np.abs(cv)) < 2e-5
+        err = np.max(np.abs(d1 - cs)) / np.max(np.abs(cs))
+        assert 0.02 < err < 0.06
+
+
+@pytest.mark.parametrize("name", ["dg_2d_default", "dg_3d_layers", "dg_3d_blocking"])
+def test_dg_goldens_regression(name):
+    from golden.make_golden import CASES
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    ocfg, otab, spec, ptab, batch = U.make_case(**CASES[name])
+    for k in ("kx", "p0", "p1", "dt1", "dt2", "t1"):
+        assert np.array_equal(getattr(batch, k).numpy(), g[k]), f"synthetic generator changed: {k}"
+    o = U.oracle_run(ocfg, otab, batch)
+    for k in ("dom", "ibc", "q", "pwf", "qw", "pwfw"):
+        assert np.array_equal(np.asarray(o[k], np.float32), g["o_" + k]), k
+    for k in ("mbc", "tde", "terms", "gp0", "gp1", "gdt1"):
+        assert U.rel_to_max(o[k], g["o_" + k]) < 1e-6, k
+
+
+def test_dg_2d_is_3d_with_one_layer_bitwise():
+    """F2: with Nz = 1 the z faces of the 3-D extension contribute exactly +0.0 (edge replication makes
+    the z neighbour the cell itself), so the result is bit-identical whatever kz is -- i.e. the 3-D
+    arithmetic reduces to the shipped 2-D arithmetic."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=17, H=13, D=1, T=2, K=2, seed=5)
+    o = U.oracle_run(ocfg, otab, batch)
+    ocfg2 = O.OracleConfig(D=1, H=13, W=17, wells=ocfg.wells, kv_kh=0.37)
+    o2 = U.oracle_run(ocfg2, otab, batch)
+    assert np.all(np.isfinite(o["dom"]))
+    assert np.array_equal(o["dom"], o2["dom"])
+
+
+def test_dg_gradient_matches_fp64_finite_differences():
+    """The custom-Function derivatives (pinned D1/D2), TF min/max/clip routing and the residual
+    autograd agree with central finite differences of the fp64 loss."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=7, H=6, D=2, T=2, K=1, seed=11, all_layers=True, near_knots=False)
+    args = [batch.kx.numpy().astype(np.float64), batch.p0.numpy().astype(np.float64), batch.p1.numpy().astype(np.float64),
+            batch.dt1.numpy().astype(np.float64), batch.dt2.numpy().astype(np.float64), batch.t1.numpy(), batch.sample_real.numpy()]
+    w = [1.0, 0.7, 1.3, 0.9, 0, 0, 0, 0]
+
+    def loss(p0, p1, d1, d2):
+        o = O.dg_forward_backward(ocfg, otab, args[0], p0, p1, d1, d2, args[5], args[6], w, dtype=torch.float64)
+        return float((o["terms"] * np.array(w)).sum()), o
+
+    L0, o = loss(args[1], args[2], args[3], args[4])
+    rng = np.random.default_rng(3)
+    for name, idx, h in (("gp0", 1, 1e-3), ("gp1", 2, 1e-3), ("gdt1", 3, 1e-6)):
+        g = o[name]
+        for _ in range(6):
+            pos = tuple(rng.integers(0, s) for s in g.shape)
+            a = [x.copy() for x in args[1:5]]
+            a[idx - 1][pos] += h
+            Lp, _ = loss(*a)
+            a[idx - 1][pos] -= 2 * h
+            Lm, _ = loss(*a)
+            fd = (Lp - Lm) / (2 * h)
+            assert abs(fd - g[pos]) <= 2e-5 * max(abs(g[pos]), np.abs(g).max() * 1e-3), (name, pos, fd, g[pos])
+
+
+def test_wells_bhp_limited_branch_and_shutin():
+    """low reservoir pressure -> rate limited by pwf_min (q = Ck*mg*(p - pwf)); shut-in window -> q = 0."""
+    wells = [O.Well(i=2, j=2, k=0, value=5000.0, shutin_days=(1000.0, 0.0)),
+             O.Well(i=4, j=1, k=0, value=500.0, shutin_days=(10.0, 20.0))]
+    cfg = O.OracleConfig(D=1, H=6, W=6, wells=wells)
+    tab = _tab()
+    p = torch.full((3, 2), 4200.0, dtype=torch.float32, requires_grad=True)
+    kx = torch.full((3, 2), 3.0)
+    q, pwf = O.wells_dg(p, kx, np.array([5.0, 15.0, 25.0], np.float32), tab, cfg, torch.float32)
+    qn = q.detach().numpy()
+    assert np.all(qn[:, 0] < 5000.0) and np.all(qn[:, 0] > 0)        # BHP-limited producer
+    assert qn[1, 1] == 0.0 and qn[0, 1] > 0 and qn[2, 1] > 0          # shut in only inside [10, 20]
+    (g,) = torch.autograd.grad(q.sum(), p)
+    assert np.all(g.numpy()[:, 0] > 0)                                # dq/dp > 0 on the limited branch
+
+
+def test_well_index_rows_are_kji():
+    wells = [O.Well(i=3, j=5, k=1), O.Well(i=0, j=2, k=0)]
+    assert O.well_connection_index(wells).tolist() == [[1, 5, 3], [0, 2, 0]]
+    assert O.well_flat_index(wells, 2, 7, 9).tolist() == [(1 * 7 + 5) * 9 + 3, (0 * 7 + 2) * 9 + 0]
+
+
+def test_denormalisation_formulas():
+    x = np.linspace(-1, 1, 11).astype(np.float32)
+    t = O.denorm_linear(x, 0.0, 365.0)
+    assert t[0] == 0.0 and abs(t[-1] - 365.0) < 1e-4
+    k = O.denorm_log(x, 0.26, 24.0)
+    assert abs(k[0] - 0.26) < 1e-6 and abs(k[-1] - 24.0) < 1e-4
+    assert abs(float(O.norm_diff_linear(5.0, 0.0, 365.0)) - 2 * 5.0 / 365.0) < 1e-8
