@@ -26,7 +26,7 @@ SRM_FLAG_SAVE_FOR_BACKWARD = 1
 
 EXPORTS = (
     "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
-    "srm_pvt_eval", "srm_denormalize_log", "srm_wells", "srm_forward", "srm_backward",
+    "srm_pvt_eval", "srm_denormalize_log", "srm_selftest_rounding", "srm_wells", "srm_forward", "srm_backward",
 )
 
 
@@ -83,6 +83,8 @@ def load_library(path: Optional[str] = None):
     lib.srm_pvt_eval.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.srm_denormalize_log.restype = C.c_int
     lib.srm_denormalize_log.argtypes = [i64, vp, fp, fp, fp, fp, vp, vp]
+    lib.srm_selftest_rounding.restype = C.c_int
+    lib.srm_selftest_rounding.argtypes = [i32, i64, C.c_uint64, C.POINTER(C.c_int64), vp]
     lib.srm_wells.restype = C.c_int
     lib.srm_wells.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.srm_forward.restype = C.c_int

@@ -22,6 +22,7 @@ void srm_set_error(const char* fmt, ...) {
 int srm_launch_denorm_log(int64_t n, const float* x, float kmin, float kmax, float lo, float hi, float* out, cudaStream_t s);
 int srm_launch_scatter_wells(const SrmHandle* h, int32_t B, const float* sorted, float* dense, cudaStream_t s);
 int srm_launch_unsort_wells(const SrmHandle* h, int32_t B, const float* sorted, float* out, cudaStream_t s);
+int srm_launch_selftest_rounding(int64_t n, uint64_t seed, int64_t* bad_host, cudaStream_t s);
 int srm_build_closed_form(SrmHandle* h, const SrmConfig* cfg);
 int srm_launch_pvt_eval_cf(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s);
 int srm_forward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
@@ -167,6 +168,12 @@ int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, 
     return SRM_ERR_INVALID;
   }
   return srm_launch_denorm_log(n, x_norm, kmin, kmax, lo, hi, out, (cudaStream_t)stream);
+}
+
+int srm_selftest_rounding(int32_t device, int64_t n, uint64_t seed, int64_t* mismatches, void* stream) {
+  if (n < 0 || !mismatches) { srm_set_error("srm_selftest_rounding: bad argument"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(device));
+  return srm_launch_selftest_rounding(n, seed, mismatches, (cudaStream_t)stream);
 }
 
 static int check_batch(const SrmHandle* h, int32_t B, int32_t R, const char* who) {

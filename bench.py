@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- residual+adjoint throughput of the physics-loss path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg2] [--numerics reference]
+
+One "step" = one forward (residual + loss terms) plus one adjoint (dL/dp0, dL/dp1, dL/ddt1,
+dL/ddt2) over one batch of synthetic input of the named BASELINE config.  Prints ONE JSON line.
+
+  value      cell-timesteps/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with HOST (pinned) buffers: H2D of the step's
+             inputs and D2H of the loss terms and gradients inside the timed region
+  roofline   algorithmic bytes (28 + 8/T per cell-timestep) / step time vs the measured
+             HBM copy peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback of B200_PROFILING.md)
+  cpu_baseline  the oracle (a port of the reference's TF op graph; TensorFlow is not installable
+             here) on the box's host cores, bounded sample of the same workload
+
+N > 1 (torchrun): weak scaling -- every rank runs the same per-GPU workload on its own
+realisations; the only collective is the all-reduce of the 16-float loss-term vector (NCCL).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+METRIC = "residual+adjoint cell-timesteps/sec"
+UNIT = "cell-timesteps/s"
+WEIGHTS = [1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0]
+
+
+def workload(name):
+    import srm_b200 as srm
+    c = dict(srm.synth.CONFIGS[name])
+    if name == "cfg5":
+        wells = srm.config.lattice_wells(c["W"], c["H"], c["D"])
+        blocking = True
+    else:
+        wells = srm.config.scaled_default_wells(c["W"], c["H"], c["D"])
+        blocking = False
+    spec = srm.PhysicsSpec(D=c["D"], H=c["H"], W=c["W"], wells=wells, use_blocking_factor=blocking, n_intervals=8)
+    return c, spec
+
+
+def alg_bytes_per_cell(T):
+    return 28.0 + 8.0 / T          # DG fwd + adjoint, SURVEY.md 8(d) / BASELINE.md section 3
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:      # NVML unavailable: report that instead of inventing numbers
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle on the host cores (threads over independent samples)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(name, target_seconds=15.0, max_samples=None):
+    import srm_oracle as O
+    import srm_b200 as srm
+    from concurrent.futures import ThreadPoolExecutor
+    c, spec = workload(name)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(1)        # parallelism comes from sample shards, one per core
+    cols = O.load_pvt_table(os.path.join(ROOT, "tests", "golden", "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    ocfg = O.OracleConfig(D=spec.D, H=spec.H, W=spec.W, use_blocking_factor=spec.use_blocking_factor,
+                          n_intervals=spec.n_intervals,
+                          wells=[O.Well(i=w.i, j=w.j, k=w.k, value=abs(w.q_target), producer=not np.signbit(w.q_target),
+                                        minimum_bhp=w.pwf_min, wellbore_radius=w.rw, completion_ratio=w.hc,
+                                        shutin_days=(w.shut_start, w.shut_stop)) for w in spec.wells])
+    N = spec.n_cells
+    # one sample per core per round; rounds until the time budget is spent
+    nb = cores if max_samples is None else max(1, min(cores, max_samples))
+    batch = srm.synth.make_batch(spec.W, spec.H, spec.D, 1, nb, [(w.i, w.j) for w in spec.wells[:8]], seed=2002)
+
+    def one(b):
+        sl = slice(b, b + 1)
+        O.dg_forward_backward(ocfg, otab, batch.kx[sl].numpy(), batch.p0[sl].numpy(), batch.p1[sl].numpy(),
+                              batch.dt1[sl].numpy(), batch.dt2[sl].numpy(), batch.t1[sl].numpy(),
+                              np.zeros(1, np.int32), WEIGHTS)
+        return N
+
+    done = 0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        while True:
+            done += sum(ex.map(one, range(nb)))
+            el = time.perf_counter() - t0
+            if el >= target_seconds or (max_samples is not None and done >= max_samples * N):
+                break
+    el = time.perf_counter() - t0
+    return dict(value=done / el, unit=UNIT, cores=cores, kind="port",
+                sample=f"{done // N} samples of the {name} grid ({spec.W}x{spec.H}x{spec.D}) fwd+autograd backward, "
+                       f"{el:.1f} s, {cores} threads over independent samples"), done, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step = max(2.0, min(20.0, 60.0 / (steps + args.warmup)))
+    vals = []
+    info = None
+    for i in range(args.warmup + steps):
+        info, done, el = cpu_oracle_throughput(args.workload, target_seconds=per_step)
+        if i >= args.warmup:
+            vals.append((done, el))
+    tot = sum(d for d, _ in vals)
+    tt = sum(e for _, e in vals)
+    v = tot / tt
+    c, spec = workload(args.workload)
+    info["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: dry-gas {spec.W}x{spec.H}x{spec.D}, T={c['T']}, K={c['K']} (bounded sample per step)",
+                       "note": "reference CPU path = oracle port of the TF op graph (TensorFlow not installable; reference not import-clean)"},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import srm_b200 as srm
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the physics-loss path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    c, spec = workload(args.workload)
+    T, K = c["T"], c["K"]
+    if args.K:
+        K = args.K
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES, order=1)
+    eng = srm.SrmPhysics(spec, tabs, device=local, numerics=args.numerics)
+    b = srm.synth.make_batch(spec.W, spec.H, spec.D, T, K, [(w.i, w.j) for w in spec.wells[:8]], seed=2002 + rank, device=dev)
+    d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
+    B = b.p0.shape[0]
+    N = B * spec.n_cells
+    dterms = torch.tensor(WEIGHTS, dtype=torch.float32, device=dev)
+
+    def step():
+        fw = eng.forward(**d)
+        if distributed:
+            srm.dist.allreduce_terms(fw["terms"])
+        g = eng.backward(dterms=dterms, **d)
+        return fw["terms"], g
+
+    def barrier():
+        if distributed:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ef = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    e0.record()
+    for i in range(args.steps):
+        fw = eng.forward(**d)
+        if distributed:
+            srm.dist.allreduce_terms(fw["terms"])
+        ef[2 * i].record()
+        eng.backward(dterms=dterms, **d)
+        ef[2 * i + 1].record()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launches - l0
+    ms = e0.elapsed_time(e1)
+    fwd_ms = np.mean([(e0 if i == 0 else ef[2 * i - 1]).elapsed_time(ef[2 * i]) for i in range(args.steps)])
+    bwd_ms = np.mean([ef[2 * i].elapsed_time(ef[2 * i + 1]) for i in range(args.steps)])
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_step = ms / args.steps
+    value = world * N * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    host = {k: v.cpu().pin_memory() for k, v in d.items()}
+    out_host = dict(gp0=torch.empty_like(host["p0"]).pin_memory(), gp1=torch.empty_like(host["p1"]).pin_memory(),
+                    gdt1=torch.empty_like(host["dt1"]).pin_memory(), gdt2=torch.empty_like(host["dt2"]).pin_memory(),
+                    terms=torch.empty((2, 8), dtype=torch.float32).pin_memory())
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    def e2e_step():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        fw = eng.forward(**dd)
+        if distributed:
+            srm.dist.allreduce_terms(fw["terms"])
+        g = eng.backward(dterms=dterms, **dd)
+        out_host["terms"].copy_(fw["terms"], non_blocking=True)
+        for k, v in zip(("gp0", "gp1", "gdt1", "gdt2"), g):
+            out_host[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        import torch.distributed as dist
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(te.item())
+    loss = float((out_host["terms"][0] * torch.tensor(WEIGHTS)).sum())
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        ab = alg_bytes_per_cell(T)
+        achieved = N * ab / (ms_step * 1e-3) / 1e9          # per GPU (each rank runs N cells per step)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _, _ = cpu_oracle_throughput(args.workload, target_seconds=12.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: dry-gas {spec.W}x{spec.H}x{spec.D}, T={T}, K={K} per GPU, B={B}, "
+                                   f"{len(spec.wells)} well connections" + (", blocking-factor integral" if spec.use_blocking_factor else ""),
+                       "numerics": args.numerics, "cells_per_gpu_per_step": N,
+                       "l2": "inputs+workspace per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % ((2 * N * 4 + eng.workspace(B).numel()) / 1e6),
+                       "parallelism": f"sample-sharded x{world}; all-reduce of the 16-float loss-term vector only"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "whole step (forward + adjoint launches); algorithmic bytes = %.2f B/cell-timestep" % ab,
+                         "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "loss": loss},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if distributed:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--numerics", default="reference", choices=["reference", "closed_form"])
+    ap.add_argument("--K", type=int, default=0, help="override realisations per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

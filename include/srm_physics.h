@@ -134,6 +134,12 @@ int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, floa
 int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi,
                         float* out, void* stream);
 
+/* Self-test of the library's own correctly rounded sqrt / division sequences (they replace the
+ * slower IEEE intrinsics inside the reference-order spline): n pseudo-random operands from the
+ * spline's operand ranges; mismatches[0..2] (host) = #sqrt, #division, #chained-division results
+ * whose bits differ from sqrt.rn / div.rn.  Synchronises the stream.  No reference counterpart. */
+int srm_selftest_rounding(int32_t device, int64_t n, uint64_t seed, int64_t* mismatches, void* stream);
+
 /* WellRatesPressure.compute_rates_and_bhp (well_rate_bhp_Subclassed.py:727-837) incl.
  * _non_iterative_method (:614-724), _compute_phase_rates (:963-1007),
  * compute_blocking_integral_and_factor (:840-960), and the integer bookkeeping of

@@ -238,3 +238,13 @@ def test_error_behaviour():
                              C.c_void_p(d["dt2"].data_ptr()), C.c_void_p(d["t1"].data_ptr()),
                              C.c_void_p(terms.data_ptr()), None, None, None, C.c_void_p(ws.data_ptr()), 16, 0, None)
     assert rc == -3 and b"workspace" in eng.lib.srm_last_error()
+
+
+def test_rounding_selftest_matches_ieee_intrinsics():
+    """the shared-rsqrt sqrt/div sequences are bit-identical to sqrt.rn / div.rn on 2^28 operands"""
+    import ctypes as C
+    lib = srm._lib.load_library()
+    bad = (C.c_int64 * 3)()
+    for seed in (1, 2):
+        srm._lib.check(lib, lib.srm_selftest_rounding(0, 1 << 27, seed, bad, None), "srm_selftest_rounding")
+        assert list(bad) == [0, 0, 0], list(bad)
