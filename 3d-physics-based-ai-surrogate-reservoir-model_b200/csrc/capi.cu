@@ -25,6 +25,8 @@ int srm_launch_unsort_wells(const SrmHandle* h, int32_t B, const float* sorted, 
 int srm_launch_selftest_rounding(int64_t n, uint64_t seed, int64_t* bad_host, cudaStream_t s);
 int srm_build_closed_form(SrmHandle* h, const SrmConfig* cfg);
 int srm_launch_pvt_eval_cf(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s);
+int srm_launch_wells_cf(const SrmHandle* h, int32_t B, const float* kx, const int32_t* sample_real, int32_t R,
+                        const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp, cudaStream_t s);
 int srm_forward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                    const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                    float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s);
@@ -151,8 +153,7 @@ void srm_destroy(SrmHandle* h) {
 size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t flags) {
   if (!h || B < 0) return 0;
   (void)flags;
-  // the backward fields are always carved so that srm_backward can run on any forward workspace
-  return srm_carve(nullptr, B, h->dev.N, h->dev.n_wells, true).bytes;
+    return srm_carve(nullptr, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM).bytes;
 }
 
 int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, void* stream) {
@@ -178,7 +179,7 @@ int srm_selftest_rounding(int32_t device, int64_t n, uint64_t seed, int64_t* mis
 
 static int check_batch(const SrmHandle* h, int32_t B, int32_t R, const char* who) {
   if (!h) { srm_set_error("%s: null handle", who); return SRM_ERR_INVALID; }
-  if (B < 1 || R < 1 || B > 65535) { srm_set_error("%s: B=%d (1..65535), R=%d", who, B, R); return SRM_ERR_INVALID; }
+  if (B < 1 || R < 1 || B > 65535 || R > SRM_MAXR) { srm_set_error("%s: B=%d (1..65535), R=%d (1..%d)", who, B, R, SRM_MAXR); return SRM_ERR_INVALID; }
   return SRM_OK;
 }
 
@@ -198,7 +199,8 @@ int srm_wells(const SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
   float* tmp = nullptr;
   SRM_CUDA_CHECK(cudaMallocAsync((void**)&tmp, sizeof(float) * 3 * (size_t)B * nw, s));
   float *tq = tmp, *tp = tmp + (size_t)B * nw, *td = tmp + 2 * (size_t)B * nw;
-  rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p, t_days, tq, tp, td, s);
+  rc = (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM) ? srm_launch_wells_cf(h, B, kx, sample_real, R, p, t_days, tq, tp, td, s)
+                                                      : srm_launch_wells_ref(h, B, kx, sample_real, R, p, t_days, tq, tp, td, s);
   if (!rc && qw) rc = srm_launch_unsort_wells(h, B, tq, qw, s);
   if (!rc && pwfw) rc = srm_launch_unsort_wells(h, B, tp, pwfw, s);
   if (!rc && dqdp) rc = srm_launch_unsort_wells(h, B, td, dqdp, s);
@@ -218,7 +220,7 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
     srm_set_error("srm_forward: null argument");
     return SRM_ERR_INVALID;
   }
-  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, true);
+  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return SRM_ERR_WORKSPACE;
@@ -251,7 +253,7 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
     srm_set_error("srm_backward: null argument");
     return SRM_ERR_INVALID;
   }
-  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, true);
+  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_backward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return SRM_ERR_WORKSPACE;

@@ -13,38 +13,26 @@
 // neighbour values re-read through L1/L2.
 #include <math_constants.h>
 #include "pvt_ref.cuh"
+#include "common.cuh"
+#include "wells.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 
-// ------------------------------------------------------------------------------------------
-// block reduction of NV doubles; result valid in thread 0
-// ------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], double* smem /* [NV*32] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int q = 0; q < NV; ++q) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+// mg = krg*invBg*invug at a (dual) pressure, reference-order spline   well_rate_bhp_Subclassed.py:799
+struct MobilityRef {
+  __device__ __forceinline__ Dual operator()(const SrmDev& P, Dual p) const {
+    float pass;
+    const float x = srm_clamp(P, p.v, pass);
+    float v[2], d[2], d2[2];
+    srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
+    const float kA = __fmul_rn(P.krg, v[0]);
+    const float mg = __fmul_rn(kA, v[1]);
+    const float dmg = P.krg * (d[0] * v[1] + v[0] * d[1]) * pass * p.d;
+    return dmk(mg, dmg);
   }
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < NV; ++q) smem[q * 32 + warp] = v[q];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-      double x = (lane < nw) ? smem[q * 32 + lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      v[q] = x;
-    }
-  }
-}
+};
 
 // ------------------------------------------------------------------------------------------
 // PVT eval
@@ -98,122 +86,6 @@ __global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ 
       G1p[g] = (d[0] * v[1] + v[0] * d[1]) * m1;
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------
-// wells: forward-mode dual numbers carry d/dp of the connection-cell pressure through the
-// min/max/clip/divide_no_nan chain with TensorFlow's gradient conventions.
-// ------------------------------------------------------------------------------------------
-struct Dual { float v, d; };
-__device__ __forceinline__ Dual dmk(float v, float d = 0.f) { Dual r; r.v = v; r.d = d; return r; }
-__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return dmk(__fadd_rn(a.v, b.v), a.d + b.d); }
-__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return dmk(__fsub_rn(a.v, b.v), a.d - b.d); }
-__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return dmk(__fmul_rn(a.v, b.v), a.d * b.v + a.v * b.d); }
-__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
-  const float q = __fdiv_rn(a.v, b.v);
-  return dmk(q, (a.d - q * b.d) / b.v);
-}
-// tf.math.divide_no_nan
-__device__ __forceinline__ Dual ddnn(Dual a, Dual b) { return (b.v == 0.f) ? dmk(0.f, 0.f) : a / b; }
-// tf.minimum / tf.maximum: ties route the gradient to the first argument
-__device__ __forceinline__ Dual dmin(Dual a, Dual b) { return (a.v <= b.v) ? a : b; }
-__device__ __forceinline__ Dual dmax(Dual a, Dual b) { return (a.v >= b.v) ? a : b; }
-// tf.clip_by_value(t, lo, hi)
-// value = max(min(t,hi),lo) (the kernel's cwiseMin/cwiseMax); gradient per _ClipByValueGrad:
-// to t where lo <= t <= hi, to lo where t < lo, to hi where t > hi
-__device__ __forceinline__ Dual dclip(Dual t, Dual lo, Dual hi) {
-  const bool below = t.v < lo.v, above = t.v > hi.v;
-  return dmk(fmaxf(fminf(t.v, hi.v), lo.v), ((!below && !above) ? t.d : 0.f) + (below ? lo.d : 0.f) + (above ? hi.d : 0.f));
-}
-
-// mg = krg*invBg*invug at a (dual) pressure                       well_rate_bhp_Subclassed.py:799
-__device__ __forceinline__ Dual mobility_ref(const SrmDev& P, Dual p) {
-  float pass;
-  const float x = srm_clamp(P, p.v, pass);
-  float v[2], d[2], d2[2];
-  srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
-  const float kA = __fmul_rn(P.krg, v[0]);
-  const float mg = __fmul_rn(kA, v[1]);
-  const float dmg = P.krg * (d[0] * v[1] + v[0] * d[1]) * pass * p.d;
-  return dmk(mg, dmg);
-}
-
-// compute_blocking_integral_and_factor, DG branch             well_rate_bhp_Subclassed.py:840-960
-__device__ Dual blocking_integral_ref(const SrmDev& P, Dual p, Dual pwf, Dual mg_n1) {
-  const int n = P.n_int;
-  const Dual delta = (pwf - p) / dmk((float)n);          // tf.linspace: delta = (stop-start)/n
-  Dual sum = dmk(0.f), mg_prev = mg_n1, pa = p;
-  for (int i = 0; i < n; ++i) {
-    const Dual pb = (i + 1 < n) ? p + delta * dmk((float)(i + 1)) : pwf;   // ends are exact
-    const Dual mg1 = mobility_ref(P, pb);                  // Sg1 = Sg_max -> same krg (:912)
-    const Dual dp = pa - pb;
-    sum = sum + dmk(0.5f) * (mg_prev + mg1) * dp;          // :920
-    mg_prev = mg1;
-    pa = pb;
-  }
-  return sum;
-}
-
-__global__ void __launch_bounds__(128) k_wells_ref(const __grid_constant__ SrmDev P, int32_t B, int32_t R,
-                                                   const float* __restrict__ kx, const int32_t* __restrict__ sample_real,
-                                                   const float* __restrict__ pfield, const float* __restrict__ t_days,
-                                                   float* __restrict__ qw, float* __restrict__ pwfw,
-                                                   float* __restrict__ dqdp) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nw = P.n_wells;
-  if (g >= (int64_t)B * nw) return;
-  const int b = (int)(g / nw), w = (int)(g % nw);
-  const WellDev wd = P.wells[w];
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
-  const float k = kx[(int64_t)r * P.N + wd.cell];
-  const Dual p = dmk(pfield[(int64_t)b * P.N + wd.cell], 1.0f);
-  // shut-in mask: 1 unless shut_start <= t <= shut_stop          welldata_processor.py:349-354
-  const float t = t_days[b];
-  const float open = (t >= wd.shut_start && t <= wd.shut_stop) ? 0.f : 1.f;
-  // Peaceman                                                  well_rate_bhp_Subclassed.py:782-788
-  const float ky = __fmul_rn(P.kx_ky, k);
-  const float ryx = __fdiv_rn(ky, k), rxy = __fdiv_rn(k, ky);
-  const float num = sqrtf(__fadd_rn(__fmul_rn(sqrtf(ryx), __fmul_rn(P.dx, P.dx)),
-                                    __fmul_rn(sqrtf(rxy), __fmul_rn(P.dy, P.dy))));
-  const float den = __fadd_rn(powf(ryx, 0.25f), powf(rxy, 0.25f));
-  const float ro = __fdiv_rn(__fmul_rn(0.28f, num), den);
-  const float two_pi = 6.283185307179586f;
-  float ck = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(two_pi, wd.hc), k), P.dz), P.C);
-  ck = __fdiv_rn(ck, logf(__fdiv_rn(ro, wd.rw)));
-  const Dual Ck = dmk(__fmul_rn(open, ck));
-  const Dual mg = mobility_ref(P, p);
-  const Dual pmin = dmk(wd.pwf_min), qt = dmk(wd.q_target), zero = dmk(0.f), tiny = dmk(1e-12f);
-  // ---- _non_iterative_method                                 :614-724
-  Dual ig_max = dmk(1.f);
-  if (P.use_blk) ig_max = blocking_integral_ref(P, p, pmin, mg);
-  const Dual dp_max = (p - pmin) + tiny;                                       // :650
-  const Dual blk_max = P.use_blk ? ddnn(ig_max, mg * dp_max) : ig_max;         // :654-657
-  const Dual ckb = Ck * blk_max;                                               // well_id == 1
-  const Dual qg_max = ckb * mg * dp_max;                                       // :662
-  const Dual qg_opt = dmax(dmin(qt, qg_max), zero);                            // :666
-  const Dual lam = dclip(ddnn(qg_opt, ckb * mg), zero, blk_max);               // :699
-  const Dual dp_opt = lam * dp_max;                                            // :721
-  const Dual pwf = dclip(p - dp_opt, pmin, p);                                 // :723
-  // ---- _compute_phase_rates                                  :963-1007
-  Dual ig = dmk(1.f);
-  if (P.use_blk) ig = blocking_integral_ref(P, p, pwf, mg);
-  const Dual dp = (p - pwf) + tiny;                                            // :987
-  const Dual blk = P.use_blk ? ddnn(ig, mg * dp) : ig;                         // :991
-  const Dual qg_max2 = Ck * blk * mg * dp;                                     // :997
-  const Dual qg = dmax(dmin(qt, qg_max2), zero);                               // :1001
-  qw[g] = qg.v;
-  pwfw[g] = pwf.v;
-  dqdp[g] = qg.d;
-}
-
-// first well (sorted by cell) with cell >= c
-__device__ __forceinline__ int well_lower_bound(const SrmDev& P, int c) {
-  int lo = 0, hi = P.n_wells;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (P.wells[mid].cell < c) lo = mid + 1; else hi = mid;
-  }
-  return lo;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -354,31 +226,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_ref(
   }
 }
 
-// mbc_b = (-sum q) - sum mb_cells ; SSE_mbc ; terms/counts        physics_loss.py:193,800-832
-__global__ void k_finalize_fwd(const __grid_constant__ SrmDev P, int32_t B, double* __restrict__ sse,
-                               const double* __restrict__ mb_sum, const double* __restrict__ q_sum,
-                               float* __restrict__ mbc, float* __restrict__ terms_out) {
-  __shared__ double red[32];
-  double v[1] = {0.0};
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float m = __fsub_rn(-(float)q_sum[b], (float)mb_sum[b]);
-    mbc[b] = m;
-    v[0] += (double)m * (double)m;
-  }
-  block_reduce<1>(v, red);
-  if (threadIdx.x == 0) {
-    sse[SRM_TERM_MBC] = v[0];
-    const double n = (double)B * (double)P.N;
-    for (int t = 0; t < SRM_N_TERMS; ++t) {
-      terms_out[t] = (float)sse[t];
-      double cnt = 0.0;
-      if (t == SRM_TERM_DOM || t == SRM_TERM_IBC || t == SRM_TERM_TDE) cnt = n;
-      if (t == SRM_TERM_MBC) cnt = (double)B;
-      terms_out[SRM_N_TERMS + t] = (float)cnt;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // adjoint
 // ------------------------------------------------------------------------------------------
@@ -512,15 +359,6 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref(
   atomicAdd(&gp1[base + c], s * (P.dv * self + dq));
 }
 
-__global__ void k_finalize_adj(int32_t B, const double* __restrict__ a1, const double* __restrict__ a2,
-                               float* __restrict__ gdt1, float* __restrict__ gdt2) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    gdt1[b] = (float)a1[b];
-    gdt2[b] = (float)a2[b];
-  }
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -540,7 +378,7 @@ int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const i
                          const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp, cudaStream_t s) {
   const int64_t n = (int64_t)B * h->dev.n_wells;
   if (n <= 0) return SRM_OK;
-  k_wells_ref<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->dev, B, R, kx, sample_real, p, t_days, qw, pwfw, dqdp);
+  k_wells<MobilityRef><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->dev, MobilityRef(), B, R, kx, sample_real, p, t_days, qw, pwfw, dqdp);
   SRM_CUDA_CHECK(cudaGetLastError());
   return SRM_OK;
 }

@@ -41,13 +41,22 @@ struct SrmDev {
   float v[SRM_MAXP][2];
 };
 
-// Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory.
+// Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory
+// (copied to shared memory by the tiled kernels).
+//   interval k in [0, n]: k = number of knots <= x;  value_q(x) = f0[q][k] + slope[q][k]*(x - x0[k])
+#define SRM_CF_MAXBUCKET 4096
 struct SrmClosedForm {
-  // interval k in [0, n_knots]: (-inf,c0), [c0,c1), ..., [c_{n-1}, inf)
-  // value(x) = f0[k] + slope[k] * (x - x0[k])
+  int32_t n;            // knots
+  int32_t use_bucket;   // bucket[] valid (every bucket holds at most one knot)
+  int32_t nb;           // buckets
+  float inv_w;          // 1 / bucket width
+  float2 lohi[SRM_MAXK + 1];            // [lo, hi) of interval k; lo(0) = -inf, hi(n) = +inf
+  float4 ent[SRM_MAXK + 1];             // DG packing: {x0, f0[0], slope[0], f0[1]}
+  float sM[SRM_MAXK + 1];               //             slope[1]
   float x0[SRM_MAXK + 1];
   float f0[SRM_MAXP][SRM_MAXK + 1];
   float slope[SRM_MAXP][SRM_MAXK + 1];
+  unsigned char bucket[SRM_CF_MAXBUCKET];   // bucket b -> number of knots <= b*w
 };
 
 struct SrmHandle {
@@ -63,6 +72,7 @@ struct SrmHandle {
 };
 
 // ---- workspace carving ------------------------------------------------------------------
+#define SRM_MAXR 65536
 struct SrmWs {
   double* sse;        // [8]
   double* mb_sum;     // [B]  sum over cells of mb_cells
@@ -74,12 +84,18 @@ struct SrmWs {
   float* pwfw;        // [B*nw]
   float* dqdp;        // [B*nw]
   float* divqw;       // [B*nw]
-  float* A0;          // fields [B*N]
+  // closed-form scheduling: samples grouped by realisation, cut into segments
+  int32_t* grp_cnt;   // [SRM_MAXR+1]  counts -> exclusive starts
+  int32_t* grp_fill;  // [SRM_MAXR]
+  int32_t* grp_list;  // [B]   sample ids, grouped by realisation, ascending within a group
+  int32_t* seg;       // [3*(B+1)] (r, offset into grp_list, count)
+  int32_t* ctl;       // [8]   ctl[0] = number of segments, ctl[1..2] = work counters
+  float* dom;         // field [B*N]
+  float* A0;          // reference-order fields [B*N]
   float* A0p;
   float* A1;
   float* G1;
-  float* dom;
-  float* A0pp;        // backward-only fields
+  float* A0pp;
   float* G1p;
   float* A1p;
   size_t bytes;
@@ -87,7 +103,7 @@ struct SrmWs {
 
 static inline size_t srm_align(size_t x) { return (x + 255) & ~size_t(255); }
 
-static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool with_bwd) {
+static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool closed_form) {
   SrmWs w;
   char* p = (char*)base;
   size_t off = 0;
@@ -103,18 +119,25 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool
   w.pwfw = (float*)take(wt);
   w.dqdp = (float*)take(wt);
   w.divqw = (float*)take(wt);
+  w.grp_cnt = w.grp_fill = w.grp_list = w.seg = w.ctl = nullptr;
+  if (closed_form) {
+    w.grp_cnt = (int32_t*)take((SRM_MAXR + 1) * sizeof(int32_t));
+    w.grp_fill = (int32_t*)take(SRM_MAXR * sizeof(int32_t));
+    w.grp_list = (int32_t*)take(B * sizeof(int32_t));
+    w.seg = (int32_t*)take(3 * (B + 1) * sizeof(int32_t));
+    w.ctl = (int32_t*)take(8 * sizeof(int32_t));
+  }
   size_t fb = (size_t)(B * N) * sizeof(float);
-  w.A0 = (float*)take(fb);
-  w.A0p = (float*)take(fb);
-  w.A1 = (float*)take(fb);
-  w.G1 = (float*)take(fb);
   w.dom = (float*)take(fb);
-  if (with_bwd) {
+  w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
+  if (!closed_form) {
+    w.A0 = (float*)take(fb);
+    w.A0p = (float*)take(fb);
+    w.A1 = (float*)take(fb);
+    w.G1 = (float*)take(fb);
     w.A0pp = (float*)take(fb);
     w.G1p = (float*)take(fb);
     w.A1p = (float*)take(fb);
-  } else {
-    w.A0pp = w.G1p = w.A1p = nullptr;
   }
   w.bytes = off;
   return w;
