@@ -56,6 +56,7 @@ int srm_build_closed_form(SrmHandle* h, const SrmConfig* cfg) {
       }
       T.f0[q][k] = (float)f;
       T.slope[q][k] = (float)sl;
+      if (q == 0) T.f0d[k] = f;
     }
     T.ent[k] = make_float4(T.x0[k], T.f0[0][k], T.slope[0][k], T.f0[1][k]);
     T.sM[k] = T.slope[1][k];
@@ -116,17 +117,23 @@ __device__ __forceinline__ float cf_clamp(const SrmDev& P, float p, float& pass)
 }
 
 // invBg and its slope at p0
-__device__ __forceinline__ void cf_pvt_p0(const SrmDev& P, const SrmClosedForm* __restrict__ T, float p, float& A, float& Ap, float& pass) {
+// (kA, dA): interval and increment sA*(x - x0[k]) over the interval's anchor value -- the material balance
+// sums A1 - A0 = (f0[k1] - f0[k0]) + (dA1 - dA0), whose first part is exact in fp64 and zero when k1 == k0
+__device__ __forceinline__ void cf_pvt_p0(const SrmDev& P, const SrmClosedForm* __restrict__ T, float p, float& A, float& Ap, float& pass,
+                                          int& kA, float& dA) {
   const float x = cf_clamp(P, p, pass);
   bool on;
   const int k = cf_interval(T, x, on);
   const float4 e = T->ent[k];
-  A = fmaf(e.z, x - e.x, e.y);
+  kA = k;
+  dA = e.z * (x - e.x);
+  A = e.y + dA;
   Ap = e.z;
   if (on) Ap = 0.5f * (e.z + T->ent[k - 1].z);
 }
 // invBg, G = invBg*invug and their slopes at p1
-__device__ __forceinline__ void cf_pvt_p1(const SrmDev& P, const SrmClosedForm* __restrict__ T, float p, float& A, float& G, float& Ap, float& Gp) {
+__device__ __forceinline__ void cf_pvt_p1(const SrmDev& P, const SrmClosedForm* __restrict__ T, float p, float& A, float& G, float& Ap, float& Gp,
+                                          int& kA, float& dA) {
   float pass;
   const float x = cf_clamp(P, p, pass);
   bool on;
@@ -134,7 +141,9 @@ __device__ __forceinline__ void cf_pvt_p1(const SrmDev& P, const SrmClosedForm* 
   const float4 e = T->ent[k];
   float sA = e.z, sM = T->sM[k];
   const float dx = x - e.x;
-  A = fmaf(sA, dx, e.y);
+  kA = k;
+  dA = sA * dx;
+  A = e.y + dA;
   const float M = fmaf(sM, dx, e.w);
   G = A * M;
   if (on) { sA = 0.5f * (sA + T->ent[k - 1].z); sM = 0.5f * (sM + T->sM[k - 1]); }
@@ -168,11 +177,19 @@ __global__ void __launch_bounds__(256) k_pvt_eval_cf(const __grid_constant__ Srm
   }
 }
 
+// A(p1) - A(p0) from the (interval, increment) pairs
+__device__ __forceinline__ float cf_dA(const SrmClosedForm* __restrict__ T, int k1, float d1, int k0, float d0) {
+  float r = d1 - d0;
+  if (k1 != k0) r += (float)(T->f0d[k1] - T->f0d[k0]);
+  return r;
+}
+
 struct MobilityCf {
   const SrmClosedForm* T;
   __device__ __forceinline__ Dual operator()(const SrmDev& P, Dual p) const {
-    float A, G, Ap, Gp;
-    cf_pvt_p1(P, T, p.v, A, G, Ap, Gp);
+    float A, G, Ap, Gp, dA;
+    int kA;
+    cf_pvt_p1(P, T, p.v, A, G, Ap, Gp, kA, dA);
     return dmk(P.krg * G, P.krg * Gp * p.d);
   }
 };
@@ -459,7 +476,8 @@ __global__ void __launch_bounds__(TX * TY, 1) k_fwd_cf(const __grid_constant__ S
       if (tid == 0) for (int j = 0; j < min(S, J); ++j) issue(j);
     }
     // registers carried along z
-    float p_prev = 0.f, G_prev = 0.f, p_cur = 0.f, G_cur = 0.f, A1_cur = 0.f;
+    float p_prev = 0.f, G_prev = 0.f, p_cur = 0.f, G_cur = 0.f, dA1_cur = 0.f;
+    int kA1_cur = 0;
     float cA = 0.f, cT = 0.f, mbk = 0.f, mb_part = 0.f;
     int b_cur = 0;
     bool flush_pending = false;
@@ -488,8 +506,9 @@ __global__ void __launch_bounds__(TX * TY, 1) k_fwd_cf(const __grid_constant__ S
       // G of the arriving plane: own cell + halo ring
       float* Gb = Gs + (j % 3) * (L::BOX1_B / 4);
       const float p_next = stage_p1(s)[(ty + 1) * BX + tx + XO];
-      float A1_next, G_next, dummy1, dummy2;
-      cf_pvt_p1(P, Ts, p_next, A1_next, G_next, dummy1, dummy2);
+      float A1_next, G_next, dummy1, dummy2, dA1_next;
+      int kA1_next;
+      cf_pvt_p1(P, Ts, p_next, A1_next, G_next, dummy1, dummy2, kA1_next, dA1_next);
       Gb[(ty + 1) * BX + tx + XO] = G_next;
       {
         int hx, hy;
@@ -520,8 +539,9 @@ __global__ void __launch_bounds__(TX * TY, 1) k_fwd_cf(const __grid_constant__ S
         const int gz = k0 + m;
         if (in_xy && gz < P.D) {
           const float p0c = stage_p0(sp1)[ty * TX + tx];
-          float A0, A0p, pass0;
-          cf_pvt_p0(P, Ts, p0c, A0, A0p, pass0);
+          float A0, A0p, pass0, dA0;
+          int kA0;
+          cf_pvt_p0(P, Ts, p0c, A0, A0p, pass0, kA0, dA0);
           const float cp = P.Sgi * fmaf(P.phi, A0p, P.phicf * A0);
           const float acc = cA * cp * (pc - p0c);
           const float tde = cT * cp;
@@ -544,12 +564,12 @@ __global__ void __launch_bounds__(TX * TY, 1) k_fwd_cf(const __grid_constant__ S
           if (A.dom_out) __stcs(&A.dom_out[g], dom);
           acc_dom = fmaf(dom, dom, acc_dom);
           acc_tde = fmaf(tde, tde, acc_tde);
-          mb_part += A1_cur - A0;
+          mb_part += cf_dA(Ts, kA1_cur, dA1_cur, kA0, dA0);
         }
       }
       // rotate the z window
       p_prev = p_cur; G_prev = G_cur;
-      p_cur = p_next; G_cur = G_next; A1_cur = A1_next;
+      p_cur = p_next; G_cur = G_next; dA1_cur = dA1_next; kA1_cur = kA1_next;
       if (kk == DZ) {   // sample finished: publish its material-balance partial
         float v[1] = {mb_part};
         warp_sum<1>(v);
@@ -663,7 +683,8 @@ __global__ void __launch_bounds__(TX * TY, 1) k_adj_cf(const __grid_constant__ S
       if (tid == 0) for (int j = 0; j < min(S, J); ++j) issue(j);
     }
     float p_prev = 0.f, G_prev = 0.f, d_prev = 0.f;
-    float p_cur = 0.f, G_cur = 0.f, d_cur = 0.f, A1_cur = 0.f, A1p_cur = 0.f, Gp_cur = 0.f;
+    float p_cur = 0.f, G_cur = 0.f, d_cur = 0.f, dA1_cur = 0.f, A1p_cur = 0.f, Gp_cur = 0.f;
+    int kA1_cur = 0;
     float cA = 0.f, cT = 0.f, mbk = 0.f, inv_d1 = 0.f, smb = 0.f, g1_part = 0.f;
     int b_cur = 0;
     bool flush_pending = false;
@@ -695,8 +716,9 @@ __global__ void __launch_bounds__(TX * TY, 1) k_adj_cf(const __grid_constant__ S
       const int c = (ty + 1) * BX + tx + XO;
       const float p_next = stage_p1(s)[c];
       const float d_next = stage_dm(s)[c];
-      float A1_next, G_next, A1p_next, Gp_next;
-      cf_pvt_p1(P, Ts, p_next, A1_next, G_next, A1p_next, Gp_next);
+      float A1_next, G_next, A1p_next, Gp_next, dA1_next;
+      int kA1_next;
+      cf_pvt_p1(P, Ts, p_next, A1_next, G_next, A1p_next, Gp_next, kA1_next, dA1_next);
       Gb[c] = G_next;
       {
         int hx, hy;
@@ -733,8 +755,9 @@ __global__ void __launch_bounds__(TX * TY, 1) k_adj_cf(const __grid_constant__ S
           g1 *= sd * P.dv;
           const float sc = sd * dc;
           const float p0c = stage_p0(sp1)[ty * TX + tx];
-          float A0, A0p, pass0;
-          cf_pvt_p0(P, Ts, p0c, A0, A0p, pass0);
+          float A0, A0p, pass0, dA0;
+          int kA0;
+          cf_pvt_p0(P, Ts, p0c, A0, A0p, pass0, kA0, dA0);
           const float cp = P.Sgi * fmaf(P.phi, A0p, P.phicf * A0);
           const float cpp = P.Sgi * P.phicf * A0p * pass0;
           const float dp10 = pc - p0c;
@@ -752,11 +775,11 @@ __global__ void __launch_bounds__(TX * TY, 1) k_adj_cf(const __grid_constant__ S
           const int64_t g = (int64_t)b_cur * P.N + cell;
           __stcs(&A.gp0[g], g0);
           __stcs(&A.gp1[g], g1);
-          g1_part += (-(sc * acc + st * tde) + smb * mbk * (A1_cur - A0)) * inv_d1;
+          g1_part += (-(sc * acc + st * tde) + smb * mbk * cf_dA(Ts, kA1_cur, dA1_cur, kA0, dA0)) * inv_d1;
         }
       }
       p_prev = p_cur; G_prev = G_cur; d_prev = d_cur;
-      p_cur = p_next; G_cur = G_next; d_cur = d_next; A1_cur = A1_next; A1p_cur = A1p_next; Gp_cur = Gp_next;
+      p_cur = p_next; G_cur = G_next; d_cur = d_next; dA1_cur = dA1_next; kA1_cur = kA1_next; A1p_cur = A1p_next; Gp_cur = Gp_next;
       if (kk == DZ) {
         float v[1] = {g1_part};
         warp_sum<1>(v);
@@ -795,9 +818,10 @@ __global__ void __launch_bounds__(128) k_ibc_adj_cf(const __grid_constant__ SrmD
   const int64_t base = (int64_t)b * P.N;
   const float* kr = kx + (int64_t)r * P.N;
   const int i = c % P.W, j = (c / P.W) % P.H, k = c / (P.W * P.H), HW = P.H * P.W;
-  float Ac, Gc, Apc, Gpc;
+  float Ac, Gc, Apc, Gpc, dAc;
+  int kAc;
   const float pc = p1f[base + c];
-  cf_pvt_p1(P, T, pc, Ac, Gc, Apc, Gpc);
+  cf_pvt_p1(P, T, pc, Ac, Gc, Apc, Gpc, kAc, dAc);
   const float kc = kr[c];
   float self = 0.f;
   auto hm = [](float a, float bb) { return 2.f * a * bb / (a + bb); };
@@ -805,8 +829,9 @@ __global__ void __launch_bounds__(128) k_ibc_adj_cf(const __grid_constant__ SrmD
     if (!ok) return;
     const float Tf = 0.5f * P.C * P.krg * idl * idl * hm(ratio * kc, ratio * kr[cn]);
     const float pn = p1f[base + cn];
-    float An, Gn, Apn, Gpn;
-    cf_pvt_p1(P, T, pn, An, Gn, Apn, Gpn);
+    float An, Gn, Apn, Gpn, dAn;
+    int kAn;
+    cf_pvt_p1(P, T, pn, An, Gn, Apn, Gpn, kAn, dAn);
     const float af = Tf * (Gc + Gn);
     self += af + Tf * Gpc * (pc - pn);
     atomicAdd(&gp1[base + cn], s * P.dv * (-af + Tf * Gpn * (pc - pn)));

@@ -56,6 +56,7 @@ struct SrmClosedForm {
   float x0[SRM_MAXK + 1];
   float f0[SRM_MAXP][SRM_MAXK + 1];
   float slope[SRM_MAXP][SRM_MAXK + 1];
+  double f0d[SRM_MAXK + 1];             // f0[0] (invBg) in fp64: exact anchor differences for the material balance
   unsigned char bucket[SRM_CF_MAXBUCKET];   // bucket b -> number of knots <= b*w
 };
 

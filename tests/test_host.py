@@ -134,3 +134,18 @@ def test_synthetic_batch_ranges():
     assert float(b.p0.min()) > 4100 and float(b.p0.max()) <= 5000 and float((b.p0 - b.p1).max()) <= 31
     assert float(b.dt1.min()) >= 0.1 and float(b.dt1.max()) <= 10.0
     assert b.sample_real.tolist() == [0, 0, 0, 0, 1, 1, 1, 1]
+
+
+def test_well_data_processor_integer_bookkeeping():
+    wdp = srm.WellDataProcessor(srm.config.DEFAULT_WELLS["connections"])
+    wd = wdp.get_well_data()
+    assert wd["connection_index"].tolist() == [[0, 29, 29], [0, 9, 29], [0, 9, 9], [0, 29, 9], [0, 19, 19]]   # rows [k, j, i]
+    assert wd["control_mode_value"].tolist()[:4] == [500.0, 1000.0, 500.0, 1000.0]
+    m = wdp.scatter_y((1, 1, 39, 39, 1), wd["connection_index"], 1.0)
+    assert float(m.sum()) == 5.0 and m[0, 0, 29, 29, 0] == 1.0 and m[0, 0, 9, 29, 0] == 1.0
+    dup = wdp.scatter_y((1, 1, 4, 4, 1), [[0, 1, 1], [0, 1, 1]], [2.0, 3.0])
+    assert dup[0, 0, 1, 1, 0] == 5.0                          # duplicates sum (tf.scatter_nd)
+    import torch
+    t = torch.tensor([5.0, 15.0, 25.0]).view(3, 1, 1, 1).expand(3, 1, 4, 4)
+    s = wdp.conn_shutins_idx(t, [[0, 1, 1], [0, 2, 3]], [[[10.0, 20.0]], [[1000.0, 0.0]]])
+    assert s[:, 0, 1, 1].tolist() == [1, 0, 1] and s[:, 0, 2, 3].tolist() == [1, 1, 1] and int(s.sum()) == 5
