@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrm_physics.so")
 
-SRM_ABI_VERSION = 1
+SRM_ABI_VERSION = 2
 SRM_N_TERMS = 8
 TERM_NAMES = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
 SRM_FLUID_DG, SRM_FLUID_GC = 0, 1
@@ -51,6 +51,7 @@ class SrmConfig(C.Structure):
         ("n_wells", C.c_int32), ("wells", C.POINTER(SrmWell)),
         ("use_blocking_factor", C.c_int32), ("n_intervals", C.c_int32),
         ("numerics", C.c_int32), ("tde_in_dom", C.c_int32),
+        ("pvt_lut", C.c_int32), ("lut_p_lo", C.c_float), ("lut_p_hi", C.c_float),
     ]
 
 
@@ -78,7 +79,7 @@ def load_library(path: Optional[str] = None):
     lib.srm_destroy.restype = None
     lib.srm_destroy.argtypes = [vp]
     lib.srm_workspace_bytes.restype = C.c_size_t
-    lib.srm_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.srm_workspace_bytes.argtypes = [vp, i32, i32, i32]
     lib.srm_pvt_eval.restype = C.c_int
     lib.srm_pvt_eval.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.srm_denormalize_log.restype = C.c_int
@@ -116,7 +117,8 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
                 phi: float, cf: float, Sgi: float, krg: float, kx_ky: float, kv_kh: float,
                 knots: np.ndarray, spline_w: np.ndarray, spline_v: np.ndarray, spline_order: int,
                 p_min: float, p_max: float, wells: Sequence[dict], use_blocking_factor: bool, n_intervals: int,
-                numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG):
+                numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG, pvt_lut: bool = False,
+                lut_range: Optional[Sequence[float]] = None):
     """Fill an SrmConfig; returns (cfg, keepalive) -- keepalive owns the host arrays cfg points into."""
     knots = np.ascontiguousarray(knots, dtype=np.float32)
     spline_w = np.ascontiguousarray(spline_w, dtype=np.float32)
@@ -132,5 +134,7 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
         pvt_method=SRM_PVT_SPLINE, spline_order=spline_order, n_knots=knots.size, n_props=spline_w.shape[0],
         knots=_fptr(knots), spline_w=_fptr(spline_w), spline_v=_fptr(spline_v), p_min=p_min, p_max=p_max,
         n_wells=len(wells), wells=warr, use_blocking_factor=int(bool(use_blocking_factor)),
-        n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)))
+        n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)),
+        pvt_lut=int(bool(pvt_lut)), lut_p_lo=float(lut_range[0]) if lut_range else 0.0,
+        lut_p_hi=float(lut_range[1]) if lut_range else 0.0)
     return cfg, (knots, spline_w, spline_v, warr)

@@ -138,6 +138,13 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     int rc = srm_build_closed_form(h, cfg);
     if (rc) { srm_destroy(h); return rc; }
   }
+  if (cfg->pvt_lut && cfg->numerics == SRM_NUMERICS_REFERENCE) {
+    const bool whole = !(cfg->lut_p_lo < cfg->lut_p_hi);
+    const float lo = whole ? cfg->p_min : std::max(cfg->lut_p_lo, cfg->p_min);
+    const float hi = whole ? cfg->p_max : std::min(cfg->lut_p_hi, cfg->p_max);
+    int rc = srm_build_pvt_lut(h, lo, hi);
+    if (rc) { srm_destroy(h); return rc; }
+  }
   *out = h;
   return SRM_OK;
 }
@@ -147,13 +154,18 @@ void srm_destroy(SrmHandle* h) {
   cudaSetDevice(h->device);
   if (h->d_wells) cudaFree(h->d_wells);
   if (h->d_cf) cudaFree(h->d_cf);
+  if (h->d_lut) cudaFree(h->d_lut);
   delete h;
 }
 
-size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t flags) {
-  if (!h || B < 0) return 0;
+static SrmWs carve(const SrmHandle* h, void* base, int32_t B, int32_t R) {
+  return srm_carve(base, B, R, h->dev.N, h->dev.n_wells, srm_ws_mode(h), srm_ref2_face_floats(h->dev));
+}
+
+size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t R, int32_t flags) {
+  if (!h || B < 0 || R < 0) return 0;
   (void)flags;
-    return srm_carve(nullptr, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM).bytes;
+  return carve(h, nullptr, B, R).bytes;
 }
 
 int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, void* stream) {
@@ -220,7 +232,7 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
     srm_set_error("srm_forward: null argument");
     return SRM_ERR_INVALID;
   }
-  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM);
+  const SrmWs ws = carve(h, workspace, B, R);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return SRM_ERR_WORKSPACE;
@@ -229,8 +241,11 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
   cudaStream_t s = (cudaStream_t)stream;
   const bool save = (flags & SRM_FLAG_SAVE_FOR_BACKWARD) != 0;
   h->st_valid = 0;
-  if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM)
+  const int mode = srm_ws_mode(h);
+  if (mode == SRM_WS_CF)
     rc = srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
+  else if (mode == SRM_WS_REF_FUSED)
+    rc = srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, s);
   else
     rc = srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
   if (rc) return rc;
@@ -253,7 +268,7 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
     srm_set_error("srm_backward: null argument");
     return SRM_ERR_INVALID;
   }
-  const SrmWs ws = srm_carve(workspace, B, h->dev.N, h->dev.n_wells, h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM);
+  const SrmWs ws = carve(h, workspace, B, R);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_backward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
     return SRM_ERR_WORKSPACE;
@@ -261,17 +276,20 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
   SRM_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const bool have = h->st_valid && h->st_ws == workspace && h->st_p0 == p0 && h->st_p1 == p1 && h->st_kx == kx && h->st_B == B;
-  const bool cf = h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM;
+  const int mode = srm_ws_mode(h);
+  const bool cf = mode == SRM_WS_CF;
   if (!have) {
     // recompute the forward state (PVT stage with derivatives, wells, residual field) into the workspace
     float* terms_tmp = nullptr;
     SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
     rc = cf ? srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s)
+         : mode == SRM_WS_REF_FUSED ? srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, s)
             : srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
     cudaFreeAsync(terms_tmp, s);
     if (rc) return rc;
   }
   rc = cf ? srm_backward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
+       : mode == SRM_WS_REF_FUSED ? srm_backward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
           : srm_backward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s);
   return rc;
 }

@@ -12,6 +12,7 @@
 // so they stage PVT results through the workspace instead of tiling: one thread per cell,
 // neighbour values re-read through L1/L2.
 #include <math_constants.h>
+#include <cstring>
 #include "pvt_ref.cuh"
 #include "common.cuh"
 #include "wells.cuh"
@@ -57,7 +58,38 @@ __global__ void __launch_bounds__(kThreads) k_pvt_eval_ref(const __grid_constant
 // ------------------------------------------------------------------------------------------
 // stage: PVT of every cell at both time levels -> workspace
 // ------------------------------------------------------------------------------------------
-template <bool SAVE>
+// Everything the residual and its adjoint need from the PVT layer is a pure function of ONE clamped
+// fp32 pressure.  pack0 (time level n): {invBg, d/dp, d2/dp2, -};  pack1 (level n+1): {invBg,
+// invBg*invug (physics_loss.py:137), d invBg/dp, d(invBg*invug)/dp}.  Derivatives are w.r.t. the
+// clamped input; the consumer applies the clamp's gradient mask.
+template <bool D2>
+__device__ __forceinline__ float4 pvt_pack0(const SrmDev& P, float x0) {
+  float v[1], d[1], d2[1];
+  d2[0] = 0.f;
+  srm_spline_ref<1, true, D2>(P, 0, x0, v, d, d2);
+  return make_float4(v[0], d[0], d2[0], 0.f);
+}
+template <bool D1>
+__device__ __forceinline__ float4 pvt_pack1(const SrmDev& P, float x1) {
+  float v[2], d[2], d2[2];
+  d[0] = d[1] = 0.f;
+  srm_spline_ref<2, D1, false>(P, 0, x1, v, d, d2);
+  return make_float4(v[0], __fmul_rn(v[0], v[1]), d[0], __fmaf_rn(d[0], v[1], __fmul_rn(v[0], d[1])));
+}
+
+// Exact tabulation (SrmConfig.pvt_lut): entry e holds pack0/pack1 of the fp32 value whose bit
+// pattern is lut_lo_bits + e, i.e. EVERY representable pressure of [lut_lo, lut_hi] -- the table
+// is the reference-order spline itself, evaluated once per distinct input instead of once per cell.
+__global__ void __launch_bounds__(kThreads) k_lut_build(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
+                                                        float4* __restrict__ t1) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.lut_n) return;
+  const float x = __uint_as_float(P.lut_lo_bits + e);
+  t0[e] = pvt_pack0<true>(P, x);
+  t1[e] = pvt_pack1<true>(P, x);
+}
+
+template <bool SAVE, bool LUT>
 __global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ SrmDev P, int64_t total,
                                                         const float* __restrict__ p0, const float* __restrict__ p1,
                                                         float* __restrict__ A0, float* __restrict__ A0p,
@@ -69,22 +101,18 @@ __global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ 
   float m0, m1;
   const float x0 = srm_clamp(P, p0[g], m0);
   const float x1 = srm_clamp(P, p1[g], m1);
-  {
-    float v[1], d[1], d2[1];
-    srm_spline_ref<1, true, SAVE>(P, 0, x0, v, d, d2);
-    A0[g] = v[0];
-    A0p[g] = d[0];                 // w.r.t. clamped input: enters cp unmasked (physics_loss.py:150)
-    if (SAVE) A0pp[g] = d2[0] * m0;
-  }
-  {
-    float v[2], d[2], d2[2];
-    srm_spline_ref<2, SAVE, false>(P, 0, x1, v, d, d2);
-    A1[g] = v[0];
-    G1[g] = __fmul_rn(v[0], v[1]);   // invBgug_n1 = invBg*invug   physics_loss.py:137
-    if (SAVE) {
-      A1p[g] = d[0] * m1;
-      G1p[g] = (d[0] * v[1] + v[0] * d[1]) * m1;
-    }
+  float4 a, b;
+  const uint32_t e0 = __float_as_uint(x0) - P.lut_lo_bits, e1 = __float_as_uint(x1) - P.lut_lo_bits;
+  if (LUT && e0 < P.lut_n) a = __ldg(P.lut0 + e0); else a = pvt_pack0<SAVE>(P, x0);
+  if (LUT && e1 < P.lut_n) b = __ldg(P.lut1 + e1); else b = pvt_pack1<SAVE>(P, x1);
+  A0[g] = a.x;
+  A0p[g] = a.y;                  // w.r.t. clamped input: enters cp unmasked (physics_loss.py:150)
+  A1[g] = b.x;
+  G1[g] = b.y;
+  if (SAVE) {
+    A0pp[g] = a.z * m0;
+    A1p[g] = b.z * m1;
+    G1p[g] = b.w * m1;
   }
 }
 
@@ -383,6 +411,26 @@ int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const i
   return SRM_OK;
 }
 
+int srm_build_pvt_lut(SrmHandle* h, float lo, float hi) {
+  SrmDev& P = h->dev;
+  uint32_t lo_bits, hi_bits;
+  memcpy(&lo_bits, &lo, 4);
+  memcpy(&hi_bits, &hi, 4);
+  if (!(lo > 0.f) || !(hi >= lo)) { srm_set_error("srm_create: pvt_lut range [%g, %g] must be positive and ascending", lo, hi); return SRM_ERR_INVALID; }
+  const uint64_t n = (uint64_t)hi_bits - lo_bits + 1;
+  if (n > (1ull << 31)) { srm_set_error("srm_create: pvt_lut range too wide"); return SRM_ERR_INVALID; }
+  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * 2 * sizeof(float4));
+  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut needs %.1f MB of device memory: %s", n * 32e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
+  P.lut_lo_bits = lo_bits;
+  P.lut_n = (uint32_t)n;
+  P.lut0 = h->d_lut;
+  P.lut1 = h->d_lut + n;
+  k_lut_build<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + n);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  SRM_CUDA_CHECK(cudaDeviceSynchronize());
+  return SRM_OK;
+}
+
 int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                     float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s) {
@@ -390,10 +438,12 @@ int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
   const int64_t total = (int64_t)B * P.N;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
   const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
-  if (save)
-    k_stage_ref<true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, ws.A0pp, ws.G1p, ws.A1p);
-  else
-    k_stage_ref<false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, nullptr, nullptr, nullptr);
+  const bool lut = P.lut_n > 0;
+#define SRM_STAGE(SV, LT) k_stage_ref<SV, LT><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, \
+                                                                           (SV) ? ws.A0pp : nullptr, (SV) ? ws.G1p : nullptr, (SV) ? ws.A1p : nullptr)
+  if (save) { if (lut) SRM_STAGE(true, true); else SRM_STAGE(true, false); }
+  else      { if (lut) SRM_STAGE(false, true); else SRM_STAGE(false, false); }
+#undef SRM_STAGE
   SRM_CUDA_CHECK(cudaGetLastError());
   int rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p1, t1, ws.qw, ws.pwfw, ws.dqdp, s);
   if (rc) return rc;

@@ -1,0 +1,547 @@
+// SRM_NUMERICS_REFERENCE, tabulated-PVT path (SrmConfig.pvt_lut): fused forward and adjoint.
+//
+// Same arithmetic, op for op, as kernels_ref.cu (forward fields stay bit-identical to the pinned
+// oracle) -- what changes is the data movement:
+//   * PVT is two 16-byte gathers per cell and pass from the exact table (L2 resident over the
+//     operating window) instead of seven staged fields: forward reads p0,p1 and writes dom (12 B per
+//     cell-timestep), adjoint reads p0,p1,dom and writes gp0,gp1 (20 B).
+//   * the static face coefficients fl(fl(C*k_f)*krg) with k_f = 2 k1 k2/(k1+k2)
+//     (physics_loss.py:56-60,152-155) are built once per call and realisation (k_faces_ref) instead of six
+//     IEEE divisions per cell and sample; boundary slots hold the edge-replicated (self) value.
+//   * one CTA = one 32x16 (x,y) tile of one sample, marching over z: z neighbours live in registers,
+//     x/y neighbours (p1, G = invBg*invug, adjoint seed) go through a double-buffered shared-memory
+//     plane with ONE barrier per plane; the plane ahead is prefetched (loads + gathers in flight while
+//     the current plane is computed).
+//
+//   k_faces_ref     static face coefficients                       physics_loss.py:56-60,152-155
+//   k_fwd_ref2      physics_error_gas residual + SSE partials      physics_loss.py:143-193,787-807
+//   k_adj_ref2      hand-derived adjoint (tape.gradient, physics_loss.py:849-859)
+//   k_ibc_adj_ref2  inner-boundary (well-cell) part of the adjoint
+#include <math_constants.h>
+#include <cstring>
+#include "pvt_ref.cuh"
+#include "common.cuh"
+
+namespace {
+
+constexpr int TX = 32, TY = 16, NT = TX * TY;
+constexpr int SW = TX + 2, SH = TY + 2;
+constexpr int NHALO = 2 * TX + 2 * TY;
+
+// (2.*k1*k2)/(k1+k2)                                             physics_loss.py:59-60
+__device__ __forceinline__ float harm2(float ka, float kb) {
+  return __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, ka), kb), __fadd_rn(ka, kb));
+}
+
+struct FaceLay { int64_t nE, nN, nU, per_real; };
+__host__ __device__ inline FaceLay face_layout(int D, int H, int W) {
+  FaceLay f;
+  f.nE = (int64_t)D * H * (W + 1);
+  f.nN = (int64_t)D * (H + 1) * W;
+  f.nU = (int64_t)(D + 1) * H * W;
+  f.per_real = f.nE + f.nN + f.nU;
+  return f;
+}
+
+// FE[k][j][i], i in [0,W]: face between columns i-1 and i; FN[k][j][i], j in [0,H]; FU[k][j][i], k in [0,D].
+// Slots 0 and W (H, D) are the image faces of the edge-replicating pad: harmonic mean of the cell with itself.
+__global__ void __launch_bounds__(256) k_faces_ref(const __grid_constant__ SrmDev P, const float* __restrict__ kx,
+                                                   float* __restrict__ faces) {
+  const FaceLay L = face_layout(P.D, P.H, P.W);
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= L.per_real) return;
+  const float* kr = kx + (int64_t)blockIdx.y * P.N;
+  float* out = faces + (int64_t)blockIdx.y * L.per_real;
+  const int W = P.W, H = P.H, D = P.D;
+  float ka, kb;   // upper/right cell, lower/left cell
+  if (e < L.nE) {
+    const int i = (int)(e % (W + 1));
+    const int64_t t = e / (W + 1);
+    const int j = (int)(t % H), k = (int)(t / H);
+    const int64_t row = ((int64_t)k * H + j) * W;
+    ka = kr[row + min(i, W - 1)];
+    kb = kr[row + max(i - 1, 0)];
+  } else if (e < L.nE + L.nN) {
+    const int64_t e2 = e - L.nE;
+    const int i = (int)(e2 % W);
+    const int64_t t = e2 / W;
+    const int j = (int)(t % (H + 1)), k = (int)(t / (H + 1));
+    ka = __fmul_rn(P.kx_ky, kr[((int64_t)k * H + min(j, H - 1)) * W + i]);
+    kb = __fmul_rn(P.kx_ky, kr[((int64_t)k * H + max(j - 1, 0)) * W + i]);
+  } else {
+    const int64_t e2 = e - L.nE - L.nN;
+    const int i = (int)(e2 % W);
+    const int64_t t = e2 / W;
+    const int j = (int)(t % H), k = (int)(t / H);
+    ka = __fmul_rn(P.kv_kh, kr[((int64_t)min(k, D - 1) * H + j) * W + i]);
+    kb = __fmul_rn(P.kv_kh, kr[((int64_t)max(k - 1, 0) * H + j) * W + i]);
+  }
+  out[e] = __fmul_rn(__fmul_rn(P.C, harm2(ka, kb)), P.krg);
+}
+
+// ---- PVT packs through the table (direct evaluation outside the tabulated range) -----------------
+template <bool LUT>
+__device__ __forceinline__ float4 pack0_at(const SrmDev& P, float p, float& m) {
+  const float x = srm_clamp(P, p, m);
+  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
+  if (LUT && e < P.lut_n) return __ldg(P.lut0 + e);
+  float v[1], d[1], d2[1];
+  srm_spline_ref<1, true, true>(P, 0, x, v, d, d2);
+  return make_float4(v[0], d[0], d2[0], 0.f);
+}
+template <bool LUT>
+__device__ __forceinline__ float4 pack1_at(const SrmDev& P, float p, float& m) {
+  const float x = srm_clamp(P, p, m);
+  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
+  if (LUT && e < P.lut_n) return __ldg(P.lut1 + e);
+  float v[2], d[2], d2[2];
+  srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
+  return make_float4(v[0], __fmul_rn(v[0], v[1]), d[0], __fmaf_rn(d[0], v[1], __fmul_rn(v[0], d[1])));
+}
+
+struct R2Args {
+  const float* p0; const float* p1; const float* dt1; const float* dt2; const int32_t* sample_real;
+  const float* faces;
+  const float* qw; float* divqw; float* dom; float* dom_out; double* sse; double* mb_sum;
+  const float* dterms; const float* mbc; const float* dqdp; float* gp0; float* gp1; double* gdt1_acc; double* gdt2_acc;
+  int32_t B, R, tiles_x;
+};
+
+// tile bookkeeping shared by both kernels
+struct Tile {
+  int tx, ty, x0, y0;
+  bool valid, halo;
+  int oc;      // own column offset inside a plane (coordinates clamped to the grid)
+  int oh;      // halo cell offset inside a plane (clamped = edge replication)
+  int hx, hy;  // halo slot in the shared plane
+};
+__device__ __forceinline__ Tile make_tile(const SrmDev& P, int tiles_x) {
+  Tile t;
+  const int tid = threadIdx.x;
+  t.tx = tid & 31; t.ty = tid >> 5;
+  const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
+  t.x0 = txi * TX; t.y0 = tyi * TY;
+  const int x = t.x0 + t.tx, y = t.y0 + t.ty;
+  t.valid = x < P.W && y < P.H;
+  t.oc = min(y, P.H - 1) * P.W + min(x, P.W - 1);
+  int gx = 0, gy = 0;
+  t.hx = 0; t.hy = 0;
+  if (tid < TX) { t.hy = 0; t.hx = tid + 1; gy = t.y0 - 1; gx = t.x0 + tid; }
+  else if (tid < 2 * TX) { t.hy = TY + 1; t.hx = tid - TX + 1; gy = t.y0 + TY; gx = t.x0 + tid - TX; }
+  else if (tid < 2 * TX + TY) { t.hx = 0; t.hy = tid - 2 * TX + 1; gx = t.x0 - 1; gy = t.y0 + tid - 2 * TX; }
+  else if (tid < NHALO) { t.hx = TX + 1; t.hy = tid - 2 * TX - TY + 1; gx = t.x0 + TX; gy = t.y0 + tid - 2 * TX - TY; }
+  t.halo = tid < NHALO;
+  gx = min(max(gx, 0), P.W - 1);
+  gy = min(max(gy, 0), P.H - 1);
+  t.oh = gy * P.W + gx;
+  return t;
+}
+
+// marks the threads whose (x,y) column holds a well connection (any layer)
+__device__ __forceinline__ bool column_has_well(const SrmDev& P, const Tile& t, unsigned char* s_flag) {
+  s_flag[threadIdx.x] = 0;
+  __syncthreads();
+  const int HW = P.H * P.W;
+  for (int w = threadIdx.x; w < P.n_wells; w += NT) {
+    const int rem = P.wells[w].cell % HW;
+    const int j = rem / P.W, i = rem - j * P.W;
+    if (i >= t.x0 && i < t.x0 + TX && j >= t.y0 && j < t.y0 + TY) s_flag[(j - t.y0) * TX + (i - t.x0)] = 1;
+  }
+  __syncthreads();
+  return s_flag[threadIdx.x] != 0 && t.valid;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <bool LUT>
+__global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
+  __shared__ float s_p[2][SH][SW];
+  __shared__ float s_G[2][SH][SW];
+  __shared__ double red[4 * 32];
+  __shared__ unsigned char s_flag[NT];
+  const Tile t = make_tile(P, A.tiles_x);
+  const int b = blockIdx.y;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const bool has_well = (P.n_wells > 0) ? column_has_well(P, t, s_flag) : false;
+  const int W = P.W, H = P.H, D = P.D, HW = H * W;
+  const FaceLay FL = face_layout(D, H, W);
+  const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
+  const float* __restrict__ p1f = A.p1 + (int64_t)b * P.N;
+  const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FN = FE + FL.nE;
+  const float* __restrict__ FU = FN + FL.nN;
+  const int yy = t.oc / W, xx = t.oc - yy * W;          // clamped coordinates
+  const int oE = yy * (W + 1) + xx;                     // FE row offset inside a plane of H*(W+1)
+  const int oN = yy * W + xx;                           // FN offset inside a plane of (H+1)*W
+  // per-sample scalars                                   physics_loss.py:126,156,171,193
+  const float d1 = A.dt1[b], d2 = A.dt2[b];
+  const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
+  const float one_rho = __fadd_rn(1.0f, rho);
+  const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const float c2e7 = __fdiv_rn(2e-7f, d1);
+  const float d12 = __fadd_rn(d1, d2);
+  const float mbfac = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
+
+  float m;
+  // plane 0 (own + halo), then the march
+  float pc = p1f[t.oc];
+  float4 e1 = pack1_at<LUT>(P, pc, m);
+  float Gc = e1.y, A1c = e1.x;
+  float pm = pc, Gm = Gc;
+  float hp = 0.f, hG = 0.f;
+  if (t.halo) { hp = p1f[t.oh]; hG = pack1_at<LUT>(P, hp, m).y; }
+  float fD = FU[t.oc];                                  // face below plane 0 (image)
+  float a_dom = 0.f, a_tde = 0.f;                       // per-thread partial sums (<= D terms each)
+  double a_ibc = 0.0, a_mb = 0.0;
+  for (int k = 0; k < D; ++k) {
+    const int buf = k & 1;
+    s_p[buf][t.ty + 1][t.tx + 1] = pc;
+    s_G[buf][t.ty + 1][t.tx + 1] = Gc;
+    if (t.halo) { s_p[buf][t.hy][t.hx] = hp; s_G[buf][t.hy][t.hx] = hG; }
+    // prefetch plane k+1
+    float pn = pc, Gn = Gc, A1n = A1c, hpn = hp;
+    const bool more = k + 1 < D;
+    if (more) {
+      pn = p1f[(int64_t)(k + 1) * HW + t.oc];
+      if (t.halo) hpn = p1f[(int64_t)(k + 1) * HW + t.oh];
+    }
+    const float p0 = p0f[(int64_t)k * HW + t.oc];
+    const float fW = FE[(int64_t)k * H * (W + 1) + oE], fE = FE[(int64_t)k * H * (W + 1) + oE + 1];
+    const float fS = FN[(int64_t)k * (H + 1) * W + oN], fN = FN[(int64_t)k * (H + 1) * W + oN + W];
+    const float fU = FU[(int64_t)(k + 1) * HW + t.oc];
+    float m0;
+    const float4 e0 = pack0_at<LUT>(P, p0, m0);
+    float hGn = hG;
+    if (more) {
+      const float4 en = pack1_at<LUT>(P, pn, m);
+      Gn = en.y; A1n = en.x;
+      if (t.halo) hGn = pack1_at<LUT>(P, hpn, m).y;
+    }
+    __syncthreads();
+    const float pW = s_p[buf][t.ty + 1][t.tx], pE = s_p[buf][t.ty + 1][t.tx + 2];
+    const float pS = s_p[buf][t.ty][t.tx + 1], pN = s_p[buf][t.ty + 2][t.tx + 1];
+    const float gW = s_G[buf][t.ty + 1][t.tx], gE = s_G[buf][t.ty + 1][t.tx + 2];
+    const float gS = s_G[buf][t.ty][t.tx + 1], gN = s_G[buf][t.ty + 2][t.tx + 1];
+    const float p1 = pc, G = Gc;
+    const float GW = __fmul_rn(__fadd_rn(G, gW), 0.5f), GE = __fmul_rn(__fadd_rn(gE, G), 0.5f);
+    const float GS = __fmul_rn(__fadd_rn(G, gS), 0.5f), GN = __fmul_rn(__fadd_rn(gN, G), 0.5f);
+    const float GD = __fmul_rn(__fadd_rn(G, Gm), 0.5f), GU = __fmul_rn(__fadd_rn(Gn, G), 0.5f);
+    // C*k_f*krg*G_f*(1/dl)*(1/dl)                       physics_loss.py:152-155
+    const float a1 = __fmul_rn(__fmul_rn(__fmul_rn(fW, GW), P.idx), P.idx);
+    const float a2 = __fmul_rn(__fmul_rn(__fmul_rn(fS, GS), P.idy), P.idy);
+    const float a3 = __fmul_rn(__fmul_rn(__fmul_rn(fE, GE), P.idx), P.idx);
+    const float a4 = __fmul_rn(__fmul_rn(__fmul_rn(fN, GN), P.idy), P.idy);
+    const float a5 = __fmul_rn(__fmul_rn(__fmul_rn(fD, GD), P.idz), P.idz);
+    const float a6 = __fmul_rn(__fmul_rn(__fmul_rn(fU, GU), P.idz), P.idz);
+    // accumulation coefficient                           physics_loss.py:149-150,156
+    const float A0 = e0.x, A0p = e0.y, A1 = A1c;
+    const float cr = __fmul_rn(P.phicf, A0);
+    const float cp = __fmul_rn(P.Sgi, __fadd_rn(__fmul_rn(P.phi, A0p), cr));
+    const float a5t = __fmul_rn(P.invDc, __fdiv_rn(cp, d1));
+    // wells in this cell (scatter_nd sums duplicates)    well_rate_bhp_Subclassed.py:128-132
+    float q = 0.f, mask = 0.f;
+    const int c = k * HW + t.oc;
+    int wfirst = 0;
+    if (has_well) {
+      wfirst = well_lower_bound(P, c);
+      for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) {
+        q = __fadd_rn(q, A.qw[(int64_t)b * P.n_wells + w]);
+        mask += 1.f;
+      }
+    }
+    // p2 by linear extrapolation, truncation term        physics_loss.py:126,171
+    const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), one_rho), p0);
+    const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(d12, p1));
+    const float E = __fadd_rn(c2e7, __fdiv_rn(numr, den));
+    const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
+    // flux divergence                                    physics_loss.py:174
+    float s = __fadd_rn(-__fmul_rn(a1, pW), -__fmul_rn(a2, pS));
+    const float asum = __fadd_rn(__fadd_rn(__fadd_rn(a1, a2), a3), a4);
+    s = __fadd_rn(s, __fmul_rn(asum, p1));
+    s = __fadd_rn(s, -__fmul_rn(a3, pE));
+    s = __fadd_rn(s, -__fmul_rn(a4, pN));
+    const float zt = __fadd_rn(__fmul_rn(a5, __fsub_rn(p1, pm)), __fmul_rn(a6, __fsub_rn(p1, pn)));   // 3-D extension
+    s = __fadd_rn(s, zt);
+    s = __fadd_rn(s, (mask != 0.f) ? __fdiv_rn(q, P.dv) : 0.f);
+    const float divq = __fmul_rn(P.dv, s);
+    const float acc = __fmul_rn(__fmul_rn(P.dv, a5t), __fsub_rn(p1, p0));       // physics_loss.py:175
+    const float dom = P.tde_in_dom ? __fadd_rn(divq, __fadd_rn(acc, tde)) : __fadd_rn(divq, acc);
+    const float mb = __fmul_rn(__fmul_rn(P.dvSgi_phi, __fsub_rn(A1, A0)), mbfac);   // physics_loss.py:193
+    if (t.valid) {
+      A.dom[(int64_t)b * P.N + c] = dom;
+      if (A.dom_out) A.dom_out[(int64_t)b * P.N + c] = dom;
+      if (mask != 0.f) {
+        for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq;
+        const float ibc = __fmul_rn(mask, divq);                                // physics_loss.py:189
+        a_ibc += (double)ibc * (double)ibc;
+      }
+      a_dom = fmaf(dom, dom, a_dom);
+      a_tde = fmaf(tde, tde, a_tde);
+      a_mb += (double)mb;
+    }
+    pm = pc; pc = pn; Gm = Gc; Gc = Gn; A1c = A1n; hp = hpn; hG = hGn; fD = fU;
+  }
+  double acc4[4] = {(double)a_dom, a_ibc, (double)a_tde, a_mb};
+  __syncthreads();
+  block_reduce<4>(acc4, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&A.sse[SRM_TERM_DOM], acc4[0]);
+    if (acc4[1] != 0.0) atomicAdd(&A.sse[SRM_TERM_IBC], acc4[1]);
+    atomicAdd(&A.sse[SRM_TERM_TDE], acc4[2]);
+    atomicAdd(&A.mb_sum[b], acc4[3]);
+  }
+}
+
+// sum of every sample's well rates (fp64)                 physics_loss.py:193
+__global__ void __launch_bounds__(128) k_qsum_ref2(int32_t B, int32_t nw, const float* __restrict__ qw, double* __restrict__ q_sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  double s = 0.0;
+  for (int w = lane; w < nw; w += 32) s += (double)qw[(int64_t)warp * nw + w];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) q_sum[warp] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------
+template <bool LUT>
+__global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
+  __shared__ float s_p[2][SH][SW];
+  __shared__ float s_G[2][SH][SW];
+  __shared__ float s_s[2][SH][SW];
+  __shared__ double red[2 * 32];
+  __shared__ unsigned char s_flag[NT];
+  const Tile t = make_tile(P, A.tiles_x);
+  const int b = blockIdx.y;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const bool has_well = (P.n_wells > 0) ? column_has_well(P, t, s_flag) : false;
+  const int W = P.W, H = P.H, D = P.D, HW = H * W;
+  const FaceLay FL = face_layout(D, H, W);
+  const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
+  const float* __restrict__ p1f = A.p1 + (int64_t)b * P.N;
+  const float* __restrict__ domf = A.dom + (int64_t)b * P.N;
+  const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FN = FE + FL.nE;
+  const float* __restrict__ FU = FN + FL.nN;
+  const int yy = t.oc / W, xx = t.oc - yy * W;
+  const int oE = yy * (W + 1) + xx, oN = yy * W + xx;
+  const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_tde = A.dterms[SRM_TERM_TDE];
+  const float d1 = A.dt1[b], d2 = A.dt2[b];
+  const float two_wd = 2.f * w_dom;
+  const float smb = 2.f * w_mbc * A.mbc[b];              // dL/d mbc_b
+  // forward's per-sample scalars (op order as the forward: E is dominated by the rounding of N)
+  const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
+  const float one_rho = __fadd_rn(1.0f, rho);
+  const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const float c2e7 = __fdiv_rn(2e-7f, d1);
+  const float d12 = __fadd_rn(d1, d2);
+  const float id1 = 1.0f / d1, iden2 = 1.0f / (den * den);
+  const float mbk = P.dvSgi_phi / (P.Dc * d1);          // d mb_cells / d(A1-A0)
+  const float hx2 = 0.5f * P.idx * P.idx, hy2 = 0.5f * P.idy * P.idy, hz2 = 0.5f * P.idz * P.idz;
+  const float dE1c = -2e-7f * id1 * id1;
+
+  float m1c, m;
+  float pc = p1f[t.oc];
+  float4 e1 = pack1_at<LUT>(P, pc, m1c);
+  float sc = two_wd * domf[t.oc];
+  float pm = pc, Gm = e1.y, sm = sc;
+  float hp = 0.f, hG = 0.f, hs = 0.f;
+  if (t.halo) { hp = p1f[t.oh]; hG = pack1_at<LUT>(P, hp, m).y; hs = two_wd * domf[t.oh]; }
+  float fD = FU[t.oc];
+  double a_g1 = 0.0, a_g2 = 0.0;
+  for (int k = 0; k < D; ++k) {
+    const int buf = k & 1;
+    s_p[buf][t.ty + 1][t.tx + 1] = pc;
+    s_G[buf][t.ty + 1][t.tx + 1] = e1.y;
+    s_s[buf][t.ty + 1][t.tx + 1] = sc;
+    if (t.halo) { s_p[buf][t.hy][t.hx] = hp; s_G[buf][t.hy][t.hx] = hG; s_s[buf][t.hy][t.hx] = hs; }
+    float pn = pc, sn = sc, hpn = hp, hsn = hs, hGn = hG, m1n = m1c;
+    float4 en = e1;
+    const bool more = k + 1 < D;
+    if (more) {
+      pn = p1f[(int64_t)(k + 1) * HW + t.oc];
+      sn = two_wd * domf[(int64_t)(k + 1) * HW + t.oc];
+      if (t.halo) { hpn = p1f[(int64_t)(k + 1) * HW + t.oh]; hsn = two_wd * domf[(int64_t)(k + 1) * HW + t.oh]; }
+    }
+    const float p0 = p0f[(int64_t)k * HW + t.oc];
+    const float fW = FE[(int64_t)k * H * (W + 1) + oE], fE = FE[(int64_t)k * H * (W + 1) + oE + 1];
+    const float fS = FN[(int64_t)k * (H + 1) * W + oN], fN = FN[(int64_t)k * (H + 1) * W + oN + W];
+    const float fU = FU[(int64_t)(k + 1) * HW + t.oc];
+    float m0;
+    const float4 e0 = pack0_at<LUT>(P, p0, m0);
+    if (more) {
+      en = pack1_at<LUT>(P, pn, m1n);
+      if (t.halo) hGn = pack1_at<LUT>(P, hpn, m).y;
+    }
+    __syncthreads();
+    const float p1 = pc, G = e1.y, Gp = e1.w * m1c, A1 = e1.x, A1p = e1.z * m1c;
+    // stencil gather: dv * sum_f (s_c - s_n) * T_f/2 * [(G_c + G_n) + G'_c (p_c - p_n)]; image faces: s_n == s_c
+    float g1 = 0.f;
+    {
+      const float pW = s_p[buf][t.ty + 1][t.tx], gW = s_G[buf][t.ty + 1][t.tx], sW = s_s[buf][t.ty + 1][t.tx];
+      g1 = fmaf((sc - sW) * (fW * hx2), (G + gW) + Gp * (p1 - pW), g1);
+      const float pE = s_p[buf][t.ty + 1][t.tx + 2], gE = s_G[buf][t.ty + 1][t.tx + 2], sE = s_s[buf][t.ty + 1][t.tx + 2];
+      g1 = fmaf((sc - sE) * (fE * hx2), (G + gE) + Gp * (p1 - pE), g1);
+      const float pS = s_p[buf][t.ty][t.tx + 1], gS = s_G[buf][t.ty][t.tx + 1], sS = s_s[buf][t.ty][t.tx + 1];
+      g1 = fmaf((sc - sS) * (fS * hy2), (G + gS) + Gp * (p1 - pS), g1);
+      const float pN = s_p[buf][t.ty + 2][t.tx + 1], gN = s_G[buf][t.ty + 2][t.tx + 1], sN = s_s[buf][t.ty + 2][t.tx + 1];
+      g1 = fmaf((sc - sN) * (fN * hy2), (G + gN) + Gp * (p1 - pN), g1);
+      g1 = fmaf((sc - sm) * (fD * hz2), (G + Gm) + Gp * (p1 - pm), g1);
+      g1 = fmaf((sc - sn) * (fU * hz2), (G + en.y) + Gp * (p1 - pn), g1);
+    }
+    g1 *= P.dv;
+    // local terms
+    const float A0 = e0.x, A0p = e0.y, A0pp = e0.z * m0;
+    const float cp = P.Sgi * (P.phi * A0p + P.phicf * A0);
+    const float cpp = P.Sgi * (P.phi * A0pp + P.phicf * A0p * m0);   // d cp / d p0
+    const float a5t = P.invDc * (cp * id1);
+    const float dp = p1 - p0;
+    const float acc = P.dv * a5t * dp;
+    const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), one_rho), p0);
+    const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(d12, p1));
+    const float E = __fadd_rn(c2e7, __fdiv_rn(numr, den));
+    const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
+    const float st = (P.tde_in_dom ? sc : 0.f) + 2.f * w_tde * tde;   // dL/d tde
+    float dq = 0.f;
+    const int c = k * HW + t.oc;
+    if (has_well) {
+      const int first = well_lower_bound(P, c);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) dq += A.dqdp[(int64_t)b * P.n_wells + w];
+    }
+    g1 += sc * (dq + P.dv * a5t) + smb * (-dq - mbk * A1p);
+    const float g0 = sc * (-P.dv * a5t + P.dv * dp * P.invDc * id1 * cpp) + st * P.dvDc * cpp * E + smb * (mbk * A0p * m0);
+    if (t.valid) {
+      A.gp0[(int64_t)b * P.N + c] = g0;
+      A.gp1[(int64_t)b * P.N + c] = g1;
+      // d/d dt1, d/d dt2 (the dN/d* pieces vanish identically; N itself is rounding noise)
+      const float dE1 = dE1c - numr * d2 * iden2;
+      const float dE2 = -numr * (d1 + 2.f * d2) * iden2;
+      const float mb = mbk * (A1 - A0);
+      a_g1 += (double)(sc * (-acc * id1) + st * P.dvDc * cp * dE1 + smb * (mb * id1));
+      a_g2 += (double)(st * P.dvDc * cp * dE2);
+    }
+    pm = pc; pc = pn; Gm = e1.y; e1 = en; m1c = m1n; sm = sc; sc = sn; hp = hpn; hG = hGn; hs = hsn; fD = fU;
+  }
+  double acc2[2] = {a_g1, a_g2};
+  __syncthreads();
+  block_reduce<2>(acc2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&A.gdt1_acc[b], acc2[0]);
+    atomicAdd(&A.gdt2_acc[b], acc2[1]);
+  }
+}
+
+// inner-boundary term: L_ibc = w_ibc * sum (mask*divq)^2 ; scatter d divq_c / d p1 to the cell and
+// its six neighbours (atomics: adjacent well cells may hit the same target).
+template <bool LUT>
+__global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = P.n_wells;
+  if (g >= (int64_t)A.B * nw) return;
+  const int b = (int)(g / nw), w = (int)(g % nw);
+  const int c = P.wells[w].cell;
+  if (w > 0 && P.wells[w - 1].cell == c) return;   // one thread per distinct cell
+  float mask = 0.f, dq = 0.f;
+  for (int u = w; u < nw && P.wells[u].cell == c; ++u) { mask += 1.f; dq += A.dqdp[(int64_t)b * nw + u]; }
+  const float s = 2.f * A.dterms[SRM_TERM_IBC] * mask * mask * A.divqw[g];
+  if (s == 0.f) return;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int W = P.W, H = P.H, D = P.D, HW = H * W;
+  const FaceLay FL = face_layout(D, H, W);
+  const float* FE = A.faces + (int64_t)r * FL.per_real;
+  const float* FN = FE + FL.nE;
+  const float* FU = FN + FL.nN;
+  const float* p1f = A.p1 + (int64_t)b * P.N;
+  float* gp1 = A.gp1 + (int64_t)b * P.N;
+  const int i = c % W, j = (c / W) % H, k = c / HW;
+  float m1, mn;
+  const float p1 = p1f[c];
+  const float4 e1 = pack1_at<LUT>(P, p1, m1);
+  const float G = e1.y, Gp = e1.w * m1;
+  float self = 0.f;
+  auto face = [&](bool inside, int cn, float f, float h2) {
+    if (!inside) return;
+    const float pn = p1f[cn];
+    const float4 en = pack1_at<LUT>(P, pn, mn);
+    const float Tf = f * h2 * 2.f;
+    const float af = Tf * 0.5f * (G + en.y);
+    self += af + 0.5f * Tf * Gp * (p1 - pn);
+    atomicAdd(&gp1[cn], s * P.dv * (-af + 0.5f * Tf * (en.w * mn) * (p1 - pn)));
+  };
+  const float hx2 = 0.5f * P.idx * P.idx, hy2 = 0.5f * P.idy * P.idy, hz2 = 0.5f * P.idz * P.idz;
+  face(i > 0, c - 1, FE[((int64_t)k * H + j) * (W + 1) + i], hx2);
+  face(i < W - 1, c + 1, FE[((int64_t)k * H + j) * (W + 1) + i + 1], hx2);
+  face(j > 0, c - W, FN[((int64_t)k * (H + 1) + j) * W + i], hy2);
+  face(j < H - 1, c + W, FN[((int64_t)k * (H + 1) + j + 1) * W + i], hy2);
+  face(k > 0, c - HW, FU[(int64_t)k * HW + j * W + i], hz2);
+  face(k < D - 1, c + HW, FU[(int64_t)(k + 1) * HW + j * W + i], hz2);
+  atomicAdd(&gp1[c], s * (P.dv * self + dq));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+size_t srm_ref2_face_floats(const SrmDev& P) { return (size_t)face_layout(P.D, P.H, P.W).per_real; }
+
+static R2Args make_args(const SrmDev& P, int32_t B, int32_t R, const int32_t* sample_real, const float* p0,
+                        const float* p1, const float* dt1, const float* dt2, const SrmWs& ws) {
+  R2Args A;
+  memset(&A, 0, sizeof(A));
+  A.p0 = p0; A.p1 = p1; A.dt1 = dt1; A.dt2 = dt2; A.sample_real = sample_real;
+  A.faces = ws.faces;
+  A.qw = ws.qw; A.divqw = ws.divqw; A.dom = ws.dom; A.sse = ws.sse; A.mb_sum = ws.mb_sum;
+  A.mbc = ws.mbc; A.dqdp = ws.dqdp; A.gdt1_acc = ws.gdt1_acc; A.gdt2_acc = ws.gdt2_acc;
+  A.B = B; A.R = R; A.tiles_x = (P.W + TX - 1) / TX;
+  return A;
+}
+
+int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
+  const FaceLay FL = face_layout(P.D, P.H, P.W);
+  k_faces_ref<<<dim3((unsigned)((FL.per_real + 255) / 256), (unsigned)R), 256, 0, s>>>(P, kx, ws.faces);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  int rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p1, t1, ws.qw, ws.pwfw, ws.dqdp, s);
+  if (rc) return rc;
+  if (P.n_wells > 0) {
+    k_qsum_ref2<<<(unsigned)((B * 32 + 127) / 128), 128, 0, s>>>(B, P.n_wells, ws.qw, ws.q_sum);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
+  A.dom_out = dom_out;
+  const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
+  k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  k_finalize_fwd<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.mbc, terms_out);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                      const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                      const SrmWs& ws, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  (void)kx; (void)t1;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
+  R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
+  A.dterms = dterms; A.gp0 = gp0; A.gp1 = gp1;
+  const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
+  k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  const int64_t n = (int64_t)B * P.n_wells;
+  if (n > 0) {
+    k_ibc_adj_ref2<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

@@ -39,6 +39,10 @@ struct SrmDev {
   float c2[SRM_MAXK];            // fl(c*c)
   float w[SRM_MAXP][SRM_MAXK];
   float v[SRM_MAXP][2];
+  // exact PVT tabulation (SrmConfig.pvt_lut); lut_n == 0: off
+  const float4* lut0;    // [lut_n] {invBg, d/dp, d2/dp2, -} at the fp32 value with bits lut_lo_bits + e
+  const float4* lut1;    // [lut_n] {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
+  uint32_t lut_lo_bits, lut_n;
 };
 
 // Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory
@@ -65,6 +69,7 @@ struct SrmHandle {
   SrmDev dev;          // device parameter block
   WellDev* d_wells;    // device
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
+  float4* d_lut;       // device (exact PVT tabulation), may be null
   int device;
   int sm_count;
   // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD)
@@ -91,6 +96,7 @@ struct SrmWs {
   int32_t* grp_list;  // [B]   sample ids, grouped by realisation, ascending within a group
   int32_t* seg;       // [3*(B+1)] (r, offset into grp_list, count)
   int32_t* ctl;       // [8]   ctl[0] = number of segments, ctl[1..2] = work counters
+  float* faces;       // fused reference path: static face coefficients [R][face floats]
   float* dom;         // field [B*N]
   float* A0;          // reference-order fields [B*N]
   float* A0p;
@@ -104,7 +110,16 @@ struct SrmWs {
 
 static inline size_t srm_align(size_t x) { return (x + 255) & ~size_t(255); }
 
-static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool closed_form) {
+// workspace flavours: staged reference order (7 PVT fields), fused reference order (tabulated PVT), closed form
+enum { SRM_WS_REF_STAGED = 0, SRM_WS_REF_FUSED = 1, SRM_WS_CF = 2 };
+size_t srm_ref2_face_floats(const SrmDev& P);
+static inline int srm_ws_mode(const SrmHandle* h) {
+  if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM) return SRM_WS_CF;
+  return h->dev.lut_n > 0 ? SRM_WS_REF_FUSED : SRM_WS_REF_STAGED;
+}
+
+static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64_t nw, int mode, size_t face_floats) {
+  const bool closed_form = mode == SRM_WS_CF;
   SrmWs w;
   char* p = (char*)base;
   size_t off = 0;
@@ -129,9 +144,11 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t N, int64_t nw, bool
     w.ctl = (int32_t*)take(8 * sizeof(int32_t));
   }
   size_t fb = (size_t)(B * N) * sizeof(float);
+  w.faces = nullptr;
+  if (mode == SRM_WS_REF_FUSED) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
   w.dom = (float*)take(fb);
   w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
-  if (!closed_form) {
+  if (mode == SRM_WS_REF_STAGED) {
     w.A0 = (float*)take(fb);
     w.A0p = (float*)take(fb);
     w.A1 = (float*)take(fb);
@@ -160,6 +177,14 @@ int srm_launch_pvt_eval_ref(const SrmHandle* h, int64_t n, const float* p, float
 int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const int32_t* sample_real, int32_t R,
                          const float* p, const float* t_days, float* qw_sorted, float* pwfw_sorted,
                          float* dqdp_sorted, cudaStream_t s);
+int srm_build_pvt_lut(SrmHandle* h, float lo, float hi);
+int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s);
+int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
+                      const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
+                      const SrmWs& ws, cudaStream_t s);
 int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                     float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s);

@@ -24,7 +24,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class SrmPhysics:
-    def __init__(self, spec: PhysicsSpec, tables: SplineTables, device: int = 0, numerics: str = "reference"):
+    def __init__(self, spec: PhysicsSpec, tables: SplineTables, device: int = 0, numerics: str = "reference",
+                 pvt_lut: bool = False, lut_range=None):
+        """pvt_lut: tabulate the reference-order PVT spline for every fp32 pressure of lut_range
+        (default: the whole clamp range, 2.5 GB) at create; bit-identical results (srm_physics.h)."""
         if not torch.cuda.is_available():
             raise RuntimeError("SrmPhysics needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = L.load_library()
@@ -40,14 +43,15 @@ class SrmPhysics:
             knots=tables.knots, spline_w=tables.w, spline_v=tables.v, spline_order=tables.order,
             p_min=spec.p_min, p_max=spec.p_max, wells=[w.as_dict() for w in spec.wells],
             use_blocking_factor=spec.use_blocking_factor, n_intervals=spec.n_intervals,
-            numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom)
+            numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range)
+        self.pvt_lut = bool(pvt_lut) and numerics == "reference"
         h = C.c_void_p()
         L.check(self.lib, self.lib.srm_create(C.byref(cfg), C.byref(h)), "srm_create")
         self._h = h
         self.n_wells = len(spec.wells)
         self.n_props = tables.w.shape[0]
         self._ws = None
-        self._ws_B = -1
+        self._ws_B = None
         self.launches = 0       # kernels launched through this handle (bench's gpu_launches claim)
 
     def close(self):
@@ -71,11 +75,11 @@ class SrmPhysics:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def workspace(self, B: int) -> torch.Tensor:
-        if self._ws is None or self._ws_B != B:
-            n = self.lib.srm_workspace_bytes(self._h, B, L.SRM_FLAG_SAVE_FOR_BACKWARD)
+    def workspace(self, B: int, R: int) -> torch.Tensor:
+        if self._ws is None or self._ws_B != (B, R):
+            n = self.lib.srm_workspace_bytes(self._h, B, R, L.SRM_FLAG_SAVE_FOR_BACKWARD)
             self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
-            self._ws_B = B
+            self._ws_B = (B, R)
         return self._ws
 
     # ---------------------------------------------------------------------------------------
@@ -125,7 +129,7 @@ class SrmPhysics:
             self._check(sample_real, "sample_real", torch.int32)
         if p0.numel() != B * self.spec.n_cells or p1.shape != p0.shape or kx.numel() != R * self.spec.n_cells:
             raise ValueError("field shapes do not match the handle's grid")
-        ws = self.workspace(B)
+        ws = self.workspace(B, R)
         terms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32, device=self.device)
         dom = torch.empty_like(p0) if want_dom else None
         qw = torch.empty((B, max(self.n_wells, 1)), dtype=torch.float32, device=self.device) if want_wells else None
@@ -141,7 +145,7 @@ class SrmPhysics:
         B = p0.shape[0]
         R = kx.shape[0]
         self._check(dterms, "dterms")
-        ws = self.workspace(B)
+        ws = self.workspace(B, R)
         gp0 = torch.empty_like(p0)
         gp1 = torch.empty_like(p1)
         gdt1 = torch.empty_like(dt1)

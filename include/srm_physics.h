@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SRM_ABI_VERSION 1
+#define SRM_ABI_VERSION 2
 
 typedef enum SrmStatus {
   SRM_OK = 0,
@@ -106,6 +106,16 @@ typedef struct SrmConfig {
   /* behaviour */
   int32_t numerics;      /* SRM_NUMERICS_* */
   int32_t tde_in_dom;    /* 1: legacy DG folds the truncation term into dom (physics_loss.py:175) */
+  /* Exact PVT tabulation (SRM_NUMERICS_REFERENCE only).  The reference re-evaluates the 37-term
+   * spline (polyhm_splines.py:138-146) and its tape derivatives (PVT_Layer_Subclassed.py:196-201) for
+   * every cell of every call, although they are a pure function of ONE clamped fp32 pressure.
+   * pvt_lut = 1 evaluates that function once, at create, for EVERY fp32 value of
+   * [lut_p_lo, lut_p_hi] (32 bytes per value; lo >= hi means the whole clamp range [p_min, p_max],
+   * 78.7 M values = 2.5 GB for [14.7, 10000]) with the same reference-order code, and the kernels
+   * index the table by the pressure's bit pattern.  Results are bit-identical to pvt_lut = 0;
+   * pressures outside the tabulated range are evaluated directly. */
+  int32_t pvt_lut;
+  float lut_p_lo, lut_p_hi;
 } SrmConfig;
 
 typedef struct SrmHandle SrmHandle;
@@ -121,8 +131,8 @@ const char* srm_last_error(void);
 int srm_create(const SrmConfig* cfg, SrmHandle** out);
 void srm_destroy(SrmHandle* h);
 
-/* Scratch needed by srm_forward/srm_backward for B samples (bytes). */
-size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t flags);
+/* Scratch needed by srm_forward/srm_backward for B samples of R realisations (bytes). */
+size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t R, int32_t flags);
 
 /* PVTLayer.call (PVT_Layer_Subclassed.py:146-216) + PolyharmonicSplineInterpolationLayer.call
  * (polyhm_splines.py:152-196): clamp, value and d/dp of every property at n pressures.

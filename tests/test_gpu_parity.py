@@ -32,16 +32,20 @@ def h3_close(a, b, rtol=RTOL):
     return np.all(np.abs(a - b) <= rtol * np.abs(b) + rtol * np.abs(b).max())
 
 
-def golden_engine(spec, g, numerics="reference"):
+def golden_engine(spec, g, numerics="reference", pvt_lut=False):
     """handle built from the golden (w, v) so the box's LAPACK does not enter"""
     tabs = srm.pvt.SplineTables(knots=g["knots"], w=g["w"], v=g["v"], order=1, properties=srm.pvt.DG_PROPERTIES)
-    return srm.SrmPhysics(spec, tabs, device=0, numerics=numerics)
+    return srm.SrmPhysics(spec, tabs, device=0, numerics=numerics, pvt_lut=pvt_lut)
+
+
+# pvt_lut=False: staged kernels (37-term spline per cell); pvt_lut=True: exact table + fused kernels
+LUT_MODES = [False, True]
 
 
 def test_library_is_the_in_tree_cuda_build():
     lib = srm._lib.load_library()
     assert os.path.samefile(srm._lib.LIB_PATH, os.path.join(U.ROOT, "3d-physics-based-ai-surrogate-reservoir-model_b200", "libsrm_physics.so"))
-    assert lib.srm_version() == 1
+    assert lib.srm_version() == srm._lib.SRM_ABI_VERSION
     assert torch.cuda.get_device_capability(0)[0] >= 10, "kernels are built for sm_100a only"
 
 
@@ -68,14 +72,15 @@ def test_pvt_layer_mirror_shape_contract():
     assert np.array_equal(out[1, 1].reshape(-1).cpu().numpy(), g["d1_Invug"][:60])
 
 
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
 @pytest.mark.parametrize("name", ["dg_2d_default", "dg_3d_layers", "dg_3d_blocking"])
-def test_forward_backward_vs_golden(name):
+def test_forward_backward_vs_golden(name, pvt_lut):
     from golden.make_golden import CASES
     g = np.load(os.path.join(U.GOLDEN, name + ".npz"))
     pg = np.load(os.path.join(U.GOLDEN, "pvt_golden.npz"))
     kw = dict(CASES[name])
     ocfg, otab, spec, ptab, batch = U.make_case(**kw)
-    eng = golden_engine(spec, pg)
+    eng = golden_engine(spec, pg, pvt_lut=pvt_lut)
     dev = torch.device("cuda", 0)
     d = {k: torch.from_numpy(g[k]).to(dev) for k in ("kx", "sample_real", "p0", "p1", "dt1", "dt2", "t1")}
     fw = eng.forward(want_dom=True, want_wells=True, **d)
@@ -101,15 +106,17 @@ CASES_LIVE = [
     dict(W=16, H=16, D=4, T=2, K=2, seed=2003, all_layers=True, use_blocking_factor=True),
     dict(W=33, H=7, D=2, T=1, K=1, seed=2004, wells="none"),                            # ragged W, no wells, B=1
     dict(W=5, H=4, D=3, T=2, K=3, seed=2005, wells="lattice"),                          # tiny grid, duplicate-cell wells
+    dict(W=70, H=37, D=5, T=2, K=1, seed=2006, all_layers=True),                        # several tiles, ragged in x and y
 ]
 
 
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
 @pytest.mark.parametrize("kw", CASES_LIVE)
-def test_forward_backward_vs_oracle_live(kw):
+def test_forward_backward_vs_oracle_live(kw, pvt_lut):
     """oracle evaluated on the box on the same seeded inputs"""
     ocfg, otab, spec, ptab, batch = U.make_case(**kw)
     o = U.oracle_run(ocfg, otab, batch)
-    c = U.cuda_run(spec, ptab, batch)
+    c = U.cuda_run(spec, ptab, batch, pvt_lut=pvt_lut)
     assert U.ulp_diff(c["dom"], o["dom"]) == 0
     if ocfg.wells:
         assert U.ulp_diff(c["qw"], o["qw"]) == 0 and U.ulp_diff(c["pwfw"], o["pwfw"]) == 0
@@ -120,7 +127,8 @@ def test_forward_backward_vs_oracle_live(kw):
     assert np.abs(c["gdt2"]).max() <= scale and np.abs(o["gdt2"]).max() <= scale
 
 
-def test_per_term_gradients_match_oracle():
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+def test_per_term_gradients_match_oracle(pvt_lut):
     """the reference differentiates each loss term separately (physics_loss.py:849-859): one-hot dterms.
 
     dom / ibc / mbc gradients are gated on their own scale (H3).  The gradient of the tde term alone is
@@ -133,7 +141,7 @@ def test_per_term_gradients_match_oracle():
         w = [0.0] * 8
         w[slot] = 1.0
         o = U.oracle_run(ocfg, otab, batch, weights=w)
-        c = U.cuda_run(spec, ptab, batch, weights=w)
+        c = U.cuda_run(spec, ptab, batch, weights=w, pvt_lut=pvt_lut, lut_range=(3000.0, 5500.0))
         for k in ("gp0", "gp1", "gdt1"):
             if slot < 3:
                 if np.abs(o[k]).max() == 0:
@@ -207,9 +215,10 @@ def test_sample_realisation_map_and_default_grouping():
     assert torch.equal(c, a[perm])                              # samples are independent units
 
 
-def test_backward_from_saved_state_equals_recompute():
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+def test_backward_from_saved_state_equals_recompute(pvt_lut):
     ocfg, otab, spec, ptab, batch = U.make_case(W=12, H=9, D=3, T=2, K=2, seed=43, all_layers=True)
-    eng = srm.SrmPhysics(spec, ptab)
+    eng = srm.SrmPhysics(spec, ptab, pvt_lut=pvt_lut, lut_range=(4000.0, 5100.0))
     d = U.to_dev(batch, "cuda")
     w = torch.tensor(U.WEIGHTS, device="cuda")
     eng.forward(save_for_backward=True, **d)
@@ -248,3 +257,36 @@ def test_rounding_selftest_matches_ieee_intrinsics():
     for seed in (1, 2):
         srm._lib.check(lib, lib.srm_selftest_rounding(0, 1 << 27, seed, bad, None), "srm_selftest_rounding")
         assert list(bad) == [0, 0, 0], list(bad)
+
+
+@pytest.mark.parametrize("lut_range", [(4500.0, 4800.0), (3000.0, 5200.0)])
+def test_pvt_lut_is_bit_identical_to_direct_evaluation(lut_range):
+    """SrmConfig.pvt_lut tabulates the reference-order spline per fp32 pressure; the forward fields must
+    carry the same bits as the direct evaluation -- inside the tabulated range (table path) and outside
+    it (direct path), in one batch -- and the adjoint must agree to the gradient gate."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=24, H=20, D=3, T=3, K=2, seed=2301, all_layers=True)
+    batch.p0[0, 0, 0, :4] = torch.tensor([10.0, 14.7, 10000.0, 12000.0])     # clamp edges
+    batch.p1[0, 0, 1, :4] = torch.tensor([lut_range[0], lut_range[1], np.nextafter(np.float32(lut_range[0]), np.float32(0)),
+                                          np.nextafter(np.float32(lut_range[1]), np.float32(1e9))])
+    dev = torch.device("cuda", 0)
+    d = U.to_dev(batch, dev)
+    dterms = torch.tensor(U.WEIGHTS, dtype=torch.float32, device=dev)
+    outs = []
+    for lut in (False, True):
+        eng = srm.SrmPhysics(spec, ptab, device=0, numerics="reference", pvt_lut=lut, lut_range=lut_range)
+        fw = eng.forward(want_dom=True, want_wells=True, **d)
+        g = eng.backward(dterms=dterms, **d)
+        torch.cuda.synchronize()
+        outs.append([fw["dom"].cpu().numpy(), fw["qw"].cpu().numpy()] + [t.cpu().numpy() for t in g]
+                    + [fw["terms"].cpu().numpy()])
+        eng.close()
+    names = ("dom", "qw", "gp0", "gp1", "gdt1", "gdt2")
+    for nm, a, b in zip(names, outs[0], outs[1]):
+        if nm in ("dom", "qw"):                                   # forward fields: same bits
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), nm
+        elif nm != "gdt2":                                        # adjoint: same terms, fused kernel associates differently
+            assert h3_close(b, a), nm
+    assert np.allclose(outs[0][-1], outs[1][-1], rtol=1e-6)     # fp64 atomics: order may differ
+    p_all = torch.cat([d["p0"].reshape(-1), d["p1"].reshape(-1)])
+    inside = ((p_all >= lut_range[0]) & (p_all <= lut_range[1])).float().mean().item()
+    assert 0.0 < inside < 1.0, "the case must exercise both the table and the direct path"

@@ -54,9 +54,9 @@ def to_dev(batch, dev):
                 dt2=c(batch.dt2), t1=c(batch.t1))
 
 
-def cuda_run(spec, ptab, batch, weights=WEIGHTS, numerics="reference", want_dom=True):
+def cuda_run(spec, ptab, batch, weights=WEIGHTS, numerics="reference", want_dom=True, pvt_lut=False, lut_range=None):
     dev = torch.device("cuda", 0)
-    eng = srm.SrmPhysics(spec, ptab, device=0, numerics=numerics)
+    eng = srm.SrmPhysics(spec, ptab, device=0, numerics=numerics, pvt_lut=pvt_lut, lut_range=lut_range)
     d = to_dev(batch, dev)
     fw = eng.forward(want_dom=want_dom, want_wells=True, **d)
     dterms = torch.tensor(weights, dtype=torch.float32, device=dev)

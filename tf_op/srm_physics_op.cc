@@ -67,7 +67,7 @@ class SrmPhysicsForwardOp : public OpKernel {
     const int32_t B = p0.dim_size(0), R = kx.dim_size(0);
     Tensor *terms, *ws;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({2, SRM_N_TERMS}), &terms));
-    const int64_t wsb = (int64_t)srm_workspace_bytes(h_, B, SRM_FLAG_SAVE_FOR_BACKWARD);
+    const int64_t wsb = (int64_t)srm_workspace_bytes(h_, B, R, SRM_FLAG_SAVE_FOR_BACKWARD);
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({wsb}), &ws));
     int rc = srm_forward(h_, B, R, kx.flat<float>().data(), sr.flat<int32>().data(), p0.flat<float>().data(),
                          p1.flat<float>().data(), dt1.flat<float>().data(), dt2.flat<float>().data(),
