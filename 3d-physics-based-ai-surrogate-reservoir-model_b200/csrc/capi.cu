@@ -144,6 +144,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     const float hi = whole ? cfg->p_max : std::min(cfg->lut_p_hi, cfg->p_max);
     int rc = srm_build_pvt_lut(h, lo, hi);
     if (rc) { srm_destroy(h); return rc; }
+    h->lut_full = (lo <= cfg->p_min && hi >= cfg->p_max) ? 1 : 0;
   }
   *out = h;
   return SRM_OK;

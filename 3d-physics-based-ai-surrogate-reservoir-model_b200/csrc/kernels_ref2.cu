@@ -80,23 +80,68 @@ __global__ void __launch_bounds__(256) k_faces_ref(const __grid_constant__ SrmDe
 }
 
 // ---- PVT packs through the table (direct evaluation outside the tabulated range) -----------------
-template <bool LUT>
+// FULL: the table covers the whole clamp range [p_min, p_max], so the lookup needs no range test.
+template <bool FULL>
 __device__ __forceinline__ float4 pack0_at(const SrmDev& P, float p, float& m) {
   const float x = srm_clamp(P, p, m);
   const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (LUT && e < P.lut_n) return __ldg(P.lut0 + e);
+  if (FULL || e < P.lut_n) return __ldg(P.lut0 + e);
   float v[1], d[1], d2[1];
   srm_spline_ref<1, true, true>(P, 0, x, v, d, d2);
   return make_float4(v[0], d[0], d2[0], 0.f);
 }
-template <bool LUT>
+template <bool FULL>
 __device__ __forceinline__ float4 pack1_at(const SrmDev& P, float p, float& m) {
   const float x = srm_clamp(P, p, m);
   const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (LUT && e < P.lut_n) return __ldg(P.lut1 + e);
+  if (FULL || e < P.lut_n) return __ldg(P.lut1 + e);
   float v[2], d[2], d2[2];
   srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
   return make_float4(v[0], __fmul_rn(v[0], v[1]), d[0], __fmaf_rn(d[0], v[1], __fmul_rn(v[0], d[1])));
+}
+// value-only variants for the forward (no gradient mask)
+template <bool FULL>
+__device__ __forceinline__ float4 pack0_val(const SrmDev& P, float p) {
+  const float x = fminf(fmaxf(p, P.p_min), P.p_max);    // == srm_clamp (NaN -> p_min as well)
+  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
+  if (FULL || e < P.lut_n) return __ldg(P.lut0 + e);
+  float v[1], d[1], d2[1];
+  srm_spline_ref<1, true, false>(P, 0, x, v, d, d2);
+  return make_float4(v[0], d[0], 0.f, 0.f);
+}
+template <bool FULL>
+__device__ __forceinline__ float2 pack1_val(const SrmDev& P, float p) {
+  const float x = fminf(fmaxf(p, P.p_min), P.p_max);
+  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
+  if (FULL || e < P.lut_n) return __ldg(reinterpret_cast<const float2*>(P.lut1 + e));
+  float v[2], d[2], d2[2];
+  srm_spline_ref<2, false, false>(P, 0, x, v, d, d2);
+  return make_float2(v[0], __fmul_rn(v[0], v[1]));
+}
+
+// ---- correctly rounded division by a per-sample constant -----------------------------------------
+// div.rn's own fast path (q = a*y, two Markstein corrections) with y = RN(1/b) hoisted out of the
+// cell loop.  Valid while b and a are far from the exponent limits; a == 0 returns the signed zero
+// a*y; anything else takes the IEEE intrinsic.  div.rn itself sends a == 0 (the usual value of the
+// truncation bracket, physics_loss.py:171) to its slow path -- a subroutine call per cell otherwise.
+// Checked against div.rn by srm_selftest_rounding (slot 3).
+struct DivC { float b, y; bool ok; };
+__device__ __forceinline__ DivC make_divc(float b) {
+  DivC d;
+  d.b = b;
+  d.y = __frcp_rn(b);
+  const float ab = fabsf(b);
+  d.ok = ab >= 0x1p-60f && ab <= 0x1p60f;
+  return d;
+}
+__device__ __forceinline__ float div_c(float a, const DivC& d) {
+  const float q0 = __fmul_rn(a, d.y);
+  float q = __fmaf_rn(__fmaf_rn(-d.b, q0, a), d.y, q0);
+  q = __fmaf_rn(__fmaf_rn(-d.b, q, a), d.y, q);
+  const float aa = fabsf(a);
+  if (aa == 0.f) q = q0;
+  if (!(d.ok && (aa == 0.f || (aa >= 0x1p-60f && aa <= 0x1p60f)))) q = __fdiv_rn(a, d.b);
+  return q;
 }
 
 struct R2Args {
@@ -151,10 +196,12 @@ __device__ __forceinline__ bool column_has_well(const SrmDev& P, const Tile& t, 
   return s_flag[threadIdx.x] != 0 && t.valid;
 }
 
+template <int V> struct IntC { static constexpr int value = V; };
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <bool LUT>
+template <bool FULL>
 __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
   __shared__ float s_p[2][SH][SW];
   __shared__ float s_G[2][SH][SW];
@@ -168,62 +215,60 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
   const FaceLay FL = face_layout(D, H, W);
   const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
   const float* __restrict__ p1f = A.p1 + (int64_t)b * P.N;
+  float* __restrict__ domf = A.dom + (int64_t)b * P.N;
+  float* __restrict__ domo = A.dom_out ? A.dom_out + (int64_t)b * P.N : nullptr;
   const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   const int yy = t.oc / W, xx = t.oc - yy * W;          // clamped coordinates
-  const int oE = yy * (W + 1) + xx;                     // FE row offset inside a plane of H*(W+1)
-  const int oN = yy * W + xx;                           // FN offset inside a plane of (H+1)*W
+  int offE = yy * (W + 1) + xx;                         // FE offset, plane stride H*(W+1)
+  int offN = yy * W + xx;                               // FN offset, plane stride (H+1)*W
+  const int strE = H * (W + 1), strN = (H + 1) * W;
   // per-sample scalars                                   physics_loss.py:126,156,171,193
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
   const float one_rho = __fadd_rn(1.0f, rho);
-  const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const DivC by_d1 = make_divc(d1);
+  const DivC by_den = make_divc(__fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2)));
   const float c2e7 = __fdiv_rn(2e-7f, d1);
   const float d12 = __fadd_rn(d1, d2);
   const float mbfac = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
 
-  float m;
   // plane 0 (own + halo), then the march
-  float pc = p1f[t.oc];
-  float4 e1 = pack1_at<LUT>(P, pc, m);
+  int off = t.oc;                                       // own cell of the current plane
+  int offh = t.oh;                                      // halo cell of the current plane
+  float pc = p1f[off];
+  const float2 e1 = pack1_val<FULL>(P, pc);
   float Gc = e1.y, A1c = e1.x;
   float pm = pc, Gm = Gc;
   float hp = 0.f, hG = 0.f;
-  if (t.halo) { hp = p1f[t.oh]; hG = pack1_at<LUT>(P, hp, m).y; }
-  float fD = FU[t.oc];                                  // face below plane 0 (image)
+  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL>(P, hp).y; }
+  float fD = FU[off];                                   // face below plane 0 (image)
   float a_dom = 0.f, a_tde = 0.f;                       // per-thread partial sums (<= D terms each)
   double a_ibc = 0.0, a_mb = 0.0;
-  for (int k = 0; k < D; ++k) {
-    const int buf = k & 1;
+
+  auto plane = [&](auto BUF, const int k) {
+    constexpr int buf = decltype(BUF)::value;
     s_p[buf][t.ty + 1][t.tx + 1] = pc;
     s_G[buf][t.ty + 1][t.tx + 1] = Gc;
     if (t.halo) { s_p[buf][t.hy][t.hx] = hp; s_G[buf][t.hy][t.hx] = hG; }
-    // prefetch plane k+1
-    float pn = pc, Gn = Gc, A1n = A1c, hpn = hp;
-    const bool more = k + 1 < D;
-    if (more) {
-      pn = p1f[(int64_t)(k + 1) * HW + t.oc];
-      if (t.halo) hpn = p1f[(int64_t)(k + 1) * HW + t.oh];
-    }
-    const float p0 = p0f[(int64_t)k * HW + t.oc];
-    const float fW = FE[(int64_t)k * H * (W + 1) + oE], fE = FE[(int64_t)k * H * (W + 1) + oE + 1];
-    const float fS = FN[(int64_t)k * (H + 1) * W + oN], fN = FN[(int64_t)k * (H + 1) * W + oN + W];
-    const float fU = FU[(int64_t)(k + 1) * HW + t.oc];
-    float m0;
-    const float4 e0 = pack0_at<LUT>(P, p0, m0);
-    float hGn = hG;
-    if (more) {
-      const float4 en = pack1_at<LUT>(P, pn, m);
-      Gn = en.y; A1n = en.x;
-      if (t.halo) hGn = pack1_at<LUT>(P, hpn, m).y;
-    }
+    // prefetch plane k+1; past the top the march re-reads the last plane (= the edge-replicated image)
+    const int up = (k + 1 < D) ? HW : 0;
+    const float pn = p1f[off + up];
+    if (t.halo) hp = p1f[offh + up];
+    const float p0 = p0f[off];
+    const float fW = FE[offE], fE = FE[offE + 1];
+    const float fS = FN[offN], fN = FN[offN + W];
+    const float fU = FU[off + HW];
+    const float4 e0 = pack0_val<FULL>(P, p0);
+    const float2 en = pack1_val<FULL>(P, pn);
+    if (t.halo) hG = pack1_val<FULL>(P, hp).y;
     __syncthreads();
     const float pW = s_p[buf][t.ty + 1][t.tx], pE = s_p[buf][t.ty + 1][t.tx + 2];
     const float pS = s_p[buf][t.ty][t.tx + 1], pN = s_p[buf][t.ty + 2][t.tx + 1];
     const float gW = s_G[buf][t.ty + 1][t.tx], gE = s_G[buf][t.ty + 1][t.tx + 2];
     const float gS = s_G[buf][t.ty][t.tx + 1], gN = s_G[buf][t.ty + 2][t.tx + 1];
-    const float p1 = pc, G = Gc;
+    const float p1 = pc, G = Gc, Gn = en.y;
     const float GW = __fmul_rn(__fadd_rn(G, gW), 0.5f), GE = __fmul_rn(__fadd_rn(gE, G), 0.5f);
     const float GS = __fmul_rn(__fadd_rn(G, gS), 0.5f), GN = __fmul_rn(__fadd_rn(gN, G), 0.5f);
     const float GD = __fmul_rn(__fadd_rn(G, Gm), 0.5f), GU = __fmul_rn(__fadd_rn(Gn, G), 0.5f);
@@ -238,22 +283,23 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
     const float A0 = e0.x, A0p = e0.y, A1 = A1c;
     const float cr = __fmul_rn(P.phicf, A0);
     const float cp = __fmul_rn(P.Sgi, __fadd_rn(__fmul_rn(P.phi, A0p), cr));
-    const float a5t = __fmul_rn(P.invDc, __fdiv_rn(cp, d1));
+    const float a5t = __fmul_rn(P.invDc, div_c(cp, by_d1));
     // wells in this cell (scatter_nd sums duplicates)    well_rate_bhp_Subclassed.py:128-132
-    float q = 0.f, mask = 0.f;
-    const int c = k * HW + t.oc;
+    float qdv = 0.f, mask = 0.f;
     int wfirst = 0;
     if (has_well) {
-      wfirst = well_lower_bound(P, c);
-      for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) {
+      float q = 0.f;
+      wfirst = well_lower_bound(P, off);
+      for (int w = wfirst; w < P.n_wells && P.wells[w].cell == off; ++w) {
         q = __fadd_rn(q, A.qw[(int64_t)b * P.n_wells + w]);
         mask += 1.f;
       }
+      if (mask != 0.f) qdv = __fdiv_rn(q, P.dv);
     }
     // p2 by linear extrapolation, truncation term        physics_loss.py:126,171
     const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), one_rho), p0);
     const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(d12, p1));
-    const float E = __fadd_rn(c2e7, __fdiv_rn(numr, den));
+    const float E = __fadd_rn(c2e7, div_c(numr, by_den));
     const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
     // flux divergence                                    physics_loss.py:174
     float s = __fadd_rn(-__fmul_rn(a1, pW), -__fmul_rn(a2, pS));
@@ -263,16 +309,16 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
     s = __fadd_rn(s, -__fmul_rn(a4, pN));
     const float zt = __fadd_rn(__fmul_rn(a5, __fsub_rn(p1, pm)), __fmul_rn(a6, __fsub_rn(p1, pn)));   // 3-D extension
     s = __fadd_rn(s, zt);
-    s = __fadd_rn(s, (mask != 0.f) ? __fdiv_rn(q, P.dv) : 0.f);
+    s = __fadd_rn(s, qdv);
     const float divq = __fmul_rn(P.dv, s);
     const float acc = __fmul_rn(__fmul_rn(P.dv, a5t), __fsub_rn(p1, p0));       // physics_loss.py:175
     const float dom = P.tde_in_dom ? __fadd_rn(divq, __fadd_rn(acc, tde)) : __fadd_rn(divq, acc);
     const float mb = __fmul_rn(__fmul_rn(P.dvSgi_phi, __fsub_rn(A1, A0)), mbfac);   // physics_loss.py:193
     if (t.valid) {
-      A.dom[(int64_t)b * P.N + c] = dom;
-      if (A.dom_out) A.dom_out[(int64_t)b * P.N + c] = dom;
+      domf[off] = dom;
+      if (domo) domo[off] = dom;
       if (mask != 0.f) {
-        for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq;
+        for (int w = wfirst; w < P.n_wells && P.wells[w].cell == off; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq;
         const float ibc = __fmul_rn(mask, divq);                                // physics_loss.py:189
         a_ibc += (double)ibc * (double)ibc;
       }
@@ -280,8 +326,13 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
       a_tde = fmaf(tde, tde, a_tde);
       a_mb += (double)mb;
     }
-    pm = pc; pc = pn; Gm = Gc; Gc = Gn; A1c = A1n; hp = hpn; hG = hGn; fD = fU;
-  }
+    pm = pc; pc = pn; Gm = Gc; Gc = Gn; A1c = en.x; fD = fU;
+    off += HW; offh += HW; offE += strE; offN += strN;
+  };
+  int k = 0;
+  for (; k + 1 < D; k += 2) { plane(IntC<0>(), k); plane(IntC<1>(), k + 1); }
+  if (k < D) plane(IntC<0>(), k);
+
   double acc4[4] = {(double)a_dom, a_ibc, (double)a_tde, a_mb};
   __syncthreads();
   block_reduce<4>(acc4, red);
@@ -307,7 +358,7 @@ __global__ void __launch_bounds__(128) k_qsum_ref2(int32_t B, int32_t nw, const 
 // ------------------------------------------------------------------------------------------
 // adjoint
 // ------------------------------------------------------------------------------------------
-template <bool LUT>
+template <bool FULL>
 __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
   __shared__ float s_p[2][SH][SW];
   __shared__ float s_G[2][SH][SW];
@@ -323,59 +374,62 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
   const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
   const float* __restrict__ p1f = A.p1 + (int64_t)b * P.N;
   const float* __restrict__ domf = A.dom + (int64_t)b * P.N;
+  float* __restrict__ gp0f = A.gp0 + (int64_t)b * P.N;
+  float* __restrict__ gp1f = A.gp1 + (int64_t)b * P.N;
   const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   const int yy = t.oc / W, xx = t.oc - yy * W;
-  const int oE = yy * (W + 1) + xx, oN = yy * W + xx;
-  const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_tde = A.dterms[SRM_TERM_TDE];
+  int offE = yy * (W + 1) + xx, offN = yy * W + xx;
+  const int strE = H * (W + 1), strN = (H + 1) * W;
+  const float w_tde2 = 2.f * A.dterms[SRM_TERM_TDE];
   const float d1 = A.dt1[b], d2 = A.dt2[b];
-  const float two_wd = 2.f * w_dom;
-  const float smb = 2.f * w_mbc * A.mbc[b];              // dL/d mbc_b
+  const float two_wd = 2.f * A.dterms[SRM_TERM_DOM];
+  const float smb = 2.f * A.dterms[SRM_TERM_MBC] * A.mbc[b];              // dL/d mbc_b
   // forward's per-sample scalars (op order as the forward: E is dominated by the rounding of N)
   const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
   const float one_rho = __fadd_rn(1.0f, rho);
   const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const DivC by_den = make_divc(den);
   const float c2e7 = __fdiv_rn(2e-7f, d1);
   const float d12 = __fadd_rn(d1, d2);
   const float id1 = 1.0f / d1, iden2 = 1.0f / (den * den);
   const float mbk = P.dvSgi_phi / (P.Dc * d1);          // d mb_cells / d(A1-A0)
   const float hx2 = 0.5f * P.idx * P.idx, hy2 = 0.5f * P.idy * P.idy, hz2 = 0.5f * P.idz * P.idz;
   const float dE1c = -2e-7f * id1 * id1;
+  const float dE1n = d2 * iden2, dE2n = (d1 + 2.f * d2) * iden2;
+  const float dvi = P.dv * P.invDc * id1;               // d acc / d(cp * dp)
+  const float smbk = smb * mbk;
 
-  float m1c, m;
-  float pc = p1f[t.oc];
-  float4 e1 = pack1_at<LUT>(P, pc, m1c);
-  float sc = two_wd * domf[t.oc];
+  int off = t.oc, offh = t.oh;
+  float m1c;
+  float pc = p1f[off];
+  float4 e1 = pack1_at<FULL>(P, pc, m1c);
+  float sc = two_wd * domf[off];
   float pm = pc, Gm = e1.y, sm = sc;
   float hp = 0.f, hG = 0.f, hs = 0.f;
-  if (t.halo) { hp = p1f[t.oh]; hG = pack1_at<LUT>(P, hp, m).y; hs = two_wd * domf[t.oh]; }
-  float fD = FU[t.oc];
+  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL>(P, hp).y; hs = two_wd * domf[offh]; }
+  float fD = FU[off];
   double a_g1 = 0.0, a_g2 = 0.0;
-  for (int k = 0; k < D; ++k) {
-    const int buf = k & 1;
+
+  auto plane = [&](auto BUF, const int k) {
+    constexpr int buf = decltype(BUF)::value;
     s_p[buf][t.ty + 1][t.tx + 1] = pc;
     s_G[buf][t.ty + 1][t.tx + 1] = e1.y;
     s_s[buf][t.ty + 1][t.tx + 1] = sc;
     if (t.halo) { s_p[buf][t.hy][t.hx] = hp; s_G[buf][t.hy][t.hx] = hG; s_s[buf][t.hy][t.hx] = hs; }
-    float pn = pc, sn = sc, hpn = hp, hsn = hs, hGn = hG, m1n = m1c;
-    float4 en = e1;
-    const bool more = k + 1 < D;
-    if (more) {
-      pn = p1f[(int64_t)(k + 1) * HW + t.oc];
-      sn = two_wd * domf[(int64_t)(k + 1) * HW + t.oc];
-      if (t.halo) { hpn = p1f[(int64_t)(k + 1) * HW + t.oh]; hsn = two_wd * domf[(int64_t)(k + 1) * HW + t.oh]; }
-    }
-    const float p0 = p0f[(int64_t)k * HW + t.oc];
-    const float fW = FE[(int64_t)k * H * (W + 1) + oE], fE = FE[(int64_t)k * H * (W + 1) + oE + 1];
-    const float fS = FN[(int64_t)k * (H + 1) * W + oN], fN = FN[(int64_t)k * (H + 1) * W + oN + W];
-    const float fU = FU[(int64_t)(k + 1) * HW + t.oc];
-    float m0;
-    const float4 e0 = pack0_at<LUT>(P, p0, m0);
-    if (more) {
-      en = pack1_at<LUT>(P, pn, m1n);
-      if (t.halo) hGn = pack1_at<LUT>(P, hpn, m).y;
-    }
+    const int up = (k + 1 < D) ? HW : 0;
+    const float pn = p1f[off + up];
+    const float sn = two_wd * domf[off + up];
+    if (t.halo) { hp = p1f[offh + up]; hs = two_wd * domf[offh + up]; }
+    const float p0 = p0f[off];
+    const float fW = FE[offE], fE = FE[offE + 1];
+    const float fS = FN[offN], fN = FN[offN + W];
+    const float fU = FU[off + HW];
+    float m0, m1n;
+    const float4 e0 = pack0_at<FULL>(P, p0, m0);
+    const float4 en = pack1_at<FULL>(P, pn, m1n);
+    if (t.halo) hG = pack1_val<FULL>(P, hp).y;
     __syncthreads();
     const float p1 = pc, G = e1.y, Gp = e1.w * m1c, A1 = e1.x, A1p = e1.z * m1c;
     // stencil gather: dv * sum_f (s_c - s_n) * T_f/2 * [(G_c + G_n) + G'_c (p_c - p_n)]; image faces: s_n == s_c
@@ -394,37 +448,40 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
     }
     g1 *= P.dv;
     // local terms
-    const float A0 = e0.x, A0p = e0.y, A0pp = e0.z * m0;
+    const float A0 = e0.x, A0p = e0.y, A0pm = e0.y * m0, A0pp = e0.z * m0;
     const float cp = P.Sgi * (P.phi * A0p + P.phicf * A0);
-    const float cpp = P.Sgi * (P.phi * A0pp + P.phicf * A0p * m0);   // d cp / d p0
-    const float a5t = P.invDc * (cp * id1);
+    const float cpp = P.Sgi * (P.phi * A0pp + P.phicf * A0pm);   // d cp / d p0
+    const float dva5t = dvi * cp;                                 // dv * a5t
     const float dp = p1 - p0;
-    const float acc = P.dv * a5t * dp;
     const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), one_rho), p0);
     const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(d12, p1));
-    const float E = __fadd_rn(c2e7, __fdiv_rn(numr, den));
+    const float E = __fadd_rn(c2e7, div_c(numr, by_den));
+    const float cE = P.dvDc * cp;
     const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
-    const float st = (P.tde_in_dom ? sc : 0.f) + 2.f * w_tde * tde;   // dL/d tde
+    const float st = (P.tde_in_dom ? sc : 0.f) + w_tde2 * tde;   // dL/d tde
     float dq = 0.f;
-    const int c = k * HW + t.oc;
     if (has_well) {
-      const int first = well_lower_bound(P, c);
-      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) dq += A.dqdp[(int64_t)b * P.n_wells + w];
+      const int first = well_lower_bound(P, off);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == off; ++w) dq += A.dqdp[(int64_t)b * P.n_wells + w];
     }
-    g1 += sc * (dq + P.dv * a5t) + smb * (-dq - mbk * A1p);
-    const float g0 = sc * (-P.dv * a5t + P.dv * dp * P.invDc * id1 * cpp) + st * P.dvDc * cpp * E + smb * (mbk * A0p * m0);
+    g1 += sc * (dq + dva5t) - smb * dq - smbk * A1p;
+    const float g0 = sc * (dvi * dp * cpp - dva5t) + st * P.dvDc * cpp * E + smbk * A0pm;
     if (t.valid) {
-      A.gp0[(int64_t)b * P.N + c] = g0;
-      A.gp1[(int64_t)b * P.N + c] = g1;
+      gp0f[off] = g0;
+      gp1f[off] = g1;
       // d/d dt1, d/d dt2 (the dN/d* pieces vanish identically; N itself is rounding noise)
-      const float dE1 = dE1c - numr * d2 * iden2;
-      const float dE2 = -numr * (d1 + 2.f * d2) * iden2;
-      const float mb = mbk * (A1 - A0);
-      a_g1 += (double)(sc * (-acc * id1) + st * P.dvDc * cp * dE1 + smb * (mb * id1));
-      a_g2 += (double)(st * P.dvDc * cp * dE2);
+      const float dE1 = dE1c - numr * dE1n;
+      const float dE2 = -numr * dE2n;
+      a_g1 += (double)((smbk * (A1 - A0) - sc * dva5t * dp) * id1 + st * cE * dE1);
+      a_g2 += (double)(st * cE * dE2);
     }
-    pm = pc; pc = pn; Gm = e1.y; e1 = en; m1c = m1n; sm = sc; sc = sn; hp = hpn; hG = hGn; hs = hsn; fD = fU;
-  }
+    pm = pc; pc = pn; Gm = e1.y; e1 = en; m1c = m1n; sm = sc; sc = sn; fD = fU;
+    off += HW; offh += HW; offE += strE; offN += strN;
+  };
+  int k = 0;
+  for (; k + 1 < D; k += 2) { plane(IntC<0>(), k); plane(IntC<1>(), k + 1); }
+  if (k < D) plane(IntC<0>(), k);
+
   double acc2[2] = {a_g1, a_g2};
   __syncthreads();
   block_reduce<2>(acc2, red);
@@ -436,7 +493,7 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
 
 // inner-boundary term: L_ibc = w_ibc * sum (mask*divq)^2 ; scatter d divq_c / d p1 to the cell and
 // its six neighbours (atomics: adjacent well cells may hit the same target).
-template <bool LUT>
+template <bool FULL>
 __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nw = P.n_wells;
@@ -459,13 +516,13 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
   const int i = c % W, j = (c / W) % H, k = c / HW;
   float m1, mn;
   const float p1 = p1f[c];
-  const float4 e1 = pack1_at<LUT>(P, p1, m1);
+  const float4 e1 = pack1_at<FULL>(P, p1, m1);
   const float G = e1.y, Gp = e1.w * m1;
   float self = 0.f;
   auto face = [&](bool inside, int cn, float f, float h2) {
     if (!inside) return;
     const float pn = p1f[cn];
-    const float4 en = pack1_at<LUT>(P, pn, mn);
+    const float4 en = pack1_at<FULL>(P, pn, mn);
     const float Tf = f * h2 * 2.f;
     const float af = Tf * 0.5f * (G + en.y);
     self += af + 0.5f * Tf * Gp * (p1 - pn);
@@ -517,7 +574,8 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dom_out = dom_out;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  if (h->lut_full) k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  else k_fwd_ref2<false><<<grid, NT, 0, s>>>(P, A);
   SRM_CUDA_CHECK(cudaGetLastError());
   k_finalize_fwd<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.mbc, terms_out);
   SRM_CUDA_CHECK(cudaGetLastError());
@@ -534,11 +592,12 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dterms = dterms; A.gp0 = gp0; A.gp1 = gp1;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  if (h->lut_full) k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
+  else k_adj_ref2<false><<<grid, NT, 0, s>>>(P, A);
   SRM_CUDA_CHECK(cudaGetLastError());
   const int64_t n = (int64_t)B * P.n_wells;
   if (n > 0) {
-    k_ibc_adj_ref2<true><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
+    k_ibc_adj_ref2<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
     SRM_CUDA_CHECK(cudaGetLastError());
   }
   k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);

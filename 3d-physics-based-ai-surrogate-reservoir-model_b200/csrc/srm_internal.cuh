@@ -70,6 +70,7 @@ struct SrmHandle {
   WellDev* d_wells;    // device
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
   float4* d_lut;       // device (exact PVT tabulation), may be null
+  int lut_full;        // the table covers the whole clamp range [p_min, p_max]
   int device;
   int sm_count;
   // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD)
