@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrm_physics.so")
+# SRM_PHYSICS_LIB: kernel-tuning experiments load an alternative build of the same library
+LIB_PATH = os.environ.get("SRM_PHYSICS_LIB") or os.path.join(_HERE, "libsrm_physics.so")
 
 SRM_ABI_VERSION = 2
 SRM_N_TERMS = 8

@@ -81,15 +81,19 @@ __device__ __forceinline__ float4 pvt_pack1(const SrmDev& P, float x1) {
 // pattern is lut_lo_bits + e, i.e. EVERY representable pressure of [lut_lo, lut_hi] -- the table
 // is the reference-order spline itself, evaluated once per distinct input instead of once per cell.
 __global__ void __launch_bounds__(kThreads) k_lut_build(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
-                                                        float4* __restrict__ t1) {
+                                                        float4* __restrict__ t1, float2* __restrict__ f0,
+                                                        float2* __restrict__ f1) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.lut_n) return;
   const float x = __uint_as_float(P.lut_lo_bits + e);
-  t0[e] = pvt_pack0<true>(P, x);
-  t1[e] = pvt_pack1<true>(P, x);
+  const float4 a = pvt_pack0<true>(P, x), b = pvt_pack1<true>(P, x);
+  t0[e] = a;
+  t1[e] = b;
+  f0[e] = make_float2(a.x, a.y);
+  f1[e] = make_float2(b.x, b.y);
 }
 
-template <bool SAVE, bool LUT>
+template <bool SAVE>
 __global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ SrmDev P, int64_t total,
                                                         const float* __restrict__ p0, const float* __restrict__ p1,
                                                         float* __restrict__ A0, float* __restrict__ A0p,
@@ -101,10 +105,7 @@ __global__ void __launch_bounds__(kThreads) k_stage_ref(const __grid_constant__ 
   float m0, m1;
   const float x0 = srm_clamp(P, p0[g], m0);
   const float x1 = srm_clamp(P, p1[g], m1);
-  float4 a, b;
-  const uint32_t e0 = __float_as_uint(x0) - P.lut_lo_bits, e1 = __float_as_uint(x1) - P.lut_lo_bits;
-  if (LUT && e0 < P.lut_n) a = __ldg(P.lut0 + e0); else a = pvt_pack0<SAVE>(P, x0);
-  if (LUT && e1 < P.lut_n) b = __ldg(P.lut1 + e1); else b = pvt_pack1<SAVE>(P, x1);
+  const float4 a = pvt_pack0<SAVE>(P, x0), b = pvt_pack1<SAVE>(P, x1);
   A0[g] = a.x;
   A0p[g] = a.y;                  // w.r.t. clamped input: enters cp unmasked (physics_loss.py:150)
   A1[g] = b.x;
@@ -419,13 +420,15 @@ int srm_build_pvt_lut(SrmHandle* h, float lo, float hi) {
   if (!(lo > 0.f) || !(hi >= lo)) { srm_set_error("srm_create: pvt_lut range [%g, %g] must be positive and ascending", lo, hi); return SRM_ERR_INVALID; }
   const uint64_t n = (uint64_t)hi_bits - lo_bits + 1;
   if (n > (1ull << 31)) { srm_set_error("srm_create: pvt_lut range too wide"); return SRM_ERR_INVALID; }
-  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * 2 * sizeof(float4));
-  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut needs %.1f MB of device memory: %s", n * 32e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
+  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * 3 * sizeof(float4));     // two 16-byte + two 8-byte tables
+  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut needs %.1f MB of device memory: %s", n * 48e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
   P.lut_lo_bits = lo_bits;
   P.lut_n = (uint32_t)n;
   P.lut0 = h->d_lut;
   P.lut1 = h->d_lut + n;
-  k_lut_build<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + n);
+  P.lutf0 = reinterpret_cast<const float2*>(h->d_lut + 2 * n);
+  P.lutf1 = P.lutf0 + n;
+  k_lut_build<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + n, (float2*)P.lutf0, (float2*)P.lutf1);
   SRM_CUDA_CHECK(cudaGetLastError());
   SRM_CUDA_CHECK(cudaDeviceSynchronize());
   return SRM_OK;
@@ -438,12 +441,10 @@ int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
   const int64_t total = (int64_t)B * P.N;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
   const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
-  const bool lut = P.lut_n > 0;
-#define SRM_STAGE(SV, LT) k_stage_ref<SV, LT><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, \
-                                                                           (SV) ? ws.A0pp : nullptr, (SV) ? ws.G1p : nullptr, (SV) ? ws.A1p : nullptr)
-  if (save) { if (lut) SRM_STAGE(true, true); else SRM_STAGE(true, false); }
-  else      { if (lut) SRM_STAGE(false, true); else SRM_STAGE(false, false); }
-#undef SRM_STAGE
+  if (save)
+    k_stage_ref<true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, ws.A0pp, ws.G1p, ws.A1p);
+  else
+    k_stage_ref<false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, ws.A0, ws.A0p, ws.A1, ws.G1, nullptr, nullptr, nullptr);
   SRM_CUDA_CHECK(cudaGetLastError());
   int rc = srm_launch_wells_ref(h, B, kx, sample_real, R, p1, t1, ws.qw, ws.pwfw, ws.dqdp, s);
   if (rc) return rc;

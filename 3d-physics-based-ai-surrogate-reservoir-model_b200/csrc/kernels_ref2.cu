@@ -17,140 +17,15 @@
 //   k_fwd_ref2      physics_error_gas residual + SSE partials      physics_loss.py:143-193,787-807
 //   k_adj_ref2      hand-derived adjoint (tape.gradient, physics_loss.py:849-859)
 //   k_ibc_adj_ref2  inner-boundary (well-cell) part of the adjoint
-#include <math_constants.h>
+#include <cstdlib>
 #include <cstring>
-#include "pvt_ref.cuh"
-#include "common.cuh"
+#include "ref_fused.cuh"
 
 namespace {
 
 constexpr int TX = 32, TY = 16, NT = TX * TY;
 constexpr int SW = TX + 2, SH = TY + 2;
 constexpr int NHALO = 2 * TX + 2 * TY;
-
-// (2.*k1*k2)/(k1+k2)                                             physics_loss.py:59-60
-__device__ __forceinline__ float harm2(float ka, float kb) {
-  return __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, ka), kb), __fadd_rn(ka, kb));
-}
-
-struct FaceLay { int64_t nE, nN, nU, per_real; };
-__host__ __device__ inline FaceLay face_layout(int D, int H, int W) {
-  FaceLay f;
-  f.nE = (int64_t)D * H * (W + 1);
-  f.nN = (int64_t)D * (H + 1) * W;
-  f.nU = (int64_t)(D + 1) * H * W;
-  f.per_real = f.nE + f.nN + f.nU;
-  return f;
-}
-
-// FE[k][j][i], i in [0,W]: face between columns i-1 and i; FN[k][j][i], j in [0,H]; FU[k][j][i], k in [0,D].
-// Slots 0 and W (H, D) are the image faces of the edge-replicating pad: harmonic mean of the cell with itself.
-__global__ void __launch_bounds__(256) k_faces_ref(const __grid_constant__ SrmDev P, const float* __restrict__ kx,
-                                                   float* __restrict__ faces) {
-  const FaceLay L = face_layout(P.D, P.H, P.W);
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= L.per_real) return;
-  const float* kr = kx + (int64_t)blockIdx.y * P.N;
-  float* out = faces + (int64_t)blockIdx.y * L.per_real;
-  const int W = P.W, H = P.H, D = P.D;
-  float ka, kb;   // upper/right cell, lower/left cell
-  if (e < L.nE) {
-    const int i = (int)(e % (W + 1));
-    const int64_t t = e / (W + 1);
-    const int j = (int)(t % H), k = (int)(t / H);
-    const int64_t row = ((int64_t)k * H + j) * W;
-    ka = kr[row + min(i, W - 1)];
-    kb = kr[row + max(i - 1, 0)];
-  } else if (e < L.nE + L.nN) {
-    const int64_t e2 = e - L.nE;
-    const int i = (int)(e2 % W);
-    const int64_t t = e2 / W;
-    const int j = (int)(t % (H + 1)), k = (int)(t / (H + 1));
-    ka = __fmul_rn(P.kx_ky, kr[((int64_t)k * H + min(j, H - 1)) * W + i]);
-    kb = __fmul_rn(P.kx_ky, kr[((int64_t)k * H + max(j - 1, 0)) * W + i]);
-  } else {
-    const int64_t e2 = e - L.nE - L.nN;
-    const int i = (int)(e2 % W);
-    const int64_t t = e2 / W;
-    const int j = (int)(t % H), k = (int)(t / H);
-    ka = __fmul_rn(P.kv_kh, kr[((int64_t)min(k, D - 1) * H + j) * W + i]);
-    kb = __fmul_rn(P.kv_kh, kr[((int64_t)max(k - 1, 0) * H + j) * W + i]);
-  }
-  out[e] = __fmul_rn(__fmul_rn(P.C, harm2(ka, kb)), P.krg);
-}
-
-// ---- PVT packs through the table (direct evaluation outside the tabulated range) -----------------
-// FULL: the table covers the whole clamp range [p_min, p_max], so the lookup needs no range test.
-template <bool FULL>
-__device__ __forceinline__ float4 pack0_at(const SrmDev& P, float p, float& m) {
-  const float x = srm_clamp(P, p, m);
-  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (FULL || e < P.lut_n) return __ldg(P.lut0 + e);
-  float v[1], d[1], d2[1];
-  srm_spline_ref<1, true, true>(P, 0, x, v, d, d2);
-  return make_float4(v[0], d[0], d2[0], 0.f);
-}
-template <bool FULL>
-__device__ __forceinline__ float4 pack1_at(const SrmDev& P, float p, float& m) {
-  const float x = srm_clamp(P, p, m);
-  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (FULL || e < P.lut_n) return __ldg(P.lut1 + e);
-  float v[2], d[2], d2[2];
-  srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
-  return make_float4(v[0], __fmul_rn(v[0], v[1]), d[0], __fmaf_rn(d[0], v[1], __fmul_rn(v[0], d[1])));
-}
-// value-only variants for the forward (no gradient mask)
-template <bool FULL>
-__device__ __forceinline__ float4 pack0_val(const SrmDev& P, float p) {
-  const float x = fminf(fmaxf(p, P.p_min), P.p_max);    // == srm_clamp (NaN -> p_min as well)
-  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (FULL || e < P.lut_n) return __ldg(P.lut0 + e);
-  float v[1], d[1], d2[1];
-  srm_spline_ref<1, true, false>(P, 0, x, v, d, d2);
-  return make_float4(v[0], d[0], 0.f, 0.f);
-}
-template <bool FULL>
-__device__ __forceinline__ float2 pack1_val(const SrmDev& P, float p) {
-  const float x = fminf(fmaxf(p, P.p_min), P.p_max);
-  const uint32_t e = __float_as_uint(x) - P.lut_lo_bits;
-  if (FULL || e < P.lut_n) return __ldg(reinterpret_cast<const float2*>(P.lut1 + e));
-  float v[2], d[2], d2[2];
-  srm_spline_ref<2, false, false>(P, 0, x, v, d, d2);
-  return make_float2(v[0], __fmul_rn(v[0], v[1]));
-}
-
-// ---- correctly rounded division by a per-sample constant -----------------------------------------
-// div.rn's own fast path (q = a*y, two Markstein corrections) with y = RN(1/b) hoisted out of the
-// cell loop.  Valid while b and a are far from the exponent limits; a == 0 returns the signed zero
-// a*y; anything else takes the IEEE intrinsic.  div.rn itself sends a == 0 (the usual value of the
-// truncation bracket, physics_loss.py:171) to its slow path -- a subroutine call per cell otherwise.
-// Checked against div.rn by srm_selftest_rounding (slot 3).
-struct DivC { float b, y; bool ok; };
-__device__ __forceinline__ DivC make_divc(float b) {
-  DivC d;
-  d.b = b;
-  d.y = __frcp_rn(b);
-  const float ab = fabsf(b);
-  d.ok = ab >= 0x1p-60f && ab <= 0x1p60f;
-  return d;
-}
-__device__ __forceinline__ float div_c(float a, const DivC& d) {
-  const float q0 = __fmul_rn(a, d.y);
-  float q = __fmaf_rn(__fmaf_rn(-d.b, q0, a), d.y, q0);
-  q = __fmaf_rn(__fmaf_rn(-d.b, q, a), d.y, q);
-  const float aa = fabsf(a);
-  if (aa == 0.f) q = q0;
-  if (!(d.ok && (aa == 0.f || (aa >= 0x1p-60f && aa <= 0x1p60f)))) q = __fdiv_rn(a, d.b);
-  return q;
-}
-
-struct R2Args {
-  const float* p0; const float* p1; const float* dt1; const float* dt2; const int32_t* sample_real;
-  const float* faces;
-  const float* qw; float* divqw; float* dom; float* dom_out; double* sse; double* mb_sum;
-  const float* dterms; const float* mbc; const float* dqdp; float* gp0; float* gp1; double* gdt1_acc; double* gdt2_acc;
-  int32_t B, R, tiles_x;
-};
 
 // tile bookkeeping shared by both kernels
 struct Tile {
@@ -196,8 +71,6 @@ __device__ __forceinline__ bool column_has_well(const SrmDev& P, const Tile& t, 
   return s_flag[threadIdx.x] != 0 && t.valid;
 }
 
-template <int V> struct IntC { static constexpr int value = V; };
-
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -221,9 +94,9 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   const int yy = t.oc / W, xx = t.oc - yy * W;          // clamped coordinates
-  int offE = yy * (W + 1) + xx;                         // FE offset, plane stride H*(W+1)
+  int offE = yy * FL.WP + xx;                         // FE offset, plane stride H*(W+1)
   int offN = yy * W + xx;                               // FN offset, plane stride (H+1)*W
-  const int strE = H * (W + 1), strN = (H + 1) * W;
+  const int strE = H * FL.WP, strN = (H + 1) * W;
   // per-sample scalars                                   physics_loss.py:126,156,171,193
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float rho = (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1);
@@ -234,15 +107,16 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
   const float d12 = __fadd_rn(d1, d2);
   const float mbfac = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
 
+  const uint64_t keep = l2_evict_last();
   // plane 0 (own + halo), then the march
   int off = t.oc;                                       // own cell of the current plane
   int offh = t.oh;                                      // halo cell of the current plane
   float pc = p1f[off];
-  const float2 e1 = pack1_val<FULL>(P, pc);
+  const float2 e1 = pack1_val<FULL>(P, pc, keep);
   float Gc = e1.y, A1c = e1.x;
   float pm = pc, Gm = Gc;
   float hp = 0.f, hG = 0.f;
-  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL>(P, hp).y; }
+  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL>(P, hp, keep).y; }
   float fD = FU[off];                                   // face below plane 0 (image)
   float a_dom = 0.f, a_tde = 0.f;                       // per-thread partial sums (<= D terms each)
   double a_ibc = 0.0, a_mb = 0.0;
@@ -260,9 +134,9 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
     const float fW = FE[offE], fE = FE[offE + 1];
     const float fS = FN[offN], fN = FN[offN + W];
     const float fU = FU[off + HW];
-    const float4 e0 = pack0_val<FULL>(P, p0);
-    const float2 en = pack1_val<FULL>(P, pn);
-    if (t.halo) hG = pack1_val<FULL>(P, hp).y;
+    const float2 e0 = pack0_val<FULL>(P, p0, keep);
+    const float2 en = pack1_val<FULL>(P, pn, keep);
+    if (t.halo) hG = pack1_val<FULL>(P, hp, keep).y;
     __syncthreads();
     const float pW = s_p[buf][t.ty + 1][t.tx], pE = s_p[buf][t.ty + 1][t.tx + 2];
     const float pS = s_p[buf][t.ty][t.tx + 1], pN = s_p[buf][t.ty + 2][t.tx + 1];
@@ -380,8 +254,8 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   const int yy = t.oc / W, xx = t.oc - yy * W;
-  int offE = yy * (W + 1) + xx, offN = yy * W + xx;
-  const int strE = H * (W + 1), strN = (H + 1) * W;
+  int offE = yy * FL.WP + xx, offN = yy * W + xx;
+  const int strE = H * FL.WP, strN = (H + 1) * W;
   const float w_tde2 = 2.f * A.dterms[SRM_TERM_TDE];
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float two_wd = 2.f * A.dterms[SRM_TERM_DOM];
@@ -401,14 +275,15 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
   const float dvi = P.dv * P.invDc * id1;               // d acc / d(cp * dp)
   const float smbk = smb * mbk;
 
+  const uint64_t keep = l2_evict_last();
   int off = t.oc, offh = t.oh;
   float m1c;
   float pc = p1f[off];
-  float4 e1 = pack1_at<FULL>(P, pc, m1c);
+  float4 e1 = pack1_at<FULL>(P, pc, m1c, keep);
   float sc = two_wd * domf[off];
   float pm = pc, Gm = e1.y, sm = sc;
   float hp = 0.f, hG = 0.f, hs = 0.f;
-  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL>(P, hp).y; hs = two_wd * domf[offh]; }
+  if (t.halo) { hp = p1f[offh]; hG = pack1_val<FULL, true>(P, hp, keep).y; hs = two_wd * domf[offh]; }
   float fD = FU[off];
   double a_g1 = 0.0, a_g2 = 0.0;
 
@@ -427,9 +302,9 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
     const float fS = FN[offN], fN = FN[offN + W];
     const float fU = FU[off + HW];
     float m0, m1n;
-    const float4 e0 = pack0_at<FULL>(P, p0, m0);
-    const float4 en = pack1_at<FULL>(P, pn, m1n);
-    if (t.halo) hG = pack1_val<FULL>(P, hp).y;
+    const float4 e0 = pack0_at<FULL>(P, p0, m0, keep);
+    const float4 en = pack1_at<FULL>(P, pn, m1n, keep);
+    if (t.halo) hG = pack1_val<FULL, true>(P, hp, keep).y;
     __syncthreads();
     const float p1 = pc, G = e1.y, Gp = e1.w * m1c, A1 = e1.x, A1p = e1.z * m1c;
     // stencil gather: dv * sum_f (s_c - s_n) * T_f/2 * [(G_c + G_n) + G'_c (p_c - p_n)]; image faces: s_n == s_c
@@ -516,21 +391,22 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
   const int i = c % W, j = (c / W) % H, k = c / HW;
   float m1, mn;
   const float p1 = p1f[c];
-  const float4 e1 = pack1_at<FULL>(P, p1, m1);
+  const uint64_t keep = l2_evict_last();
+  const float4 e1 = pack1_at<FULL>(P, p1, m1, keep);
   const float G = e1.y, Gp = e1.w * m1;
   float self = 0.f;
   auto face = [&](bool inside, int cn, float f, float h2) {
     if (!inside) return;
     const float pn = p1f[cn];
-    const float4 en = pack1_at<FULL>(P, pn, mn);
+    const float4 en = pack1_at<FULL>(P, pn, mn, keep);
     const float Tf = f * h2 * 2.f;
     const float af = Tf * 0.5f * (G + en.y);
     self += af + 0.5f * Tf * Gp * (p1 - pn);
     atomicAdd(&gp1[cn], s * P.dv * (-af + 0.5f * Tf * (en.w * mn) * (p1 - pn)));
   };
   const float hx2 = 0.5f * P.idx * P.idx, hy2 = 0.5f * P.idy * P.idy, hz2 = 0.5f * P.idz * P.idz;
-  face(i > 0, c - 1, FE[((int64_t)k * H + j) * (W + 1) + i], hx2);
-  face(i < W - 1, c + 1, FE[((int64_t)k * H + j) * (W + 1) + i + 1], hx2);
+  face(i > 0, c - 1, FE[((int64_t)k * H + j) * FL.WP + i], hx2);
+  face(i < W - 1, c + 1, FE[((int64_t)k * H + j) * FL.WP + i + 1], hx2);
   face(j > 0, c - W, FN[((int64_t)k * (H + 1) + j) * W + i], hy2);
   face(j < H - 1, c + W, FN[((int64_t)k * (H + 1) + j + 1) * W + i], hy2);
   face(k > 0, c - HW, FU[(int64_t)k * HW + j * W + i], hz2);
@@ -543,6 +419,16 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+bool srm_ref3_applicable(const SrmDev& P);
+cudaError_t srm_ref3_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+cudaError_t srm_ref3_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+
+// the 4-cells-per-thread kernels move every field as 16-byte vectors: W % 4 == 0 and 16-byte aligned fields
+static bool use_ref3(const SrmDev& P, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+  auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return srm_ref3_applicable(P) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
+}
+
 size_t srm_ref2_face_floats(const SrmDev& P) { return (size_t)face_layout(P.D, P.H, P.W).per_real; }
 
 static R2Args make_args(const SrmDev& P, int32_t B, int32_t R, const int32_t* sample_real, const float* p0,
@@ -573,10 +459,14 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   }
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dom_out = dom_out;
-  const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  if (h->lut_full) k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
-  else k_fwd_ref2<false><<<grid, NT, 0, s>>>(P, A);
-  SRM_CUDA_CHECK(cudaGetLastError());
+  if (use_ref3(P, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+    SRM_CUDA_CHECK(srm_ref3_launch_fwd(h, &A, B, s));
+  } else {
+    const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
+    if (h->lut_full) k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
+    else k_fwd_ref2<false><<<grid, NT, 0, s>>>(P, A);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
   k_finalize_fwd<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.mbc, terms_out);
   SRM_CUDA_CHECK(cudaGetLastError());
   return SRM_OK;
@@ -591,10 +481,17 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dterms = dterms; A.gp0 = gp0; A.gp1 = gp1;
-  const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  if (h->lut_full) k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
-  else k_adj_ref2<false><<<grid, NT, 0, s>>>(P, A);
-  SRM_CUDA_CHECK(cudaGetLastError());
+  // the 4-cell adjoint spills at the 128-register cap and is slower than the generic kernel on B200 (0.78 vs 0.57 ms
+  // at cfg2); it stays selectable for tuning (SRM_ADJ4=1)
+  static const bool adj4 = getenv("SRM_ADJ4") != nullptr;
+  if (adj4 && use_ref3(P, p0, p1, ws.dom, nullptr, gp0, gp1)) {
+    SRM_CUDA_CHECK(srm_ref3_launch_adj(h, &A, B, s));
+  } else {
+    const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
+    if (h->lut_full) k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
+    else k_adj_ref2<false><<<grid, NT, 0, s>>>(P, A);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
   const int64_t n = (int64_t)B * P.n_wells;
   if (n > 0) {
     k_ibc_adj_ref2<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);

@@ -42,6 +42,8 @@ struct SrmDev {
   // exact PVT tabulation (SrmConfig.pvt_lut); lut_n == 0: off
   const float4* lut0;    // [lut_n] {invBg, d/dp, d2/dp2, -} at the fp32 value with bits lut_lo_bits + e
   const float4* lut1;    // [lut_n] {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
+  const float2* lutf0;   // [lut_n] {invBg, d/dp}            -- the forward's 8-byte views: half the L2 footprint
+  const float2* lutf1;   // [lut_n] {invBg, invBg*invug}
   uint32_t lut_lo_bits, lut_n;
 };
 

@@ -107,6 +107,8 @@ CASES_LIVE = [
     dict(W=33, H=7, D=2, T=1, K=1, seed=2004, wells="none"),                            # ragged W, no wells, B=1
     dict(W=5, H=4, D=3, T=2, K=3, seed=2005, wells="lattice"),                          # tiny grid, duplicate-cell wells
     dict(W=70, H=37, D=5, T=2, K=1, seed=2006, all_layers=True),                        # several tiles, ragged in x and y
+    dict(W=136, H=19, D=3, T=2, K=1, seed=2007, all_layers=True),                       # W % 4 == 0: 4-cell threads, 3 tiles in x
+    dict(W=64, H=32, D=1, T=2, K=2, seed=2008, wells="lattice"),                        # single plane, full-width tile
 ]
 
 
@@ -290,3 +292,28 @@ def test_pvt_lut_is_bit_identical_to_direct_evaluation(lut_range):
     p_all = torch.cat([d["p0"].reshape(-1), d["p1"].reshape(-1)])
     inside = ((p_all >= lut_range[0]) & (p_all <= lut_range[1])).float().mean().item()
     assert 0.0 < inside < 1.0, "the case must exercise both the table and the direct path"
+
+
+def test_four_cell_adjoint_kernel_matches_oracle():
+    """The 4-cells-per-thread adjoint (kernels_ref3.cu) is not the default on B200 (the generic kernel is
+    faster there); SRM_ADJ4=1 selects it.  It must meet the same gradient gate.  The switch is read once per
+    process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import util as U
+kw = dict(W=136, H=19, D=3, T=2, K=1, seed=2007, all_layers=True)
+ocfg, otab, spec, ptab, batch = U.make_case(**kw)
+o = U.oracle_run(ocfg, otab, batch)
+c = U.cuda_run(spec, ptab, batch, pvt_lut=True)
+assert U.ulp_diff(c["dom"], o["dom"]) == 0
+for k in ("gp0", "gp1", "gdt1"):
+    a, b = np.asarray(c[k], np.float64), np.asarray(o[k], np.float64)
+    assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-5 * np.abs(b).max()), k
+print("ADJ4 OK")
+'''
+    env = dict(os.environ, SRM_ADJ4="1")
+    out = subprocess.run([sys.executable, "-c", code], cwd=U.ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ADJ4 OK" in out.stdout, out.stdout + out.stderr
