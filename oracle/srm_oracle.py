@@ -686,6 +686,271 @@ def dg_forward_backward(cfg, tab, kx, p0, p1, dt1, dt2, t_days, sample_real, wei
 
 
 # --------------------------------------------------------------------------------------------
+# GC (gas-condensate, two-phase gas-oil) residual  (physics_loss.py:230-712)
+# --------------------------------------------------------------------------------------------
+# Additional pins for this path (TF leaves them open):
+#   * tf.math.pow with an INTEGER-valued exponent n (Corey exponents nog = 3, ng = 6,
+#     relative_permeability.py:59-60) is the left-to-right product ((x*x)*x)...  -- libm's pow and CUDA's
+#     powf are not bit-identical, repeated multiplication is; non-integer exponents use pow and are
+#     tolerance-checked only;
+#   * python-float factors that multiply by exactly 1 (tdew_idx = 1, physics_loss.py:380) are dropped;
+#   * 3-D extension as in the DG path: the k+-1 faces enter every component's divergence in
+#     difference form a5*(p-pD) + a6*(p-pU) after the in-plane terms; the relative permeability on the
+#     U face is selected like the E/N faces (pot = p_nbr - p_c), on the D face like the W/S faces
+#     (pot = p_c - p_nbr)  (physics_loss.py:538-551 as written, including its W/S-face convention).
+def _pow_pinned(x, n: float):
+    if float(n).is_integer() and 1 <= n <= 16:
+        y = x
+        for _ in range(int(n) - 1):
+            y = y * x
+        return y
+    return torch.pow(x, n)
+
+
+def corey_krog_krgo_t(sg, cfg: OracleConfig, dtype=torch.float32):
+    """RelativePermeability.compute_krog_krgo (relative_permeability.py:49-75), torch, TF gradient routing."""
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    t = npdt
+    swmin, sorg, sgc, socr = t(cfg.Swmin), t(cfg.Sorg), t(cfg.Sgc), t(cfg.Socr)
+    c = lambda v: torch.tensor(float(v), dtype=dtype)
+    den_o = (t(1.0) - swmin) - sorg                                   # :59
+    den_g = ((t(1.0) - sgc) - swmin) - sorg                           # :60
+    so = (1.0 - sg) - c(swmin)                                        # :58
+    krog = c(t(cfg.kro_Somax)) * _pow_pinned((so - c(sorg)) / c(den_o), cfg.nog)
+    krgo = c(t(cfg.krg_Sorg)) * _pow_pinned((sg - c(sgc)) / c(den_g), cfg.ng)
+    sorg_eff = max(sorg, socr)                                        # :66
+    krog = torch.where(so <= c(swmin + sorg_eff), torch.zeros_like(krog), krog)             # :67
+    krgo = torch.where(sg > c(t(1.0) - (swmin + sorg)), torch.ones_like(krgo) * c(t(cfg.krg_Swmin)), krgo)   # :68
+    krog = _tf_maximum(_tf_minimum(krog, torch.ones_like(krog) * c(t(cfg.kro_Somax))), torch.zeros_like(krog))   # :71
+    krgo = _tf_maximum(_tf_minimum(krgo, torch.ones_like(krgo) * c(t(cfg.krg_Swmin))), torch.zeros_like(krgo))   # :72
+    return krog, krgo
+
+
+def wells_gc(p_cell, sg_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConfig, dtype):
+    """WellRatesPressure.compute_rates_and_bhp, fluid_type 'GC', non-iterative control, blocking factor off
+    (well_rate_bhp_Subclassed.py:727-837, 614-724, 963-1034), at the connection cells.
+
+    returns (qgg, qgo, qoo, qog) each (B,nw), pwf (B,nw)"""
+    if cfg.use_blocking_factor:
+        raise NotImplementedError("GC blocking-factor integral (Newton/Chandrupatla root find) is not restated")
+    dt = dtype
+    wells = cfg.wells
+    nw = len(wells)
+    as_t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), dtype=dt).reshape(1, nw)
+    rw = as_t([w.wellbore_radius for w in wells])
+    hc = as_t([w.completion_ratio for w in wells])
+    q_t = as_t([well_control_value(w) for w in wells])
+    pmin = as_t([w.minimum_bhp for w in wells])
+    shut = torch.as_tensor(shutin_open_mask(t_days, wells), dtype=dt)
+    ck = shut * peaceman_static(kx_cell, cfg, rw, hc, dt)                        # :788
+    p = p_cell
+    krog, krgo = corey_krog_krgo_t(sg_cell, cfg, dt)                             # :791
+    v, _ = pvt_eval(p, tab, cfg, props=(0, 1, 2, 3, 4, 5))                       # :794-795
+    invBg, invBo, invug, invuo, Rs, Rv = (v[i] for i in range(6))
+    mgg = krgo * invBg * invug                                                   # :802-807
+    mgo = krog * invBo * invuo * Rs
+    moo = krog * invBo * invuo
+    mog = krgo * invBg * invug * Rv
+    mg = mgg + mgo
+    mo = moo + mog
+    tiny = 1e-12
+    one = torch.ones_like(p)
+    zero = torch.zeros_like(p)
+    # ---- _non_iterative_method (:614-724), blocking off: Ig_max = Io_max = 1
+    dp_max = p - pmin + tiny                                                     # :650
+    blk_g_max = one                                                              # :657
+    qg_max = ck * blk_g_max * mg * dp_max                                        # :662 (well_id == 1)
+    qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), zero)            # :666
+    lam = _tf_clip(_dnn(qg_opt, ck * blk_g_max * mg), zero, blk_g_max)           # :699
+    pwf = _tf_clip(p - lam * dp_max, pmin.expand_as(p), p)                       # :721-723
+    # ---- _compute_phase_rates (:963-1007)
+    dp = p - pwf + tiny                                                          # :987
+    qg_max2 = ck * one * mg * dp                                                 # :997
+    qo_max2 = ck * one * mo * dp                                                 # :998
+    qg = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), zero)               # :1001
+    qo_target = qg * (1.0 / (Rv + tiny))                                         # :1004
+    qo = _tf_maximum(_tf_minimum(qo_target, qo_max2), zero)                      # :1005
+    # ---- _split_condensate_components (:1010-1034)
+    denom_g = mgg + mgo + tiny
+    denom_o = moo + mog + tiny
+    return (qg * (mgg / denom_g), qg * (mgo / denom_g), qo * (moo / denom_o), qo * (mog / denom_o)), pwf
+
+
+def gc_residual(cfg: OracleConfig, tab: SplineTable, kx, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t_days, sample_real,
+                dtype=torch.float32):
+    """physics_error_gas_oil (physics_loss.py:319-693) given the networks' outputs p, Sg, So at both time
+    levels.  tab must hold the 7 GC properties in GC_PROPS order.  Differentiable w.r.t.
+    p0, p1, sg0, sg1, so0, so1, dt1, dt2."""
+    dt = dtype
+    T = lambda v: torch.tensor(v, dtype=dt)
+    B = p0.shape[0]
+    sr = torch.as_tensor(np.asarray(sample_real), dtype=torch.long)
+    kxb = kx.to(dt)
+    st = {k: v.index_select(0, sr) for k, v in dg_static(kxb, cfg).items()}       # :283-284 (+ z faces)
+    dx, dy, dz = T(cfg.dx), T(cfg.dy), T(cfg.dz)
+    dv = dx * dy * dz                                                        # :255
+    C, Dc = T(cfg.C), T(cfg.Dc)
+    phi = T(cfg.phi)
+    cf = torch.tensor(float(rock_compressibility(cfg.phi)), dtype=dt) if dt == torch.float32 else \
+        T(97.32e-6 / (1 + 55.8721 * cfg.phi ** 1.428586))                    # :288
+    d1 = dt1.reshape(B, 1, 1, 1)
+    d2 = dt2.reshape(B, 1, 1, 1)
+
+    # PVT: values at n0 and n1, dp-derivatives at n0 of invBg, invBo, Rs, Rv      :324-372, 506-514
+    v0, dv0 = pvt_eval(p0, tab, cfg, props=(0, 1, 4, 5), need_deriv=(0, 1, 4, 5))
+    invBg0, invBo0, Rs0, Rv0 = v0[0], v0[1], v0[4], v0[5]
+    dinvBg0, dinvBo0, dRs0, dRv0 = dv0[0], dv0[1], dv0[4], dv0[5]
+    v1, _ = pvt_eval(p1, tab, cfg, props=(0, 1, 2, 3, 4, 5))
+    invBg1, invBo1, invug1, invuo1, Rs1, Rv1 = (v1[i] for i in range(6))
+    RsinvBo0 = Rs0 * invBo0                                                  # :343
+    RvinvBg0 = Rv0 * invBg0                                                  # :344
+    Mgg = invBg1 * invug1                                                    # :386 invBgug_n1
+    Moo = invBo1 * invuo1                                                    # :387 invBouo_n1
+    RsinvBo1 = Rs1 * invBo1                                                  # :388
+    RvinvBg1 = Rv1 * invBg1                                                  # :389
+    Mgo = Rs1 * invBo1 * invuo1                                              # :390 RsinvBouo_n1
+    Mog = Rv1 * invBg1 * invug1                                              # :391 RvinvBgug_n1
+
+    # masses and truncation terms                                            :419-441
+    rho1 = 1.0 + _dnn(d2, d1)
+    mg0 = phi * ((invBg0 * sg0) + (RsinvBo0 * so0))
+    mo0 = phi * ((invBo0 * so0) + (RvinvBg0 * sg0))
+    mg1 = phi * ((invBg1 * sg1) + (RsinvBo1 * so1))
+    mo1 = phi * ((invBo1 * so1) + (RvinvBg1 * sg1))
+    mg2 = (mg1 - mg0) * rho1 + mg0
+    mo2 = (mo1 - mo0) * rho1 + mo0
+    rte = 1e-7 * (1 / 4)                                                     # :439
+    den = (d1 * d2) + d2 * d2
+    trn_g = (dv / Dc) * ((rte / d1) + ((((d2 * mg0) + (d1 * mg2)) - ((d1 + d2) * mg1)) / den))   # :440
+    trn_o = (dv / Dc) * ((rte / d1) + ((((d2 * mo0) + (d1 * mo2)) - ((d1 + d2) * mo1)) / den))   # :441
+
+    krog1, krgo1 = corey_krog_krgo_t(sg1, cfg, dt)                           # :457
+
+    # wells (rates are model outputs in the legacy code, :461; here WellRatesPressure is evaluated at the connections)
+    nw = len(cfg.wells)
+    zf = torch.zeros_like(p1)
+    q4 = [zf, zf, zf, zf]
+    pwf = zf
+    mask = torch.zeros((cfg.D, cfg.H, cfg.W), dtype=dt)
+    qw4 = pwfw = None
+    if nw:
+        flat = torch.as_tensor(well_flat_index(cfg.wells, cfg.D, cfg.H, cfg.W).astype(np.int64))
+        N = cfg.D * cfg.H * cfg.W
+        p_cell = p1.reshape(B, -1).index_select(1, flat)
+        sg_cell = sg1.reshape(B, -1).index_select(1, flat)
+        kx_cell = kxb.index_select(0, sr).reshape(B, -1).index_select(1, flat)
+        qw4, pwfw = wells_gc(p_cell, sg_cell, kx_cell, np.asarray(t_days), tab, cfg, dt)
+        q4 = [torch.zeros((B, N), dtype=dt).index_add(1, flat, q).reshape(p1.shape) for q in qw4]
+        pwf = torch.zeros((B, N), dtype=dt).index_add(1, flat, pwfw).reshape(p1.shape)
+        mask = torch.zeros(N, dtype=dt).index_add(0, flat, torch.ones(nw, dtype=dt)).reshape(cfg.D, cfg.H, cfg.W)
+    qfg, qdg, qfo, qvo = q4
+
+    # chord slopes                                                           :465-466
+    dpc = p1 - p0
+    dSg = _dnn(sg1 - sg0, dpc)
+    dSo = _dnn(so1 - so0, dpc)
+    # product-rule PVT derivatives                                           :506-514
+    dRsinvBo = (Rs0 * dinvBo0) + (invBo0 * dRs0)
+    dRvinvBg = (Rv0 * dinvBg0) + (invBg0 * dRv0)
+
+    # neighbours and face values
+    def faces(X):                                                            # :517-525
+        return dict(W=(X + _nbr(X, -1, -1)) / 2.0, E=(_nbr(X, -1, +1) + X) / 2.0,
+                    S=(X + _nbr(X, -2, -1)) / 2.0, N=(_nbr(X, -2, +1) + X) / 2.0,
+                    D=(X + _nbr(X, -3, -1)) / 2.0, U=(_nbr(X, -3, +1) + X) / 2.0)
+    pn = dict(W=_nbr(p1, -1, -1), E=_nbr(p1, -1, +1), S=_nbr(p1, -2, -1), N=_nbr(p1, -2, +1),
+              D=_nbr(p1, -3, -1), U=_nbr(p1, -3, +1))
+    # potentials as written: "plus" faces nbr - cell, "minus" faces cell - nbr      :538-541
+    pot = dict(E=pn["E"] - p1, W=p1 - pn["W"], N=pn["N"] - p1, S=p1 - pn["S"], U=pn["U"] - p1, D=p1 - pn["D"])
+    off = dict(W=(-1, -1), E=(-1, +1), S=(-2, -1), N=(-2, +1), D=(-3, -1), U=(-3, +1))
+
+    def upstream(kr):                                                        # :543-551 (selects carry no gradient)
+        out = {}
+        for f in "WESNDU":
+            le = (pot[f] <= 0).to(dt)
+            gt = (pot[f] > 0).to(dt)
+            out[f] = le * kr + gt * _nbr(kr, *off[f])
+        return out
+    krg_f, kro_f = upstream(krgo1), upstream(krog1)
+    fMgg, fMoo, fMog, fMgo = faces(Mgg), faces(Moo), faces(Mog), faces(Mgo)
+    kf = dict(W=st["kW"], E=st["kE"], S=st["kS"], N=st["kN"], D=st["kD"], U=st["kU"])
+    idl = dict(W=1.0 / dx, E=1.0 / dx, S=1.0 / dy, N=1.0 / dy, D=1.0 / dz, U=1.0 / dz)
+
+    def coef(kr_f, M_f):                                                     # :563-583
+        return {f: C * kf[f] * (kr_f[f] * M_f[f]) * idl[f] * idl[f] for f in "WESNDU"}
+    agg, ago, aoo, aog = coef(krg_f, fMgg), coef(kro_f, fMgo), coef(kro_f, fMoo), coef(krg_f, fMog)
+
+    phicf = phi * cf
+    cprgg, cprgo, cproo, cprog = phicf * invBg0, phicf * RsinvBo0, phicf * invBo0, phicf * RvinvBg0   # :557-560
+    idt = 1.0 / (Dc * d1)
+    cpgg = idt * ((phi * invBg1 * dSg) + sg0 * ((phi * dinvBg0) + cprgg)) * dpc                        # :572
+    cpgo = idt * ((phi * RsinvBo1 * dSo) + so0 * ((phi * dRsinvBo) + cprgo)) * dpc                     # :573
+    cpoo = idt * ((phi * invBo1 * dSo) + so0 * ((phi * dinvBo0) + cproo)) * dpc                        # :585
+    cpog = idt * ((phi * RvinvBg1 * dSg) + sg0 * ((phi * dRvinvBg) + cprog)) * dpc                     # :586
+
+    def divq(a, q):                                                          # :590-611
+        s = (-a["W"] * pn["W"]) + (-a["S"] * pn["S"]) + ((a["W"] + a["S"] + a["E"] + a["N"]) * p1) \
+            + (-a["E"] * pn["E"]) + (-a["N"] * pn["N"])
+        s = s + ((a["D"] * (p1 - pn["D"])) + (a["U"] * (p1 - pn["U"])))      # 3-D extension, == 0 for Nz = 1
+        s = s + (q / dv)
+        return dv * s
+    divq_gg, divq_go, divq_oo, divq_og = divq(agg, qfg), divq(ago, qdg), divq(aoo, qfo), divq(aog, qvo)
+    dom_gg = divq_gg + dv * cpgg                                             # :597-600
+    dom_go = divq_go + dv * cpgo
+    dom_oo = divq_oo + dv * cpoo                                             # :614-620
+    dom_og = divq_og + dv * cpog
+    dom = (dom_gg + dom_go) + (dom_oo + dom_og)                              # :638
+    trn = trn_g + trn_o                                                      # :637
+    ibc = mask * ((divq_gg + divq_go) + (divq_oo + divq_og))                 # :650
+    mfac = dv * idt * phi                                                    # :655-659
+    mbc_gg = mfac * ((sg1 * invBg1) - (sg0 * invBg0))
+    mbc_go = mfac * ((so1 * RsinvBo1) - (so0 * RsinvBo0))
+    mbc_oo = mfac * ((so1 * invBo1) - (so0 * invBo0))
+    mbc_og = mfac * ((sg1 * RvinvBg1) - (sg0 * RvinvBg0))
+    sm = lambda x: x.sum(dim=(1, 2, 3))
+    mbc_g = (-sm(qfg + qdg)) - sm(mbc_gg + mbc_go)                           # :661
+    mbc_o = (-sm(qfo + qvo)) - sm(mbc_oo + mbc_og)                           # :662
+    mbc = mbc_g + mbc_o                                                      # :665
+    return dict(dom=dom, ibc=ibc, mbc=mbc, cmbc=trn, divq=(divq_gg + divq_go) + (divq_oo + divq_og), q4=q4, pwf=pwf,
+                qw4=qw4, pwfw=pwfw, krog1=krog1, krgo1=krgo1, mask=mask,
+                parts=dict(divq_gg=divq_gg, divq_go=divq_go, divq_oo=divq_oo, divq_og=divq_og,
+                           cpgg=cpgg, cpgo=cpgo, cpoo=cpoo, cpog=cpog, trn_g=trn_g, trn_o=trn_o))
+
+
+def gc_loss_terms(res) -> torch.Tensor:
+    """SSE per term (physics_loss.py:787-807): dom, ibc, mbc and cmbc (= truncation term, :680)."""
+    z = torch.zeros((), dtype=res["dom"].dtype)
+    return torch.stack([(res["dom"] ** 2).sum(), (res["ibc"] ** 2).sum(), (res["mbc"] ** 2).sum(), z, z, z, z,
+                        (res["cmbc"] ** 2).sum()])
+
+
+def gc_counts(cfg: OracleConfig, B: int) -> np.ndarray:
+    n = B * cfg.D * cfg.H * cfg.W
+    return np.array([n, n, B, 0, 0, 0, 0, n], dtype=np.float64)
+
+
+def gc_forward_backward(cfg, tab, kx, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t_days, sample_real, weights,
+                        dtype=torch.float32):
+    """Loss terms and the gradient of sum_k weights[k]*SSE_k w.r.t. p0,p1,sg0,sg1,so0,so1,dt1,dt2."""
+    tt = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype).clone().requires_grad_(True)
+    ins = [tt(a) for a in (p0, p1, sg0, sg1, so0, so1, dt1, dt2)]
+    kxt = torch.as_tensor(np.asarray(kx), dtype=dtype)
+    res = gc_residual(cfg, tab, kxt, *ins, t_days, sample_real, dtype=dtype)
+    terms = gc_loss_terms(res)
+    wt = torch.as_tensor(np.asarray(weights, dtype=np.float64), dtype=dtype)
+    loss = (terms * wt).sum()
+    grads = torch.autograd.grad(loss, ins, allow_unused=True)
+    out = dict(dom=res["dom"].detach().numpy(), ibc=res["ibc"].detach().numpy(), mbc=res["mbc"].detach().numpy(),
+               cmbc=res["cmbc"].detach().numpy(), terms=terms.detach().numpy(), loss=float(loss.detach()))
+    if res["qw4"] is not None:
+        out["qw4"] = np.stack([q.detach().numpy() for q in res["qw4"]])
+        out["pwfw"] = res["pwfw"].detach().numpy()
+    for name, g, ref in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2"), grads, ins):
+        out[name] = (torch.zeros_like(ref) if g is None else g).numpy()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # (de)normalisation  (data_processing/data_processing_utils.py:1065-1183)
 # --------------------------------------------------------------------------------------------
 def denorm_linear(x, vmin, vmax, lo=-1.0, hi=1.0, dtype=np.float32):
