@@ -28,6 +28,7 @@ SRM_FLAG_SAVE_FOR_BACKWARD = 1
 EXPORTS = (
     "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
     "srm_pvt_eval", "srm_denormalize_log", "srm_selftest_rounding", "srm_wells", "srm_forward", "srm_backward",
+    "srm_relperm", "srm_forward_gc", "srm_backward_gc",
 )
 
 
@@ -53,6 +54,8 @@ class SrmConfig(C.Structure):
         ("use_blocking_factor", C.c_int32), ("n_intervals", C.c_int32),
         ("numerics", C.c_int32), ("tde_in_dom", C.c_int32),
         ("pvt_lut", C.c_int32), ("lut_p_lo", C.c_float), ("lut_p_hi", C.c_float),
+        ("Swmin", C.c_float), ("Sorg", C.c_float), ("Sgc", C.c_float), ("Socr", C.c_float),
+        ("kro_Somax", C.c_float), ("krg_Sorg", C.c_float), ("krg_Swmin", C.c_float), ("nog", C.c_float), ("ng", C.c_float),
     ]
 
 
@@ -93,6 +96,12 @@ def load_library(path: Optional[str] = None):
     lib.srm_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
     lib.srm_backward.restype = C.c_int
     lib.srm_backward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, i32, vp]
+    lib.srm_relperm.restype = C.c_int
+    lib.srm_relperm.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.srm_forward_gc.restype = C.c_int
+    lib.srm_forward_gc.argtypes = [vp, i32, i32] + [vp] * 11 + [vp] * 4 + [vp, C.c_size_t, i32, vp]
+    lib.srm_backward_gc.restype = C.c_int
+    lib.srm_backward_gc.argtypes = [vp, i32, i32] + [vp] * 11 + [vp] + [vp] * 8 + [vp, C.c_size_t, i32, vp]
     if lib.srm_version() != SRM_ABI_VERSION:
         raise RuntimeError(f"libsrm_physics ABI {lib.srm_version()} != binding {SRM_ABI_VERSION}")
     if path == LIB_PATH:
@@ -119,7 +128,8 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
                 knots: np.ndarray, spline_w: np.ndarray, spline_v: np.ndarray, spline_order: int,
                 p_min: float, p_max: float, wells: Sequence[dict], use_blocking_factor: bool, n_intervals: int,
                 numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG, pvt_lut: bool = False,
-                lut_range: Optional[Sequence[float]] = None):
+                lut_range: Optional[Sequence[float]] = None, end_points: Optional[dict] = None,
+                corey_exponents: Optional[dict] = None):
     """Fill an SrmConfig; returns (cfg, keepalive) -- keepalive owns the host arrays cfg points into."""
     knots = np.ascontiguousarray(knots, dtype=np.float32)
     spline_w = np.ascontiguousarray(spline_w, dtype=np.float32)
@@ -138,4 +148,9 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
         n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)),
         pvt_lut=int(bool(pvt_lut)), lut_p_lo=float(lut_range[0]) if lut_range else 0.0,
         lut_p_hi=float(lut_range[1]) if lut_range else 0.0)
+    if end_points is not None:
+        for k in ("Swmin", "Sorg", "Sgc", "Socr", "kro_Somax", "krg_Sorg", "krg_Swmin"):
+            setattr(cfg, k, float(end_points[k]))
+        cfg.nog = float(corey_exponents["nog"])
+        cfg.ng = float(corey_exponents["ng"])
     return cfg, (knots, spline_w, spline_v, warr)

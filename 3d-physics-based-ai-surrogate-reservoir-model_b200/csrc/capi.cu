@@ -51,7 +51,14 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     srm_set_error("srm_create: bad grid %d x %d x %d", cfg->D, cfg->H, cfg->W);
     return SRM_ERR_INVALID;
   }
-  if (cfg->fluid_type != SRM_FLUID_DG) { srm_set_error("srm_create: only SRM_FLUID_DG is implemented"); return SRM_ERR_INVALID; }
+  if (cfg->fluid_type != SRM_FLUID_DG && cfg->fluid_type != SRM_FLUID_GC) { srm_set_error("srm_create: unknown fluid_type %d", cfg->fluid_type); return SRM_ERR_INVALID; }
+  if (cfg->fluid_type == SRM_FLUID_GC) {
+    if (cfg->n_props != 7) { srm_set_error("srm_create: SRM_FLUID_GC needs the 7 GC properties (InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro), got %d", cfg->n_props); return SRM_ERR_INVALID; }
+    if (cfg->numerics != SRM_NUMERICS_REFERENCE) { srm_set_error("srm_create: SRM_FLUID_GC is built for SRM_NUMERICS_REFERENCE only"); return SRM_ERR_INVALID; }
+    if (cfg->use_blocking_factor) { srm_set_error("srm_create: the GC blocking-factor integral (well_rate_bhp_Subclassed.py:897-911) is not built"); return SRM_ERR_INVALID; }
+    if (cfg->pvt_lut) { srm_set_error("srm_create: pvt_lut is not built for SRM_FLUID_GC yet"); return SRM_ERR_INVALID; }
+    if (cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
+  }
   if (cfg->pvt_method != SRM_PVT_SPLINE) { srm_set_error("srm_create: only SRM_PVT_SPLINE is implemented"); return SRM_ERR_INVALID; }
   if (cfg->n_knots < 2 || cfg->n_knots > SRM_MAXK || cfg->n_props < 2 || cfg->n_props > SRM_MAXP ||
       !cfg->knots || !cfg->spline_w || !cfg->spline_v) {
@@ -110,6 +117,17 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   P.tde_in_dom = cfg->tde_in_dom;
   P.use_blk = cfg->use_blocking_factor; P.n_int = cfg->n_intervals;
   P.n_knots = cfg->n_knots; P.order = cfg->spline_order; P.n_props = cfg->n_props;
+  // SCAL: constants formed in fp32 like relative_permeability.py:58-68
+  P.fluid = cfg->fluid_type;
+  P.swmin = cfg->Swmin; P.sorg = cfg->Sorg; P.sgc = cfg->Sgc;
+  P.kro_somax = cfg->kro_Somax; P.krg_sorg = cfg->krg_Sorg; P.krg_swmin = cfg->krg_Swmin;
+  P.nog = cfg->nog; P.ng = cfg->ng;
+  P.kr_den_o = (1.0f - cfg->Swmin) - cfg->Sorg;
+  P.kr_den_g = ((1.0f - cfg->Sgc) - cfg->Swmin) - cfg->Sorg;
+  P.kr_so_zero = cfg->Swmin + std::max(cfg->Sorg, cfg->Socr);
+  P.kr_sg_full = 1.0f - (cfg->Swmin + cfg->Sorg);
+  auto as_int = [](float e) { return (e >= 1.f && e <= 16.f && e == std::floor(e)) ? (int)e : 0; };
+  P.nog_i = as_int(cfg->nog); P.ng_i = as_int(cfg->ng);
   for (int i = 0; i < cfg->n_knots; ++i) {
     P.c[i] = cfg->knots[i];
     P.c2[i] = cfg->knots[i] * cfg->knots[i];
@@ -190,6 +208,13 @@ int srm_selftest_rounding(int32_t device, int64_t n, uint64_t seed, int64_t* mis
   return srm_launch_selftest_rounding(n, seed, mismatches, (cudaStream_t)stream);
 }
 
+int srm_relperm(const SrmHandle* h, int64_t n, const float* sg, float* krog, float* krgo, float* dkrog, float* dkrgo, void* stream) {
+  if (!h || n < 0 || (n > 0 && !sg)) { srm_set_error("srm_relperm: bad argument"); return SRM_ERR_INVALID; }
+  if (!(h->dev.kr_den_o > 0.f) || !(h->dev.kr_den_g > 0.f)) { srm_set_error("srm_relperm: the handle carries no SCAL end points"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  return srm_launch_relperm(h, n, sg, krog, krgo, dkrog, dkrgo, (cudaStream_t)stream);
+}
+
 static int check_batch(const SrmHandle* h, int32_t B, int32_t R, const char* who) {
   if (!h) { srm_set_error("%s: null handle", who); return SRM_ERR_INVALID; }
   if (B < 1 || R < 1 || B > 65535 || R > SRM_MAXR) { srm_set_error("%s: B=%d (1..65535), R=%d (1..%d)", who, B, R, SRM_MAXR); return SRM_ERR_INVALID; }
@@ -233,6 +258,7 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
     srm_set_error("srm_forward: null argument");
     return SRM_ERR_INVALID;
   }
+  if (h->cfg.fluid_type != SRM_FLUID_DG) { srm_set_error("srm_forward: the handle is not dry gas (use srm_forward_gc)"); return SRM_ERR_INVALID; }
   const SrmWs ws = carve(h, workspace, B, R);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
@@ -269,6 +295,7 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
     srm_set_error("srm_backward: null argument");
     return SRM_ERR_INVALID;
   }
+  if (h->cfg.fluid_type != SRM_FLUID_DG) { srm_set_error("srm_backward: the handle is not dry gas (use srm_backward_gc)"); return SRM_ERR_INVALID; }
   const SrmWs ws = carve(h, workspace, B, R);
   if (ws.bytes > workspace_bytes) {
     srm_set_error("srm_backward: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
@@ -293,6 +320,73 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
        : mode == SRM_WS_REF_FUSED ? srm_backward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
           : srm_backward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s);
   return rc;
+}
+
+int srm_forward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                   const float* p0, const float* p1, const float* sg0, const float* sg1, const float* so0,
+                   const float* so1, const float* dt1, const float* dt2, const float* t1, float* terms_out,
+                   float* dom_out, float* q4w_out, float* pwfw_out, void* workspace, size_t workspace_bytes,
+                   int32_t flags, void* stream) {
+  int rc = check_batch(h, B, R, "srm_forward_gc");
+  if (rc) return rc;
+  if (!kx || !p0 || !p1 || !sg0 || !sg1 || !so0 || !so1 || !dt1 || !dt2 || !t1 || !terms_out || !workspace) {
+    srm_set_error("srm_forward_gc: null argument");
+    return SRM_ERR_INVALID;
+  }
+  if (h->cfg.fluid_type != SRM_FLUID_GC) { srm_set_error("srm_forward_gc: the handle is not gas condensate"); return SRM_ERR_INVALID; }
+  const SrmWs ws = carve(h, workspace, B, R);
+  if (ws.bytes > workspace_bytes) {
+    srm_set_error("srm_forward_gc: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return SRM_ERR_WORKSPACE;
+  }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool save = (flags & SRM_FLAG_SAVE_FOR_BACKWARD) != 0;
+  h->st_valid = 0;
+  rc = srm_forward_gc_impl(h, B, R, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
+  if (rc) return rc;
+  const int nw = h->dev.n_wells;
+  if (nw) {
+    const size_t wt = (size_t)B * nw;
+    if (q4w_out)
+      for (int X = 0; X < 4; ++X) { rc = srm_launch_unsort_wells(h, B, ws.gc_wells + X * wt, q4w_out + X * wt, s); if (rc) return rc; }
+    if (pwfw_out) { rc = srm_launch_unsort_wells(h, B, ws.pwfw, pwfw_out, s); if (rc) return rc; }
+  }
+  if (save) { h->st_ws = workspace; h->st_p0 = p0; h->st_p1 = p1; h->st_kx = kx; h->st_B = B; h->st_valid = 1; }
+  return SRM_OK;
+}
+
+int srm_backward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                    const float* p0, const float* p1, const float* sg0, const float* sg1, const float* so0,
+                    const float* so1, const float* dt1, const float* dt2, const float* t1, const float* dterms,
+                    float* gp0, float* gp1, float* gsg0, float* gsg1, float* gso0, float* gso1, float* gdt1,
+                    float* gdt2, void* workspace, size_t workspace_bytes, int32_t flags, void* stream) {
+  int rc = check_batch(h, B, R, "srm_backward_gc");
+  if (rc) return rc;
+  (void)flags;
+  if (!kx || !p0 || !p1 || !sg0 || !sg1 || !so0 || !so1 || !dt1 || !dt2 || !t1 || !dterms || !gp0 || !gp1 || !gsg0 || !gsg1 ||
+      !gso0 || !gso1 || !gdt1 || !gdt2 || !workspace) {
+    srm_set_error("srm_backward_gc: null argument");
+    return SRM_ERR_INVALID;
+  }
+  if (h->cfg.fluid_type != SRM_FLUID_GC) { srm_set_error("srm_backward_gc: the handle is not gas condensate"); return SRM_ERR_INVALID; }
+  const SrmWs ws = carve(h, workspace, B, R);
+  if (ws.bytes > workspace_bytes) {
+    srm_set_error("srm_backward_gc: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    return SRM_ERR_WORKSPACE;
+  }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool have = h->st_valid && h->st_ws == workspace && h->st_p0 == p0 && h->st_p1 == p1 && h->st_kx == kx && h->st_B == B;
+  if (!have) {
+    float* terms_tmp = nullptr;
+    SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
+    rc = srm_forward_gc_impl(h, B, R, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
+    cudaFreeAsync(terms_tmp, s);
+    if (rc) return rc;
+  }
+  return srm_backward_gc_impl(h, B, R, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms, gp0, gp1, gsg0, gsg1,
+                              gso0, gso1, gdt1, gdt2, ws, s);
 }
 
 }  // extern "C"

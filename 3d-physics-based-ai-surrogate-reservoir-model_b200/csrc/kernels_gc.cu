@@ -1,0 +1,701 @@
+// Gas-condensate (two-phase gas-oil, fluid_type 'GC') path: physics_error_gas_oil and its gradient.
+//
+//   k_relperm         RelativePermeability.compute_krog_krgo          relative_permeability.py:49-75
+//   k_stage_gc        PVTLayer (7 properties) at both time levels,     PVT_Layer_Subclassed.py:146-216
+//                     mobility products, relative permeabilities       physics_loss.py:336-391,457
+//   k_wells_gc        WellRatesPressure, GC branch                     well_rate_bhp_Subclassed.py:614-724,727-837,963-1034
+//   k_resid_fwd_gc    residual, truncation term, material balance      physics_loss.py:419-441,465-665
+//   k_resid_adj_gc    hand-derived adjoint (tape.gradient, physics_loss.py:849-859)
+//   k_ibc_adj_gc      inner-boundary (well-cell) part of the adjoint
+//
+// Numerics: the reference's fp32 op order, explicitly rounded (no FMA contraction) in every forward
+// quantity, as in kernels_ref.cu; tf.pow with the integer Corey exponents is the left-to-right product the
+// oracle pins.  One thread per cell; PVT and the per-cell products are staged through the workspace
+// (SRM_GC_NFIELDS fields), neighbours re-read through L1/L2.  This first GC build evaluates the 37-term
+// spline per cell (7 properties): it is compute bound; the exact tabulation of kernels_ref2.cu is the
+// next step for this path.
+#include <math_constants.h>
+#include <cstring>
+#include "pvt_ref.cuh"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// staged fields (index into ws.gc, each [B*N])
+enum {
+  F_A0 = 0, F_B0, F_RS0, F_RV0, F_DA0, F_DB0, F_DRS0, F_DRV0,        // n0: invBg, invBo, Rs, Rv and d/dp (unmasked)
+  F_D2A0, F_D2B0, F_D2RS0, F_D2RV0,                                  // n0: d2/dp2 (masked by the clamp)      [adjoint]
+  F_MGG, F_MOO, F_MGO, F_MOG, F_KRG, F_KRO,                          // n1: neighbour-visible
+  F_A1, F_B1, F_R1, F_V1,                                            // n1: invBg, invBo, Rs*invBo, Rv*invBg
+  F_DMG, F_DMO, F_DA1, F_DB1, F_DR1, F_DV1, F_DKRG, F_DKRO,          // n1 derivatives (masked)               [adjoint]
+  F_COUNT
+};
+static_assert(F_COUNT <= SRM_GC_NFIELDS, "workspace carve");
+
+// ---- relative permeability ------------------------------------------------------------------
+__device__ __forceinline__ float pow_pinned(float x, float n, int ni) {
+  if (ni > 0) {
+    float y = x;
+    for (int i = 1; i < ni; ++i) y = __fmul_rn(y, x);
+    return y;
+  }
+  return powf(x, n);
+}
+// d/dx of pow_pinned as the product rule delivers it: n * x^(n-1)
+__device__ __forceinline__ float dpow_pinned(float x, float n, int ni) {
+  if (ni > 0) {
+    float y = 1.f;
+    for (int i = 1; i < ni; ++i) y *= x;
+    return (float)ni * y;
+  }
+  return n * powf(x, n - 1.f);
+}
+// relative_permeability.py:58-73; derivatives follow TF's routing: tf.where picks a branch, tf.minimum /
+// tf.maximum pass the gradient to the first argument on ties.
+__device__ __forceinline__ void corey(const SrmDev& P, float sg, float& krog, float& krgo, float& dkrog, float& dkrgo) {
+  const float so = __fsub_rn(__fsub_rn(1.0f, sg), P.swmin);                              // :58
+  const float xo = __fdiv_rn(__fsub_rn(so, P.sorg), P.kr_den_o);
+  const float xg = __fdiv_rn(__fsub_rn(sg, P.sgc), P.kr_den_g);
+  float ko = __fmul_rn(P.kro_somax, pow_pinned(xo, P.nog, P.nog_i));                     // :59
+  float kg = __fmul_rn(P.krg_sorg, pow_pinned(xg, P.ng, P.ng_i));                        // :60
+  float dko = P.kro_somax * dpow_pinned(xo, P.nog, P.nog_i) * (-1.0f / P.kr_den_o);
+  float dkg = P.krg_sorg * dpow_pinned(xg, P.ng, P.ng_i) * (1.0f / P.kr_den_g);
+  if (so <= P.kr_so_zero) { ko = 0.f; dko = 0.f; }                                       // :67
+  if (sg > P.kr_sg_full) { kg = P.krg_swmin; dkg = 0.f; }                                // :68
+  if (!(ko <= P.kro_somax)) { ko = P.kro_somax; dko = 0.f; }                             // :71 tf.minimum
+  if (!(ko >= 0.f)) { ko = 0.f; dko = 0.f; }                                             //     tf.maximum
+  if (!(kg <= P.krg_swmin)) { kg = P.krg_swmin; dkg = 0.f; }                             // :72
+  if (!(kg >= 0.f)) { kg = 0.f; dkg = 0.f; }
+  krog = ko; krgo = kg; dkrog = dko; dkrgo = dkg;
+}
+
+__global__ void __launch_bounds__(kThreads) k_relperm(const __grid_constant__ SrmDev P, int64_t n, const float* __restrict__ sg,
+                                                      float* __restrict__ krog, float* __restrict__ krgo,
+                                                      float* __restrict__ dkrog, float* __restrict__ dkrgo) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  float ko, kg, dko, dkg;
+  corey(P, sg[g], ko, kg, dko, dkg);
+  if (krog) krog[g] = ko;
+  if (krgo) krgo[g] = kg;
+  if (dkrog) dkrog[g] = dko;
+  if (dkrgo) dkrgo[g] = dkg;
+}
+
+// ---- stage -------------------------------------------------------------------------------------
+template <bool SAVE>
+__global__ void __launch_bounds__(kThreads) k_stage_gc(const __grid_constant__ SrmDev P, int64_t total,
+                                                       const float* __restrict__ p0, const float* __restrict__ p1,
+                                                       const float* __restrict__ sg1, float* __restrict__ F) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  auto out = [&](int f, float v) { F[(int64_t)f * total + g] = v; };
+  float m0, m1;
+  const float x0 = srm_clamp(P, p0[g], m0);
+  const float x1 = srm_clamp(P, p1[g], m1);
+  {
+    float v[2], d[2], d2[2];
+    d2[0] = d2[1] = 0.f;
+    srm_spline_ref<2, true, SAVE>(P, 0, x0, v, d, d2);          // InvBg, InvBo
+    out(F_A0, v[0]); out(F_B0, v[1]); out(F_DA0, d[0]); out(F_DB0, d[1]);
+    if (SAVE) { out(F_D2A0, d2[0] * m0); out(F_D2B0, d2[1] * m0); }
+    srm_spline_ref<2, true, SAVE>(P, 4, x0, v, d, d2);          // Rs, Rv
+    out(F_RS0, v[0]); out(F_RV0, v[1]); out(F_DRS0, d[0]); out(F_DRV0, d[1]);
+    if (SAVE) { out(F_D2RS0, d2[0] * m0); out(F_D2RV0, d2[1] * m0); }
+  }
+  {
+    float v[6], d[6], d2[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = 0.f;
+    srm_spline_ref<6, SAVE, false>(P, 0, x1, v, d, d2);         // InvBg, InvBo, Invug, Invuo, Rs, Rv
+    const float a = v[0], b = v[1], ug = v[2], uo = v[3], rs = v[4], rv = v[5];
+    const float r = __fmul_rn(rs, b), vv = __fmul_rn(rv, a);                     // physics_loss.py:388-389
+    out(F_MGG, __fmul_rn(a, ug));                                                // :386
+    out(F_MOO, __fmul_rn(b, uo));                                                // :387
+    out(F_MGO, __fmul_rn(r, uo));                                                // :390
+    out(F_MOG, __fmul_rn(vv, ug));                                               // :391
+    out(F_A1, a); out(F_B1, b); out(F_R1, r); out(F_V1, vv);
+    float ko, kg, dko, dkg;
+    corey(P, sg1[g], ko, kg, dko, dkg);                                          // :457
+    out(F_KRG, kg); out(F_KRO, ko);
+    if (SAVE) {
+      const float da = d[0] * m1, db = d[1] * m1, dug = d[2] * m1, duo = d[3] * m1, drs = d[4] * m1, drv = d[5] * m1;
+      const float dr = drs * b + rs * db, dvv = drv * a + rv * da;
+      const float dMgg = da * ug + a * dug, dMoo = db * uo + b * duo;
+      const float dMgo = dr * uo + r * duo, dMog = dvv * ug + vv * dug;
+      out(F_DMG, dMgg + dMog); out(F_DMO, dMgo + dMoo);
+      out(F_DA1, da); out(F_DB1, db); out(F_DR1, dr); out(F_DV1, dvv);
+      out(F_DKRG, dkg); out(F_DKRO, dko);
+    }
+  }
+}
+
+// ---- wells: forward-mode numbers carrying d/dp and d/dSg of the connection cell ----------------------
+struct D2 { float v, a, b; };
+__device__ __forceinline__ D2 mk(float v, float a = 0.f, float b = 0.f) { D2 r; r.v = v; r.a = a; r.b = b; return r; }
+__device__ __forceinline__ D2 operator+(D2 x, D2 y) { return mk(__fadd_rn(x.v, y.v), x.a + y.a, x.b + y.b); }
+__device__ __forceinline__ D2 operator-(D2 x, D2 y) { return mk(__fsub_rn(x.v, y.v), x.a - y.a, x.b - y.b); }
+__device__ __forceinline__ D2 operator*(D2 x, D2 y) { return mk(__fmul_rn(x.v, y.v), x.a * y.v + x.v * y.a, x.b * y.v + x.v * y.b); }
+__device__ __forceinline__ D2 operator/(D2 x, D2 y) {
+  const float q = __fdiv_rn(x.v, y.v);
+  return mk(q, (x.a - q * y.a) / y.v, (x.b - q * y.b) / y.v);
+}
+__device__ __forceinline__ D2 dnn2(D2 x, D2 y) { return (y.v == 0.f) ? mk(0.f) : x / y; }       // tf.math.divide_no_nan
+__device__ __forceinline__ D2 min2(D2 x, D2 y) { return (x.v <= y.v) ? x : y; }                  // ties -> first argument
+__device__ __forceinline__ D2 max2(D2 x, D2 y) { return (x.v >= y.v) ? x : y; }
+__device__ __forceinline__ D2 clip2(D2 t, D2 lo, D2 hi) {                                         // tf.clip_by_value
+  const bool below = t.v < lo.v, above = t.v > hi.v;
+  const D2& g = below ? lo : (above ? hi : t);
+  return mk(fmaxf(fminf(t.v, hi.v), lo.v), g.a, g.b);
+}
+
+__global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev P, int32_t B, int32_t R,
+                                                  const float* __restrict__ kx, const int32_t* __restrict__ sample_real,
+                                                  const float* __restrict__ pfield, const float* __restrict__ sgfield,
+                                                  const float* __restrict__ t_days, float* __restrict__ W7,
+                                                  float* __restrict__ pwfw) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = P.n_wells;
+  const int64_t tot = (int64_t)B * nw;
+  if (g >= tot) return;
+  const int b = (int)(g / nw), w = (int)(g % nw);
+  const WellDev wd = P.wells[w];
+  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const float k = kx[(int64_t)r * P.N + wd.cell];
+  const float pv = pfield[(int64_t)b * P.N + wd.cell], sv = sgfield[(int64_t)b * P.N + wd.cell];
+  const float t = t_days[b];
+  const float open = (t >= wd.shut_start && t <= wd.shut_stop) ? 0.f : 1.f;      // welldata_processor.py:349-354
+  // Peaceman                                                  well_rate_bhp_Subclassed.py:782-788
+  const float ky = __fmul_rn(P.kx_ky, k);
+  const float ryx = __fdiv_rn(ky, k), rxy = __fdiv_rn(k, ky);
+  const float num = sqrtf(__fadd_rn(__fmul_rn(sqrtf(ryx), __fmul_rn(P.dx, P.dx)), __fmul_rn(sqrtf(rxy), __fmul_rn(P.dy, P.dy))));
+  const float den = __fadd_rn(powf(ryx, 0.25f), powf(rxy, 0.25f));
+  const float ro = __fdiv_rn(__fmul_rn(0.28f, num), den);
+  float ck = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(6.283185307179586f, wd.hc), k), P.dz), P.C);
+  ck = __fdiv_rn(ck, logf(__fdiv_rn(ro, wd.rw)));
+  const D2 Ck = mk(__fmul_rn(open, ck));
+  // relative permeabilities and PVT at the connection cell      :791-795
+  float ko, kg, dko, dkg;
+  corey(P, sv, ko, kg, dko, dkg);
+  const D2 krog = mk(ko, 0.f, dko), krgo = mk(kg, 0.f, dkg);
+  float m1;
+  const float x1 = srm_clamp(P, pv, m1);
+  float v[6], d[6], d2[6];
+  srm_spline_ref<6, true, false>(P, 0, x1, v, d, d2);
+  const D2 invBg = mk(v[0], d[0] * m1), invBo = mk(v[1], d[1] * m1), invug = mk(v[2], d[2] * m1), invuo = mk(v[3], d[3] * m1),
+           Rs = mk(v[4], d[4] * m1), Rv = mk(v[5], d[5] * m1);
+  const D2 mgg = krgo * invBg * invug;                                           // :802-807
+  const D2 mgo = krog * invBo * invuo * Rs;
+  const D2 moo = krog * invBo * invuo;
+  const D2 mog = krgo * invBg * invug * Rv;
+  const D2 mg = mgg + mgo, mo = moo + mog;
+  const D2 p = mk(pv, 1.f, 0.f), pmin = mk(wd.pwf_min), qt = mk(wd.q_target), zero = mk(0.f), one = mk(1.f), tiny = mk(1e-12f);
+  // ---- _non_iterative_method, blocking factor off (:614-724)
+  const D2 dp_max = (p - pmin) + tiny;                                           // :650
+  const D2 qg_max = Ck * one * mg * dp_max;                                      // :662
+  const D2 qg_opt = max2(min2(qt, qg_max), zero);                                // :666
+  const D2 lam = clip2(dnn2(qg_opt, Ck * one * mg), zero, one);                  // :699
+  const D2 pwf = clip2(p - lam * dp_max, pmin, p);                               // :721-723
+  // ---- _compute_phase_rates (:963-1007)
+  const D2 dp = (p - pwf) + tiny;                                                // :987
+  const D2 qg = max2(min2(qt, Ck * one * mg * dp), zero);                        // :997,1001
+  const D2 qo_target = qg * (one / (Rv + tiny));                                 // :1004
+  const D2 qo = max2(min2(qo_target, Ck * one * mo * dp), zero);                 // :998,1005
+  // ---- _split_condensate_components (:1010-1034)
+  const D2 dg = (mgg + mgo) + tiny, dn = (moo + mog) + tiny;
+  const D2 qgg = qg * (mgg / dg), qgo = qg * (mgo / dg), qoo = qo * (moo / dn), qog = qo * (mog / dn);
+  W7[0 * tot + g] = qgg.v; W7[1 * tot + g] = qgo.v; W7[2 * tot + g] = qoo.v; W7[3 * tot + g] = qog.v;
+  W7[4 * tot + g] = (qgg.a + qgo.a) + (qoo.a + qog.a);       // d(sum of the four rates)/dp
+  W7[5 * tot + g] = (qgg.b + qgo.b) + (qoo.b + qog.b);       // d(sum)/dSg
+  pwfw[g] = pwf.v;
+}
+
+// ---- residual ----------------------------------------------------------------------------------
+struct CellIdx { int i, j, k; int n[6]; };   // neighbour cells W,E,S,N,D,U with edge replication
+__device__ __forceinline__ CellIdx cell_index(const SrmDev& P, int c) {
+  CellIdx x;
+  x.i = c % P.W;
+  const int t = c / P.W;
+  x.j = t % P.H;
+  x.k = t / P.H;
+  const int HW = P.H * P.W;
+  x.n[0] = (x.i > 0) ? c - 1 : c;
+  x.n[1] = (x.i < P.W - 1) ? c + 1 : c;
+  x.n[2] = (x.j > 0) ? c - P.W : c;
+  x.n[3] = (x.j < P.H - 1) ? c + P.W : c;
+  x.n[4] = (x.k > 0) ? c - HW : c;
+  x.n[5] = (x.k < P.D - 1) ? c + HW : c;
+  return x;
+}
+__device__ __forceinline__ float harm_ref(float kc, float kn) {                  // physics_loss.py:283-284
+  return __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, kc), kn), __fadd_rn(kc, kn));
+}
+// C*k_f for the six faces (W,E,S,N,D,U)
+__device__ __forceinline__ void face_perms(const SrmDev& P, const float* __restrict__ kr, int c, const CellIdx& ix, float (&ckf)[6]) {
+  const float kc = kr[c];
+  const float kyc = __fmul_rn(P.kx_ky, kc), kzc = __fmul_rn(P.kv_kh, kc);
+  ckf[0] = __fmul_rn(P.C, harm_ref(kc, kr[ix.n[0]]));
+  ckf[1] = __fmul_rn(P.C, harm_ref(kr[ix.n[1]], kc));
+  ckf[2] = __fmul_rn(P.C, harm_ref(kyc, __fmul_rn(P.kx_ky, kr[ix.n[2]])));
+  ckf[3] = __fmul_rn(P.C, harm_ref(__fmul_rn(P.kx_ky, kr[ix.n[3]]), kyc));
+  ckf[4] = __fmul_rn(P.C, harm_ref(kzc, __fmul_rn(P.kv_kh, kr[ix.n[4]])));
+  ckf[5] = __fmul_rn(P.C, harm_ref(__fmul_rn(P.kv_kh, kr[ix.n[5]]), kzc));
+}
+
+struct GcFwd {
+  const float* kx; const int32_t* sample_real;
+  const float* p0; const float* p1; const float* sg0; const float* sg1; const float* so0; const float* so1;
+  const float* dt1; const float* dt2;
+  const float* F; const float* W7;
+  float* divqw; float* dom; float* dom_out;
+  double* sse; double* s_mg; double* s_qg; double* s_mo; double* s_qo;
+  int32_t B, R;
+};
+
+__global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
+  __shared__ double red[7 * 32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int64_t total = (int64_t)A.B * P.N;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // dom^2, ibc^2, trn^2, sum mg cells, sum mo cells, sum qg, sum qo
+  if (c < P.N) {
+    const int64_t base = (int64_t)b * P.N;
+    auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
+    const CellIdx ix = cell_index(P, c);
+    const float d1 = A.dt1[b], d2 = A.dt2[b];
+    const float p0 = A.p0[base + c], p1 = A.p1[base + c];
+    const float sg0 = A.sg0[base + c], sg1 = A.sg1[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
+    float ckf[6];
+    face_perms(P, A.kx + (int64_t)r * P.N, c, ix, ckf);
+    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    const float Mc[4] = {F(F_MGG, c), F(F_MGO, c), F(F_MOO, c), F(F_MOG, c)};      // gg, go, oo, og
+    const float krg_c = F(F_KRG, c), kro_c = F(F_KRO, c);
+    float pn[6], a[4][6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      const int cn = ix.n[f];
+      pn[f] = A.p1[base + cn];
+      // potentials as written (physics_loss.py:538-541): "plus" faces nbr - cell, "minus" faces cell - nbr
+      const float pot = (f & 1) ? __fsub_rn(pn[f], p1) : __fsub_rn(p1, pn[f]);
+      const bool own = pot <= 0.f;                                                // :543-551
+      const float krg_f = own ? krg_c : F(F_KRG, cn), kro_f = own ? kro_c : F(F_KRO, cn);
+      const float Mn[4] = {F(F_MGG, cn), F(F_MGO, cn), F(F_MOO, cn), F(F_MOG, cn)};
+#pragma unroll
+      for (int X = 0; X < 4; ++X) {
+        const float Mf = __fmul_rn(__fadd_rn(Mc[X], Mn[X]), 0.5f);                // :517-525
+        const float kr = (X == 0 || X == 3) ? krg_f : kro_f;                      // gg, og: gas phase; go, oo: oil phase
+        a[X][f] = __fmul_rn(__fmul_rn(__fmul_rn(ckf[f], __fmul_rn(kr, Mf)), idl[f]), idl[f]);   // :563-583
+      }
+    }
+    // wells in this cell (scatter_nd sums duplicates)
+    float q4[4] = {0.f, 0.f, 0.f, 0.f}, mask = 0.f;
+    int wfirst = 0;
+    const int64_t wt = (int64_t)A.B * P.n_wells;
+    if (P.n_wells > 0) {
+      wfirst = well_lower_bound(P, c);
+      for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) {
+#pragma unroll
+        for (int X = 0; X < 4; ++X) q4[X] = __fadd_rn(q4[X], A.W7[X * wt + (int64_t)b * P.n_wells + w]);
+        mask += 1.f;
+      }
+    }
+    // divergence of each component                               physics_loss.py:590-611
+    float divq[4];
+#pragma unroll
+    for (int X = 0; X < 4; ++X) {
+      float s = __fadd_rn(-__fmul_rn(a[X][0], pn[0]), -__fmul_rn(a[X][2], pn[2]));
+      const float asum = __fadd_rn(__fadd_rn(__fadd_rn(a[X][0], a[X][2]), a[X][1]), a[X][3]);
+      s = __fadd_rn(s, __fmul_rn(asum, p1));
+      s = __fadd_rn(s, -__fmul_rn(a[X][1], pn[1]));
+      s = __fadd_rn(s, -__fmul_rn(a[X][3], pn[3]));
+      s = __fadd_rn(s, __fadd_rn(__fmul_rn(a[X][4], __fsub_rn(p1, pn[4])), __fmul_rn(a[X][5], __fsub_rn(p1, pn[5]))));   // 3-D extension
+      s = __fadd_rn(s, __fdiv_rn(q4[X], P.dv));
+      divq[X] = __fmul_rn(P.dv, s);
+    }
+    // accumulation                                               physics_loss.py:465-466,506-514,557-586
+    const float A0 = F(F_A0, c), B0 = F(F_B0, c), Rs0 = F(F_RS0, c), Rv0 = F(F_RV0, c);
+    const float dA0 = F(F_DA0, c), dB0 = F(F_DB0, c), dRs0 = F(F_DRS0, c), dRv0 = F(F_DRV0, c);
+    const float a1 = F(F_A1, c), b1 = F(F_B1, c), r1 = F(F_R1, c), v1 = F(F_V1, c);
+    const float R0 = __fmul_rn(Rs0, B0), V0 = __fmul_rn(Rv0, A0);                 // :343-344
+    const float dpc = __fsub_rn(p1, p0);
+    const float dSg = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(sg1, sg0), dpc);   // :465
+    const float dSo = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(so1, so0), dpc);   // :466
+    const float dR0 = __fadd_rn(__fmul_rn(Rs0, dB0), __fmul_rn(B0, dRs0));        // :511
+    const float dV0 = __fadd_rn(__fmul_rn(Rv0, dA0), __fmul_rn(A0, dRv0));        // :513
+    const float idt = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
+    auto cpX = [&](float prop1, float dS, float s0, float dprop0, float prop0) {
+      const float cpr = __fmul_rn(P.phicf, prop0);                                // :557-560
+      const float t1 = __fmul_rn(__fmul_rn(P.phi, prop1), dS);
+      const float t2 = __fmul_rn(s0, __fadd_rn(__fmul_rn(P.phi, dprop0), cpr));
+      return __fmul_rn(__fmul_rn(idt, __fadd_rn(t1, t2)), dpc);                   // :572-573,585-586
+    };
+    const float cpgg = cpX(a1, dSg, sg0, dA0, A0), cpgo = cpX(r1, dSo, so0, dR0, R0);
+    const float cpoo = cpX(b1, dSo, so0, dB0, B0), cpog = cpX(v1, dSg, sg0, dV0, V0);
+    const float dom_gg = __fadd_rn(divq[0], __fmul_rn(P.dv, cpgg)), dom_go = __fadd_rn(divq[1], __fmul_rn(P.dv, cpgo));
+    const float dom_oo = __fadd_rn(divq[2], __fmul_rn(P.dv, cpoo)), dom_og = __fadd_rn(divq[3], __fmul_rn(P.dv, cpog));
+    const float dom = __fadd_rn(__fadd_rn(dom_gg, dom_go), __fadd_rn(dom_oo, dom_og));      // :638
+    const float divq_tot = __fadd_rn(__fadd_rn(divq[0], divq[1]), __fadd_rn(divq[2], divq[3]));
+    const float ibc = __fmul_rn(mask, divq_tot);                                  // :650
+    // masses and truncation terms                                physics_loss.py:419-441
+    const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
+    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+    const float rte_d1 = __fdiv_rn(2.5e-8f, d1);                                  // :439-440
+    const float d12 = __fadd_rn(d1, d2);
+    auto trnX = [&](float m0, float m1) {
+      const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(m1, m0), rho1), m0);
+      const float num = __fsub_rn(__fadd_rn(__fmul_rn(d2, m0), __fmul_rn(d1, m2)), __fmul_rn(d12, m1));
+      return __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(num, den)));
+    };
+    const float mg0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(A0, sg0), __fmul_rn(R0, so0)));
+    const float mo0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(B0, so0), __fmul_rn(V0, sg0)));
+    const float mg1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(a1, sg1), __fmul_rn(r1, so1)));
+    const float mo1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(b1, so1), __fmul_rn(v1, sg1)));
+    const float trn = __fadd_rn(trnX(mg0, mg1), trnX(mo0, mo1));                  // :637
+    // material balance summands                                  physics_loss.py:655-662
+    const float mfac = __fmul_rn(__fmul_rn(P.dv, idt), P.phi);
+    const float mb_gg = __fmul_rn(mfac, __fsub_rn(__fmul_rn(sg1, a1), __fmul_rn(sg0, A0)));
+    const float mb_go = __fmul_rn(mfac, __fsub_rn(__fmul_rn(so1, r1), __fmul_rn(so0, R0)));
+    const float mb_oo = __fmul_rn(mfac, __fsub_rn(__fmul_rn(so1, b1), __fmul_rn(so0, B0)));
+    const float mb_og = __fmul_rn(mfac, __fsub_rn(__fmul_rn(sg1, v1), __fmul_rn(sg0, V0)));
+    A.dom[base + c] = dom;
+    if (A.dom_out) A.dom_out[base + c] = dom;
+    if (mask != 0.f)
+      for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq_tot;
+    acc[0] = (double)dom * (double)dom;
+    acc[1] = (double)ibc * (double)ibc;
+    acc[2] = (double)trn * (double)trn;
+    acc[3] = (double)__fadd_rn(mb_gg, mb_go);
+    acc[4] = (double)__fadd_rn(mb_oo, mb_og);
+    acc[5] = (double)__fadd_rn(q4[0], q4[1]);
+    acc[6] = (double)__fadd_rn(q4[2], q4[3]);
+  }
+  block_reduce<7>(acc, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&A.sse[SRM_TERM_DOM], acc[0]);
+    if (acc[1] != 0.0) atomicAdd(&A.sse[SRM_TERM_IBC], acc[1]);
+    atomicAdd(&A.sse[SRM_TERM_CMBC], acc[2]);
+    atomicAdd(&A.s_mg[b], acc[3]);
+    atomicAdd(&A.s_mo[b], acc[4]);
+    if (acc[5] != 0.0) atomicAdd(&A.s_qg[b], acc[5]);
+    if (acc[6] != 0.0) atomicAdd(&A.s_qo[b], acc[6]);
+  }
+}
+
+// mbc_b = (-sum qg - sum mbc_g cells) + (-sum qo - sum mbc_o cells); terms and counts      physics_loss.py:661-665,800-832
+__global__ void k_finalize_fwd_gc(const __grid_constant__ SrmDev P, int32_t B, double* __restrict__ sse,
+                                  const double* __restrict__ s_mg, const double* __restrict__ s_qg,
+                                  const double* __restrict__ s_mo, const double* __restrict__ s_qo,
+                                  float* __restrict__ mbc, float* __restrict__ terms_out) {
+  __shared__ double red[32];
+  double v[1] = {0.0};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float mg = __fsub_rn(-(float)s_qg[b], (float)s_mg[b]);
+    const float mo = __fsub_rn(-(float)s_qo[b], (float)s_mo[b]);
+    const float m = __fadd_rn(mg, mo);
+    mbc[b] = m;
+    v[0] += (double)m * (double)m;
+  }
+  block_reduce<1>(v, red);
+  if (threadIdx.x == 0) {
+    sse[SRM_TERM_MBC] = v[0];
+    const double n = (double)B * (double)P.N;
+    for (int t = 0; t < SRM_N_TERMS; ++t) {
+      terms_out[t] = (float)sse[t];
+      double cnt = 0.0;
+      if (t == SRM_TERM_DOM || t == SRM_TERM_IBC || t == SRM_TERM_CMBC) cnt = n;
+      if (t == SRM_TERM_MBC) cnt = (double)B;
+      terms_out[SRM_N_TERMS + t] = (float)cnt;
+    }
+  }
+}
+
+// ---- adjoint -----------------------------------------------------------------------------------
+struct GcAdj {
+  const float* kx; const int32_t* sample_real;
+  const float* p0; const float* p1; const float* sg0; const float* sg1; const float* so0; const float* so1;
+  const float* dt1; const float* dt2; const float* dterms;
+  const float* F; const float* W7; const float* divqw; const float* dom; const float* mbc;
+  float* gp0; float* gp1; float* gsg0; float* gsg1; float* gso0; float* gso1;
+  double* gdt1_acc; double* gdt2_acc;
+  int32_t B, R;
+};
+
+// per face, seen from cell c with neighbour n: Lc / Ln = sum over the four components of kr_sel * <M>_f as the
+// cell / the neighbour selects the relative permeability; dLc_p, dLn_p = their derivative w.r.t. p1 of c (through
+// <M>_f); dL_s = derivative w.r.t. Sg1 of c of whichever view selects c.
+struct FaceAdj { float Lc, Ln, dLc_p, dLn_p, dLc_s, dLn_s; };
+__device__ __forceinline__ FaceAdj face_adj(bool own, float krg_c, float kro_c, float krg_n, float kro_n, float Mg_c, float Mo_c,
+                                            float Mg_n, float Mo_n, float dMg_c, float dMo_c, float dkrg_c, float dkro_c) {
+  const float hMg = 0.5f * (Mg_c + Mg_n), hMo = 0.5f * (Mo_c + Mo_n);
+  // c's view selects c when own, n's view selects n when own (same potential, see kernels_gc.cu header of this block)
+  const float kg_c = own ? krg_c : krg_n, ko_c = own ? kro_c : kro_n;
+  const float kg_n = own ? krg_n : krg_c, ko_n = own ? kro_n : kro_c;
+  FaceAdj r;
+  r.Lc = kg_c * hMg + ko_c * hMo;
+  r.Ln = kg_n * hMg + ko_n * hMo;
+  r.dLc_p = 0.5f * (kg_c * dMg_c + ko_c * dMo_c);
+  r.dLn_p = 0.5f * (kg_n * dMg_c + ko_n * dMo_c);
+  const float ds = dkrg_c * hMg + dkro_c * hMo;
+  r.dLc_s = own ? ds : 0.f;
+  r.dLn_s = own ? 0.f : ds;
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
+  __shared__ double red[2 * 32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int64_t total = (int64_t)A.B * P.N;
+  double acc2[2] = {0.0, 0.0};
+  if (c < P.N) {
+    const int64_t base = (int64_t)b * P.N;
+    auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
+    const CellIdx ix = cell_index(P, c);
+    const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_trn = A.dterms[SRM_TERM_CMBC];
+    const float d1 = A.dt1[b], d2 = A.dt2[b];
+    const float p0 = A.p0[base + c], p1 = A.p1[base + c];
+    const float sg0 = A.sg0[base + c], sg1 = A.sg1[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
+    const float sc = 2.f * w_dom * A.dom[base + c];          // dL/d dom_c
+    const float smb = 2.f * w_mbc * A.mbc[b];                // dL/d mbc_b
+    float ckf[6];
+    face_perms(P, A.kx + (int64_t)r * P.N, c, ix, ckf);
+    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    const float Mg_c = F(F_MGG, c) + F(F_MOG, c), Mo_c = F(F_MGO, c) + F(F_MOO, c);
+    const float krg_c = F(F_KRG, c), kro_c = F(F_KRO, c);
+    const float dMg_c = F(F_DMG, c), dMo_c = F(F_DMO, c), dkrg_c = F(F_DKRG, c), dkro_c = F(F_DKRO, c);
+    float g1 = 0.f, gs1 = 0.f;
+    // ---- divergence part: gather over the cell's own residual and its six neighbours' residuals
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      const int cn = ix.n[f];
+      if (cn == c) continue;                                 // image face: both views identical, no net contribution
+      const float pn = A.p1[base + cn];
+      const float sn = 2.f * w_dom * A.dom[base + cn];
+      const float pot = (f & 1) ? (pn - p1) : (p1 - pn);
+      const bool own = pot <= 0.f;
+      const FaceAdj fa = face_adj(own, krg_c, kro_c, F(F_KRG, cn), F(F_KRO, cn), Mg_c, Mo_c, F(F_MGG, cn) + F(F_MOG, cn),
+                                  F(F_MGO, cn) + F(F_MOO, cn), dMg_c, dMo_c, dkrg_c, dkro_c);
+      const float Tf = ckf[f] * idl[f] * idl[f];
+      const float dpf = p1 - pn;
+      g1 += Tf * ((sc * fa.Lc - sn * fa.Ln) + dpf * (sc * fa.dLc_p - sn * fa.dLn_p));
+      gs1 += Tf * dpf * (sc * fa.dLc_s - sn * fa.dLn_s);
+    }
+    g1 *= P.dv;
+    gs1 *= P.dv;
+    // ---- local terms
+    float m0;
+    (void)srm_clamp(P, p0, m0);
+    const float A0 = F(F_A0, c), B0 = F(F_B0, c), Rs0 = F(F_RS0, c), Rv0 = F(F_RV0, c);
+    const float dA0 = F(F_DA0, c), dB0 = F(F_DB0, c), dRs0 = F(F_DRS0, c), dRv0 = F(F_DRV0, c);
+    const float d2A0 = F(F_D2A0, c), d2B0 = F(F_D2B0, c), d2Rs0 = F(F_D2RS0, c), d2Rv0 = F(F_D2RV0, c);
+    const float a1 = F(F_A1, c), b1 = F(F_B1, c), r1 = F(F_R1, c), v1 = F(F_V1, c);
+    const float da1 = F(F_DA1, c), db1 = F(F_DB1, c), dr1 = F(F_DR1, c), dv1 = F(F_DV1, c);
+    const float R0 = Rs0 * B0, V0 = Rv0 * A0;
+    const float dR0 = Rs0 * dB0 + B0 * dRs0, dV0 = Rv0 * dA0 + A0 * dRv0;
+    // d/dp0 of the n0 quantities (first derivatives masked by the clamp, second derivatives staged masked)
+    const float pA0 = dA0 * m0, pB0 = dB0 * m0, pR0 = dR0 * m0, pV0 = dV0 * m0;
+    const float pdA0 = d2A0, pdB0 = d2B0;
+    const float pdR0 = 2.f * dRs0 * dB0 * m0 + Rs0 * d2B0 + B0 * d2Rs0;
+    const float pdV0 = 2.f * dRv0 * dA0 * m0 + Rv0 * d2A0 + A0 * d2Rv0;
+    const float idt = 1.0f / (P.Dc * d1);
+    const float dpc = p1 - p0;
+    const float nz = (dpc == 0.f) ? 0.f : 1.f;               // divide_no_nan: the chord-slope terms vanish with dpc
+    const float dSgS = (sg1 - sg0) * nz, dSoS = (so1 - so0) * nz;
+    // acc = dv*idt*( phi*(a1+v1)*dSg*dpc + phi*(r1+b1)*dSo*dpc + dpc*(sg0*Kg + so0*Ko) ),  dS*dpc = S1-S0
+    const float Kg = P.phi * (dA0 + dV0) + P.phicf * (A0 + V0);
+    const float Ko = P.phi * (dR0 + dB0) + P.phicf * (R0 + B0);
+    const float pKg = P.phi * (pdA0 + pdV0) + P.phicf * (pA0 + pV0);
+    const float pKo = P.phi * (pdR0 + pdB0) + P.phicf * (pR0 + pB0);
+    const float sacc = sc * P.dv * idt;
+    g1 += sacc * (P.phi * ((da1 + dv1) * dSgS + (dr1 + db1) * dSoS) + (sg0 * Kg + so0 * Ko));
+    float g0 = sacc * (dpc * (sg0 * pKg + so0 * pKo) - (sg0 * Kg + so0 * Ko));
+    gs1 += sacc * P.phi * (a1 + v1) * nz;
+    float gs0 = sacc * (dpc * Kg - P.phi * (a1 + v1) * nz);
+    float go1 = sacc * P.phi * (r1 + b1) * nz;
+    float go0 = sacc * (dpc * Ko - P.phi * (r1 + b1) * nz);
+    const float acc_tot = P.dv * idt * (P.phi * ((a1 + v1) * dSgS + (r1 + b1) * dSoS) + dpc * (sg0 * Kg + so0 * Ko));
+    // material balance: mbc_b = -sum q - sum mcell
+    const float mfac = P.dv * idt * P.phi;
+    const float mcell = mfac * ((sg1 * a1 - sg0 * A0) + (so1 * r1 - so0 * R0) + (so1 * b1 - so0 * B0) + (sg1 * v1 - sg0 * V0));
+    const float smf = smb * mfac;
+    g1 -= smf * (sg1 * (da1 + dv1) + so1 * (dr1 + db1));
+    g0 += smf * (sg0 * (pA0 + pV0) + so0 * (pR0 + pB0));
+    gs1 -= smf * (a1 + v1);
+    gs0 += smf * (A0 + V0);
+    go1 -= smf * (r1 + b1);
+    go0 += smf * (R0 + B0);
+    // wells in this cell: sum of the four rates enters dom (+) and mbc (-)
+    if (P.n_wells > 0) {
+      const int64_t wt = (int64_t)A.B * P.n_wells;
+      const int first = well_lower_bound(P, c);
+      for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) {
+        const float dqp = A.W7[4 * wt + (int64_t)b * P.n_wells + w], dqs = A.W7[5 * wt + (int64_t)b * P.n_wells + w];
+        g1 += (sc - smb) * dqp;
+        gs1 += (sc - smb) * dqs;
+      }
+    }
+    // truncation term (cmbc): trn = (dv/Dc) * (2*rte/d1 + (Ng + No)/den); the brackets N vanish identically for the
+    // linear extrapolation, so only the explicit time steps carry a gradient (N itself is rounding noise, evaluated in
+    // the forward's op order)
+    {
+      const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
+      const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+      const float rte_d1 = __fdiv_rn(2.5e-8f, d1);
+      const float d12 = __fadd_rn(d1, d2);
+      const float R0f = __fmul_rn(Rs0, B0), V0f = __fmul_rn(Rv0, A0);
+      auto numX = [&](float mm0, float mm1) {
+        const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(mm1, mm0), rho1), mm0);
+        return __fsub_rn(__fadd_rn(__fmul_rn(d2, mm0), __fmul_rn(d1, m2)), __fmul_rn(d12, mm1));
+      };
+      const float mg0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(A0, sg0), __fmul_rn(R0f, so0)));
+      const float mo0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(B0, so0), __fmul_rn(V0f, sg0)));
+      const float mg1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(a1, sg1), __fmul_rn(r1, so1)));
+      const float mo1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(b1, so1), __fmul_rn(v1, sg1)));
+      const float Ng = numX(mg0, mg1), No = numX(mo0, mo1);
+      const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(Ng, den))),
+                                  __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(No, den))));
+      const float st = 2.f * w_trn * trn;
+      const float iden2 = 1.0f / (den * den);
+      const float dE1 = -2.f * 2.5e-8f / (d1 * d1) - (Ng + No) * d2 * iden2;
+      const float dE2 = -(Ng + No) * (d1 + 2.f * d2) * iden2;
+      acc2[0] = (double)(-sc * acc_tot / d1 + smb * (mcell / d1) + st * P.dvDc * dE1);
+      acc2[1] = (double)(st * P.dvDc * dE2);
+    }
+    A.gp0[base + c] = g0;
+    A.gp1[base + c] = g1;
+    A.gsg0[base + c] = gs0;
+    A.gsg1[base + c] = gs1;
+    A.gso0[base + c] = go0;
+    A.gso1[base + c] = go1;
+  }
+  block_reduce<2>(acc2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&A.gdt1_acc[b], acc2[0]);
+    atomicAdd(&A.gdt2_acc[b], acc2[1]);
+  }
+}
+
+// inner-boundary term L_ibc = w_ibc * sum (mask*divq_tot)^2: scatter d divq_tot(c)/d(p1, Sg1) to the well cell and
+// its six neighbours (atomics: neighbouring well cells may hit the same target).
+__global__ void __launch_bounds__(128) k_ibc_adj_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = P.n_wells;
+  if (g >= (int64_t)A.B * nw) return;
+  const int b = (int)(g / nw), w = (int)(g % nw);
+  const int c = P.wells[w].cell;
+  if (w > 0 && P.wells[w - 1].cell == c) return;   // one thread per distinct cell
+  const int64_t wt = (int64_t)A.B * nw;
+  float mask = 0.f, dqp = 0.f, dqs = 0.f;
+  for (int u = w; u < nw && P.wells[u].cell == c; ++u) {
+    mask += 1.f;
+    dqp += A.W7[4 * wt + (int64_t)b * nw + u];
+    dqs += A.W7[5 * wt + (int64_t)b * nw + u];
+  }
+  const float s = 2.f * A.dterms[SRM_TERM_IBC] * mask * mask * A.divqw[g];
+  if (s == 0.f) return;
+  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int64_t total = (int64_t)A.B * P.N, base = (int64_t)b * P.N;
+  auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
+  const CellIdx ix = cell_index(P, c);
+  float ckf[6];
+  face_perms(P, A.kx + (int64_t)r * P.N, c, ix, ckf);
+  const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+  const float p1 = A.p1[base + c];
+  const float Mg_c = F(F_MGG, c) + F(F_MOG, c), Mo_c = F(F_MGO, c) + F(F_MOO, c);
+  const float krg_c = F(F_KRG, c), kro_c = F(F_KRO, c);
+  float self_p = 0.f, self_s = 0.f;
+  for (int f = 0; f < 6; ++f) {
+    const int cn = ix.n[f];
+    if (cn == c) continue;
+    const float pn = A.p1[base + cn];
+    const float pot = (f & 1) ? (pn - p1) : (p1 - pn);
+    const bool own = pot <= 0.f;
+    const float krg_n = F(F_KRG, cn), kro_n = F(F_KRO, cn);
+    const float Mg_n = F(F_MGG, cn) + F(F_MOG, cn), Mo_n = F(F_MGO, cn) + F(F_MOO, cn);
+    const float hMg = 0.5f * (Mg_c + Mg_n), hMo = 0.5f * (Mo_c + Mo_n);
+    const float kg = own ? krg_c : krg_n, ko = own ? kro_c : kro_n;
+    const float L = kg * hMg + ko * hMo;
+    const float Tf = ckf[f] * idl[f] * idl[f] * P.dv;
+    const float dpf = p1 - pn;
+    // divq_tot(c) = dv * sum_f Tf' * L * (p_c - p_n) + sum q
+    self_p += Tf * (L + dpf * 0.5f * (kg * F(F_DMG, c) + ko * F(F_DMO, c)));
+    atomicAdd(&A.gp1[base + cn], s * Tf * (-L + dpf * 0.5f * (kg * F(F_DMG, cn) + ko * F(F_DMO, cn))));
+    if (own) self_s += Tf * dpf * (F(F_DKRG, c) * hMg + F(F_DKRO, c) * hMo);
+    else atomicAdd(&A.gsg1[base + cn], s * Tf * dpf * (F(F_DKRG, cn) * hMg + F(F_DKRO, cn) * hMo));
+  }
+  atomicAdd(&A.gp1[base + c], s * (self_p + dqp));
+  atomicAdd(&A.gsg1[base + c], s * (self_s + dqs));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int srm_launch_relperm(const SrmHandle* h, int64_t n, const float* sg, float* krog, float* krgo, float* dkrog, float* dkrgo, cudaStream_t s) {
+  if (n <= 0) return SRM_OK;
+  k_relperm<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(h->dev, n, sg, krog, krgo, dkrog, dkrgo);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real, const float* p0,
+                        const float* p1, const float* sg0, const float* sg1, const float* so0, const float* so1,
+                        const float* dt1, const float* dt2, const float* t1, float* terms_out, float* dom_out,
+                        const SrmWs& ws, bool save, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  const int64_t total = (int64_t)B * P.N;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse and the four per-sample sums
+  const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
+  if (save) k_stage_gc<true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+  else k_stage_gc<false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  const int64_t nwt = (int64_t)B * P.n_wells;
+  if (nwt > 0) {
+    k_wells_gc<<<(unsigned)((nwt + 127) / 128), 128, 0, s>>>(P, B, R, kx, sample_real, p1, sg1, t1, ws.gc_wells, ws.pwfw);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  GcFwd A;
+  memset(&A, 0, sizeof(A));
+  A.kx = kx; A.sample_real = sample_real; A.p0 = p0; A.p1 = p1; A.sg0 = sg0; A.sg1 = sg1; A.so0 = so0; A.so1 = so1;
+  A.dt1 = dt1; A.dt2 = dt2; A.F = ws.gc; A.W7 = ws.gc_wells; A.divqw = ws.divqw; A.dom = ws.dom; A.dom_out = dom_out;
+  A.sse = ws.sse; A.s_mg = ws.mb_sum; A.s_qg = ws.q_sum; A.s_mo = ws.gdt1_acc; A.s_qo = ws.gdt2_acc;   // the adjoint re-zeroes its accumulators
+  A.B = B; A.R = R;
+  const dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  k_finalize_fwd_gc<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.gdt1_acc, ws.gdt2_acc, ws.mbc, terms_out);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real, const float* p0,
+                         const float* p1, const float* sg0, const float* sg1, const float* so0, const float* so1,
+                         const float* dt1, const float* dt2, const float* t1, const float* dterms, float* gp0, float* gp1,
+                         float* gsg0, float* gsg1, float* gso0, float* gso1, float* gdt1, float* gdt2, const SrmWs& ws,
+                         cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  (void)t1;
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
+  GcAdj A;
+  memset(&A, 0, sizeof(A));
+  A.kx = kx; A.sample_real = sample_real; A.p0 = p0; A.p1 = p1; A.sg0 = sg0; A.sg1 = sg1; A.so0 = so0; A.so1 = so1;
+  A.dt1 = dt1; A.dt2 = dt2; A.dterms = dterms; A.F = ws.gc; A.W7 = ws.gc_wells; A.divqw = ws.divqw; A.dom = ws.dom; A.mbc = ws.mbc;
+  A.gp0 = gp0; A.gp1 = gp1; A.gsg0 = gsg0; A.gsg1 = gsg1; A.gso0 = gso0; A.gso1 = gso1;
+  A.gdt1_acc = ws.gdt1_acc; A.gdt2_acc = ws.gdt2_acc; A.B = B; A.R = R;
+  const dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  const int64_t n = (int64_t)B * P.n_wells;
+  if (n > 0) {
+    k_ibc_adj_gc<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

@@ -39,6 +39,13 @@ struct SrmDev {
   float c2[SRM_MAXK];            // fl(c*c)
   float w[SRM_MAXP][SRM_MAXK];
   float v[SRM_MAXP][2];
+  // SCAL (gas-condensate path): thresholds and denominators formed in fp32 the way relative_permeability.py:58-68 does
+  float swmin, sorg, sgc, kro_somax, krg_sorg, krg_swmin, nog, ng;
+  float kr_den_o, kr_den_g;      // (1-Swmin)-Sorg ; ((1-Sgc)-Swmin)-Sorg
+  float kr_so_zero;              // Swmin + max(Sorg, Socr): krog = 0 at or below
+  float kr_sg_full;              // 1 - (Swmin+Sorg): krgo = krg_Swmin above
+  int32_t nog_i, ng_i;           // integer exponents (0: not integer-valued -> powf)
+  int32_t fluid;
   // exact PVT tabulation (SrmConfig.pvt_lut); lut_n == 0: off
   const float4* lut0;    // [lut_n] {invBg, d/dp, d2/dp2, -} at the fp32 value with bits lut_lo_bits + e
   const float4* lut1;    // [lut_n] {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
@@ -100,6 +107,8 @@ struct SrmWs {
   int32_t* seg;       // [3*(B+1)] (r, offset into grp_list, count)
   int32_t* ctl;       // [8]   ctl[0] = number of segments, ctl[1..2] = work counters
   float* faces;       // fused reference path: static face coefficients [R][face floats]
+  float* gc;          // gas-condensate path: SRM_GC_NFIELDS staged fields [B*N] each, 4+1+2 extra well tables
+  float* gc_wells;    // [7][B*nw]: qgg,qgo,qoo,qog (sorted order), d(sum q)/dp, d(sum q)/dSg, spare
   float* dom;         // field [B*N]
   float* A0;          // reference-order fields [B*N]
   float* A0p;
@@ -114,9 +123,11 @@ struct SrmWs {
 static inline size_t srm_align(size_t x) { return (x + 255) & ~size_t(255); }
 
 // workspace flavours: staged reference order (7 PVT fields), fused reference order (tabulated PVT), closed form
-enum { SRM_WS_REF_STAGED = 0, SRM_WS_REF_FUSED = 1, SRM_WS_CF = 2 };
+enum { SRM_WS_REF_STAGED = 0, SRM_WS_REF_FUSED = 1, SRM_WS_CF = 2, SRM_WS_GC = 3 };
+#define SRM_GC_NFIELDS 32
 size_t srm_ref2_face_floats(const SrmDev& P);
 static inline int srm_ws_mode(const SrmHandle* h) {
+  if (h->cfg.fluid_type == SRM_FLUID_GC) return SRM_WS_GC;
   if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM) return SRM_WS_CF;
   return h->dev.lut_n > 0 ? SRM_WS_REF_FUSED : SRM_WS_REF_STAGED;
 }
@@ -151,6 +162,11 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64
   if (mode == SRM_WS_REF_FUSED) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
   w.dom = (float*)take(fb);
   w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
+  w.gc = w.gc_wells = nullptr;
+  if (mode == SRM_WS_GC) {
+    w.gc_wells = (float*)take(7 * wt);
+    w.gc = (float*)take((size_t)SRM_GC_NFIELDS * fb);
+  }
   if (mode == SRM_WS_REF_STAGED) {
     w.A0 = (float*)take(fb);
     w.A0p = (float*)take(fb);
@@ -188,6 +204,16 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
                       const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                       const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
                       const SrmWs& ws, cudaStream_t s);
+int srm_launch_relperm(const SrmHandle* h, int64_t n, const float* sg, float* krog, float* krgo, float* dkrog, float* dkrgo, cudaStream_t s);
+int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real, const float* p0,
+                        const float* p1, const float* sg0, const float* sg1, const float* so0, const float* so1,
+                        const float* dt1, const float* dt2, const float* t1, float* terms_out, float* dom_out,
+                        const SrmWs& ws, bool save, cudaStream_t s);
+int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real, const float* p0,
+                         const float* p1, const float* sg0, const float* sg1, const float* so0, const float* so1,
+                         const float* dt1, const float* dt2, const float* t1, const float* dterms, float* gp0, float* gp1,
+                         float* gsg0, float* gsg1, float* gso0, float* gso1, float* gdt1, float* gdt2, const SrmWs& ws,
+                         cudaStream_t s);
 int srm_forward_ref(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                     const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                     float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s);

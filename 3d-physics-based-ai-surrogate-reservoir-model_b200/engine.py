@@ -35,15 +35,17 @@ class SrmPhysics:
         self.tables = tables
         self.device = torch.device("cuda", device)
         self.numerics = numerics
-        if spec.fluid_type != "DG":
-            raise NotImplementedError("only the dry-gas (DG) path is built")
+        if spec.fluid_type not in ("DG", "GC"):
+            raise ValueError(f"fluid_type {spec.fluid_type!r}: 'DG' (dry gas) or 'GC' (gas condensate)")
         cfg, self._keep = L.make_config(
             device=device, D=spec.D, H=spec.H, W=spec.W, dx=spec.dx, dy=spec.dy, dz=spec.dz, C_=spec.C, Dc=spec.Dc,
             phi=spec.phi, cf=spec.cf, Sgi=spec.Sgi, krg=spec.krg, kx_ky=spec.kx_ky, kv_kh=spec.kv_kh,
             knots=tables.knots, spline_w=tables.w, spline_v=tables.v, spline_order=tables.order,
             p_min=spec.p_min, p_max=spec.p_max, wells=[w.as_dict() for w in spec.wells],
             use_blocking_factor=spec.use_blocking_factor, n_intervals=spec.n_intervals,
-            numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range)
+            numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range,
+            fluid_type=L.SRM_FLUID_GC if spec.fluid_type == "GC" else L.SRM_FLUID_DG,
+            end_points=spec.end_points, corey_exponents=spec.corey_exponents)
         self.pvt_lut = bool(pvt_lut) and numerics == "reference"
         h = C.c_void_p()
         L.check(self.lib, self.lib.srm_create(C.byref(cfg), C.byref(h)), "srm_create")
@@ -156,3 +158,53 @@ class SrmPhysics:
                 "srm_backward")
         self.launches += 3
         return gp0, gp1, gdt1, gdt2
+
+    # ---------------------------------------------------------------------------------------
+    # gas condensate (two-phase)                                   physics_loss.py:230-712
+    def relperm(self, sg: torch.Tensor):
+        """RelativePermeability.compute_krog_krgo (relative_permeability.py:49-75): krog, krgo, d/dSg of both."""
+        self._check(sg, "sg")
+        outs = [torch.empty_like(sg) for _ in range(4)]
+        L.check(self.lib, self.lib.srm_relperm(self._h, sg.numel(), _ptr(sg), *[_ptr(o) for o in outs], self._stream()),
+                "srm_relperm")
+        self.launches += 1
+        return tuple(outs)
+
+    def forward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, want_dom: bool = False,
+                   want_wells: bool = False, save_for_backward: bool = True):
+        B, R = p0.shape[0], kx.shape[0]
+        for t, nm in ((kx, "kx"), (p0, "p0"), (p1, "p1"), (sg0, "sg0"), (sg1, "sg1"), (so0, "so0"), (so1, "so1"),
+                      (dt1, "dt1"), (dt2, "dt2"), (t1, "t1")):
+            self._check(t, nm)
+        if sample_real is not None:
+            self._check(sample_real, "sample_real", torch.int32)
+        for t in (p1, sg0, sg1, so0, so1):
+            if t.shape != p0.shape:
+                raise ValueError("field shapes differ")
+        if p0.numel() != B * self.spec.n_cells or kx.numel() != R * self.spec.n_cells:
+            raise ValueError("field shapes do not match the handle's grid")
+        ws = self.workspace(B, R)
+        terms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32, device=self.device)
+        dom = torch.empty_like(p0) if want_dom else None
+        nw = max(self.n_wells, 1)
+        q4 = torch.zeros((4, B, nw), dtype=torch.float32, device=self.device) if want_wells else None
+        pwfw = torch.zeros((B, nw), dtype=torch.float32, device=self.device) if want_wells else None
+        flags = L.SRM_FLAG_SAVE_FOR_BACKWARD if save_for_backward else 0
+        L.check(self.lib, self.lib.srm_forward_gc(
+            self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1), _ptr(sg0), _ptr(sg1), _ptr(so0), _ptr(so1),
+            _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(terms), _ptr(dom), _ptr(q4), _ptr(pwfw), _ptr(ws), ws.numel(), flags,
+            self._stream()), "srm_forward_gc")
+        self.launches += 5 + (5 if want_wells else 0)
+        return dict(terms=terms, dom=dom, q4w=q4, pwfw=pwfw)
+
+    def backward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms):
+        B, R = p0.shape[0], kx.shape[0]
+        self._check(dterms, "dterms")
+        ws = self.workspace(B, R)
+        g = [torch.empty_like(p0) for _ in range(6)] + [torch.empty_like(dt1), torch.empty_like(dt2)]
+        L.check(self.lib, self.lib.srm_backward_gc(
+            self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1), _ptr(sg0), _ptr(sg1), _ptr(so0), _ptr(so1),
+            _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(dterms), *[_ptr(t) for t in g], _ptr(ws), ws.numel(), 0, self._stream()),
+            "srm_backward_gc")
+        self.launches += 3
+        return tuple(g)        # gp0, gp1, gsg0, gsg1, gso0, gso1, gdt1, gdt2

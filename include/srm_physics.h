@@ -116,6 +116,10 @@ typedef struct SrmConfig {
    * pressures outside the tabulated range are evaluated directly. */
   int32_t pvt_lut;
   float lut_p_lo, lut_p_hi;
+  /* SCAL end points and Corey exponents (relative_permeability.py:19-45; default_configurations.py:262-266).
+   * Used by the gas-condensate path (SRM_FLUID_GC) and by srm_relperm; the dry-gas path only needs the
+   * host-computed scalar krg above. */
+  float Swmin, Sorg, Sgc, Socr, kro_Somax, krg_Sorg, krg_Swmin, nog, ng;
 } SrmConfig;
 
 typedef struct SrmHandle SrmHandle;
@@ -185,6 +189,36 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
                  const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                  const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
                  void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
+
+/* RelativePermeability.compute_krog_krgo (relative_permeability.py:49-75): Corey gas-oil relative
+ * permeabilities with the end-point rules, and their d/dSg as TF's tape routes it (zero where a
+ * where/min/max branch holds the value).  Any output may be NULL. */
+int srm_relperm(const SrmHandle* h, int64_t n, const float* sg, float* krog, float* krgo, float* dkrog,
+                float* dkrgo, void* stream);
+
+/* physics_error_gas_oil (physics_loss.py:319-693) + the SSE reduction of pinn_batch_sse_grad, for a handle
+ * created with fluid_type = SRM_FLUID_GC (n_props = 7: InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro;
+ * PVT_Layer_Subclassed.py:71-72).  Inputs are the networks' outputs at both time levels: pressure, gas
+ * and oil saturation (physics_loss.py:330-332,372-374).  Well rates come from the GC branch of
+ * WellRatesPressure (non-iterative control, _split_condensate_components;
+ * well_rate_bhp_Subclassed.py:614-724,963-1034); the GC blocking-factor integral is not built (the handle
+ * refuses use_blocking_factor with SRM_FLUID_GC).
+ *   terms_out [2][SRM_N_TERMS]: slots DOM, IBC, MBC and CMBC (= the truncation term, physics_loss.py:680)
+ *   q4w_out   [4][B][n_wells]: qgg, qgo, qoo, qog per connection (nullable);  pwfw_out [B][n_wells] */
+int srm_forward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                   const float* p0, const float* p1, const float* sg0, const float* sg1, const float* so0,
+                   const float* so1, const float* dt1, const float* dt2, const float* t1, float* terms_out,
+                   float* dom_out, float* q4w_out, float* pwfw_out, void* workspace, size_t workspace_bytes,
+                   int32_t flags, void* stream);
+
+/* Gradient of L = sum_k dterms[k] * SSE_k w.r.t. the eight differentiable inputs of srm_forward_gc
+ * (what tape.gradient delivers to the networks, physics_loss.py:849-859).  Upstream selects of the
+ * relative permeabilities carry no gradient (tf.cast, physics_loss.py:543-551). */
+int srm_backward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
+                    const float* p0, const float* p1, const float* sg0, const float* sg1, const float* so0,
+                    const float* so1, const float* dt1, const float* dt2, const float* t1, const float* dterms,
+                    float* gp0, float* gp1, float* gsg0, float* gsg1, float* gso0, float* gso1, float* gdt1,
+                    float* gdt2, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
 #ifdef __cplusplus
 }
