@@ -56,7 +56,6 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     if (cfg->n_props != 7) { srm_set_error("srm_create: SRM_FLUID_GC needs the 7 GC properties (InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro), got %d", cfg->n_props); return SRM_ERR_INVALID; }
     if (cfg->numerics != SRM_NUMERICS_REFERENCE) { srm_set_error("srm_create: SRM_FLUID_GC is built for SRM_NUMERICS_REFERENCE only"); return SRM_ERR_INVALID; }
     if (cfg->use_blocking_factor) { srm_set_error("srm_create: the GC blocking-factor integral (well_rate_bhp_Subclassed.py:897-911) is not built"); return SRM_ERR_INVALID; }
-    if (cfg->pvt_lut) { srm_set_error("srm_create: pvt_lut is not built for SRM_FLUID_GC yet"); return SRM_ERR_INVALID; }
     if (cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
   }
   if (cfg->pvt_method != SRM_PVT_SPLINE) { srm_set_error("srm_create: only SRM_PVT_SPLINE is implemented"); return SRM_ERR_INVALID; }
@@ -160,7 +159,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     const bool whole = !(cfg->lut_p_lo < cfg->lut_p_hi);
     const float lo = whole ? cfg->p_min : std::max(cfg->lut_p_lo, cfg->p_min);
     const float hi = whole ? cfg->p_max : std::min(cfg->lut_p_hi, cfg->p_max);
-    int rc = srm_build_pvt_lut(h, lo, hi);
+    int rc = cfg->fluid_type == SRM_FLUID_GC ? srm_build_pvt_lut_gc(h, lo, hi) : srm_build_pvt_lut(h, lo, hi);
     if (rc) { srm_destroy(h); return rc; }
     h->lut_full = (lo <= cfg->p_min && hi >= cfg->p_max) ? 1 : 0;
   }

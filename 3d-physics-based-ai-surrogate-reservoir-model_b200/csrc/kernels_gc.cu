@@ -11,9 +11,9 @@
 // Numerics: the reference's fp32 op order, explicitly rounded (no FMA contraction) in every forward
 // quantity, as in kernels_ref.cu; tf.pow with the integer Corey exponents is the left-to-right product the
 // oracle pins.  One thread per cell; PVT and the per-cell products are staged through the workspace
-// (SRM_GC_NFIELDS fields), neighbours re-read through L1/L2.  This first GC build evaluates the 37-term
-// spline per cell (7 properties): it is compute bound; the exact tabulation of kernels_ref2.cu is the
-// next step for this path.
+// (SRM_GC_NFIELDS fields), neighbours re-read through L1/L2.  With SrmConfig.pvt_lut the stage kernel gathers
+// the PVT packs from the exact per-pressure table instead of evaluating the 37-term spline of 7 properties per
+// cell; the residual kernels are not fused yet (the dry-gas path's kernels_ref2.cu shows the next step).
 #include <math_constants.h>
 #include <cstring>
 #include "pvt_ref.cuh"
@@ -85,7 +85,65 @@ __global__ void __launch_bounds__(kThreads) k_relperm(const __grid_constant__ Sr
 }
 
 // ---- stage -------------------------------------------------------------------------------------
+// Everything the GC residual and its adjoint need from the PVT layer, as two packs of 12 floats, each a
+// pure function of ONE clamped fp32 pressure (derivatives w.r.t. the clamped input; the consumer applies
+// the clamp's gradient mask):
+//   pack0 (time level n)  : invBg, invBo, Rs, Rv | d/dp of the four | d2/dp2 of the four
+//   pack1 (level n+1)     : Mgg, Moo, Mgo, Mog | invBg, invBo, Rs*invBo, Rv*invBg | d(Mgg+Mog), d(Mgo+Moo), d invBg, d invBo
+//                           | d(Rs*invBo), d(Rv*invBg)   (14 values; stored as 16 floats)
+struct GcPack0 { float v[12]; };
+struct GcPack1 { float v[16]; };
 template <bool SAVE>
+__device__ __forceinline__ GcPack0 gc_pack0(const SrmDev& P, float x0) {
+  GcPack0 o;
+  float v[2], d[2], d2[2];
+  d2[0] = d2[1] = 0.f;
+  srm_spline_ref<2, true, SAVE>(P, 0, x0, v, d, d2);          // InvBg, InvBo
+  o.v[0] = v[0]; o.v[1] = v[1]; o.v[4] = d[0]; o.v[5] = d[1]; o.v[8] = d2[0]; o.v[9] = d2[1];
+  d2[0] = d2[1] = 0.f;
+  srm_spline_ref<2, true, SAVE>(P, 4, x0, v, d, d2);          // Rs, Rv
+  o.v[2] = v[0]; o.v[3] = v[1]; o.v[6] = d[0]; o.v[7] = d[1]; o.v[10] = d2[0]; o.v[11] = d2[1];
+  return o;
+}
+template <bool SAVE>
+__device__ __forceinline__ GcPack1 gc_pack1(const SrmDev& P, float x1) {
+  GcPack1 o;
+  float v[6], d[6], d2[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) d[q] = 0.f;
+  srm_spline_ref<6, SAVE, false>(P, 0, x1, v, d, d2);         // InvBg, InvBo, Invug, Invuo, Rs, Rv
+  const float a = v[0], b = v[1], ug = v[2], uo = v[3], rs = v[4], rv = v[5];
+  const float r = __fmul_rn(rs, b), vv = __fmul_rn(rv, a);                     // physics_loss.py:388-389
+  o.v[0] = __fmul_rn(a, ug);                                                   // :386
+  o.v[1] = __fmul_rn(b, uo);                                                   // :387
+  o.v[2] = __fmul_rn(r, uo);                                                   // :390
+  o.v[3] = __fmul_rn(vv, ug);                                                  // :391
+  o.v[4] = a; o.v[5] = b; o.v[6] = r; o.v[7] = vv;
+  const float da = d[0], db = d[1], dug = d[2], duo = d[3], drs = d[4], drv = d[5];
+  const float dr = __fmaf_rn(drs, b, __fmul_rn(rs, db)), dvv = __fmaf_rn(drv, a, __fmul_rn(rv, da));
+  const float dMgg = __fmaf_rn(da, ug, __fmul_rn(a, dug)), dMoo = __fmaf_rn(db, uo, __fmul_rn(b, duo));
+  const float dMgo = __fmaf_rn(dr, uo, __fmul_rn(r, duo)), dMog = __fmaf_rn(dvv, ug, __fmul_rn(vv, dug));
+  o.v[8] = __fadd_rn(dMgg, dMog); o.v[9] = __fadd_rn(dMgo, dMoo);
+  o.v[10] = da; o.v[11] = db; o.v[12] = dr; o.v[13] = dvv; o.v[14] = 0.f; o.v[15] = 0.f;
+  return o;
+}
+
+// exact tabulation (SrmConfig.pvt_lut, see kernels_ref.cu): entry e = the packs of the fp32 pressure with bit
+// pattern lut_lo_bits + e; 48 + 64 bytes per representable pressure.
+__global__ void __launch_bounds__(kThreads) k_lut_build_gc(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
+                                                           float4* __restrict__ t1) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.lut_n) return;
+  const float x = __uint_as_float(P.lut_lo_bits + e);
+  const GcPack0 a = gc_pack0<true>(P, x);
+  const GcPack1 b = gc_pack1<true>(P, x);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t0[(size_t)e * 3 + i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t1[(size_t)e * 4 + i] = make_float4(b.v[4 * i], b.v[4 * i + 1], b.v[4 * i + 2], b.v[4 * i + 3]);
+}
+
+template <bool SAVE, bool LUT>
 __global__ void __launch_bounds__(kThreads) k_stage_gc(const __grid_constant__ SrmDev P, int64_t total,
                                                        const float* __restrict__ p0, const float* __restrict__ p1,
                                                        const float* __restrict__ sg1, float* __restrict__ F) {
@@ -95,40 +153,39 @@ __global__ void __launch_bounds__(kThreads) k_stage_gc(const __grid_constant__ S
   float m0, m1;
   const float x0 = srm_clamp(P, p0[g], m0);
   const float x1 = srm_clamp(P, p1[g], m1);
-  {
-    float v[2], d[2], d2[2];
-    d2[0] = d2[1] = 0.f;
-    srm_spline_ref<2, true, SAVE>(P, 0, x0, v, d, d2);          // InvBg, InvBo
-    out(F_A0, v[0]); out(F_B0, v[1]); out(F_DA0, d[0]); out(F_DB0, d[1]);
-    if (SAVE) { out(F_D2A0, d2[0] * m0); out(F_D2B0, d2[1] * m0); }
-    srm_spline_ref<2, true, SAVE>(P, 4, x0, v, d, d2);          // Rs, Rv
-    out(F_RS0, v[0]); out(F_RV0, v[1]); out(F_DRS0, d[0]); out(F_DRV0, d[1]);
-    if (SAVE) { out(F_D2RS0, d2[0] * m0); out(F_D2RV0, d2[1] * m0); }
-  }
-  {
-    float v[6], d[6], d2[6];
+  GcPack0 a;
+  GcPack1 b;
+  const uint32_t e0 = __float_as_uint(x0) - P.lut_lo_bits, e1 = __float_as_uint(x1) - P.lut_lo_bits;
+  if (LUT && e0 < P.lut_n) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) d[q] = 0.f;
-    srm_spline_ref<6, SAVE, false>(P, 0, x1, v, d, d2);         // InvBg, InvBo, Invug, Invuo, Rs, Rv
-    const float a = v[0], b = v[1], ug = v[2], uo = v[3], rs = v[4], rv = v[5];
-    const float r = __fmul_rn(rs, b), vv = __fmul_rn(rv, a);                     // physics_loss.py:388-389
-    out(F_MGG, __fmul_rn(a, ug));                                                // :386
-    out(F_MOO, __fmul_rn(b, uo));                                                // :387
-    out(F_MGO, __fmul_rn(r, uo));                                                // :390
-    out(F_MOG, __fmul_rn(vv, ug));                                               // :391
-    out(F_A1, a); out(F_B1, b); out(F_R1, r); out(F_V1, vv);
-    float ko, kg, dko, dkg;
-    corey(P, sg1[g], ko, kg, dko, dkg);                                          // :457
-    out(F_KRG, kg); out(F_KRO, ko);
-    if (SAVE) {
-      const float da = d[0] * m1, db = d[1] * m1, dug = d[2] * m1, duo = d[3] * m1, drs = d[4] * m1, drv = d[5] * m1;
-      const float dr = drs * b + rs * db, dvv = drv * a + rv * da;
-      const float dMgg = da * ug + a * dug, dMoo = db * uo + b * duo;
-      const float dMgo = dr * uo + r * duo, dMog = dvv * ug + vv * dug;
-      out(F_DMG, dMgg + dMog); out(F_DMO, dMgo + dMoo);
-      out(F_DA1, da); out(F_DB1, db); out(F_DR1, dr); out(F_DV1, dvv);
-      out(F_DKRG, dkg); out(F_DKRO, dko);
+    for (int i = 0; i < (SAVE ? 3 : 2); ++i) {
+      const float4 t = __ldg(P.lut0 + (size_t)e0 * 3 + i);
+      a.v[4 * i] = t.x; a.v[4 * i + 1] = t.y; a.v[4 * i + 2] = t.z; a.v[4 * i + 3] = t.w;
     }
+  } else {
+    a = gc_pack0<SAVE>(P, x0);
+  }
+  if (LUT && e1 < P.lut_n) {
+#pragma unroll
+    for (int i = 0; i < (SAVE ? 4 : 2); ++i) {
+      const float4 t = __ldg(P.lut1 + (size_t)e1 * 4 + i);
+      b.v[4 * i] = t.x; b.v[4 * i + 1] = t.y; b.v[4 * i + 2] = t.z; b.v[4 * i + 3] = t.w;
+    }
+  } else {
+    b = gc_pack1<SAVE>(P, x1);
+  }
+  out(F_A0, a.v[0]); out(F_B0, a.v[1]); out(F_RS0, a.v[2]); out(F_RV0, a.v[3]);
+  out(F_DA0, a.v[4]); out(F_DB0, a.v[5]); out(F_DRS0, a.v[6]); out(F_DRV0, a.v[7]);
+  out(F_MGG, b.v[0]); out(F_MOO, b.v[1]); out(F_MGO, b.v[2]); out(F_MOG, b.v[3]);
+  out(F_A1, b.v[4]); out(F_B1, b.v[5]); out(F_R1, b.v[6]); out(F_V1, b.v[7]);
+  float ko, kg, dko, dkg;
+  corey(P, sg1[g], ko, kg, dko, dkg);                                            // :457
+  out(F_KRG, kg); out(F_KRO, ko);
+  if (SAVE) {
+    out(F_D2A0, a.v[8] * m0); out(F_D2B0, a.v[9] * m0); out(F_D2RS0, a.v[10] * m0); out(F_D2RV0, a.v[11] * m0);
+    out(F_DMG, b.v[8] * m1); out(F_DMO, b.v[9] * m1);
+    out(F_DA1, b.v[10] * m1); out(F_DB1, b.v[11] * m1); out(F_DR1, b.v[12] * m1); out(F_DV1, b.v[13] * m1);
+    out(F_DKRG, dkg); out(F_DKRO, dko);
   }
 }
 
@@ -643,6 +700,27 @@ int srm_launch_relperm(const SrmHandle* h, int64_t n, const float* sg, float* kr
   return SRM_OK;
 }
 
+int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi) {
+  SrmDev& P = h->dev;
+  uint32_t lo_bits, hi_bits;
+  memcpy(&lo_bits, &lo, 4);
+  memcpy(&hi_bits, &hi, 4);
+  if (!(lo > 0.f) || !(hi >= lo)) { srm_set_error("srm_create: pvt_lut range [%g, %g] must be positive and ascending", lo, hi); return SRM_ERR_INVALID; }
+  const uint64_t n = (uint64_t)hi_bits - lo_bits + 1;
+  if (n > (1ull << 31)) { srm_set_error("srm_create: pvt_lut range too wide"); return SRM_ERR_INVALID; }
+  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * 7 * sizeof(float4));       // 3 + 4 float4 per pressure
+  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut (GC) needs %.1f MB of device memory: %s", n * 112e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
+  P.lut_lo_bits = lo_bits;
+  P.lut_n = (uint32_t)n;
+  P.lut0 = h->d_lut;
+  P.lut1 = h->d_lut + 3 * n;
+  P.lutf0 = nullptr; P.lutf1 = nullptr;
+  k_lut_build_gc<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + 3 * n);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  SRM_CUDA_CHECK(cudaDeviceSynchronize());
+  return SRM_OK;
+}
+
 int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real, const float* p0,
                         const float* p1, const float* sg0, const float* sg1, const float* so0, const float* so1,
                         const float* dt1, const float* dt2, const float* t1, float* terms_out, float* dom_out,
@@ -651,8 +729,11 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
   const int64_t total = (int64_t)B * P.N;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse and the four per-sample sums
   const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
-  if (save) k_stage_gc<true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
-  else k_stage_gc<false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+  const bool lut = P.lut_n > 0;
+  if (save) { if (lut) k_stage_gc<true, true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+              else k_stage_gc<true, false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc); }
+  else      { if (lut) k_stage_gc<false, true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+              else k_stage_gc<false, false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc); }
   SRM_CUDA_CHECK(cudaGetLastError());
   const int64_t nwt = (int64_t)B * P.n_wells;
   if (nwt > 0) {

@@ -197,6 +197,7 @@ int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const i
                          const float* p, const float* t_days, float* qw_sorted, float* pwfw_sorted,
                          float* dqdp_sorted, cudaStream_t s);
 int srm_build_pvt_lut(SrmHandle* h, float lo, float hi);
+int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi);
 int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                      float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s);

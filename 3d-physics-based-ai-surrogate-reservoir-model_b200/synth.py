@@ -19,6 +19,7 @@ CONFIGS = {
     "cfg1": dict(W=39, H=39, D=1, T=8, K=4),          # default grid, batch 32
     "cfg2": dict(W=64, H=64, D=16, T=32, K=16),
     "cfg3": dict(W=128, H=128, D=32, T=24, K=64),
+    "cfg4": dict(W=128, H=128, D=32, T=24, K=32),     # two-phase (gas condensate)
     "cfg5": dict(W=256, H=256, D=64, T=32, K=8),
 }
 
@@ -112,3 +113,20 @@ def make_batch(W, H, D, T, K, wells_ij, seed=2000, device="cpu", near_knots=None
     sample_real = (torch.arange(B, device=dev) // T).to(torch.int32)
     return SynthBatch(kx=kx, p0=p0.contiguous(), p1=p1.contiguous(), dt1=dt1, dt2=dt2, t1=t1,
                       sample_real=sample_real)
+
+
+def make_saturations(batch: SynthBatch, seed=2000, Swmin=0.22, sg_lo=0.50, sg_hi=0.78):
+    """Gas / oil saturations at both time levels for the two-phase (GC) configs: smooth Sg in [sg_lo, sg_hi]
+    (Sgc ... 1-Swmin), Sg1 slightly below Sg0 (liquid drop-out as pressure falls), So = 1-Swmin-Sg
+    (relative_permeability.py:58).  Returns sg0, sg1, so0, so1 shaped like batch.p0."""
+    dev = batch.p0.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed) + 77)
+    u = torch.rand(batch.p0.shape, generator=gen, device=dev)
+    u = _gauss_smooth(u, (2.0, 2.0, 1.0))
+    u = (u - u.amin()) / (u.amax() - u.amin() + 1e-12)
+    sg0 = (sg_lo + (sg_hi - sg_lo) * u).to(torch.float32)
+    drop = 0.02 * torch.rand(batch.p0.shape, generator=gen, device=dev)
+    sg1 = (sg0 - drop).clamp_(0.0, 1.0 - Swmin)
+    top = torch.tensor(float(1.0 - Swmin), dtype=torch.float32, device=dev)
+    return sg0.contiguous(), sg1.contiguous(), (top - sg0).contiguous(), (top - sg1).contiguous()

@@ -46,12 +46,16 @@ def workload(name):
     else:
         wells = srm.config.scaled_default_wells(c["W"], c["H"], c["D"])
         blocking = False
-    spec = srm.PhysicsSpec(D=c["D"], H=c["H"], W=c["W"], wells=wells, use_blocking_factor=blocking, n_intervals=8)
+    spec = srm.PhysicsSpec(D=c["D"], H=c["H"], W=c["W"], wells=wells, use_blocking_factor=blocking, n_intervals=8,
+                           fluid_type="GC" if name == "cfg4" else "DG")
     return c, spec
 
 
-def alg_bytes_per_cell(T):
-    return 28.0 + 8.0 / T          # DG fwd + adjoint, SURVEY.md 8(d) / BASELINE.md section 3
+def alg_bytes_per_cell(T, gc=False):
+    # DG fwd + adjoint 28 + 8/T; GC (p, Sg, So at two levels; one dom) 68 + 8/T: forward reads 6 fields and
+    # writes dom (28), adjoint reads 6 fields + dom and writes 6 gradients (52), minus nothing shared
+    # (SURVEY.md 8(d) counts 52 + 8/T with So derived from Sg; the reference's So is a separate network output)
+    return (80.0 if gc else 28.0) + 8.0 / T
 
 
 def peak_hbm():
@@ -128,7 +132,8 @@ def cpu_oracle_throughput(name, target_seconds=15.0, max_samples=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(1)        # parallelism comes from sample shards, one per core
     cols = O.load_pvt_table(os.path.join(ROOT, "tests", "golden", "pvt_table.npz"))
-    otab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    gc = spec.fluid_type == "GC"
+    otab = O.build_spline_table(cols, O.GC_PROPS if gc else O.DG_PROPS, order=1, lam=0.001)
     ocfg = O.OracleConfig(D=spec.D, H=spec.H, W=spec.W, use_blocking_factor=spec.use_blocking_factor,
                           n_intervals=spec.n_intervals,
                           wells=[O.Well(i=w.i, j=w.j, k=w.k, value=abs(w.q_target), producer=not np.signbit(w.q_target),
@@ -138,9 +143,16 @@ def cpu_oracle_throughput(name, target_seconds=15.0, max_samples=None):
     # one sample per core per round; rounds until the time budget is spent
     nb = cores if max_samples is None else max(1, min(cores, max_samples))
     batch = srm.synth.make_batch(spec.W, spec.H, spec.D, 1, nb, [(w.i, w.j) for w in spec.wells[:8]], seed=2002)
+    sat = [t.numpy() for t in srm.synth.make_saturations(batch, seed=2002)] if gc else None
 
     def one(b):
         sl = slice(b, b + 1)
+        if gc:
+            O.gc_forward_backward(ocfg, otab, batch.kx[sl].numpy(), batch.p0[sl].numpy(), batch.p1[sl].numpy(),
+                                  sat[0][sl], sat[1][sl], sat[2][sl], sat[3][sl], batch.dt1[sl].numpy(),
+                                  batch.dt2[sl].numpy(), batch.t1[sl].numpy(), np.zeros(1, np.int32),
+                                  [1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0])
+            return N
         O.dg_forward_backward(ocfg, otab, batch.kx[sl].numpy(), batch.p0[sl].numpy(), batch.p1[sl].numpy(),
                               batch.dt1[sl].numpy(), batch.dt2[sl].numpy(), batch.t1[sl].numpy(),
                               np.zeros(1, np.int32), WEIGHTS)
@@ -180,7 +192,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: dry-gas {spec.W}x{spec.H}x{spec.D}, T={c['T']}, K={c['K']} (bounded sample per step)",
+            "config": {"workload": f"{args.workload}: {'gas-condensate (two-phase)' if spec.fluid_type == 'GC' else 'dry-gas'} {spec.W}x{spec.H}x{spec.D}, T={c['T']}, K={c['K']} (bounded sample per step)",
                        "note": "reference CPU path = oracle port of the TF op graph (TensorFlow not installable; reference not import-clean)"},
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -206,7 +218,8 @@ def run_ours(args):
     T, K = c["T"], c["K"]
     if args.K:
         K = args.K
-    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES, order=1)
+    gc = spec.fluid_type == "GC"
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.GC_PROPERTIES if gc else srm.pvt.DG_PROPERTIES, order=1)
     lut = args.numerics == "reference" and not args.no_pvt_lut
     torch.cuda.synchronize(dev)
     t_create = time.perf_counter()
@@ -215,15 +228,19 @@ def run_ours(args):
     t_create = time.perf_counter() - t_create
     b = srm.synth.make_batch(spec.W, spec.H, spec.D, T, K, [(w.i, w.j) for w in spec.wells[:8]], seed=2002 + rank, device=dev)
     d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
+    if gc:
+        d["sg0"], d["sg1"], d["so0"], d["so1"] = srm.synth.make_saturations(b, seed=2002 + rank)
+    fwd = eng.forward_gc if gc else eng.forward
+    bwd = eng.backward_gc if gc else eng.backward
     B = b.p0.shape[0]
     N = B * spec.n_cells
-    dterms = torch.tensor(WEIGHTS, dtype=torch.float32, device=dev)
+    dterms = torch.tensor([1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0] if gc else WEIGHTS, dtype=torch.float32, device=dev)
 
     def step():
-        fw = eng.forward(**d)
+        fw = fwd(**d)
         if distributed:
             srm.dist.allreduce_terms(fw["terms"])
-        g = eng.backward(dterms=dterms, **d)
+        g = bwd(dterms=dterms, **d)
         return fw["terms"], g
 
     def barrier():
@@ -242,11 +259,11 @@ def run_ours(args):
     ef = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     e0.record()
     for i in range(args.steps):
-        fw = eng.forward(**d)
+        fw = fwd(**d)
         if distributed:
             srm.dist.allreduce_terms(fw["terms"])
         ef[2 * i].record()
-        eng.backward(dterms=dterms, **d)
+        bwd(dterms=dterms, **d)
         ef[2 * i + 1].record()
     e1.record()
     barrier()
@@ -265,20 +282,21 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
-    out_host = dict(gp0=torch.empty_like(host["p0"]).pin_memory(), gp1=torch.empty_like(host["p1"]).pin_memory(),
-                    gdt1=torch.empty_like(host["dt1"]).pin_memory(), gdt2=torch.empty_like(host["dt2"]).pin_memory(),
-                    terms=torch.empty((2, 8), dtype=torch.float32).pin_memory())
+    gnames = ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2") if gc else ("gp0", "gp1", "gdt1", "gdt2")
+    out_host = {k: (torch.empty_like(host["dt1"]) if k.startswith("gdt") else torch.empty_like(host["p0"])).pin_memory()
+                for k in gnames}
+    out_host["terms"] = torch.empty((2, 8), dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
     def e2e_step():
         dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        fw = eng.forward(**dd)
+        fw = fwd(**dd)
         if distributed:
             srm.dist.allreduce_terms(fw["terms"])
-        g = eng.backward(dterms=dterms, **dd)
+        g = bwd(dterms=dterms, **dd)
         out_host["terms"].copy_(fw["terms"], non_blocking=True)
-        for k, v in zip(("gp0", "gp1", "gdt1", "gdt2"), g):
+        for k, v in zip(gnames, g):
             out_host[k].copy_(v, non_blocking=True)
         torch.cuda.synchronize(dev)
 
@@ -295,11 +313,11 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N * e2e_steps / float(te.item())
-    loss = float((out_host["terms"][0] * torch.tensor(WEIGHTS)).sum())
+    loss = float((out_host["terms"][0] * dterms.cpu()).sum())
 
     if rank == 0:
         peak, peak_src = peak_hbm()
-        ab = alg_bytes_per_cell(T)
+        ab = alg_bytes_per_cell(T, gc)
         achieved = N * ab / (ms_step * 1e-3) / 1e9          # per GPU (each rank runs N cells per step)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -308,7 +326,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: dry-gas {spec.W}x{spec.H}x{spec.D}, T={T}, K={K} per GPU, B={B}, "
+            "config": {"workload": f"{args.workload}: {'gas-condensate (two-phase)' if gc else 'dry-gas'} {spec.W}x{spec.H}x{spec.D}, T={T}, K={K} per GPU, B={B}, "
                                    f"{len(spec.wells)} well connections" + (", blocking-factor integral" if spec.use_blocking_factor else ""),
                        "numerics": args.numerics, "cells_per_gpu_per_step": N,
                        "pvt": ("reference-order spline tabulated per fp32 pressure over the clamp range at handle creation "
@@ -338,7 +356,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--numerics", default="reference", choices=["reference", "closed_form"])
     ap.add_argument("--K", type=int, default=0, help="override realisations per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -62,7 +62,34 @@ def case_golden(name, kw):
     print(name, "B =", batch.p0.shape[0], "terms", o["terms"][:4])
 
 
+GC_CASES = {
+    "gc_3d": dict(seed=2201, B=2, D=2, H=6, W=8, sg_lo=0.2, sg_hi=0.6, wells="dup"),
+}
+GC_WEIGHTS = [1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+GC_GRADS = ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2")
+
+
+def gc_golden(name, kw):
+    """gas-condensate case: inputs, the spline weights of the 7 properties, the fp32 oracle's outputs and the
+    element-wise distance of its gradients to the fp64 twin (the reference's own fp32 noise, see tests/test_gpu_gc.py)"""
+    ocfg, otab, spec, ptab, d = U.gc_case(**kw)
+    args = (ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"], d["dt1"], d["dt2"], d["t1"],
+            d["sample_real"], GC_WEIGHTS)
+    o = O.gc_forward_backward(*args)
+    o64 = O.gc_forward_backward(*args, dtype=torch.float64)
+    keep = dict(d)
+    keep.update(knots=otab.c, w=otab.w, v=otab.v, weights=np.array(GC_WEIGHTS, dtype=np.float32))
+    for k in ("dom", "ibc", "mbc", "cmbc", "terms", "qw4", "pwfw") + GC_GRADS:
+        keep["o_" + k] = np.asarray(o[k], dtype=np.float32)
+    for k in GC_GRADS[:-1]:
+        keep["noise_" + k] = (o[k].astype(np.float64) - o64[k]).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **keep)
+    print(name, "terms", o["terms"])
+
+
 if __name__ == "__main__":
+    for n, kw in GC_CASES.items():
+        gc_golden(n, kw)
     pvt_golden()
     for n, kw in CASES.items():
         case_golden(n, kw)

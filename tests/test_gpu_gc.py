@@ -34,46 +34,17 @@ def h3_close(a, b, rtol=RTOL, noise=None):
     return np.all(np.abs(a - b) <= tol)
 
 
-def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, small_dp=False):
-    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
-    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
-    if wells == "two":
-        wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=W - 2, j=H - 2, k=D - 1, value=1000.0)]
-    elif wells == "dup":     # two connections in one cell + a neighbouring well cell
-        wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=2, j=2, k=0, value=300.0), dict(i=3, j=2, k=0, value=800.0)]
-    else:
-        wl = []
-    ocfg = O.OracleConfig(D=D, H=H, W=W, wells=[O.Well(**w) for w in wl])
-    conns = [dict(i=w["i"], j=w["j"], k=w["k"], type="producer", control="ORAT", value=w["value"], minimum_bhp=4100.0,
-                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for w in wl]
-    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC")
-    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
-    rng = np.random.default_rng(seed)
-    shp = (B, D, H, W)
-    d = dict(kx=rng.uniform(1, 6, (R, D, H, W)).astype(np.float32))
-    d["p0"] = (4700 + rng.uniform(-40, 40, shp)).astype(np.float32)
-    d["p1"] = (d["p0"] - rng.uniform(-3 if small_dp else 1, 25, shp)).astype(np.float32)
-    if small_dp:
-        d["p1"][0, 0, 0, :2] = d["p0"][0, 0, 0, :2]            # p1 == p0: divide_no_nan branch
-    d["sg0"] = rng.uniform(sg_lo, sg_hi, shp).astype(np.float32)
-    d["sg1"] = (d["sg0"] - rng.uniform(0.001, 0.02, shp)).astype(np.float32)
-    d["so0"] = (np.float32(0.78) - d["sg0"]).astype(np.float32)
-    d["so1"] = (np.float32(0.78) - d["sg1"]).astype(np.float32)
-    d["dt1"] = rng.uniform(1, 6, B).astype(np.float32)
-    d["dt2"] = rng.uniform(1, 6, B).astype(np.float32)
-    d["t1"] = np.linspace(5, 50, B).astype(np.float32)
-    d["sample_real"] = (np.arange(B) % R).astype(np.int32)
-    return ocfg, otab, spec, ptab, d
+gc_case = U.gc_case
 
 
-def run_both(ocfg, otab, spec, ptab, d, weights=W_ALL, want64=False):
+def run_both(ocfg, otab, spec, ptab, d, weights=W_ALL, want64=False, pvt_lut=False):
     o = O.gc_forward_backward(ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"], d["dt1"],
                               d["dt2"], d["t1"], d["sample_real"], weights)
     if want64:
         o64 = O.gc_forward_backward(ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"],
                                     d["dt1"], d["dt2"], d["t1"], d["sample_real"], weights, dtype=torch.float64)
         o["noise"] = {k: o[k].astype(np.float64) - o64[k] for k in ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1")}
-    eng = srm.SrmPhysics(spec, ptab, device=0)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut, lut_range=(4650.0, 4720.0) if pvt_lut else None)
     dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     fw = eng.forward_gc(want_dom=True, want_wells=True, **dev)
     g = eng.backward_gc(dterms=torch.tensor(weights, dtype=torch.float32, device="cuda"), **dev)
@@ -111,10 +82,12 @@ CASES = [
 ]
 
 
+# pvt_lut: the stage kernel gathers from the exact table inside [4650, 4720] psi and evaluates directly outside it
+@pytest.mark.parametrize("pvt_lut", [False, True])
 @pytest.mark.parametrize("kw", CASES)
-def test_gc_forward_backward_vs_oracle(kw):
+def test_gc_forward_backward_vs_oracle(kw, pvt_lut):
     ocfg, otab, spec, ptab, d = gc_case(**kw)
-    o, c = run_both(ocfg, otab, spec, ptab, d, want64=True)
+    o, c = run_both(ocfg, otab, spec, ptab, d, want64=True, pvt_lut=pvt_lut)
     assert U.ulp_diff(c["dom"], o["dom"]) == 0
     if ocfg.wells:
         assert np.allclose(c["q4w"], o["qw4"], rtol=RTOL, atol=0) and np.allclose(c["pwfw"], o["pwfw"], rtol=RTOL, atol=0)
@@ -157,4 +130,23 @@ def test_gc_handle_rules():
     dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     with pytest.raises(srm._lib.SrmError):                       # a GC handle refuses the dry-gas entry point
         eng.forward(dev["kx"], dev["sample_real"], dev["p0"], dev["p1"], dev["dt1"], dev["dt2"], dev["t1"])
+    eng.close()
+
+
+def test_gc_vs_committed_golden():
+    """the committed fixture (tests/golden/gc_3d.npz, made by tests/golden/make_golden.py): no oracle run needed"""
+    from golden.make_golden import GC_CASES
+    g = np.load(os.path.join(U.GOLDEN, "gc_3d.npz"))
+    ocfg, otab, spec, ptab, d = gc_case(**GC_CASES["gc_3d"])
+    ptab = srm.pvt.SplineTables(knots=g["knots"], w=g["w"], v=g["v"], order=1, properties=srm.pvt.GC_PROPERTIES)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    dev = {k: torch.from_numpy(g[k]).cuda() for k in ("kx", "sample_real", "p0", "p1", "sg0", "sg1", "so0", "so1", "dt1", "dt2", "t1")}
+    fw = eng.forward_gc(want_dom=True, want_wells=True, **dev)
+    gr = eng.backward_gc(dterms=torch.from_numpy(g["weights"]).cuda(), **dev)
+    torch.cuda.synchronize()
+    assert U.ulp_diff(fw["dom"].cpu().numpy(), g["o_dom"]) == 0
+    assert np.allclose(fw["q4w"].cpu().numpy(), g["o_qw4"], rtol=RTOL, atol=0)
+    assert np.allclose(fw["terms"][0].cpu().numpy(), g["o_terms"], rtol=RTOL, atol=0)
+    for name, t in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1"), gr):
+        assert h3_close(t.cpu().numpy(), g["o_" + name], noise=g["noise_" + name]), name
     eng.close()

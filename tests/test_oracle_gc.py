@@ -99,3 +99,18 @@ def test_gc_wells_split_sums_to_phase_rates():
     assert (res["krog1"] > 0).any()
     assert torch.all(qgg + qgo <= torch.tensor([500.0, 1000.0]) * (1 + 1e-6))
     assert torch.all(qoo >= 0) and torch.all(qog >= 0)
+
+
+def test_gc_oracle_reproduces_golden():
+    from golden.make_golden import GC_CASES, GC_WEIGHTS
+    g = np.load(os.path.join(U.GOLDEN, "gc_3d.npz"))
+    ocfg, otab, spec, ptab, d = U.gc_case(**GC_CASES["gc_3d"])
+    for k in ("kx", "p0", "p1", "sg0", "sg1", "so0", "so1", "dt1", "dt2"):
+        assert np.array_equal(d[k], g[k]), k                    # the seeded inputs are reproducible
+    otab.w[:], otab.v[:] = g["w"], g["v"]                       # the golden's weights: this box's LAPACK does not enter
+    o = O.gc_forward_backward(ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"], d["dt1"],
+                              d["dt2"], d["t1"], d["sample_real"], GC_WEIGHTS)
+    assert np.array_equal(o["dom"], g["o_dom"])
+    assert np.allclose(o["terms"], g["o_terms"], rtol=1e-6)
+    for k in ("gp0", "gp1", "gsg1"):
+        assert np.allclose(o[k], g["o_" + k], rtol=1e-5, atol=1e-6 * np.abs(g["o_" + k]).max())

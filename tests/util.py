@@ -85,3 +85,35 @@ def ulp_diff(a, b):
     ai = np.where(ai < 0, np.int64(-2**31) - ai, ai)
     bi = np.where(bi < 0, np.int64(-2**31) - bi, bi)
     return int(np.abs(ai - bi).max())
+
+
+def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, small_dp=False):
+    cols = O.load_pvt_table(os.path.join(GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    if wells == "two":
+        wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=W - 2, j=H - 2, k=D - 1, value=1000.0)]
+    elif wells == "dup":     # two connections in one cell + a neighbouring well cell
+        wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=2, j=2, k=0, value=300.0), dict(i=3, j=2, k=0, value=800.0)]
+    else:
+        wl = []
+    ocfg = O.OracleConfig(D=D, H=H, W=W, wells=[O.Well(**w) for w in wl])
+    conns = [dict(i=w["i"], j=w["j"], k=w["k"], type="producer", control="ORAT", value=w["value"], minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for w in wl]
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC")
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    rng = np.random.default_rng(seed)
+    shp = (B, D, H, W)
+    d = dict(kx=rng.uniform(1, 6, (R, D, H, W)).astype(np.float32))
+    d["p0"] = (4700 + rng.uniform(-40, 40, shp)).astype(np.float32)
+    d["p1"] = (d["p0"] - rng.uniform(-3 if small_dp else 1, 25, shp)).astype(np.float32)
+    if small_dp:
+        d["p1"][0, 0, 0, :2] = d["p0"][0, 0, 0, :2]            # p1 == p0: divide_no_nan branch
+    d["sg0"] = rng.uniform(sg_lo, sg_hi, shp).astype(np.float32)
+    d["sg1"] = (d["sg0"] - rng.uniform(0.001, 0.02, shp)).astype(np.float32)
+    d["so0"] = (np.float32(0.78) - d["sg0"]).astype(np.float32)
+    d["so1"] = (np.float32(0.78) - d["sg1"]).astype(np.float32)
+    d["dt1"] = rng.uniform(1, 6, B).astype(np.float32)
+    d["dt2"] = rng.uniform(1, 6, B).astype(np.float32)
+    d["t1"] = np.linspace(5, 50, B).astype(np.float32)
+    d["sample_real"] = (np.arange(B) % R).astype(np.int32)
+    return ocfg, otab, spec, ptab, d
