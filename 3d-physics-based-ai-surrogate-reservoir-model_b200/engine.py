@@ -55,6 +55,7 @@ class SrmPhysics:
         self._ws = None
         self._ws_B = None
         self.launches = 0       # kernels launched through this handle (bench's gpu_launches claim)
+        self.fluid = spec.fluid_type
 
     def close(self):
         if getattr(self, "_h", None):
@@ -140,23 +141,34 @@ class SrmPhysics:
         L.check(self.lib, self.lib.srm_forward(self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1),
                                                _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(terms), _ptr(dom), _ptr(qw),
                                                _ptr(pwfw), _ptr(ws), ws.numel(), flags, self._stream()), "srm_forward")
-        self.launches += 4 + (2 if want_wells else 0)
+        # kernels per forward (memsets are not kernels): fused reference = faces, wells, qsum, residual, finalize;
+        # staged reference = stage, wells, residual, finalize; closed form = grouping, wells, qsum, residual, finalize
+        nk = 4 if (self.numerics == "reference" and not self.pvt_lut) else 5
+        if self.n_wells == 0:
+            nk -= 1 if nk == 4 else 2
+        self.launches += nk + (2 if (want_wells and self.n_wells) else 0)
         return dict(terms=terms, dom=dom, qw=qw, pwfw=pwfw)
 
-    def backward(self, kx, sample_real, p0, p1, dt1, dt2, t1, dterms):
+    def backward(self, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, out=None):
+        """out: optional preallocated (gp0, gp1, gdt1, gdt2) to write into"""
         B = p0.shape[0]
         R = kx.shape[0]
         self._check(dterms, "dterms")
         ws = self.workspace(B, R)
-        gp0 = torch.empty_like(p0)
-        gp1 = torch.empty_like(p1)
-        gdt1 = torch.empty_like(dt1)
-        gdt2 = torch.empty_like(dt2)
+        if out is not None:
+            gp0, gp1, gdt1, gdt2 = out
+            for t, nm in ((gp0, "gp0"), (gp1, "gp1"), (gdt1, "gdt1"), (gdt2, "gdt2")):
+                self._check(t, nm)
+        else:
+            gp0 = torch.empty_like(p0)
+            gp1 = torch.empty_like(p1)
+            gdt1 = torch.empty_like(dt1)
+            gdt2 = torch.empty_like(dt2)
         L.check(self.lib, self.lib.srm_backward(self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1),
                                                 _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(dterms), _ptr(gp0), _ptr(gp1),
                                                 _ptr(gdt1), _ptr(gdt2), _ptr(ws), ws.numel(), 0, self._stream()),
                 "srm_backward")
-        self.launches += 3
+        self.launches += 3 if self.n_wells else 2       # adjoint, inner-boundary scatter (wells only), finalize
         return gp0, gp1, gdt1, gdt2
 
     # ---------------------------------------------------------------------------------------
@@ -194,17 +206,130 @@ class SrmPhysics:
             self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1), _ptr(sg0), _ptr(sg1), _ptr(so0), _ptr(so1),
             _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(terms), _ptr(dom), _ptr(q4), _ptr(pwfw), _ptr(ws), ws.numel(), flags,
             self._stream()), "srm_forward_gc")
-        self.launches += 5 + (5 if want_wells else 0)
+        self.launches += (4 if self.n_wells else 3) + (5 if (want_wells and self.n_wells) else 0)   # stage, wells, residual, finalize
         return dict(terms=terms, dom=dom, q4w=q4, pwfw=pwfw)
 
-    def backward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms):
+    def backward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms, out=None):
         B, R = p0.shape[0], kx.shape[0]
         self._check(dterms, "dterms")
         ws = self.workspace(B, R)
-        g = [torch.empty_like(p0) for _ in range(6)] + [torch.empty_like(dt1), torch.empty_like(dt2)]
+        if out is not None:
+            g = list(out)
+            for t in g:
+                self._check(t, "out")
+        else:
+            g = [torch.empty_like(p0) for _ in range(6)] + [torch.empty_like(dt1), torch.empty_like(dt2)]
         L.check(self.lib, self.lib.srm_backward_gc(
             self._h, B, R, _ptr(kx), _ptr(sample_real), _ptr(p0), _ptr(p1), _ptr(sg0), _ptr(sg1), _ptr(so0), _ptr(so1),
             _ptr(dt1), _ptr(dt2), _ptr(t1), _ptr(dterms), *[_ptr(t) for t in g], _ptr(ws), ws.numel(), 0, self._stream()),
             "srm_backward_gc")
-        self.launches += 3
+        self.launches += 3 if self.n_wells else 2
         return tuple(g)        # gp0, gp1, gsg0, gsg1, gso0, gso1, gdt1, gdt2
+
+
+class HostPipeline:
+    """The end-to-end call with HOST buffers: loss terms and gradients for a batch that lives in pinned host memory.
+
+    The reference converts its numpy batch to device tensors every step (training.py:595-600) and pulls the loss
+    terms back with .numpy() (training.py:608-610).  Here the batch is cut into chunks of whole realisations
+    (samples are independent units and the loss terms are additive); chunk i+1 travels host->device on a copy
+    stream while chunk i runs forward + adjoint and the gradients of chunk i-1 travel device->host on a third
+    stream, so the PCIe link is used in both directions at once and the kernels hide behind the copies.
+    Requires the realisation-major sample order BatchGenerator produces (training.py:187-204): sample_real ascending.
+    """
+
+    DG_FIELDS = ("p0", "p1")
+    GC_FIELDS = ("p0", "p1", "sg0", "sg1", "so0", "so1")
+
+    def __init__(self, eng: "SrmPhysics", host: dict, dterms, n_chunks: int = 8):
+        self.eng = eng
+        self.gc = eng.fluid == "GC"
+        self.fields = self.GC_FIELDS if self.gc else self.DG_FIELDS
+        self.scalars = ("dt1", "dt2", "t1")
+        dev = eng.device
+        for k, v in host.items():
+            if not (isinstance(v, torch.Tensor) and v.device.type == "cpu" and v.is_pinned() and v.is_contiguous()):
+                raise ValueError(f"{k}: need a contiguous pinned host tensor")
+        sr = host["sample_real"]
+        if sr.numel() > 1 and bool((sr[1:] < sr[:-1]).any()):
+            raise ValueError("HostPipeline needs realisation-major sample order (sample_real ascending)")
+        self.host = host
+        self.B = host["p0"].shape[0]
+        R = host["kx"].shape[0]
+        n_chunks = max(1, min(int(n_chunks), R))
+        # chunk = a range of whole realisations and the (contiguous) samples that belong to it
+        starts = torch.searchsorted(sr.to(torch.int64), torch.arange(R + 1, dtype=torch.int64)).tolist()
+        self.chunks = []
+        for c in range(n_chunks):
+            r0, r1 = (c * R) // n_chunks, ((c + 1) * R) // n_chunks
+            if r1 > r0 and starts[r1] > starts[r0]:
+                self.chunks.append((r0, r1, starts[r0], starts[r1]))
+        mb = max(b1 - b0 for _, _, b0, b1 in self.chunks)
+        mr = max(r1 - r0 for r0, r1, _, _ in self.chunks)
+        cell = host["p0"].shape[1:]
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.din = [dict(kx=torch.empty((mr,) + tuple(cell), **f32), sample_real=torch.empty(mb, dtype=torch.int32, device=dev),
+                         **{k: torch.empty((mb,) + tuple(cell), **f32) for k in self.fields},
+                         **{k: torch.empty(mb, **f32) for k in self.scalars}) for _ in range(2)]
+        self.dout = [[torch.empty((mb,) + tuple(cell), **f32) for _ in self.fields] + [torch.empty(mb, **f32), torch.empty(mb, **f32)]
+                     for _ in range(2)]
+        self.gnames = tuple("g" + k for k in self.fields) + ("gdt1", "gdt2")
+        self.hout = {n: (torch.empty(self.B, dtype=torch.float32) if n.startswith("gdt") else torch.empty_like(host["p0"])).pin_memory()
+                     for n in self.gnames}
+        self.hterms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32).pin_memory()
+        self.terms = torch.zeros((2, L.SRM_N_TERMS), **f32)
+        self.dterms = dterms
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+        self.d2h_bytes = sum(v.numel() * v.element_size() for v in self.hout.values()) + self.hterms.numel() * 4
+
+    def step(self, reduce_terms=None):
+        """one forward + adjoint over the whole host batch; returns (host terms [2][8], dict of host gradients)"""
+        eng, host = self.eng, self.host
+        comp = torch.cuda.current_stream(eng.device)
+        self.s_in.wait_stream(comp)
+        self.s_out.wait_stream(comp)
+        self.terms.zero_()
+        ev_in = [None, None]; ev_free_in = [None, None]; ev_comp = [None, None]; ev_free_out = [None, None]
+        for c, (r0, r1, b0, b1) in enumerate(self.chunks):
+            slot = c & 1
+            nb, nr = b1 - b0, r1 - r0
+            din, dout = self.din[slot], self.dout[slot]
+            with torch.cuda.stream(self.s_in):
+                if ev_free_in[slot] is not None:
+                    self.s_in.wait_event(ev_free_in[slot])
+                din["kx"][:nr].copy_(host["kx"][r0:r1], non_blocking=True)
+                din["sample_real"][:nb].copy_(host["sample_real"][b0:b1], non_blocking=True)
+                for k in self.fields + self.scalars:
+                    din[k][:nb].copy_(host[k][b0:b1], non_blocking=True)
+                ev_in[slot] = self.s_in.record_event()
+            comp.wait_event(ev_in[slot])
+            if ev_free_out[slot] is not None:
+                comp.wait_event(ev_free_out[slot])
+            a = {k: din[k][:nb] for k in self.fields + self.scalars}
+            a["kx"] = din["kx"][:nr]
+            a["sample_real"] = din["sample_real"][:nb]
+            if r0:
+                a["sample_real"].sub_(r0)
+            out = [t[:nb] for t in dout]
+            if self.gc:
+                fw = eng.forward_gc(**a)
+                self.terms.add_(fw["terms"])
+                eng.backward_gc(dterms=self.dterms, out=out, **a)
+            else:
+                fw = eng.forward(**a)
+                self.terms.add_(fw["terms"])
+                eng.backward(dterms=self.dterms, out=out, **a)
+            ev_comp[slot] = comp.record_event()
+            ev_free_in[slot] = ev_comp[slot]
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_comp[slot])
+                for n, t in zip(self.gnames, out):
+                    self.hout[n][b0:b1].copy_(t, non_blocking=True)
+                ev_free_out[slot] = self.s_out.record_event()
+        if reduce_terms is not None:
+            reduce_terms(self.terms)
+        self.hterms.copy_(self.terms, non_blocking=True)
+        comp.wait_stream(self.s_out)
+        torch.cuda.synchronize(eng.device)
+        return self.hterms, self.hout

@@ -280,32 +280,18 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = world * N * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with host buffers: srm.engine.HostPipeline (chunks of whole
+    # realisations; H2D, kernels and D2H overlap on three streams)
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
-    gnames = ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2") if gc else ("gp0", "gp1", "gdt1", "gdt2")
-    out_host = {k: (torch.empty_like(host["dt1"]) if k.startswith("gdt") else torch.empty_like(host["p0"])).pin_memory()
-                for k in gnames}
-    out_host["terms"] = torch.empty((2, 8), dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
-
-    def e2e_step():
-        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        fw = fwd(**dd)
-        if distributed:
-            srm.dist.allreduce_terms(fw["terms"])
-        g = bwd(dterms=dterms, **dd)
-        out_host["terms"].copy_(fw["terms"], non_blocking=True)
-        for k, v in zip(gnames, g):
-            out_host[k].copy_(v, non_blocking=True)
-        torch.cuda.synchronize(dev)
-
+    pipe = srm.engine.HostPipeline(eng, host, dterms, n_chunks=args.e2e_chunks)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    red = srm.dist.allreduce_terms if distributed else None
     e2e_steps = max(1, min(args.steps, 5))
-    e2e_step()
+    pipe.step(red)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
+        hterms, hgrads = pipe.step(red)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -313,7 +299,14 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N * e2e_steps / float(te.item())
-    loss = float((out_host["terms"][0] * dterms.cpu()).sum())
+    loss = float((hterms[0] * dterms.cpu()).sum())
+    # the chunked pipeline must reproduce the resident run: terms are additive over samples
+    ref_terms = step()[0]
+    if distributed:
+        pass        # step() already all-reduced
+    torch.cuda.synchronize(dev)
+    if not torch.allclose(hterms[0], ref_terms[0].cpu(), rtol=1e-5):
+        raise SystemExit(f"bench.py: e2e pipeline terms {hterms[0].tolist()} != resident terms {ref_terms[0].cpu().tolist()}")
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -340,7 +333,8 @@ def run_ours(args):
                          "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "loss": loss},
+                    "steps": e2e_steps, "loss": loss,
+                    "api": f"srm.engine.HostPipeline.step: pinned host batch, {len(pipe.chunks)} chunks of whole realisations, H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -360,6 +354,7 @@ def main():
     ap.add_argument("--numerics", default="reference", choices=["reference", "closed_form"])
     ap.add_argument("--K", type=int, default=0, help="override realisations per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="realisation chunks of the host-buffer pipeline")
     ap.add_argument("--no-pvt-lut", action="store_true", help="reference numerics: evaluate the 37-term spline per cell instead of the exact table")
     args = ap.parse_args()
     if args.impl == "reference":
