@@ -182,6 +182,24 @@ class SrmPhysics:
         self.launches += 1
         return tuple(outs)
 
+    def wells_gc(self, kx, sample_real, p, sg, t_days):
+        """WellRatesPressure.compute_rates_and_bhp, GC (well_rate_bhp_Subclassed.py:727-837): dense (qgg, qgo, qoo, qog)
+        and pwf fields, zero off-well, duplicates summed (scatter_nd).  The well kernel runs inside srm_forward_gc; the
+        rates do not depend on the time-level-n fields or the time steps, so neutral values stand in for them."""
+        B, nw = p.shape[0], self.n_wells
+        one = torch.ones(B, dtype=torch.float32, device=self.device)
+        so = (1.0 - float(self.spec.end_points["Swmin"])) - sg
+        fw = self.forward_gc(kx, sample_real, p, p, sg, sg, so, so, one, one, t_days, want_wells=True, save_for_backward=False)
+        N = self.spec.n_cells
+        dense = torch.zeros((5, B, N), dtype=torch.float32, device=self.device)
+        if nw:
+            cells = torch.tensor([(w.k * self.spec.H + w.j) * self.spec.W + w.i for w in self.spec.wells], dtype=torch.long,
+                                 device=self.device)
+            vals = torch.cat([fw["q4w"], fw["pwfw"].unsqueeze(0)], dim=0)           # (5, B, nw), caller's well order
+            dense.index_add_(2, cells, vals)
+        dense = dense.reshape((5,) + tuple(p.shape))
+        return tuple(dense[:4]), dense[4]
+
     def forward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, want_dom: bool = False,
                    want_wells: bool = False, save_for_backward: bool = True):
         B, R = p0.shape[0], kx.shape[0]

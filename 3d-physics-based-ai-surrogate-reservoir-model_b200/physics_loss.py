@@ -44,6 +44,27 @@ class _SrmPhysicsFn(torch.autograd.Function):
         return None, None, None, None, gp0, gp1, gdt1, gdt2
 
 
+class _SrmPhysicsGcFn(torch.autograd.Function):
+    """gas condensate: terms = srm_forward_gc(...); cotangents of p, Sg, So at both levels and of dt1, dt2"""
+
+    @staticmethod
+    def forward(ctx, engine, kx, sample_real, t1, p0, p1, sg0, sg1, so0, so1, dt1, dt2):
+        c = [t.detach().contiguous() for t in (p0, p1, sg0, sg1, so0, so1, dt1, dt2)]
+        fw = engine.forward_gc(kx, sample_real, *c, t1, save_for_backward=True)
+        terms = fw["terms"]
+        sdist.allreduce_terms(terms)
+        ctx.engine = engine
+        ctx.save_for_backward(kx, sample_real, t1, *c)
+        return terms
+
+    @staticmethod
+    def backward(ctx, gterms):
+        kx, sample_real, t1, *c = ctx.saved_tensors
+        dterms = gterms[0].contiguous().to(torch.float32)
+        g = ctx.engine.backward_gc(kx, sample_real, *c, t1, dterms)
+        return (None, None, None, None) + tuple(g)
+
+
 class _OptimizerSlot:
     def __init__(self, optimizer):
         self.optimizer = optimizer
@@ -62,28 +83,35 @@ class PhysicsLoss:
     def __init__(self, main_model, pvt_model, time_step_model, well_rate_bhp_model, saturation_model=None,
                  optimizer_model_names_map: Optional[Dict[str, str]] = None, *, optimizers: Optional[Dict[str, object]] = None,
                  general_config: Optional[dict] = None, kx_stats=(0.26, 24.0), weights: Optional[Dict[str, float]] = None):
-        if saturation_model is not None:
-            raise NotImplementedError("two-phase (GC) loss is not built; saturation_model must be None")
         self.main_model = main_model
         self.pvt_model = pvt_model
         self.time_step_model = time_step_model
         self.well_rate_bhp_model = well_rate_bhp_model
-        self.saturation_model = None
+        self.saturation_model = saturation_model
         self.engine = getattr(pvt_model, "engine", None) or getattr(well_rate_bhp_model, "engine", None)
         if self.engine is None:
             raise ValueError("pvt_model / well_rate_bhp_model must carry an SrmPhysics engine")
+        if (saturation_model is not None) != (self.engine.fluid == "GC"):
+            raise ValueError("saturation_model goes with a gas-condensate ('GC') engine, and only with one")
         g = {**DEFAULT_GENERAL, **(general_config or {})}
         self.general_config = g
         self.physics_mode_fraction = float(g["physics_mode_fraction"])           # training.py:605
-        self.fluid_type = "DG"
-        self.loss_keys = {"gas": list(LOSS_KEYS)}                               # training.py:559-560
+        self.fluid_type = self.engine.fluid
+        # training.py:559-560.  The legacy two-phase arithmetic sums the gas and oil equations into ONE residual
+        # per term (physics_loss.py:638,650,665,680), so the GC terms are reported under 'gas' and 'oil' holds zeros.
+        self.loss_keys = {"gas": list(LOSS_KEYS)}
+        if self.fluid_type == "GC":
+            self.loss_keys["oil"] = list(LOSS_KEYS)
         w = dict(g["default_weights"]["gas"])
         if weights:
             w.update(weights)
         self.weights = w
-        self.optimizer_model_names_map = optimizer_model_names_map or {"pressure": "pressure", "time_step": "time_step"}
+        default_map = {"pressure": "pressure", "time_step": "time_step"}
+        if saturation_model is not None:
+            default_map["saturation"] = "saturation"
+        self.optimizer_model_names_map = optimizer_model_names_map or default_map
         self.trainable_models_keys = list(self.optimizer_model_names_map.keys())  # training.py:554
-        by_key = {"pressure": main_model, "time_step": time_step_model}
+        by_key = {"pressure": main_model, "time_step": time_step_model, "saturation": saturation_model}
         self.trainable_models = [by_key[k] for k in self.trainable_models_keys]   # training.py:553
         self.optimizer_model_map = {k: _OptimizerSlot((optimizers or {}).get(k)) for k in self.trainable_models_keys}
         self.t_min, self.t_max = float(g["srm_start_time"]), float(g["srm_end_time"])
@@ -122,7 +150,14 @@ class PhysicsLoss:
         p1 = self.main_model(x1)[..., 0]                                          # physics_loss.py:111-115
         dt2 = self.time_step_model(x1).reshape(B, -1).mean(dim=1)                 # physics_loss.py:122
         t1 = self._time_days(x1).detach().contiguous()
-        terms = _SrmPhysicsFn.apply(eng, kx, sample_real, t1, p0, p1, dt1, dt2)
+        if self.fluid_type == "GC":
+            top = 1.0 - float(eng.spec.end_points["Swmin"])
+            sg0 = self.saturation_model(x)[..., 0]                                # physics_loss.py:331,373
+            sg1 = self.saturation_model(x1)[..., 0]
+            so0, so1 = top - sg0, top - sg1                                       # relative_permeability.py:58
+            terms = _SrmPhysicsGcFn.apply(eng, kx, sample_real, t1, p0, p1, sg0, sg1, so0, so1, dt1, dt2)
+        else:
+            terms = _SrmPhysicsFn.apply(eng, kx, sample_real, t1, p0, p1, dt1, dt2)
         wvec = torch.tensor([self.weights[k] for k in self.loss_keys["gas"]], device=eng.device)
         slots = torch.tensor([_SLOT[k] for k in self.loss_keys["gas"]], device=eng.device)
         wsse = wvec * terms[0][slots]                                             # physics_loss.py:809-819
@@ -136,4 +171,8 @@ class PhysicsLoss:
             i += len(ps)
         counts = terms[1][slots]
         wmse = wsse / torch.clamp(counts, min=1.0)                                # zeros_to_ones, :835-846
-        return [wmse.detach()], out, [wsse.detach()], [counts.detach()], p0.detach().unsqueeze(-1)
+        phases = [wmse.detach()], [wsse.detach()], [counts.detach()]
+        if self.fluid_type == "GC":
+            for lst in phases:
+                lst.append(torch.zeros_like(lst[0]))
+        return phases[0], out, phases[1], phases[2], p0.detach().unsqueeze(-1)

@@ -68,19 +68,20 @@ class WellDataProcessor:
 
 class WellRatesPressure:
     """compute_rates_and_bhp(x_n1, p_n1, Sg_n1, relperm_model, model_PVT, q_target=None, shutin_days=None)
-    -> (qg, pwf), both (B, D, H, W, 1), zero off-well   (well_rate_bhp_Subclassed.py:727-837, DG)."""
+    -> DG: (qg, pwf);  GC: ((qgg, qgo, qoo, qog), pwf) -- every field (B, D, H, W, 1), zero off-well
+    (well_rate_bhp_Subclassed.py:727-837)."""
 
     def __init__(self, engine, fluid_type="DG", use_blocking_factor=None, n_intervals=None, use_non_iterative=True,
                  general_config=None, kx_stats=(0.26, 24.0), t_range=(0.0, 365.0), norm_limits=(-1.0, 1.0)):
-        if fluid_type.upper() != "DG":
-            raise NotImplementedError("only the dry-gas well model is built")
+        if fluid_type.upper() != engine.fluid:
+            raise ValueError(f"fluid_type {fluid_type!r} does not match the engine ({engine.fluid})")
         if not use_non_iterative:
             raise NotImplementedError("only the non-iterative BHP control (the reference default) is built")
         spec: PhysicsSpec = engine.spec
         if use_blocking_factor is not None and bool(use_blocking_factor) != bool(spec.use_blocking_factor):
             raise ValueError("use_blocking_factor must match the engine's PhysicsSpec")
         self.engine = engine
-        self.fluid_type = "DG"
+        self.fluid_type = engine.fluid
         self.use_blocking_factor = spec.use_blocking_factor
         self.n_intervals = spec.n_intervals
         self.k_min, self.k_max = kx_stats
@@ -99,5 +100,12 @@ class WellRatesPressure:
         tn = x[:, 0, 0, 0, 3]
         t = ((self.t_max - self.t_min) * ((tn - self.lo) / (self.hi - self.lo)) + self.t_min).contiguous()
         p = p_n1.to(eng.device, torch.float32).reshape(x.shape[:-1]).contiguous()
-        out = eng.wells(kx, torch.arange(B, dtype=torch.int32, device=eng.device), p, t, dense=True)
+        sr = torch.arange(B, dtype=torch.int32, device=eng.device)
+        if self.fluid_type == "GC":
+            if Sg_n1 is None:
+                raise ValueError("the gas-condensate well model needs Sg_n1")
+            sg = Sg_n1.to(eng.device, torch.float32).reshape(x.shape[:-1]).contiguous()
+            q4, pwf = eng.wells_gc(kx, sr, p, sg, t)
+            return tuple(q.unsqueeze(-1) for q in q4), pwf.unsqueeze(-1)
+        out = eng.wells(kx, sr, p, t, dense=True)
         return out["q"].unsqueeze(-1), out["pwf"].unsqueeze(-1)
