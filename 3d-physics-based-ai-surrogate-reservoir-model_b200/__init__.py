@@ -11,10 +11,10 @@ The directory name is not a Python identifier; import it with
 """
 from . import _lib, config, pvt, synth  # noqa: F401
 from .config import PhysicsSpec, spec_from_reference_configs  # noqa: F401
-from .pvt import PVTLayer, build_spline_tables, load_default_pvt_table  # noqa: F401
+from .pvt import PVTLayer, build_polynomial_tables, build_spline_tables, load_default_pvt_table  # noqa: F401
 
 __all__ = ["_lib", "config", "pvt", "synth", "PhysicsSpec", "spec_from_reference_configs", "PVTLayer",
-           "build_spline_tables", "load_default_pvt_table"]
+           "build_spline_tables", "build_polynomial_tables", "load_default_pvt_table"]
 
 
 def __getattr__(name):

@@ -129,12 +129,13 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
                 p_min: float, p_max: float, wells: Sequence[dict], use_blocking_factor: bool, n_intervals: int,
                 numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG, pvt_lut: bool = False,
                 lut_range: Optional[Sequence[float]] = None, end_points: Optional[dict] = None,
-                corey_exponents: Optional[dict] = None):
+                corey_exponents: Optional[dict] = None, pvt_method: int = SRM_PVT_SPLINE):
     """Fill an SrmConfig; returns (cfg, keepalive) -- keepalive owns the host arrays cfg points into."""
     knots = np.ascontiguousarray(knots, dtype=np.float32)
     spline_w = np.ascontiguousarray(spline_w, dtype=np.float32)
     spline_v = np.ascontiguousarray(spline_v, dtype=np.float32)
-    assert spline_w.shape == (spline_v.shape[0], knots.size) and spline_v.shape[1] == 2
+    if pvt_method == SRM_PVT_SPLINE:
+        assert spline_w.shape == (spline_v.shape[0], knots.size) and spline_v.shape[1] == 2
     warr = (SrmWell * max(1, len(wells)))()
     for n, w in enumerate(wells):
         warr[n] = SrmWell(int(w["i"]), int(w["j"]), int(w["k"]), float(w["q_target"]), float(w["pwf_min"]),
@@ -142,7 +143,8 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
     cfg = SrmConfig(
         abi_version=SRM_ABI_VERSION, device=device, D=D, H=H, W=W, dx=dx, dy=dy, dz=dz, C=C_, Dc=Dc,
         phi=phi, cf=cf, Sgi=Sgi, krg=krg, kx_ky=kx_ky, kv_kh=kv_kh, fluid_type=fluid_type,
-        pvt_method=SRM_PVT_SPLINE, spline_order=spline_order, n_knots=knots.size, n_props=spline_w.shape[0],
+        pvt_method=int(pvt_method), spline_order=spline_order,
+        n_knots=knots.size if pvt_method == SRM_PVT_SPLINE else spline_w.shape[1], n_props=spline_w.shape[0],
         knots=_fptr(knots), spline_w=_fptr(spline_w), spline_v=_fptr(spline_v), p_min=p_min, p_max=p_max,
         n_wells=len(wells), wells=warr, use_blocking_factor=int(bool(use_blocking_factor)),
         n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)),

@@ -56,17 +56,21 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     if (cfg->n_props != 7) { srm_set_error("srm_create: SRM_FLUID_GC needs the 7 GC properties (InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro), got %d", cfg->n_props); return SRM_ERR_INVALID; }
     if (cfg->numerics != SRM_NUMERICS_REFERENCE) { srm_set_error("srm_create: SRM_FLUID_GC is built for SRM_NUMERICS_REFERENCE only"); return SRM_ERR_INVALID; }
     if (cfg->use_blocking_factor) { srm_set_error("srm_create: the GC blocking-factor integral (well_rate_bhp_Subclassed.py:897-911) is not built"); return SRM_ERR_INVALID; }
-    if (cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
+    if (cfg->pvt_method == SRM_PVT_SPLINE && cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
   }
-  if (cfg->pvt_method != SRM_PVT_SPLINE) { srm_set_error("srm_create: only SRM_PVT_SPLINE is implemented"); return SRM_ERR_INVALID; }
-  if (cfg->n_knots < 2 || cfg->n_knots > SRM_MAXK || cfg->n_props < 2 || cfg->n_props > SRM_MAXP ||
-      !cfg->knots || !cfg->spline_w || !cfg->spline_v) {
-    srm_set_error("srm_create: bad spline table (n_knots=%d, n_props=%d)", cfg->n_knots, cfg->n_props);
+  const bool poly = cfg->pvt_method == SRM_PVT_POLYNOMIAL;
+  if (cfg->pvt_method != SRM_PVT_SPLINE && !poly) { srm_set_error("srm_create: unknown pvt_method %d", cfg->pvt_method); return SRM_ERR_INVALID; }
+  if (cfg->n_knots < (poly ? 1 : 2) || cfg->n_knots > SRM_MAXK || cfg->n_props < 2 || cfg->n_props > SRM_MAXP || !cfg->spline_w ||
+      (!poly && (!cfg->knots || !cfg->spline_v))) {
+    srm_set_error("srm_create: bad PVT table (n_knots=%d, n_props=%d)", cfg->n_knots, cfg->n_props);
     return SRM_ERR_INVALID;
   }
-  if (cfg->spline_order != 1 && cfg->spline_order != 2) { srm_set_error("srm_create: spline_order must be 1 or 2"); return SRM_ERR_INVALID; }
-  for (int i = 1; i < cfg->n_knots; ++i)
-    if (!(cfg->knots[i] > cfg->knots[i - 1])) { srm_set_error("srm_create: knots must be strictly ascending"); return SRM_ERR_INVALID; }
+  if (!poly) {
+    if (cfg->spline_order != 1 && cfg->spline_order != 2) { srm_set_error("srm_create: spline_order must be 1 or 2"); return SRM_ERR_INVALID; }
+    for (int i = 1; i < cfg->n_knots; ++i)
+      if (!(cfg->knots[i] > cfg->knots[i - 1])) { srm_set_error("srm_create: knots must be strictly ascending"); return SRM_ERR_INVALID; }
+  }
+  if (poly && cfg->numerics != SRM_NUMERICS_REFERENCE) { srm_set_error("srm_create: the polynomial PVT fit is built for SRM_NUMERICS_REFERENCE"); return SRM_ERR_INVALID; }
   if (cfg->n_wells < 0 || (cfg->n_wells > 0 && !cfg->wells)) { srm_set_error("srm_create: bad wells"); return SRM_ERR_INVALID; }
   if (cfg->numerics != SRM_NUMERICS_REFERENCE && cfg->numerics != SRM_NUMERICS_CLOSED_FORM) {
     srm_set_error("srm_create: unknown numerics %d", cfg->numerics);
@@ -127,12 +131,13 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   P.kr_sg_full = 1.0f - (cfg->Swmin + cfg->Sorg);
   auto as_int = [](float e) { return (e >= 1.f && e <= 16.f && e == std::floor(e)) ? (int)e : 0; };
   P.nog_i = as_int(cfg->nog); P.ng_i = as_int(cfg->ng);
+  P.pvt_method = cfg->pvt_method;
   for (int i = 0; i < cfg->n_knots; ++i) {
-    P.c[i] = cfg->knots[i];
-    P.c2[i] = cfg->knots[i] * cfg->knots[i];
+    if (!poly) { P.c[i] = cfg->knots[i]; P.c2[i] = cfg->knots[i] * cfg->knots[i]; }
     for (int q = 0; q < cfg->n_props; ++q) P.w[q][i] = cfg->spline_w[q * cfg->n_knots + i];
   }
-  for (int q = 0; q < cfg->n_props; ++q) { P.v[q][0] = cfg->spline_v[2 * q]; P.v[q][1] = cfg->spline_v[2 * q + 1]; }
+  if (!poly)
+    for (int q = 0; q < cfg->n_props; ++q) { P.v[q][0] = cfg->spline_v[2 * q]; P.v[q][1] = cfg->spline_v[2 * q + 1]; }
 
   // wells: [k,j,i] -> flat cell, sorted (stable) by cell; integer work, bit-exact
   P.n_wells = cfg->n_wells;
@@ -151,7 +156,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     if (e != cudaSuccess) { srm_set_error("srm_create: wells upload: %s", cudaGetErrorString(e)); srm_destroy(h); return SRM_ERR_CUDA; }
     P.wells = h->d_wells;
   }
-  if (cfg->spline_order == 1) {
+  if (!poly && cfg->spline_order == 1) {
     int rc = srm_build_closed_form(h, cfg);
     if (rc) { srm_destroy(h); return rc; }
   }

@@ -98,10 +98,10 @@ __device__ __forceinline__ GcPack0 gc_pack0(const SrmDev& P, float x0) {
   GcPack0 o;
   float v[2], d[2], d2[2];
   d2[0] = d2[1] = 0.f;
-  srm_spline_ref<2, true, SAVE>(P, 0, x0, v, d, d2);          // InvBg, InvBo
+  srm_pvt_ref<2, true, SAVE>(P, 0, x0, v, d, d2);          // InvBg, InvBo
   o.v[0] = v[0]; o.v[1] = v[1]; o.v[4] = d[0]; o.v[5] = d[1]; o.v[8] = d2[0]; o.v[9] = d2[1];
   d2[0] = d2[1] = 0.f;
-  srm_spline_ref<2, true, SAVE>(P, 4, x0, v, d, d2);          // Rs, Rv
+  srm_pvt_ref<2, true, SAVE>(P, 4, x0, v, d, d2);          // Rs, Rv
   o.v[2] = v[0]; o.v[3] = v[1]; o.v[6] = d[0]; o.v[7] = d[1]; o.v[10] = d2[0]; o.v[11] = d2[1];
   return o;
 }
@@ -111,7 +111,7 @@ __device__ __forceinline__ GcPack1 gc_pack1(const SrmDev& P, float x1) {
   float v[6], d[6], d2[6];
 #pragma unroll
   for (int q = 0; q < 6; ++q) d[q] = 0.f;
-  srm_spline_ref<6, SAVE, false>(P, 0, x1, v, d, d2);         // InvBg, InvBo, Invug, Invuo, Rs, Rv
+  srm_pvt_ref<6, SAVE, false>(P, 0, x1, v, d, d2);         // InvBg, InvBo, Invug, Invuo, Rs, Rv
   const float a = v[0], b = v[1], ug = v[2], uo = v[3], rs = v[4], rv = v[5];
   const float r = __fmul_rn(rs, b), vv = __fmul_rn(rv, a);                     // physics_loss.py:388-389
   o.v[0] = __fmul_rn(a, ug);                                                   // :386
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev
   float m1;
   const float x1 = srm_clamp(P, pv, m1);
   float v[6], d[6], d2[6];
-  srm_spline_ref<6, true, false>(P, 0, x1, v, d, d2);
+  srm_pvt_ref<6, true, false>(P, 0, x1, v, d, d2);
   const D2 invBg = mk(v[0], d[0] * m1), invBo = mk(v[1], d[1] * m1), invug = mk(v[2], d[2] * m1), invuo = mk(v[3], d[3] * m1),
            Rs = mk(v[4], d[4] * m1), Rv = mk(v[5], d[5] * m1);
   const D2 mgg = krgo * invBg * invug;                                           // :802-807

@@ -27,7 +27,7 @@ struct MobilityRef {
     float pass;
     const float x = srm_clamp(P, p.v, pass);
     float v[2], d[2], d2[2];
-    srm_spline_ref<2, true, false>(P, 0, x, v, d, d2);
+    srm_pvt_ref<2, true, false>(P, 0, x, v, d, d2);
     const float kA = __fmul_rn(P.krg, v[0]);
     const float mg = __fmul_rn(kA, v[1]);
     const float dmg = P.krg * (d[0] * v[1] + v[0] * d[1]) * pass * p.d;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kThreads) k_pvt_eval_ref(const __grid_constant
   float pass;
   const float x = srm_clamp(P, p[g], pass);
   float v[NP], d[NP], d2[NP];
-  srm_spline_ref<NP, true, false>(P, 0, x, v, d, d2);
+  srm_pvt_ref<NP, true, false>(P, 0, x, v, d, d2);
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
     if (val) val[(int64_t)q * n + g] = v[q];
@@ -66,14 +66,14 @@ template <bool D2>
 __device__ __forceinline__ float4 pvt_pack0(const SrmDev& P, float x0) {
   float v[1], d[1], d2[1];
   d2[0] = 0.f;
-  srm_spline_ref<1, true, D2>(P, 0, x0, v, d, d2);
+  srm_pvt_ref<1, true, D2>(P, 0, x0, v, d, d2);
   return make_float4(v[0], d[0], d2[0], 0.f);
 }
 template <bool D1>
 __device__ __forceinline__ float4 pvt_pack1(const SrmDev& P, float x1) {
   float v[2], d[2], d2[2];
   d[0] = d[1] = 0.f;
-  srm_spline_ref<2, D1, false>(P, 0, x1, v, d, d2);
+  srm_pvt_ref<2, D1, false>(P, 0, x1, v, d, d2);
   return make_float4(v[0], __fmul_rn(v[0], v[1]), d[0], __fmaf_rn(d[0], v[1], __fmul_rn(v[0], d[1])));
 }
 

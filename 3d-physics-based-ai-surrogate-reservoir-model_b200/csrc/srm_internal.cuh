@@ -34,7 +34,8 @@ struct SrmDev {
   int32_t n_wells;
   const WellDev* wells;  // device, sorted by cell
   // spline
-  int32_t n_knots, order, n_props;
+  int32_t n_knots, order, n_props;   // polynomial fit: n_knots = number of coefficients, w[q][i] = coefficient i
+  int32_t pvt_method;                // SRM_PVT_*
   float c[SRM_MAXK];
   float c2[SRM_MAXK];            // fl(c*c)
   float w[SRM_MAXP][SRM_MAXK];

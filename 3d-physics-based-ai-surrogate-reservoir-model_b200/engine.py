@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as L
 from .config import PhysicsSpec
-from .pvt import SplineTables
+from .pvt import PolynomialTables, SplineTables
 
 NUMERICS = {"reference": L.SRM_NUMERICS_REFERENCE, "closed_form": L.SRM_NUMERICS_CLOSED_FORM}
 
@@ -37,10 +37,13 @@ class SrmPhysics:
         self.numerics = numerics
         if spec.fluid_type not in ("DG", "GC"):
             raise ValueError(f"fluid_type {spec.fluid_type!r}: 'DG' (dry gas) or 'GC' (gas condensate)")
+        poly = isinstance(tables, PolynomialTables)
         cfg, self._keep = L.make_config(
             device=device, D=spec.D, H=spec.H, W=spec.W, dx=spec.dx, dy=spec.dy, dz=spec.dz, C_=spec.C, Dc=spec.Dc,
             phi=spec.phi, cf=spec.cf, Sgi=spec.Sgi, krg=spec.krg, kx_ky=spec.kx_ky, kv_kh=spec.kv_kh,
-            knots=tables.knots, spline_w=tables.w, spline_v=tables.v, spline_order=tables.order,
+            knots=np.zeros(1, np.float32) if poly else tables.knots, spline_w=tables.w,
+            spline_v=np.zeros((tables.w.shape[0], 2), np.float32) if poly else tables.v,
+            spline_order=1 if poly else tables.order, pvt_method=L.SRM_PVT_POLYNOMIAL if poly else L.SRM_PVT_SPLINE,
             p_min=spec.p_min, p_max=spec.p_max, wells=[w.as_dict() for w in spec.wells],
             use_blocking_factor=spec.use_blocking_factor, n_intervals=spec.n_intervals,
             numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range,

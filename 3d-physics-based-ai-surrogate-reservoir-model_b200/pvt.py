@@ -101,22 +101,50 @@ def build_spline_tables(table: PVTTable, properties: Sequence[str], order: int =
                         properties=tuple(properties))
 
 
+@dataclass
+class PolynomialTables:
+    """PVTLayer, fitting_method='polynomial' (PVT_Layer_Subclassed.py:77-87,218-266): value = sum_i a_i p^i per
+    property; ``coefficients[q]`` = [a_0, a_1, ...] of property q (all properties padded to one length)."""
+    coefficients: np.ndarray          # (P, n) float32
+    properties: Tuple[str, ...]
+
+    @property
+    def w(self):                      # the engine reads .w for the property count
+        return self.coefficients
+
+
+def build_polynomial_tables(polynomial_config: Dict[str, Sequence[float]], properties: Sequence[str]) -> PolynomialTables:
+    """from a ``polynomial_config`` dict shaped like default_configurations.py:231-234 (keys case-insensitive)"""
+    low = {k.lower(): v for k, v in polynomial_config.items()}
+    rows = []
+    for p in properties:
+        if p.lower() not in low:
+            raise ValueError(f"Polynomial coefficients missing for property: {p}")     # PVT_Layer_Subclassed.py:84-86
+        rows.append(list(low[p.lower()]))
+    n = max(len(r) for r in rows)
+    coef = np.zeros((len(rows), n), dtype=np.float32)
+    for q, r in enumerate(rows):
+        coef[q, :len(r)] = np.asarray(r, dtype=np.float32)
+    return PolynomialTables(coefficients=coef, properties=tuple(properties))
+
+
 class PVTLayer:
     """Drop-in for the reference's ``PVTLayer`` call contract (PVT_Layer_Subclassed.py:146-216):
 
         out = layer(p)      # p: (B, *spatial, 1) pressure  ->  out: (2, n_prop, B, *spatial, 1)
 
     ``out[0]`` are the property values, ``out[1]`` their derivatives w.r.t. the clamped pressure.
-    Only the spline fitting method is implemented; ``engine`` is the SrmPhysics handle that owns the
-    device tables (so the loss and the layer share them).
+    ``engine`` is the SrmPhysics handle that owns the device tables (so the loss and the layer share them); the
+    fitting method (spline or polynomial) is the one its tables were built for.
     """
 
-    def __init__(self, engine, fluid_type: str = "DG", fitting_method: str = "spline", name: str = "pvt_layer"):
-        if fitting_method.lower() != "spline":
-            raise NotImplementedError("PVTLayer: only fitting_method='spline' is implemented on the CUDA path")
+    def __init__(self, engine, fluid_type: str = "DG", fitting_method: Optional[str] = None, name: str = "pvt_layer"):
+        have = "polynomial" if isinstance(engine.tables, PolynomialTables) else "spline"
+        if fitting_method is not None and fitting_method.lower() != have:
+            raise ValueError(f"PVTLayer: the engine's tables are {have!r}, not {fitting_method!r}")
         self.engine = engine
         self.fluid_type = fluid_type.upper()
-        self.fitting_method = "spline"
+        self.fitting_method = have
         self.properties = list(DG_PROPERTIES if self.fluid_type == "DG" else GC_PROPERTIES)
         self.name = name
         self.trainable_variables = []

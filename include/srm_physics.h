@@ -90,7 +90,9 @@ typedef struct SrmConfig {
   float kx_ky, kv_kh;
   int32_t fluid_type;    /* SRM_FLUID_* */
   /* PVT (PVT_Layer_Subclassed.py:23-216; polyhm_splines.py) -- host pointers, copied at create */
-  int32_t pvt_method;    /* SRM_PVT_* */
+  int32_t pvt_method;    /* SRM_PVT_*.  SRM_PVT_POLYNOMIAL (PVTLayer.evaluate_polynomial, PVT_Layer_Subclassed.py:218-266):
+                          * n_knots = number of coefficients, spline_w[q][i] = coefficient a_i of property q
+                          * (value = sum a_i p^i), knots / spline_v / spline_order unused */
   int32_t spline_order;  /* 1 (example) or 2 (default config) */
   int32_t n_knots;       /* <= 64 */
   int32_t n_props;       /* DG: 2 [invBg, invug] */

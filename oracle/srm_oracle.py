@@ -228,6 +228,46 @@ def build_spline_table(columns: Dict[str, np.ndarray], props: Sequence[str], ord
     return SplineTable(c=c, f=np.stack(fs), w=np.stack(ws), v=np.stack(vs), order=order, lam=lam, names=tuple(props))
 
 
+@dataclass
+class PolyTable:
+    """PVTLayer, fitting_method='polynomial' (PVT_Layer_Subclassed.py:77-87): coefficients [a_0, a_1, ...] per property"""
+    coef: np.ndarray         # (P, n) float32
+    names: Tuple[str, ...]
+    order: int = 0
+
+
+def poly_eval_np(x, tab: PolyTable, prop: int, dtype=np.float32, need=2):
+    """PVTLayer.evaluate_polynomial (PVT_Layer_Subclassed.py:218-266), every line one rounded op:
+        value = sum_i a_i * pow(x, i)               accumulated from zero, i ascending     :239-245
+        d1    = sum_{i>=1} (i*a_i) * pow(x, i-1)    the layer's explicit derivative        :248-255
+        d2    = TF's gradient of d1: sum_{i>=2} (i*a_i) * ((i-1) * pow(x, i-2))
+    tf.pow with the integer exponents is pinned as the left-to-right product (pow(x,0)=1, pow(x,1)=x)."""
+    t = dtype
+    x = np.asarray(x, dtype=t)
+    a = tab.coef[prop].astype(t)
+    acc = np.zeros_like(x)
+    a1 = np.zeros_like(x)
+    a2 = np.zeros_like(x)
+    pw, pwm1, pwm2 = np.ones_like(x), np.zeros_like(x), np.zeros_like(x)
+    for i in range(a.size):
+        acc = acc + a[i] * pw
+        if i >= 1 and need >= 1:
+            ic = t(i) * a[i]
+            a1 = a1 + ic * pwm1
+            if i >= 2 and need >= 2:
+                a2 = a2 + ic * (t(i - 1) * pwm2)
+        pwm2, pwm1 = pwm1, pw
+        pw = x.copy() if i == 0 else pw * x
+    return acc, (a1 if need >= 1 else None), (a2 if need >= 2 else None)
+
+
+def prop_eval_np(x, tab, prop, dtype=np.float32, need=2):
+    """value / d1 / d2 of one property: spline or polynomial fit, whichever table is given"""
+    if isinstance(tab, PolyTable):
+        return poly_eval_np(x, tab, prop, dtype, need)
+    return spline_eval_np(x, tab, prop, dtype, need)
+
+
 def _tf_maximum(x, y):
     """tf.maximum forward+gradient semantics: gradient to x where x >= y (ties -> first arg)."""
     return torch.where(x >= y, x, y)
@@ -335,7 +375,7 @@ class _SplineD1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ph, tab, prop):
         npdt = np.float64 if ph.dtype == torch.float64 else np.float32
-        _, d1, d2 = spline_eval_np(ph.detach().numpy(), tab, prop, npdt, need=2)
+        _, d1, d2 = prop_eval_np(ph.detach().numpy(), tab, prop, npdt, need=2)
         ctx.save_for_backward(torch.from_numpy(np.ascontiguousarray(d2)))
         return torch.from_numpy(np.ascontiguousarray(d1))
 
@@ -351,7 +391,7 @@ class _SplineVal(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ph, tab, prop):
         npdt = np.float64 if ph.dtype == torch.float64 else np.float32
-        val, d1, _ = spline_eval_np(ph.detach().numpy(), tab, prop, npdt, need=1)
+        val, d1, _ = prop_eval_np(ph.detach().numpy(), tab, prop, npdt, need=1)
         ctx.save_for_backward(torch.from_numpy(np.ascontiguousarray(d1)))
         return torch.from_numpy(np.ascontiguousarray(val))
 

@@ -317,3 +317,29 @@ print("ADJ4 OK")
     env = dict(os.environ, SRM_ADJ4="1")
     out = subprocess.run([sys.executable, "-c", code], cwd=U.ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ADJ4 OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+def test_polynomial_pvt_fit(pvt_lut):
+    """fitting_method='polynomial' (PVT_Layer_Subclassed.py:218-266): PVT values and derivatives bit-exact, the dry-gas
+    forward bit-exact and the gradients within the gate, with per-cell evaluation and through the exact table"""
+    from test_oracle import _poly_tables
+    otab, coef = _poly_tables()
+    ocfg, _, spec, _, batch = U.make_case(W=20, H=9, D=3, T=2, K=2, seed=2401, all_layers=True, near_knots=False)
+    ptab = srm.build_polynomial_tables({"invBg": coef[0].tolist(), "invug": coef[1].tolist()}, srm.pvt.DG_PROPERTIES)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut, lut_range=(4200.0, 5100.0))
+    p = torch.linspace(10.0, 10500.0, 4001).cuda()
+    val, der = eng.pvt_eval(p)
+    ph = O.pvt_clamp(p.cpu(), ocfg).numpy()
+    for q in range(2):
+        v, d1, _ = O.poly_eval_np(ph, otab, q, np.float32, need=1)
+        assert np.array_equal(val[q].cpu().numpy(), v) and np.array_equal(der[q].cpu().numpy(), d1)
+    layer = srm.PVTLayer(eng, fitting_method="polynomial")
+    assert tuple(layer(p[:24].reshape(2, 1, 3, 4, 1)).shape) == (2, 2, 2, 1, 3, 4, 1)
+    eng.close()
+    o = U.oracle_run(ocfg, otab, batch)
+    c = U.cuda_run(spec, ptab, batch, pvt_lut=pvt_lut, lut_range=(4200.0, 5100.0))
+    assert U.ulp_diff(c["dom"], o["dom"]) == 0
+    assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
+    for k in ("gp0", "gp1", "gdt1"):
+        assert h3_close(c[k], o[k]), (k, U.rel_to_max(c[k], o[k]))

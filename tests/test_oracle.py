@@ -173,3 +173,41 @@ def test_denormalisation_formulas():
     k = O.denorm_log(x, 0.26, 24.0)
     assert abs(k[0] - 0.26) < 1e-6 and abs(k[-1] - 24.0) < 1e-4
     assert abs(float(O.norm_diff_linear(5.0, 0.0, 365.0)) - 2 * 5.0 / 365.0) < 1e-8
+
+
+def _poly_tables():
+    """cubic fits of the shipped table inside the operating window (the default_configurations.py:231-234
+    coefficients are placeholders: 1 + 0.1 p + 0.01 p^2 is not a formation-volume factor)"""
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    m = (cols["Pre"] >= 3000) & (cols["Pre"] <= 5600)
+    coef = np.stack([np.polyfit(cols["Pre"][m].astype(np.float64), cols[k][m].astype(np.float64), 3)[::-1]
+                     for k in ("InvBg", "Invug")]).astype(np.float32)
+    return O.PolyTable(coef=coef, names=("InvBg", "Invug")), coef
+
+
+def test_polynomial_pvt_oracle():
+    """PVTLayer.evaluate_polynomial restated: value, explicit derivative, and the tape's derivative of it"""
+    tab, coef = _poly_tables()
+    x = np.linspace(3000.0, 5600.0, 257)
+    for q in range(2):
+        v, d1, d2 = O.poly_eval_np(x, tab, q, np.float64)
+        c = coef[q].astype(np.float64)[::-1]
+        assert np.allclose(v, np.polyval(c, x), rtol=1e-12)
+        assert np.allclose(d1, np.polyval(np.polyder(c), x), rtol=1e-12)
+        assert np.allclose(d2, np.polyval(np.polyder(c, 2), x), rtol=1e-12)
+        v32, d32, _ = O.poly_eval_np(x.astype(np.float32), tab, q, np.float32)
+        assert np.allclose(v32, v, rtol=2e-6) and np.allclose(d32, d1, rtol=2e-6)
+    # the DG loss with polynomial PVT: autograd vs fp64 finite differences
+    ocfg, otab, spec, ptab, batch = U.make_case(W=6, H=5, D=2, T=1, K=1, seed=61, near_knots=False)
+    args = [batch.kx.numpy(), batch.p0.numpy().astype(np.float64), batch.p1.numpy().astype(np.float64), batch.dt1.numpy(),
+            batch.dt2.numpy(), batch.t1.numpy(), batch.sample_real.numpy(), U.WEIGHTS]
+    o = O.dg_forward_backward(ocfg, tab, *args, dtype=torch.float64)
+    loss = lambda a: float((O.dg_forward_backward(ocfg, tab, *a, dtype=torch.float64)["terms"] * np.array(U.WEIGHTS)).sum())
+    for which, g in ((1, "gp0"), (2, "gp1")):
+        idx = (0, 1, 2, 3)
+        h = 1e-3
+        ap, am = [x.copy() if hasattr(x, "copy") else x for x in args], [x.copy() if hasattr(x, "copy") else x for x in args]
+        ap[which][idx] += h
+        am[which][idx] -= h
+        fd = (loss(ap) - loss(am)) / (2 * h)
+        assert abs(fd - o[g][idx]) <= 1e-5 * abs(o[g][idx]) + 1e-7 * np.abs(o[g]).max()
