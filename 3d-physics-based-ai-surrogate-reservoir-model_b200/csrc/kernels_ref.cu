@@ -82,15 +82,24 @@ __device__ __forceinline__ float4 pvt_pack1(const SrmDev& P, float x1) {
 // is the reference-order spline itself, evaluated once per distinct input instead of once per cell.
 __global__ void __launch_bounds__(kThreads) k_lut_build(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
                                                         float4* __restrict__ t1, float2* __restrict__ f0,
-                                                        float2* __restrict__ f1) {
+                                                        float2* __restrict__ f1, int* __restrict__ cp_unsafe) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.lut_n) return;
   const float x = __uint_as_float(P.lut_lo_bits + e);
-  const float4 a = pvt_pack0<true>(P, x), b = pvt_pack1<true>(P, x);
-  t0[e] = a;
-  t1[e] = b;
-  f0[e] = make_float2(a.x, a.y);
-  f1[e] = make_float2(b.x, b.y);
+  float4 a = pvt_pack0<true>(P, x);
+  const float4 b = pvt_pack1<true>(P, x);
+  // accumulation coefficient cp = Sgi*(phi*invBg' + (phi*cf)*invBg), physics_loss.py:149-150: a pure function of the
+  // (clamped) pressure as well, so it is tabulated with the spline it is built from
+  a.w = srm_cp_ref(P, a.x, a.y);
+  // interleaved: one 32-byte entry {pack0, pack1} (adjoint) and one 16-byte entry {invBg, cp, invBg, G} (forward) per
+  // pressure, so a kernel addresses both time levels from ONE base
+  t0[2 * (size_t)e] = a;
+  t1[2 * (size_t)e] = b;
+  f0[2 * (size_t)e] = make_float2(a.x, a.w);
+  f1[2 * (size_t)e] = make_float2(b.x, b.y);
+  // div_c's fast path needs |cp| well inside the exponent range (ref_fused.cuh)
+  const float ac = fabsf(a.w);
+  if (!(ac >= 0x1p-60f && ac <= 0x1p60f)) atomicOr(cp_unsafe, 1);
 }
 
 template <bool SAVE>
@@ -424,13 +433,19 @@ int srm_build_pvt_lut(SrmHandle* h, float lo, float hi) {
   if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut needs %.1f MB of device memory: %s", n * 48e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
   P.lut_lo_bits = lo_bits;
   P.lut_n = (uint32_t)n;
-  P.lut0 = h->d_lut;
-  P.lut1 = h->d_lut + n;
-  P.lutf0 = reinterpret_cast<const float2*>(h->d_lut + 2 * n);
-  P.lutf1 = P.lutf0 + n;
-  k_lut_build<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + n, (float2*)P.lutf0, (float2*)P.lutf1);
+  P.lut0 = h->d_lut;                  // entry e at lut0 + 2e
+  P.lut1 = h->d_lut + 1;              //            lut1 + 2e
+  P.lutf0 = reinterpret_cast<const float2*>(h->d_lut + 2 * n);   // lutf0 + 2e
+  P.lutf1 = P.lutf0 + 1;                                         // lutf1 + 2e
+  int* d_flag = nullptr;
+  SRM_CUDA_CHECK(cudaMalloc((void**)&d_flag, sizeof(int)));
+  SRM_CUDA_CHECK(cudaMemset(d_flag, 0, sizeof(int)));
+  k_lut_build<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + 1, (float2*)P.lutf0, (float2*)P.lutf1, d_flag);
   SRM_CUDA_CHECK(cudaGetLastError());
-  SRM_CUDA_CHECK(cudaDeviceSynchronize());
+  int unsafe = 1;
+  SRM_CUDA_CHECK(cudaMemcpy(&unsafe, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_flag);
+  P.cp_safe = unsafe ? 0 : 1;
   return SRM_OK;
 }
 

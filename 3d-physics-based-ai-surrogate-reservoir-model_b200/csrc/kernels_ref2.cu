@@ -154,9 +154,7 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
     const float a5 = __fmul_rn(__fmul_rn(__fmul_rn(fD, GD), P.idz), P.idz);
     const float a6 = __fmul_rn(__fmul_rn(__fmul_rn(fU, GU), P.idz), P.idz);
     // accumulation coefficient                           physics_loss.py:149-150,156
-    const float A0 = e0.x, A0p = e0.y, A1 = A1c;
-    const float cr = __fmul_rn(P.phicf, A0);
-    const float cp = __fmul_rn(P.Sgi, __fadd_rn(__fmul_rn(P.phi, A0p), cr));
+    const float A0 = e0.x, cp = e0.y, A1 = A1c;                    // cp: physics_loss.py:149-150, tabulated with the spline
     const float a5t = __fmul_rn(P.invDc, div_c(cp, by_d1));
     // wells in this cell (scatter_nd sums duplicates)    well_rate_bhp_Subclassed.py:128-132
     float qdv = 0.f, mask = 0.f;
@@ -419,14 +417,16 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-bool srm_ref3_applicable(const SrmDev& P);
-cudaError_t srm_ref3_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
-cudaError_t srm_ref3_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+bool srm_dg4_applicable(const SrmHandle* h);
+cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+cudaError_t srm_dg4_finalize_adj(const void* args, int32_t B, float* gdt1, float* gdt2, cudaStream_t s);
 
-// the 4-cells-per-thread kernels move every field as 16-byte vectors: W % 4 == 0 and 16-byte aligned fields
-static bool use_ref3(const SrmDev& P, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+// the lean kernels (kernels_dg4.cu) need the table over the whole clamp range and vector-aligned fields
+static bool use_dg4(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+  const bool off = getenv("SRM_NO_DG4") != nullptr;     // read per call: the tests compare both kernel families in one process
   auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  return srm_ref3_applicable(P) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
+  return !off && srm_dg4_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
 }
 
 size_t srm_ref2_face_floats(const SrmDev& P) { return (size_t)face_layout(P.D, P.H, P.W).per_real; }
@@ -459,8 +459,8 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   }
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dom_out = dom_out;
-  if (use_ref3(P, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
-    SRM_CUDA_CHECK(srm_ref3_launch_fwd(h, &A, B, s));
+  if (use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+    SRM_CUDA_CHECK(srm_dg4_launch_fwd(h, &A, B, s));
   } else {
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
     if (h->lut_full) k_fwd_ref2<true><<<grid, NT, 0, s>>>(P, A);
@@ -481,11 +481,9 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dterms = dterms; A.gp0 = gp0; A.gp1 = gp1;
-  // the 4-cell adjoint spills at the 128-register cap and is slower than the generic kernel on B200 (0.78 vs 0.57 ms
-  // at cfg2); it stays selectable for tuning (SRM_ADJ4=1)
-  static const bool adj4 = getenv("SRM_ADJ4") != nullptr;
-  if (adj4 && use_ref3(P, p0, p1, ws.dom, nullptr, gp0, gp1)) {
-    SRM_CUDA_CHECK(srm_ref3_launch_adj(h, &A, B, s));
+  const bool dg4 = use_dg4(h, p0, p1, ws.dom, nullptr, gp0, gp1);
+  if (dg4) {
+    SRM_CUDA_CHECK(srm_dg4_launch_adj(h, &A, B, s));
   } else {
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
     if (h->lut_full) k_adj_ref2<true><<<grid, NT, 0, s>>>(P, A);
@@ -497,7 +495,11 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
     k_ibc_adj_ref2<false><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
     SRM_CUDA_CHECK(cudaGetLastError());
   }
-  k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);
-  SRM_CUDA_CHECK(cudaGetLastError());
+  if (dg4) {
+    SRM_CUDA_CHECK(srm_dg4_finalize_adj(&A, B, gdt1, gdt2, s));
+  } else {
+    k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
   return SRM_OK;
 }

@@ -48,11 +48,13 @@ struct SrmDev {
   int32_t nog_i, ng_i;           // integer exponents (0: not integer-valued -> powf)
   int32_t fluid;
   // exact PVT tabulation (SrmConfig.pvt_lut); lut_n == 0: off
-  const float4* lut0;    // [lut_n] {invBg, d/dp, d2/dp2, -} at the fp32 value with bits lut_lo_bits + e
-  const float4* lut1;    // [lut_n] {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
-  const float2* lutf0;   // [lut_n] {invBg, d/dp}            -- the forward's 8-byte views: half the L2 footprint
-  const float2* lutf1;   // [lut_n] {invBg, invBg*invug}
+  // dry gas: entries interleaved, element e of each view at ptr + 2e (kernels_ref.cu, k_lut_build)
+  const float4* lut0;    // {invBg, d/dp, d2/dp2, cp} at the fp32 value with bits lut_lo_bits + e
+  const float4* lut1;    // {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
+  const float2* lutf0;   // {invBg, cp}             -- the forward's 8-byte views: half the L2 footprint
+  const float2* lutf1;   // {invBg, invBg*invug}
   uint32_t lut_lo_bits, lut_n;
+  int32_t cp_safe;       // every tabulated |cp| lies in [2^-60, 2^60]: division by dt1 needs no per-cell range test
 };
 
 // Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory

@@ -294,29 +294,37 @@ def test_pvt_lut_is_bit_identical_to_direct_evaluation(lut_range):
     assert 0.0 < inside < 1.0, "the case must exercise both the table and the direct path"
 
 
-def test_four_cell_adjoint_kernel_matches_oracle():
-    """The 4-cells-per-thread adjoint (kernels_ref3.cu) is not the default on B200 (the generic kernel is
-    faster there); SRM_ADJ4=1 selects it.  It must meet the same gradient gate.  The switch is read once per
-    process, hence the subprocess."""
-    import subprocess
-    import sys
-    code = r'''
-import sys, numpy as np
-sys.path.insert(0, "tests")
-import util as U
-kw = dict(W=136, H=19, D=3, T=2, K=1, seed=2007, all_layers=True)
-ocfg, otab, spec, ptab, batch = U.make_case(**kw)
-o = U.oracle_run(ocfg, otab, batch)
-c = U.cuda_run(spec, ptab, batch, pvt_lut=True)
-assert U.ulp_diff(c["dom"], o["dom"]) == 0
-for k in ("gp0", "gp1", "gdt1"):
-    a, b = np.asarray(c[k], np.float64), np.asarray(o[k], np.float64)
-    assert np.all(np.abs(a - b) <= 1e-5 * np.abs(b) + 1e-5 * np.abs(b).max()), k
-print("ADJ4 OK")
-'''
-    env = dict(os.environ, SRM_ADJ4="1")
-    out = subprocess.run([sys.executable, "-c", code], cwd=U.ROOT, env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "ADJ4 OK" in out.stdout, out.stdout + out.stderr
+DG4_CASES = [
+    dict(W=136, H=19, D=3, T=2, K=1, seed=2007, all_layers=True),     # tiles cut by the grid in x and y
+    dict(W=64, H=64, D=16, T=2, K=2, seed=2008),                      # the cfg2 grid
+    dict(W=34, H=9, D=1, T=3, K=1, seed=2009),                        # one plane; W % 4 != 0
+    dict(W=6, H=5, D=2, T=2, K=2, seed=2010, all_layers=True),        # two planes, grid smaller than a tile
+]
+
+
+@pytest.mark.parametrize("kw", DG4_CASES, ids=lambda k: f"{k['W']}x{k['H']}x{k['D']}")
+def test_lean_kernels_match_oracle_and_generic(kw):
+    """kernels_dg4.cu (exact table over the whole clamp range, W even: plane-ahead gathers, shared face values, split
+    barrier) against the oracle (forward bit-exact, gradients within the gate) and against the generic fused kernels
+    of kernels_ref2.cu, which SRM_NO_DG4 selects (read per call)."""
+    ocfg, otab, spec, ptab, batch = U.make_case(**kw)
+    o = U.oracle_run(ocfg, otab, batch)
+    assert "SRM_NO_DG4" not in os.environ
+    c = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    os.environ["SRM_NO_DG4"] = "1"
+    try:
+        g = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    finally:
+        del os.environ["SRM_NO_DG4"]
+    assert U.ulp_diff(c["dom"], o["dom"]) == 0
+    assert np.array_equal(np.asarray(c["dom"]).view(np.uint32), np.asarray(g["dom"]).view(np.uint32))
+    assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
+    assert np.allclose(c["terms"], g["terms"], rtol=1e-6, atol=0)
+    for k in ("gp0", "gp1", "gdt1"):
+        assert h3_close(c[k], o[k]), (k, U.rel_to_max(c[k], o[k]))
+        assert h3_close(c[k], g[k]), (k, U.rel_to_max(c[k], g[k]))
+    scale = 1e-5 * np.abs(o["gdt1"]).max()                     # gdt2 is rounding noise around an analytic zero
+    assert np.abs(c["gdt2"]).max() <= scale and np.abs(g["gdt2"]).max() <= scale
 
 
 @pytest.mark.parametrize("pvt_lut", LUT_MODES)
