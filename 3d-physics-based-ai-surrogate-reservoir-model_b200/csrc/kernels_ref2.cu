@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+bool srm_dg5_applicable(const SrmHandle* h);
+cudaError_t srm_dg5_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
 bool srm_dg4_applicable(const SrmHandle* h);
 cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
 cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
@@ -427,6 +429,15 @@ static bool use_dg4(const SrmHandle* h, const void* a, const void* b, const void
   const bool off = getenv("SRM_NO_DG4") != nullptr;     // read per call: the tests compare both kernel families in one process
   auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   return !off && srm_dg4_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
+}
+
+// warp-specialised forward (kernels_dg5.cu): W % 4 == 0, at least two planes.  Measured SLOWER than kernels_dg4.cu on
+// B200 (0.64 vs 0.45 ms at cfg2: with one 12-warp CTA per SM the producer/consumer hand-offs and the CTA prologue are
+// not hidden); kept selectable (SRM_DG5=1) as the starting point for a two-CTA variant.
+static bool use_dg5(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+  const bool on = getenv("SRM_DG5") != nullptr && getenv("SRM_NO_DG4") == nullptr;
+  auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return on && srm_dg5_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
 }
 
 size_t srm_ref2_face_floats(const SrmDev& P) { return (size_t)face_layout(P.D, P.H, P.W).per_real; }
@@ -459,7 +470,9 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   }
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dom_out = dom_out;
-  if (use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+  if (use_dg5(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+    SRM_CUDA_CHECK(srm_dg5_launch_fwd(h, &A, B, s));
+  } else if (use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
     SRM_CUDA_CHECK(srm_dg4_launch_fwd(h, &A, B, s));
   } else {
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);

@@ -316,10 +316,17 @@ def test_lean_kernels_match_oracle_and_generic(kw):
         g = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
     finally:
         del os.environ["SRM_NO_DG4"]
+    os.environ["SRM_DG5"] = "1"                                  # the warp-specialised forward (kernels_dg5.cu), opt-in
+    try:
+        w5 = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    finally:
+        del os.environ["SRM_DG5"]
     assert U.ulp_diff(c["dom"], o["dom"]) == 0
     assert np.array_equal(np.asarray(c["dom"]).view(np.uint32), np.asarray(g["dom"]).view(np.uint32))
+    assert np.array_equal(np.asarray(c["dom"]).view(np.uint32), np.asarray(w5["dom"]).view(np.uint32))
     assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
     assert np.allclose(c["terms"], g["terms"], rtol=1e-6, atol=0)
+    assert np.allclose(c["terms"], w5["terms"], rtol=1e-6, atol=0)
     for k in ("gp0", "gp1", "gdt1"):
         assert h3_close(c[k], o[k]), (k, U.rel_to_max(c[k], o[k]))
         assert h3_close(c[k], g[k]), (k, U.rel_to_max(c[k], g[k]))
