@@ -3,7 +3,7 @@
 Only the hot path is here: PVT splines, well sources, the finite-difference
 mass-balance residual and its hand-written adjoint, as sm_100a CUDA kernels behind a C ABI
 (``include/srm_physics.h``, ``libsrm_physics.so``), plus the host-side mirror of the reference's
-``PhysicsLoss`` / ``PVTLayer`` / ``WellRatesPressure`` call contracts.
+``PhysicsLoss`` / ``PVTLayer`` / ``WellRatesPressure`` / ``HardLayer`` call contracts.
 
 The directory name is not a Python identifier; import it with
 ``importlib.import_module("3d-physics-based-ai-surrogate-reservoir-model_b200")`` or through the
@@ -20,12 +20,14 @@ __all__ = ["_lib", "config", "pvt", "synth", "PhysicsSpec", "spec_from_reference
 def __getattr__(name):
     # engine / physics_loss import torch.cuda-facing code lazily
     import importlib
-    if name in ("engine", "physics_loss", "wells", "dist"):
+    if name in ("engine", "physics_loss", "wells", "dist", "hard_layer"):
         return importlib.import_module(f"{__name__}.{name}")
     if name == "SrmPhysics":
         return importlib.import_module(f"{__name__}.engine").SrmPhysics
     if name in ("PhysicsLoss",):
         return getattr(importlib.import_module(f"{__name__}.physics_loss"), name)
+    if name in ("HardLayer", "CompleteTrainableModule"):
+        return getattr(importlib.import_module(f"{__name__}.hard_layer"), name)
     if name in ("WellRatesPressure", "WellDataProcessor"):
         return getattr(importlib.import_module(f"{__name__}.wells"), name)
     raise AttributeError(name)

@@ -28,7 +28,7 @@ SRM_FLAG_SAVE_FOR_BACKWARD = 1
 EXPORTS = (
     "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
     "srm_pvt_eval", "srm_denormalize_log", "srm_selftest_rounding", "srm_wells", "srm_forward", "srm_backward",
-    "srm_relperm", "srm_forward_gc", "srm_backward_gc",
+    "srm_relperm", "srm_forward_gc", "srm_backward_gc", "srm_glue_workspace_bytes", "srm_glue_forward", "srm_glue_backward",
 )
 
 
@@ -102,6 +102,12 @@ def load_library(path: Optional[str] = None):
     lib.srm_forward_gc.argtypes = [vp, i32, i32] + [vp] * 11 + [vp] * 4 + [vp, C.c_size_t, i32, vp]
     lib.srm_backward_gc.restype = C.c_int
     lib.srm_backward_gc.argtypes = [vp, i32, i32] + [vp] * 11 + [vp] + [vp] * 8 + [vp, C.c_size_t, i32, vp]
+    lib.srm_glue_workspace_bytes.restype = C.c_size_t
+    lib.srm_glue_workspace_bytes.argtypes = [i32]
+    lib.srm_glue_forward.restype = C.c_int
+    lib.srm_glue_forward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 11 + [vp, C.c_size_t, vp]
+    lib.srm_glue_backward.restype = C.c_int
+    lib.srm_glue_backward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 14 + [vp]
     if lib.srm_version() != SRM_ABI_VERSION:
         raise RuntimeError(f"libsrm_physics ABI {lib.srm_version()} != binding {SRM_ABI_VERSION}")
     if path == LIB_PATH:

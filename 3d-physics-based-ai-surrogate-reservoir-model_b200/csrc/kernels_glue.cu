@@ -1,0 +1,184 @@
+// The element-wise glue either side of the physics kernels, both time levels in one pass:
+//   HardLayer.call                      Hard_Layer_Subclassed.py:219-242 (via CompleteTrainableModule.call,
+//                                       complete_trainable_module.py:142-176)
+//   per-sample mean of the dt field     physics_loss.py:102,122
+// and their cotangents (what tape.gradient delivers to the networks' outputs and to the layer's kernel_exponent).
+//
+//   p_l[b,c]  = init_value - alpha_t(tn_l[b]) ^ expo[c] * y_l[b,c],   alpha_t(t) = (t - t_lo) / (t_hi - t_lo)
+//   dt_l[b]   = mean_c dtf_l[b,c]
+//
+// HBM bound: forward reads y0, y1, dtf1, dtf2 and writes p0, p1 (24 B per cell-timestep); backward reads gp0, gp1,
+// y0, y1 and writes gy0, gy1, gdtf1, gdtf2 (32 B).  alpha = 2^(e * log2 alpha_t): log2 alpha_t once per sample in
+// fp64, the product split into an fp32 head for ex2 and a first-order tail (~2 ulp against pow()).
+#include <math_constants.h>
+#include <algorithm>
+#include "common.cuh"
+
+namespace {
+
+constexpr int GT = 256;
+
+struct GlueLevel { double l2; float lnat; float at; };      // log2(alpha_t), ln(alpha_t) (0 where alpha_t <= 0), alpha_t
+
+__device__ __forceinline__ GlueLevel glue_level(float tn, float t_lo, float t_hi) {
+  GlueLevel g;
+  g.at = __fdiv_rn(__fsub_rn(tn, t_lo), __fsub_rn(t_hi, t_lo));
+  g.l2 = log2((double)g.at);
+  g.lnat = (g.at > 0.f) ? (float)log((double)g.at) : 0.f;     // tf pow gradient: log of the safe base
+  return g;
+}
+// alpha_t ^ e
+__device__ __forceinline__ float glue_pow(const GlueLevel& g, float e) {
+  if (g.at == 0.f) return (e > 0.f) ? 0.f : ((e == 0.f) ? 1.f : CUDART_INF_F);
+  const double pr = (double)e * g.l2;
+  const float hi = (float)pr;
+  const float lo = (float)(pr - (double)hi);
+  return exp2f(hi) * fmaf(lo, 0.69314718f, 1.0f);
+}
+
+__global__ void __launch_bounds__(GT) k_glue_fwd(int64_t N, float init_value, float t_lo, float t_hi,
+                                                 const float* __restrict__ expo, const float* __restrict__ tn0,
+                                                 const float* __restrict__ tn1, const float* __restrict__ y0,
+                                                 const float* __restrict__ y1, const float* __restrict__ dtf1,
+                                                 const float* __restrict__ dtf2, float* __restrict__ p0,
+                                                 float* __restrict__ p1, double* __restrict__ dsum) {
+  __shared__ double red[2 * 32];
+  const int b = blockIdx.y;
+  const GlueLevel g0 = glue_level(tn0[b], t_lo, t_hi), g1 = glue_level(tn1[b], t_lo, t_hi);
+  const int64_t base = (int64_t)b * N;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t c = ((int64_t)blockIdx.x * GT + threadIdx.x) * 4; c < N; c += (int64_t)gridDim.x * GT * 4) {
+    if (c + 3 < N && (N & 3) == 0) {
+      const float4 e = expo ? __ldg(reinterpret_cast<const float4*>(expo + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(y0 + base + c));
+      const float4 bb = __ldcs(reinterpret_cast<const float4*>(y1 + base + c));
+      float4 o0, o1;
+      o0.x = init_value - glue_pow(g0, e.x) * a.x; o0.y = init_value - glue_pow(g0, e.y) * a.y;
+      o0.z = init_value - glue_pow(g0, e.z) * a.z; o0.w = init_value - glue_pow(g0, e.w) * a.w;
+      o1.x = init_value - glue_pow(g1, e.x) * bb.x; o1.y = init_value - glue_pow(g1, e.y) * bb.y;
+      o1.z = init_value - glue_pow(g1, e.z) * bb.z; o1.w = init_value - glue_pow(g1, e.w) * bb.w;
+      __stcs(reinterpret_cast<float4*>(p0 + base + c), o0);
+      __stcs(reinterpret_cast<float4*>(p1 + base + c), o1);
+      if (dtf1) { const float4 d = __ldcs(reinterpret_cast<const float4*>(dtf1 + base + c)); s1 += (d.x + d.y) + (d.z + d.w); }
+      if (dtf2) { const float4 d = __ldcs(reinterpret_cast<const float4*>(dtf2 + base + c)); s2 += (d.x + d.y) + (d.z + d.w); }
+    } else {
+      for (int64_t q = c; q < min(c + 4, N); ++q) {
+        const float e = expo ? expo[q] : 1.f;
+        p0[base + q] = init_value - glue_pow(g0, e) * y0[base + q];
+        p1[base + q] = init_value - glue_pow(g1, e) * y1[base + q];
+        if (dtf1) s1 += dtf1[base + q];
+        if (dtf2) s2 += dtf2[base + q];
+      }
+    }
+  }
+  if (dsum) {
+    double v[2] = {(double)s1, (double)s2};
+    block_reduce<2>(v, red);
+    if (threadIdx.x == 0) { atomicAdd(&dsum[2 * b], v[0]); atomicAdd(&dsum[2 * b + 1], v[1]); }
+  }
+}
+
+__global__ void k_glue_mean(int32_t B, int64_t N, const double* __restrict__ dsum, float* __restrict__ dt1, float* __restrict__ dt2) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (dt1) dt1[b] = (float)(dsum[2 * b] / (double)N);
+  if (dt2) dt2[b] = (float)(dsum[2 * b + 1] / (double)N);
+}
+
+// one thread: 4 cells x SB consecutive samples; the kernel_exponent cotangent is summed over the samples in registers,
+// then one atomic per cell and sample group
+constexpr int SB = 8;
+__global__ void __launch_bounds__(GT) k_glue_bwd(int32_t B, int64_t N, float t_lo, float t_hi, const float* __restrict__ expo,
+                                                 const float* __restrict__ tn0, const float* __restrict__ tn1,
+                                                 const float* __restrict__ y0, const float* __restrict__ y1,
+                                                 const float* __restrict__ gp0, const float* __restrict__ gp1,
+                                                 const float* __restrict__ gdt1, const float* __restrict__ gdt2,
+                                                 float* __restrict__ gy0, float* __restrict__ gy1, float* __restrict__ gexpo,
+                                                 float* __restrict__ gdtf1, float* __restrict__ gdtf2) {
+  const int64_t c = ((int64_t)blockIdx.x * GT + threadIdx.x) * 4;
+  if (c >= N) return;
+  const int b0 = blockIdx.y * SB, b1 = min(b0 + SB, B);
+  const bool vec = (c + 3 < N) && (N & 3) == 0;
+  const int nc = vec ? 4 : (int)min((int64_t)4, N - c);
+  float e[4] = {1.f, 1.f, 1.f, 1.f}, ge[4] = {0.f, 0.f, 0.f, 0.f};
+  if (expo) { _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) e[q] = expo[c + q]; }
+  const float invN = 1.0f / (float)N;
+  for (int b = b0; b < b1; ++b) {
+    const GlueLevel g0 = glue_level(tn0[b], t_lo, t_hi), g1 = glue_level(tn1[b], t_lo, t_hi);
+    const int64_t o = (int64_t)b * N + c;
+    float ya[4], yb[4], ga[4], gb[4], ra[4], rb[4];
+    if (vec) {
+      const float4 t0 = __ldcs(reinterpret_cast<const float4*>(y0 + o)), t1 = __ldcs(reinterpret_cast<const float4*>(y1 + o));
+      const float4 t2 = __ldcs(reinterpret_cast<const float4*>(gp0 + o)), t3 = __ldcs(reinterpret_cast<const float4*>(gp1 + o));
+      ya[0] = t0.x; ya[1] = t0.y; ya[2] = t0.z; ya[3] = t0.w; yb[0] = t1.x; yb[1] = t1.y; yb[2] = t1.z; yb[3] = t1.w;
+      ga[0] = t2.x; ga[1] = t2.y; ga[2] = t2.z; ga[3] = t2.w; gb[0] = t3.x; gb[1] = t3.y; gb[2] = t3.z; gb[3] = t3.w;
+    } else {
+      _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) { ya[q] = y0[o + q]; yb[q] = y1[o + q]; ga[q] = gp0[o + q]; gb[q] = gp1[o + q]; }
+    }
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) {
+      const float a0 = glue_pow(g0, e[q]), a1 = glue_pow(g1, e[q]);
+      ra[q] = -a0 * ga[q];
+      rb[q] = -a1 * gb[q];
+      // d/d expo of -alpha_t^e * y = -y * alpha * ln(alpha_t)
+      ge[q] = fmaf(ra[q] * ya[q], g0.lnat, fmaf(rb[q] * yb[q], g1.lnat, ge[q]));
+    }
+    const float d1 = gdt1 ? gdt1[b] * invN : 0.f, d2 = gdt2 ? gdt2[b] * invN : 0.f;
+    if (vec) {
+      __stcs(reinterpret_cast<float4*>(gy0 + o), make_float4(ra[0], ra[1], ra[2], ra[3]));
+      __stcs(reinterpret_cast<float4*>(gy1 + o), make_float4(rb[0], rb[1], rb[2], rb[3]));
+      if (gdtf1) __stcs(reinterpret_cast<float4*>(gdtf1 + o), make_float4(d1, d1, d1, d1));
+      if (gdtf2) __stcs(reinterpret_cast<float4*>(gdtf2 + o), make_float4(d2, d2, d2, d2));
+    } else {
+      _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) {
+        gy0[o + q] = ra[q]; gy1[o + q] = rb[q];
+        if (gdtf1) gdtf1[o + q] = d1;
+        if (gdtf2) gdtf2[o + q] = d2;
+      }
+    }
+  }
+  if (gexpo) { _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) atomicAdd(&gexpo[c + q], ge[q]); }
+}
+
+}  // namespace
+
+extern "C" size_t srm_glue_workspace_bytes(int32_t B) { return B > 0 ? (size_t)B * 2 * sizeof(double) : 0; }
+
+extern "C" int srm_glue_forward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
+                                const float* tn0, const float* tn1, const float* y0, const float* y1, const float* dtf1,
+                                const float* dtf2, float* p0, float* p1, float* dt1, float* dt2, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!h || B < 1 || B > 65535 || !tn0 || !tn1 || !y0 || !y1 || !p0 || !p1 || !(t_hi > t_lo)) { srm_set_error("srm_glue_forward: bad argument"); return SRM_ERR_INVALID; }
+  if ((dtf1 != nullptr) != (dt1 != nullptr) || (dtf2 != nullptr) != (dt2 != nullptr)) { srm_set_error("srm_glue_forward: dtf_l and dt_l go together"); return SRM_ERR_INVALID; }
+  const bool means = dtf1 || dtf2;
+  if (means && (!workspace || workspace_bytes < srm_glue_workspace_bytes(B))) { srm_set_error("srm_glue_forward: workspace %zu < required %zu bytes", workspace_bytes, srm_glue_workspace_bytes(B)); return SRM_ERR_WORKSPACE; }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t N = h->dev.N;
+  double* dsum = means ? (double*)workspace : nullptr;
+  if (means) SRM_CUDA_CHECK(cudaMemsetAsync(dsum, 0, srm_glue_workspace_bytes(B), s));
+  const unsigned gx = (unsigned)std::min<int64_t>((N / 4 + GT - 1) / GT + 1, 8 * 148);
+  k_glue_fwd<<<dim3(gx, (unsigned)B), GT, 0, s>>>(N, init_value, t_lo, t_hi, expo, tn0, tn1, y0, y1, dtf1, dtf2, p0, p1, dsum);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  if (means) {
+    k_glue_mean<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(B, N, dsum, dt1, dt2);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  return SRM_OK;
+}
+
+extern "C" int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
+                                 const float* tn0, const float* tn1, const float* y0, const float* y1, const float* gp0,
+                                 const float* gp1, const float* gdt1, const float* gdt2, float* gy0, float* gy1,
+                                 float* gexpo, float* gdtf1, float* gdtf2, void* stream) {
+  (void)init_value;
+  if (!h || B < 1 || B > 65535 || !tn0 || !tn1 || !y0 || !y1 || !gp0 || !gp1 || !gy0 || !gy1 || !(t_hi > t_lo)) { srm_set_error("srm_glue_backward: bad argument"); return SRM_ERR_INVALID; }
+  if ((gdtf1 != nullptr) != (gdt1 != nullptr) || (gdtf2 != nullptr) != (gdt2 != nullptr)) { srm_set_error("srm_glue_backward: gdtf_l and gdt_l go together"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t N = h->dev.N;
+  if (gexpo) SRM_CUDA_CHECK(cudaMemsetAsync(gexpo, 0, sizeof(float) * (size_t)N, s));
+  const dim3 grid((unsigned)((N / 4 + GT) / GT), (unsigned)((B + SB - 1) / SB));
+  k_glue_bwd<<<grid, GT, 0, s>>>(B, N, t_lo, t_hi, expo, tn0, tn1, y0, y1, gp0, gp1, gdt1, gdt2, gy0, gy1, gexpo, gdtf1, gdtf2);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

@@ -107,6 +107,46 @@ class SrmPhysics:
         self.launches += 1
         return out
 
+    # -- glue either side of the physics kernels: HardLayer + per-sample mean of the dt field, both levels ------------
+    def glue_forward(self, y0, y1, tn0, tn1, expo=None, dtf1=None, dtf2=None, init_value: float = 1.0,
+                     t_lo: float = -1.0, t_hi: float = 1.0):
+        """p_l = init_value - ((tn_l - t_lo)/(t_hi - t_lo)) ** expo * y_l  (Hard_Layer_Subclassed.py:219-242);
+        dt_l = per-sample mean of dtf_l (physics_loss.py:102,122).  Returns (p0, p1, dt1, dt2); dt_l is None without dtf_l."""
+        B = y0.shape[0]
+        for t, nm in ((y0, "y0"), (y1, "y1"), (tn0, "tn0"), (tn1, "tn1")):
+            self._check(t, nm)
+        for t, nm in ((expo, "expo"), (dtf1, "dtf1"), (dtf2, "dtf2")):
+            if t is not None:
+                self._check(t, nm)
+        p0, p1 = torch.empty_like(y0), torch.empty_like(y1)
+        dt1 = torch.empty(B, dtype=torch.float32, device=self.device) if dtf1 is not None else None
+        dt2 = torch.empty(B, dtype=torch.float32, device=self.device) if dtf2 is not None else None
+        nbytes = self.lib.srm_glue_workspace_bytes(B)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        L.check(self.lib, self.lib.srm_glue_forward(self._h, B, init_value, t_lo, t_hi, _ptr(expo), _ptr(tn0), _ptr(tn1),
+                                                    _ptr(y0), _ptr(y1), _ptr(dtf1), _ptr(dtf2), _ptr(p0), _ptr(p1),
+                                                    _ptr(dt1), _ptr(dt2), _ptr(ws), nbytes, self._stream()),
+                "srm_glue_forward")
+        self.launches += 1 + (1 if (dtf1 is not None or dtf2 is not None) else 0)
+        return p0, p1, dt1, dt2
+
+    def glue_backward(self, y0, y1, tn0, tn1, gp0, gp1, expo=None, gdt1=None, gdt2=None, init_value: float = 1.0,
+                      t_lo: float = -1.0, t_hi: float = 1.0, want_gexpo: bool = True):
+        """cotangents of glue_forward: (gy0, gy1, gexpo, gdtf1, gdtf2)"""
+        B = y0.shape[0]
+        for t, nm in ((y0, "y0"), (y1, "y1"), (tn0, "tn0"), (tn1, "tn1"), (gp0, "gp0"), (gp1, "gp1")):
+            self._check(t, nm)
+        gy0, gy1 = torch.empty_like(y0), torch.empty_like(y1)
+        gexpo = torch.empty(y0.shape[1:], dtype=torch.float32, device=self.device) if want_gexpo else None
+        gdtf1 = torch.empty_like(y0) if gdt1 is not None else None
+        gdtf2 = torch.empty_like(y0) if gdt2 is not None else None
+        L.check(self.lib, self.lib.srm_glue_backward(self._h, B, init_value, t_lo, t_hi, _ptr(expo), _ptr(tn0), _ptr(tn1),
+                                                     _ptr(y0), _ptr(y1), _ptr(gp0), _ptr(gp1), _ptr(gdt1), _ptr(gdt2),
+                                                     _ptr(gy0), _ptr(gy1), _ptr(gexpo), _ptr(gdtf1), _ptr(gdtf2),
+                                                     self._stream()), "srm_glue_backward")
+        self.launches += 1
+        return gy0, gy1, gexpo, gdtf1, gdtf2
+
     def wells(self, kx, sample_real, p, t_days, dense: bool = False):
         B = p.shape[0]
         R = kx.shape[0]

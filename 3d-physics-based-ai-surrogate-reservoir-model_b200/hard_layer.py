@@ -1,0 +1,111 @@
+"""HardLayer / CompleteTrainableModule: host-side mirrors of the reference's output layer
+(Hard_Layer_Subclassed.py:21-260) and of the wrapper the example builds its pressure model from
+(complete_trainable_module.py:27-176), plus the fused "glue" of the physics loss: both time
+levels of the layer and the per-sample means of the time-step field in ONE CUDA pass either side of the residual
+kernels, with the cotangents tape.gradient would deliver.
+
+torch modules stand in for the Keras layers (the torch-harness twin of the TF binding).  The arithmetic
+runs in libsrm_physics.so (srm_glue_forward / srm_glue_backward); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+
+class _GlueFn(torch.autograd.Function):
+    """(p0, p1, dt1, dt2) = glue(y0, y1, expo, dtf1, dtf2); time inputs carry no gradient here: the reference
+    differentiates w.r.t. the networks' weights only (physics_loss.py:849-859), and the layer's time input is data."""
+
+    @staticmethod
+    def forward(ctx, engine, init_value, t_lo, t_hi, tn0, tn1, y0, y1, expo, dtf1, dtf2):
+        c = lambda t: None if t is None else t.detach().contiguous()
+        y0c, y1c, ec, d1c, d2c = c(y0), c(y1), c(expo), c(dtf1), c(dtf2)
+        p0, p1, dt1, dt2 = engine.glue_forward(y0c, y1c, tn0, tn1, ec, d1c, d2c, init_value, t_lo, t_hi)
+        ctx.engine, ctx.k = engine, (init_value, t_lo, t_hi)
+        ctx.has = (expo is not None, dtf1 is not None, dtf2 is not None)
+        ctx.save_for_backward(tn0, tn1, y0c, y1c, ec if ec is not None else torch.empty(0, device=y0c.device))
+        z = torch.zeros(0, device=y0c.device)
+        return p0, p1, (dt1 if dt1 is not None else z), (dt2 if dt2 is not None else z)
+
+    @staticmethod
+    def backward(ctx, gp0, gp1, gdt1, gdt2):
+        tn0, tn1, y0, y1, expo = ctx.saved_tensors
+        has_e, has1, has2 = ctx.has
+        gy0, gy1, gexpo, gdtf1, gdtf2 = ctx.engine.glue_backward(
+            y0, y1, tn0, tn1, gp0.contiguous(), gp1.contiguous(), expo if has_e else None,
+            gdt1.contiguous() if has1 else None, gdt2.contiguous() if has2 else None, *ctx.k, want_gexpo=has_e)
+        return None, None, None, None, None, None, gy0, gy1, gexpo if has_e else None, gdtf1, gdtf2
+
+
+class HardLayer(torch.nn.Module):
+    """HardLayer(norm_limits=[-1, 1], init_value=..., kernel_exponent_config={...})  -- Hard_Layer_Subclassed.py:29-118
+
+    call([time, property], p) -> init_value - alpha_t ** kernel_exponent * p with a trainable exponent per cell
+    (shape (D, H, W), constant-initialised, clipped to [min_value, max_value] after each optimiser step as Keras'
+    MinMaxNorm constraint does for a one-element axis).  use_rbf / rectifier / activations are the example's defaults
+    (off); asking for them raises."""
+
+    def __init__(self, engine, norm_limits: Sequence[float] = (-1.0, 1.0), init_value: float = 1.0,
+                 kernel_exponent_config: Optional[dict] = None, use_rbf: bool = False, kernel_activation=None,
+                 input_activation=None, rectifier=None, name: str = "hard_layer"):
+        super().__init__()
+        if use_rbf or rectifier is not None or kernel_activation not in (None, "") or input_activation not in (None, ""):
+            raise NotImplementedError("HardLayer mirror: use_rbf / rectifier / activations are not built (example defaults are off)")
+        self.engine = engine
+        self.norm_limits = (float(norm_limits[0]), float(norm_limits[1]))
+        self.init_value = float(init_value)
+        cfg = {"initial_value": 0.5, "trainable": True, "min_value": 0.01, "max_value": 0.99, **(kernel_exponent_config or {})}
+        iv = cfg["initial_value"]
+        iv = float(iv[0] if isinstance(iv, (tuple, list)) else iv)       # the example passes a 1-tuple (training_case_dry_gas_i.py:94)
+        self.kernel_exponent_config = cfg
+        shape = (engine.spec.D, engine.spec.H, engine.spec.W)
+        self.kernel_exponent = torch.nn.Parameter(torch.full(shape, iv, dtype=torch.float32, device=engine.device),
+                                                  requires_grad=bool(cfg["trainable"]))
+        self.name = name
+
+    def apply_constraint(self):
+        with torch.no_grad():
+            self.kernel_exponent.clamp_(float(self.kernel_exponent_config["min_value"]), float(self.kernel_exponent_config["max_value"]))
+
+    def forward(self, inputs, p=None):
+        """inputs = [[time, property], p] (the reference's list form) or (time, p); time (B,D,H,W,1) or (B,)"""
+        if p is None:
+            (time, _prop), p = inputs[0], inputs[1]
+        else:
+            time = inputs
+        tn = time.reshape(time.shape[0], -1)[:, 0].contiguous()
+        y = p[..., 0] if p.dim() == 5 else p
+        out, _, _, _ = _GlueFn.apply(self.engine, self.init_value, *self.norm_limits, tn, tn, y, y, self.kernel_exponent, None, None)
+        return out.unsqueeze(-1) if p.dim() == 5 else out
+
+
+class CompleteTrainableModule(torch.nn.Module):
+    """CompleteTrainableModule(main_network, hard_layer): call(inputs, rectifier_input=None, training=False)
+    (complete_trainable_module.py:142-176): network output through the HardLayer, time = channel -2 and property =
+    channel -1 of the feature tensor (DEFAULT_INPUT_SLICE_CONFIG, default_configurations.py:217-225)."""
+
+    def __init__(self, main_network, hard_layer: Optional[HardLayer] = None, use_hard_layer: bool = True):
+        super().__init__()
+        self.main_network = main_network
+        self.hard_layer = hard_layer
+        self.use_hard_layer = bool(use_hard_layer and hard_layer is not None)
+
+    def forward(self, inputs, rectifier_input=None, training: bool = False):
+        y = self.main_network(inputs)
+        if not self.use_hard_layer:
+            return y
+        return self.hard_layer([[inputs[..., -2:-1], inputs[..., -1:]], y])
+
+
+def fused_two_level(module: CompleteTrainableModule, time_step_model, x0, x1):
+    """Both evaluations of the physics loss' glue in one CUDA pass: p_n = module(x_n), p_n1 = module(x_n1) and
+    dt1 = mean(time_step_model(x_n)), dt2 = mean(time_step_model(x_n1))   (physics_loss.py:88-122).
+    x_n1 must already carry the shifted time (it depends on dt1: the caller evaluates time_step_model(x_n) first)."""
+    hl = module.hard_layer
+    y0, y1 = module.main_network(x0)[..., 0], module.main_network(x1)[..., 0]
+    tn0, tn1 = x0[:, 0, 0, 0, -2].contiguous(), x1[:, 0, 0, 0, -2].contiguous()
+    dtf2 = time_step_model(x1)[..., 0]
+    p0, p1, _, dt2 = _GlueFn.apply(hl.engine, hl.init_value, *hl.norm_limits, tn0, tn1, y0, y1, hl.kernel_exponent, None, dtf2)
+    return p0, p1, dt2

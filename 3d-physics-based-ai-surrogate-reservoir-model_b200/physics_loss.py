@@ -144,11 +144,16 @@ class PhysicsLoss:
         B = x.shape[0]
         kx = eng.denormalize_log(x[..., 4].contiguous(), self.k_min, self.k_max, self.norm_lo, self.norm_hi)
         sample_real = torch.arange(B, dtype=torch.int32, device=eng.device)
-        p0 = self.main_model(x)[..., 0]                                           # physics_loss.py:88-95
         dt1 = self.time_step_model(x).reshape(B, -1).mean(dim=1)                  # physics_loss.py:102
         x1 = self._shift_time(x, dt1)
-        p1 = self.main_model(x1)[..., 0]                                          # physics_loss.py:111-115
-        dt2 = self.time_step_model(x1).reshape(B, -1).mean(dim=1)                 # physics_loss.py:122
+        from .hard_layer import CompleteTrainableModule, fused_two_level
+        if isinstance(self.main_model, CompleteTrainableModule) and self.main_model.use_hard_layer:
+            # both HardLayer evaluations and the second time-step mean in one CUDA pass (srm_glue_forward)
+            p0, p1, dt2 = fused_two_level(self.main_model, self.time_step_model, x, x1)
+        else:
+            p0 = self.main_model(x)[..., 0]                                       # physics_loss.py:88-95
+            p1 = self.main_model(x1)[..., 0]                                      # physics_loss.py:111-115
+            dt2 = self.time_step_model(x1).reshape(B, -1).mean(dim=1)             # physics_loss.py:122
         t1 = self._time_days(x1).detach().contiguous()
         if self.fluid_type == "GC":
             top = 1.0 - float(eng.spec.end_points["Swmin"])

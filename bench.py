@@ -58,6 +58,17 @@ def alg_bytes_per_cell(T, gc=False):
     return (80.0 if gc else 28.0) + 8.0 / T
 
 
+def measured_traffic(workload, numerics):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two dominant kernels, from the committed
+    `ncu --set full` capture of this command (profiles/traffic.json, written by tools/ncu_traffic.py)"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))
+        return t.get(f"{workload}:{numerics}")
+    except Exception:
+        return None
+
+
 def peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -308,9 +319,39 @@ def run_ours(args):
     if not torch.allclose(hterms[0], ref_terms[0].cpu(), rtol=1e-5):
         raise SystemExit(f"bench.py: e2e pipeline terms {hterms[0].tolist()} != resident terms {ref_terms[0].cpu().tolist()}")
 
+    # ---- the fused glue either side of the kernels: HardLayer at both levels + dt means and
+    # their cotangents, timed on the same resident batch (not part of `value`: the reference's metric is the residual)
+    glue = None
+    if not gc:
+        ydev = torch.rand_like(d["p0"]) * 600.0
+        expo = torch.full(d["p0"].shape[1:], 0.5, device=dev)
+        tn = torch.linspace(-0.9, 0.9, B, device=dev)
+        gsteps = max(3, min(args.steps, 10))
+
+        def gstep():
+            p0g, p1g, dt1g, dt2g = eng.glue_forward(ydev, d["p1"], tn, tn, expo, d["p0"], d["p1"], 5000.0)
+            return eng.glue_backward(ydev, d["p1"], tn, tn, p0g, p1g, expo, dt1g, dt2g, 5000.0)
+        for _ in range(3):
+            gstep()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        g0.record()
+        for _ in range(gsteps):
+            gstep()
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gms = g0.elapsed_time(g1) / gsteps
+        gbytes = 56.0            # forward: read y0,y1,dtf1,dtf2, write p0,p1 (24 B); backward: read y0,y1,gp0,gp1, write gy0,gy1,gdtf1,gdtf2 (32 B)
+        glue = {"ms_per_step": gms, "cell_timesteps_per_s": N / (gms * 1e-3), "alg_bytes_per_cell": gbytes,
+                "achieved_GBps": N * gbytes / (gms * 1e-3) / 1e9,
+                "kernels": "k_glue_fwd + k_glue_mean + k_glue_bwd (srm_glue_forward / srm_glue_backward)"}
+        del ydev
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         ab = alg_bytes_per_cell(T, gc)
+        if glue:
+            glue["frac"] = glue["achieved_GBps"] / peak
         achieved = N * ab / (ms_step * 1e-3) / 1e9          # per GPU (each rank runs N cells per step)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -328,7 +369,9 @@ def run_ours(args):
                        "l2": "inputs+workspace per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % ((2 * N * 4 + eng.workspace(B, b.kx.shape[0]).numel()) / 1e6),
                        "parallelism": f"sample-sharded x{world}; all-reduce of the 16-float loss-term vector only"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (measured_traffic(args.workload, args.numerics) or {}).get("bytes_per_step"),
+                         "traffic_source": (measured_traffic(args.workload, args.numerics) or {}).get("source"),
+                         "peak_source": peak_src,
                          "kernel": "whole step (forward + adjoint launches); algorithmic bytes = %.2f B/cell-timestep" % ab,
                          "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms)},
             "cpu_baseline": cpu,
@@ -337,6 +380,7 @@ def run_ours(args):
                     "api": f"srm.engine.HostPipeline.step: pinned host batch, {len(pipe.chunks)} chunks of whole realisations, H2D / kernels / D2H on three streams"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "glue": glue,
         }
         print(json.dumps(line))
     if distributed:

@@ -222,6 +222,28 @@ int srm_backward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
                     float* gp0, float* gp1, float* gsg0, float* gsg1, float* gso0, float* gso1, float* gdt1,
                     float* gdt2, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
+/* ---- the element-wise glue either side of the physics kernels (both time levels in one pass) --------------------
+ * HardLayer.call (Hard_Layer_Subclassed.py:219-242, reached through CompleteTrainableModule.call,
+ * complete_trainable_module.py:142-176) and the per-sample mean of the time-step field (physics_loss.py:102,122):
+ *   p_l[b,c] = init_value - alpha_t(tn_l[b]) ^ expo[c] * y_l[b,c],   alpha_t(t) = (t - t_lo) / (t_hi - t_lo)
+ *   dt_l[b]  = mean_c dtf_l[b,c]
+ * y_l (B,D,H,W): network output at level l = n, n+1;  expo (D,H,W): the layer's kernel_exponent (NULL: 1);
+ * tn_l (B,): the layer's time input (normalised time with the default identity nonormalize_func; norm_limits =
+ * [t_lo, t_hi]);  dtf_l (B,D,H,W): time-step field, NULL (with dt_l NULL) skips the mean.
+ * workspace: srm_glue_workspace_bytes(B) bytes (fp64 partial sums), only read when a mean is requested. */
+size_t srm_glue_workspace_bytes(int32_t B);
+int srm_glue_forward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
+                     const float* tn0, const float* tn1, const float* y0, const float* y1, const float* dtf1,
+                     const float* dtf2, float* p0, float* p1, float* dt1, float* dt2, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* Cotangents of srm_glue_forward (what tape.gradient hands to the networks and to kernel_exponent):
+ *   gy_l = -alpha * gp_l;   gexpo[c] = sum_b sum_l gp_l * (-y_l * alpha * ln alpha_t)  (0 where alpha_t <= 0, as
+ *   tf.pow's gradient);   gdtf_l[b,c] = gdt_l[b] / N.   gexpo, gdtf_l (with gdt_l) may be NULL. */
+int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
+                      const float* tn0, const float* tn1, const float* y0, const float* y1, const float* gp0,
+                      const float* gp1, const float* gdt1, const float* gdt2, float* gy0, float* gy1, float* gexpo,
+                      float* gdtf1, float* gdtf2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

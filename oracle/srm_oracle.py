@@ -1011,3 +1011,38 @@ def norm_diff_linear(d, vmin, vmax, lo=-1.0, hi=1.0, dtype=np.float32):
     """normalize_diff linear branch (:1166-1168): (hi-lo)/(max-min)*diff."""
     t = dtype
     return ((t(hi) - t(lo)) / (t(vmax) - t(vmin)) * np.asarray(d, dtype=t)).astype(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# glue either side of the residual (SURVEY 8(f) rank 1): HardLayer and the time-step mean
+# ------------------------------------------------------------------------------------------------
+def hard_layer_t(y, tn, expo, init_value=1.0, t_lo=-1.0, t_hi=1.0):
+    """HardLayer.call (Hard_Layer_Subclassed.py:219-242) with the example's configuration (no rbf, no rectifier,
+    identity activations, identity nonormalize_func): output = init_value - alpha_t ** kernel_exponent * p,
+    alpha_t = (t - norm_limits[0]) / (norm_limits[1] - norm_limits[0]).  torch tensors (autograd-capable);
+    y (B,D,H,W), tn (B,), expo (D,H,W).  tf.pow's gradient w.r.t. the exponent uses log of the SAFE base
+    (where(x > 0, x, 1)): torch.pow's would give nan at alpha_t = 0, hence the explicit Function."""
+    at = ((tn - t_lo) / (t_hi - t_lo)).view(-1, 1, 1, 1)
+    alpha = _TfPow.apply(at.expand_as(y), expo.expand_as(y))
+    return init_value - alpha * y
+
+
+class _TfPow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, e):
+        z = torch.pow(x, e)
+        ctx.save_for_backward(x, e, z)
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        x, e, z = ctx.saved_tensors
+        safe = torch.where(x > 0, x, torch.ones_like(x))
+        gx = g * e * torch.pow(x, e - 1)
+        ge = g * z * torch.where(x > 0, torch.log(safe), torch.zeros_like(x))
+        return gx, ge
+
+
+def time_step_mean_t(dtf):
+    """tstep = reduce_mean(fac, axis=[1,2,3]) (physics_loss.py:102,122)"""
+    return dtf.reshape(dtf.shape[0], -1).mean(dim=1)

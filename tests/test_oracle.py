@@ -211,3 +211,31 @@ def test_polynomial_pvt_oracle():
         am[which][idx] -= h
         fd = (loss(ap) - loss(am)) / (2 * h)
         assert abs(fd - o[g][idx]) <= 1e-5 * abs(o[g][idx]) + 1e-7 * np.abs(o[g]).max()
+
+
+def test_hard_layer_oracle_gradients_fp64():
+    """HardLayer restatement (Hard_Layer_Subclassed.py:219-242): closed form, tf.pow's safe-log exponent gradient at
+    alpha_t = 0, and central finite differences in fp64"""
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W = 3, 2, 3, 4
+    y = (600.0 * torch.rand((B, D, H, W), generator=g)).double()
+    e = (0.1 + 0.8 * torch.rand((D, H, W), generator=g)).double()
+    tn = torch.tensor([-1.0, -0.2, 0.7], dtype=torch.float64)
+    yv, ev = y.clone().requires_grad_(True), e.clone().requires_grad_(True)
+    out = O.hard_layer_t(yv, tn, ev, 5000.0)
+    at = (tn + 1.0) / 2.0
+    assert torch.allclose(out, 5000.0 - at.view(-1, 1, 1, 1) ** e * y)
+    assert torch.all(out[0] == 5000.0)                              # the initial condition is enforced exactly at t_lo
+    w = torch.randn(out.shape, generator=g).double()
+    (out * w).sum().backward()
+    assert torch.all(torch.isfinite(ev.grad)) and torch.all(torch.isfinite(yv.grad))
+    h = 1e-6
+    for idx in [(0, 1, 2), (1, 0, 3), (1, 2, 0)]:
+        ep, em = e.clone(), e.clone()
+        ep[idx] += h
+        em[idx] -= h
+        fd = ((O.hard_layer_t(y, tn, ep, 5000.0) * w).sum() - (O.hard_layer_t(y, tn, em, 5000.0) * w).sum()) / (2 * h)
+        assert abs(float(fd) - float(ev.grad[idx])) <= 1e-6 * max(1.0, abs(float(fd)))
+    assert torch.allclose(yv.grad, -(at.view(-1, 1, 1, 1) ** e) * w)
+    dtf = torch.rand((B, D, H, W), generator=g).double()
+    assert torch.allclose(O.time_step_mean_t(dtf), dtf.mean(dim=(1, 2, 3)))
