@@ -35,3 +35,17 @@ def allreduce_terms(terms: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group)
     return terms
+
+
+class _Done:
+    def wait(self):
+        return True
+
+
+def allreduce_terms_async(terms: torch.Tensor, group=None):
+    """Same reduction, not ordered before the work queued next on the current stream: the backward does not read the
+    reduced terms (its upstream weights are given), so its kernels need not wait for the 128-byte collective.  Returns
+    a handle; ``handle.wait()`` orders the current stream after the reduction (no host synchronisation)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return _Done()
