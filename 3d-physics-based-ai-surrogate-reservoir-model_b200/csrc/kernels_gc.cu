@@ -16,8 +16,7 @@
 // cell; the residual kernels are not fused yet (the dry-gas path's kernels_ref2.cu shows the next step).
 #include <math_constants.h>
 #include <cstring>
-#include "pvt_ref.cuh"
-#include "common.cuh"
+#include "ref_fused.cuh"
 
 namespace {
 
@@ -301,7 +300,43 @@ __device__ __forceinline__ void face_perms(const SrmDev& P, const float* __restr
   ckf[5] = __fmul_rn(P.C, harm_ref(__fmul_rn(P.kv_kh, kr[ix.n[5]]), kzc));
 }
 
+// neighbour cells of (i, j, k) with edge replication, without the integer divisions of cell_index
+__device__ __forceinline__ CellIdx cell_index3(const SrmDev& P, int i, int j, int k, int c) {
+  CellIdx x;
+  x.i = i; x.j = j; x.k = k;
+  const int HW = P.H * P.W;
+  x.n[0] = (i > 0) ? c - 1 : c;
+  x.n[1] = (i < P.W - 1) ? c + 1 : c;
+  x.n[2] = (j > 0) ? c - P.W : c;
+  x.n[3] = (j < P.H - 1) ? c + P.W : c;
+  x.n[4] = (k > 0) ? c - HW : c;
+  x.n[5] = (k < P.D - 1) ? c + HW : c;
+  return x;
+}
+// C*k_f of the six faces (W,E,S,N,D,U) from the per-realisation table k_faces_ref builds with krg = 1
+// (fl(x*1) = x: the same bits as face_perms; image faces hold the harmonic mean of the cell with itself)
+__device__ __forceinline__ void face_perms_tab(const FaceLay& L, const float* __restrict__ fr, int W, int H, int i, int j, int k,
+                                               float (&ckf)[6]) {
+  const float* FE = fr;
+  const float* FN = fr + L.nE;
+  const float* FU = FN + L.nN;
+  const int64_t e = ((int64_t)k * H + j) * L.WP + i, n = ((int64_t)k * (H + 1) + j) * W + i, u = ((int64_t)k * H + j) * W + i;
+  ckf[0] = __ldg(FE + e); ckf[1] = __ldg(FE + e + 1);
+  ckf[2] = __ldg(FN + n); ckf[3] = __ldg(FN + n + W);
+  ckf[4] = __ldg(FU + u); ckf[5] = __ldg(FU + u + (int64_t)H * W);
+}
+// does the (i, j) column hold a connection in any layer?  (short well lists: one scan per thread and march;
+// long ones: every cell searches)
+__device__ __forceinline__ bool column_has_well_gc(const SrmDev& P, int col, int HW) {
+  if (P.n_wells <= 0) return false;
+  if (P.n_wells > 64) return true;
+  bool any = false;
+  for (int w = 0; w < P.n_wells; ++w) any |= (P.wells[w].cell % HW) == col;
+  return any;
+}
+
 struct GcFwd {
+  const float* faces;
   const float* kx; const int32_t* sample_real;
   const float* p0; const float* p1; const float* sg0; const float* sg1; const float* so0; const float* so1;
   const float* dt1; const float* dt2;
@@ -312,22 +347,37 @@ struct GcFwd {
 };
 
 __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
+  // one thread per (j, i) column, marching over z: per-sample scalars (five IEEE divisions), the column's position and
+  // its well flag are formed once per march, and the seven partial sums are reduced once per thread instead of once per cell
   __shared__ double red[7 * 32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = P.H * P.W;
   const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
   const int64_t total = (int64_t)A.B * P.N;
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // dom^2, ibc^2, trn^2, sum mg cells, sum mo cells, sum qg, sum qo
-  if (c < P.N) {
+  if (col < HW) {
     const int64_t base = (int64_t)b * P.N;
     auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
-    const CellIdx ix = cell_index(P, c);
+    const int cj = col / P.W, ci = col - cj * P.W;
+    const FaceLay FL = face_layout(P.D, P.H, P.W);
+    const float* __restrict__ fr = A.faces + (int64_t)r * FL.per_real;
+    const bool col_wells = column_has_well_gc(P, col, HW);
     const float d1 = A.dt1[b], d2 = A.dt2[b];
+    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    const float idt = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
+    const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
+    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+    const float rte_d1 = __fdiv_rn(2.5e-8f, d1);                                  // :439-440
+    const float d12 = __fadd_rn(d1, d2);
+    const float mfac = __fmul_rn(__fmul_rn(P.dv, idt), P.phi);
+    for (int k = 0; k < P.D; ++k) {
+    const int c = k * HW + col;
+    const CellIdx ix = cell_index3(P, ci, cj, k, c);
     const float p0 = A.p0[base + c], p1 = A.p1[base + c];
     const float sg0 = A.sg0[base + c], sg1 = A.sg1[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
     float ckf[6];
-    face_perms(P, A.kx + (int64_t)r * P.N, c, ix, ckf);
-    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    face_perms_tab(FL, fr, P.W, P.H, ci, cj, k, ckf);
     const float Mc[4] = {F(F_MGG, c), F(F_MGO, c), F(F_MOO, c), F(F_MOG, c)};      // gg, go, oo, og
     const float krg_c = F(F_KRG, c), kro_c = F(F_KRO, c);
     float pn[6], a[4][6];
@@ -351,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
     float q4[4] = {0.f, 0.f, 0.f, 0.f}, mask = 0.f;
     int wfirst = 0;
     const int64_t wt = (int64_t)A.B * P.n_wells;
-    if (P.n_wells > 0) {
+    if (col_wells) {
       wfirst = well_lower_bound(P, c);
       for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) {
 #pragma unroll
@@ -369,7 +419,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
       s = __fadd_rn(s, -__fmul_rn(a[X][1], pn[1]));
       s = __fadd_rn(s, -__fmul_rn(a[X][3], pn[3]));
       s = __fadd_rn(s, __fadd_rn(__fmul_rn(a[X][4], __fsub_rn(p1, pn[4])), __fmul_rn(a[X][5], __fsub_rn(p1, pn[5]))));   // 3-D extension
-      s = __fadd_rn(s, __fdiv_rn(q4[X], P.dv));
+      s = __fadd_rn(s, (mask != 0.f) ? __fdiv_rn(q4[X], P.dv) : 0.0f);          // off-well: 0/dv = +0 without the division
       divq[X] = __fmul_rn(P.dv, s);
     }
     // accumulation                                               physics_loss.py:465-466,506-514,557-586
@@ -382,7 +432,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
     const float dSo = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(so1, so0), dpc);   // :466
     const float dR0 = __fadd_rn(__fmul_rn(Rs0, dB0), __fmul_rn(B0, dRs0));        // :511
     const float dV0 = __fadd_rn(__fmul_rn(Rv0, dA0), __fmul_rn(A0, dRv0));        // :513
-    const float idt = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
     auto cpX = [&](float prop1, float dS, float s0, float dprop0, float prop0) {
       const float cpr = __fmul_rn(P.phicf, prop0);                                // :557-560
       const float t1 = __fmul_rn(__fmul_rn(P.phi, prop1), dS);
@@ -397,10 +446,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
     const float divq_tot = __fadd_rn(__fadd_rn(divq[0], divq[1]), __fadd_rn(divq[2], divq[3]));
     const float ibc = __fmul_rn(mask, divq_tot);                                  // :650
     // masses and truncation terms                                physics_loss.py:419-441
-    const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
-    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
-    const float rte_d1 = __fdiv_rn(2.5e-8f, d1);                                  // :439-440
-    const float d12 = __fadd_rn(d1, d2);
     auto trnX = [&](float m0, float m1) {
       const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(m1, m0), rho1), m0);
       const float num = __fsub_rn(__fadd_rn(__fmul_rn(d2, m0), __fmul_rn(d1, m2)), __fmul_rn(d12, m1));
@@ -412,7 +457,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
     const float mo1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(b1, so1), __fmul_rn(v1, sg1)));
     const float trn = __fadd_rn(trnX(mg0, mg1), trnX(mo0, mo1));                  // :637
     // material balance summands                                  physics_loss.py:655-662
-    const float mfac = __fmul_rn(__fmul_rn(P.dv, idt), P.phi);
     const float mb_gg = __fmul_rn(mfac, __fsub_rn(__fmul_rn(sg1, a1), __fmul_rn(sg0, A0)));
     const float mb_go = __fmul_rn(mfac, __fsub_rn(__fmul_rn(so1, r1), __fmul_rn(so0, R0)));
     const float mb_oo = __fmul_rn(mfac, __fsub_rn(__fmul_rn(so1, b1), __fmul_rn(so0, B0)));
@@ -421,13 +465,13 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant
     if (A.dom_out) A.dom_out[base + c] = dom;
     if (mask != 0.f)
       for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq_tot;
-    acc[0] = (double)dom * (double)dom;
-    acc[1] = (double)ibc * (double)ibc;
-    acc[2] = (double)trn * (double)trn;
-    acc[3] = (double)__fadd_rn(mb_gg, mb_go);
-    acc[4] = (double)__fadd_rn(mb_oo, mb_og);
-    acc[5] = (double)__fadd_rn(q4[0], q4[1]);
-    acc[6] = (double)__fadd_rn(q4[2], q4[3]);
+    acc[0] += (double)dom * (double)dom;
+    if (mask != 0.f) acc[1] += (double)ibc * (double)ibc;
+    acc[2] += (double)trn * (double)trn;
+    acc[3] += (double)__fadd_rn(mb_gg, mb_go);
+    acc[4] += (double)__fadd_rn(mb_oo, mb_og);
+    if (mask != 0.f) { acc[5] += (double)__fadd_rn(q4[0], q4[1]); acc[6] += (double)__fadd_rn(q4[2], q4[3]); }
+    }   // march
   }
   block_reduce<7>(acc, red);
   if (threadIdx.x == 0) {
@@ -471,6 +515,7 @@ __global__ void k_finalize_fwd_gc(const __grid_constant__ SrmDev P, int32_t B, d
 
 // ---- adjoint -----------------------------------------------------------------------------------
 struct GcAdj {
+  const float* faces;
   const float* kx; const int32_t* sample_real;
   const float* p0; const float* p1; const float* sg0; const float* sg1; const float* so0; const float* so1;
   const float* dt1; const float* dt2; const float* dterms;
@@ -502,25 +547,44 @@ __device__ __forceinline__ FaceAdj face_adj(bool own, float krg_c, float kro_c, 
 }
 
 __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
+  // one thread per (j, i) column, marching over z (see k_resid_fwd_gc)
   __shared__ double red[2 * 32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = P.H * P.W;
   const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
   const int64_t total = (int64_t)A.B * P.N;
   double acc2[2] = {0.0, 0.0};
-  if (c < P.N) {
+  if (col < HW) {
     const int64_t base = (int64_t)b * P.N;
     auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
-    const CellIdx ix = cell_index(P, c);
+    const int cj = col / P.W, ci = col - cj * P.W;
+    const FaceLay FL = face_layout(P.D, P.H, P.W);
+    const float* __restrict__ fr = A.faces + (int64_t)r * FL.per_real;
+    const bool col_wells = column_has_well_gc(P, col, HW);
     const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_trn = A.dterms[SRM_TERM_CMBC];
     const float d1 = A.dt1[b], d2 = A.dt2[b];
+    const float smb = 2.f * w_mbc * A.mbc[b];                // dL/d mbc_b
+    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    const float idt = 1.0f / (P.Dc * d1);
+    const float id1 = 1.0f / d1;
+    const float mfac = P.dv * idt * P.phi;
+    const float smf = smb * mfac;
+    // forward's per-sample scalars of the truncation term, in the forward's op order
+    const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
+    const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+    const float rte_d1 = __fdiv_rn(2.5e-8f, d1);
+    const float d12 = __fadd_rn(d1, d2);
+    const float iden2 = 1.0f / (den * den);
+    const float dE1c = -2.f * 2.5e-8f / (d1 * d1);
+    for (int k = 0; k < P.D; ++k) {
+    const int c = k * HW + col;
+    const CellIdx ix = cell_index3(P, ci, cj, k, c);
     const float p0 = A.p0[base + c], p1 = A.p1[base + c];
     const float sg0 = A.sg0[base + c], sg1 = A.sg1[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
     const float sc = 2.f * w_dom * A.dom[base + c];          // dL/d dom_c
-    const float smb = 2.f * w_mbc * A.mbc[b];                // dL/d mbc_b
     float ckf[6];
-    face_perms(P, A.kx + (int64_t)r * P.N, c, ix, ckf);
-    const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
+    face_perms_tab(FL, fr, P.W, P.H, ci, cj, k, ckf);
     const float Mg_c = F(F_MGG, c) + F(F_MOG, c), Mo_c = F(F_MGO, c) + F(F_MOO, c);
     const float krg_c = F(F_KRG, c), kro_c = F(F_KRO, c);
     const float dMg_c = F(F_DMG, c), dMo_c = F(F_DMO, c), dkrg_c = F(F_DKRG, c), dkro_c = F(F_DKRO, c);
@@ -558,7 +622,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
     const float pdA0 = d2A0, pdB0 = d2B0;
     const float pdR0 = 2.f * dRs0 * dB0 * m0 + Rs0 * d2B0 + B0 * d2Rs0;
     const float pdV0 = 2.f * dRv0 * dA0 * m0 + Rv0 * d2A0 + A0 * d2Rv0;
-    const float idt = 1.0f / (P.Dc * d1);
     const float dpc = p1 - p0;
     const float nz = (dpc == 0.f) ? 0.f : 1.f;               // divide_no_nan: the chord-slope terms vanish with dpc
     const float dSgS = (sg1 - sg0) * nz, dSoS = (so1 - so0) * nz;
@@ -576,9 +639,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
     float go0 = sacc * (dpc * Ko - P.phi * (r1 + b1) * nz);
     const float acc_tot = P.dv * idt * (P.phi * ((a1 + v1) * dSgS + (r1 + b1) * dSoS) + dpc * (sg0 * Kg + so0 * Ko));
     // material balance: mbc_b = -sum q - sum mcell
-    const float mfac = P.dv * idt * P.phi;
     const float mcell = mfac * ((sg1 * a1 - sg0 * A0) + (so1 * r1 - so0 * R0) + (so1 * b1 - so0 * B0) + (sg1 * v1 - sg0 * V0));
-    const float smf = smb * mfac;
     g1 -= smf * (sg1 * (da1 + dv1) + so1 * (dr1 + db1));
     g0 += smf * (sg0 * (pA0 + pV0) + so0 * (pR0 + pB0));
     gs1 -= smf * (a1 + v1);
@@ -586,7 +647,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
     go1 -= smf * (r1 + b1);
     go0 += smf * (R0 + B0);
     // wells in this cell: sum of the four rates enters dom (+) and mbc (-)
-    if (P.n_wells > 0) {
+    if (col_wells) {
       const int64_t wt = (int64_t)A.B * P.n_wells;
       const int first = well_lower_bound(P, c);
       for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) {
@@ -599,10 +660,6 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
     // linear extrapolation, so only the explicit time steps carry a gradient (N itself is rounding noise, evaluated in
     // the forward's op order)
     {
-      const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
-      const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
-      const float rte_d1 = __fdiv_rn(2.5e-8f, d1);
-      const float d12 = __fadd_rn(d1, d2);
       const float R0f = __fmul_rn(Rs0, B0), V0f = __fmul_rn(Rv0, A0);
       auto numX = [&](float mm0, float mm1) {
         const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(mm1, mm0), rho1), mm0);
@@ -616,11 +673,10 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
       const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(Ng, den))),
                                   __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(No, den))));
       const float st = 2.f * w_trn * trn;
-      const float iden2 = 1.0f / (den * den);
-      const float dE1 = -2.f * 2.5e-8f / (d1 * d1) - (Ng + No) * d2 * iden2;
+      const float dE1 = dE1c - (Ng + No) * d2 * iden2;
       const float dE2 = -(Ng + No) * (d1 + 2.f * d2) * iden2;
-      acc2[0] = (double)(-sc * acc_tot / d1 + smb * (mcell / d1) + st * P.dvDc * dE1);
-      acc2[1] = (double)(st * P.dvDc * dE2);
+      acc2[0] += (double)((smb * mcell - sc * acc_tot) * id1 + st * P.dvDc * dE1);
+      acc2[1] += (double)(st * P.dvDc * dE2);
     }
     A.gp0[base + c] = g0;
     A.gp1[base + c] = g1;
@@ -628,6 +684,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant
     A.gsg1[base + c] = gs1;
     A.gso0[base + c] = go0;
     A.gso1[base + c] = go1;
+    }   // march
   }
   block_reduce<2>(acc2, red);
   if (threadIdx.x == 0) {
@@ -746,7 +803,16 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
   A.dt1 = dt1; A.dt2 = dt2; A.F = ws.gc; A.W7 = ws.gc_wells; A.divqw = ws.divqw; A.dom = ws.dom; A.dom_out = dom_out;
   A.sse = ws.sse; A.s_mg = ws.mb_sum; A.s_qg = ws.q_sum; A.s_mo = ws.gdt1_acc; A.s_qo = ws.gdt2_acc;   // the adjoint re-zeroes its accumulators
   A.B = B; A.R = R;
-  const dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  {
+    // static face coefficients C*k_f per realisation: k_faces_ref (ref_fused.cuh) with krg = 1, fl(x*1) = x
+    SrmDev P1 = P;
+    P1.krg = 1.0f;
+    const FaceLay FL = face_layout(P.D, P.H, P.W);
+    k_faces_ref<<<dim3((unsigned)((FL.per_real + 255) / 256), (unsigned)R), 256, 0, s>>>(P1, kx, ws.faces);
+    SRM_CUDA_CHECK(cudaGetLastError());
+  }
+  A.faces = ws.faces;
+  const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
   k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
   SRM_CUDA_CHECK(cudaGetLastError());
   k_finalize_fwd_gc<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.gdt1_acc, ws.gdt2_acc, ws.mbc, terms_out);
@@ -768,7 +834,8 @@ int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, co
   A.dt1 = dt1; A.dt2 = dt2; A.dterms = dterms; A.F = ws.gc; A.W7 = ws.gc_wells; A.divqw = ws.divqw; A.dom = ws.dom; A.mbc = ws.mbc;
   A.gp0 = gp0; A.gp1 = gp1; A.gsg0 = gsg0; A.gsg1 = gsg1; A.gso0 = gso0; A.gso1 = gso1;
   A.gdt1_acc = ws.gdt1_acc; A.gdt2_acc = ws.gdt2_acc; A.B = B; A.R = R;
-  const dim3 grid((unsigned)((P.N + kThreads - 1) / kThreads), (unsigned)B);
+  A.faces = ws.faces;                                        // built by the forward (state in the workspace)
+  const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
   k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);
   SRM_CUDA_CHECK(cudaGetLastError());
   const int64_t n = (int64_t)B * P.n_wells;

@@ -109,7 +109,7 @@ struct SrmWs {
   int32_t* grp_list;  // [B]   sample ids, grouped by realisation, ascending within a group
   int32_t* seg;       // [3*(B+1)] (r, offset into grp_list, count)
   int32_t* ctl;       // [8]   ctl[0] = number of segments, ctl[1..2] = work counters
-  float* faces;       // fused reference path: static face coefficients [R][face floats]
+  float* faces;       // fused reference path and gas condensate: static face coefficients [R][face floats]
   float* gc;          // gas-condensate path: SRM_GC_NFIELDS staged fields [B*N] each, 4+1+2 extra well tables
   float* gc_wells;    // [7][B*nw]: qgg,qgo,qoo,qog (sorted order), d(sum q)/dp, d(sum q)/dSg, spare
   float* dom;         // field [B*N]
@@ -162,7 +162,7 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64
   }
   size_t fb = (size_t)(B * N) * sizeof(float);
   w.faces = nullptr;
-  if (mode == SRM_WS_REF_FUSED) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
+  if (mode == SRM_WS_REF_FUSED || mode == SRM_WS_GC) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
   w.dom = (float*)take(fb);
   w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
   w.gc = w.gc_wells = nullptr;
