@@ -346,7 +346,7 @@ struct GcFwd {
   int32_t B, R;
 };
 
-__global__ void __launch_bounds__(kThreads) k_resid_fwd_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
+__global__ void __launch_bounds__(kThreads, 3) k_resid_fwd_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
   // one thread per (j, i) column, marching over z: per-sample scalars (five IEEE divisions), the column's position and
   // its well flag are formed once per march, and the seven partial sums are reduced once per thread instead of once per cell
   __shared__ double red[7 * 32];
@@ -546,7 +546,7 @@ __device__ __forceinline__ FaceAdj face_adj(bool own, float krg_c, float kro_c, 
   return r;
 }
 
-__global__ void __launch_bounds__(kThreads) k_resid_adj_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
+__global__ void __launch_bounds__(kThreads, 3) k_resid_adj_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
   // one thread per (j, i) column, marching over z (see k_resid_fwd_gc)
   __shared__ double red[2 * 32];
   const int b = blockIdx.y;
