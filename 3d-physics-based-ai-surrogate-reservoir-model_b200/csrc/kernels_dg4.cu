@@ -54,13 +54,21 @@ constexpr int SH = TY + 2;
 constexpr int PLANE = SH * SW;
 
 // ---- CPT-wide moves ---------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ld_hint2(const float* p, uint64_t pol) { return ld_hint(reinterpret_cast<const float2*>(p), pol); }
+#ifndef SRM_D4_NOALLOC
+#define SRM_D4_NOALLOC 1
+#endif
+#if SRM_D4_NOALLOC
+#define LD_STRM ld_stream
+#else
+#define LD_STRM ld_hint
+#endif
+__device__ __forceinline__ float2 ld_hint2(const float* p, uint64_t pol) { return LD_STRM(reinterpret_cast<const float2*>(p), pol); }
 __device__ __forceinline__ void st_hint(float2* p, float2 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
 }
 // streamed fields: evict-first in L2 (ref_fused.cuh)
 __device__ __forceinline__ void ldgs(const float* p, float (&v)[CPT], uint64_t pol) {
-  if constexpr (CPT == 4) { const float4 t = ld_hint(reinterpret_cast<const float4*>(p), pol); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  if constexpr (CPT == 4) { const float4 t = LD_STRM(reinterpret_cast<const float4*>(p), pol); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   else { const float2 t = ld_hint2(p, pol); v[0] = t.x; v[1] = t.y; }
 }
 __device__ __forceinline__ void stgs(float* p, const float (&v)[CPT], uint64_t pol) {
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
       ldgs(p0f + off, p0a, strm);
       ldgs(p0f + off + s1, p0b, strm);
       float hp0 = 0.f;
-      if (t.halo) { hp0 = ld_hint(p1f + t.h_off, strm); hq = ld_hint(p1f + (s1 + t.h_off), strm); }
+      if (t.halo) { hp0 = LD_STRM(p1f + t.h_off, strm); hq = LD_STRM(p1f + (s1 + t.h_off), strm); }
       ldgs(p1f + off + s2, pq, strm);
       ldgs(p0f + off + s2, p0q, strm);
       float2 e1a[CPT], e1b[CPT], e0a[CPT], e0b[CPT];
@@ -262,7 +270,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
         const int u3 = min(3, rem) * HW;
         ldgs(p1f + off + u3, pq, strm);
         ldgs(p0f + off + u3, p0q, strm);
-        if (t.halo && rem >= 2) hq = ld_hint(p1f + (off - t.oc + 2 * HW + t.h_off), strm);
+        if (t.halo && rem >= 2) hq = LD_STRM(p1f + (off - t.oc + 2 * HW + t.h_off), strm);
       }
       // gathers of plane k+2 (own) and k+1 (halo): in flight during the stencil of plane k
       float2 e1nn[CPT], e0nn[CPT];
@@ -489,7 +497,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
       ldgs(domf + off, sc, strm);
       ldgs(domf + off + s1, sn, strm);
       float hp0 = 0.f, hs0 = 0.f;
-      if (t.halo) { hp0 = ld_hint(p1f + t.h_off, strm); hs0 = ld_hint(domf + t.h_off, strm); hq = ld_hint(p1f + (s1 + t.h_off), strm); }
+      if (t.halo) { hp0 = LD_STRM(p1f + t.h_off, strm); hs0 = LD_STRM(domf + t.h_off, strm); hq = LD_STRM(p1f + (s1 + t.h_off), strm); }
       ldgs(p1f + off + s2, pq, strm);
       ldgs(p0f + off + s2, p0q, strm);
       float4 e1a[CPT], e1b[CPT], e0a[CPT], e0b[CPT];
@@ -534,8 +542,8 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
         ldgs(p1f + off + u3, pq, strm);
         ldgs(p0f + off + u3, p0q, strm);
         ldgs(domf + off + u2, snn, strm);
-        if (t.halo && rem >= 2) hq = ld_hint(p1f + (off - t.oc + 2 * HW + t.h_off), strm);
-        if (t.halo && rem >= 1) hs = ld_hint(domf + (off - t.oc + HW + t.h_off), strm);
+        if (t.halo && rem >= 2) hq = LD_STRM(p1f + (off - t.oc + 2 * HW + t.h_off), strm);
+        if (t.halo && rem >= 1) hs = LD_STRM(domf + (off - t.oc + HW + t.h_off), strm);
       }
       float4 e1nn[CPT], e0nn[CPT];
 #pragma unroll
@@ -667,8 +675,28 @@ bool srm_dg4_applicable(const SrmHandle* h) {
   return h->lut_full && P.lut_n > 0 && P.W % CPT == 0 && P.W >= CPT;
 }
 
+// The table gathers miss the L1 by construction, and the number of misses an SM keeps in flight grows with the L1's
+// capacity (tools/gather_probe2.cu: 1.1 SM-cycles per gather with the whole 256 KB array as L1, 2.4 with a 227 KB
+// shared-memory carve-out).  Left alone the driver configures ~100 KB of shared memory for these kernels although four
+// resident CTAs need 35-46 KB, so the carve-out is requested explicitly (percent of the maximum; SRM_D4_CARVEOUT overrides).
+static cudaError_t dg4_set_carveout() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  int pct = 20;
+  if (const char* e = getenv("SRM_D4_CARVEOUT")) pct = atoi(e);
+  if (pct >= 0) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_fwd4, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e1 != cudaSuccess) return e1;
+    e1 = cudaFuncSetAttribute(k_adj4, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e1 != cudaSuccess) return e1;
+  }
+  done = true;
+  return cudaSuccess;
+}
+
 cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s) {
   const SrmDev& P = h->dev;
+  { cudaError_t ce = dg4_set_carveout(); if (ce != cudaSuccess) return ce; }
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
@@ -681,6 +709,7 @@ cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, 
 
 cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s) {
   const SrmDev& P = h->dev;
+  { cudaError_t ce = dg4_set_carveout(); if (ce != cudaSuccess) return ce; }
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
