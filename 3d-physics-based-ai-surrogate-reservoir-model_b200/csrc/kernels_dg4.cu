@@ -679,8 +679,9 @@ bool srm_dg4_applicable(const SrmHandle* h) {
 // capacity (tools/gather_probe2.cu: 1.1 SM-cycles per gather with the whole 256 KB array as L1, 2.4 with a 227 KB
 // shared-memory carve-out).  Left alone the driver configures ~100 KB of shared memory for these kernels although four
 // resident CTAs need 35-46 KB, so the carve-out is requested explicitly (percent of the maximum; SRM_D4_CARVEOUT overrides).
-static cudaError_t dg4_set_carveout() {
-  static bool done = false;
+static cudaError_t dg4_set_carveout(int device) {
+  static bool done_dev[64] = {};              // function attributes are per device
+  bool& done = done_dev[device & 63];
   if (done) return cudaSuccess;
   int pct = 20;
   if (const char* e = getenv("SRM_D4_CARVEOUT")) pct = atoi(e);
@@ -696,7 +697,7 @@ static cudaError_t dg4_set_carveout() {
 
 cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s) {
   const SrmDev& P = h->dev;
-  { cudaError_t ce = dg4_set_carveout(); if (ce != cudaSuccess) return ce; }
+  { cudaError_t ce = dg4_set_carveout(h->device); if (ce != cudaSuccess) return ce; }
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
@@ -709,7 +710,7 @@ cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, 
 
 cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s) {
   const SrmDev& P = h->dev;
-  { cudaError_t ce = dg4_set_carveout(); if (ce != cudaSuccess) return ce; }
+  { cudaError_t ce = dg4_set_carveout(h->device); if (ce != cudaSuccess) return ce; }
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);

@@ -359,7 +359,8 @@ cudaError_t srm_dg5_launch_fwd(const SrmHandle* h, const void* args, int32_t B, 
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW5 - 1) / TW5;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY5 - 1) / TY5)), (unsigned)B);
-  static bool attr = false;
+  static bool attr_dev[64] = {};              // function attributes are per device
+  bool& attr = attr_dev[h->device & 63];
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_fwd5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemF));
     if (e != cudaSuccess) return e;
