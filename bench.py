@@ -9,8 +9,10 @@ dL/ddt2) over one batch of synthetic input of the named BASELINE config.  Prints
   value      cell-timesteps/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public API with HOST (pinned) buffers: H2D of the step's
              inputs and D2H of the loss terms and gradients inside the timed region
-  roofline   algorithmic bytes (28 + 8/T per cell-timestep) / step time vs the measured
-             HBM copy peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback of B200_PROFILING.md)
+  roofline   the dominant kernel (the adjoint pass): algorithmic bytes (16 + 4/T per cell-timestep) /
+             its CUDA-event-timed duration vs the measured HBM copy peak (MEASURED_PEAKS.json, else the 6650 GB/s
+             fallback of B200_PROFILING.md); `forward` (12 + 4/T) and `step` (28 + 8/T, whole step) beside it;
+             `traffic` = dram bytes per launch from the committed ncu capture (profiles/traffic.json)
   cpu_baseline  the oracle (a port of the reference's TF op graph; TensorFlow is not installable
              here) on the box's host cores, bounded sample of the same workload
 
@@ -375,6 +377,39 @@ def run_ours(args):
         if glue:
             glue["frac"] = glue["achieved_GBps"] / peak
         achieved = N * reps * ab / (ms_step * 1e-3) / 1e9   # per GPU (each rank runs N * reps cells per step)
+        # roofline of the dominant kernel (the adjoint pass) per the bench contract, with the forward pass and the whole
+        # step beside it.  Pass durations are CUDA-event windows on the launching stream over the timed region: the
+        # adjoint window holds k_adj4 (or the GC adjoint) plus its sparse inner-boundary and finalize kernels (~2 %).
+        tr = measured_traffic(args.workload, args.numerics) or {}
+        pk = tr.get("per_kernel", {})
+
+        def kernel_traffic(*names):
+            for n in names:
+                if n in pk:
+                    return pk[n]["read"] + pk[n]["write"]
+            return None
+        ab_f = (28.0 if gc else 12.0) + 4.0 / T
+        ab_a = (52.0 if gc else 16.0) + 4.0 / T
+        one = N / 1e9                       # cells of one chunk (the pass windows cover one chunk)
+
+        def pass_obj(name, ms_, abytes, traffic):
+            ach = one * abytes / (ms_ * 1e-3) if ms_ == ms_ and ms_ > 0 else None
+            return {"kernel": name, "ms": float(ms_), "alg_bytes_per_cell": abytes, "achieved": ach,
+                    "frac": (ach / peak) if ach else None, "traffic": traffic}
+        adj = pass_obj("adjoint pass: " + ("k_resid_adj_gc" if gc else "k_adj4") + " (+ inner-boundary scatter, finalize)", bwd_ms, ab_a,
+                       kernel_traffic("k_adj4", "k_resid_adj_gc"))
+        fwdp = pass_obj("forward pass: " + ("k_stage_gc + k_resid_fwd_gc" if gc else "k_fwd4") + " (+ faces, wells, finalize)", fwd_ms, ab_f,
+                        kernel_traffic("k_fwd4", "k_resid_fwd_gc"))
+        roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                "kernel": adj["kernel"], "achieved": adj["achieved"], "frac": adj["frac"], "traffic": adj["traffic"],
+                "alg_bytes_per_cell": ab_a, "ms": adj["ms"],
+                "traffic_source": tr.get("source"),
+                "forward": fwdp,
+                "step": {"kernel": "whole step (forward + adjoint launches)", "ms": ms_step, "alg_bytes_per_cell": ab,
+                         "achieved": achieved, "frac": achieved / peak, "traffic": tr.get("bytes_per_step")},
+                "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms),
+                "note": ("reference-order numerics: the exact-table gathers bound both passes at the L2 sector rate "
+                         "(tools/gather_probe2.cu; floor = 25 % of the HBM roofline, DESIGN.md 5.1)") if (lut and not gc) else None}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = cpu_oracle_throughput(args.workload, target_seconds=12.0)
@@ -390,12 +425,7 @@ def run_ours(args):
                               else "evaluated per cell",
                        "l2": "inputs+workspace per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % ((2 * N * 4 + eng.workspace(B, b.kx.shape[0]).numel()) / 1e6),
                        "parallelism": f"sample-sharded x{world}; all-reduce of the 16-float loss-term vector only"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (measured_traffic(args.workload, args.numerics) or {}).get("bytes_per_step"),
-                         "traffic_source": (measured_traffic(args.workload, args.numerics) or {}).get("source"),
-                         "peak_source": peak_src,
-                         "kernel": "whole step (forward + adjoint launches); algorithmic bytes = %.2f B/cell-timestep" % ab,
-                         "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms)},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * reps, "d2h_bytes_per_step": int(d2h) * reps,
                     "steps": e2e_steps, "loss": loss,
