@@ -20,12 +20,14 @@ __all__ = ["_lib", "config", "pvt", "synth", "PhysicsSpec", "spec_from_reference
 def __getattr__(name):
     # engine / physics_loss import torch.cuda-facing code lazily
     import importlib
-    if name in ("engine", "physics_loss", "wells", "dist", "hard_layer"):
+    if name in ("engine", "physics_loss", "wells", "dist", "hard_layer", "batching"):
         return importlib.import_module(f"{__name__}.{name}")
     if name == "SrmPhysics":
         return importlib.import_module(f"{__name__}.engine").SrmPhysics
     if name in ("PhysicsLoss",):
         return getattr(importlib.import_module(f"{__name__}.physics_loss"), name)
+    if name == "BatchGenerator":
+        return importlib.import_module(f"{__name__}.batching").BatchGenerator
     if name in ("HardLayer", "CompleteTrainableModule"):
         return getattr(importlib.import_module(f"{__name__}.hard_layer"), name)
     if name in ("WellRatesPressure", "WellDataProcessor"):

@@ -28,7 +28,7 @@ SRM_FLAG_SAVE_FOR_BACKWARD = 1
 EXPORTS = (
     "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
     "srm_pvt_eval", "srm_denormalize_log", "srm_selftest_rounding", "srm_wells", "srm_forward", "srm_backward",
-    "srm_relperm", "srm_forward_gc", "srm_backward_gc", "srm_glue_workspace_bytes", "srm_glue_forward", "srm_glue_backward",
+    "srm_relperm", "srm_forward_gc", "srm_backward_gc", "srm_glue_workspace_bytes", "srm_glue_forward", "srm_glue_backward", "srm_gather_rows",
 )
 
 
@@ -108,6 +108,8 @@ def load_library(path: Optional[str] = None):
     lib.srm_glue_forward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 11 + [vp, C.c_size_t, vp]
     lib.srm_glue_backward.restype = C.c_int
     lib.srm_glue_backward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 14 + [vp]
+    lib.srm_gather_rows.restype = C.c_int
+    lib.srm_gather_rows.argtypes = [i32, vp, vp, i64, i64, i64, vp, vp]
     if lib.srm_version() != SRM_ABI_VERSION:
         raise RuntimeError(f"libsrm_physics ABI {lib.srm_version()} != binding {SRM_ABI_VERSION}")
     if path == LIB_PATH:

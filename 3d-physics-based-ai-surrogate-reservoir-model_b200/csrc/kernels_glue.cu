@@ -182,3 +182,47 @@ extern "C" int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value
   SRM_CUDA_CHECK(cudaGetLastError());
   return SRM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// BatchGenerator.__getitem__ on a device-resident data set: tf.gather(x_all, batch_inds, axis=0)
+// (training.py:110-143) without the per-step host-to-device conversion of the whole data set.  Byte work: bit-exact.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// one CTA per (row, 16 KB segment of the row): 16-byte vectors when rows are 16-byte multiples and both bases aligned
+template <class V>
+__global__ void __launch_bounds__(256) k_gather_rows(const V* __restrict__ src, const int32_t* __restrict__ idx, int64_t n_rows,
+                                                     int64_t row_vecs, V* __restrict__ dst) {
+  const int64_t r = blockIdx.y;
+  const int32_t s = idx[r];
+  V* out = dst + r * row_vecs;
+  const bool ok = s >= 0 && (int64_t)s < n_rows;             // out-of-range index: zero row (tf.gather on a GPU)
+  const V* in = src + (int64_t)(ok ? s : 0) * row_vecs;
+  V zero;
+  memset(&zero, 0, sizeof(V));
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < row_vecs; v += (int64_t)gridDim.x * blockDim.x)
+    out[v] = ok ? in[v] : zero;
+}
+
+}  // namespace
+
+extern "C" int srm_gather_rows(int32_t device, const void* src, const int32_t* idx, int64_t n_idx, int64_t n_rows,
+                               int64_t row_bytes, void* dst, void* stream) {
+  if (n_idx < 0 || n_rows < 1 || row_bytes < 1 || (n_idx > 0 && (!src || !idx || !dst)) || n_idx > 65535) {
+    srm_set_error("srm_gather_rows: bad argument (n_idx <= 65535)");
+    return SRM_ERR_INVALID;
+  }
+  if (n_idx == 0) return SRM_OK;
+  SRM_CUDA_CHECK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool a16 = row_bytes % 16 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  const bool a4 = row_bytes % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0;
+  const int64_t vecs = a16 ? row_bytes / 16 : (a4 ? row_bytes / 4 : row_bytes);
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((vecs + 1023) / 1024, 1024));
+  const dim3 grid(gx, (unsigned)n_idx);
+  if (a16) k_gather_rows<uint4><<<grid, 256, 0, s>>>((const uint4*)src, idx, n_rows, vecs, (uint4*)dst);
+  else if (a4) k_gather_rows<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)src, idx, n_rows, vecs, (uint32_t*)dst);
+  else k_gather_rows<unsigned char><<<grid, 256, 0, s>>>((const unsigned char*)src, idx, n_rows, vecs, (unsigned char*)dst);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

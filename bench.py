@@ -370,12 +370,43 @@ def run_ours(args):
                 "achieved_GBps": N * gbytes / (gms * 1e-3) / 1e9,
                 "kernels": "k_glue_fwd + k_glue_mean + k_glue_bwd (srm_glue_forward / srm_glue_backward)"}
         del ydev
+        # batch gather of the device-resident feature tensor (BatchGenerator.__getitem__)
+        try:
+            lib = srm._lib.load_library()
+            rowb = spec.n_cells * 5 * 4
+            nb = min(B, max(1, int(2e9 // rowb)))
+            xs = torch.rand((nb, spec.n_cells * 5), device=dev)
+            xo = torch.empty_like(xs)
+            perm = torch.randperm(nb, device=dev, dtype=torch.int32)
+            st = torch.cuda.current_stream(dev).cuda_stream
+
+            def gat():
+                for a in range(0, nb, 65535):
+                    e = min(nb, a + 65535)
+                    srm._lib.check(lib, lib.srm_gather_rows(local, xs.data_ptr(), perm[a:e].data_ptr(), e - a, nb, rowb, xo[a:e].data_ptr(), st), "srm_gather_rows")
+            for _ in range(3):
+                gat()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            q0.record()
+            for _ in range(gsteps):
+                gat()
+            q1.record()
+            torch.cuda.synchronize(dev)
+            qms = q0.elapsed_time(q1) / gsteps
+            glue["batch_gather"] = {"ms": qms, "rows": nb, "row_bytes": rowb, "achieved_GBps": 2.0 * nb * rowb / (qms * 1e-3) / 1e9,
+                                    "kernel": "k_gather_rows (srm_gather_rows): x_batch = x_all[batch_inds] on the device-resident data set"}
+            del xs, xo
+        except Exception as e:      # never let an auxiliary measurement break the bench line
+            glue["batch_gather"] = {"error": repr(e)}
 
     if rank == 0:
         peak, peak_src = peak_hbm()
         ab = alg_bytes_per_cell(T, gc)
         if glue:
             glue["frac"] = glue["achieved_GBps"] / peak
+            if "achieved_GBps" in glue.get("batch_gather", {}):
+                glue["batch_gather"]["frac"] = glue["batch_gather"]["achieved_GBps"] / peak
         achieved = N * reps * ab / (ms_step * 1e-3) / 1e9   # per GPU (each rank runs N * reps cells per step)
         # roofline of the dominant kernel (the adjoint pass) per the bench contract, with the forward pass and the whole
         # step beside it.  Pass durations are CUDA-event windows on the launching stream over the timed region: the

@@ -244,6 +244,13 @@ int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_l
                       const float* gp1, const float* gdt1, const float* gdt2, float* gy0, float* gy1, float* gexpo,
                       float* gdtf1, float* gdtf2, void* stream);
 
+/* BatchGenerator.__getitem__ on a device-resident data set (training.py:110-143: tf.gather(x_all, batch_inds,
+ * axis=0) after converting the WHOLE data set to a tensor every step): dst[r] = src[idx[r]] for r < n_idx, rows of
+ * row_bytes bytes; idx is a DEVICE int32[n_idx] (<= 65535 rows per call); an index outside [0, n_rows) yields a zero
+ * row, as tf.gather does on a GPU.  Byte work: bit-exact. */
+int srm_gather_rows(int32_t device, const void* src, const int32_t* idx, int64_t n_idx, int64_t n_rows,
+                    int64_t row_bytes, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
