@@ -358,3 +358,27 @@ def test_polynomial_pvt_fit(pvt_lut):
     assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
     for k in ("gp0", "gp1", "gdt1"):
         assert h3_close(c[k], o[k]), (k, U.rel_to_max(c[k], o[k]))
+
+
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_cuda_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut):
+    """The CUDA forward against golden fields made by the reference's OWN physics_error_gas_2D (physics_loss.py:9-224,
+    tests/golden/make_reference_dg_golden.py): dom bit for bit, on every kernel family (per-cell spline; exact table:
+    kernels_dg4.cu for the even-W case, kernels_ref2.cu for the odd one)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_dg_residual.npz"))
+    W, H = int(g[f"{case}_W"]), int(g[f"{case}_H"])
+    ocfg, otab, spec, ptab, _ = U.make_case(W=W, H=H, D=1, T=1, K=1, seed=1)
+    ref_wells = O.default_wells(W, H, 1)
+    assert [(w.i, w.j, w.k, w.value, w.producer) for w in ocfg.wells] == [(w.i, w.j, w.k, w.value, w.producer) for w in ref_wells]
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut)
+    dev = eng.device
+    tt = lambda k, dt=torch.float32: torch.as_tensor(g[f"{case}_{k}"]).to(dev, dt).contiguous()
+    fw = eng.forward(tt("kx"), tt("sample_real", torch.int32), tt("p0"), tt("p1"), tt("dt1"), tt("dt2"), tt("t_days"), want_dom=True)
+    torch.cuda.synchronize()
+    dom = fw["dom"].cpu().numpy()
+    assert np.array_equal(dom.view(np.uint32), g[f"{case}_ref_dom"].view(np.uint32))
+    ref_terms = [float((g[f"{case}_ref_dom"].astype(np.float64) ** 2).sum()), float((g[f"{case}_ref_ibc"].astype(np.float64) ** 2).sum()),
+                 float((g[f"{case}_ref_mbc"].astype(np.float64) ** 2).sum())]
+    assert np.allclose(fw["terms"][0, :3].cpu().numpy(), ref_terms, rtol=RTOL)
+    eng.close()

@@ -239,3 +239,22 @@ def test_hard_layer_oracle_gradients_fp64():
     assert torch.allclose(yv.grad, -(at.view(-1, 1, 1, 1) ** e) * w)
     dtf = torch.rand((B, D, H, W), generator=g).double()
     assert torch.allclose(O.time_step_mean_t(dtf), dtf.mean(dim=(1, 2, 3)))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_oracle_dg_residual_equals_the_reference_fragment_bit_for_bit(case):
+    """PIN: tests/golden/reference_dg_residual.npz was produced by the reference's OWN physics_error_gas_2D
+    (physics_loss.py:9-224, executed by tests/golden/make_reference_dg_golden.py through a torch-backed stand-in for the
+    ~20 TensorFlow ops it uses).  The oracle's restatement must reproduce its dom and ibc fields bit for bit and its mbc
+    to summation order, on the same inputs (2-D grids: the shipped stencil has no z faces)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_dg_residual.npz"))
+    W, H = int(g[f"{case}_W"]), int(g[f"{case}_H"])
+    cfg = O.OracleConfig(D=1, H=H, W=W, wells=O.default_wells(W, H, 1))
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    tt = lambda k: torch.as_tensor(g[f"{case}_{k}"])
+    res = O.dg_residual(cfg, tab, tt("kx"), tt("p0"), tt("p1"), tt("dt1"), tt("dt2"), g[f"{case}_t_days"], g[f"{case}_sample_real"])
+    assert np.array_equal(res["dom"].numpy().view(np.uint32), g[f"{case}_ref_dom"].view(np.uint32))
+    assert np.array_equal(res["ibc"].numpy().view(np.uint32), g[f"{case}_ref_ibc"].view(np.uint32))
+    assert np.allclose(res["mbc"].numpy(), g[f"{case}_ref_mbc"], rtol=1e-6, atol=0)
+    assert np.abs(g[f"{case}_ref_ibc"]).max() > 0 and np.abs(g[f"{case}_ref_dom"]).max() > 0
