@@ -137,3 +137,159 @@ math = types.SimpleNamespace(
 )
 random = types.SimpleNamespace(normal=lambda **k: (_ for _ in ()).throw(NotImplementedError("tf.random.normal")))
 keras = types.SimpleNamespace(backend=types.SimpleNamespace(epsilon=lambda: 1e-7))
+
+
+# ---- additions for polyhm_splines.py / PVT_Layer_Subclassed.py / relative_permeability.py ----------------------------
+class _Shape(tuple):
+    @property
+    def rank(self):
+        return len(self)
+
+
+class _T(torch.Tensor):
+    """tensor whose .shape carries .rank (TensorShape), which the spline layer's constructor reads"""
+
+    @property
+    def shape(self):          # noqa: D401
+        return _Shape(super().shape)
+
+
+def convert_to_tensor(value, dtype=None):       # noqa: F811
+    return _t(value, dtype).clone().as_subclass(_T)
+
+
+class _SqrtTF(torch.autograd.Function):
+    """correctly rounded sqrt (numpy; torch-CPU's vectorised sqrt is not), TF's SqrtGrad: (0.5 * dy) / y"""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.from_numpy(np.sqrt(x.detach().numpy()))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        return (0.5 * g) / y
+
+
+def sqrt(x):
+    return _SqrtTF.apply(_t(x).as_subclass(torch.Tensor))
+
+
+def square(x):
+    x = _t(x)
+    return x * x
+
+
+def exp(x):
+    return torch.exp(_t(x))
+
+
+def reshape(x, shape_):
+    sh = [int(s) for s in (shape_.tolist() if isinstance(shape_, torch.Tensor) else shape_)]
+    return _t(x).reshape(sh)
+
+
+def transpose(x, perm=None):
+    x = _t(x)
+    return x.permute(*perm) if perm is not None else x.t()
+
+
+def unstack(x, num=None, axis=0):
+    return [int(v) for v in _t(x).tolist()] if _t(x).dim() == 1 else list(torch.unbind(_t(x), dim=axis))
+
+
+def eye(n, batch_shape=None, dtype=torch.float32):
+    e = torch.eye(int(n), dtype=dtype)
+    return e.expand(*[int(b) for b in batch_shape], int(n), int(n)).clone() if batch_shape else e
+
+
+def ones(shape_, dtype=torch.float32):
+    return torch.ones([int(s) for s in shape_], dtype=dtype)
+
+
+def zeros(shape_, dtype=torch.float32):
+    return torch.zeros([int(s) for s in shape_], dtype=dtype)
+
+
+def concat(values, axis):
+    return torch.cat([_t(v) for v in values], dim=axis)
+
+
+def tile(x, multiples):
+    return _t(x).repeat(*[int(m) for m in multiples])
+
+
+def rank(x):
+    return _t(x).dim()
+
+
+def reduce_prod(x, axis=None):
+    x = _t(x)
+    return int(torch.prod(x)) if axis is None else torch.prod(x, dim=axis)
+
+
+def matmul(a, b, transpose_b=False):
+    """batched matmul with the inner index accumulated SEQUENTIALLY in fp32, one rounded multiply and one rounded add
+    per term (no FMA): the accumulation order this repository's oracle pins where TensorFlow leaves it open"""
+    a, b = _t(a), _t(b)
+    if transpose_b:
+        b = b.transpose(-1, -2)
+    n = a.shape[-1]
+    assert b.shape[-2] == n
+    acc = a[..., :, 0:1] * b[..., 0:1, :]
+    for i in range(1, n):
+        acc = acc + a[..., :, i:i + 1] * b[..., i:i + 1, :]
+    return acc
+
+
+def pow(x, y):            # noqa: A001
+    return torch.pow(_t(x), y)
+
+
+def clip_by_value(x, lo, hi):
+    return torch.minimum(torch.maximum(_t(x), _t(lo, _t(x).dtype)), _t(hi, _t(x).dtype))
+
+
+linalg = types.SimpleNamespace(solve=lambda a, b: torch.linalg.solve(_t(a), _t(b)))
+
+
+class GradientTape:
+    def __init__(self, persistent=False):
+        self._watched = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def watch(self, x):
+        x.requires_grad_(True)
+
+    def gradient(self, y, x):
+        return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True)[0]
+
+
+class _Layer:
+    def __init__(self, name=None, dtype=None, **kwargs):
+        self.name = name
+        self._built = False
+
+    def build(self, input_shape):
+        self._built = True
+
+    def __call__(self, *a, **k):
+        if not self._built:
+            self.build(getattr(a[0], "shape", None) if a else None)
+        return self.call(*a, **k)
+
+
+keras.layers = types.SimpleNamespace(Layer=_Layer)
+keras.initializers = types.SimpleNamespace(Constant=lambda v: v)
+math.exp = exp
+math.sqrt = sqrt
+math.maximum = maximum
+math.minimum = minimum
+math.square = square

@@ -150,3 +150,21 @@ def test_gc_vs_committed_golden():
     for name, t in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1"), gr):
         assert h3_close(t.cpu().numpy(), g["o_" + name], noise=g["noise_" + name]), name
     eng.close()
+
+
+def test_cuda_pvt_and_relperm_against_reference_made_goldens():
+    """CUDA srm_pvt_eval (seven gas-condensate properties, the oracle's (w, v) as data) against values produced by the
+    reference's OWN PolyharmonicSplineInterpolationLayer: bit for bit; CUDA srm_relperm against the reference's OWN
+    RelativePermeability.compute_krog_krgo: <= 2 ulp (tf.pow pinned as a product), end-point branches exact.
+    Goldens: tests/golden/make_reference_pvt_golden.py."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_pvt_relperm.npz"))
+    ocfg, otab, spec, ptab, d = U.gc_case(1)
+    tabs = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    eng = srm.SrmPhysics(spec, tabs, device=0)
+    val, der = eng.pvt_eval(torch.from_numpy(g["p"]).cuda())
+    for q, name in enumerate(O.GC_PROPS):
+        assert np.array_equal(val[q].cpu().numpy().view(np.uint32), g[f"o1_{name}_wv"].view(np.uint32)), name
+    a = [t.cpu().numpy() for t in eng.relperm(torch.from_numpy(g["sg"]).cuda())]
+    assert U.ulp_diff(a[0], g["krog"]) <= 2 and U.ulp_diff(a[1], g["krgo"]) <= 2
+    assert np.array_equal(a[0] == 0, g["krog"] == 0) and np.array_equal(a[1] == np.float32(0.9), g["krgo"] == np.float32(0.9))
+    eng.close()

@@ -258,3 +258,60 @@ def test_oracle_dg_residual_equals_the_reference_fragment_bit_for_bit(case):
     assert np.array_equal(res["ibc"].numpy().view(np.uint32), g[f"{case}_ref_ibc"].view(np.uint32))
     assert np.allclose(res["mbc"].numpy(), g[f"{case}_ref_mbc"], rtol=1e-6, atol=0)
     assert np.abs(g[f"{case}_ref_ibc"]).max() > 0 and np.abs(g[f"{case}_ref_dom"]).max() > 0
+
+
+def _ref_pvt():
+    return np.load(os.path.join(U.GOLDEN, "reference_pvt_relperm.npz"))
+
+
+def test_oracle_spline_equals_the_reference_layer_bit_for_bit():
+    """PIN: the reference's OWN PolyharmonicSplineInterpolationLayer (polyhm_splines.py, executed whole by
+    tests/golden/make_reference_pvt_golden.py through the torch-backed TF stand-in whose matmul accumulates sequentially)
+    evaluated with the oracle's (w, v) as data: order-1 values of all seven properties bit for bit.  With the layer's own
+    in-call solve (LAPACK through torch instead of numpy; cond ~ 3.6e6) the values agree to 5e-6."""
+    g = _ref_pvt()
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    for pi, prop in enumerate(O.GC_PROPS):
+        val = O.spline_eval_np(g["p"], tab, pi, np.float32, need=0)[0]
+        assert np.array_equal(val.view(np.uint32), g[f"o1_{prop}_wv"].view(np.uint32)), prop
+        assert np.abs(val - g[f"o1_{prop}_full"]).max() <= 5e-6 * np.abs(val).max(), prop
+        assert np.abs(tab.w[pi] - g[f"o1_{prop}_w"]).max() <= 1e-3 * np.abs(tab.w[pi]).max(), prop
+    # order 2 (0.5 r ln r): log is not bit-identical across libraries and the terms cancel heavily; formula-level check
+    tab2 = O.build_spline_table(cols, O.GC_PROPS, order=2, lam=0.001)
+    for pi, prop in enumerate(O.GC_PROPS):
+        val = O.spline_eval_np(g["p"], tab2, pi, np.float32, need=0)[0]
+        assert np.abs(val - g[f"o2_{prop}_wv"]).max() <= 5e-3 * np.abs(val).max(), prop
+
+
+def test_oracle_pvt_layer_contract_against_the_reference_layer():
+    """PVTLayer.call cut out of PVT_Layer_Subclassed.py and executed: output layout [2, n_prop, B, ..., 1], clamp to
+    [14.7, 10000], derivative w.r.t. the CLAMPED input (torch autograd standing in for TF's tape: same formula chain,
+    the accumulation order of the gradient is the framework's, hence 1e-4 of max instead of bits)."""
+    g = _ref_pvt()
+    out, pp = g["pvt_layer_out"], g["pvt_p"]
+    assert out.shape == (2, 2, 1, pp.size, 1, 1)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    xc = O.pvt_clamp(torch.as_tensor(pp), O.OracleConfig()).numpy()
+    assert xc.min() == np.float32(14.7) and xc.max() == np.float32(10000.0)
+    for q in range(2):
+        v, d1, _ = O.spline_eval_np(xc, tab, q, np.float32, need=1)
+        assert np.abs(v - out[0, q].reshape(-1)).max() <= 1e-5 * np.abs(v).max()
+        assert np.abs(d1 - out[1, q].reshape(-1)).max() <= 1e-4 * np.abs(d1).max()
+        # below / above the clamp the layer returns the edge value AND the edge derivative
+        lo, hi = np.where(pp == np.float32(5.0))[0][0], np.where(pp == np.float32(12000.0))[0][0]
+        e_lo, e_hi = np.where(pp == np.float32(14.7))[0][0], np.where(pp == np.float32(10000.0))[0][0]
+        for a, b in ((lo, e_lo), (hi, e_hi)):
+            assert out[0, q].reshape(-1)[a] == out[0, q].reshape(-1)[b] and out[1, q].reshape(-1)[a] == out[1, q].reshape(-1)[b]
+
+
+def test_oracle_relperm_against_the_reference_class():
+    """RelativePermeability.compute_krog_krgo (relative_permeability.py, executed whole): the oracle pins tf.pow with the
+    integer Corey exponents as a left-to-right product, libm's pow differs by at most 2 ulp; the end-point rules agree
+    exactly."""
+    g = _ref_pvt()
+    krog, krgo = O.corey_krog_krgo_np(g["sg"], O.OracleConfig(), np.float32)
+    assert U.ulp_diff(krog, g["krog"]) <= 2 and U.ulp_diff(krgo, g["krgo"]) <= 2
+    assert np.array_equal(krog == 0, g["krog"] == 0) and np.array_equal(krgo == np.float32(0.9), g["krgo"] == np.float32(0.9))
+    assert (g["krog"] == 0).sum() > 10 and (g["krgo"] == np.float32(0.9)).sum() > 3
