@@ -168,3 +168,31 @@ def test_cuda_pvt_and_relperm_against_reference_made_goldens():
     assert U.ulp_diff(a[0], g["krog"]) <= 2 and U.ulp_diff(a[1], g["krgo"]) <= 2
     assert np.array_equal(a[0] == 0, g["krog"] == 0) and np.array_equal(a[1] == np.float32(0.9), g["krgo"] == np.float32(0.9))
     eng.close()
+
+
+@pytest.mark.parametrize("pvt_lut", [False, True])
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_cuda_gc_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut):
+    """The CUDA gas-condensate forward against fields computed by the reference's OWN physics_error_gas_oil_2D
+    (tests/golden/make_reference_gc_golden.py): dom bit for bit; the SSE terms (dom, ibc, mbc, cmbc) to 1e-5."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_gc_residual.npz"))
+    W, H = int(g[f"{case}_W"]), int(g[f"{case}_H"])
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for r in g[f"{case}_wells"]]
+    spec = srm.PhysicsSpec(D=1, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC")
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut, lut_range=(4650.0, 4720.0) if pvt_lut else None)
+    dev = eng.device
+    tt = lambda k, dt=torch.float32: torch.as_tensor(g[f"{case}_{k}"]).to(dev, dt).contiguous()
+    fw = eng.forward_gc(tt("kx"), tt("sample_real", torch.int32), tt("p0"), tt("p1"), tt("sg0"), tt("sg1"), tt("so0"), tt("so1"),
+                        tt("dt1"), tt("dt2"), tt("t1"), want_dom=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(fw["dom"].cpu().numpy().view(np.uint32), g[f"{case}_ref_dom"].view(np.uint32))
+    sse = lambda k: float((g[f"{case}_{k}"].astype(np.float64) ** 2).sum())
+    terms = fw["terms"][0].cpu().numpy()
+    T = srm._lib.TERM_NAMES
+    for name, k in (("dom", "ref_dom"), ("ibc", "ref_ibc"), ("mbc", "ref_mbc"), ("cmbc", "ref_cmbc")):
+        assert np.isclose(terms[T.index(name)], sse(k), rtol=1e-5, atol=1e-30), name
+    eng.close()

@@ -114,3 +114,28 @@ def test_gc_oracle_reproduces_golden():
     assert np.allclose(o["terms"], g["o_terms"], rtol=1e-6)
     for k in ("gp0", "gp1", "gsg1"):
         assert np.allclose(o[k], g["o_" + k], rtol=1e-5, atol=1e-6 * np.abs(g["o_" + k]).max())
+
+
+def _gc_ref_case(g, case):
+    import srm_oracle as O
+    W, H = int(g[f"{case}_W"]), int(g[f"{case}_H"])
+    wl = [O.Well(i=int(r[0]), j=int(r[1]), k=int(r[2]), value=float(r[3])) for r in g[f"{case}_wells"]]
+    return O.OracleConfig(D=1, H=H, W=W, wells=wl)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_oracle_gc_residual_equals_the_reference_fragment_bit_for_bit(case):
+    """PIN: tests/golden/reference_gc_residual.npz holds dom, ibc, mbc, cmbc computed by the reference's OWN
+    physics_error_gas_oil_2D (physics_loss.py:230-714, executed by tests/golden/make_reference_gc_golden.py through the
+    torch-backed TF stand-in).  The oracle must reproduce the fields bit for bit on the same inputs (2-D grids)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_gc_residual.npz"))
+    cfg = _gc_ref_case(g, case)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    tt = lambda k: torch.as_tensor(g[f"{case}_{k}"])
+    res = O.gc_residual(cfg, tab, tt("kx"), tt("p0"), tt("p1"), tt("sg0"), tt("sg1"), tt("so0"), tt("so1"), tt("dt1"), tt("dt2"),
+                        g[f"{case}_t1"], g[f"{case}_sample_real"])
+    for k, rk in (("dom", "ref_dom"), ("ibc", "ref_ibc"), ("cmbc", "ref_cmbc")):
+        assert np.array_equal(res[k].detach().numpy().view(np.uint32), g[f"{case}_{rk}"].view(np.uint32)), k
+    assert np.allclose(res["mbc"].detach().numpy(), g[f"{case}_ref_mbc"], rtol=1e-6, atol=0)
+    assert np.abs(g[f"{case}_ref_dom"]).max() > 0 and np.abs(g[f"{case}_ref_cmbc"]).max() > 0
