@@ -83,7 +83,7 @@ def scatter_nd(indices, updates, shape):
     idx = _t(indices).long()
     upd = _t(updates)
     out = torch.zeros(tuple(int(s) for s in np.asarray(shape).tolist()), dtype=upd.dtype)
-    out.index_put_(tuple(idx[:, k] for k in range(idx.shape[1])), upd, accumulate=True)     # duplicates sum
+    out.index_put_(tuple(idx[:, k] for k in builtins_range(idx.shape[1])), upd, accumulate=True)     # duplicates sum
     return out
 
 
@@ -104,7 +104,7 @@ def reduce_sum(x, axis=None, keepdims=False):
 
 
 def where(cond, a, b):
-    return torch.where(cond, _t(a), _t(b))
+    return torch.where(_t(cond).to(torch.bool) if not isinstance(cond, torch.Tensor) else cond, _t(a), _t(b))
 
 
 def maximum(a, b):
@@ -293,3 +293,122 @@ math.sqrt = sqrt
 math.maximum = maximum
 math.minimum = minimum
 math.square = square
+
+
+# ---- additions for welldata_processor.py / well_rate_bhp_Subclassed.py ------------------------------------------------
+Tensor = torch.Tensor
+string = object()
+
+
+def size(x):
+    return torch.tensor(_t(x).numel(), dtype=torch.int32)
+
+
+def equal(a, b):
+    if isinstance(a, str) or isinstance(b, str):
+        return torch.tensor(a == b)
+    return _t(a) == _t(b)
+
+
+def less(a, b):
+    return _t(a) < _t(b)
+
+
+def greater(a, b):
+    return _t(a) > _t(b)
+
+
+def logical_and(a, b):
+    return _t(a) & _t(b)
+
+
+def logical_or(a, b):
+    return _t(a) | _t(b)
+
+
+def logical_not(a):
+    return ~_t(a)
+
+
+def reduce_any(x, axis=None):
+    x = _t(x)
+    return x.any() if axis is None else x.any(dim=axis)
+
+
+def cond(pred, true_fn, false_fn):
+    return true_fn() if _b.bool(pred) else false_fn()
+
+
+def fill(shape_, value):
+    return torch.full([int(s) for s in (shape_.tolist() if isinstance(shape_, torch.Tensor) else shape_)], float(value), dtype=torch.float32)
+
+
+def range(*a, dtype=None):            # noqa: A001
+    return torch.arange(*[int(v) for v in a], dtype=dtype or torch.int32)
+
+
+def gather(params, indices, axis=0):
+    idx = _t(indices).long()
+    return _t(params).index_select(axis, idx.reshape(-1)).reshape(*_t(params).shape[:axis], *idx.shape, *_t(params).shape[axis + 1:]) \
+        if idx.dim() != 0 else _t(params).select(axis, int(idx))
+
+
+def gather_nd(params, indices):
+    idx = _t(indices).long()
+    return _t(params)[tuple(idx[..., k] for k in builtins_range(idx.shape[-1]))]
+
+
+def tensor_scatter_nd_update(tensor, indices, updates):
+    out = _t(tensor).clone()
+    idx = _t(indices).long()
+    out[tuple(idx[:, k] for k in builtins_range(idx.shape[1]))] = _t(updates).to(out.dtype)       # last writer wins
+    return out
+
+
+def linspace(start, stop, num):
+    """tf.linspace with tensor end points along a new leading axis: start + delta*i for the interior, the END POINTS
+    THEMSELVES at both ends (math_ops.linspace_nd concatenates (start, interior, stop))"""
+    start, stop = torch.broadcast_tensors(_t(start), _t(stop))
+    num = int(num)
+    delta = (stop - start) / float(num - 1)
+    interior = [start + delta * float(i) for i in builtins_range(1, num - 1)]
+    return torch.stack([start] + interior + [stop], dim=0)
+
+
+class TensorArray:
+    def __init__(self, dtype=None, size=0, dynamic_size=False, clear_after_read=True):
+        self._items = {}
+
+    def write(self, i, v):
+        self._items[int(i)] = v
+        return self
+
+    def stack(self):
+        return torch.stack([self._items[k] for k in sorted(self._items)]) if self._items else torch.zeros(0)
+
+
+import builtins as _b      # noqa: E402
+builtins_range = _b.range
+math.cumsum = lambda x, axis=0: torch.cumsum(_t(x), dim=axis)
+debugging = types.SimpleNamespace(assert_shapes=lambda *a, **k: None, assert_equal=lambda *a, **k: None,
+                                  assert_none_equal=lambda *a, **k: None, assert_greater_equal=lambda *a, **k: None,
+                                  assert_less_equal=lambda *a, **k: None)
+bool = torch.bool
+
+
+def while_loop(cond, body, loop_vars, shape_invariants=None, **k):
+    v = list(loop_vars)
+    while _b.bool(cond(*v)):
+        v = list(body(*v))
+    return v
+
+
+def less_equal(a, b):
+    return _t(a) <= _t(b)
+
+
+def greater_equal(a, b):
+    return _t(a) >= _t(b)
+
+
+torch.Tensor.get_shape = lambda self: tuple(self.shape)     # only read to fill tf.while_loop's shape_invariants

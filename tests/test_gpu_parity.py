@@ -382,3 +382,28 @@ def test_cuda_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut):
                  float((g[f"{case}_ref_mbc"].astype(np.float64) ** 2).sum())]
     assert np.allclose(fw["terms"][0, :3].cpu().numpy(), ref_terms, rtol=RTOL)
     eng.close()
+
+
+@pytest.mark.parametrize("name,blocking", [("dg", False), ("dgblk", True)])
+def test_cuda_wells_against_the_reference_class(name, blocking):
+    """CUDA srm_wells against the rate / BHP fields returned by the reference's OWN WellRatesPressure.compute_rates_and_bhp
+    (tests/golden/make_reference_wells_golden.py).  Integer work (cells, shut-in identity, zeros off the connections) is
+    exact; rates and BHP to 1e-5: the Peaceman factor goes through pow/log, which are not bit-identical between libm
+    and CUDA (the oracle, which uses libm like the stand-in, matches the reference bit for bit: tests/test_oracle.py)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells.npz"))
+    D, H, W, B = (int(g[f"{name}_{k}"]) for k in ("D", "H", "W", "B"))
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[float(r[4]), float(r[5])]]) for r in g[f"{name}_wells"]]
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), use_blocking_factor=blocking, n_intervals=8)
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    eng = srm.SrmPhysics(spec, tabs)
+    dev = eng.device
+    out = eng.wells(torch.from_numpy(g[f"{name}_kx"]).to(dev), torch.arange(B, dtype=torch.int32, device=dev),
+                    torch.from_numpy(g[f"{name}_p"]).to(dev), torch.from_numpy(g[f"{name}_t_days"]).to(dev), dense=True)
+    torch.cuda.synchronize()
+    q, pwf = out["q"].cpu().numpy(), out["pwf"].cpu().numpy()
+    rq, rp = g[f"{name}_q"], g[f"{name}_pwf"]
+    assert np.array_equal(q == 0, rq == 0) and np.array_equal(pwf == 0, rp == 0)         # cells, shut-ins, zeros elsewhere
+    assert np.allclose(q, rq, rtol=RTOL, atol=0) and np.allclose(pwf, rp, rtol=RTOL, atol=0)
+    assert (rq > 0).sum() >= 2 * B
+    eng.close()

@@ -315,3 +315,53 @@ def test_oracle_relperm_against_the_reference_class():
     assert U.ulp_diff(krog, g["krog"]) <= 2 and U.ulp_diff(krgo, g["krgo"]) <= 2
     assert np.array_equal(krog == 0, g["krog"] == 0) and np.array_equal(krgo == np.float32(0.9), g["krgo"] == np.float32(0.9))
     assert (g["krog"] == 0).sum() > 10 and (g["krgo"] == np.float32(0.9)).sum() > 3
+
+
+def _wells_ref_case(g, name, blocking):
+    wl = [O.Well(i=int(r[0]), j=int(r[1]), k=int(r[2]), value=float(r[3]), shutin_days=(float(r[4]), float(r[5]))) for r in g[f"{name}_wells"]]
+    D, H, W = int(g[f"{name}_D"]), int(g[f"{name}_H"]), int(g[f"{name}_W"])
+    return O.OracleConfig(D=D, H=H, W=W, wells=wl, use_blocking_factor=blocking, n_intervals=8), wl
+
+
+@pytest.mark.parametrize("name,fluid,blocking", [("dg", "DG", False), ("dgblk", "DG", True), ("gc", "GC", False)])
+def test_oracle_wells_equal_the_reference_class_bit_for_bit(name, fluid, blocking):
+    """PIN: tests/golden/reference_wells.npz holds the dense rate / BHP fields returned by the reference's OWN
+    WellRatesPressure.compute_rates_and_bhp (non-iterative control, phase rates, the dry-gas blocking-factor integral,
+    the condensate split) and the masks of its OWN WellDataProcessor.scatter_y / conn_shutins_idx, executed by
+    tests/golden/make_reference_wells_golden.py through the torch-backed TF stand-in.  The oracle's sparse restatement
+    must equal them bit for bit at the connection cells (a shut-in window and a BHP-limited target included); off the
+    connections the reference's fields are zero."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells.npz"))
+    cfg, wl = _wells_ref_case(g, name, blocking)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.GC_PROPS if fluid == "GC" else O.DG_PROPS, order=1, lam=0.001)
+    B = int(g[f"{name}_B"])
+    flat = O.well_flat_index(wl, cfg.D, cfg.H, cfg.W).astype(np.int64)
+    at = lambda a: np.asarray(a).reshape(B, -1)[:, flat]
+    pc, kc = torch.as_tensor(at(g[f"{name}_p"])), torch.as_tensor(at(g[f"{name}_kx"]))
+    t_days = g[f"{name}_t_days"]
+    eq = lambda a, b: np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+    if fluid == "GC":
+        q4, pwf = O.wells_gc(pc, torch.as_tensor(at(g[f"{name}_sg"])), kc, t_days, tab, cfg, torch.float32)
+        for c in range(4):
+            assert eq(q4[c].numpy(), at(g[f"{name}_q4"][c])), c
+            dense = g[f"{name}_q4"][c].reshape(B, -1).copy()
+            dense[:, flat] = 0
+            assert not dense.any()
+    else:
+        q, pwf = O.wells_dg(pc, kc, t_days, tab, cfg, torch.float32)
+        assert eq(q.numpy(), at(g[f"{name}_q"]))
+        dense = g[f"{name}_q"].reshape(B, -1).copy()
+        dense[:, flat] = 0
+        assert not dense.any()
+        assert (at(g[f"{name}_q"]) == 0).any() and (at(g[f"{name}_q"]) > 0).any()       # the shut-in window is exercised
+    assert eq(pwf.numpy(), at(g[f"{name}_pwf"]))
+    # integer work: scatter positions ([k, j, i] rows, welldata_processor.py:26-40) and the shut-in identity
+    wid = g[f"{name}_well_id"].reshape(-1)
+    assert sorted(np.nonzero(wid)[0].tolist()) == sorted(flat.tolist()) and np.all(wid[flat] == 1.0)
+    assert np.array_equal(g[f"{name}_q0"].reshape(-1)[flat], np.asarray([w.value for w in wl], np.float32))
+    shut = g[f"{name}_shut"].reshape(B, -1)[:, flat]
+    assert np.array_equal(shut, O.shutin_open_mask(t_days, wl))
+    off = g[f"{name}_shut"].reshape(B, -1).copy()
+    off[:, flat] = 0
+    assert not off.any()                                          # 0 at every non-well cell (welldata_processor.py:382)
