@@ -4,13 +4,40 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 legs may import this module.  The product path (the CUDA library behind ``include/srm_physics.h``)
 never routes through it.
 
-**PARITY UNPINNED.**  The reference (molokwuvictor/3d-physics-based-ai-surrogate-reservoir-model) is
-pure Python/TensorFlow; TensorFlow is not installable in the build container, the shipped reference
-is not import-clean, and it ships no test with an assertion, no golden vector and no known-answer
-fixture for this path.  This file is therefore a *restatement* of the
-reference arithmetic, op by op, in torch-CPU (fp32 for parity, fp64 as the exact-arithmetic twin),
-each function citing the reference lines it follows.  Its own outputs, pinned under ``tests/golden``,
-are the goldens.
+**PARITY PINNED AGAINST THE REFERENCE'S OWN CODE (forward values; TensorFlow's kernels stood in for).**  The
+reference (molokwuvictor/3d-physics-based-ai-surrogate-reservoir-model) is pure Python/TensorFlow; TensorFlow is not
+installable in the build container, the shipped reference is not import-clean, and it ships no test with an
+assertion, no golden vector and no known-answer fixture for this path.  This file is a
+*restatement* of the reference arithmetic, op by op, in torch-CPU / numpy (fp32 for parity, fp64 as the
+exact-arithmetic twin), each function citing the reference lines it follows.  It is pinned by running the reference's
+OWN source in the build container: ``tests/golden/make_reference_*_golden.py`` cut the functions / classes out of
+``/root/reference`` by AST (nothing is copied into this repository) and execute them on seeded inputs with
+``tests/golden/tf_torch_shim.py`` -- a torch-backed stand-in for the ~60 TensorFlow ops they use -- in place of
+TensorFlow.  The committed goldens (``tests/golden/reference_*.npz``) hold the outputs, and ``tests/test_oracle*.py``
+require this file to reproduce them:
+
+  =====================================================  ===========================================  ==============
+  reference code executed                                 what it pins                                 agreement
+  =====================================================  ===========================================  ==============
+  physics_error_gas_2D (physics_loss.py:9-224)            dry-gas dom, ibc, mbc (2-D grids)            bit for bit
+  physics_error_gas_oil_2D (physics_loss.py:230-714)      gas-condensate dom, ibc, mbc, cmbc           bit for bit
+  PolyharmonicSplineInterpolationLayer (polyhm_splines)   order-1 values of the 7 properties           bit for bit *
+  PVTLayer.call (PVT_Layer_Subclassed.py:146-216)         clamp, layout, derivative w.r.t. clamped p   1e-5 / 1e-4 **
+  RelativePermeability.compute_krog_krgo                  Corey values and end-point rules             <= 2 ulp ***
+  WellRatesPressure.compute_rates_and_bhp (+ helpers)     DG, DG + blocking integral, GC rates, BHP    bit for bit
+  WellDataProcessor.scatter_y / conn_shutins_idx          scatter positions, shut-in identity          exact
+  DataSummary.nonormalize / normalize_diff                linear rows / log permeability row           exact / 2 ulp
+  BatchGenerator._maybe_flatten (training.py)             sample order of the flattened batch axis     exact
+  =====================================================  ===========================================  ==============
+  *   with (w, v) as data and the stand-in's matmul accumulating the inner index sequentially (assumption below);
+      the layer's own in-call solve (LAPACK through torch instead of numpy, cond ~ 3.6e6) moves values by <= 5e-6.
+  **  torch autograd stands in for TF's tape: same formula chain, framework-specific accumulation order.
+  *** tf.pow with the integer Corey exponents is pinned as a product here; libm's pow differs by <= 2 ulp.
+
+What the stand-in cannot pin (it implements TF's op SEMANTICS, not Eigen's kernels): the accumulation order inside
+tf.matmul / tf.reduce_sum and inside TF's gradient kernels, and ulp-level differences of pow / exp / log.  Those are
+the assumptions listed next.  Gradients are validated against fp64 central finite differences of this file's own loss
+(tests/test_oracle.py, tests/test_oracle_gc.py); the z faces are an extension (below) with nothing to pin against.
 
 What is pinned here that TensorFlow leaves unspecified (so that "fp32, 1e-5" is well defined):
   * no FMA contraction anywhere: every ``*`` and ``+`` of the reference is a separately rounded op;

@@ -412,3 +412,17 @@ def greater_equal(a, b):
 
 
 torch.Tensor.get_shape = lambda self: tuple(self.shape)     # only read to fill tf.while_loop's shape_invariants
+
+
+# ---- additions for DataSummary.nonormalize / normalize_diff (data_processing/data_processing_utils.py) -------------
+def not_equal(a, b):
+    return _t(a) != _t(b)
+
+
+def broadcast_to(x, shape_):
+    return _t(x).expand(*[int(s) for s in (shape_.tolist() if isinstance(shape_, torch.Tensor) else shape_)])
+
+
+math.is_nan = lambda x: torch.isnan(_t(x))
+math.is_inf = lambda x: torch.isinf(_t(x))
+DType = object

@@ -365,3 +365,18 @@ def test_oracle_wells_equal_the_reference_class_bit_for_bit(name, fluid, blockin
     off = g[f"{name}_shut"].reshape(B, -1).copy()
     off[:, flat] = 0
     assert not off.any()                                          # 0 at every non-well cell (welldata_processor.py:382)
+
+
+def test_oracle_denormalisation_equals_the_reference_data_summary():
+    """PIN: DataSummary.nonormalize / normalize_diff (data_processing_utils.py:1065-1183) cut out of the reference and
+    executed (tests/golden/make_reference_norm_golden.py): linear rows bit for bit; the logarithmic permeability row to
+    2 ulp (exp/log of torch vs numpy)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_norm.npz"))
+    st, x = g["stats"], g["x"]
+    for ch in range(4):
+        got = O.denorm_linear(x[..., ch], st[ch, 0], st[ch, 1])
+        assert np.array_equal(got.view(np.uint32), g["denorm"][..., ch].view(np.uint32)), ch
+    k = O.denorm_log(x[..., 4], st[4, 0], st[4, 1])
+    assert U.ulp_diff(k, g["denorm"][..., 4]) <= 2
+    assert np.array_equal(O.denorm_linear(x[..., 3:4], st[3, 0], st[3, 1]).view(np.uint32), g["t_only"].view(np.uint32))
+    assert np.array_equal(O.norm_diff_linear(g["dt"], st[3, 0], st[3, 1]).view(np.uint32), g["dt_norm"].view(np.uint32))
