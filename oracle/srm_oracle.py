@@ -27,6 +27,7 @@ require this file to reproduce them:
   WellRatesPressure.compute_rates_and_bhp (+ helpers)     DG, DG + blocking integral, GC rates, BHP    bit for bit
   WellDataProcessor.scatter_y / conn_shutins_idx          scatter positions, shut-in identity          exact
   DataSummary.nonormalize / normalize_diff                linear rows / log permeability row           exact / 2 ulp
+  HardLayer (Hard_Layer_Subclassed.py:21-260)             layer output / cotangents                    bit for bit / 1e-6
   BatchGenerator._maybe_flatten (training.py)             sample order of the flattened batch axis     exact
   =====================================================  ===========================================  ==============
   *   with (w, v) as data and the stand-in's matmul accumulating the inner index sequentially (assumption below);

@@ -1,0 +1,50 @@
+"""Golden vectors for HardLayer made by the REFERENCE'S OWN class (Hard_Layer_Subclassed.py:21-260, cut out by AST) executed
+through the torch-backed TensorFlow stand-in: the example's configuration (no rbf, no rectifier, identity activations,
+identity nonormalize_func, norm_limits [-1, 1], per-cell trainable kernel_exponent).  Values and the cotangents torch
+autograd delivers for the network output and for kernel_exponent (time inputs > t_lo: tf.pow's and torch.pow's
+gradients coincide there).   Output: tests/golden/reference_hardlayer.npz
+"""
+import ast
+import os
+import sys
+import textwrap
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import tf_torch_shim as tf          # noqa: E402
+
+REF = "/root/reference/Hard_Layer_Subclassed.py"
+
+
+def main():
+    src = open(REF).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "HardLayer")
+    ns = {"tf": tf, "np": np, "get_configuration": lambda *a, **k: {"dew_point": 4048.49},
+          "DEFAULT_GENERAL_CONFIG": {"fluid_type": "DG"}, "DEFAULT_RESERVOIR_CONFIG": {"initialization": {"Pi": 5000.0, "Pa": 14.7}}}
+    exec(textwrap.dedent(ast.get_source_segment(src, node)), ns)
+    rng = np.random.default_rng(5600)
+    B, D, H, W = 5, 2, 4, 6
+    layer = ns["HardLayer"](norm_limits=[-1, 1], init_value=5000.0,
+                            kernel_exponent_config={"initial_value": (0.5,), "trainable": True, "min_value": 0.1, "max_value": 1.0})
+    layer.build([(B, D, H, W, 1), (B, D, H, W, 1)])
+    expo = (0.1 + 0.85 * rng.random((D, H, W, 1))).astype(np.float32)
+    layer.kernel_exponent = torch.as_tensor(expo).requires_grad_(True)
+    tn = np.asarray([-1.0, -0.6, 0.0, 0.45, 1.0], np.float32)
+    time = torch.as_tensor(np.broadcast_to(tn.reshape(B, 1, 1, 1, 1), (B, D, H, W, 1)).copy())
+    prop = torch.zeros(B, D, H, W, 1)
+    y = torch.as_tensor((600.0 * rng.random((B, D, H, W, 1))).astype(np.float32)).requires_grad_(True)
+    out = layer([[time, prop], y])
+    wgt = torch.as_tensor(rng.standard_normal((B, D, H, W, 1)).astype(np.float32))
+    # cotangents over the samples with alpha_t > 0 only (at alpha_t = 0 torch.pow's exponent gradient is nan, tf's is 0)
+    sel = torch.as_tensor((tn > -1.0).astype(np.float32)).view(B, 1, 1, 1, 1)
+    gy, ge = torch.autograd.grad((out * wgt * sel).sum(), [y, layer.kernel_exponent])
+    np.savez_compressed(os.path.join(HERE, "reference_hardlayer.npz"), tn=tn, expo=expo[..., 0], y=y.detach().numpy()[..., 0],
+                        out=out.detach().numpy()[..., 0], wgt=(wgt * sel).numpy()[..., 0], gy=gy.numpy()[..., 0], gexpo=ge.numpy()[..., 0])
+    print("wrote reference_hardlayer.npz", out.shape)
+
+
+if __name__ == "__main__":
+    main()

@@ -426,3 +426,16 @@ def broadcast_to(x, shape_):
 math.is_nan = lambda x: torch.isnan(_t(x))
 math.is_inf = lambda x: torch.isinf(_t(x))
 DType = object
+
+
+# ---- additions for Hard_Layer_Subclassed.py ------------------------------------------------------------------------
+def _add_weight(self, shape=None, initializer=None, constraint=None, trainable=True, name=None, **k):
+    v = initializer(shape) if callable(initializer) else torch.full(tuple(int(s) for s in shape), float(initializer))
+    return v.clone().requires_grad_(_b.bool(trainable))
+
+
+_Layer.add_weight = _add_weight
+constant_initializer = lambda value=0.0: (lambda shape: torch.full(tuple(int(s) for s in shape), float(value[0] if isinstance(value, (tuple, list)) else value)))
+keras.constraints = types.SimpleNamespace(MinMaxNorm=lambda **k: None, UnitNorm=lambda **k: None)
+keras.initializers.get = lambda name: None
+nn = types.SimpleNamespace(sigmoid=torch.sigmoid, relu=torch.relu, tanh=torch.tanh)

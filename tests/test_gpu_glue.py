@@ -165,3 +165,21 @@ def test_physics_loss_with_fused_glue_equals_unfused():
     for a, b in zip(res[0][1], res[1][1]):
         assert a.shape == b.shape and np.all(np.isfinite(a)) and np.abs(a).max() > 0
     eng.close()
+
+
+def test_glue_against_the_reference_hard_layer_class():
+    """srm_glue_forward / srm_glue_backward against values and cotangents produced by the reference's OWN HardLayer class
+    (tests/golden/make_reference_hardlayer_golden.py): values 1e-6 relative (2^(e log2 a) vs libm pow), cotangents 1e-5."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_hardlayer.npz"))
+    B, D, H, W = g["y"].shape
+    ocfg, otab, spec, ptab, _ = U.make_case(W=W, H=H, D=D, T=1, K=1, seed=1)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    dev = eng.device
+    c = lambda k: torch.as_tensor(g[k]).to(dev).contiguous()
+    p0, p1, _, _ = eng.glue_forward(c("y"), c("y"), c("tn"), c("tn"), c("expo"), None, None, 5000.0)
+    assert np.allclose(p0.cpu().numpy(), g["out"], rtol=1e-6, atol=0) and torch.equal(p0, p1)
+    zero = torch.zeros_like(c("wgt"))
+    gy0, gy1, gexpo, _, _ = eng.glue_backward(c("y"), c("y"), c("tn"), c("tn"), c("wgt"), zero, c("expo"), None, None, 5000.0)
+    assert U.rel_to_max(gy0.cpu().numpy(), g["gy"]) < 1e-5 and U.rel_to_max(gexpo.cpu().numpy(), g["gexpo"]) < 1e-5
+    assert not gy1.any()
+    eng.close()

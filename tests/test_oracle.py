@@ -380,3 +380,17 @@ def test_oracle_denormalisation_equals_the_reference_data_summary():
     assert U.ulp_diff(k, g["denorm"][..., 4]) <= 2
     assert np.array_equal(O.denorm_linear(x[..., 3:4], st[3, 0], st[3, 1]).view(np.uint32), g["t_only"].view(np.uint32))
     assert np.array_equal(O.norm_diff_linear(g["dt"], st[3, 0], st[3, 1]).view(np.uint32), g["dt_norm"].view(np.uint32))
+
+
+def test_oracle_hard_layer_equals_the_reference_class():
+    """PIN: HardLayer (Hard_Layer_Subclassed.py:21-260) cut out of the reference and executed
+    (tests/golden/make_reference_hardlayer_golden.py): values bit for bit (same libm pow), cotangents of the network
+    output and of kernel_exponent to 1e-6 of their max."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_hardlayer.npz"))
+    y = torch.as_tensor(g["y"]).requires_grad_(True)
+    e = torch.as_tensor(g["expo"]).requires_grad_(True)
+    out = O.hard_layer_t(y, torch.as_tensor(g["tn"]), e, 5000.0)
+    assert np.array_equal(out.detach().numpy().view(np.uint32), g["out"].view(np.uint32))
+    assert np.all(g["out"][0] == np.float32(5000.0))                      # alpha_t = 0 enforces the initial condition
+    gy, ge = torch.autograd.grad((out * torch.as_tensor(g["wgt"])).sum(), [y, e])
+    assert U.rel_to_max(gy.numpy(), g["gy"]) < 1e-6 and U.rel_to_max(ge.numpy(), g["gexpo"]) < 1e-6
