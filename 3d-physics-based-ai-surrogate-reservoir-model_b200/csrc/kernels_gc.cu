@@ -507,7 +507,7 @@ __global__ void k_finalize_fwd_gc(const __grid_constant__ SrmDev P, int32_t B, d
       terms_out[t] = (float)sse[t];
       double cnt = 0.0;
       if (t == SRM_TERM_DOM || t == SRM_TERM_IBC || t == SRM_TERM_CMBC) cnt = n;
-      if (t == SRM_TERM_MBC) cnt = (double)B;
+      if (t == SRM_TERM_MBC) cnt = n;      // the reference counts mbc with the ic field's shape (physics_loss.py:830)
       terms_out[SRM_N_TERMS + t] = (float)cnt;
     }
   }

@@ -27,6 +27,7 @@ require this file to reproduce them:
   WellRatesPressure.compute_rates_and_bhp (+ helpers)     DG, DG + blocking integral, GC rates, BHP    bit for bit
   WellDataProcessor.scatter_y / conn_shutins_idx          scatter positions, shut-in identity          exact
   DataSummary.nonormalize / normalize_diff                linear rows / log permeability row           exact / 2 ulp
+  pinn_batch_sse_grad (physics_loss.py:742-870)           SSE per term, weights, counts, reported MSE  1e-5 / exact
   HardLayer (Hard_Layer_Subclassed.py:21-260)             layer output / cotangents                    bit for bit / 1e-6
   BatchGenerator._maybe_flatten (training.py)             sample order of the flattened batch axis     exact
   =====================================================  ===========================================  ==============
@@ -729,10 +730,10 @@ def dg_loss_terms(res) -> torch.Tensor:
 
 
 def dg_counts(cfg: OracleConfig, B: int) -> np.ndarray:
-    """error counts (physics_loss.py:825-832): dom/ibc/ic-like terms count every cell, mbc too
-    (legacy counts mbc with the ic shape); we report elements actually squared per term."""
+    """error counts (physics_loss.py:825-832): dom, ibc and the truncation term count every cell; mbc is counted with
+    the ic FIELD's shape (physics_loss.py:830: reduce_sum(ones_like(ic_pinn_se))), i.e. every cell too."""
     n = B * cfg.D * cfg.H * cfg.W
-    return np.array([n, n, B, n, 0, 0, 0, 0], dtype=np.float64)
+    return np.array([n, n, n, n, 0, 0, 0, 0], dtype=np.float64)
 
 
 def dg_forward_backward(cfg, tab, kx, p0, p1, dt1, dt2, t_days, sample_real, weights, dtype=torch.float32):
@@ -994,7 +995,7 @@ def gc_loss_terms(res) -> torch.Tensor:
 
 def gc_counts(cfg: OracleConfig, B: int) -> np.ndarray:
     n = B * cfg.D * cfg.H * cfg.W
-    return np.array([n, n, B, 0, 0, 0, 0, n], dtype=np.float64)
+    return np.array([n, n, n, 0, 0, 0, 0, n], dtype=np.float64)       # mbc counted with the ic field's shape (:830)
 
 
 def gc_forward_backward(cfg, tab, kx, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t_days, sample_real, weights,

@@ -268,7 +268,12 @@ class GradientTape:
     def watch(self, x):
         x.requires_grad_(True)
 
-    def gradient(self, y, x):
+    def gradient(self, y, x, unconnected_gradients=None):
+        if isinstance(x, (list, tuple)):
+            if len(x) == 0:
+                return []
+            g = torch.autograd.grad(y, list(x), grad_outputs=torch.ones_like(y), retain_graph=True, allow_unused=True)
+            return [torch.zeros_like(v) if gi is None else gi for gi, v in zip(g, x)]
         return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True)[0]
 
 
@@ -439,3 +444,4 @@ constant_initializer = lambda value=0.0: (lambda shape: torch.full(tuple(int(s) 
 keras.constraints = types.SimpleNamespace(MinMaxNorm=lambda **k: None, UnitNorm=lambda **k: None)
 keras.initializers.get = lambda name: None
 nn = types.SimpleNamespace(sigmoid=torch.sigmoid, relu=torch.relu, tanh=torch.tanh)
+math.reduce_sum = reduce_sum

@@ -93,7 +93,7 @@ def test_gc_forward_backward_vs_oracle(kw, pvt_lut):
         assert np.allclose(c["q4w"], o["qw4"], rtol=RTOL, atol=0) and np.allclose(c["pwfw"], o["pwfw"], rtol=RTOL, atol=0)
     assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
     B, N = d["p0"].shape[0], int(np.prod(d["p0"].shape[1:]))
-    assert c["counts"].tolist() == [B * N, B * N, B, 0, 0, 0, 0, B * N]
+    assert c["counts"].tolist() == [B * N, B * N, B * N, 0, 0, 0, 0, B * N]      # mbc counted with the ic shape, physics_loss.py:830
     for k in ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1"):
         assert h3_close(c[k], o[k], noise=o["noise"][k]), (k, U.rel_to_max(c[k], o[k]))
         assert U.rel_to_max(c[k], o[k]) < (1e-3 if kw.get("small_dp") else 3e-5), k

@@ -92,7 +92,7 @@ def test_forward_backward_vs_golden(name, pvt_lut):
     terms = fw["terms"].cpu().numpy()
     assert np.allclose(terms[0], g["o_terms"], rtol=RTOL, atol=0)
     B, N = g["p0"].shape[0], int(np.prod(g["p0"].shape[1:]))
-    assert terms[1].tolist() == [B * N, B * N, B, B * N, 0, 0, 0, 0]
+    assert terms[1].tolist() == [B * N, B * N, B * N, B * N, 0, 0, 0, 0]        # mbc counted with the ic shape (physics_loss.py:830)
     assert h3_close(gp0.cpu().numpy(), g["o_gp0"])
     assert h3_close(gp1.cpu().numpy(), g["o_gp1"])
     assert h3_close(gdt1.cpu().numpy(), g["o_gdt1"])
@@ -406,4 +406,25 @@ def test_cuda_wells_against_the_reference_class(name, blocking):
     assert np.array_equal(q == 0, rq == 0) and np.array_equal(pwf == 0, rp == 0)         # cells, shut-ins, zeros elsewhere
     assert np.allclose(q, rq, rtol=RTOL, atol=0) and np.allclose(pwf, rp, rtol=RTOL, atol=0)
     assert (rq > 0).sum() >= 2 * B
+    eng.close()
+
+
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+def test_cuda_terms_and_counts_against_the_reference_pinn_batch_sse_grad(pvt_lut):
+    """srm_forward's SSE terms and error counts against the reference's OWN pinn_batch_sse_grad (executed with its own
+    physics_error_gas_2D behind it, tests/golden/make_reference_loss_golden.py): counts exact (mbc counted with the ic
+    field's shape), SSE 1e-5 (fp64 accumulation here, fp32 reduce_sum there)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_loss.npz"))
+    W, H, B = int(g["W"]), int(g["H"]), int(g["B"])
+    ocfg, otab, spec, ptab, _ = U.make_case(W=W, H=H, D=1, T=1, K=1, seed=1)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut)
+    dev = eng.device
+    tt = lambda k, dt=torch.float32: torch.as_tensor(g[k]).to(dev, dt).contiguous()
+    fw = eng.forward(tt("kx"), tt("sample_real", torch.int32), tt("p0"), tt("p1"), tt("dt1"), tt("dt2"), tt("t_days"))
+    terms = fw["terms"].cpu().numpy()
+    nwt, wsse, cnt = g["nwt"], g["wsse"], g["count"]
+    T = srm._lib.TERM_NAMES
+    for name, i, w in (("dom", 1, nwt[0]), ("ibc", 4, nwt[3]), ("mbc", 6, nwt[5])):
+        assert np.isclose(terms[0, T.index(name)], wsse[i] / w, rtol=RTOL), name
+        assert terms[1, T.index(name)] == cnt[i] == B * H * W, name
     eng.close()

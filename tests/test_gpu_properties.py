@@ -28,7 +28,7 @@ def test_terms_are_the_sums_of_squares_of_the_fields(cfg2):
     dom = fw["dom"].double()
     assert abs(float((dom * dom).sum()) / float(fw["terms"][0, 0]) - 1.0) < 1e-5
     B, N = d["p0"].shape[0], d["p0"][0].numel()
-    assert fw["terms"][1].tolist() == [B * N, B * N, B, B * N, 0, 0, 0, 0]
+    assert fw["terms"][1].tolist() == [B * N, B * N, B * N, B * N, 0, 0, 0, 0]
     assert torch.isfinite(fw["dom"]).all()
 
 

@@ -394,3 +394,33 @@ def test_oracle_hard_layer_equals_the_reference_class():
     assert np.all(g["out"][0] == np.float32(5000.0))                      # alpha_t = 0 enforces the initial condition
     gy, ge = torch.autograd.grad((out * torch.as_tensor(g["wgt"])).sum(), [y, e])
     assert U.rel_to_max(gy.numpy(), g["gy"]) < 1e-6 and U.rel_to_max(ge.numpy(), g["gexpo"]) < 1e-6
+
+
+def _loss_golden_terms(g):
+    """reference order [batch, dom, dbc, nbc, ibc, ic, mbc, cmbc] -> (dom, ibc, mbc) unweighted SSE and their counts"""
+    nwt, wsse, cnt = g["nwt"], g["wsse"], g["count"]
+    return dict(dom=wsse[1] / nwt[0], ibc=wsse[4] / nwt[3], mbc=wsse[6] / nwt[5]), dict(dom=cnt[1], ibc=cnt[4], mbc=cnt[6])
+
+
+def test_oracle_loss_assembly_equals_the_reference_pinn_batch_sse_grad():
+    """PIN: pinn_batch_sse_grad (physics_loss.py:742-870) executed with the reference's own physics_error_gas_2D behind it
+    (tests/golden/make_reference_loss_golden.py): SSE per term, weighting by nwt, error counts (mbc counted with the ic
+    field's shape, :830), reported MSE = weighted SSE / count, batch loss = sum of the weighted terms."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_loss.npz"))
+    W, H, B = int(g["W"]), int(g["H"]), int(g["B"])
+    cfg = O.OracleConfig(D=1, H=H, W=W, wells=O.default_wells(W, H, 1))
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.DG_PROPS, order=1, lam=0.001)
+    tt = lambda k: torch.as_tensor(g[k])
+    res = O.dg_residual(cfg, tab, tt("kx"), tt("p0"), tt("p1"), tt("dt1"), tt("dt2"), g["t_days"], g["sample_real"])
+    terms = O.dg_loss_terms(res).numpy()
+    counts = O.dg_counts(cfg, B)
+    sse, cnt = _loss_golden_terms(g)
+    for name in ("dom", "ibc", "mbc"):
+        k = O.TERM_NAMES.index(name)
+        assert np.isclose(terms[k], sse[name], rtol=1e-5), name
+        assert counts[k] == cnt[name] == B * H * W, name
+    # reported MSE and the batch loss, as the reference forms them
+    nwt, wsse, wmse = g["nwt"], g["wsse"], g["wmse"]
+    assert np.allclose(wmse[1:8], wsse[1:8] / np.maximum(g["count"][1:8], 1.0), rtol=1e-6)
+    assert np.isclose(wsse[0], wsse[1:8].sum(), rtol=1e-6)
