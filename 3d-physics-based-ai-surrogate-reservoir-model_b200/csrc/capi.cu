@@ -164,9 +164,9 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     const bool whole = !(cfg->lut_p_lo < cfg->lut_p_hi);
     const float lo = whole ? cfg->p_min : std::max(cfg->lut_p_lo, cfg->p_min);
     const float hi = whole ? cfg->p_max : std::min(cfg->lut_p_hi, cfg->p_max);
+    h->lut_full = (lo <= cfg->p_min && hi >= cfg->p_max) ? 1 : 0;
     int rc = cfg->fluid_type == SRM_FLUID_GC ? srm_build_pvt_lut_gc(h, lo, hi) : srm_build_pvt_lut(h, lo, hi);
     if (rc) { srm_destroy(h); return rc; }
-    h->lut_full = (lo <= cfg->p_min && hi >= cfg->p_max) ? 1 : 0;
   }
   *out = h;
   return SRM_OK;

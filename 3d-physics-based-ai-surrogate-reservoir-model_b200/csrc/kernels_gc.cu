@@ -16,6 +16,7 @@
 // cell; the residual kernels are not fused yet (the dry-gas path's kernels_ref2.cu shows the next step).
 #include <math_constants.h>
 #include <cstring>
+#include <cstdlib>
 #include "ref_fused.cuh"
 
 namespace {
@@ -130,7 +131,8 @@ __device__ __forceinline__ GcPack1 gc_pack1(const SrmDev& P, float x1) {
 // exact tabulation (SrmConfig.pvt_lut, see kernels_ref.cu): entry e = the packs of the fp32 pressure with bit
 // pattern lut_lo_bits + e; 48 + 64 bytes per representable pressure.
 __global__ void __launch_bounds__(kThreads) k_lut_build_gc(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
-                                                           float4* __restrict__ t1) {
+                                                           float4* __restrict__ t1, float4* __restrict__ f0, float4* __restrict__ f1,
+                                                           float2* __restrict__ fv) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.lut_n) return;
   const float x = __uint_as_float(P.lut_lo_bits + e);
@@ -140,6 +142,13 @@ __global__ void __launch_bounds__(kThreads) k_lut_build_gc(const __grid_constant
   for (int i = 0; i < 3; ++i) t0[(size_t)e * 3 + i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
 #pragma unroll
   for (int i = 0; i < 4; ++i) t1[(size_t)e * 4 + i] = make_float4(b.v[4 * i], b.v[4 * i + 1], b.v[4 * i + 2], b.v[4 * i + 3]);
+  if (f0) {     // the fused forward's 32-byte views (gc_fused.cuh): values and first derivatives of level n, products of level n+1
+#pragma unroll
+    for (int i = 0; i < 2; ++i) f0[(size_t)e * 2 + i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+    f1[(size_t)e * 2] = make_float4(b.v[0], b.v[2], b.v[1], b.v[3]);            // component order gg, go, oo, og
+    f1[(size_t)e * 2 + 1] = make_float4(b.v[4], b.v[5], b.v[6], b.v[7]);
+    fv[e] = make_float2(b.v[0] + b.v[3], b.v[2] + b.v[1]);                      // the adjoint's neighbour-visible sums
+  }
 }
 
 template <bool SAVE, bool LUT>
@@ -343,7 +352,7 @@ struct GcFwd {
   const float* F; const float* W7;
   float* divqw; float* dom; float* dom_out;
   double* sse; double* s_mg; double* s_qg; double* s_mo; double* s_qo;
-  int32_t B, R;
+  int32_t B, R, tiles_x;
 };
 
 __global__ void __launch_bounds__(kThreads, 3) k_resid_fwd_gc(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
@@ -522,7 +531,7 @@ struct GcAdj {
   const float* F; const float* W7; const float* divqw; const float* dom; const float* mbc;
   float* gp0; float* gp1; float* gsg0; float* gsg1; float* gso0; float* gso1;
   double* gdt1_acc; double* gdt2_acc;
-  int32_t B, R;
+  int32_t B, R, tiles_x;
 };
 
 // per face, seen from cell c with neighbour n: Lc / Ln = sum over the four components of kr_sel * <M>_f as the
@@ -745,6 +754,8 @@ __global__ void __launch_bounds__(128) k_ibc_adj_gc(const __grid_constant__ SrmD
   atomicAdd(&A.gsg1[base + c], s * (self_s + dqs));
 }
 
+#include "gc_fused.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -765,14 +776,21 @@ int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi) {
   if (!(lo > 0.f) || !(hi >= lo)) { srm_set_error("srm_create: pvt_lut range [%g, %g] must be positive and ascending", lo, hi); return SRM_ERR_INVALID; }
   const uint64_t n = (uint64_t)hi_bits - lo_bits + 1;
   if (n > (1ull << 31)) { srm_set_error("srm_create: pvt_lut range too wide"); return SRM_ERR_INVALID; }
-  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * 7 * sizeof(float4));       // 3 + 4 float4 per pressure
-  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut (GC) needs %.1f MB of device memory: %s", n * 112e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
+  // fused pair (gc_fused.cuh): needs the table over the whole clamp range; SRM_NO_GC2 keeps the staged pipeline
+  h->gc_fused = (h->lut_full && !getenv("SRM_NO_GC2")) ? 1 : 0;
+  const uint64_t per = h->gc_fused ? 11 : 7;                                    // 3 + 4 float4 per pressure (+ 2 + 2 forward views)
+  cudaError_t e = cudaMalloc((void**)&h->d_lut, n * per * sizeof(float4) + (h->gc_fused ? n * sizeof(float2) : 0));
+  if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut (GC) needs %.1f MB of device memory: %s", n * per * 16e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
   P.lut_lo_bits = lo_bits;
   P.lut_n = (uint32_t)n;
   P.lut0 = h->d_lut;
   P.lut1 = h->d_lut + 3 * n;
-  P.lutf0 = nullptr; P.lutf1 = nullptr;
-  k_lut_build_gc<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + 3 * n);
+  float4* f0 = h->gc_fused ? h->d_lut + 7 * n : nullptr;
+  float4* f1 = h->gc_fused ? h->d_lut + 9 * n : nullptr;
+  P.lutf0 = reinterpret_cast<const float2*>(f0); P.lutf1 = reinterpret_cast<const float2*>(f1);
+  float2* fv = h->gc_fused ? reinterpret_cast<float2*>(h->d_lut + 11 * n) : nullptr;
+  P.gcv = fv;
+  k_lut_build_gc<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + 3 * n, f0, f1, fv);
   SRM_CUDA_CHECK(cudaGetLastError());
   SRM_CUDA_CHECK(cudaDeviceSynchronize());
   return SRM_OK;
@@ -787,7 +805,9 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse and the four per-sample sums
   const unsigned sblocks = (unsigned)((total + kThreads - 1) / kThreads);
   const bool lut = P.lut_n > 0;
-  if (save) { if (lut) k_stage_gc<true, true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
+  const bool fused = h->gc_fused != 0;
+  if (fused) {}
+  else if (save) { if (lut) k_stage_gc<true, true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
               else k_stage_gc<true, false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc); }
   else      { if (lut) k_stage_gc<false, true><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc);
               else k_stage_gc<false, false><<<sblocks, kThreads, 0, s>>>(P, total, p0, p1, sg1, ws.gc); }
@@ -812,8 +832,14 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
     SRM_CUDA_CHECK(cudaGetLastError());
   }
   A.faces = ws.faces;
-  const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
-  k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
+  if (fused) {
+    A.tiles_x = (P.W + G2X - 1) / G2X;
+    const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
+    k_fwd_gc2<<<grid, kThreads, 0, s>>>(P, A);
+  } else {
+    const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
+    k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
+  }
   SRM_CUDA_CHECK(cudaGetLastError());
   k_finalize_fwd_gc<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.gdt1_acc, ws.gdt2_acc, ws.mbc, terms_out);
   SRM_CUDA_CHECK(cudaGetLastError());
@@ -835,12 +861,20 @@ int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, co
   A.gp0 = gp0; A.gp1 = gp1; A.gsg0 = gsg0; A.gsg1 = gsg1; A.gso0 = gso0; A.gso1 = gso1;
   A.gdt1_acc = ws.gdt1_acc; A.gdt2_acc = ws.gdt2_acc; A.B = B; A.R = R;
   A.faces = ws.faces;                                        // built by the forward (state in the workspace)
-  const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
-  k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);
+  const bool fused = h->gc_fused != 0;
+  if (fused) {
+    A.tiles_x = (P.W + G2X - 1) / G2X;
+    const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
+    k_adj_gc2<<<grid, kThreads, 0, s>>>(P, A);
+  } else {
+    const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
+    k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);
+  }
   SRM_CUDA_CHECK(cudaGetLastError());
   const int64_t n = (int64_t)B * P.n_wells;
   if (n > 0) {
-    k_ibc_adj_gc<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
+    if (fused) k_ibc_adj_gc2<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
+    else k_ibc_adj_gc<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(P, A);
     SRM_CUDA_CHECK(cudaGetLastError());
   }
   k_finalize_adj<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.gdt2_acc, gdt1, gdt2);

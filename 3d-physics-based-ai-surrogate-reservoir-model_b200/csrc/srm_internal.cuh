@@ -53,6 +53,7 @@ struct SrmDev {
   const float4* lut1;    // {invBg, invBg*invug, d invBg/dp, d(invBg*invug)/dp}
   const float2* lutf0;   // {invBg, cp}             -- the forward's 8-byte views: half the L2 footprint
   const float2* lutf1;   // {invBg, invBg*invug}
+  const float2* gcv;     // gas condensate, fused pair: {Mgg + Mog, Mgo + Moo} at level n+1 (the adjoint's neighbour-visible sums)
   uint32_t lut_lo_bits, lut_n;
   int32_t cp_safe;       // every tabulated |cp| lies in [2^-60, 2^60]: division by dt1 needs no per-cell range test
 };
@@ -83,6 +84,7 @@ struct SrmHandle {
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
   float4* d_lut;       // device (exact PVT tabulation), may be null
   int lut_full;        // the table covers the whole clamp range [p_min, p_max]
+  int gc_fused;        // gas condensate: the fused pair (gc_fused.cuh) runs, no staged fields in the workspace
   int device;
   int sm_count;
   // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD)
@@ -126,11 +128,11 @@ struct SrmWs {
 static inline size_t srm_align(size_t x) { return (x + 255) & ~size_t(255); }
 
 // workspace flavours: staged reference order (7 PVT fields), fused reference order (tabulated PVT), closed form
-enum { SRM_WS_REF_STAGED = 0, SRM_WS_REF_FUSED = 1, SRM_WS_CF = 2, SRM_WS_GC = 3 };
+enum { SRM_WS_REF_STAGED = 0, SRM_WS_REF_FUSED = 1, SRM_WS_CF = 2, SRM_WS_GC = 3, SRM_WS_GC_FUSED = 4 };
 #define SRM_GC_NFIELDS 32
 size_t srm_ref2_face_floats(const SrmDev& P);
 static inline int srm_ws_mode(const SrmHandle* h) {
-  if (h->cfg.fluid_type == SRM_FLUID_GC) return SRM_WS_GC;
+  if (h->cfg.fluid_type == SRM_FLUID_GC) return h->gc_fused ? SRM_WS_GC_FUSED : SRM_WS_GC;
   if (h->cfg.numerics == SRM_NUMERICS_CLOSED_FORM) return SRM_WS_CF;
   return h->dev.lut_n > 0 ? SRM_WS_REF_FUSED : SRM_WS_REF_STAGED;
 }
@@ -162,14 +164,12 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64
   }
   size_t fb = (size_t)(B * N) * sizeof(float);
   w.faces = nullptr;
-  if (mode == SRM_WS_REF_FUSED || mode == SRM_WS_GC) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
+  if (mode == SRM_WS_REF_FUSED || mode == SRM_WS_GC || mode == SRM_WS_GC_FUSED) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
   w.dom = (float*)take(fb);
   w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
   w.gc = w.gc_wells = nullptr;
-  if (mode == SRM_WS_GC) {
-    w.gc_wells = (float*)take(7 * wt);
-    w.gc = (float*)take((size_t)SRM_GC_NFIELDS * fb);
-  }
+  if (mode == SRM_WS_GC || mode == SRM_WS_GC_FUSED) w.gc_wells = (float*)take(7 * wt);
+  if (mode == SRM_WS_GC) w.gc = (float*)take((size_t)SRM_GC_NFIELDS * fb);
   if (mode == SRM_WS_REF_STAGED) {
     w.A0 = (float*)take(fb);
     w.A0p = (float*)take(fb);

@@ -302,8 +302,11 @@ class HostPipeline:
     DG_FIELDS = ("p0", "p1")
     GC_FIELDS = ("p0", "p1", "sg0", "sg1", "so0", "so1")
 
-    def __init__(self, eng: "SrmPhysics", host: dict, dterms, n_chunks: int = 8):
+    def __init__(self, eng: "SrmPhysics", host: dict, dterms, n_chunks: int = 8, grads_to_host: bool = True):
+        """grads_to_host=False keeps the cotangents on the device (where the networks that consume them live, as in
+        the reference's training loop): only the loss terms travel back, step() returns device gradient tensors."""
         self.eng = eng
+        self.grads_to_host = bool(grads_to_host)
         self.gc = eng.fluid == "GC"
         self.fields = self.GC_FIELDS if self.gc else self.DG_FIELDS
         self.scalars = ("dt1", "dt2", "t1")
@@ -332,11 +335,16 @@ class HostPipeline:
         self.din = [dict(kx=torch.empty((mr,) + tuple(cell), **f32), sample_real=torch.empty(mb, dtype=torch.int32, device=dev),
                          **{k: torch.empty((mb,) + tuple(cell), **f32) for k in self.fields},
                          **{k: torch.empty(mb, **f32) for k in self.scalars}) for _ in range(2)]
-        self.dout = [[torch.empty((mb,) + tuple(cell), **f32) for _ in self.fields] + [torch.empty(mb, **f32), torch.empty(mb, **f32)]
-                     for _ in range(2)]
         self.gnames = tuple("g" + k for k in self.fields) + ("gdt1", "gdt2")
-        self.hout = {n: (torch.empty(self.B, dtype=torch.float32) if n.startswith("gdt") else torch.empty_like(host["p0"])).pin_memory()
-                     for n in self.gnames}
+        if self.grads_to_host:
+            self.dout = [[torch.empty((mb,) + tuple(cell), **f32) for _ in self.fields] + [torch.empty(mb, **f32), torch.empty(mb, **f32)]
+                         for _ in range(2)]
+            self.hout = {n: (torch.empty(self.B, dtype=torch.float32) if n.startswith("gdt") else torch.empty_like(host["p0"])).pin_memory()
+                         for n in self.gnames}
+        else:
+            self.dgrads = {n: (torch.empty(self.B, **f32) if n.startswith("gdt") else torch.empty((self.B,) + tuple(cell), **f32))
+                           for n in self.gnames}
+            self.hout = {}
         self.hterms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32).pin_memory()
         self.terms = torch.zeros((2, L.SRM_N_TERMS), **f32)
         self.dterms = dterms
@@ -355,7 +363,7 @@ class HostPipeline:
         for c, (r0, r1, b0, b1) in enumerate(self.chunks):
             slot = c & 1
             nb, nr = b1 - b0, r1 - r0
-            din, dout = self.din[slot], self.dout[slot]
+            din = self.din[slot]
             with torch.cuda.stream(self.s_in):
                 if ev_free_in[slot] is not None:
                     self.s_in.wait_event(ev_free_in[slot])
@@ -372,7 +380,10 @@ class HostPipeline:
             a["sample_real"] = din["sample_real"][:nb]
             if r0:
                 a["sample_real"].sub_(r0)
-            out = [t[:nb] for t in dout]
+            if self.grads_to_host:
+                out = [t[:nb] for t in self.dout[slot]]
+            else:
+                out = [self.dgrads[n][b0:b1] for n in self.gnames]
             if self.gc:
                 fw = eng.forward_gc(**a)
                 self.terms.add_(fw["terms"])
@@ -383,14 +394,15 @@ class HostPipeline:
                 eng.backward(dterms=self.dterms, out=out, **a)
             ev_comp[slot] = comp.record_event()
             ev_free_in[slot] = ev_comp[slot]
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(ev_comp[slot])
-                for n, t in zip(self.gnames, out):
-                    self.hout[n][b0:b1].copy_(t, non_blocking=True)
-                ev_free_out[slot] = self.s_out.record_event()
+            if self.grads_to_host:
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(ev_comp[slot])
+                    for n, t in zip(self.gnames, out):
+                        self.hout[n][b0:b1].copy_(t, non_blocking=True)
+                    ev_free_out[slot] = self.s_out.record_event()
         if reduce_terms is not None:
             reduce_terms(self.terms)
         self.hterms.copy_(self.terms, non_blocking=True)
         comp.wait_stream(self.s_out)
         torch.cuda.synchronize(eng.device)
-        return self.hterms, self.hout
+        return self.hterms, (self.hout if self.grads_to_host else self.dgrads)

@@ -44,7 +44,7 @@ def run_both(ocfg, otab, spec, ptab, d, weights=W_ALL, want64=False, pvt_lut=Fal
         o64 = O.gc_forward_backward(ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"],
                                     d["dt1"], d["dt2"], d["t1"], d["sample_real"], weights, dtype=torch.float64)
         o["noise"] = {k: o[k].astype(np.float64) - o64[k] for k in ("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1")}
-    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut, lut_range=(4650.0, 4720.0) if pvt_lut else None)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=bool(pvt_lut), lut_range=(4650.0, 4720.0) if pvt_lut is True else None)
     dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     fw = eng.forward_gc(want_dom=True, want_wells=True, **dev)
     g = eng.backward_gc(dterms=torch.tensor(weights, dtype=torch.float32, device="cuda"), **dev)
@@ -82,8 +82,9 @@ CASES = [
 ]
 
 
-# pvt_lut: the stage kernel gathers from the exact table inside [4650, 4720] psi and evaluates directly outside it
-@pytest.mark.parametrize("pvt_lut", [False, True])
+# pvt_lut True: the stage kernel gathers from the exact table inside [4650, 4720] psi and evaluates directly outside it;
+# "full": the table covers the clamp range and the fused pair (csrc/gc_fused.cuh) replaces stage + residual kernels
+@pytest.mark.parametrize("pvt_lut", [False, True, "full"])
 @pytest.mark.parametrize("kw", CASES)
 def test_gc_forward_backward_vs_oracle(kw, pvt_lut):
     ocfg, otab, spec, ptab, d = gc_case(**kw)
@@ -170,7 +171,7 @@ def test_cuda_pvt_and_relperm_against_reference_made_goldens():
     eng.close()
 
 
-@pytest.mark.parametrize("pvt_lut", [False, True])
+@pytest.mark.parametrize("pvt_lut", [False, True, "full"])
 @pytest.mark.parametrize("case", ["a", "b", "c"])
 def test_cuda_gc_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut):
     """The CUDA gas-condensate forward against fields computed by the reference's OWN physics_error_gas_oil_2D
@@ -183,7 +184,7 @@ def test_cuda_gc_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut
     cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
     otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
     ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
-    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut, lut_range=(4650.0, 4720.0) if pvt_lut else None)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=bool(pvt_lut), lut_range=(4650.0, 4720.0) if pvt_lut is True else None)
     dev = eng.device
     tt = lambda k, dt=torch.float32: torch.as_tensor(g[f"{case}_{k}"]).to(dev, dt).contiguous()
     fw = eng.forward_gc(tt("kx"), tt("sample_real", torch.int32), tt("p0"), tt("p1"), tt("sg0"), tt("sg1"), tt("so0"), tt("so1"),
@@ -196,3 +197,33 @@ def test_cuda_gc_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut
     for name, k in (("dom", "ref_dom"), ("ibc", "ref_ibc"), ("mbc", "ref_mbc"), ("cmbc", "ref_cmbc")):
         assert np.isclose(terms[T.index(name)], sse(k), rtol=1e-5, atol=1e-30), name
     eng.close()
+
+
+@pytest.mark.parametrize("kw", [dict(seed=41, D=5, H=19, W=70, B=3, R=2, wells="dup", sg_lo=0.2, sg_hi=0.5),   # ragged tiles in x and y
+                                dict(seed=42, D=2, H=8, W=32, B=2),                                              # exactly one tile
+                                dict(seed=43, D=1, H=17, W=33, B=2, wells="none")])
+def test_gc_fused_pair_equals_the_staged_pipeline(kw, monkeypatch):
+    """csrc/gc_fused.cuh (table over the whole clamp range) against the staged kernels (SRM_NO_GC2, read at handle
+    creation): residual field and every forward output bit for bit, gradients to rounding (same expressions; only
+    the float atomics of the inner-boundary scatter and the block sums may order differently)."""
+    ocfg, otab, spec, ptab, d = gc_case(**kw)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    w = torch.tensor(W_ALL, dtype=torch.float32, device="cuda")
+    out = {}
+    for mode in ("staged", "fused"):
+        if mode == "staged":
+            monkeypatch.setenv("SRM_NO_GC2", "1")
+        else:
+            monkeypatch.delenv("SRM_NO_GC2", raising=False)
+        eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=True)
+        fw = eng.forward_gc(want_dom=True, want_wells=True, **dev)
+        g = eng.backward_gc(dterms=w, **dev)
+        torch.cuda.synchronize()
+        out[mode] = (fw["dom"].cpu().numpy(), fw["terms"].cpu().numpy(), [t.cpu().numpy() for t in g], eng.workspace(dev["p0"].shape[0], dev["kx"].shape[0]).numel())
+        eng.close()
+    a, b = out["staged"], out["fused"]
+    assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32))
+    assert np.allclose(a[1], b[1], rtol=1e-6, atol=0)
+    for name, x, y in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2"), a[2], b[2]):
+        assert np.allclose(x, y, rtol=1e-5, atol=1e-6 * max(float(np.abs(x).max()), 1e-30)), (name, U.rel_to_max(y, x))
+    assert b[3] < a[3] / 4          # no staged fields in the fused workspace

@@ -95,8 +95,9 @@ def test_directional_derivative_of_the_loss(cfg2):
     assert abs(fd - an) <= 2e-3 * abs(an)
 
 
+@pytest.mark.parametrize("to_host", [True, False])
 @pytest.mark.parametrize("n_chunks", [1, 3])
-def test_host_pipeline_matches_resident_run(n_chunks):
+def test_host_pipeline_matches_resident_run(n_chunks, to_host):
     """engine.HostPipeline (pinned host batch, chunks of whole realisations over three streams) returns the same
     gradients (bit for bit where no atomics are involved) and the same loss terms as one resident forward + adjoint: samples are independent."""
     ocfg, otab, spec, ptab, batch = U.make_case(W=16, H=12, D=3, T=4, K=5, seed=77, all_layers=True)
@@ -106,10 +107,13 @@ def test_host_pipeline_matches_resident_run(n_chunks):
     fw = eng.forward(**d)
     g = eng.backward(dterms=w, **d)
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
-    pipe = srm.engine.HostPipeline(eng, host, w, n_chunks=n_chunks)
+    pipe = srm.engine.HostPipeline(eng, host, w, n_chunks=n_chunks, grads_to_host=to_host)
     for _ in range(2):                                   # the second pass reuses the slots
         hterms, hg = pipe.step()
     assert len(pipe.chunks) == n_chunks
+    assert all(v.is_cuda != to_host for v in hg.values())
+    assert pipe.d2h_bytes == hterms.numel() * 4 + (sum(v.numel() * 4 for v in hg.values()) if to_host else 0)
+    hg = {k: v.cpu() for k, v in hg.items()}
     assert torch.allclose(hterms, fw["terms"].cpu(), rtol=1e-6)
     for name, t in zip(("gp0", "gp1", "gdt1", "gdt2"), g):
         if name == "gp1":     # the inner-boundary scatter uses float atomics where well cells are adjacent: order-dependent last bits
