@@ -8,8 +8,11 @@
 //             plane k+1 while plane k is consumed, one barrier per plane.  Halo cells outside the grid take the
 //             clamped coordinates: the edge-replicating pad of the reference (image faces see the cell itself).
 //   registers the z neighbours: the thread's own values of planes k-1, k, k+1 rotate through registers
-//   gathers   forward: {Mgg,Moo,Mgo,Mog} at p1 for tile + halo, {invBg,invBo,Rs*invBo,Rv*invBg} at p1 and the
-//             32-byte level-n pack at p0 for the tile; adjoint: the 64-byte and 48-byte packs of the staged tables
+//   gathers   forward: {Mgg,Mgo,Moo,Mog} at p1 for tile + halo, {invBg,invBo,Rs*invBo,Rv*invBg} at p1 and the
+//             32-byte level-n pack at p0 for the tile; adjoint: {Mgg+Mog, Mgo+Moo} at p1 for tile + halo, the rest of
+//             the 64-byte and the 48-byte packs of the staged tables for the tile.  The halo ring's gathers are
+//             cp.async copies straight into shared memory (no registers, landing while the plane is computed);
+//             raw p0 / p1 / Sg1 (/ dom) of the next plane are loaded one plane ahead of the gathers they address.
 //
 // The arithmetic of each cell is the staged kernels' (same expressions, same order): the forward is bit-identical
 // to k_stage_gc + k_resid_fwd_gc, the adjoint to k_resid_adj_gc.
@@ -50,6 +53,19 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
 }
 __device__ __forceinline__ void cp_async8(void* smem, const void* g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+// Experiment switch: ask for the own-cell packs of the NEXT plane one plane ahead with prefetch.global (1: L2, 2: L1).
+// Measured slower on B200 (cfg4: forward 16.6 -> 17.2 ms, adjoint 20.8 -> 25.3 ms): the prefetches are extra L2
+// requests on a path that is already bound by the gather request rate.  Off by default.
+#ifndef G2_PF
+#define G2_PF 0
+#endif
+__device__ __forceinline__ void g2_prefetch(const void* p) {
+#if G2_PF == 1
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#elif G2_PF == 2
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -109,8 +125,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     s_q[0][g.hs] = make_float4(h.p1, h.krg, h.kro, 0.f);
   }
   float p1n = 0.f, sg1n = 0.f, hp1 = 0.f, hsg1 = 0.f;
+  float p0c = A.p0[base + g.col], p0n = 0.f;
   if (P.D > 1) {
-    p1n = P1[HW + g.col]; sg1n = SG1[HW + g.col];
+    p1n = P1[HW + g.col]; sg1n = SG1[HW + g.col]; p0n = A.p0[base + HW + g.col];
     if (g.halo) { hp1 = P1[HW + g.hcol]; hsg1 = SG1[HW + g.hcol]; }
   }
   VisF vP = vC;
@@ -122,10 +139,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     // ---- stage plane k+1 (gathers issued before this plane's arithmetic)
     VisF vN = vC;
     float sg1nn = sg1c;
+    const float p0 = p0c;
     if (k + 1 < P.D) {
       vN = g2_vis_fwd(P, T1, p1n, sg1n);
       sg1nn = sg1n;
-      if (k + 2 < P.D) { p1n = P1[(k + 2) * HW + g.col]; sg1n = SG1[(k + 2) * HW + g.col]; }
+      {   // level-n pack of plane k+1
+        float mm;
+        g2_prefetch(T0 + 2 * (size_t)g2_entry(P, p0n, mm));
+        p0c = p0n;
+      }
+      if (k + 2 < P.D) { p1n = P1[(k + 2) * HW + g.col]; sg1n = SG1[(k + 2) * HW + g.col]; p0n = A.p0[base + (k + 2) * HW + g.col]; }
       if (g.halo) {     // raw values arrived a plane ago: the gather goes straight to shared memory, asynchronously
         float hm, hko, hkg, hdko, hdkg;
         cp_async16(&s_m[buf ^ 1][g.hs], T1 + 2 * (size_t)g2_entry(P, hp1, hm));
@@ -136,7 +159,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     }
     // ---- own-cell loads of plane k
     const float p1 = vC.p1, sg1 = sg1c;
-    const float p0 = A.p0[base + c];
     const float sg0 = A.sg0[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
     float m0, m1;
     const uint32_t e0 = g2_entry(P, p0, m0), e1 = g2_entry(P, p1, m1);
@@ -255,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
       s_m[buf ^ 1][g.so] = vN.m;
       s_q[buf ^ 1][g.so] = make_float4(vN.p1, vN.krg, vN.kro, 0.f);
     }
+    if (k + 2 < P.D) { float mm; g2_prefetch(T1 + 2 * (size_t)g2_entry(P, p1n, mm)); }   // next iteration's stage gather
     cp_async_wait_all();
     __syncthreads();
     vP = vC; vC = vN; sg1c = sg1nn;
@@ -329,8 +352,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     s_k[0][g.hs] = make_float2(h.Mg, h.Mo);
   }
   float p1n = 0.f, sg1n = 0.f, domn = 0.f, hp1 = 0.f, hsg1 = 0.f, hdom = 0.f;
+  float p0c = A.p0[base + g.col], p0n = 0.f;
   if (P.D > 1) {
-    p1n = P1[HW + g.col]; sg1n = SG1[HW + g.col]; domn = DOM[HW + g.col];
+    p1n = P1[HW + g.col]; sg1n = SG1[HW + g.col]; domn = DOM[HW + g.col]; p0n = A.p0[base + HW + g.col];
     if (g.halo) { hp1 = P1[HW + g.hcol]; hsg1 = SG1[HW + g.hcol]; hdom = DOM[HW + g.hcol]; }
   }
   VisA vP = vC;
@@ -341,10 +365,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     const int buf = k & 1;
     VisA vN = vC;
     float sg1nn = sg1c;
+    const float p0 = p0c;
     if (k + 1 < P.D) {
       vN = g2_vis_adj(P, p1n, sg1n, domn, w2);
       sg1nn = sg1n;
-      if (k + 2 < P.D) { p1n = P1[(k + 2) * HW + g.col]; sg1n = SG1[(k + 2) * HW + g.col]; domn = DOM[(k + 2) * HW + g.col]; }
+      {   // own-cell packs of plane k+1: 48 bytes at p0 (two sectors at most), 32 at p1
+        float mm;
+        const float4* a0 = P.lut0 + 3 * (size_t)g2_entry(P, p0n, mm);
+        const float4* a1 = P.lut1 + 2 * (size_t)g2_entry(P, p1n, mm);
+        g2_prefetch(a0); g2_prefetch(a0 + 2);
+        g2_prefetch(a1);
+        p0c = p0n;
+      }
+      if (k + 2 < P.D) { p1n = P1[(k + 2) * HW + g.col]; sg1n = SG1[(k + 2) * HW + g.col]; domn = DOM[(k + 2) * HW + g.col]; p0n = A.p0[base + (k + 2) * HW + g.col]; }
       if (g.halo) {
         float hm, hko, hkg, hdko, hdkg;
         cp_async8(&s_k[buf ^ 1][g.hs], P.gcv + g2_entry(P, hp1, hm));
@@ -355,12 +388,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     }
     // ---- own-cell loads of plane k
     const float p1 = vC.p1, sg1 = sg1c;
-    const float p0 = A.p0[base + c];
     const float sg0 = A.sg0[base + c], so0 = A.so0[base + c], so1 = A.so1[base + c];
     float m0, m1;
     const uint32_t e0 = g2_entry(P, p0, m0), e1 = g2_entry(P, p1, m1);
     const float4 n0a = __ldg(P.lut0 + 3 * (size_t)e0), n0b = __ldg(P.lut0 + 3 * (size_t)e0 + 1), n0c = __ldg(P.lut0 + 3 * (size_t)e0 + 2);
-    const float4 n1b = __ldg(P.lut1 + 4 * (size_t)e1 + 1), n1c = __ldg(P.lut1 + 4 * (size_t)e1 + 2), n1d = __ldg(P.lut1 + 4 * (size_t)e1 + 3);
+    const float4 n1b = __ldg(P.lut1 + 2 * (size_t)e1), n1c = __ldg(P.lut1 + 2 * (size_t)e1 + 1);   // {a1,b1,r1,v1}, {dMg,dMo,da1+dv1,dr1+db1}
     const float sc = vC.sn;                                  // dL/d dom_c
     float ckf[6];
     face_perms_tab(FL, fr, P.W, P.H, g.ci, g.cj, k, ckf);
@@ -399,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     const float dA0 = n0b.x, dB0 = n0b.y, dRs0 = n0b.z, dRv0 = n0b.w;
     const float d2A0 = n0c.x * m0, d2B0 = n0c.y * m0, d2Rs0 = n0c.z * m0, d2Rv0 = n0c.w * m0;
     const float a1 = n1b.x, b1 = n1b.y, r1 = n1b.z, v1 = n1b.w;
-    const float da1 = n1c.z * m1, db1 = n1c.w * m1, dr1 = n1d.x * m1, dv1 = n1d.y * m1;
+    const float dav1 = n1c.z * m1, drb1 = n1c.w * m1;      // d(a1 + v1)/dp1, d(r1 + b1)/dp1
     const float R0 = Rs0 * B0, V0 = Rv0 * A0;
     const float dR0 = Rs0 * dB0 + B0 * dRs0, dV0 = Rv0 * dA0 + A0 * dRv0;
     // d/dp0 of the n0 quantities (first derivatives masked by the clamp, second derivatives masked above)
@@ -415,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     const float pKg = P.phi * (pdA0 + pdV0) + P.phicf * (pA0 + pV0);
     const float pKo = P.phi * (pdR0 + pdB0) + P.phicf * (pR0 + pB0);
     const float sacc = sc * P.dv * idt;
-    g1 += sacc * (P.phi * ((da1 + dv1) * dSgS + (dr1 + db1) * dSoS) + (sg0 * Kg + so0 * Ko));
+    g1 += sacc * (P.phi * (dav1 * dSgS + drb1 * dSoS) + (sg0 * Kg + so0 * Ko));
     float g0 = sacc * (dpc * (sg0 * pKg + so0 * pKo) - (sg0 * Kg + so0 * Ko));
     gs1 += sacc * P.phi * (a1 + v1) * nz;
     float gs0 = sacc * (dpc * Kg - P.phi * (a1 + v1) * nz);
@@ -424,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     const float acc_tot = P.dv * idt * (P.phi * ((a1 + v1) * dSgS + (r1 + b1) * dSoS) + dpc * (sg0 * Kg + so0 * Ko));
     // material balance: mbc_b = -sum q - sum mcell
     const float mcell = mfac * ((sg1 * a1 - sg0 * A0) + (so1 * r1 - so0 * R0) + (so1 * b1 - so0 * B0) + (sg1 * v1 - sg0 * V0));
-    g1 -= smf * (sg1 * (da1 + dv1) + so1 * (dr1 + db1));
+    g1 -= smf * (sg1 * dav1 + so1 * drb1);
     g0 += smf * (sg0 * (pA0 + pV0) + so0 * (pR0 + pB0));
     gs1 -= smf * (a1 + v1);
     gs0 += smf * (A0 + V0);
@@ -470,6 +502,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
       s_v[buf ^ 1][g.so] = make_float4(vN.p1, vN.sn, vN.krg, vN.kro);
       s_k[buf ^ 1][g.so] = make_float2(vN.Mg, vN.Mo);
     }
+    if (k + 2 < P.D) { float mm; g2_prefetch(P.gcv + g2_entry(P, p1n, mm)); }             // next iteration's stage gather
     cp_async_wait_all();
     __syncthreads();
     vP = vC; vC = vN; sg1c = sg1nn;
@@ -487,7 +520,7 @@ __device__ __forceinline__ IbcCell g2_ibc_cell(const SrmDev& P, float p1, float 
   float m1;
   const uint32_t e = g2_entry(P, p1, m1);
   const float2 t = __ldg(P.gcv + e);
-  const float4 d = __ldg(P.lut1 + 4 * (size_t)e + 2);
+  const float4 d = __ldg(P.lut1 + 2 * (size_t)e + 1);
   IbcCell v;
   corey(P, sg1, v.kro, v.krg, v.dkro, v.dkrg);
   v.Mg = t.x;

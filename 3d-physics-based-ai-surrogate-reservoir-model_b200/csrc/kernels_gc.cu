@@ -35,22 +35,37 @@ enum {
 static_assert(F_COUNT <= SRM_GC_NFIELDS, "workspace carve");
 
 // ---- relative permeability ------------------------------------------------------------------
-__device__ __forceinline__ float pow_pinned(float x, float n, int ni) {
-  if (ni > 0) {
-    float y = x;
-    for (int i = 1; i < ni; ++i) y = __fmul_rn(y, x);
-    return y;
+// non-integer exponents: out of line, so the residual kernels do not carry several inlined copies of powf
+__device__ __noinline__ float pow_general(float x, float n) { return powf(x, n); }
+// x^N as the left-to-right product x*x*...*x (N >= 1), straight-line
+template <int N>
+__device__ __forceinline__ float powi(float x) {
+  float y = x;
+#pragma unroll
+  for (int i = 1; i < N; ++i) y = __fmul_rn(y, x);
+  return y;
+}
+__device__ __forceinline__ float powi_rt(float x, int ni) {     // ni >= 1, uniform over the grid
+  switch (ni) {
+    case 1: return x;
+    case 2: return powi<2>(x);
+    case 3: return powi<3>(x);
+    case 4: return powi<4>(x);
+    case 5: return powi<5>(x);
+    case 6: return powi<6>(x);
+    default: break;
   }
-  return powf(x, n);
+  float y = powi<6>(x);
+  for (int i = 6; i < ni; ++i) y = __fmul_rn(y, x);
+  return y;
+}
+__device__ __forceinline__ float pow_pinned(float x, float n, int ni) {
+  return ni > 0 ? powi_rt(x, ni) : pow_general(x, n);
 }
 // d/dx of pow_pinned as the product rule delivers it: n * x^(n-1)
 __device__ __forceinline__ float dpow_pinned(float x, float n, int ni) {
-  if (ni > 0) {
-    float y = 1.f;
-    for (int i = 1; i < ni; ++i) y *= x;
-    return (float)ni * y;
-  }
-  return n * powf(x, n - 1.f);
+  if (ni > 0) return (float)ni * (ni > 1 ? powi_rt(x, ni - 1) : 1.f);
+  return n * pow_general(x, n - 1.f);
 }
 // relative_permeability.py:58-73; derivatives follow TF's routing: tf.where picks a branch, tf.minimum /
 // tf.maximum pass the gradient to the first argument on ties.
@@ -132,7 +147,7 @@ __device__ __forceinline__ GcPack1 gc_pack1(const SrmDev& P, float x1) {
 // pattern lut_lo_bits + e; 48 + 64 bytes per representable pressure.
 __global__ void __launch_bounds__(kThreads) k_lut_build_gc(const __grid_constant__ SrmDev P, float4* __restrict__ t0,
                                                            float4* __restrict__ t1, float4* __restrict__ f0, float4* __restrict__ f1,
-                                                           float2* __restrict__ fv) {
+                                                           float2* __restrict__ fv, float4* __restrict__ a1) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.lut_n) return;
   const float x = __uint_as_float(P.lut_lo_bits + e);
@@ -140,14 +155,20 @@ __global__ void __launch_bounds__(kThreads) k_lut_build_gc(const __grid_constant
   const GcPack1 b = gc_pack1<true>(P, x);
 #pragma unroll
   for (int i = 0; i < 3; ++i) t0[(size_t)e * 3 + i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+  if (t1) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) t1[(size_t)e * 4 + i] = make_float4(b.v[4 * i], b.v[4 * i + 1], b.v[4 * i + 2], b.v[4 * i + 3]);
+    for (int i = 0; i < 4; ++i) t1[(size_t)e * 4 + i] = make_float4(b.v[4 * i], b.v[4 * i + 1], b.v[4 * i + 2], b.v[4 * i + 3]);
+  }
   if (f0) {     // the fused forward's 32-byte views (gc_fused.cuh): values and first derivatives of level n, products of level n+1
 #pragma unroll
     for (int i = 0; i < 2; ++i) f0[(size_t)e * 2 + i] = make_float4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
     f1[(size_t)e * 2] = make_float4(b.v[0], b.v[2], b.v[1], b.v[3]);            // component order gg, go, oo, og
     f1[(size_t)e * 2 + 1] = make_float4(b.v[4], b.v[5], b.v[6], b.v[7]);
     fv[e] = make_float2(b.v[0] + b.v[3], b.v[2] + b.v[1]);                      // the adjoint's neighbour-visible sums
+    // the adjoint's own-cell view of level n+1, one 32-byte sector: values, d(Mgg+Mog), d(Mgo+Moo) and the two sums
+    // of derivatives its expressions use (d invBg + d(Rv invBg), d(Rs invBo) + d invBo)
+    a1[(size_t)e * 2] = make_float4(b.v[4], b.v[5], b.v[6], b.v[7]);
+    a1[(size_t)e * 2 + 1] = make_float4(b.v[8], b.v[9], b.v[10] + b.v[13], b.v[12] + b.v[11]);
   }
 }
 
@@ -778,19 +799,22 @@ int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi) {
   if (n > (1ull << 31)) { srm_set_error("srm_create: pvt_lut range too wide"); return SRM_ERR_INVALID; }
   // fused pair (gc_fused.cuh): needs the table over the whole clamp range; SRM_NO_GC2 keeps the staged pipeline
   h->gc_fused = (h->lut_full && !getenv("SRM_NO_GC2")) ? 1 : 0;
-  const uint64_t per = h->gc_fused ? 11 : 7;                                    // 3 + 4 float4 per pressure (+ 2 + 2 forward views)
+  // staged: 3 + 4 float4 per pressure; fused: 3 (level n) + 2 + 2 (forward views) + 2 (adjoint view of level n+1)
+  const uint64_t per = h->gc_fused ? 9 : 7;
   cudaError_t e = cudaMalloc((void**)&h->d_lut, n * per * sizeof(float4) + (h->gc_fused ? n * sizeof(float2) : 0));
   if (e != cudaSuccess) { srm_set_error("srm_create: pvt_lut (GC) needs %.1f MB of device memory: %s", n * per * 16e-6, cudaGetErrorString(e)); return SRM_ERR_CUDA; }
   P.lut_lo_bits = lo_bits;
   P.lut_n = (uint32_t)n;
   P.lut0 = h->d_lut;
-  P.lut1 = h->d_lut + 3 * n;
-  float4* f0 = h->gc_fused ? h->d_lut + 7 * n : nullptr;
-  float4* f1 = h->gc_fused ? h->d_lut + 9 * n : nullptr;
+  float4* t1 = h->gc_fused ? nullptr : h->d_lut + 3 * n;           // staged 64-byte pack of level n+1
+  float4* f0 = h->gc_fused ? h->d_lut + 3 * n : nullptr;
+  float4* f1 = h->gc_fused ? h->d_lut + 5 * n : nullptr;
+  float4* a1 = h->gc_fused ? h->d_lut + 7 * n : nullptr;
+  float2* fv = h->gc_fused ? reinterpret_cast<float2*>(h->d_lut + 9 * n) : nullptr;
+  P.lut1 = h->gc_fused ? a1 : t1;                                  // fused: the adjoint's 32-byte view (gc_fused.cuh)
   P.lutf0 = reinterpret_cast<const float2*>(f0); P.lutf1 = reinterpret_cast<const float2*>(f1);
-  float2* fv = h->gc_fused ? reinterpret_cast<float2*>(h->d_lut + 11 * n) : nullptr;
   P.gcv = fv;
-  k_lut_build_gc<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, h->d_lut + 3 * n, f0, f1, fv);
+  k_lut_build_gc<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads>>>(P, h->d_lut, t1, f0, f1, fv, a1);
   SRM_CUDA_CHECK(cudaGetLastError());
   SRM_CUDA_CHECK(cudaDeviceSynchronize());
   return SRM_OK;
