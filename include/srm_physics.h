@@ -112,10 +112,12 @@ typedef struct SrmConfig {
    * spline (polyhm_splines.py:138-146) and its tape derivatives (PVT_Layer_Subclassed.py:196-201) for
    * every cell of every call, although they are a pure function of ONE clamped fp32 pressure.
    * pvt_lut = 1 evaluates that function once, at create, for EVERY fp32 value of
-   * [lut_p_lo, lut_p_hi] (32 bytes per value; lo >= hi means the whole clamp range [p_min, p_max],
-   * 78.7 M values = 2.5 GB for [14.7, 10000]) with the same reference-order code, and the kernels
-   * index the table by the pressure's bit pattern.  Results are bit-identical to pvt_lut = 0;
-   * pressures outside the tabulated range are evaluated directly. */
+   * [lut_p_lo, lut_p_hi] (48 bytes per value dry gas, 112-152 gas condensate; lo >= hi means the whole
+   * clamp range [p_min, p_max], 78.7 M values for [14.7, 10000]) with the same reference-order code, and
+   * the kernels index the table by the pressure's bit pattern.  Results are bit-identical to pvt_lut = 0;
+   * pressures outside the tabulated range are evaluated directly.  A table over the whole clamp range
+   * selects the fused kernels (dry gas: kernels_dg4.cu; gas condensate: gc_fused.cuh, whose workspace
+   * then holds no staged fields). */
   int32_t pvt_lut;
   float lut_p_lo, lut_p_hi;
   /* SCAL end points and Corey exponents (relative_permeability.py:19-45; default_configurations.py:262-266).
