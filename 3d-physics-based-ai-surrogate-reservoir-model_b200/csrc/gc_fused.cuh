@@ -69,6 +69,15 @@ __device__ __forceinline__ void g2_prefetch(const void* p) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// a / b, IEEE.  div.rn sends a == 0 to its slow path (a subroutine call with some thirty instructions); the
+// truncation brackets vanish identically (physics_loss.py:419-441) and saturation differences are often exactly zero,
+// so the zero numerator is answered first: (+-0) / b = +-0 with the sign product, for any finite non-zero b.
+__device__ __forceinline__ float div_z(float a, float b) {
+  const float ab = fabsf(b);
+  if (a == 0.f && ab > 0.f && ab <= 3.402823466e38f) return __fmul_rn(a, copysignf(1.0f, b));
+  return __fdiv_rn(a, b);
+}
+
 __device__ __forceinline__ uint32_t g2_entry(const SrmDev& P, float p, float& m) {
   const float x = srm_clamp(P, p, m);
   return __float_as_uint(x) - P.lut_lo_bits;
@@ -102,13 +111,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   const float* __restrict__ P1 = A.p1 + base;
   const float* __restrict__ SG1 = A.sg1 + base;
   const FaceLay FL = face_layout(P.D, P.H, P.W);
-  const float* __restrict__ fr = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FN = FE + FL.nE;
+  const float* __restrict__ FU = FN + FL.nN;
+  int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
   const bool col_wells = g.active && column_has_well_gc(P, g.col, HW);
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
   const float idt = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
   const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
   const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const DivC den_c = make_divc(den);          // correctly rounded division by the per-sample constant (ref_fused.cuh)
   const float rte_d1 = __fdiv_rn(2.5e-8f, d1);                                  // :439-440
   const float d12 = __fadd_rn(d1, d2);
   const float mfac = __fmul_rn(__fmul_rn(P.dv, idt), P.phi);
@@ -164,8 +177,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     const uint32_t e0 = g2_entry(P, p0, m0), e1 = g2_entry(P, p1, m1);
     const float4 n0a = __ldg(T0 + 2 * (size_t)e0), n0b = __ldg(T0 + 2 * (size_t)e0 + 1);
     const float4 n1b = __ldg(T1 + 2 * (size_t)e1 + 1);
-    float ckf[6];
-    face_perms_tab(FL, fr, P.W, P.H, g.ci, g.cj, k, ckf);
+    float ckf[6];      // C*k_f of the six faces (W,E,S,N,D,U), see face_perms_tab; offsets advance by one plane per step
+    ckf[0] = __ldg(FE + fe); ckf[1] = __ldg(FE + fe + 1);
+    ckf[2] = __ldg(FN + fn); ckf[3] = __ldg(FN + fn + P.W);
+    ckf[4] = __ldg(FU + fu); ckf[5] = __ldg(FU + fu + HW);
+    fe += P.H * FL.WP; fn += (P.H + 1) * P.W; fu += HW;
     const float Mc[4] = {vC.m.x, vC.m.y, vC.m.z, vC.m.w};                          // gg, go, oo, og
     const float krg_c = vC.krg, kro_c = vC.kro;
     // neighbours W,E,S,N from the shared plane, D,U from registers
@@ -227,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     const float a1 = n1b.x, b1 = n1b.y, r1 = n1b.z, v1 = n1b.w;
     const float R0 = __fmul_rn(Rs0, B0), V0 = __fmul_rn(Rv0, A0);                 // :343-344
     const float dpc = __fsub_rn(p1, p0);
-    const float dSg = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(sg1, sg0), dpc);   // :465
-    const float dSo = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(so1, so0), dpc);   // :466
+    const float dSg = (dpc == 0.f) ? 0.f : div_z(__fsub_rn(sg1, sg0), dpc);       // :465
+    const float dSo = (dpc == 0.f) ? 0.f : div_z(__fsub_rn(so1, so0), dpc);       // :466
     const float dR0 = __fadd_rn(__fmul_rn(Rs0, dB0), __fmul_rn(B0, dRs0));        // :511
     const float dV0 = __fadd_rn(__fmul_rn(Rv0, dA0), __fmul_rn(A0, dRv0));        // :513
     auto cpX = [&](float prop1, float dS, float s0, float dprop0, float prop0) {
@@ -248,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     auto trnX = [&](float mm0, float mm1) {
       const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(mm1, mm0), rho1), mm0);
       const float num = __fsub_rn(__fadd_rn(__fmul_rn(d2, mm0), __fmul_rn(d1, m2)), __fmul_rn(d12, mm1));
-      return __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(num, den)));
+      return __fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_c(num, den_c)));
     };
     const float mg0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(A0, sg0), __fmul_rn(R0, so0)));
     const float mo0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(B0, so0), __fmul_rn(V0, sg0)));
@@ -323,7 +339,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const float* __restrict__ SG1 = A.sg1 + base;
   const float* __restrict__ DOM = A.dom + base;
   const FaceLay FL = face_layout(P.D, P.H, P.W);
-  const float* __restrict__ fr = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FE = A.faces + (int64_t)r * FL.per_real;
+  const float* __restrict__ FN = FE + FL.nE;
+  const float* __restrict__ FU = FN + FL.nN;
+  int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
   const bool col_wells = g.active && column_has_well_gc(P, g.col, HW);
   const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_trn = A.dterms[SRM_TERM_CMBC];
   const float w2 = 2.f * w_dom;
@@ -337,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   // forward's per-sample scalars of the truncation term, in the forward's op order
   const float rho1 = __fadd_rn(1.0f, (d1 == 0.f) ? 0.f : __fdiv_rn(d2, d1));
   const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
+  const DivC den_c = make_divc(den);
   const float rte_d1 = __fdiv_rn(2.5e-8f, d1);
   const float d12 = __fadd_rn(d1, d2);
   const float iden2 = 1.0f / (den * den);
@@ -394,8 +414,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     const float4 n0a = __ldg(P.lut0 + 3 * (size_t)e0), n0b = __ldg(P.lut0 + 3 * (size_t)e0 + 1), n0c = __ldg(P.lut0 + 3 * (size_t)e0 + 2);
     const float4 n1b = __ldg(P.lut1 + 2 * (size_t)e1), n1c = __ldg(P.lut1 + 2 * (size_t)e1 + 1);   // {a1,b1,r1,v1}, {dMg,dMo,da1+dv1,dr1+db1}
     const float sc = vC.sn;                                  // dL/d dom_c
-    float ckf[6];
-    face_perms_tab(FL, fr, P.W, P.H, g.ci, g.cj, k, ckf);
+    float ckf[6];      // C*k_f of the six faces (W,E,S,N,D,U), see face_perms_tab; offsets advance by one plane per step
+    ckf[0] = __ldg(FE + fe); ckf[1] = __ldg(FE + fe + 1);
+    ckf[2] = __ldg(FN + fn); ckf[3] = __ldg(FN + fn + P.W);
+    ckf[4] = __ldg(FU + fu); ckf[5] = __ldg(FU + fu + HW);
+    fe += P.H * FL.WP; fn += (P.H + 1) * P.W; fu += HW;
     const float Mg_c = vC.Mg, Mo_c = vC.Mo, krg_c = vC.krg, kro_c = vC.kro;
     const float dMg_c = n1c.x * m1, dMo_c = n1c.y * m1, dkrg_c = vC.dkrg, dkro_c = vC.dkro;
     float4 nv[6];
@@ -484,8 +507,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
       const float mg1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(a1, sg1), __fmul_rn(r1, so1)));
       const float mo1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(b1, so1), __fmul_rn(v1, sg1)));
       const float Ng = numX(mg0, mg1), No = numX(mo0, mo1);
-      const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(Ng, den))),
-                                  __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(No, den))));
+      const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_c(Ng, den_c))),
+                                  __fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_c(No, den_c))));
       const float st = 2.f * w_trn * trn;
       const float dE1 = dE1c - (Ng + No) * d2 * iden2;
       const float dE2 = -(Ng + No) * (d1 + 2.f * d2) * iden2;
