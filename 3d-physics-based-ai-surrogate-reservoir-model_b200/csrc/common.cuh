@@ -33,6 +33,15 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* smem /* [N
 }
 
 
+// a / b, IEEE.  div.rn sends a == 0 to its slow path (a subroutine call with some thirty instructions); the
+// truncation brackets vanish identically (physics_loss.py:171, 419-441) and saturation differences are often exactly
+// zero, so the zero numerator is answered first: (+-0) / b = +-0 with the sign product, for any finite non-zero b.
+__device__ __forceinline__ float div_z(float a, float b) {
+  const float ab = fabsf(b);
+  if (a == 0.f && ab > 0.f && ab <= 3.402823466e38f) return __fmul_rn(a, copysignf(1.0f, b));
+  return __fdiv_rn(a, b);
+}
+
 // first well (sorted by cell) with cell >= c
 __device__ __forceinline__ int well_lower_bound(const SrmDev& P, int c) {
   int lo = 0, hi = P.n_wells;

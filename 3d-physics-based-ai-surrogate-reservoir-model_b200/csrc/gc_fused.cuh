@@ -69,15 +69,6 @@ __device__ __forceinline__ void g2_prefetch(const void* p) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// a / b, IEEE.  div.rn sends a == 0 to its slow path (a subroutine call with some thirty instructions); the
-// truncation brackets vanish identically (physics_loss.py:419-441) and saturation differences are often exactly zero,
-// so the zero numerator is answered first: (+-0) / b = +-0 with the sign product, for any finite non-zero b.
-__device__ __forceinline__ float div_z(float a, float b) {
-  const float ab = fabsf(b);
-  if (a == 0.f && ab > 0.f && ab <= 3.402823466e38f) return __fmul_rn(a, copysignf(1.0f, b));
-  return __fdiv_rn(a, b);
-}
-
 __device__ __forceinline__ uint32_t g2_entry(const SrmDev& P, float p, float& m) {
   const float x = srm_clamp(P, p, m);
   return __float_as_uint(x) - P.lut_lo_bits;

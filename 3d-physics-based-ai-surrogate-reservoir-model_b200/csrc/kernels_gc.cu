@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_resid_fwd_gc(const __grid_const
     const float a1 = F(F_A1, c), b1 = F(F_B1, c), r1 = F(F_R1, c), v1 = F(F_V1, c);
     const float R0 = __fmul_rn(Rs0, B0), V0 = __fmul_rn(Rv0, A0);                 // :343-344
     const float dpc = __fsub_rn(p1, p0);
-    const float dSg = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(sg1, sg0), dpc);   // :465
-    const float dSo = (dpc == 0.f) ? 0.f : __fdiv_rn(__fsub_rn(so1, so0), dpc);   // :466
+    const float dSg = (dpc == 0.f) ? 0.f : div_z(__fsub_rn(sg1, sg0), dpc);       // :465
+    const float dSo = (dpc == 0.f) ? 0.f : div_z(__fsub_rn(so1, so0), dpc);       // :466
     const float dR0 = __fadd_rn(__fmul_rn(Rs0, dB0), __fmul_rn(B0, dRs0));        // :511
     const float dV0 = __fadd_rn(__fmul_rn(Rv0, dA0), __fmul_rn(A0, dRv0));        // :513
     auto cpX = [&](float prop1, float dS, float s0, float dprop0, float prop0) {
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_resid_fwd_gc(const __grid_const
     auto trnX = [&](float m0, float m1) {
       const float m2 = __fadd_rn(__fmul_rn(__fsub_rn(m1, m0), rho1), m0);
       const float num = __fsub_rn(__fadd_rn(__fmul_rn(d2, m0), __fmul_rn(d1, m2)), __fmul_rn(d12, m1));
-      return __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(num, den)));
+      return __fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_z(num, den)));
     };
     const float mg0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(A0, sg0), __fmul_rn(R0, so0)));
     const float mo0 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(B0, so0), __fmul_rn(V0, sg0)));
@@ -700,8 +700,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_resid_adj_gc(const __grid_const
       const float mg1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(a1, sg1), __fmul_rn(r1, so1)));
       const float mo1 = __fmul_rn(P.phi, __fadd_rn(__fmul_rn(b1, so1), __fmul_rn(v1, sg1)));
       const float Ng = numX(mg0, mg1), No = numX(mo0, mo1);
-      const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(Ng, den))),
-                                  __fmul_rn(P.dvDc, __fadd_rn(rte_d1, __fdiv_rn(No, den))));
+      const float trn = __fadd_rn(__fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_z(Ng, den))),
+                                  __fmul_rn(P.dvDc, __fadd_rn(rte_d1, div_z(No, den))));
       const float st = 2.f * w_trn * trn;
       const float dE1 = dE1c - (Ng + No) * d2 * iden2;
       const float dE2 = -(Ng + No) * (d1 + 2.f * d2) * iden2;

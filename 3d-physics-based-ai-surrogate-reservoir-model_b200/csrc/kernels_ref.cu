@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_ref(
     // truncation term                                          physics_loss.py:171
     const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
     const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(__fadd_rn(d1, d2), p1));
-    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), __fdiv_rn(numr, den));
+    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), div_z(numr, den));
     const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
     // flux divergence                                          physics_loss.py:174
     float s = __fadd_rn(-__fmul_rn(a1, pW), -__fmul_rn(a2, pS));
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_ref(
     const float p2 = __fadd_rn(__fmul_rn(__fsub_rn(p1, p0), __fadd_rn(1.0f, rho)), p0);
     const float den = __fadd_rn(__fmul_rn(d1, d2), __fmul_rn(d2, d2));
     const float numr = __fsub_rn(__fadd_rn(__fmul_rn(d2, p0), __fmul_rn(d1, p2)), __fmul_rn(__fadd_rn(d1, d2), p1));
-    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), __fdiv_rn(numr, den));
+    const float E = __fadd_rn(__fdiv_rn(2e-7f, d1), div_z(numr, den));
     const float tde = __fmul_rn(__fmul_rn(P.dvDc, cp), E);
     const float st = (P.tde_in_dom ? sc : 0.f) + 2.f * w_tde * tde;   // dL/d tde
     // wells in this cell
