@@ -249,6 +249,16 @@ def test_error_behaviour():
                              C.c_void_p(d["dt2"].data_ptr()), C.c_void_p(d["t1"].data_ptr()),
                              C.c_void_p(terms.data_ptr()), None, None, None, C.c_void_p(ws.data_ptr()), 16, 0, None)
     assert rc == -3 and b"workspace" in eng.lib.srm_last_error()
+    # an empty batch is refused with a message, not launched with an empty grid (the kernels' grid.y is the sample axis)
+    for B in (0, 65536):
+        rc = eng.lib.srm_forward(eng._h, B, 1, C.c_void_p(d["kx"].data_ptr()), None, C.c_void_p(d["p0"].data_ptr()),
+                                 C.c_void_p(d["p1"].data_ptr()), C.c_void_p(d["dt1"].data_ptr()),
+                                 C.c_void_p(d["dt2"].data_ptr()), C.c_void_p(d["t1"].data_ptr()),
+                                 C.c_void_p(terms.data_ptr()), None, None, None, C.c_void_p(ws.data_ptr()), 16, 0, None)
+        assert rc == -1 and b"B=" in eng.lib.srm_last_error(), (B, rc)
+    empty = {k: (v if k == "kx" else v[:0]) for k, v in d.items()}
+    with pytest.raises((ValueError, srm._lib.SrmError)):
+        eng.forward(**empty)
 
 
 def test_rounding_selftest_matches_ieee_intrinsics():
