@@ -449,9 +449,12 @@ def run_ours(args):
             ach = one * abytes / (ms_ * 1e-3) if ms_ == ms_ and ms_ > 0 else None
             return {"kernel": name, "ms": float(ms_), "alg_bytes_per_cell": abytes, "achieved": ach,
                     "frac": (ach / peak) if ach else None, "traffic": traffic}
-        adj = pass_obj("adjoint pass: " + ("k_adj_gc2" if gc else "k_adj4") + " (+ inner-boundary scatter, finalize)", bwd_ms, ab_a,
+        lean = lut and spec.W % 2 == 0          # kernels_dg4.cu takes even widths with the full-range table; else kernels_ref2.cu
+        k_a = "k_adj_gc2" if gc else ("k_adj4" if lean else "k_adj_ref2" if lut else "adjoint kernels")
+        k_f = "k_fwd_gc2" if gc else ("k_fwd4" if lean else "k_fwd_ref2" if lut else "forward kernels")
+        adj = pass_obj("adjoint pass: " + k_a + " (+ inner-boundary scatter, finalize)", bwd_ms, ab_a,
                        kernel_traffic("k_adj4", "k_adj_gc2"))
-        fwdp = pass_obj("forward pass: " + ("k_fwd_gc2" if gc else "k_fwd4") + " (+ faces, wells, finalize)", fwd_ms, ab_f,
+        fwdp = pass_obj("forward pass: " + k_f + " (+ faces, wells, finalize)", fwd_ms, ab_f,
                         kernel_traffic("k_fwd4", "k_fwd_gc2"))
         roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
                 "kernel": adj["kernel"], "achieved": adj["achieved"], "frac": adj["frac"], "traffic": adj["traffic"],
