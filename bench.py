@@ -365,6 +365,27 @@ def run_ours(args):
     if not torch.allclose(hterms[0], ref_terms[0].cpu(), rtol=1e-5):
         raise SystemExit(f"bench.py: e2e pipeline terms {hterms[0].tolist()} != resident terms {ref_terms[0].cpu().tolist()}")
 
+    # ---- the same step replayed from a CUDA graph (engine.GraphedStep): what a launch-bound case gains (cfg1, the
+    # reference's own grid, is a dozen launches of a few microseconds); reported beside `value`, not instead of it
+    graph = None
+    if reps == 1 and B * spec.n_cells * 4 <= 2e9:
+        gs = srm.engine.GraphedStep(eng, d, dterms)
+        for _ in range(3):
+            gs.replay()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            gs.replay()
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gms = g0.elapsed_time(g1) / args.steps
+        if not distributed and not torch.allclose(gs.terms, ref_terms, rtol=1e-5):
+            raise SystemExit("bench.py: graph replay terms differ from the eager step")
+        graph = {"ms_per_step": gms, "value": world * N / (gms * 1e-3), "unit": UNIT, "kernels_per_replay": gs.kernels,
+                 "api": "srm.engine.GraphedStep.replay: forward + adjoint captured once in a CUDA graph"}
+        del gs
+
     # ---- the fused glue either side of the kernels: HardLayer at both levels + dt means and
     # their cotangents, timed on the same resident batch (not part of `value`: the reference's metric is the residual)
     glue = None
@@ -489,6 +510,7 @@ def run_ours(args):
                            "value = full round trip (all cotangent fields back to pinned host memory)",
                     "grads_on_device": {"value": e2e_loss_only, "unit": UNIT, "d2h_bytes_per_step": int(d2h_loss_only) * reps,
                                         "note": "same call with grads_to_host=False: inputs from host, loss terms to host, cotangents stay in HBM for the networks' backward"}},
+            "cuda_graph": graph,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "glue": glue,

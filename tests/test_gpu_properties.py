@@ -121,3 +121,26 @@ def test_host_pipeline_matches_resident_run(n_chunks, to_host):
         else:
             assert torch.equal(hg[name], t.cpu()), name
     eng.close()
+
+
+@pytest.mark.parametrize("W", [16, 39])       # even width: kernels_dg4.cu; odd: kernels_ref2.cu
+def test_graphed_step_replays_the_eager_step(W):
+    """engine.GraphedStep (forward + adjoint captured in one CUDA graph): a replay returns what the eager calls return,
+    also after the static input buffers have been refilled."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=W, H=12, D=2, T=4, K=2, seed=91)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=True)
+    d = U.to_dev(batch, "cuda")
+    w = torch.tensor(U.WEIGHTS, device="cuda")
+    gs = srm.engine.GraphedStep(eng, d, w)
+    assert gs.kernels >= 5
+    for shift in (0.0, -7.25):
+        cur = {**d, "p0": d["p0"] + shift, "p1": d["p1"] + shift}
+        gs.load(p0=cur["p0"], p1=cur["p1"])
+        terms, grads = gs.replay()
+        torch.cuda.synchronize()
+        fw = eng.forward(**cur)
+        g = eng.backward(dterms=w, **cur)
+        assert torch.allclose(terms, fw["terms"], rtol=1e-6)
+        for name, a, b in zip(("gp0", "gp1", "gdt1", "gdt2"), grads, g):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max())), name
+    eng.close()
