@@ -251,3 +251,44 @@ def test_gc_host_pipeline_matches_resident_run(to_host):
         a = hg[name].cpu()
         assert torch.allclose(a, t.cpu(), rtol=1e-5, atol=1e-6 * float(t.abs().max())), name
     eng.close()
+
+
+def test_gc_full_grid_fused_equals_staged_and_is_additive(monkeypatch):
+    """BASELINE config 4's grid (128 x 128 x 32, two realisations of 12 time points): size-independent properties --
+    the fused pair's residual field equals the staged pipeline's bit for bit, its gradients agree to rounding, and
+    the loss terms are additive over realisation shards."""
+    W, H, D, T, K = 128, 128, 32, 12, 2
+    wells = srm.config.scaled_default_wells(W, H, D)
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=wells, fluid_type="GC")
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.GC_PROPERTIES, order=1)
+    b = srm.synth.make_batch(W, H, D, T, K, [(w.i, w.j) for w in wells], seed=404, device="cuda")
+    d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
+    d["sg0"], d["sg1"], d["so0"], d["so1"] = srm.synth.make_saturations(b, seed=404)
+    w = torch.tensor(W_ALL, dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in ("staged", "fused"):
+        if mode == "staged":
+            monkeypatch.setenv("SRM_NO_GC2", "1")
+        else:
+            monkeypatch.delenv("SRM_NO_GC2", raising=False)
+        eng = srm.SrmPhysics(spec, tabs, device=0, pvt_lut=True)
+        fw = eng.forward_gc(want_dom=True, **d)
+        g = [t.clone() for t in eng.backward_gc(dterms=w, **d)]
+        res[mode] = (fw["dom"].clone(), fw["terms"].clone(), g)
+        if mode == "fused":
+            parts = []
+            for r in range(K):
+                sl = slice(r * T, (r + 1) * T)
+                sub = {k: (v[r:r + 1] if k == "kx" else v[sl].contiguous()) for k, v in d.items()}
+                sub["sample_real"] = torch.zeros(T, dtype=torch.int32, device="cuda")
+                parts.append(eng.forward_gc(**sub)["terms"][0].double())
+            whole = fw["terms"][0].double()
+            assert torch.allclose(parts[0] + parts[1], whole, rtol=1e-6), (parts, whole)
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    a, f = res["staged"], res["fused"]
+    assert torch.equal(a[0].view(torch.int32), f[0].view(torch.int32))
+    assert torch.allclose(a[1], f[1], rtol=1e-6)
+    for name, x, y in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2"), a[2], f[2]):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-6 * max(float(x.abs().max()), 1e-30)), name
