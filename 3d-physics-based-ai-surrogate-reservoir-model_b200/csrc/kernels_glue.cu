@@ -204,7 +204,140 @@ __global__ void __launch_bounds__(256) k_gather_rows(const V* __restrict__ src, 
     out[v] = ok ? in[v] : zero;
 }
 
+
+// ---- feature tensor: time shift and permeability channel -------------------------------------------------------
+// x is (B, cells, C) with the channels innermost (the reference's (B,D,H,W,5) features).  One pass reads x once and
+// writes x_n1 = x with t_norm += dn[b] (physics_loss.py:105-110) and, if asked, the de-normalised permeability of
+// channel kc (DataSummary.nonormalize, log branch: data_processing_utils.py:1098-1106, same arithmetic as
+// k_denorm_log).  The reference does this with a zeros_like, a strided assignment, an add and a strided slice.
+template <int CT, int VEC>
+__global__ void __launch_bounds__(256) k_features(int64_t per_sample, int32_t C_rt, int32_t tc, int32_t kc,
+                                                  const float* __restrict__ x, const float* __restrict__ dn,
+                                                  float lr, float lmin, float lo, float span,
+                                                  float* __restrict__ x1, float* __restrict__ kx) {
+  const int C = CT > 0 ? CT : C_rt;
+  const int b = blockIdx.y;
+  const float d = dn ? dn[b] : 0.f;
+  const float* xs = x + (int64_t)b * per_sample;
+  float* x1s = x1 ? x1 + (int64_t)b * per_sample : nullptr;
+  float* kxs = kx ? kx + (int64_t)b * (per_sample / C) : nullptr;
+  const int64_t nv = per_sample / VEC;                      // VEC = 4: per_sample % 4 == 0 and aligned (launcher)
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    float e[VEC];
+    if (VEC == 4) {
+      const float4 q = reinterpret_cast<const float4*>(xs)[v];
+      e[0] = q.x; e[VEC > 1 ? 1 : 0] = q.y; e[VEC > 2 ? 2 : 0] = q.z; e[VEC > 3 ? 3 : 0] = q.w;
+    } else {
+      e[0] = xs[v];
+    }
+    const int64_t e0 = v * VEC;
+    int ch = (int)(e0 % C);
+    int64_t cell = e0 / C;
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      o[j] = (ch == tc) ? __fadd_rn(e[j], d) : e[j];
+      if (kxs && ch == kc) {
+        const float u = __fdiv_rn(__fsub_rn(e[j], lo), span);
+        float y = expf(__fadd_rn(__fmul_rn(lr, u), lmin));
+        if (isnan(y) || isinf(y)) y = 0.f;
+        kxs[cell] = y;
+      }
+      if (++ch == C) { ch = 0; ++cell; }
+    }
+    if (x1s) {
+      if (VEC == 4) reinterpret_cast<float4*>(x1s)[v] = make_float4(o[0], o[VEC > 1 ? 1 : 0], o[VEC > 2 ? 2 : 0], o[VEC > 3 ? 3 : 0]);
+      else x1s[v] = o[0];
+    }
+  }
+}
+
+// cotangent of dn: gdn[b] = sum over cells of gx1[b, cell, tc]   (the cotangent of x passes through unchanged)
+template <int CT, int VEC>
+__global__ void __launch_bounds__(256) k_features_bwd(int64_t per_sample, int32_t C_rt, int32_t tc,
+                                                      const float* __restrict__ gx1, float* __restrict__ gdn) {
+  __shared__ double red[32];
+  const int C = CT > 0 ? CT : C_rt;
+  const int b = blockIdx.y;
+  const float* gs = gx1 + (int64_t)b * per_sample;
+  const int64_t nv = per_sample / VEC;
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    float e[VEC];
+    if (VEC == 4) {
+      const float4 q = reinterpret_cast<const float4*>(gs)[v];
+      e[0] = q.x; e[VEC > 1 ? 1 : 0] = q.y; e[VEC > 2 ? 2 : 0] = q.z; e[VEC > 3 ? 3 : 0] = q.w;
+    } else {
+      e[0] = gs[v];
+    }
+    int ch = (int)((v * VEC) % C);
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (ch == tc) part += e[j];
+      if (++ch == C) ch = 0;
+    }
+    acc += (double)part;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (lane == 0) atomicAdd(&gdn[b], (float)t);
+  }
+}
+
 }  // namespace
+
+extern "C" int srm_features_forward(int32_t device, const float* x, const float* dn, int32_t B, int64_t cells, int32_t C,
+                                    int32_t t_channel, int32_t k_channel, float kmin, float kmax, float lo, float hi,
+                                    float* x1_out, float* kx_out, void* stream) {
+  const int64_t per = cells * C;
+  if (B < 1 || B > 65535 || cells < 1 || C < 1 || !x || (!x1_out && !kx_out) || (x1_out && !dn) || t_channel >= C || k_channel >= C) {
+    srm_set_error("srm_features_forward: bad argument (1 <= B <= 65535, channels < C, x1_out needs dn)");
+    return SRM_ERR_INVALID;
+  }
+  const bool vec = per % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x1_out)) & 15u) == 0;
+  if (kx_out && !(kmin > 0.f && kmax > kmin && hi > lo)) { srm_set_error("srm_features_forward: bad normalisation range"); return SRM_ERR_INVALID; }
+  SRM_CUDA_CHECK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const float lr = kx_out ? logf(kmax / kmin) : 0.f, lmin = kx_out ? logf(kmin) : 0.f;
+  const int64_t nv = vec ? per / 4 : per;
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((nv + 255) / 256, 2048)), (unsigned)B);
+  const int kc = kx_out ? k_channel : -1, tc = x1_out ? t_channel : -1;
+  if (C == 5 && vec) k_features<5, 4><<<grid, 256, 0, s>>>(per, C, tc, kc, x, dn, lr, lmin, lo, hi - lo, x1_out, kx_out);
+  else if (vec) k_features<0, 4><<<grid, 256, 0, s>>>(per, C, tc, kc, x, dn, lr, lmin, lo, hi - lo, x1_out, kx_out);
+  else k_features<0, 1><<<grid, 256, 0, s>>>(per, C, tc, kc, x, dn, lr, lmin, lo, hi - lo, x1_out, kx_out);   // ragged rows (39 x 39 x 5)
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+extern "C" int srm_features_backward(int32_t device, const float* gx1, int32_t B, int64_t cells, int32_t C, int32_t t_channel,
+                                     float* gdn, void* stream) {
+  const int64_t per = cells * C;
+  if (B < 1 || B > 65535 || cells < 1 || C < 1 || !gx1 || !gdn || t_channel < 0 || t_channel >= C) {
+    srm_set_error("srm_features_backward: bad argument");
+    return SRM_ERR_INVALID;
+  }
+  const bool vec = per % 4 == 0 && (reinterpret_cast<uintptr_t>(gx1) & 15u) == 0;
+  SRM_CUDA_CHECK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  SRM_CUDA_CHECK(cudaMemsetAsync(gdn, 0, sizeof(float) * B, s));
+  const int64_t nv = vec ? per / 4 : per;
+  // a few CTAs per sample: enough loads in flight when B is small and the grid is large
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nv + 256 * 64 - 1) / (256 * 64), 64));
+  const dim3 grid(gx, (unsigned)B);
+  if (C == 5 && vec) k_features_bwd<5, 4><<<grid, 256, 0, s>>>(per, C, t_channel, gx1, gdn);
+  else if (vec) k_features_bwd<0, 4><<<grid, 256, 0, s>>>(per, C, t_channel, gx1, gdn);
+  else k_features_bwd<0, 1><<<grid, 256, 0, s>>>(per, C, t_channel, gx1, gdn);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
 
 extern "C" int srm_gather_rows(int32_t device, const void* src, const int32_t* idx, int64_t n_idx, int64_t n_rows,
                                int64_t row_bytes, void* dst, void* stream) {

@@ -107,6 +107,34 @@ class SrmPhysics:
         self.launches += 1
         return out
 
+    def features_forward(self, x: torch.Tensor, dn: Optional[torch.Tensor] = None, kx_range=None, lo: float = -1.0,
+                         hi: float = 1.0, t_channel: int = 3, k_channel: int = 4):
+        """one pass over the (B, ..., C) feature tensor: x1 = x with t_norm += dn[b] (if dn is given) and the
+        de-normalised permeability channel (if kx_range = (kmin, kmax) is given).  Returns (x1, kx)."""
+        self._check(x, "x")
+        B, Cc = x.shape[0], x.shape[-1]
+        cells = x.numel() // (B * Cc)
+        x1 = torch.empty_like(x) if dn is not None else None
+        kx = torch.empty(x.shape[:-1], dtype=torch.float32, device=self.device) if kx_range is not None else None
+        if dn is not None:
+            self._check(dn, "dn")
+        kmin, kmax = kx_range if kx_range is not None else (1.0, 2.0)
+        L.check(self.lib, self.lib.srm_features_forward(self.device.index, _ptr(x), _ptr(dn), B, cells, Cc, t_channel, k_channel,
+                                                        kmin, kmax, lo, hi, _ptr(x1), _ptr(kx), self._stream()),
+                "srm_features_forward")
+        self.launches += 1
+        return x1, kx
+
+    def features_backward(self, gx1: torch.Tensor, t_channel: int = 3) -> torch.Tensor:
+        """cotangent of dn: per-sample sum of the time channel of gx1"""
+        self._check(gx1, "gx1")
+        B, Cc = gx1.shape[0], gx1.shape[-1]
+        gdn = torch.empty(B, dtype=torch.float32, device=self.device)
+        L.check(self.lib, self.lib.srm_features_backward(self.device.index, _ptr(gx1), B, gx1.numel() // (B * Cc), Cc, t_channel,
+                                                         _ptr(gdn), self._stream()), "srm_features_backward")
+        self.launches += 1
+        return gdn
+
     # -- glue either side of the physics kernels: HardLayer + per-sample mean of the dt field, both levels ------------
     def glue_forward(self, y0, y1, tn0, tn1, expo=None, dtf1=None, dtf2=None, init_value: float = 1.0,
                      t_lo: float = -1.0, t_hi: float = 1.0):

@@ -70,6 +70,21 @@ class _OptimizerSlot:
         self.optimizer = optimizer
 
 
+class _ShiftTimeFn(torch.autograd.Function):
+    """x1 = x with channel 3 += dn[b]; d/dx = identity, d/d dn[b] = sum of the time channel of the cotangent"""
+
+    @staticmethod
+    def forward(ctx, eng, x, dn):
+        ctx.eng = eng
+        return eng.features_forward(x, dn.detach())[0]
+
+    @staticmethod
+    def backward(ctx, gx1):
+        gx1 = gx1.contiguous()
+        gdn = ctx.eng.features_backward(gx1) if ctx.needs_input_grad[2] else None
+        return None, (gx1 if ctx.needs_input_grad[1] else None), gdn
+
+
 class PhysicsLoss:
     """PhysicsLoss(main_model, pvt_model, time_step_model, well_rate_bhp_model, saturation_model=None,
                    optimizer_model_names_map=...)
@@ -124,11 +139,10 @@ class PhysicsLoss:
         return (self.t_max - self.t_min) * ((tn - self.norm_lo) / (self.norm_hi - self.norm_lo)) + self.t_min
 
     def _shift_time(self, x, dt):
-        """x_n1 = x_n0 with t_norm += normalize_diff(dt)   (physics_loss.py:105-110)"""
+        """x_n1 = x_n0 with t_norm += normalize_diff(dt)   (physics_loss.py:105-110); one CUDA pass over x
+        (srm_features_forward), its cotangent w.r.t. dt by srm_features_backward"""
         dn = (self.norm_hi - self.norm_lo) / (self.t_max - self.t_min) * dt
-        shift = torch.zeros_like(x)
-        shift[..., 3] = dn.view(-1, 1, 1, 1)
-        return x + shift
+        return _ShiftTimeFn.apply(self.engine, x.contiguous(), dn.contiguous())
 
     @staticmethod
     def _params(model):
@@ -142,7 +156,8 @@ class PhysicsLoss:
         eng = self.engine
         x = x.to(eng.device, torch.float32)
         B = x.shape[0]
-        kx = eng.denormalize_log(x[..., 4].contiguous(), self.k_min, self.k_max, self.norm_lo, self.norm_hi)
+        # permeability channel, de-normalised, straight from the feature tensor (no strided copy of the channel)
+        kx = eng.features_forward(x.contiguous(), None, (self.k_min, self.k_max), self.norm_lo, self.norm_hi)[1]
         sample_real = torch.arange(B, dtype=torch.int32, device=eng.device)
         dt1 = self.time_step_model(x).reshape(B, -1).mean(dim=1)                  # physics_loss.py:102
         x1 = self._shift_time(x, dt1)

@@ -439,7 +439,27 @@ def run_ours(args):
             qms = q0.elapsed_time(q1) / gsteps
             glue["batch_gather"] = {"ms": qms, "rows": nb, "row_bytes": rowb, "achieved_GBps": 2.0 * nb * rowb / (qms * 1e-3) / 1e9,
                                     "kernel": "k_gather_rows (srm_gather_rows): x_batch = x_all[batch_inds] on the device-resident data set"}
-            del xs, xo
+            # feature glue on the same rows: x_n1 = x with t_norm += dn[b], de-normalised permeability channel, and
+            # the cotangent of dn (srm_features_forward / _backward): 20 + 20 + 4 B forward, 20 B backward per cell
+            xf = xs.view(nb, spec.n_cells, 5)
+            dnb = torch.rand(nb, device=dev) * 0.01
+
+            def feat():
+                x1f, kxf = eng.features_forward(xf, dnb, (0.26, 24.0))
+                return eng.features_backward(x1f)
+            for _ in range(3):
+                feat()
+            torch.cuda.synchronize(dev)
+            q0.record()
+            for _ in range(gsteps):
+                feat()
+            q1.record()
+            torch.cuda.synchronize(dev)
+            fms = q0.elapsed_time(q1) / gsteps
+            glue["features"] = {"ms": fms, "rows": nb, "alg_bytes_per_cell": 64.0,
+                                "achieved_GBps": nb * spec.n_cells * 64.0 / (fms * 1e-3) / 1e9,
+                                "kernel": "k_features + k_features_bwd (srm_features_forward / srm_features_backward): time-shifted features, permeability channel, d/d dt"}
+            del xs, xo, xf
         except Exception as e:      # never let an auxiliary measurement break the bench line
             glue["batch_gather"] = {"error": repr(e)}
 
@@ -450,6 +470,8 @@ def run_ours(args):
             glue["frac"] = glue["achieved_GBps"] / peak
             if "achieved_GBps" in glue.get("batch_gather", {}):
                 glue["batch_gather"]["frac"] = glue["batch_gather"]["achieved_GBps"] / peak
+            if "achieved_GBps" in glue.get("features", {}):
+                glue["features"]["frac"] = glue["features"]["achieved_GBps"] / peak
         achieved = N * reps * ab / (ms_step * 1e-3) / 1e9   # per GPU (each rank runs N * reps cells per step)
         # roofline of the dominant kernel (the adjoint pass) per the bench contract, with the forward pass and the whole
         # step beside it.  Pass durations are CUDA-event windows on the launching stream over the timed region: the

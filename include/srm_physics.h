@@ -253,6 +253,21 @@ int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_l
 int srm_gather_rows(int32_t device, const void* src, const int32_t* idx, int64_t n_idx, int64_t n_rows,
                     int64_t row_bytes, void* dst, void* stream);
 
+/* Feature-tensor glue of the step.  x is (B, cells, C) fp32 with the channels innermost -- the
+ * reference's (B,D,H,W,5) features [z,y,x,t,k].  One pass over x writes
+ *   x1_out = x with channel t_channel += dn[b]       the time-shifted features of level n+1; the reference builds
+ *            them with zeros_like + strided assign + add (physics_loss.py:105-110), dn = normalize_diff(dt1)
+ *   kx_out[b][cell] = exp(ln(kmax/kmin)*((x[..,k_channel]-lo)/(hi-lo)) + ln kmin)   the de-normalised permeability
+ *            (DataSummary.nonormalize, log branch; same arithmetic as srm_denormalize_log, NaN/Inf -> 0)
+ * Either output may be NULL.  Rows with cells*C a multiple of 4 in 16-byte aligned tensors take the vector path. */
+int srm_features_forward(int32_t device, const float* x, const float* dn, int32_t B, int64_t cells, int32_t C,
+                         int32_t t_channel, int32_t k_channel, float kmin, float kmax, float lo, float hi,
+                         float* x1_out, float* kx_out, void* stream);
+/* Cotangent of dn: gdn[b] = sum over cells of gx1[b][cell][t_channel] (fp64 accumulation); the cotangent of x is gx1
+ * itself. */
+int srm_features_backward(int32_t device, const float* gx1, int32_t B, int64_t cells, int32_t C, int32_t t_channel,
+                          float* gdn, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -183,3 +183,44 @@ def test_glue_against_the_reference_hard_layer_class():
     assert U.rel_to_max(gy0.cpu().numpy(), g["gy"]) < 1e-5 and U.rel_to_max(gexpo.cpu().numpy(), g["gexpo"]) < 1e-5
     assert not gy1.any()
     eng.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 6, 8, 5), (4, 1, 39, 39, 5), (2, 2, 5, 6, 7)])   # vector rows, ragged rows (39 x 39 x 5), C != 5
+def test_feature_glue_time_shift_and_permeability_channel(shape):
+    """srm_features_forward / _backward against the reference's torch-side construction (physics_loss.py:105-110:
+    zeros_like + strided assign + add) and against srm_denormalize_log on the strided channel: bit for bit."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=8, H=6, D=2, T=2, K=1, seed=5)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand(shape, generator=g, device="cuda") * 2.0 - 1.0
+    dn = torch.rand(shape[0], generator=g, device="cuda") * 0.05
+    tc, kc = 3, 4
+    x1, kx = eng.features_forward(x, dn, (0.26, 24.0), -1.0, 1.0, t_channel=tc, k_channel=kc)
+    shift = torch.zeros_like(x)
+    shift[..., tc] = dn.view(-1, 1, 1, 1)
+    assert torch.equal(x1, x + shift)
+    assert torch.equal(kx, eng.denormalize_log(x[..., kc].contiguous(), 0.26, 24.0, -1.0, 1.0))
+    assert eng.features_forward(x, None, (0.26, 24.0))[0] is None           # permeability only
+    gx1 = torch.randn(shape, generator=g, device="cuda")
+    gdn = eng.features_backward(gx1, t_channel=tc)
+    ref = gx1[..., tc].double().sum(dim=(1, 2, 3)).float()
+    assert torch.allclose(gdn, ref, rtol=1e-5, atol=1e-6)
+    eng.close()
+
+
+def test_shift_time_autograd_function_matches_torch():
+    _ShiftTimeFn = srm.physics_loss._ShiftTimeFn
+    ocfg, otab, spec, ptab, batch = U.make_case(W=8, H=6, D=2, T=2, K=1, seed=5)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = (torch.rand((3, 2, 6, 8, 5), generator=g, device="cuda") * 2 - 1).requires_grad_(True)
+    dn = (torch.rand(3, generator=g, device="cuda") * 0.05).requires_grad_(True)
+    wgt = torch.randn((3, 2, 6, 8, 5), generator=g, device="cuda")
+    (_ShiftTimeFn.apply(eng, x, dn) * wgt).sum().backward()
+    gx, gdn = x.grad.clone(), dn.grad.clone()
+    x.grad = None; dn.grad = None
+    shift = torch.zeros_like(x)
+    idx = torch.zeros(5, device="cuda"); idx[3] = 1.0
+    ((x + dn.view(-1, 1, 1, 1, 1) * idx) * wgt).sum().backward()
+    assert torch.equal(gx, x.grad) and torch.allclose(gdn, dn.grad, rtol=1e-5, atol=1e-6)
+    eng.close()
