@@ -185,7 +185,7 @@ def test_glue_against_the_reference_hard_layer_class():
     eng.close()
 
 
-@pytest.mark.parametrize("shape", [(3, 2, 6, 8, 5), (4, 1, 39, 39, 5), (2, 2, 5, 6, 7)])   # vector rows, ragged rows (39 x 39 x 5), C != 5
+@pytest.mark.parametrize("shape", [(3, 2, 6, 8, 5), (4, 1, 39, 39, 5), (2, 2, 5, 6, 7), (2, 1, 4, 4, 3)])   # vector rows, ragged rows (39 x 39 x 5), C != 5, C < 4
 def test_feature_glue_time_shift_and_permeability_channel(shape):
     """srm_features_forward / _backward against the reference's torch-side construction (physics_loss.py:105-110:
     zeros_like + strided assign + add) and against srm_denormalize_log on the strided channel: bit for bit."""
@@ -194,13 +194,13 @@ def test_feature_glue_time_shift_and_permeability_channel(shape):
     g = torch.Generator(device="cuda").manual_seed(3)
     x = torch.rand(shape, generator=g, device="cuda") * 2.0 - 1.0
     dn = torch.rand(shape[0], generator=g, device="cuda") * 0.05
-    tc, kc = 3, 4
+    tc, kc = (3, 4) if shape[-1] >= 5 else (1, 2)
     x1, kx = eng.features_forward(x, dn, (0.26, 24.0), -1.0, 1.0, t_channel=tc, k_channel=kc)
     shift = torch.zeros_like(x)
     shift[..., tc] = dn.view(-1, 1, 1, 1)
     assert torch.equal(x1, x + shift)
     assert torch.equal(kx, eng.denormalize_log(x[..., kc].contiguous(), 0.26, 24.0, -1.0, 1.0))
-    assert eng.features_forward(x, None, (0.26, 24.0))[0] is None           # permeability only
+    assert eng.features_forward(x, None, (0.26, 24.0), t_channel=tc, k_channel=kc)[0] is None   # permeability only
     gx1 = torch.randn(shape, generator=g, device="cuda")
     gdn = eng.features_backward(gx1, t_channel=tc)
     ref = gx1[..., tc].double().sum(dim=(1, 2, 3)).float()
