@@ -10,10 +10,12 @@
 //
 // Numerics: the reference's fp32 op order, explicitly rounded (no FMA contraction) in every forward
 // quantity, as in kernels_ref.cu; tf.pow with the integer Corey exponents is the left-to-right product the
-// oracle pins.  One thread per cell; PVT and the per-cell products are staged through the workspace
-// (SRM_GC_NFIELDS fields), neighbours re-read through L1/L2.  With SrmConfig.pvt_lut the stage kernel gathers
-// the PVT packs from the exact per-pressure table instead of evaluating the 37-term spline of 7 properties per
-// cell; the residual kernels are not fused yet (the dry-gas path's kernels_ref2.cu shows the next step).
+// oracle pins.  Two pipelines with the same per-cell arithmetic:
+//   staged   k_stage_gc writes the PVT packs and per-cell products to the workspace (SRM_GC_NFIELDS fields; from the
+//            exact per-pressure table where it covers the pressure, else the 37-term spline of 7 properties), the
+//            residual kernels march z-columns and re-read the fields of six neighbours through L1/L2
+//   fused    gc_fused.cuh (table over the whole clamp range): tile + halo in shared memory, gathers in-kernel, no
+//            staged fields
 #include <math_constants.h>
 #include <cstring>
 #include <cstdlib>
