@@ -292,3 +292,28 @@ def test_gc_full_grid_fused_equals_staged_and_is_additive(monkeypatch):
     assert torch.allclose(a[1], f[1], rtol=1e-6)
     for name, x, y in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1", "gdt2"), a[2], f[2]):
         assert torch.allclose(x, y, rtol=1e-5, atol=1e-6 * max(float(x.abs().max()), 1e-30)), name
+
+
+def test_gc_fused_pair_repeats_bit_for_bit():
+    """A shared-memory hazard in the plane pipeline of csrc/gc_fused.cuh (double-buffered tile + halo ring, cp.async
+    halo gathers, one barrier per plane) would show as run-to-run differences under load: 25 repeats on BASELINE
+    config 4's grid give the same residual field and the same atomic-free gradient fields, bit for bit."""
+    W, H, D, T, K = 128, 128, 32, 12, 2
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=[], fluid_type="GC")
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.GC_PROPERTIES, order=1)
+    b = srm.synth.make_batch(W, H, D, T, K, [(32, 32), (96, 96)], seed=405, device="cuda")
+    d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
+    d["sg0"], d["sg1"], d["so0"], d["so1"] = srm.synth.make_saturations(b, seed=405)
+    w = torch.tensor(W_ALL, dtype=torch.float32, device="cuda")
+    eng = srm.SrmPhysics(spec, tabs, device=0, pvt_lut=True)
+    ref = None
+    for _ in range(25):
+        dom = eng.forward_gc(want_dom=True, **d)["dom"]
+        g = eng.backward_gc(dterms=w, **d)
+        cur = [dom.clone()] + [t.clone() for t in g[:6]]
+        if ref is None:
+            ref = cur
+        else:
+            for i, (a, c) in enumerate(zip(ref, cur)):
+                assert torch.equal(a.view(torch.int32), c.view(torch.int32)), i
+    eng.close()
