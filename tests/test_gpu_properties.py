@@ -144,3 +144,29 @@ def test_graphed_step_replays_the_eager_step(W):
         for name, a, b in zip(("gp0", "gp1", "gdt1", "gdt2"), grads, g):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max())), name
     eng.close()
+
+
+def test_lean_pair_at_full_size_equals_the_per_cell_path_and_repeats(cfg2):
+    """The headline kernels (kernels_dg4.cu: exact table, z-marching tiles, split barrier) at BASELINE config 2's full
+    size: residual field bit-identical to the per-cell spline path (no table, no tiles), gradients equal to rounding,
+    and 20 repeats under load return the same bits (a hazard in the plane pipeline would show as run-to-run noise)."""
+    eng0, d = cfg2
+    w = torch.tensor(U.WEIGHTS, device="cuda")
+    fw0 = eng0.forward(want_dom=True, **d)
+    g0 = [t.clone() for t in eng0.backward(dterms=w, **d)]
+    dom0 = fw0["dom"].clone()
+    eng = srm.SrmPhysics(eng0.spec, eng0.tables, device=0, pvt_lut=True)
+    ref = None
+    for _ in range(20):
+        dom = eng.forward(want_dom=True, **d)["dom"]
+        g = eng.backward(dterms=w, **d)
+        cur = [dom.clone(), g[0].clone()]                # dom and gp0 carry no atomics
+        if ref is None:
+            ref = cur + [g[1].clone(), g[2].clone()]
+        else:
+            for i, (a, c) in enumerate(zip(ref, cur)):
+                assert torch.equal(a.view(torch.int32), c.view(torch.int32)), i
+    assert torch.equal(ref[0].view(torch.int32), dom0.view(torch.int32))
+    for name, a, b in zip(("gp0", "gp1", "gdt1"), (ref[1], ref[2], ref[3]), g0):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max())), name
+    eng.close()
