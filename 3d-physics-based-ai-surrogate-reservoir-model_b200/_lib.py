@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SRM_PHYSICS_LIB: kernel-tuning experiments load an alternative build of the same library
 LIB_PATH = os.environ.get("SRM_PHYSICS_LIB") or os.path.join(_HERE, "libsrm_physics.so")
 
-SRM_ABI_VERSION = 2
+SRM_ABI_VERSION = 3
 SRM_N_TERMS = 8
 TERM_NAMES = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
 SRM_FLUID_DG, SRM_FLUID_GC = 0, 1
@@ -88,7 +88,7 @@ def load_library(path: Optional[str] = None):
     lib.srm_pvt_eval.restype = C.c_int
     lib.srm_pvt_eval.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.srm_denormalize_log.restype = C.c_int
-    lib.srm_denormalize_log.argtypes = [i64, vp, fp, fp, fp, fp, vp, vp]
+    lib.srm_denormalize_log.argtypes = [i32, i64, vp, fp, fp, fp, fp, vp, vp]
     lib.srm_selftest_rounding.restype = C.c_int
     lib.srm_selftest_rounding.argtypes = [i32, i64, C.c_uint64, C.POINTER(C.c_int64), vp]
     lib.srm_wells.restype = C.c_int
@@ -108,7 +108,7 @@ def load_library(path: Optional[str] = None):
     lib.srm_glue_forward.restype = C.c_int
     lib.srm_glue_forward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 11 + [vp, C.c_size_t, vp]
     lib.srm_glue_backward.restype = C.c_int
-    lib.srm_glue_backward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 14 + [vp]
+    lib.srm_glue_backward.argtypes = [vp, i32, fp, fp, fp] + [vp] * 16 + [vp]
     lib.srm_gather_rows.restype = C.c_int
     lib.srm_gather_rows.argtypes = [i32, vp, vp, i64, i64, i64, vp, vp]
     lib.srm_features_forward.restype = C.c_int

@@ -198,11 +198,12 @@ int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, floa
   return srm_launch_pvt_eval_ref(h, n, p, val, dval, (cudaStream_t)stream);
 }
 
-int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi, float* out, void* stream) {
+int srm_denormalize_log(int32_t device, int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi, float* out, void* stream) {
   if (n < 0 || (n > 0 && (!x_norm || !out)) || !(kmin > 0.f) || !(kmax > kmin) || !(hi > lo)) {
     srm_set_error("srm_denormalize_log: bad argument");
     return SRM_ERR_INVALID;
   }
+  SRM_CUDA_CHECK(cudaSetDevice(device));
   return srm_launch_denorm_log(n, x_norm, kmin, kmax, lo, hi, out, (cudaStream_t)stream);
 }
 
@@ -282,9 +283,7 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
   if (rc) return rc;
   if (qw_out && h->dev.n_wells) { rc = srm_launch_unsort_wells(h, B, ws.qw, qw_out, s); if (rc) return rc; }
   if (pwfw_out && h->dev.n_wells) { rc = srm_launch_unsort_wells(h, B, ws.pwfw, pwfw_out, s); if (rc) return rc; }
-  if (save) {
-    h->st_ws = workspace; h->st_p0 = p0; h->st_p1 = p1; h->st_kx = kx; h->st_B = B; h->st_valid = 1;
-  }
+  if (save) srm_state_set(h, B, R, workspace, kx, sample_real, p0, p1, nullptr, nullptr, nullptr, nullptr, dt1, dt2, t1);
   return SRM_OK;
 }
 
@@ -307,10 +306,11 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
   }
   SRM_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const bool have = h->st_valid && h->st_ws == workspace && h->st_p0 == p0 && h->st_p1 == p1 && h->st_kx == kx && h->st_B == B;
+  const bool have = srm_state_is(h, B, R, workspace, kx, sample_real, p0, p1, nullptr, nullptr, nullptr, nullptr, dt1, dt2, t1);
   const int mode = srm_ws_mode(h);
   const bool cf = mode == SRM_WS_CF;
   if (!have) {
+    h->st_valid = 0;
     // recompute the forward state (PVT stage with derivatives, wells, residual field) into the workspace
     float* terms_tmp = nullptr;
     SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
@@ -319,6 +319,8 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
             : srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
     cudaFreeAsync(terms_tmp, s);
     if (rc) return rc;
+    // the workspace now holds THIS call's forward state (it overwrote whatever forward was saved there before)
+    srm_state_set(h, B, R, workspace, kx, sample_real, p0, p1, nullptr, nullptr, nullptr, nullptr, dt1, dt2, t1);
   }
   rc = cf ? srm_backward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
        : mode == SRM_WS_REF_FUSED ? srm_backward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, gp0, gp1, gdt1, gdt2, ws, s)
@@ -356,7 +358,7 @@ int srm_forward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const in
       for (int X = 0; X < 4; ++X) { rc = srm_launch_unsort_wells(h, B, ws.gc_wells + X * wt, q4w_out + X * wt, s); if (rc) return rc; }
     if (pwfw_out) { rc = srm_launch_unsort_wells(h, B, ws.pwfw, pwfw_out, s); if (rc) return rc; }
   }
-  if (save) { h->st_ws = workspace; h->st_p0 = p0; h->st_p1 = p1; h->st_kx = kx; h->st_B = B; h->st_valid = 1; }
+  if (save) srm_state_set(h, B, R, workspace, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1);
   return SRM_OK;
 }
 
@@ -381,13 +383,15 @@ int srm_backward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
   }
   SRM_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const bool have = h->st_valid && h->st_ws == workspace && h->st_p0 == p0 && h->st_p1 == p1 && h->st_kx == kx && h->st_B == B;
+  const bool have = srm_state_is(h, B, R, workspace, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1);
   if (!have) {
+    h->st_valid = 0;
     float* terms_tmp = nullptr;
     SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
     rc = srm_forward_gc_impl(h, B, R, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
     cudaFreeAsync(terms_tmp, s);
     if (rc) return rc;
+    srm_state_set(h, B, R, workspace, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1);
   }
   return srm_backward_gc_impl(h, B, R, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms, gp0, gp1, gsg0, gsg1,
                               gso0, gso1, gdt1, gdt2, ws, s);

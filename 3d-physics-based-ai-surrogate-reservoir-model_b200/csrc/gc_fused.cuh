@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   const int b = blockIdx.y;
   const int HW = P.H * P.W;
   const G2Geom g = g2_geom(P, A.tiles_x);
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const float4* __restrict__ T0 = reinterpret_cast<const float4*>(P.lutf0);
   const float4* __restrict__ T1 = reinterpret_cast<const float4*>(P.lutf1);
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // dom^2, ibc^2, trn^2, sum mg cells, sum mo cells, sum qg, sum qo
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const int b = blockIdx.y;
   const int HW = P.H * P.W;
   const G2Geom g = g2_geom(P, A.tiles_x);
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   double acc2[2] = {0.0, 0.0};
   const int64_t base = (int64_t)b * P.N;
   const float* __restrict__ P1 = A.p1 + base;
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(128) k_ibc_adj_gc2(const __grid_constant__ Srm
   }
   const float s = 2.f * A.dterms[SRM_TERM_IBC] * mask * mask * A.divqw[g];
   if (s == 0.f) return;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const int64_t base = (int64_t)b * P.N;
   const CellIdx ix = cell_index(P, c);
   float ckf[6];

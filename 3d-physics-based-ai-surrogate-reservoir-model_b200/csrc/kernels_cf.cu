@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(1024) k_group_samples(int32_t B, int32_t R, co
   __shared__ int32_t s_key[1024];
   __shared__ int32_t s_scan[1024];
   const int tid = threadIdx.x;
-  auto key_of = [&](int b) { return sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B); };
+  auto key_of = [&](int b) { return srm_real_of(sample_real, b, B, R); };
   for (int r = tid; r <= R; r += 1024) cnt[r] = 0;
   for (int r = tid; r < R; r += 1024) fill[r] = 0;
   __syncthreads();
@@ -814,7 +814,7 @@ __global__ void __launch_bounds__(128) k_ibc_adj_cf(const __grid_constant__ SrmD
   for (int u = w; u < nw && P.wells[u].cell == c; ++u) { mask += 1.f; dq += dqdp[(int64_t)b * nw + u]; }
   const float s = 2.f * dterms[SRM_TERM_IBC] * mask * mask * divqw[g];
   if (s == 0.f) return;
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   const int64_t base = (int64_t)b * P.N;
   const float* kr = kx + (int64_t)r * P.N;
   const int i = c % P.W, j = (c / P.W) % P.H, k = c / (P.W * P.H), HW = P.H * P.W;

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
   __shared__ __align__(8) uint64_t s_bar;
   const Tile4 t = make_tile4(P, A.tiles_x);
   const int b = blockIdx.y;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   if (threadIdx.x == 0) mbar_init(&s_bar, NT / 32);
   __syncthreads();
   const bool has_well = (P.n_wells > 0) ? thread_has_well4(P, t, s_flag) : false;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
   __shared__ __align__(8) uint64_t s_bar;
   const Tile4 t = make_tile4(P, A.tiles_x);
   const int b = blockIdx.y;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   if (threadIdx.x == 0) mbar_init(&s_bar, NT / 32);
   __syncthreads();
   const bool has_well = (P.n_wells > 0) ? thread_has_well4(P, t, s_flag) : false;

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NT5, 1) k_fwd5(const __grid_constant__ SrmDev 
     const int xcl = min(x, W - 4), ycl = min(y, H - 1);
     const bool edgeE = xcl + 4 >= W;
     const int oc = ycl * W + xcl;
-    const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+    const int r = srm_real_of(A.sample_real, b, A.B, A.R);
     const FaceLay FL = face_layout(D, H, W);
     float* __restrict__ domf = A.dom + (int64_t)b * P.N;
     const float* __restrict__ FB = A.faces + (int64_t)r * FL.per_real;      // [FE | FN | FU]

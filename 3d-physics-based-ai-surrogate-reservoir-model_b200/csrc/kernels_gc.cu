@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev
   if (g >= tot) return;
   const int b = (int)(g / nw), w = (int)(g % nw);
   const WellDev wd = P.wells[w];
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   const float k = kx[(int64_t)r * P.N + wd.cell];
   const float pv = pfield[(int64_t)b * P.N + wd.cell], sv = sgfield[(int64_t)b * P.N + wd.cell];
   const float t = t_days[b];
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_resid_fwd_gc(const __grid_const
   const int b = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = P.H * P.W;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const int64_t total = (int64_t)A.B * P.N;
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};   // dom^2, ibc^2, trn^2, sum mg cells, sum mo cells, sum qg, sum qo
   if (col < HW) {
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_resid_adj_gc(const __grid_const
   const int b = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = P.H * P.W;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const int64_t total = (int64_t)A.B * P.N;
   double acc2[2] = {0.0, 0.0};
   if (col < HW) {
@@ -743,7 +743,7 @@ __global__ void __launch_bounds__(128) k_ibc_adj_gc(const __grid_constant__ SrmD
   }
   const float s = 2.f * A.dterms[SRM_TERM_IBC] * mask * mask * A.divqw[g];
   if (s == 0.f) return;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const int64_t total = (int64_t)A.B * P.N, base = (int64_t)b * P.N;
   auto F = [&](int f, int cell) { return A.F[(int64_t)f * total + base + cell]; };
   const CellIdx ix = cell_index(P, c);

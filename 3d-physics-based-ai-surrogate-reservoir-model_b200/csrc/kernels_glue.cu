@@ -27,6 +27,12 @@ __device__ __forceinline__ GlueLevel glue_level(float tn, float t_lo, float t_hi
   g.lnat = (g.at > 0.f) ? (float)log((double)g.at) : 0.f;     // tf pow gradient: log of the safe base
   return g;
 }
+// d(alpha_t ^ e) / d alpha_t = e * alpha_t^(e-1), as tf.pow's gradient forms it (a = alpha_t ^ e)
+__device__ __forceinline__ float glue_dpow(const GlueLevel& g, float a, float e) {
+  if (g.at > 0.f) return __fdiv_rn(e * a, g.at);
+  if (g.at == 0.f) return (e > 1.f) ? 0.f : ((e == 1.f) ? 1.f : CUDART_INF_F);
+  return e * powf(g.at, e - 1.f);
+}
 // alpha_t ^ e
 __device__ __forceinline__ float glue_pow(const GlueLevel& g, float e) {
   if (g.at == 0.f) return (e > 0.f) ? 0.f : ((e == 0.f) ? 1.f : CUDART_INF_F);
@@ -47,8 +53,10 @@ __global__ void __launch_bounds__(GT) k_glue_fwd(int64_t N, float init_value, fl
   const GlueLevel g0 = glue_level(tn0[b], t_lo, t_hi), g1 = glue_level(tn1[b], t_lo, t_hi);
   const int64_t base = (int64_t)b * N;
   float s1 = 0.f, s2 = 0.f;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(expo) | reinterpret_cast<uintptr_t>(y0) | reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(p0) |
+                      reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(dtf1) | reinterpret_cast<uintptr_t>(dtf2)) & 15u) == 0;
   for (int64_t c = ((int64_t)blockIdx.x * GT + threadIdx.x) * 4; c < N; c += (int64_t)gridDim.x * GT * 4) {
-    if (c + 3 < N && (N & 3) == 0) {
+    if (c + 3 < N && (N & 3) == 0 && al16) {
       const float4 e = expo ? __ldg(reinterpret_cast<const float4*>(expo + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
       const float4 a = __ldcs(reinterpret_cast<const float4*>(y0 + base + c));
       const float4 bb = __ldcs(reinterpret_cast<const float4*>(y1 + base + c));
@@ -94,12 +102,18 @@ __global__ void __launch_bounds__(GT) k_glue_bwd(int32_t B, int64_t N, float t_l
                                                  const float* __restrict__ gp0, const float* __restrict__ gp1,
                                                  const float* __restrict__ gdt1, const float* __restrict__ gdt2,
                                                  float* __restrict__ gy0, float* __restrict__ gy1, float* __restrict__ gexpo,
-                                                 float* __restrict__ gdtf1, float* __restrict__ gdtf2) {
+                                                 float* __restrict__ gdtf1, float* __restrict__ gdtf2,
+                                                 float* __restrict__ gtn0, float* __restrict__ gtn1) {
+  __shared__ float tred[2][GT / 32];
   const int64_t c = ((int64_t)blockIdx.x * GT + threadIdx.x) * 4;
-  if (c >= N) return;
+  const bool want_t = gtn0 != nullptr || gtn1 != nullptr;      // block-uniform: every thread stays for the reduction
+  if (c >= N && !want_t) return;
   const int b0 = blockIdx.y * SB, b1 = min(b0 + SB, B);
-  const bool vec = (c + 3 < N) && (N & 3) == 0;
-  const int nc = vec ? 4 : (int)min((int64_t)4, N - c);
+  const bool vec = (c + 3 < N) && (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(y0) | reinterpret_cast<uintptr_t>(y1) | reinterpret_cast<uintptr_t>(gp0) |
+                    reinterpret_cast<uintptr_t>(gp1) | reinterpret_cast<uintptr_t>(gy0) | reinterpret_cast<uintptr_t>(gy1) |
+                    reinterpret_cast<uintptr_t>(gdtf1) | reinterpret_cast<uintptr_t>(gdtf2)) & 15u) == 0;
+  const int nc = c >= N ? 0 : (vec ? 4 : (int)min((int64_t)4, N - c));
+  const float inv_span = 1.0f / (t_hi - t_lo);
   float e[4] = {1.f, 1.f, 1.f, 1.f}, ge[4] = {0.f, 0.f, 0.f, 0.f};
   if (expo) { _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) e[q] = expo[c + q]; }
   const float invN = 1.0f / (float)N;
@@ -115,13 +129,32 @@ __global__ void __launch_bounds__(GT) k_glue_bwd(int32_t B, int64_t N, float t_l
     } else {
       _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) { ya[q] = y0[o + q]; yb[q] = y1[o + q]; ga[q] = gp0[o + q]; gb[q] = gp1[o + q]; }
     }
+    float ta = 0.f, tb = 0.f;       // d/d tn_l of -alpha_t^e * y = -y * e * alpha_t^(e-1) / (t_hi - t_lo), summed over this thread's cells
     _Pragma("unroll") for (int q = 0; q < 4; ++q) if (q < nc) {
       const float a0 = glue_pow(g0, e[q]), a1 = glue_pow(g1, e[q]);
       ra[q] = -a0 * ga[q];
       rb[q] = -a1 * gb[q];
       // d/d expo of -alpha_t^e * y = -y * alpha * ln(alpha_t)
       ge[q] = fmaf(ra[q] * ya[q], g0.lnat, fmaf(rb[q] * yb[q], g1.lnat, ge[q]));
+      if (want_t) {
+        ta = fmaf(-ga[q] * ya[q], glue_dpow(g0, a0, e[q]), ta);
+        tb = fmaf(-gb[q] * yb[q], glue_dpow(g1, a1, e[q]), tb);
+      }
     }
+    if (want_t) {        // Hard_Layer_Subclassed.py:219-228: the layer's time input is differentiable (physics_loss.py:105-111)
+      _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) { ta += __shfl_down_sync(0xffffffffu, ta, o); tb += __shfl_down_sync(0xffffffffu, tb, o); }
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      __syncthreads();
+      if (lane == 0) { tred[0][warp] = ta; tred[1][warp] = tb; }
+      __syncthreads();
+      if (threadIdx.x < 2) {
+        float t = 0.f;
+        _Pragma("unroll") for (int w = 0; w < GT / 32; ++w) t += tred[threadIdx.x][w];
+        float* dst = threadIdx.x == 0 ? gtn0 : gtn1;
+        if (dst) atomicAdd(&dst[b], t * inv_span);
+      }
+    }
+    if (nc == 0) continue;
     const float d1 = gdt1 ? gdt1[b] * invN : 0.f, d2 = gdt2 ? gdt2[b] * invN : 0.f;
     if (vec) {
       __stcs(reinterpret_cast<float4*>(gy0 + o), make_float4(ra[0], ra[1], ra[2], ra[3]));
@@ -169,7 +202,7 @@ extern "C" int srm_glue_forward(const SrmHandle* h, int32_t B, float init_value,
 extern "C" int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
                                  const float* tn0, const float* tn1, const float* y0, const float* y1, const float* gp0,
                                  const float* gp1, const float* gdt1, const float* gdt2, float* gy0, float* gy1,
-                                 float* gexpo, float* gdtf1, float* gdtf2, void* stream) {
+                                 float* gexpo, float* gdtf1, float* gdtf2, float* gtn0, float* gtn1, void* stream) {
   (void)init_value;
   if (!h || B < 1 || B > 65535 || !tn0 || !tn1 || !y0 || !y1 || !gp0 || !gp1 || !gy0 || !gy1 || !(t_hi > t_lo)) { srm_set_error("srm_glue_backward: bad argument"); return SRM_ERR_INVALID; }
   if ((gdtf1 != nullptr) != (gdt1 != nullptr) || (gdtf2 != nullptr) != (gdt2 != nullptr)) { srm_set_error("srm_glue_backward: gdtf_l and gdt_l go together"); return SRM_ERR_INVALID; }
@@ -177,8 +210,10 @@ extern "C" int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t N = h->dev.N;
   if (gexpo) SRM_CUDA_CHECK(cudaMemsetAsync(gexpo, 0, sizeof(float) * (size_t)N, s));
+  if (gtn0) SRM_CUDA_CHECK(cudaMemsetAsync(gtn0, 0, sizeof(float) * (size_t)B, s));
+  if (gtn1) SRM_CUDA_CHECK(cudaMemsetAsync(gtn1, 0, sizeof(float) * (size_t)B, s));
   const dim3 grid((unsigned)((N / 4 + GT) / GT), (unsigned)((B + SB - 1) / SB));
-  k_glue_bwd<<<grid, GT, 0, s>>>(B, N, t_lo, t_hi, expo, tn0, tn1, y0, y1, gp0, gp1, gdt1, gdt2, gy0, gy1, gexpo, gdtf1, gdtf2);
+  k_glue_bwd<<<grid, GT, 0, s>>>(B, N, t_lo, t_hi, expo, tn0, tn1, y0, y1, gp0, gp1, gdt1, gdt2, gy0, gy1, gexpo, gdtf1, gdtf2, gtn0, gtn1);
   SRM_CUDA_CHECK(cudaGetLastError());
   return SRM_OK;
 }

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_fwd_ref(
   __shared__ double red[4 * 32];
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   double acc4[4] = {0.0, 0.0, 0.0, 0.0};   // dom^2, ibc^2, tde^2, mb_cells
   if (c < P.N) {
     const int64_t base = (int64_t)b * P.N;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) k_resid_adj_ref(
   __shared__ double red[2 * 32];
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   double acc2[2] = {0.0, 0.0};
   if (c < P.N) {
     const int64_t base = (int64_t)b * P.N;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref(
   const float w_ibc = dterms[SRM_TERM_IBC];
   const float s = 2.f * w_ibc * mask * mask * divqw[g];
   if (s == 0.f) return;
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   const int64_t base = (int64_t)b * P.N;
   const float* kr = kx + (int64_t)r * P.N;
   const CellIdx ix = cell_index(P, c);

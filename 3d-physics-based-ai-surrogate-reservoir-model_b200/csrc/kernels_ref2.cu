@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_ref2(const __grid_constant__ SrmD
   __shared__ unsigned char s_flag[NT];
   const Tile t = make_tile(P, A.tiles_x);
   const int b = blockIdx.y;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const bool has_well = (P.n_wells > 0) ? column_has_well(P, t, s_flag) : false;
   const int W = P.W, H = P.H, D = P.D, HW = H * W;
   const FaceLay FL = face_layout(D, H, W);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(NT, 2) k_adj_ref2(const __grid_constant__ SrmD
   __shared__ unsigned char s_flag[NT];
   const Tile t = make_tile(P, A.tiles_x);
   const int b = blockIdx.y;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const bool has_well = (P.n_wells > 0) ? column_has_well(P, t, s_flag) : false;
   const int W = P.W, H = P.H, D = P.D, HW = H * W;
   const FaceLay FL = face_layout(D, H, W);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
   for (int u = w; u < nw && P.wells[u].cell == c; ++u) { mask += 1.f; dq += A.dqdp[(int64_t)b * nw + u]; }
   const float s = 2.f * A.dterms[SRM_TERM_IBC] * mask * mask * A.divqw[g];
   if (s == 0.f) return;
-  const int r = A.sample_real ? A.sample_real[b] : (int)(((int64_t)b * A.R) / A.B);
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const int W = P.W, H = P.H, D = P.D, HW = H * W;
   const FaceLay FL = face_layout(D, H, W);
   const float* FE = A.faces + (int64_t)r * FL.per_real;

@@ -58,6 +58,14 @@ struct SrmDev {
   int32_t cp_safe;       // every tabulated |cp| lies in [2^-60, 2^60]: division by dt1 needs no per-cell range test
 };
 
+// realisation of sample b: the caller's map clamped into [0, R) (an index outside it must not become an out-of-bounds
+// read of kx / the face coefficients), or realisation-major equal-sized groups without a map
+__host__ __device__ __forceinline__ int srm_real_of(const int32_t* __restrict__ sample_real, int b, int B, int R) {
+  if (!sample_real) return (int)(((int64_t)b * R) / B);
+  const int r = sample_real[b];
+  return r < 0 ? 0 : (r >= R ? R - 1 : r);
+}
+
 // Closed-form (piecewise-linear) tables for SRM_NUMERICS_CLOSED_FORM, device global memory
 // (copied to shared memory by the tiled kernels).
 //   interval k in [0, n]: k = number of knots <= x;  value_q(x) = f0[q][k] + slope[q][k]*(x - x0[k])
@@ -87,10 +95,26 @@ struct SrmHandle {
   int gc_fused;        // gas condensate: the fused pair (gc_fused.cuh) runs, no staged fields in the workspace
   int device;
   int sm_count;
-  // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD)
-  const void* st_ws; const void* st_p0; const void* st_p1; const void* st_kx;
-  int32_t st_B; int32_t st_valid;
+  // fingerprint of the forward state held in a workspace (SRM_FLAG_SAVE_FOR_BACKWARD): every input pointer of the
+  // call that produced it (dry gas leaves the saturation slots null), so a backward on other inputs recomputes
+  const void* st_ptr[13];    // ws, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, spare
+  int32_t st_B, st_R; int32_t st_valid;
 };
+static inline void srm_state_set(SrmHandle* h, int32_t B, int32_t R, const void* ws, const void* kx, const void* sr, const void* p0,
+                                 const void* p1, const void* sg0, const void* sg1, const void* so0, const void* so1,
+                                 const void* dt1, const void* dt2, const void* t1) {
+  const void* v[13] = {ws, kx, sr, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, nullptr};
+  for (int i = 0; i < 13; ++i) h->st_ptr[i] = v[i];
+  h->st_B = B; h->st_R = R; h->st_valid = 1;
+}
+static inline bool srm_state_is(const SrmHandle* h, int32_t B, int32_t R, const void* ws, const void* kx, const void* sr, const void* p0,
+                                const void* p1, const void* sg0, const void* sg1, const void* so0, const void* so1,
+                                const void* dt1, const void* dt2, const void* t1) {
+  const void* v[13] = {ws, kx, sr, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, nullptr};
+  if (!h->st_valid || h->st_B != B || h->st_R != R) return false;
+  for (int i = 0; i < 13; ++i) if (h->st_ptr[i] != v[i]) return false;
+  return true;
+}
 
 // ---- workspace carving ------------------------------------------------------------------
 #define SRM_MAXR 65536

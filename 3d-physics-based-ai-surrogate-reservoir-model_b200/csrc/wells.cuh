@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) k_wells(const __grid_constant__ SrmDev P,
   if (g >= (int64_t)B * nw) return;
   const int b = (int)(g / nw), w = (int)(g % nw);
   const WellDev wd = P.wells[w];
-  const int r = sample_real ? sample_real[b] : (int)(((int64_t)b * R) / B);
+  const int r = srm_real_of(sample_real, b, B, R);
   const float k = kx[(int64_t)r * P.N + wd.cell];
   const Dual p = dmk(pfield[(int64_t)b * P.N + wd.cell], 1.0f);
   // shut-in mask: 1 unless shut_start <= t <= shut_stop          welldata_processor.py:349-354

@@ -81,12 +81,39 @@ class SrmPhysics:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def workspace_bytes(self, B: int, R: int) -> int:
+        return int(self.lib.srm_workspace_bytes(self._h, B, R, L.SRM_FLAG_SAVE_FOR_BACKWARD))
+
+    def new_workspace(self, B: int, R: int) -> torch.Tensor:
+        """a workspace the caller owns (pass it as ws= to forward / backward): CUDA graphs and pipelines keep theirs"""
+        return torch.empty(self.workspace_bytes(B, R), dtype=torch.uint8, device=self.device)
+
     def workspace(self, B: int, R: int) -> torch.Tensor:
+        """the engine's own cached workspace, re-allocated when the batch shape changes"""
         if self._ws is None or self._ws_B != (B, R):
-            n = self.lib.srm_workspace_bytes(self._h, B, R, L.SRM_FLAG_SAVE_FOR_BACKWARD)
-            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._ws = None
+            self._ws = self.new_workspace(B, R)
             self._ws_B = (B, R)
         return self._ws
+
+    def _ws_for(self, ws, B: int, R: int) -> torch.Tensor:
+        if ws is None:
+            return self.workspace(B, R)
+        if not (ws.is_cuda and ws.device == self.device and ws.dtype == torch.uint8 and ws.is_contiguous()):
+            raise ValueError("ws: need a contiguous uint8 CUDA tensor on the engine's device")
+        if ws.numel() < self.workspace_bytes(B, R):
+            raise ValueError(f"ws: {ws.numel()} bytes < {self.workspace_bytes(B, R)} needed for B={B}, R={R}")
+        return ws
+
+    def _check_batch(self, B: int, R: int, sample_real, *per_sample):
+        """lengths of the per-sample inputs (a short one would be an out-of-bounds device read)"""
+        for t, nm in per_sample:
+            if t.numel() != B:
+                raise ValueError(f"{nm}: {t.numel()} elements, need B = {B}")
+        if sample_real is not None:
+            self._check(sample_real, "sample_real", torch.int32)
+            if sample_real.numel() != B:
+                raise ValueError(f"sample_real: {sample_real.numel()} elements, need B = {B}")
 
     # ---------------------------------------------------------------------------------------
     def pvt_eval(self, p: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -102,7 +129,7 @@ class SrmPhysics:
     def denormalize_log(self, x_norm: torch.Tensor, kmin: float, kmax: float, lo: float = -1.0, hi: float = 1.0):
         self._check(x_norm, "x_norm")
         out = torch.empty_like(x_norm)
-        L.check(self.lib, self.lib.srm_denormalize_log(x_norm.numel(), _ptr(x_norm), kmin, kmax, lo, hi, _ptr(out),
+        L.check(self.lib, self.lib.srm_denormalize_log(self.device.index, x_norm.numel(), _ptr(x_norm), kmin, kmax, lo, hi, _ptr(out),
                                                        self._stream()), "srm_denormalize_log")
         self.launches += 1
         return out
@@ -159,8 +186,9 @@ class SrmPhysics:
         return p0, p1, dt1, dt2
 
     def glue_backward(self, y0, y1, tn0, tn1, gp0, gp1, expo=None, gdt1=None, gdt2=None, init_value: float = 1.0,
-                      t_lo: float = -1.0, t_hi: float = 1.0, want_gexpo: bool = True):
-        """cotangents of glue_forward: (gy0, gy1, gexpo, gdtf1, gdtf2)"""
+                      t_lo: float = -1.0, t_hi: float = 1.0, want_gexpo: bool = True, want_gtn=(False, False)):
+        """cotangents of glue_forward: (gy0, gy1, gexpo, gdtf1, gdtf2), plus (gtn0, gtn1) -- the cotangents of the
+        layer's time inputs, Hard_Layer_Subclassed.py:214-228 -- when want_gtn asks for either"""
         B = y0.shape[0]
         for t, nm in ((y0, "y0"), (y1, "y1"), (tn0, "tn0"), (tn1, "tn1"), (gp0, "gp0"), (gp1, "gp1")):
             self._check(t, nm)
@@ -168,11 +196,15 @@ class SrmPhysics:
         gexpo = torch.empty(y0.shape[1:], dtype=torch.float32, device=self.device) if want_gexpo else None
         gdtf1 = torch.empty_like(y0) if gdt1 is not None else None
         gdtf2 = torch.empty_like(y0) if gdt2 is not None else None
+        gtn0 = torch.empty(B, dtype=torch.float32, device=self.device) if want_gtn[0] else None
+        gtn1 = torch.empty(B, dtype=torch.float32, device=self.device) if want_gtn[1] else None
         L.check(self.lib, self.lib.srm_glue_backward(self._h, B, init_value, t_lo, t_hi, _ptr(expo), _ptr(tn0), _ptr(tn1),
                                                      _ptr(y0), _ptr(y1), _ptr(gp0), _ptr(gp1), _ptr(gdt1), _ptr(gdt2),
                                                      _ptr(gy0), _ptr(gy1), _ptr(gexpo), _ptr(gdtf1), _ptr(gdtf2),
-                                                     self._stream()), "srm_glue_backward")
+                                                     _ptr(gtn0), _ptr(gtn1), self._stream()), "srm_glue_backward")
         self.launches += 1
+        if want_gtn[0] or want_gtn[1]:
+            return gy0, gy1, gexpo, gdtf1, gdtf2, gtn0, gtn1
         return gy0, gy1, gexpo, gdtf1, gdtf2
 
     def wells(self, kx, sample_real, p, t_days, dense: bool = False):
@@ -194,16 +226,15 @@ class SrmPhysics:
         return dict(qw=qw, pwfw=pwfw, dqdp=dqdp, q=qd, pwf=pd)
 
     def forward(self, kx, sample_real, p0, p1, dt1, dt2, t1, want_dom: bool = False, want_wells: bool = False,
-                save_for_backward: bool = True):
+                save_for_backward: bool = True, ws=None):
         B = p0.shape[0]
         R = kx.shape[0]
         for t, nm in ((kx, "kx"), (p0, "p0"), (p1, "p1"), (dt1, "dt1"), (dt2, "dt2"), (t1, "t1")):
             self._check(t, nm)
-        if sample_real is not None:
-            self._check(sample_real, "sample_real", torch.int32)
+        self._check_batch(B, R, sample_real, (dt1, "dt1"), (dt2, "dt2"), (t1, "t1"))
         if p0.numel() != B * self.spec.n_cells or p1.shape != p0.shape or kx.numel() != R * self.spec.n_cells:
             raise ValueError("field shapes do not match the handle's grid")
-        ws = self.workspace(B, R)
+        ws = self._ws_for(ws, B, R)
         terms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32, device=self.device)
         dom = torch.empty_like(p0) if want_dom else None
         qw = torch.empty((B, max(self.n_wells, 1)), dtype=torch.float32, device=self.device) if want_wells else None
@@ -220,12 +251,17 @@ class SrmPhysics:
         self.launches += nk + (2 if (want_wells and self.n_wells) else 0)
         return dict(terms=terms, dom=dom, qw=qw, pwfw=pwfw)
 
-    def backward(self, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, out=None):
+    def backward(self, kx, sample_real, p0, p1, dt1, dt2, t1, dterms, out=None, ws=None):
         """out: optional preallocated (gp0, gp1, gdt1, gdt2) to write into"""
         B = p0.shape[0]
         R = kx.shape[0]
         self._check(dterms, "dterms")
-        ws = self.workspace(B, R)
+        if dterms.numel() != L.SRM_N_TERMS:
+            raise ValueError(f"dterms: {dterms.numel()} elements, need {L.SRM_N_TERMS}")
+        for t, nm in ((kx, "kx"), (p0, "p0"), (p1, "p1"), (dt1, "dt1"), (dt2, "dt2"), (t1, "t1")):
+            self._check(t, nm)
+        self._check_batch(B, R, sample_real, (dt1, "dt1"), (dt2, "dt2"), (t1, "t1"))
+        ws = self._ws_for(ws, B, R)
         if out is not None:
             gp0, gp1, gdt1, gdt2 = out
             for t, nm in ((gp0, "gp0"), (gp1, "gp1"), (gdt1, "gdt1"), (gdt2, "gdt2")):
@@ -272,19 +308,18 @@ class SrmPhysics:
         return tuple(dense[:4]), dense[4]
 
     def forward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, want_dom: bool = False,
-                   want_wells: bool = False, save_for_backward: bool = True):
+                   want_wells: bool = False, save_for_backward: bool = True, ws=None):
         B, R = p0.shape[0], kx.shape[0]
         for t, nm in ((kx, "kx"), (p0, "p0"), (p1, "p1"), (sg0, "sg0"), (sg1, "sg1"), (so0, "so0"), (so1, "so1"),
                       (dt1, "dt1"), (dt2, "dt2"), (t1, "t1")):
             self._check(t, nm)
-        if sample_real is not None:
-            self._check(sample_real, "sample_real", torch.int32)
+        self._check_batch(B, R, sample_real, (dt1, "dt1"), (dt2, "dt2"), (t1, "t1"))
         for t in (p1, sg0, sg1, so0, so1):
             if t.shape != p0.shape:
                 raise ValueError("field shapes differ")
         if p0.numel() != B * self.spec.n_cells or kx.numel() != R * self.spec.n_cells:
             raise ValueError("field shapes do not match the handle's grid")
-        ws = self.workspace(B, R)
+        ws = self._ws_for(ws, B, R)
         terms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32, device=self.device)
         dom = torch.empty_like(p0) if want_dom else None
         nw = max(self.n_wells, 1)
@@ -298,10 +333,13 @@ class SrmPhysics:
         self.launches += (4 if self.n_wells else 3) + (5 if (want_wells and self.n_wells) else 0)   # stage, wells, residual, finalize
         return dict(terms=terms, dom=dom, q4w=q4, pwfw=pwfw)
 
-    def backward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms, out=None):
+    def backward_gc(self, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, dterms, out=None, ws=None):
         B, R = p0.shape[0], kx.shape[0]
         self._check(dterms, "dterms")
-        ws = self.workspace(B, R)
+        if dterms.numel() != L.SRM_N_TERMS:
+            raise ValueError(f"dterms: {dterms.numel()} elements, need {L.SRM_N_TERMS}")
+        self._check_batch(B, R, sample_real, (dt1, "dt1"), (dt2, "dt2"), (t1, "t1"))
+        ws = self._ws_for(ws, B, R)
         if out is not None:
             g = list(out)
             for t in g:
@@ -331,20 +369,23 @@ class GraphedStep:
         fwd, bwd = (eng.forward_gc, eng.backward_gc) if gc else (eng.forward, eng.backward)
         self.inputs = {k: v.clone() for k, v in batch.items()}
         self.dterms = dterms.clone()
+        # the graph bakes the workspace address in: it owns one, so later calls on the engine (other batch shapes
+        # re-allocate the engine's cached workspace) cannot pull it from under the replays
+        self.ws = eng.new_workspace(self.inputs["p0"].shape[0], self.inputs["kx"].shape[0])
         cur = torch.cuda.current_stream(eng.device)
         side = torch.cuda.Stream(eng.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):           # workspace, function attributes and first-call work happen here, uncaptured
             for _ in range(max(1, warmup)):
-                fwd(**self.inputs)
-                bwd(dterms=self.dterms, **self.inputs)
+                fwd(ws=self.ws, **self.inputs)
+                bwd(dterms=self.dterms, ws=self.ws, **self.inputs)
         cur.wait_stream(side)
         torch.cuda.synchronize(eng.device)
         self.graph = torch.cuda.CUDAGraph()
         l0 = eng.launches
         with torch.cuda.graph(self.graph):
-            fw = fwd(**self.inputs)
-            self.grads = bwd(dterms=self.dterms, **self.inputs)
+            fw = fwd(ws=self.ws, **self.inputs)
+            self.grads = bwd(dterms=self.dterms, ws=self.ws, **self.inputs)
         self.terms = fw["terms"]
         self.kernels = eng.launches - l0        # kernels inside one replay
 
@@ -418,6 +459,7 @@ class HostPipeline:
             self.dgrads = {n: (torch.empty(self.B, **f32) if n.startswith("gdt") else torch.empty((self.B,) + tuple(cell), **f32))
                            for n in self.gnames}
             self.hout = {}
+        self.ws = torch.empty(max(eng.workspace_bytes(b1 - b0, r1 - r0) for r0, r1, b0, b1 in self.chunks), dtype=torch.uint8, device=dev)
         self.hterms = torch.empty((2, L.SRM_N_TERMS), dtype=torch.float32).pin_memory()
         self.terms = torch.zeros((2, L.SRM_N_TERMS), **f32)
         self.dterms = dterms
@@ -458,13 +500,13 @@ class HostPipeline:
             else:
                 out = [self.dgrads[n][b0:b1] for n in self.gnames]
             if self.gc:
-                fw = eng.forward_gc(**a)
+                fw = eng.forward_gc(ws=self.ws, **a)
                 self.terms.add_(fw["terms"])
-                eng.backward_gc(dterms=self.dterms, out=out, **a)
+                eng.backward_gc(dterms=self.dterms, out=out, ws=self.ws, **a)
             else:
-                fw = eng.forward(**a)
+                fw = eng.forward(ws=self.ws, **a)
                 self.terms.add_(fw["terms"])
-                eng.backward(dterms=self.dterms, out=out, **a)
+                eng.backward(dterms=self.dterms, out=out, ws=self.ws, **a)
             ev_comp[slot] = comp.record_event()
             ev_free_in[slot] = ev_comp[slot]
             if self.grads_to_host:

@@ -15,13 +15,15 @@ import torch
 
 
 class _GlueFn(torch.autograd.Function):
-    """(p0, p1, dt1, dt2) = glue(y0, y1, expo, dtf1, dtf2); time inputs carry no gradient here: the reference
-    differentiates w.r.t. the networks' weights only (physics_loss.py:849-859), and the layer's time input is data."""
+    """(p0, p1, dt1, dt2) = glue(tn0, tn1, y0, y1, expo, dtf1, dtf2).  The layer's time input is differentiable
+    (Hard_Layer_Subclassed.py:214-228 reads it from the feature tensor with no stop_gradient): at level n+1 it is
+    t_n + normalize_diff(dt1) (physics_loss.py:105-111), so tape.gradient reaches the time-step model through it."""
 
     @staticmethod
     def forward(ctx, engine, init_value, t_lo, t_hi, tn0, tn1, y0, y1, expo, dtf1, dtf2):
         c = lambda t: None if t is None else t.detach().contiguous()
         y0c, y1c, ec, d1c, d2c = c(y0), c(y1), c(expo), c(dtf1), c(dtf2)
+        tn0, tn1 = tn0.detach().contiguous(), tn1.detach().contiguous()
         p0, p1, dt1, dt2 = engine.glue_forward(y0c, y1c, tn0, tn1, ec, d1c, d2c, init_value, t_lo, t_hi)
         ctx.engine, ctx.k = engine, (init_value, t_lo, t_hi)
         ctx.has = (expo is not None, dtf1 is not None, dtf2 is not None)
@@ -33,10 +35,13 @@ class _GlueFn(torch.autograd.Function):
     def backward(ctx, gp0, gp1, gdt1, gdt2):
         tn0, tn1, y0, y1, expo = ctx.saved_tensors
         has_e, has1, has2 = ctx.has
-        gy0, gy1, gexpo, gdtf1, gdtf2 = ctx.engine.glue_backward(
+        want_t = (bool(ctx.needs_input_grad[4]), bool(ctx.needs_input_grad[5]))
+        res = ctx.engine.glue_backward(
             y0, y1, tn0, tn1, gp0.contiguous(), gp1.contiguous(), expo if has_e else None,
-            gdt1.contiguous() if has1 else None, gdt2.contiguous() if has2 else None, *ctx.k, want_gexpo=has_e)
-        return None, None, None, None, None, None, gy0, gy1, gexpo if has_e else None, gdtf1, gdtf2
+            gdt1.contiguous() if has1 else None, gdt2.contiguous() if has2 else None, *ctx.k, want_gexpo=has_e, want_gtn=want_t)
+        gy0, gy1, gexpo, gdtf1, gdtf2 = res[:5]
+        gtn0, gtn1 = (res[5], res[6]) if (want_t[0] or want_t[1]) else (None, None)
+        return None, None, None, None, gtn0, gtn1, gy0, gy1, gexpo if has_e else None, gdtf1, gdtf2
 
 
 class HardLayer(torch.nn.Module):
@@ -75,9 +80,10 @@ class HardLayer(torch.nn.Module):
             (time, _prop), p = inputs[0], inputs[1]
         else:
             time = inputs
-        tn = time.reshape(time.shape[0], -1)[:, 0].contiguous()
+        tn = time.reshape(time.shape[0], -1)[:, 0]
         y = p[..., 0] if p.dim() == 5 else p
-        out, _, _, _ = _GlueFn.apply(self.engine, self.init_value, *self.norm_limits, tn, tn, y, y, self.kernel_exponent, None, None)
+        # one level: the second slot re-uses the inputs detached (its outputs are dropped, its cotangents are zero)
+        out, _, _, _ = _GlueFn.apply(self.engine, self.init_value, *self.norm_limits, tn, tn.detach(), y, y.detach(), self.kernel_exponent, None, None)
         return out.unsqueeze(-1) if p.dim() == 5 else out
 
 
@@ -105,7 +111,7 @@ def fused_two_level(module: CompleteTrainableModule, time_step_model, x0, x1):
     x_n1 must already carry the shifted time (it depends on dt1: the caller evaluates time_step_model(x_n) first)."""
     hl = module.hard_layer
     y0, y1 = module.main_network(x0)[..., 0], module.main_network(x1)[..., 0]
-    tn0, tn1 = x0[:, 0, 0, 0, -2].contiguous(), x1[:, 0, 0, 0, -2].contiguous()
+    tn0, tn1 = x0[:, 0, 0, 0, -2], x1[:, 0, 0, 0, -2]        # differentiable: x1 carries t_n + normalize_diff(dt1)
     dtf2 = time_step_model(x1)[..., 0]
     p0, p1, _, dt2 = _GlueFn.apply(hl.engine, hl.init_value, *hl.norm_limits, tn0, tn1, y0, y1, hl.kernel_exponent, None, dtf2)
     return p0, p1, dt2

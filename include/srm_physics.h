@@ -12,7 +12,8 @@
  *   - Fields are fp32, layout (B, D, H, W) with W (x, index i) contiguous; kx is (R, D, H, W).
  *     "sample" b = one (realisation, time point) pair (training.py:187-204 flattens K x T into B).
  *   - sample_real[b] in [0, R) maps a sample to its permeability realisation (device int32;
- *     NULL means b * R / B, i.e. realisation-major equal-sized groups).
+ *     NULL means b * R / B, i.e. realisation-major equal-sized groups).  An index outside [0, R) is clamped
+ *     into the range by the kernels (never an out-of-bounds read); dt1, dt2, t1, sample_real hold B elements.
  *   - The caller owns every buffer.  The library owns only the handle's immutable device tables.
  *     No allocation happens inside forward/backward: scratch comes from the caller's workspace
  *     (query srm_workspace_bytes once).
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SRM_ABI_VERSION 2
+#define SRM_ABI_VERSION 3
 
 typedef enum SrmStatus {
   SRM_OK = 0,
@@ -149,7 +150,7 @@ int srm_pvt_eval(const SrmHandle* h, int64_t n, const float* p, float* val, floa
 
 /* DataSummary.nonormalize, log branch used for permeability
  * (data_processing/data_processing_utils.py:1098-1106): kx = exp(ln(kmax/kmin)*((x-lo)/(hi-lo)) + ln kmin). */
-int srm_denormalize_log(int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi,
+int srm_denormalize_log(int32_t device, int64_t n, const float* x_norm, float kmin, float kmax, float lo, float hi,
                         float* out, void* stream);
 
 /* Self-test of the library's own correctly rounded sqrt / division sequences (they replace the
@@ -240,11 +241,14 @@ int srm_glue_forward(const SrmHandle* h, int32_t B, float init_value, float t_lo
                      size_t workspace_bytes, void* stream);
 /* Cotangents of srm_glue_forward (what tape.gradient hands to the networks and to kernel_exponent):
  *   gy_l = -alpha * gp_l;   gexpo[c] = sum_b sum_l gp_l * (-y_l * alpha * ln alpha_t)  (0 where alpha_t <= 0, as
- *   tf.pow's gradient);   gdtf_l[b,c] = gdt_l[b] / N.   gexpo, gdtf_l (with gdt_l) may be NULL. */
+ *   tf.pow's gradient);   gdtf_l[b,c] = gdt_l[b] / N;
+ *   gtn_l[b] = sum_c gp_l * (-y_l * expo[c] * alpha_t^(expo[c]-1)) / (t_hi - t_lo): the layer's time input is
+ *   differentiable -- at level n+1 it carries the time-step model's output (physics_loss.py:105-111,
+ *   Hard_Layer_Subclassed.py:214-228).   gexpo, gdtf_l (with gdt_l), gtn_l (B,) may be NULL. */
 int srm_glue_backward(const SrmHandle* h, int32_t B, float init_value, float t_lo, float t_hi, const float* expo,
                       const float* tn0, const float* tn1, const float* y0, const float* y1, const float* gp0,
                       const float* gp1, const float* gdt1, const float* gdt2, float* gy0, float* gy1, float* gexpo,
-                      float* gdtf1, float* gdtf2, void* stream);
+                      float* gdtf1, float* gdtf2, float* gtn0, float* gtn1, void* stream);
 
 /* BatchGenerator.__getitem__ on a device-resident data set (training.py:110-143: tf.gather(x_all, batch_inds,
  * axis=0) after converting the WHOLE data set to a tensor every step): dst[r] = src[idx[r]] for r < n_idx, rows of

@@ -1,7 +1,7 @@
 """Golden vectors for HardLayer made by the REFERENCE'S OWN class (Hard_Layer_Subclassed.py:21-260, cut out by AST) executed
 through the torch-backed TensorFlow stand-in: the example's configuration (no rbf, no rectifier, identity activations,
 identity nonormalize_func, norm_limits [-1, 1], per-cell trainable kernel_exponent).  Values and the cotangents torch
-autograd delivers for the network output and for kernel_exponent (time inputs > t_lo: tf.pow's and torch.pow's
+autograd delivers for the network output, for kernel_exponent and for the time input (time inputs > t_lo: tf.pow's and torch.pow's
 gradients coincide there).   Output: tests/golden/reference_hardlayer.npz
 """
 import ast
@@ -33,16 +33,18 @@ def main():
     expo = (0.1 + 0.85 * rng.random((D, H, W, 1))).astype(np.float32)
     layer.kernel_exponent = torch.as_tensor(expo).requires_grad_(True)
     tn = np.asarray([-1.0, -0.6, 0.0, 0.45, 1.0], np.float32)
-    time = torch.as_tensor(np.broadcast_to(tn.reshape(B, 1, 1, 1, 1), (B, D, H, W, 1)).copy())
+    tn_t = torch.as_tensor(tn).requires_grad_(True)          # the layer's time input is differentiable (physics_loss.py:105-111)
+    time = tn_t.view(B, 1, 1, 1, 1).expand(B, D, H, W, 1)
     prop = torch.zeros(B, D, H, W, 1)
     y = torch.as_tensor((600.0 * rng.random((B, D, H, W, 1))).astype(np.float32)).requires_grad_(True)
     out = layer([[time, prop], y])
     wgt = torch.as_tensor(rng.standard_normal((B, D, H, W, 1)).astype(np.float32))
     # cotangents over the samples with alpha_t > 0 only (at alpha_t = 0 torch.pow's exponent gradient is nan, tf's is 0)
     sel = torch.as_tensor((tn > -1.0).astype(np.float32)).view(B, 1, 1, 1, 1)
-    gy, ge = torch.autograd.grad((out * wgt * sel).sum(), [y, layer.kernel_exponent])
+    gy, ge, gt = torch.autograd.grad((out * wgt * sel).sum(), [y, layer.kernel_exponent, tn_t])
     np.savez_compressed(os.path.join(HERE, "reference_hardlayer.npz"), tn=tn, expo=expo[..., 0], y=y.detach().numpy()[..., 0],
-                        out=out.detach().numpy()[..., 0], wgt=(wgt * sel).numpy()[..., 0], gy=gy.numpy()[..., 0], gexpo=ge.numpy()[..., 0])
+                        out=out.detach().numpy()[..., 0], wgt=(wgt * sel).numpy()[..., 0], gy=gy.numpy()[..., 0], gexpo=ge.numpy()[..., 0],
+                        gtn=gt.numpy())
     print("wrote reference_hardlayer.npz", out.shape)
 
 

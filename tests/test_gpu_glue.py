@@ -179,9 +179,56 @@ def test_glue_against_the_reference_hard_layer_class():
     p0, p1, _, _ = eng.glue_forward(c("y"), c("y"), c("tn"), c("tn"), c("expo"), None, None, 5000.0)
     assert np.allclose(p0.cpu().numpy(), g["out"], rtol=1e-6, atol=0) and torch.equal(p0, p1)
     zero = torch.zeros_like(c("wgt"))
-    gy0, gy1, gexpo, _, _ = eng.glue_backward(c("y"), c("y"), c("tn"), c("tn"), c("wgt"), zero, c("expo"), None, None, 5000.0)
+    gy0, gy1, gexpo, _, _, gtn0, gtn1 = eng.glue_backward(c("y"), c("y"), c("tn"), c("tn"), c("wgt"), zero, c("expo"), None, None, 5000.0,
+                                                          want_gtn=(True, True))
     assert U.rel_to_max(gy0.cpu().numpy(), g["gy"]) < 1e-5 and U.rel_to_max(gexpo.cpu().numpy(), g["gexpo"]) < 1e-5
     assert not gy1.any()
+    # the cotangent of the layer's time input (the path to the time-step model, physics_loss.py:105-111); sample 0 sits at
+    # alpha_t = 0 where the reference's own gradient is 0 * inf
+    assert U.rel_to_max(gtn0.cpu().numpy()[1:], g["gtn"][1:]) < 1e-5
+    assert not gtn1.cpu().numpy()[1:].any()
+    eng.close()
+
+
+def test_fused_two_level_carries_the_time_cotangent_to_the_time_step_model():
+    """d p1 / d tn1 = -e alpha_t^(e-1) y1 / (t_hi - t_lo) must reach the time-step model through x1's time
+    channel.  fused_two_level (one CUDA pass) against the same graph in plain torch ops on the same device."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=12, H=8, D=2, T=2, K=2, seed=3302)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=False)
+    dev = eng.device
+    B = 4
+    g = torch.Generator().manual_seed(17)
+    x0 = (2.0 * torch.rand((B, 2, 8, 12, 5), generator=g) - 1.0)
+    x0[..., 3] = (-0.8 + 1.2 * torch.rand(B, generator=g)).view(B, 1, 1, 1)
+    x0 = x0.to(dev)
+    net = _Net(21).to(dev)
+    hl = srm.HardLayer(eng, init_value=5000.0)
+    with torch.no_grad():
+        hl.kernel_exponent.copy_(0.2 + 0.7 * torch.rand(hl.kernel_exponent.shape, generator=g).to(dev))
+    mod = srm.CompleteTrainableModule(net, hl)
+    step = torch.nn.Linear(5, 1).to(dev)
+    w0 = torch.randn((B, 2, 8, 12), generator=g).to(dev)
+    w1 = torch.randn((B, 2, 8, 12), generator=g).to(dev)
+    idx = torch.zeros(5, device=dev); idx[3] = 1.0
+    res = []
+    for fused in (True, False):
+        for m in (net, step, hl):
+            m.zero_grad()
+        dn = 0.01 * torch.sigmoid(step(x0)).reshape(B, -1).mean(dim=1)
+        x1 = x0 + dn.view(B, 1, 1, 1, 1) * idx
+        if fused:
+            p0, p1, dt2 = srm.hard_layer.fused_two_level(mod, lambda x: torch.sigmoid(step(x)), x0, x1)
+        else:
+            e = hl.kernel_exponent
+            p0 = O.hard_layer_t(net(x0)[..., 0], x0[:, 0, 0, 0, 3], e, 5000.0)
+            p1 = O.hard_layer_t(net(x1)[..., 0], x1[:, 0, 0, 0, 3], e, 5000.0)
+            dt2 = torch.sigmoid(step(x1))[..., 0].reshape(B, -1).mean(dim=1)
+        ((p0 * w0).sum() + (p1 * w1).sum() + dt2.sum()).backward()
+        res.append([step.weight.grad.clone().cpu().numpy(), step.bias.grad.clone().cpu().numpy(),
+                    net.lin.weight.grad.clone().cpu().numpy(), hl.kernel_exponent.grad.clone().cpu().numpy()])
+    for a, b in zip(*res):
+        assert U.rel_to_max(a, b) < 1e-4, (a, b)          # fp32 reductions over B*N terms in different orders
+    assert np.abs(res[0][0]).max() > 0
     eng.close()
 
 

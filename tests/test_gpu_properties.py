@@ -170,3 +170,79 @@ def test_lean_pair_at_full_size_equals_the_per_cell_path_and_repeats(cfg2):
     for name, a, b in zip(("gp0", "gp1", "gdt1"), (ref[1], ref[2], ref[3]), g0):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max())), name
     eng.close()
+
+
+@pytest.mark.parametrize("pvt_lut", [True, False])
+def test_interleaved_batches_share_one_workspace(pvt_lut):
+    """fwd(A), fwd(B), bwd(A), bwd(B) on ONE workspace (gradient accumulation with two .backward() calls): bwd(A)
+    must recompute A's forward state -- the workspace holds B's -- and bwd(B) must then NOT take A's recomputed
+    state for its own (the saved-state fingerprint went stale after a recompute)."""
+    _, _, spec, ptab, b1 = U.make_case(W=24, H=10, D=3, T=2, K=2, seed=4101)
+    _, _, _, _, b2 = U.make_case(W=24, H=10, D=3, T=2, K=2, seed=4102)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=pvt_lut)
+    dev = torch.device("cuda", 0)
+    dA, dB = U.to_dev(b1, dev), U.to_dev(b2, dev)
+    w = torch.tensor(U.WEIGHTS, dtype=torch.float32, device=dev)
+    ref = {}
+    for nm, d in (("A", dA), ("B", dB)):
+        eng.forward(**d)
+        ref[nm] = [t.clone() for t in eng.backward(dterms=w, **d)]
+    eng.forward(**dA)
+    eng.forward(**dB)
+    gA = [t.clone() for t in eng.backward(dterms=w, **dA)]
+    gB = [t.clone() for t in eng.backward(dterms=w, **dB)]
+    for got, want in ((gA, ref["A"]), (gB, ref["B"])):
+        for x, y in zip(got, want):
+            assert torch.equal(x, y)
+    # same pointers, other per-sample scalars: the fingerprint covers dt1 / dt2 / t1 too
+    d3 = dict(dA)
+    d3["dt1"] = (dA["dt1"] * 1.5).contiguous()
+    eng.forward(**dA)
+    g3 = eng.backward(dterms=w, **d3)
+    eng.forward(**d3)
+    g3r = eng.backward(dterms=w, **d3)
+    for x, y in zip(g3, g3r):
+        assert torch.equal(x, y)
+    eng.close()
+
+
+def test_graphed_step_owns_its_workspace():
+    """replays stay valid after the engine's cached workspace is re-allocated by calls with another batch shape"""
+    _, _, spec, ptab, b1 = U.make_case(W=24, H=10, D=3, T=2, K=2, seed=4103)
+    _, _, _, _, b2 = U.make_case(W=24, H=10, D=3, T=3, K=3, seed=4104)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=True)
+    dev = torch.device("cuda", 0)
+    dA, dB = U.to_dev(b1, dev), U.to_dev(b2, dev)
+    w = torch.tensor(U.WEIGHTS, dtype=torch.float32, device=dev)
+    gs = srm.engine.GraphedStep(eng, dA, w)
+    t0, g0 = gs.replay()
+    t0 = t0.clone(); g0 = [t.clone() for t in g0]
+    for _ in range(3):                       # other shapes: the engine drops and re-allocates its own workspace
+        eng.forward(**dB); eng.backward(dterms=w, **dB)
+        junk = torch.full((eng.workspace_bytes(4, 2),), 255, dtype=torch.uint8, device=dev)   # recycle freed blocks
+        eng.forward(**dA); eng.backward(dterms=w, **dA)
+        del junk
+    t1, g1 = gs.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(t0, t1)
+    for x, y in zip(g0, g1):
+        assert torch.equal(x, y)
+    eng.close()
+
+
+def test_engine_rejects_short_per_sample_inputs():
+    _, _, spec, ptab, b1 = U.make_case(W=24, H=10, D=3, T=2, K=2, seed=4105)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    d = U.to_dev(b1, torch.device("cuda", 0))
+    for k in ("dt1", "dt2", "t1", "sample_real"):
+        bad = dict(d)
+        bad[k] = d[k][:-1].contiguous()
+        with pytest.raises(ValueError):
+            eng.forward(**bad)
+    # an out-of-range realisation index is clamped by the kernels, not an out-of-bounds read
+    bad = dict(d)
+    bad["sample_real"] = torch.full_like(d["sample_real"], 7)
+    last = dict(d)
+    last["sample_real"] = torch.full_like(d["sample_real"], d["kx"].shape[0] - 1)
+    assert torch.equal(eng.forward(**bad)["terms"], eng.forward(**last)["terms"])
+    eng.close()
