@@ -24,6 +24,7 @@ int srm_launch_scatter_wells(const SrmHandle* h, int32_t B, const float* sorted,
 int srm_launch_unsort_wells(const SrmHandle* h, int32_t B, const float* sorted, float* out, cudaStream_t s);
 int srm_launch_selftest_rounding(int64_t n, uint64_t seed, int64_t* bad_host, cudaStream_t s);
 int srm_build_closed_form(SrmHandle* h, const SrmConfig* cfg);
+int srm_build_cf2(SrmHandle* h, const SrmConfig* cfg);
 int srm_launch_pvt_eval_cf(const SrmHandle* h, int64_t n, const float* p, float* val, float* dval, cudaStream_t s);
 int srm_launch_wells_cf(const SrmHandle* h, int32_t B, const float* kx, const int32_t* sample_real, int32_t R,
                         const float* p, const float* t_days, float* qw, float* pwfw, float* dqdp, cudaStream_t s);
@@ -158,6 +159,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   }
   if (!poly && cfg->spline_order == 1) {
     int rc = srm_build_closed_form(h, cfg);
+    if (!rc && cfg->fluid_type == SRM_FLUID_DG) rc = srm_build_cf2(h, cfg);
     if (rc) { srm_destroy(h); return rc; }
   }
   if (cfg->pvt_lut && cfg->numerics == SRM_NUMERICS_REFERENCE) {
@@ -177,6 +179,7 @@ void srm_destroy(SrmHandle* h) {
   cudaSetDevice(h->device);
   if (h->d_wells) cudaFree(h->d_wells);
   if (h->d_cf) cudaFree(h->d_cf);
+  if (h->d_cf2) cudaFree(h->d_cf2);
   if (h->d_lut) cudaFree(h->d_lut);
   delete h;
 }

@@ -960,6 +960,15 @@ int srm_launch_wells_cf(const SrmHandle* h, int32_t B, const float* kx, const in
   return SRM_OK;
 }
 
+// the lean pair (kernels_cf2.cu)
+bool srm_cf2_applicable(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e);
+int srm_cf2_faces(const SrmHandle* h, int32_t R, const float* kx, float* faces, cudaStream_t s);
+int srm_cf2_forward(const SrmHandle* h, int32_t B, int32_t R, const int32_t* sample_real, const float* p0, const float* p1,
+                    const float* dt1, const SrmWs& ws, cudaStream_t s);
+int srm_cf2_backward(const SrmHandle* h, int32_t B, int32_t R, const int32_t* sample_real, const float* p0, const float* p1,
+                     const float* dt1, const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2, const SrmWs& ws,
+                     cudaStream_t s);
+
 int srm_forward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                    const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                    float* terms_out, float* dom_out, const SrmWs& ws, bool save, cudaStream_t s) {
@@ -967,14 +976,26 @@ int srm_forward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const in
   const SrmDev& P = h->dev;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));
   const Plan pl = choose_plan(P, p0, p1, nullptr);
-  k_group_samples<<<1, 1024, 0, s>>>(B, R, sample_real, tchunk_for(h, pl, B), ws.grp_cnt, ws.grp_fill, ws.grp_list, ws.seg, ws.ctl);
-  SRM_CUDA_CHECK(cudaGetLastError());
+  h->cf_faces_ok = h->cf_grouped = 0;
   int rc = srm_launch_wells_cf(h, B, kx, sample_real, R, p1, t1, ws.qw, ws.pwfw, ws.dqdp, s);
   if (rc) return rc;
   if (P.n_wells > 0) {
     k_qsum_cf<<<(B + 127) / 128, 128, 0, s>>>(B, P.n_wells, ws.qw, ws.q_sum);
     SRM_CUDA_CHECK(cudaGetLastError());
   }
+  if (srm_cf2_applicable(h, p0, p1, ws.dom, ws.faces, nullptr)) {
+    rc = srm_cf2_faces(h, R, kx, ws.faces, s);
+    if (!rc) rc = srm_cf2_forward(h, B, R, sample_real, p0, p1, dt1, ws, s);
+    if (rc) return rc;
+    h->cf_faces_ok = 1;
+    if (dom_out) SRM_CUDA_CHECK(cudaMemcpyAsync(dom_out, ws.dom, sizeof(float) * (size_t)B * (size_t)P.N, cudaMemcpyDeviceToDevice, s));
+    k_finalize_fwd<<<1, 256, 0, s>>>(P, B, ws.sse, ws.mb_sum, ws.q_sum, ws.mbc, terms_out);
+    SRM_CUDA_CHECK(cudaGetLastError());
+    return SRM_OK;
+  }
+  k_group_samples<<<1, 1024, 0, s>>>(B, R, sample_real, tchunk_for(h, pl, B), ws.grp_cnt, ws.grp_fill, ws.grp_list, ws.seg, ws.ctl);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  h->cf_grouped = 1;
   CfArgs A;
   std::memset(&A, 0, sizeof(A));
   A.p0 = p0; A.p1 = p1; A.kx = kx; A.dt1 = dt1; A.dt2 = dt2;
@@ -1004,8 +1025,25 @@ int srm_backward_cf(SrmHandle* h, int32_t B, int32_t R, const float* kx, const i
   (void)t1;
   const SrmDev& P = h->dev;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.gdt1_acc, 0, (char*)ws.mbc - (char*)ws.gdt1_acc, s));
-  SRM_CUDA_CHECK(cudaMemsetAsync(ws.ctl + 2, 0, sizeof(int32_t), s));
   const Plan pl = choose_plan(P, p0, p1, ws.dom);
+  if (srm_cf2_applicable(h, p0, p1, ws.dom, gp0, gp1) && srm_cf2_applicable(h, ws.faces, nullptr, nullptr, nullptr, nullptr)) {
+    // the forward's kernel family left dom, mbc, the well tables -- and, if it was the lean one, the face planes
+    int rc2 = h->cf_faces_ok ? SRM_OK : srm_cf2_faces(h, R, kx, ws.faces, s);
+    if (!rc2) { h->cf_faces_ok = 1; rc2 = srm_cf2_backward(h, B, R, sample_real, p0, p1, dt1, dterms, gp0, gp1, gdt1, gdt2, ws, s); }
+    if (rc2) return rc2;
+    const int64_t nwb = (int64_t)B * P.n_wells;
+    if (nwb > 0) {
+      k_ibc_adj_cf<<<(unsigned)((nwb + 127) / 128), 128, 0, s>>>(P, h->d_cf, B, R, kx, sample_real, p1, dterms, ws.divqw, ws.dqdp, gp1);
+      SRM_CUDA_CHECK(cudaGetLastError());
+    }
+    return SRM_OK;
+  }
+  if (!h->cf_grouped) {
+    k_group_samples<<<1, 1024, 0, s>>>(B, R, sample_real, tchunk_for(h, pl, B), ws.grp_cnt, ws.grp_fill, ws.grp_list, ws.seg, ws.ctl);
+    SRM_CUDA_CHECK(cudaGetLastError());
+    h->cf_grouped = 1;
+  }
+  SRM_CUDA_CHECK(cudaMemsetAsync(ws.ctl + 2, 0, sizeof(int32_t), s));
   CfArgs A;
   std::memset(&A, 0, sizeof(A));
   A.p0 = p0; A.p1 = p1; A.kx = kx; A.dt1 = dt1; A.dt2 = dt2;

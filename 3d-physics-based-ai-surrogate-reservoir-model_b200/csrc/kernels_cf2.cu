@@ -1,0 +1,788 @@
+// SRM_NUMERICS_CLOSED_FORM, second generation: the HBM-bound dry-gas pair (physics_loss.py:79-208, 742-870).
+//
+// Same formulas as kernels_cf.cu (order-1 polyharmonic interpolant in its exact piecewise-linear form, flux in
+// difference form, truncation bracket == 0); what changes is how a cell-timestep is paid for:
+//   * one CTA = one (128 x 8 | 64 x 16 | 32 x 32) column tile of ONE sample, marching over z; 256 threads, FOUR
+//     x-adjacent cells per thread (16-byte shared loads and global stores);
+//   * every global read is a TMA box copy (cp.async.bulk.tensor.4d, mbarrier complete_tx) into a ring of stages:
+//     p1 and dom with their halo, p0, and the three static face-transmissibility planes (k_faces_cf2: zero on the
+//     grid boundary, so the zero fill of out-of-bounds box elements IS the reference's edge-replicating pad) --
+//     no address arithmetic, no boundary branches and no global loads in the instruction stream;
+//   * G = invBg*invug is evaluated once per cell and plane (tile + halo ring) and shared through a triple-buffered
+//     shared plane, one barrier per plane; x neighbours travel by warp shuffles, z neighbours in registers, and the
+//     z-face terms are formed once and handed to the plane above;
+//   * PVT: bucket -> interval -> one 16-byte coefficient load per pressure, all from shared memory.
+// Algorithmic bytes per cell-timestep: forward 12 + 12/T, adjoint 20 + 12/T.
+#include <cuda.h>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+#define CF2_NB 4096
+
+// closed-form tables of the lean pair, device global memory; every CTA copies them to shared memory
+struct Cf2Tab {
+  float lo, hi, inv_w, off;        // clamp range; bucket of x = uint(x * inv_w + off)
+  int32_t nb, n, pad0, pad1;
+  float hik[SRM_MAXK + 2];         // upper bound of interval k (k = number of knots <= x); +inf for k = n
+  float4 e0[SRM_MAXK + 1];         // {x0, f0[invBg], slope[invBg], f0[invug]}       anchor form: f = f0 + slope (x - x0)
+  float4 e1[SRM_MAXK + 1];         // {slope[invug], on-knot slope[invBg], on-knot slope[invug], low part of f0[invBg]}
+  unsigned char bucket[CF2_NB];    // bucket -> interval of (bucket start - margin); at most one knot per bucket window
+};
+
+int srm_build_cf2(SrmHandle* h, const SrmConfig* cfg) {
+  h->d_cf2 = nullptr;
+  const int n = cfg->n_knots;
+  if (cfg->n_props < 2 || cfg->spline_order != 1 || cfg->pvt_method != SRM_PVT_SPLINE) return SRM_OK;
+  std::vector<Cf2Tab> host(1);
+  Cf2Tab& T = host[0];
+  std::memset(&T, 0, sizeof(T));
+  T.n = n; T.lo = cfg->p_min; T.hi = cfg->p_max;
+  std::vector<double> sl0(n + 1), sl1(n + 1);
+  for (int k = 0; k <= n; ++k) {
+    const double xa = (k == 0) ? (double)cfg->knots[0] : (double)cfg->knots[k - 1];
+    double f[2], s[2];
+    for (int q = 0; q < 2; ++q) {
+      const float* w = cfg->spline_w + (size_t)q * n;
+      const double v0 = cfg->spline_v[2 * q], v1 = cfg->spline_v[2 * q + 1];
+      f[q] = v0 * xa + v1; s[q] = v0;
+      for (int i = 0; i < n; ++i) {
+        f[q] += (double)w[i] * std::fabs(xa - (double)cfg->knots[i]);
+        s[q] += (i < k) ? (double)w[i] : -(double)w[i];
+      }
+    }
+    sl0[k] = s[0]; sl1[k] = s[1];
+    const float f0h = (float)f[0];
+    T.e0[k] = make_float4((float)xa, f0h, (float)s[0], (float)f[1]);
+    T.e1[k] = make_float4((float)s[1], (float)s[0], (float)s[1], (float)(f[0] - (double)f0h));
+    T.hik[k] = (k == n) ? INFINITY : cfg->knots[k];
+  }
+  // exactly on a knot the reference's gradient mask drops the knot's own term: mean of the two slopes (kernels_cf.cu)
+  for (int k = 1; k <= n; ++k) { T.e1[k].y = (float)(0.5 * (sl0[k] + sl0[k - 1])); T.e1[k].z = (float)(0.5 * (sl1[k] + sl1[k - 1])); }
+  // buckets over [lo, hi]: width 0.45 x the smallest knot spacing that touches the clamp range
+  double wmin = 1e300;
+  for (int i = 1; i < n; ++i)
+    if (cfg->knots[i] >= cfg->p_min && cfg->knots[i - 1] <= cfg->p_max) wmin = std::fmin(wmin, (double)cfg->knots[i] - cfg->knots[i - 1]);
+  if (!(wmin < 1e300) || !(cfg->p_max > cfg->p_min)) return SRM_OK;
+  const double w = 0.45 * wmin;
+  const int nb = (int)std::floor(((double)cfg->p_max - cfg->p_min) / w) + 2;
+  if (nb > CF2_NB) return SRM_OK;             // the generic kernels (kernels_cf.cu) take such tables
+  T.nb = nb;
+  T.inv_w = (float)(1.0 / w);
+  T.off = -(float)((double)cfg->p_min / w);
+  for (int b = 0; b < CF2_NB; ++b) {
+    const double edge = (double)cfg->p_min + ((double)std::min(b, nb - 1) - 0.01) * w;
+    int cnt = 0;
+    while (cnt < n && (double)cfg->knots[cnt] <= edge) ++cnt;
+    T.bucket[b] = (unsigned char)cnt;
+  }
+  cudaError_t e = cudaMalloc((void**)&h->d_cf2, sizeof(Cf2Tab));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_cf2, &T, sizeof(Cf2Tab), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { srm_set_error("closed-form table upload: %s", cudaGetErrorString(e)); return SRM_ERR_CUDA; }
+  return SRM_OK;
+}
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int S_FWD = 3, S_ADJ = 3;      // TMA stages (planes in flight)
+
+__host__ __device__ constexpr int al128(int b) { return (b + 127) & ~127; }
+
+template <int LX>
+struct Geo {
+  static constexpr int TX = 4 * LX;                 // cells per tile row
+  static constexpr int RPW = 32 / LX;               // tile rows per warp
+  static constexpr int TY = (NT / 32) * RPW;
+  static constexpr int BX = TX + 8, BY = TY + 2;    // haloed box: columns x0-4 .. x0+TX+3, rows y0-1 .. y0+TY
+  static constexpr int FEX = TX + 4;                // east-face box: columns x0-4 .. x0+TX-1 (column 3 = W face of the tile's first cell)
+  static constexpr int P1_B = BX * BY * 4, P0_B = TX * TY * 4, FE_B = FEX * TY * 4, FN_B = TX * (TY + 1) * 4, FU_B = TX * TY * 4;
+  static constexpr int O_P1 = 0;
+  static constexpr int O_P0 = O_P1 + al128(P1_B);
+  static constexpr int O_FE = O_P0 + al128(P0_B);
+  static constexpr int O_FN = O_FE + al128(FE_B);
+  static constexpr int O_FU = O_FN + al128(FN_B);
+  static constexpr int STAGE_F = O_FU + al128(FU_B);                 // forward stage
+  static constexpr int O_DM = STAGE_F;
+  static constexpr int STAGE_A = O_DM + al128(P1_B);                 // adjoint stage (+ dom box)
+  static constexpr int TX_F = P1_B + P0_B + FE_B + FN_B + FU_B;      // bytes a stage's mbarrier expects
+  static constexpr int TX_A = TX_F + P1_B;
+  static constexpr int RING = 2 * TX + 2 * TY;
+  static constexpr int GPL = al128(P1_B);                            // one G plane (same layout as the p1 box)
+  template <bool ADJ> static constexpr int total() {
+    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + 3 * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + TY * TX /*well flags*/;
+  }
+};
+
+struct Cf2Args {
+  const float* dt1; const int32_t* sample_real;
+  const float* qw; const float* dqdp; float* divqw;
+  float* dom; double* sse; double* mb_sum;
+  const float* dterms; const float* mbc; float* gp0; float* gp1; double* gdt1_acc;
+  const Cf2Tab* T;
+  int32_t B, R, tiles_x;
+};
+
+// ---- TMA / mbarrier ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z, int b, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(b), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t pol_evict_last() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t pol_evict_first() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void a4(float (&d)[4], float4 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+
+// ---- PVT from the shared tables -------------------------------------------------------------------------------
+// interval of the clamped pressure: bucket, then at most one step up (at most one knot per bucket window)
+__device__ __forceinline__ int cf2_interval(const Cf2Tab* __restrict__ T, float x) {
+  const uint32_t b = __float2uint_rz(fmaf(x, T->inv_w, T->off));
+  int k = T->bucket[b];
+  k += (x >= T->hik[k]) ? 1 : 0;
+  return k;
+}
+__device__ __forceinline__ float cf2_clamp(const Cf2Tab* __restrict__ T, float p) { return fminf(fmaxf(p, T->lo), T->hi); }   // NaN -> lo
+
+// G = invBg * invug only (halo ring)
+__device__ __forceinline__ float cf2_G(const Cf2Tab* __restrict__ T, float p) {
+  const float x = cf2_clamp(T, p);
+  const int k = cf2_interval(T, x);
+  const float4 e = T->e0[k];
+  const float dx = x - e.x;
+  return fmaf(e.z, dx, e.y) * fmaf(T->e1[k].x, dx, e.w);
+}
+
+// first connection (sorted by cell) with cell >= c: well_lower_bound of common.cuh on the slim parameter block
+struct Cf2Dev {
+  int32_t D, H, W, N;
+  float dv, invDc, dvDc, Dc, K1, K2, dvSgi_phi;    // K1 = Sgi*phi, K2 = Sgi*phi*cf
+  int32_t tde_in_dom, n_wells;
+  const WellDev* wells;
+};
+__device__ __forceinline__ int cf2_lower_bound(const Cf2Dev& P, int c) {
+  int lo = 0, hi = P.n_wells;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (P.wells[mid].cell < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// static face transmissibilities of one realisation, cell-indexed, zero on the grid boundary:
+//   TE[c] = face between (i, i+1), TN[c] = face between (j, j+1), TU[c] = face between (k, k+1)
+//   value = 0.5 * C * krg / dl^2 * 2 ka kb / (ka + kb)                       physics_loss.py:59-60,152-155
+// layout [3][R][D][H][W]
+__global__ void __launch_bounds__(256) k_faces_cf2(const __grid_constant__ SrmDev P, int32_t R, const float* __restrict__ kx,
+                                                   float* __restrict__ faces) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.N) return;
+  const int r = blockIdx.y;
+  const float* kr = kx + (int64_t)r * P.N;
+  const int W = P.W, H = P.H, D = P.D, HW = H * W;
+  const int i = (int)(e % W), j = (int)((e / W) % H), k = (int)(e / HW);
+  const float cx = 0.5f * P.C * P.krg * P.idx * P.idx, cy = 0.5f * P.C * P.krg * P.idy * P.idy, cz = 0.5f * P.C * P.krg * P.idz * P.idz;
+  auto hm = [](float a, float b) { return __fdividef(2.f * a * b, a + b); };
+  const float kc = kr[e];
+  const int64_t RN = (int64_t)R * P.N, o = (int64_t)r * P.N + e;
+  faces[o] = (i + 1 < W) ? cx * hm(kc, kr[e + 1]) : 0.f;
+  faces[RN + o] = (j + 1 < H) ? cy * hm(P.kx_ky * kc, P.kx_ky * kr[e + W]) : 0.f;
+  faces[2 * RN + o] = (k + 1 < D) ? cz * hm(P.kv_kh * kc, P.kv_kh * kr[e + HW]) : 0.f;
+}
+
+// what a thread knows about its place in the tile
+template <int LX>
+struct Place {
+  int lx, ry, x0, y0, own;      // own = offset of the thread's first cell inside a haloed box
+  bool valid;
+  int ring0, ring1;             // halo-ring duty: offsets inside a haloed box (-1: none)
+};
+template <int LX>
+__device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
+  using G = Geo<LX>;
+  Place<LX> t;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  t.lx = lane % LX; t.ry = warp * G::RPW + lane / LX;
+  const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
+  t.x0 = txi * G::TX; t.y0 = tyi * G::TY;
+  t.own = (t.ry + 1) * G::BX + 4 + 4 * t.lx;
+  t.valid = (t.x0 + 4 * t.lx < P.W) && (t.y0 + t.ry < P.H);
+  auto ring = [&](int h) {
+    if (h < G::TX) return 4 + h;                                               // row y0-1
+    if (h < 2 * G::TX) return (G::TY + 1) * G::BX + 4 + (h - G::TX);             // row y0+TY
+    if (h < 2 * G::TX + G::TY) return (h - 2 * G::TX + 1) * G::BX + 3;           // column x0-1
+    if (h < G::RING) return (h - 2 * G::TX - G::TY + 1) * G::BX + 4 + G::TX;     // column x0+TX
+    return -1;
+  };
+  t.ring0 = ring(tid);
+  t.ring1 = ring(tid + NT);
+  static_assert(G::RING <= 2 * NT, "two halo cells per thread at most");
+  return t;
+}
+
+// marks threads that own a column with a well connection (any layer); block-uniform result in *any
+template <int LX>
+__device__ __forceinline__ bool thread_has_well(const Cf2Dev& P, const Place<LX>& t, unsigned char* flags, bool& any) {
+  using G = Geo<LX>;
+  for (int i = threadIdx.x; i < G::TY * G::TX; i += NT) flags[i] = 0;
+  __syncthreads();
+  const int HW = P.H * P.W;
+  for (int w = threadIdx.x; w < P.n_wells; w += NT) {
+    const int rem = P.wells[w].cell % HW;
+    const int j = rem / P.W, i = rem - j * P.W;
+    if (i >= t.x0 && i < t.x0 + G::TX && j >= t.y0 && j < t.y0 + G::TY) flags[(j - t.y0) * G::TX + (i - t.x0)] = 1;
+  }
+  __syncthreads();
+  bool mine = false;
+  if (t.valid) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mine |= flags[t.ry * G::TX + 4 * t.lx + c] != 0;
+  }
+  any = __syncthreads_or(mine ? 1 : 0) != 0;
+  return mine;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward                                                                     physics_loss.py:137-193,787-807
+//   dom = dv * sum_f T_f (G_c + G_n)(p_c - p_n) + q + cA cp (p1 - p0) (+ cT cp),   cp = Sgi (phi A0' + phi cf A0)
+// ------------------------------------------------------------------------------------------------------------
+template <int LX>
+__global__ void __launch_bounds__(NT, 2) k_fwd_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
+                                                   const __grid_constant__ CUtensorMap m_p1, const __grid_constant__ CUtensorMap m_p0,
+                                                   const __grid_constant__ CUtensorMap m_fe, const __grid_constant__ CUtensorMap m_fn,
+                                                   const __grid_constant__ CUtensorMap m_fu) {
+  using G = Geo<LX>;
+  constexpr int S = S_FWD;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_F);
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_F + 3 * G::GPL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_F + 3 * G::GPL + al128((int)sizeof(Cf2Tab)));
+  unsigned char* flags = smem + S * G::STAGE_F + 3 * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  __shared__ double red[4 * 32];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
+  const Place<LX> t = make_place<LX>(P, A.tiles_x);
+  const int D = P.D;
+  auto stage = [&](int s) { return smem + s * G::STAGE_F; };
+  auto issue = [&](int plane) {      // one thread
+    const int s = plane % S;
+    unsigned char* st = stage(s);
+    const uint64_t keep = pol_evict_last(), strm = pol_evict_first();
+    mbar_expect_tx(&full[s], G::TX_F);
+    tma_4d(st + G::O_P1, &m_p1, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
+    tma_4d(st + G::O_P0, &m_p0, &full[s], t.x0, t.y0, plane, b, strm);
+    tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
+    tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
+    tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = 0; k < S && k < D; ++k) issue(k);
+  }
+  for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
+  bool tile_wells = false;
+  const bool has_well = (P.n_wells > 0) ? thread_has_well<LX>(P, t, flags, tile_wells) : false;
+  __syncthreads();
+
+  // per-sample scalars                                                      physics_loss.py:156,171,193
+  const float d1 = A.dt1[b];
+  const float cA = P.dv * P.invDc / d1;
+  const float cT = P.dvDc * 2e-7f / d1;
+  const float mbk = P.dvSgi_phi / (P.Dc * d1);
+  float* domf = A.dom + (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+
+  float a_dom = 0.f, a_tde = 0.f, a_mb = 0.f;
+  double d_dom = 0.0, d_tde = 0.0, d_mb = 0.0, d_ibc = 0.0;
+
+  // z window in registers: plane m (cur) and the arriving plane (next); the upper z-face term of plane m-1
+  float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
+  float a1c[4] = {0.f, 0.f, 0.f, 0.f}, a1lc[4] = {0.f, 0.f, 0.f, 0.f};      // invBg at level n+1 of plane m: value, anchor low part
+  float pn[4], Gn[4], a1n[4], a1ln[4];
+
+  for (int k = 0; k <= D; ++k) {
+    if (k < D) {
+      const int s = k % S;
+      mbar_wait(&full[s], (k / S) & 1);
+      const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
+      float* Gb = Gs + (k % 3) * (G::GPL / 4);
+      a4(pn, lds4(sp1 + t.own));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x = cf2_clamp(T, pn[c]);
+        const int kk = cf2_interval(T, x);
+        const float4 e = T->e0[kk];
+        const float4 f = T->e1[kk];
+        const float dx = x - e.x;
+        const float dA = e.z * dx;
+        a1n[c] = e.y + dA;
+        a1ln[c] = f.w;
+        Gn[c] = a1n[c] * fmaf(f.x, dx, e.w);
+      }
+      sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
+      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
+      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
+    }
+    __syncthreads();
+    // the stage of plane k-2 has been consumed by every thread: refill it
+    if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    const int m = k - 1;
+    if (m >= 0) {
+      const unsigned char* st = stage(m % S);
+      const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
+      const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
+      const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
+      const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
+      const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
+      const float* Gm = Gs + (m % 3) * (G::GPL / 4);
+      float pS[4], pN[4], gS[4], gN[4], fE[4], fS[4], fN[4], fU[4], p0[4];
+      a4(pS, lds4(sp1 + t.own - G::BX)); a4(pN, lds4(sp1 + t.own + G::BX));
+      a4(gS, lds4(Gm + t.own - G::BX)); a4(gN, lds4(Gm + t.own + G::BX));
+      a4(fE, lds4(sfe + t.ry * G::FEX + 4 + 4 * t.lx));
+      a4(fS, lds4(sfn + t.ry * G::TX + 4 * t.lx)); a4(fN, lds4(sfn + (t.ry + 1) * G::TX + 4 * t.lx));
+      a4(fU, lds4(sfu + t.ry * G::TX + 4 * t.lx));
+      a4(p0, lds4(sp0 + t.ry * G::TX + 4 * t.lx));
+      float pW = __shfl_up_sync(0xffffffffu, pc[3], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[3], 1, LX);
+      float fW = __shfl_up_sync(0xffffffffu, fE[3], 1, LX);
+      float pE = __shfl_down_sync(0xffffffffu, pc[0], 1, LX), gE = __shfl_down_sync(0xffffffffu, Gc[0], 1, LX);
+      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = Gm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
+      if (t.lx == LX - 1) { pE = sp1[t.own + 4]; gE = Gm[t.own + 4]; }
+      // x faces, one evaluation per face: F_i = T_i (G_l + G_r)(p_l - p_r); cell c takes -F_c + F_{c+1}
+      float Fx[5];
+      Fx[0] = fW * (gW + Gc[0]) * (pW - pc[0]);
+#pragma unroll
+      for (int i = 1; i < 4; ++i) Fx[i] = fE[i - 1] * (Gc[i - 1] + Gc[i]) * (pc[i - 1] - pc[i]);
+      Fx[4] = fE[3] * (Gc[3] + gE) * (pc[3] - pE);
+      float dvf[4], rest[4], domv[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float flux = Fx[c + 1] - Fx[c];
+        flux = fmaf(fS[c] * (Gc[c] + gS[c]), pc[c] - pS[c], flux);
+        flux = fmaf(fN[c] * (Gc[c] + gN[c]), pc[c] - pN[c], flux);
+        const float fu = fU[c] * (Gc[c] + Gn[c]) * (pc[c] - pn[c]);     // upper z face; the plane above takes -fu
+        flux += fu - fz[c];
+        fz[c] = fu;
+        // cell-local part: level-n PVT, accumulation, truncation term, material balance
+        const float x = cf2_clamp(T, p0[c]);
+        const int kk = cf2_interval(T, x);
+        const float4 e = T->e0[kk];
+        const float4 f = T->e1[kk];
+        const float dx = x - e.x;
+        const float A0 = fmaf(e.z, dx, e.y);
+        const float Ap = (dx < 1e-5f) ? f.y : e.z;          // on a knot: mean of the two slopes
+        const float cp = fmaf(P.K1, Ap, P.K2 * A0);
+        const float tde = cT * cp;
+        dvf[c] = P.dv * flux;
+        rest[c] = P.tde_in_dom ? fmaf(cA * cp, pc[c] - p0[c], tde) : cA * cp * (pc[c] - p0[c]);
+        a_tde = fmaf(tde, tde, a_tde);
+        a_mb += (a1c[c] - A0) + (a1lc[c] - f.w);
+      }
+      if (tile_wells && has_well) {     // wells in this thread's columns (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cell = m * P.H * P.W + cell0 + c;
+          const int first = cf2_lower_bound(P, cell);
+          float q = 0.f, mask = 0.f;
+          for (int w = first; w < P.n_wells && P.wells[w].cell == cell; ++w) { q += A.qw[(int64_t)b * P.n_wells + w]; mask += 1.f; }
+          if (mask != 0.f && t.valid) {
+            dvf[c] += q;                                                      // divq = dv * flux + q    physics_loss.py:174
+            for (int w = first; w < P.n_wells && P.wells[w].cell == cell; ++w) A.divqw[(int64_t)b * P.n_wells + w] = dvf[c];
+            const float ibc = mask * dvf[c];                                  // physics_loss.py:189
+            d_ibc += (double)ibc * (double)ibc;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) domv[c] = dvf[c] + rest[c];
+      if (t.valid) {
+        __stcs(reinterpret_cast<float4*>(domf + (int64_t)m * P.H * P.W), make_float4(domv[0], domv[1], domv[2], domv[3]));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
+      } else {
+        a_tde = 0.f; a_mb = 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
+    if ((k & 7) == 7) { d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f; }
+  }
+  double acc4[4] = {d_dom + (double)a_dom, d_ibc, d_tde + (double)a_tde, (d_mb + (double)a_mb) * (double)mbk};
+  __syncthreads();
+  block_reduce<4>(acc4, red);
+  if (tid == 0) {
+    atomicAdd(&A.sse[SRM_TERM_DOM], acc4[0]);
+    if (acc4[1] != 0.0) atomicAdd(&A.sse[SRM_TERM_IBC], acc4[1]);
+    atomicAdd(&A.sse[SRM_TERM_TDE], acc4[2]);
+    atomicAdd(&A.mb_sum[b], acc4[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// adjoint: what tape.gradient delivers (physics_loss.py:849-859), with d2A/dp2 = 0 and the bracket == 0
+//   gp1 = 2 w_dom dv sum_f (d_c - d_n) T_f [ (G_c + G_n) + G'_c (p_c - p_n) ] + s_c (dq + cA cp) + smb (-dq - mbk A1')
+//   gp0 = s_c cA (cpp (p1 - p0) - cp) + st cT cpp + smb mbk A0',     cpp = Sgi phi cf A0' (inside the clamp)
+//   gdt1 = sum -(s_c acc + st tde)/dt1  (+ the per-sample material-balance part, k_finalize_adj_cf2)
+// ------------------------------------------------------------------------------------------------------------
+template <int LX>
+__global__ void __launch_bounds__(NT, 2) k_adj_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
+                                                   const __grid_constant__ CUtensorMap m_p1, const __grid_constant__ CUtensorMap m_p0,
+                                                   const __grid_constant__ CUtensorMap m_fe, const __grid_constant__ CUtensorMap m_fn,
+                                                   const __grid_constant__ CUtensorMap m_fu, const __grid_constant__ CUtensorMap m_dm) {
+  using G = Geo<LX>;
+  constexpr int S = S_ADJ;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_A);
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_A + 3 * G::GPL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_A + 3 * G::GPL + al128((int)sizeof(Cf2Tab)));
+  unsigned char* flags = smem + S * G::STAGE_A + 3 * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  __shared__ double red[32];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int r = srm_real_of(A.sample_real, b, A.B, A.R);
+  const Place<LX> t = make_place<LX>(P, A.tiles_x);
+  const int D = P.D;
+  auto stage = [&](int s) { return smem + s * G::STAGE_A; };
+  auto issue = [&](int plane) {
+    const int s = plane % S;
+    unsigned char* st = stage(s);
+    const uint64_t keep = pol_evict_last(), strm = pol_evict_first();
+    mbar_expect_tx(&full[s], G::TX_A);
+    tma_4d(st + G::O_P1, &m_p1, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
+    tma_4d(st + G::O_DM, &m_dm, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
+    tma_4d(st + G::O_P0, &m_p0, &full[s], t.x0, t.y0, plane, b, strm);
+    tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
+    tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
+    tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = 0; k < S && k < D; ++k) issue(k);
+  }
+  for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
+  bool tile_wells = false;
+  const bool has_well = (P.n_wells > 0) ? thread_has_well<LX>(P, t, flags, tile_wells) : false;
+  __syncthreads();
+
+  const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_tde = A.dterms[SRM_TERM_TDE];
+  const float sd = 2.f * w_dom;
+  const float d1 = A.dt1[b];
+  const float inv_d1 = 1.f / d1;
+  const float cA = P.dv * P.invDc * inv_d1;
+  const float cT = P.dvDc * 2e-7f * inv_d1;
+  const float mbk = P.dvSgi_phi / (P.Dc * d1);
+  const float smb = 2.f * w_mbc * A.mbc[b];
+  const float sddv = sd * P.dv;
+  const float smbk = smb * mbk;
+  const float wt2 = 2.f * w_tde;
+  const float seed_tde = P.tde_in_dom ? 1.f : 0.f;
+  const int64_t fo = (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+  const float lo = T->lo, hi = T->hi;
+
+  float a_g1 = 0.f;
+  double d_g1 = 0.0;
+  // plane m (cur) in registers; (X, Y) of the lower z face handed up by plane m-1
+  float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
+  float Gpc[4] = {0.f, 0.f, 0.f, 0.f}, Apc[4] = {0.f, 0.f, 0.f, 0.f};
+  float Xz[4] = {0.f, 0.f, 0.f, 0.f}, Yz[4] = {0.f, 0.f, 0.f, 0.f};
+  float pn[4], Gn[4], dn[4], Gpn[4], Apn[4];
+
+  for (int k = 0; k <= D; ++k) {
+    if (k < D) {
+      const int s = k % S;
+      mbar_wait(&full[s], (k / S) & 1);
+      const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
+      const float* sdm = reinterpret_cast<const float*>(stage(s) + G::O_DM);
+      float* Gb = Gs + (k % 3) * (G::GPL / 4);
+      a4(pn, lds4(sp1 + t.own));
+      a4(dn, lds4(sdm + t.own));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x = cf2_clamp(T, pn[c]);
+        const int kk = cf2_interval(T, x);
+        const float4 e = T->e0[kk];
+        const float4 f = T->e1[kk];
+        const float dx = x - e.x;
+        const float A1 = fmaf(e.z, dx, e.y);
+        const float M = fmaf(f.x, dx, e.w);
+        const bool on = dx < 1e-5f;
+        const bool pass = pn[c] >= lo && pn[c] <= hi;          // clamp's gradient mask (PVT_Layer_Subclassed.py:165-167)
+        const float sA = on ? f.y : e.z, sM = on ? f.z : f.x;
+        Gn[c] = A1 * M;
+        Apn[c] = pass ? sA : 0.f;
+        Gpn[c] = pass ? fmaf(sA, M, A1 * sM) : 0.f;
+      }
+      sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
+      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
+      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
+    }
+    __syncthreads();
+    if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    const int m = k - 1;
+    if (m >= 0) {
+      const unsigned char* st = stage(m % S);
+      const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
+      const float* sdm = reinterpret_cast<const float*>(st + G::O_DM);
+      const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
+      const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
+      const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
+      const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
+      const float* Gm = Gs + (m % 3) * (G::GPL / 4);
+      float pS[4], pN[4], gS[4], gN[4], dS[4], dN[4], fE[4], fS[4], fN[4], fU[4], p0[4];
+      a4(pS, lds4(sp1 + t.own - G::BX)); a4(pN, lds4(sp1 + t.own + G::BX));
+      a4(gS, lds4(Gm + t.own - G::BX)); a4(gN, lds4(Gm + t.own + G::BX));
+      a4(dS, lds4(sdm + t.own - G::BX)); a4(dN, lds4(sdm + t.own + G::BX));
+      a4(fE, lds4(sfe + t.ry * G::FEX + 4 + 4 * t.lx));
+      a4(fS, lds4(sfn + t.ry * G::TX + 4 * t.lx)); a4(fN, lds4(sfn + (t.ry + 1) * G::TX + 4 * t.lx));
+      a4(fU, lds4(sfu + t.ry * G::TX + 4 * t.lx));
+      a4(p0, lds4(sp0 + t.ry * G::TX + 4 * t.lx));
+      float pW = __shfl_up_sync(0xffffffffu, pc[3], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[3], 1, LX);
+      float dW = __shfl_up_sync(0xffffffffu, dc[3], 1, LX), fW = __shfl_up_sync(0xffffffffu, fE[3], 1, LX);
+      float pE = __shfl_down_sync(0xffffffffu, pc[0], 1, LX), gE = __shfl_down_sync(0xffffffffu, Gc[0], 1, LX);
+      float dE = __shfl_down_sync(0xffffffffu, dc[0], 1, LX);
+      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = Gm[t.own - 1]; dW = sdm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
+      if (t.lx == LX - 1) { pE = sp1[t.own + 4]; gE = Gm[t.own + 4]; dE = sdm[t.own + 4]; }
+      float g1v[4], g0v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // in-plane faces in gather form; the z faces once per face: this plane's upper face is the next one's lower
+        const float plW = (c == 0) ? pW : pc[c - (c > 0)], glW = (c == 0) ? gW : Gc[c - (c > 0)], dlW = (c == 0) ? dW : dc[c - (c > 0)];
+        const float plE = (c == 3) ? pE : pc[c + (c < 3)], glE = (c == 3) ? gE : Gc[c + (c < 3)], dlE = (c == 3) ? dE : dc[c + (c < 3)];
+        const float tW = (c == 0) ? fW : fE[c - (c > 0)];
+        float g1 = 0.f;
+        g1 = fmaf((dc[c] - dlW) * tW, fmaf(Gpc[c], pc[c] - plW, Gc[c] + glW), g1);
+        g1 = fmaf((dc[c] - dlE) * fE[c], fmaf(Gpc[c], pc[c] - plE, Gc[c] + glE), g1);
+        g1 = fmaf((dc[c] - dS[c]) * fS[c], fmaf(Gpc[c], pc[c] - pS[c], Gc[c] + gS[c]), g1);
+        g1 = fmaf((dc[c] - dN[c]) * fN[c], fmaf(Gpc[c], pc[c] - pN[c], Gc[c] + gN[c]), g1);
+        const float u = (dc[c] - dn[c]) * fU[c];
+        const float X = u * (Gc[c] + Gn[c]), Y = u * (pc[c] - pn[c]);
+        g1 += (X - Xz[c]) + Gpc[c] * (Y + Yz[c]);
+        Xz[c] = X; Yz[c] = Y;
+        g1 *= sddv;
+        // cell-local part
+        const float sc = sd * dc[c];
+        const float x = cf2_clamp(T, p0[c]);
+        const int kk = cf2_interval(T, x);
+        const float4 e = T->e0[kk];
+        const float dx = x - e.x;
+        const float A0 = fmaf(e.z, dx, e.y);
+        const float Ap = (dx < 1e-5f) ? T->e1[kk].y : e.z;
+        const bool pass0 = p0[c] >= lo && p0[c] <= hi;
+        const float Apm = pass0 ? Ap : 0.f;
+        const float cp = fmaf(P.K1, Ap, P.K2 * A0);
+        const float cpp = P.K2 * Apm;
+        const float dp10 = pc[c] - p0[c];
+        const float acc = cA * cp * dp10;
+        const float tde = cT * cp;
+        const float stt = fmaf(seed_tde, sc, wt2 * tde);
+        g1 += sc * (cA * cp) - smbk * Apc[c];
+        g1v[c] = g1;
+        g0v[c] = sc * cA * (cpp * dp10 - cp) + stt * cT * cpp + smbk * Apm;
+        a_g1 -= (sc * acc + stt * tde) * inv_d1;
+      }
+      if (tile_wells && has_well) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cell = m * P.H * P.W + cell0 + c;
+          float dq = 0.f;
+          const int first = cf2_lower_bound(P, cell);
+          for (int w = first; w < P.n_wells && P.wells[w].cell == cell; ++w) dq += A.dqdp[(int64_t)b * P.n_wells + w];
+          g1v[c] += (sd * dc[c] - smb) * dq;
+        }
+      }
+      if (t.valid) {
+        __stcs(reinterpret_cast<float4*>(A.gp0 + fo + (int64_t)m * P.H * P.W), make_float4(g0v[0], g0v[1], g0v[2], g0v[3]));
+        __stcs(reinterpret_cast<float4*>(A.gp1 + fo + (int64_t)m * P.H * P.W), make_float4(g1v[0], g1v[1], g1v[2], g1v[3]));
+      } else {
+        a_g1 = 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; dc[c] = dn[c]; Gpc[c] = Gpn[c]; Apc[c] = Apn[c]; }
+    if ((k & 7) == 7) { d_g1 += (double)a_g1; a_g1 = 0.f; }
+  }
+  double acc1[1] = {d_g1 + (double)a_g1};
+  __syncthreads();
+  block_reduce<1>(acc1, red);
+  if (tid == 0) atomicAdd(&A.gdt1_acc[b], acc1[0]);
+}
+
+// dL/ddt1: block partials plus the material-balance part (mbc_b = -sum q - sum mb, mb ~ 1/dt1); dL/ddt2 == 0
+__global__ void k_finalize_adj_cf2(int32_t B, const double* __restrict__ a1, const double* __restrict__ mb_sum,
+                                   const float* __restrict__ mbc, const float* __restrict__ dterms, const float* __restrict__ dt1,
+                                   float* __restrict__ gdt1, float* __restrict__ gdt2) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const double smb = 2.0 * (double)dterms[SRM_TERM_MBC] * (double)mbc[b];
+    gdt1[b] = (float)(a1[b] + smb * mb_sum[b] / (double)dt1[b]);
+    gdt2[b] = 0.f;
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 4-D map over an (n4, D, H, W) fp32 array, box = bx x by x 1 x 1
+bool make_map(CUtensorMap* m, const float* base, int W, int H, int D, int n4, int bx, int by) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n4};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * D * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+Cf2Dev slim(const SrmDev& P) {
+  Cf2Dev d;
+  d.D = P.D; d.H = P.H; d.W = P.W; d.N = P.N;
+  d.dv = P.dv; d.invDc = P.invDc; d.dvDc = P.dvDc; d.Dc = P.Dc;
+  d.K1 = P.Sgi * P.phi; d.K2 = P.Sgi * P.phicf; d.dvSgi_phi = P.dvSgi_phi;
+  d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells;
+  return d;
+}
+int lanes_for(int W) { return W >= 96 ? 32 : (W >= 48 ? 16 : 8); }
+
+template <int LX>
+int launch_fwd(const SrmHandle* h, const Cf2Args& A0, int32_t B, int32_t R, const float* p0, const float* p1, const float* faces, cudaStream_t s) {
+  using G = Geo<LX>;
+  const SrmDev& P = h->dev;
+  CUtensorMap m1, m0, me, mn, mu;
+  const int64_t RN = (int64_t)R * P.N;
+  if (!(make_map(&m1, p1, P.W, P.H, P.D, B, G::BX, G::BY) && make_map(&m0, p0, P.W, P.H, P.D, B, G::TX, G::TY) &&
+        make_map(&me, faces, P.W, P.H, P.D, R, G::FEX, G::TY) && make_map(&mn, faces + RN, P.W, P.H, P.D, R, G::TX, G::TY + 1) &&
+        make_map(&mu, faces + 2 * RN, P.W, P.H, P.D, R, G::TX, G::TY))) {
+    srm_set_error("cuTensorMapEncodeTiled failed (closed-form forward)");
+    return SRM_ERR_CUDA;
+  }
+  constexpr int sm = G::template total<false>();
+  static bool done[64] = {};
+  if (!done[h->device & 63]) {
+    SRM_CUDA_CHECK(cudaFuncSetAttribute(k_fwd_cf2<LX>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    done[h->device & 63] = true;
+  }
+  Cf2Args A = A0;
+  A.tiles_x = (P.W + G::TX - 1) / G::TX;
+  const dim3 grid((unsigned)(A.tiles_x * ((P.H + G::TY - 1) / G::TY)), (unsigned)B);
+  k_fwd_cf2<LX><<<grid, NT, sm, s>>>(slim(P), A, m1, m0, me, mn, mu);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+template <int LX>
+int launch_adj(const SrmHandle* h, const Cf2Args& A0, int32_t B, int32_t R, const float* p0, const float* p1, const float* faces, cudaStream_t s) {
+  using G = Geo<LX>;
+  const SrmDev& P = h->dev;
+  CUtensorMap m1, m0, me, mn, mu, md;
+  const int64_t RN = (int64_t)R * P.N;
+  if (!(make_map(&m1, p1, P.W, P.H, P.D, B, G::BX, G::BY) && make_map(&m0, p0, P.W, P.H, P.D, B, G::TX, G::TY) &&
+        make_map(&me, faces, P.W, P.H, P.D, R, G::FEX, G::TY) && make_map(&mn, faces + RN, P.W, P.H, P.D, R, G::TX, G::TY + 1) &&
+        make_map(&mu, faces + 2 * RN, P.W, P.H, P.D, R, G::TX, G::TY) && make_map(&md, A0.dom, P.W, P.H, P.D, B, G::BX, G::BY))) {
+    srm_set_error("cuTensorMapEncodeTiled failed (closed-form adjoint)");
+    return SRM_ERR_CUDA;
+  }
+  constexpr int sm = G::template total<true>();
+  static bool done[64] = {};
+  if (!done[h->device & 63]) {
+    SRM_CUDA_CHECK(cudaFuncSetAttribute(k_adj_cf2<LX>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    done[h->device & 63] = true;
+  }
+  Cf2Args A = A0;
+  A.tiles_x = (P.W + G::TX - 1) / G::TX;
+  const dim3 grid((unsigned)(A.tiles_x * ((P.H + G::TY - 1) / G::TY)), (unsigned)B);
+  k_adj_cf2<LX><<<grid, NT, sm, s>>>(slim(P), A, m1, m0, me, mn, mu, md);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+}  // namespace
+
+// the lean pair takes grids with W % 4 == 0 and 16-byte aligned fields; anything else runs kernels_cf.cu
+bool srm_cf2_applicable(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e) {
+  auto ok = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return h->d_cf2 != nullptr && h->dev.W % 4 == 0 && h->dev.W >= 8 && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && get_encode() != nullptr;
+}
+
+int srm_cf2_faces(const SrmHandle* h, int32_t R, const float* kx, float* faces, cudaStream_t s) {
+  const SrmDev& P = h->dev;
+  k_faces_cf2<<<dim3((unsigned)((P.N + 255) / 256), (unsigned)R), 256, 0, s>>>(P, R, kx, faces);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
+int srm_cf2_forward(const SrmHandle* h, int32_t B, int32_t R, const int32_t* sample_real, const float* p0, const float* p1,
+                    const float* dt1, const SrmWs& ws, cudaStream_t s) {
+  Cf2Args A;
+  std::memset(&A, 0, sizeof(A));
+  A.dt1 = dt1; A.sample_real = sample_real; A.qw = ws.qw; A.dqdp = ws.dqdp; A.divqw = ws.divqw;
+  A.dom = ws.dom; A.sse = ws.sse; A.mb_sum = ws.mb_sum; A.T = (const Cf2Tab*)h->d_cf2; A.B = B; A.R = R;
+  switch (lanes_for(h->dev.W)) {
+    case 32: return launch_fwd<32>(h, A, B, R, p0, p1, ws.faces, s);
+    case 16: return launch_fwd<16>(h, A, B, R, p0, p1, ws.faces, s);
+    default: return launch_fwd<8>(h, A, B, R, p0, p1, ws.faces, s);
+  }
+}
+
+int srm_cf2_backward(const SrmHandle* h, int32_t B, int32_t R, const int32_t* sample_real, const float* p0, const float* p1,
+                     const float* dt1, const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2, const SrmWs& ws,
+                     cudaStream_t s) {
+  Cf2Args A;
+  std::memset(&A, 0, sizeof(A));
+  A.dt1 = dt1; A.sample_real = sample_real; A.qw = ws.qw; A.dqdp = ws.dqdp; A.divqw = ws.divqw;
+  A.dom = ws.dom; A.dterms = dterms; A.mbc = ws.mbc; A.gp0 = gp0; A.gp1 = gp1; A.gdt1_acc = ws.gdt1_acc;
+  A.T = (const Cf2Tab*)h->d_cf2; A.B = B; A.R = R;
+  int rc;
+  switch (lanes_for(h->dev.W)) {
+    case 32: rc = launch_adj<32>(h, A, B, R, p0, p1, ws.faces, s); break;
+    case 16: rc = launch_adj<16>(h, A, B, R, p0, p1, ws.faces, s); break;
+    default: rc = launch_adj<8>(h, A, B, R, p0, p1, ws.faces, s); break;
+  }
+  if (rc) return rc;
+  k_finalize_adj_cf2<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(B, ws.gdt1_acc, ws.mb_sum, ws.mbc, dterms, dt1, gdt1, gdt2);
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}

@@ -90,6 +90,8 @@ struct SrmHandle {
   SrmDev dev;          // device parameter block
   WellDev* d_wells;    // device
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
+  void* d_cf2;         // device (tables of the lean closed-form pair, kernels_cf2.cu), may be null
+  int cf_faces_ok, cf_grouped;   // closed form: which per-call scratch the last forward left in the workspace
   float4* d_lut;       // device (exact PVT tabulation), may be null
   int lut_full;        // the table covers the whole clamp range [p_min, p_max]
   int gc_fused;        // gas condensate: the fused pair (gc_fused.cuh) runs, no staged fields in the workspace
@@ -189,6 +191,7 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64
   size_t fb = (size_t)(B * N) * sizeof(float);
   w.faces = nullptr;
   if (mode == SRM_WS_REF_FUSED || mode == SRM_WS_GC || mode == SRM_WS_GC_FUSED) w.faces = (float*)take((size_t)R * face_floats * sizeof(float));
+  if (mode == SRM_WS_CF) w.faces = (float*)take((size_t)R * 3 * (size_t)N * sizeof(float));      // kernels_cf2.cu: [3][R][N]
   w.dom = (float*)take(fb);
   w.A0 = w.A0p = w.A1 = w.G1 = w.A0pp = w.G1p = w.A1p = nullptr;
   w.gc = w.gc_wells = nullptr;
