@@ -87,8 +87,26 @@ int srm_build_cf2(SrmHandle* h, const SrmConfig* cfg) {
 
 namespace {
 
-constexpr int NT = 256;
-constexpr int S_FWD = 3, S_ADJ = 3;      // TMA stages (planes in flight)
+#ifndef CF2_NT
+#define CF2_NT 256
+#endif
+#ifndef CF2_OCCF
+#define CF2_OCCF 2
+#endif
+#ifndef CF2_OCCA
+#define CF2_OCCA 2
+#endif
+#ifndef CF2_SF
+#define CF2_SF 3
+#endif
+#ifndef CF2_SA
+#define CF2_SA 3
+#endif
+#ifndef CF2_LXMAX
+#define CF2_LXMAX 32
+#endif
+constexpr int NT = CF2_NT;
+constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // TMA stages (planes in flight)
 
 __host__ __device__ constexpr int al128(int b) { return (b + 127) & ~127; }
 
@@ -215,7 +233,7 @@ template <int LX>
 struct Place {
   int lx, ry, x0, y0, own;      // own = offset of the thread's first cell inside a haloed box
   bool valid;
-  int ring0, ring1;             // halo-ring duty: offsets inside a haloed box (-1: none)
+  int ring0, ring1, ring2;      // halo-ring duty: offsets inside a haloed box (-1: none)
 };
 template <int LX>
 __device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
@@ -236,7 +254,8 @@ __device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
   };
   t.ring0 = ring(tid);
   t.ring1 = ring(tid + NT);
-  static_assert(G::RING <= 2 * NT, "two halo cells per thread at most");
+  t.ring2 = (G::RING > 2 * NT) ? ring(tid + 2 * NT) : -1;
+  static_assert(G::RING <= 3 * NT, "three halo cells per thread at most");
   return t;
 }
 
@@ -267,7 +286,7 @@ __device__ __forceinline__ bool thread_has_well(const Cf2Dev& P, const Place<LX>
 //   dom = dv * sum_f T_f (G_c + G_n)(p_c - p_n) + q + cA cp (p1 - p0) (+ cT cp),   cp = Sgi (phi A0' + phi cf A0)
 // ------------------------------------------------------------------------------------------------------------
 template <int LX>
-__global__ void __launch_bounds__(NT, 2) k_fwd_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
+__global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
                                                    const __grid_constant__ CUtensorMap m_p1, const __grid_constant__ CUtensorMap m_p0,
                                                    const __grid_constant__ CUtensorMap m_fe, const __grid_constant__ CUtensorMap m_fn,
                                                    const __grid_constant__ CUtensorMap m_fu) {
@@ -346,6 +365,7 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_cf2(const __grid_constant__ Cf2De
       sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
       if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
       if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
+      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G(T, sp1[t.ring2]);
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
@@ -451,7 +471,7 @@ __global__ void __launch_bounds__(NT, 2) k_fwd_cf2(const __grid_constant__ Cf2De
 //   gdt1 = sum -(s_c acc + st tde)/dt1  (+ the per-sample material-balance part, k_finalize_adj_cf2)
 // ------------------------------------------------------------------------------------------------------------
 template <int LX>
-__global__ void __launch_bounds__(NT, 2) k_adj_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
+__global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant__ Cf2Dev P, const __grid_constant__ Cf2Args A,
                                                    const __grid_constant__ CUtensorMap m_p1, const __grid_constant__ CUtensorMap m_p0,
                                                    const __grid_constant__ CUtensorMap m_fe, const __grid_constant__ CUtensorMap m_fn,
                                                    const __grid_constant__ CUtensorMap m_fu, const __grid_constant__ CUtensorMap m_dm) {
@@ -545,6 +565,7 @@ __global__ void __launch_bounds__(NT, 2) k_adj_cf2(const __grid_constant__ Cf2De
       sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
       if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
       if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
+      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G(T, sp1[t.ring2]);
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
@@ -686,7 +707,7 @@ Cf2Dev slim(const SrmDev& P) {
   d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells;
   return d;
 }
-int lanes_for(int W) { return W >= 96 ? 32 : (W >= 48 ? 16 : 8); }
+int lanes_for(int W) { const int l = W >= 96 ? 32 : (W >= 48 ? 16 : 8); return l > CF2_LXMAX ? CF2_LXMAX : l; }
 
 template <int LX>
 int launch_fwd(const SrmHandle* h, const Cf2Args& A0, int32_t B, int32_t R, const float* p0, const float* p1, const float* faces, cudaStream_t s) {

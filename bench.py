@@ -314,6 +314,16 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = world * N * reps * args.steps / (ms * 1e-3)
 
+    if args.kernels_only:       # tuning runs: the device-timed step alone
+        if rank == 0:
+            peak, _ = peak_hbm()
+            print(json.dumps({"workload": args.workload, "numerics": args.numerics, "ms_per_step": ms_step, "fwd_ms": float(fwd_ms),
+                              "bwd_ms": float(bwd_ms), "value": value,
+                              "frac_step": N * reps * alg_bytes_per_cell(T, gc) / (ms_step * 1e-3) / 1e9 / peak}))
+        if distributed:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
     # ---- end to end through the public API with host buffers: srm.engine.HostPipeline (chunks of whole
     # realisations; H2D, kernels and D2H overlap on three streams)
     host = {k: v.cpu().pin_memory() for k, v in d.items()}
@@ -553,6 +563,7 @@ def main():
     ap.add_argument("--numerics", default="reference", choices=["reference", "closed_form"])
     ap.add_argument("--K", type=int, default=0, help="override realisations per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="tuning: print the device-timed step only (no e2e, graph, glue, cpu legs)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="realisation chunks of the host-buffer pipeline")
     ap.add_argument("--no-pvt-lut", action="store_true", help="reference numerics: evaluate the 37-term spline per cell instead of the exact table")
     args = ap.parse_args()

@@ -107,12 +107,27 @@ def where(cond, a, b):
     return torch.where(_t(cond).to(torch.bool) if not isinstance(cond, torch.Tensor) else cond, _t(a), _t(b))
 
 
+def _pair(a, b):
+    """python scalars take the tensor operand's dtype (TF's promotion of weak scalars)"""
+    ta, tb = isinstance(a, torch.Tensor), isinstance(b, torch.Tensor)
+    if ta and not tb:
+        return a, torch.as_tensor(np.asarray(b), dtype=a.dtype)
+    if tb and not ta:
+        return torch.as_tensor(np.asarray(a), dtype=b.dtype), b
+    return _t(a), _t(b)
+
+
 def maximum(a, b):
-    return torch.maximum(_t(a), _t(b))
+    """value of tf.maximum; gradient as TensorFlow's MaximumGrad routes it: to x where x >= y (ties go to the FIRST
+    argument), to y elsewhere -- torch.maximum would split a tie 50/50"""
+    a, b = _pair(a, b)
+    return torch.where(a >= b, a, b)
 
 
 def minimum(a, b):
-    return torch.minimum(_t(a), _t(b))
+    """tf.minimum; MinimumGrad: to x where x <= y (ties to the first argument)"""
+    a, b = _pair(a, b)
+    return torch.where(a <= b, a, b)
 
 
 def function(*a, **k):
@@ -249,7 +264,10 @@ def pow(x, y):            # noqa: A001
 
 
 def clip_by_value(x, lo, hi):
-    return torch.minimum(torch.maximum(_t(x), _t(lo, _t(x).dtype)), _t(hi, _t(x).dtype))
+    """tf.clip_by_value; ClipByValueGrad: 1 to x on the closed interval [lo, hi], to lo where x < lo, to hi where x > hi"""
+    x = _t(x)
+    lo, hi = _t(lo, x.dtype), _t(hi, x.dtype)
+    return torch.where(x < lo, lo, torch.where(x > hi, hi, x))
 
 
 linalg = types.SimpleNamespace(solve=lambda a, b: torch.linalg.solve(_t(a), _t(b)))
@@ -272,9 +290,13 @@ class GradientTape:
         if isinstance(x, (list, tuple)):
             if len(x) == 0:
                 return []
+            if not y.requires_grad:
+                return [torch.zeros_like(v) for v in x]
             g = torch.autograd.grad(y, list(x), grad_outputs=torch.ones_like(y), retain_graph=True, allow_unused=True)
             return [torch.zeros_like(v) if gi is None else gi for gi, v in zip(g, x)]
-        return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True)[0]
+        # a watched tensor that is itself part of an enclosing graph (PVTLayer's inner tape under the loss tape): the
+        # derivative stays differentiable, as TensorFlow's nested tapes record it
+        return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True, create_graph=x.grad_fn is not None)[0]
 
 
 class _Layer:

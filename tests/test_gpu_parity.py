@@ -438,3 +438,62 @@ def test_cuda_terms_and_counts_against_the_reference_pinn_batch_sse_grad(pvt_lut
         assert np.isclose(terms[0, T.index(name)], wsse[i] / w, rtol=RTOL), name
         assert terms[1, T.index(name)] == cnt[i] == B * H * W, name
     eng.close()
+
+
+# ---- the adjoint against gradients of the reference's OWN op graph ----------------------------------------------------
+# tests/golden/reference_dg_grad.npz (make_reference_grad_golden.py): tape.gradient of every weighted SSE term through
+# pinn_batch_sse_grad -> physics_error_gas_2D -> PVTLayer (nested tape) and WellRatesPressure, all the reference's own
+# code, with the network outputs as the trainable variables.  Gate: H3, |cuda - ref| <= rtol |ref| + rtol max|ref|.
+# The oracle (fp32 autograd of the restatement) sits at rtol 1.0e-5 (gp1), 1.4e-5 (gdt1), 2.2e-5 (gp0) from the same
+# goldens (tests/test_oracle.py) -- two fp32 backward passes of one formula chain in different accumulation orders -- so
+# the gates are 2e-5 / 2e-5 / 3e-5, and 3e-4 for gp0 of the `dom` term of case b (second spline derivative = fp32 noise).
+GRAD_GATES = {"gp1": 2e-5, "gdt1": 2e-5, "gp0": 3e-5}
+
+
+def h3_min_rtol(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    den = np.abs(b) + np.abs(b).max()
+    return float((np.abs(a - b) / np.maximum(den, 1e-300)).max()) if den.max() > 0 else float(np.abs(a).max())
+
+
+@pytest.mark.parametrize("pvt_lut", LUT_MODES)
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_cuda_adjoint_equals_the_reference_graph_gradients(case, pvt_lut, capsys):
+    g = np.load(os.path.join(U.GOLDEN, "reference_dg_grad.npz"))
+    W, H, B = int(g[f"{case}_W"]), int(g[f"{case}_H"]), int(g[f"{case}_B"])
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for r in g[f"{case}_wells"]]
+    spec = srm.PhysicsSpec(D=1, H=H, W=W, wells=srm.config.wells_from_connections(conns),
+                           use_blocking_factor=bool(g[f"{case}_blocking"]), n_intervals=8)
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    eng = srm.SrmPhysics(spec, tabs, device=0, pvt_lut=pvt_lut)
+    dev = eng.device
+    tt = lambda k, dt=torch.float32: torch.as_tensor(g[f"{case}_{k}"]).to(dev, dt).contiguous()
+    d = dict(kx=tt("kx"), sample_real=tt("sample_real", torch.int32), p0=tt("p0"), p1=tt("p1"), dt1=tt("dt1"), dt2=tt("dt2"), t1=tt("t1"))
+    fw = eng.forward(**d)
+    nwt = g[f"{case}_nwt"]
+    # the reference's weighted SSEs: batch, dom, dbc, nbc, ibc, ic, mbc, cmbc (physics_loss.py:864)
+    terms = fw["terms"][0].cpu().numpy()
+    T = srm._lib.TERM_NAMES
+    for name, i, w in (("dom", 1, nwt[0]), ("ibc", 4, nwt[3]), ("mbc", 6, nwt[5])):
+        assert np.isclose(w * terms[T.index(name)], g[f"{case}_wsse"][i], rtol=RTOL), name
+    sel = {"batch": [nwt[0], nwt[3], nwt[5], 0, 0, 0, 0, 0], "dom": [nwt[0], 0, 0, 0, 0, 0, 0, 0],
+           "ibc": [0, nwt[3], 0, 0, 0, 0, 0, 0], "mbc": [0, 0, nwt[5], 0, 0, 0, 0, 0]}
+    worst = {}
+    for name, wts in sel.items():
+        out = eng.backward(dterms=torch.tensor(wts, dtype=torch.float32, device=dev), **d)
+        torch.cuda.synchronize()
+        got = dict(zip(("gp0", "gp1", "gdt1", "gdt2"), (t.cpu().numpy().reshape(g[f"{case}_g_{name}_{k}"].shape)
+                                                        for t, k in zip(out, ("p0", "p1", "dt1", "dt2")))))
+        for k in ("gp0", "gp1", "gdt1"):
+            ref = g[f"{case}_g_{name}_{k[1:]}"]
+            m = h3_min_rtol(got[k], ref)
+            worst[k] = max(worst.get(k, 0.0), m if (case, name, k) != ("b", "dom", "gp0") else 0.0)
+            gate = 3e-4 if (case, name, k) == ("b", "dom", "gp0") else GRAD_GATES[k]
+            assert m <= gate, (case, name, k, m)
+        s = max(np.abs(g[f"{case}_g_{name}_dt1"]).max(), 1e-300)
+        assert np.abs(got["gdt2"]).max() <= 1e-4 * s
+    with capsys.disabled():
+        print(f"\n[reference-graph gradients, case {case}, pvt_lut={pvt_lut}] smallest passing H3 rtol: "
+              + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    eng.close()

@@ -7,6 +7,7 @@ import csv, os, re, subprocess, sys, tempfile
 from collections import defaultdict
 
 rep, obj, want = sys.argv[1], os.path.abspath(sys.argv[2]), sys.argv[3]
+want_rep = os.environ.get('REP_NAME', want)      # demangled name in the report when it differs (templates)
 N = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 
 with tempfile.TemporaryDirectory() as td:
@@ -33,7 +34,7 @@ kern = None; hdr = None; data = []
 for r in rows:
     if r and r[0] == 'Kernel Name':
         if kern is not None and data: break
-        kern = r[1] if want in r[1] else None; data = []; continue
+        kern = r[1] if want_rep in r[1] else None; data = []; continue
     if r and r[0] == 'Address': hdr = r; continue
     if kern is not None and r: data.append(r)
 assert data, 'kernel not in report'
