@@ -31,6 +31,7 @@ struct Cf2Tab {
   float4 e0[SRM_MAXK + 1];         // {x0, f0[invBg], slope[invBg], f0[invug]}       anchor form: f = f0 + slope (x - x0)
   float4 e1[SRM_MAXK + 1];         // {slope[invug], on-knot slope[invBg], on-knot slope[invug], low part of f0[invBg]}
   unsigned char bucket[CF2_NB];    // bucket -> interval of (bucket start - margin); at most one knot per bucket window
+  float4 cur0, cur1;               // shared-memory copy only: the CTA's cached interval {lo, hi, x0, f0[invBg]}, {slope[invBg], f0[invug], slope[invug], low part}
 };
 
 int srm_build_cf2(SrmHandle* h, const SrmConfig* cfg) {
@@ -105,8 +106,16 @@ namespace {
 #ifndef CF2_LXMAX
 #define CF2_LXMAX 32
 #endif
+#define CF2_STR2(x) #x
+#define CF2_STR(x) CF2_STR2(x)
+#ifdef CF2_UNROLL
+#define CF2_LOOP_PRAGMA _Pragma(CF2_STR(unroll CF2_UNROLL))
+#else
+#define CF2_LOOP_PRAGMA
+#endif
 constexpr int NT = CF2_NT;
 constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // TMA stages (planes in flight)
+static_assert(S_FWD >= 3 && S_ADJ >= 3, "plane k is waited for at the top of iteration k and refilled stages are issued at k-2+S: fewer than 3 stages deadlocks");
 
 __host__ __device__ constexpr int al128(int b) { return (b + 127) & ~127; }
 
@@ -191,6 +200,26 @@ __device__ __forceinline__ float cf2_G(const Cf2Tab* __restrict__ T, float p) {
   return fmaf(e.z, dx, e.y) * fmaf(T->e1[k].x, dx, e.w);
 }
 
+// The CTA's cached interval: pressures are smooth, so almost every value a tile meets lies strictly inside ONE knot
+// interval; its coefficients sit in two 16-byte shared words every thread reads by broadcast, and a value inside
+// (lo, hi) costs a clamp, two compares and the polynomial -- no bucket, no knot compare, no dependent table loads.
+// Anything else (another interval, exactly on a knot) takes the table path above.
+__device__ __forceinline__ void cf2_cache_interval(Cf2Tab* T, float p) {      // one thread
+  const float x = cf2_clamp(T, p);
+  const int k = cf2_interval(T, x);
+  const float4 e = T->e0[k], f = T->e1[k];
+  // (lo, hi) also stays inside the clamp range, so a value strictly inside needs no clamp and passes its gradient mask
+  T->cur0 = make_float4(fmaxf(k > 0 ? T->hik[k - 1] : -INFINITY, T->lo), fminf(T->hik[k], T->hi), e.x, e.y);
+  T->cur1 = make_float4(e.z, e.w, f.x, f.w);
+}
+__device__ __forceinline__ float cf2_G_cached(const Cf2Tab* __restrict__ T, const float4 c0, const float4 c1, float p) {
+  if (p > c0.x && p < c0.y) {
+    const float dx = p - c0.z;
+    return fmaf(c1.x, dx, c0.w) * fmaf(c1.z, dx, c1.y);
+  }
+  return cf2_G(T, p);
+}
+
 // first connection (sorted by cell) with cell >= c: well_lower_bound of common.cuh on the slim parameter block
 struct Cf2Dev {
   int32_t D, H, W, N;
@@ -253,7 +282,11 @@ __device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
     return -1;
   };
   t.ring0 = ring(tid);
+#ifdef CF2_RING_LAST
+  t.ring1 = ring(NT + (NT - 1 - tid));      // the second halo cell goes to the LAST warp: warp 0 already issues the TMA copies
+#else
   t.ring1 = ring(tid + NT);
+#endif
   t.ring2 = (G::RING > 2 * NT) ? ring(tid + 2 * NT) : -1;
   static_assert(G::RING <= 3 * NT, "three halo cells per thread at most");
   return t;
@@ -338,11 +371,18 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   float a_dom = 0.f, a_tde = 0.f, a_mb = 0.f;
   double d_dom = 0.0, d_tde = 0.0, d_mb = 0.0, d_ibc = 0.0;
 
+  // the cached interval: that of the tile's first pressure of plane 0
+  mbar_wait(&full[0], 0);
+  if (tid == 0) cf2_cache_interval(T, reinterpret_cast<const float*>(stage(0) + G::O_P1)[G::BX + 4]);
+  __syncthreads();
+  const float4 c0 = T->cur0, c1 = T->cur1;
+
   // z window in registers: plane m (cur) and the arriving plane (next); the upper z-face term of plane m-1
   float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
   float a1c[4] = {0.f, 0.f, 0.f, 0.f}, a1lc[4] = {0.f, 0.f, 0.f, 0.f};      // invBg at level n+1 of plane m: value, anchor low part
   float pn[4], Gn[4], a1n[4], a1ln[4];
 
+  CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
     if (k < D) {
       const int s = k % S;
@@ -350,22 +390,32 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
       float* Gb = Gs + (k % 3) * (G::GPL / 4);
       a4(pn, lds4(sp1 + t.own));
+      bool in = true;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float x = cf2_clamp(T, pn[c]);
-        const int kk = cf2_interval(T, x);
-        const float4 e = T->e0[kk];
-        const float4 f = T->e1[kk];
-        const float dx = x - e.x;
-        const float dA = e.z * dx;
-        a1n[c] = e.y + dA;
-        a1ln[c] = f.w;
-        Gn[c] = a1n[c] * fmaf(f.x, dx, e.w);
+        in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
+        const float dx = pn[c] - c0.z;
+        a1n[c] = fmaf(c1.x, dx, c0.w);
+        a1ln[c] = c1.w;
+        Gn[c] = a1n[c] * fmaf(c1.z, dx, c1.y);
+      }
+      if (!in) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x = cf2_clamp(T, pn[c]);
+          const int kk = cf2_interval(T, x);
+          const float4 e = T->e0[kk];
+          const float4 f = T->e1[kk];
+          const float dx = x - e.x;
+          a1n[c] = fmaf(e.z, dx, e.y);
+          a1ln[c] = f.w;
+          Gn[c] = a1n[c] * fmaf(f.x, dx, e.w);
+        }
       }
       sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
-      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
-      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
-      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G(T, sp1[t.ring2]);
+      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
+      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
+      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
@@ -401,6 +451,29 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       for (int i = 1; i < 4; ++i) Fx[i] = fE[i - 1] * (Gc[i - 1] + Gc[i]) * (pc[i - 1] - pc[i]);
       Fx[4] = fE[3] * (Gc[3] + gE) * (pc[3] - pE);
       float dvf[4], rest[4], domv[4];
+      // level-n PVT of the four cells: A0 = invBg(p0), Ap = its slope, low part of the anchor value
+      float A0[4], Ap[4], A0l[4];
+      bool in0 = true;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
+        A0[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
+        Ap[c] = c1.x;
+        A0l[c] = c1.w;
+      }
+      if (!in0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x = cf2_clamp(T, p0[c]);
+          const int kk = cf2_interval(T, x);
+          const float4 e = T->e0[kk];
+          const float4 f = T->e1[kk];
+          const float dx = x - e.x;
+          A0[c] = fmaf(e.z, dx, e.y);
+          Ap[c] = (dx < 1e-5f) ? f.y : e.z;          // on a knot: mean of the two slopes
+          A0l[c] = f.w;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float flux = Fx[c + 1] - Fx[c];
@@ -409,20 +482,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         const float fu = fU[c] * (Gc[c] + Gn[c]) * (pc[c] - pn[c]);     // upper z face; the plane above takes -fu
         flux += fu - fz[c];
         fz[c] = fu;
-        // cell-local part: level-n PVT, accumulation, truncation term, material balance
-        const float x = cf2_clamp(T, p0[c]);
-        const int kk = cf2_interval(T, x);
-        const float4 e = T->e0[kk];
-        const float4 f = T->e1[kk];
-        const float dx = x - e.x;
-        const float A0 = fmaf(e.z, dx, e.y);
-        const float Ap = (dx < 1e-5f) ? f.y : e.z;          // on a knot: mean of the two slopes
-        const float cp = fmaf(P.K1, Ap, P.K2 * A0);
+        // cell-local part: accumulation, truncation term, material balance
+        const float cp = fmaf(P.K1, Ap[c], P.K2 * A0[c]);
         const float tde = cT * cp;
         dvf[c] = P.dv * flux;
         rest[c] = P.tde_in_dom ? fmaf(cA * cp, pc[c] - p0[c], tde) : cA * cp * (pc[c] - p0[c]);
         a_tde = fmaf(tde, tde, a_tde);
-        a_mb += (a1c[c] - A0) + (a1lc[c] - f.w);
+        a_mb += (a1c[c] - A0[c]) + (a1lc[c] - A0l[c]);
       }
       if (tile_wells && has_well) {     // wells in this thread's columns (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
 #pragma unroll
@@ -531,12 +597,17 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
 
   float a_g1 = 0.f;
   double d_g1 = 0.0;
+  mbar_wait(&full[0], 0);
+  if (tid == 0) cf2_cache_interval(T, reinterpret_cast<const float*>(stage(0) + G::O_P1)[G::BX + 4]);
+  __syncthreads();
+  const float4 c0 = T->cur0, c1 = T->cur1;
   // plane m (cur) in registers; (X, Y) of the lower z face handed up by plane m-1
   float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
   float Gpc[4] = {0.f, 0.f, 0.f, 0.f}, Apc[4] = {0.f, 0.f, 0.f, 0.f};
   float Xz[4] = {0.f, 0.f, 0.f, 0.f}, Yz[4] = {0.f, 0.f, 0.f, 0.f};
   float pn[4], Gn[4], dn[4], Gpn[4], Apn[4];
 
+  CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
     if (k < D) {
       const int s = k % S;
@@ -546,26 +617,39 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       float* Gb = Gs + (k % 3) * (G::GPL / 4);
       a4(pn, lds4(sp1 + t.own));
       a4(dn, lds4(sdm + t.own));
+      bool in = true;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float x = cf2_clamp(T, pn[c]);
-        const int kk = cf2_interval(T, x);
-        const float4 e = T->e0[kk];
-        const float4 f = T->e1[kk];
-        const float dx = x - e.x;
-        const float A1 = fmaf(e.z, dx, e.y);
-        const float M = fmaf(f.x, dx, e.w);
-        const bool on = dx < 1e-5f;
-        const bool pass = pn[c] >= lo && pn[c] <= hi;          // clamp's gradient mask (PVT_Layer_Subclassed.py:165-167)
-        const float sA = on ? f.y : e.z, sM = on ? f.z : f.x;
+      for (int c = 0; c < 4; ++c) {        // strictly inside the cached interval: inside the clamp too, off every knot
+        in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
+        const float dx = pn[c] - c0.z;
+        const float A1 = fmaf(c1.x, dx, c0.w);
+        const float M = fmaf(c1.z, dx, c1.y);
         Gn[c] = A1 * M;
-        Apn[c] = pass ? sA : 0.f;
-        Gpn[c] = pass ? fmaf(sA, M, A1 * sM) : 0.f;
+        Apn[c] = c1.x;
+        Gpn[c] = fmaf(c1.x, M, A1 * c1.z);
+      }
+      if (!in) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x = cf2_clamp(T, pn[c]);
+          const int kk = cf2_interval(T, x);
+          const float4 e = T->e0[kk];
+          const float4 f = T->e1[kk];
+          const float dx = x - e.x;
+          const float A1 = fmaf(e.z, dx, e.y);
+          const float M = fmaf(f.x, dx, e.w);
+          const bool on = dx < 1e-5f;
+          const bool pass = pn[c] >= lo && pn[c] <= hi;          // clamp's gradient mask (PVT_Layer_Subclassed.py:165-167)
+          const float sA = on ? f.y : e.z, sM = on ? f.z : f.x;
+          Gn[c] = A1 * M;
+          Apn[c] = pass ? sA : 0.f;
+          Gpn[c] = pass ? fmaf(sA, M, A1 * sM) : 0.f;
+        }
       }
       sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
-      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G(T, sp1[t.ring0]);
-      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G(T, sp1[t.ring1]);
-      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G(T, sp1[t.ring2]);
+      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
+      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
+      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
     } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
@@ -597,6 +681,28 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       if (t.lx == 0) { pW = sp1[t.own - 1]; gW = Gm[t.own - 1]; dW = sdm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
       if (t.lx == LX - 1) { pE = sp1[t.own + 4]; gE = Gm[t.own + 4]; dE = sdm[t.own + 4]; }
       float g1v[4], g0v[4];
+      // level-n PVT: A0 = invBg(p0), Ap = its slope, Apm = the slope behind the clamp's gradient mask
+      float A0v[4], Apv[4], Apmv[4];
+      bool in0 = true;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
+        A0v[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
+        Apv[c] = c1.x;
+        Apmv[c] = c1.x;
+      }
+      if (!in0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x = cf2_clamp(T, p0[c]);
+          const int kk = cf2_interval(T, x);
+          const float4 e = T->e0[kk];
+          const float dx = x - e.x;
+          A0v[c] = fmaf(e.z, dx, e.y);
+          Apv[c] = (dx < 1e-5f) ? T->e1[kk].y : e.z;
+          Apmv[c] = (p0[c] >= lo && p0[c] <= hi) ? Apv[c] : 0.f;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         // in-plane faces in gather form; the z faces once per face: this plane's upper face is the next one's lower
@@ -615,14 +721,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         g1 *= sddv;
         // cell-local part
         const float sc = sd * dc[c];
-        const float x = cf2_clamp(T, p0[c]);
-        const int kk = cf2_interval(T, x);
-        const float4 e = T->e0[kk];
-        const float dx = x - e.x;
-        const float A0 = fmaf(e.z, dx, e.y);
-        const float Ap = (dx < 1e-5f) ? T->e1[kk].y : e.z;
-        const bool pass0 = p0[c] >= lo && p0[c] <= hi;
-        const float Apm = pass0 ? Ap : 0.f;
+        const float A0 = A0v[c], Ap = Apv[c], Apm = Apmv[c];
         const float cp = fmaf(P.K1, Ap, P.K2 * A0);
         const float cpp = P.K2 * Apm;
         const float dp10 = pc[c] - p0[c];

@@ -30,8 +30,7 @@ class _SrmPhysicsFn(torch.autograd.Function):
     def forward(ctx, engine, kx, sample_real, t1, p0, p1, dt1, dt2):
         p0c, p1c, d1c, d2c = (t.detach().contiguous() for t in (p0, p1, dt1, dt2))
         fw = engine.forward(kx, sample_real, p0c, p1c, d1c, d2c, t1, save_for_backward=True)
-        terms = fw["terms"]
-        sdist.allreduce_terms(terms)            # ranks hold disjoint sample shards; 64 bytes
+        terms = fw["terms"]                     # this rank's shard: the caller reduces AFTER it has queued the backward
         ctx.engine = engine
         ctx.save_for_backward(kx, sample_real, t1, p0c, p1c, d1c, d2c)
         return terms
@@ -52,7 +51,6 @@ class _SrmPhysicsGcFn(torch.autograd.Function):
         c = [t.detach().contiguous() for t in (p0, p1, sg0, sg1, so0, so1, dt1, dt2)]
         fw = engine.forward_gc(kx, sample_real, *c, t1, save_for_backward=True)
         terms = fw["terms"]
-        sdist.allreduce_terms(terms)
         ctx.engine = engine
         ctx.save_for_backward(kx, sample_real, t1, *c)
         return terms
@@ -180,8 +178,7 @@ class PhysicsLoss:
             terms = _SrmPhysicsFn.apply(eng, kx, sample_real, t1, p0, p1, dt1, dt2)
         wvec = torch.tensor([self.weights[k] for k in self.loss_keys["gas"]], device=eng.device)
         slots = torch.tensor([_SLOT[k] for k in self.loss_keys["gas"]], device=eng.device)
-        wsse = wvec * terms[0][slots]                                             # physics_loss.py:809-819
-        loss = wsse.sum()
+        loss = (wvec * terms[0][slots]).sum()                                     # physics_loss.py:809-819
         params = [self._params(m) for m in self.trainable_models]
         flat = [p for ps in params for p in ps]
         grads = torch.autograd.grad(loss, flat, allow_unused=True) if flat else []
@@ -189,6 +186,13 @@ class PhysicsLoss:
         for ps in params:
             out.append([torch.zeros_like(p) if g is None else g for p, g in zip(ps, grads[i:i + len(ps)])])
             i += len(ps)
+        # Ranks hold disjoint sample shards.  The adjoint's upstream weights are the constants `wvec`, not the reduced
+        # terms, so the 128-byte all-reduce of the REPORTED terms is queued only now, behind the backward kernels: no
+        # rank waits for another in the middle of a step (reducing inside the forward re-synchronised the ranks before
+        # every adjoint).  The handle is waited on where the values are first read.
+        terms = terms.detach().clone()
+        sdist.allreduce_terms_async(terms).wait()
+        wsse = wvec * terms[0][slots]
         counts = terms[1][slots]
         wmse = wsse / torch.clamp(counts, min=1.0)                                # zeros_to_ones, :835-846
         phases = [wmse.detach()], [wsse.detach()], [counts.detach()]

@@ -16,8 +16,12 @@ dL/ddt2) over one batch of synthetic input of the named BASELINE config.  Prints
   cpu_baseline  the oracle (a port of the reference's TF op graph; TensorFlow is not installable
              here) on the box's host cores, bounded sample of the same workload
 
-N > 1 (torchrun): weak scaling -- every rank runs the same per-GPU workload on its own
-realisations; the only collective is the all-reduce of the 16-float loss-term vector (NCCL).
+Default workload: cfg5 (256 x 256 x 64, T = 32, K = 8 realisations per GPU, 2048 well connections with the
+blocking-factor integral) -- the grid BASELINE.json quotes its 70 %-of-HBM target on.  N > 1 (torchrun): weak scaling,
+every rank runs the same per-GPU workload on its own realisations (cfg5's batch sweep: K = 8 N in total);
+`--strong` shards the named config's K realisations over the ranks instead (cfg3: K = 64 over 1/2/4/8 GPUs).  The only
+collective is the all-reduce of the 16-float loss-term vector (NCCL), queued behind the adjoint and waited on one step
+later, so no rank waits for another inside a step.
 """
 import argparse
 import json
@@ -142,6 +146,16 @@ def cpu_oracle_throughput(name, target_seconds=15.0, max_samples=None):
     import srm_b200 as srm
     from concurrent.futures import ThreadPoolExecutor
     c, spec = workload(name)
+    # grids beyond ~1 M cells: the CPU unit of work is a z-slab of the grid (same x-y extent, same arithmetic per cell,
+    # the lattice wells completed in the slab's layers), so that one round of one-unit-per-core ends in seconds
+    slab = None
+    if spec.n_cells > (1 << 21):
+        Ds = max(1, (1 << 20) // (spec.W * spec.H))
+        if Ds < spec.D:
+            slab = Ds
+            wl = srm.config.lattice_wells(spec.W, spec.H, Ds) if name == "cfg5" else srm.config.scaled_default_wells(spec.W, spec.H, Ds)
+            spec = srm.PhysicsSpec(D=Ds, H=spec.H, W=spec.W, wells=wl, use_blocking_factor=spec.use_blocking_factor,
+                                   n_intervals=spec.n_intervals, fluid_type=spec.fluid_type)
     cores = os.cpu_count() or 1
     torch.set_num_threads(1)        # parallelism comes from sample shards, one per core
     cols = O.load_pvt_table(os.path.join(ROOT, "tests", "golden", "pvt_table.npz"))
@@ -181,8 +195,10 @@ def cpu_oracle_throughput(name, target_seconds=15.0, max_samples=None):
                 break
     el = time.perf_counter() - t0
     return dict(value=done / el, unit=UNIT, cores=cores, kind="port",
-                sample=f"{done // N} samples of the {name} grid ({spec.W}x{spec.H}x{spec.D}) fwd+autograd backward, "
-                       f"{el:.1f} s, {cores} threads over independent samples"), done, el
+                sample=(f"{done // N} samples of the {name} grid ({spec.W}x{spec.H}x{spec.D}) fwd+autograd backward, "
+                        if slab is None else
+                        f"{done // N} z-slabs of {slab} layers of the {name} grid ({spec.W}x{spec.H}x{slab} cells each, wells completed in "
+                        f"the slab) fwd+autograd backward, ") + f"{el:.1f} s, {cores} threads over independent samples"), done, el
 
 
 def run_reference(args):
@@ -205,7 +221,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'gas-condensate (two-phase)' if spec.fluid_type == 'GC' else 'dry-gas'} {spec.W}x{spec.H}x{spec.D}, T={c['T']}, K={c['K']} (bounded sample per step)",
+            "config": {"workload": f"{args.workload}: {'gas-condensate (two-phase)' if spec.fluid_type == 'GC' else 'dry-gas'} {spec.W}x{spec.H}x{spec.D}, T={c['T']}, K={c['K']} (same grid, fewer samples: a bounded sample per step)",
                        "note": "reference CPU path = oracle port of the TF op graph (TensorFlow not installable; reference not import-clean)"},
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -231,6 +247,14 @@ def run_ours(args):
     T, K = c["T"], c["K"]
     if args.K:
         K = args.K
+    if args.strong:             # the config's K realisations are sharded over the ranks (dist.shard_realisations)
+        lo_r, hi_r = srm.dist.shard_realisations(K, rank, world)
+        if hi_r - lo_r != K // world or K % world:
+            raise SystemExit(f"bench.py --strong: K = {K} realisations do not split evenly over {world} ranks")
+        K_job = K
+        K = hi_r - lo_r
+    else:
+        K_job = K * world
     # batches beyond ~8 GB per field (cfg5 at large K: 137 GB per field at K=256) run as `reps` chunks of K_res
     # realisations; the resident synthetic chunk is re-evaluated (same work per chunk, SURVEY 8(d): "large-K cases
     # stream device-generated chunks")
@@ -250,24 +274,40 @@ def run_ours(args):
     eng = srm.SrmPhysics(spec, tabs, device=local, numerics=args.numerics, pvt_lut=lut)
     torch.cuda.synchronize(dev)
     t_create = time.perf_counter() - t_create
-    b = srm.synth.make_batch(spec.W, spec.H, spec.D, T, K, [(w.i, w.j) for w in spec.wells[:8]], seed=2002 + rank, device=dev)
-    d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
-    if gc:
-        d["sg0"], d["sg1"], d["so0"], d["so1"] = srm.synth.make_saturations(b, seed=2002 + rank)
+    def make_inputs(seed):
+        b_ = srm.synth.make_batch(spec.W, spec.H, spec.D, T, K, [(w.i, w.j) for w in spec.wells[:8]], seed=seed, device=dev)
+        if args.p_window:       # stretch the synthetic pressures over [lo, hi] psi: how far the exact table's window reaches
+            lo_p, hi_p = (float(v) for v in args.p_window.split(":"))
+            for f in ("p0", "p1"):
+                t = getattr(b_, f)
+                t.sub_(4101.0).mul_((hi_p - lo_p) / (5000.0 - 4101.0)).add_(lo_p)
+        d_ = dict(kx=b_.kx, sample_real=b_.sample_real, p0=b_.p0, p1=b_.p1, dt1=b_.dt1, dt2=b_.dt2, t1=b_.t1)
+        if gc:
+            d_["sg0"], d_["sg1"], d_["so0"], d_["so1"] = srm.synth.make_saturations(b_, seed=seed)
+        return b_, d_
+    b, d = make_inputs(2002 + rank)
+    # rotating inputs: a second, differently seeded batch alternates with the first when both fit comfortably
+    field_bytes = 4 * K * T * spec.n_cells
+    sets = [d]
+    if reps == 1 and field_bytes * (6 if gc else 2) <= 12e9:
+        sets.append(make_inputs(3002 + rank)[1])
     fwd = eng.forward_gc if gc else eng.forward
     bwd = eng.backward_gc if gc else eng.backward
     B = b.p0.shape[0]
     N = B * spec.n_cells
     dterms = torch.tensor([1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0] if gc else WEIGHTS, dtype=torch.float32, device=dev)
 
-    def step():
+    gout = None
+
+    def step(i=0):
+        nonlocal gout
+        di = sets[i % len(sets)]
         for _ in range(reps):
-            fw = fwd(**d)
-            h = srm.dist.allreduce_terms_async(fw["terms"]) if distributed else None
-            g = bwd(dterms=dterms, **d)
-            if h is not None:
-                h.wait()
-        return fw["terms"], g
+            fw = fwd(**di)
+            gout = bwd(dterms=dterms, out=gout, **di)
+        if distributed:
+            srm.dist.allreduce_terms(fw["terms"])
+        return fw["terms"], gout
 
     def barrier():
         if distributed:
@@ -275,26 +315,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for i in range(max(args.warmup, 3)):
+        step(i)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ef = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    pending = None              # the previous step's loss-term all-reduce (NCCL's own stream)
     e0.record()
     for i in range(args.steps):
+        di = sets[i % len(sets)]
         for rep in range(reps):
-            fw = fwd(**d)
-            # the 128-byte all-reduce of the loss terms overlaps the adjoint (which does not read them)
-            h = srm.dist.allreduce_terms_async(fw["terms"]) if distributed else None
+            fw = fwd(**di)
             if rep == reps - 1:
                 ef[2 * i].record()
-            bwd(dterms=dterms, **d)
-            if h is not None:
-                h.wait()
+            gout = bwd(dterms=dterms, out=gout, **di)
         ef[2 * i + 1].record()
+        if distributed:
+            # The adjoint's upstream weights are constants, so nothing in a step reads the REDUCED terms: the 128-byte
+            # all-reduce is queued behind the adjoint and waited on one step later (reporting only).  A rank never
+            # waits for another rank inside a step, and NCCL's kernel never shares the SMs with the adjoint.
+            if pending is not None:
+                pending.wait()
+            pending = srm.dist.allreduce_terms_async(fw["terms"])
+    if pending is not None:
+        pending.wait()
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -313,6 +360,7 @@ def run_ours(args):
     ms = float(t.item())
     ms_step = ms / args.steps
     value = world * N * reps * args.steps / (ms * 1e-3)
+    scaling = "strong" if args.strong else "weak"
 
     if args.kernels_only:       # tuning runs: the device-timed step alone
         if rank == 0:
@@ -396,6 +444,42 @@ def run_ours(args):
                  "api": "srm.engine.GraphedStep.replay: forward + adjoint captured once in a CUDA graph"}
         del gs
 
+    # ---- the closed-form numerics mode on the same batch (the route past the exact-table gather floor):
+    # same formulas evaluated as exact arithmetic would, <= 2.5e-6 from the fp64 oracle (tests/test_gpu_closed_form.py);
+    # its distance to the fp32 reference-order results of THIS batch is measured here
+    closed = None
+    if not gc and args.numerics == "reference" and not args.no_closed_form:
+        g_ref = [t.clone() for t in gout[:2]]
+        eng_cf = srm.SrmPhysics(spec, tabs, device=local, numerics="closed_form")
+        gcf = None
+        for i in range(3):
+            fwc = eng_cf.forward(**sets[0])
+            gcf = eng_cf.backward(dterms=dterms, out=gcf, **sets[0])
+        torch.cuda.synchronize(dev)
+        dist_cf = {"terms_rel": [float(abs(a - b) / max(abs(b), 1e-30)) for a, b in zip(fwc["terms"][0].tolist()[:4], ref_terms[0].tolist()[:4])],
+                   "gp0_rel_to_max": float((gcf[0] - g_ref[0]).abs().max() / g_ref[0].abs().max()),
+                   "gp1_rel_to_max": float((gcf[1] - g_ref[1]).abs().max() / g_ref[1].abs().max())}
+        del g_ref
+        ec = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+        barrier()
+        ec[0].record()
+        for i in range(args.steps):
+            di = sets[i % len(sets)]
+            eng_cf.forward(**di)
+            ec[2 * i + 1].record()
+            gcf = eng_cf.backward(dterms=dterms, out=gcf, **di)
+            ec[2 * i + 2].record()
+        torch.cuda.synchronize(dev)
+        cf_ms = ec[0].elapsed_time(ec[-1]) / args.steps
+        cf_f = float(np.mean([ec[2 * i].elapsed_time(ec[2 * i + 1]) for i in range(args.steps)]))
+        cf_a = float(np.mean([ec[2 * i + 1].elapsed_time(ec[2 * i + 2]) for i in range(args.steps)]))
+        closed = {"ms_per_step": cf_ms, "fwd_ms": cf_f, "bwd_ms": cf_a, "value_per_gpu": N / (cf_ms * 1e-3),
+                  "kernels": "k_fwd_cf2 / k_adj_cf2 (kernels_cf2.cu: every global read a TMA box copy, cp.async.bulk.tensor.4d)",
+                  "error_vs_fp64_oracle": "dom <= 1.9e-7, gp0 <= 2.5e-6, gp1 <= 8e-7 of max (gate of tests/test_gpu_closed_form.py)",
+                  "distance_to_fp32_reference_order": dist_cf}
+        eng_cf.close()
+        del eng_cf, gcf
+
     # ---- the fused glue either side of the kernels: HardLayer at both levels + dt means and
     # their cotangents, timed on the same resident batch (not part of `value`: the reference's metric is the residual)
     glue = None
@@ -476,6 +560,10 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = peak_hbm()
         ab = alg_bytes_per_cell(T, gc)
+        # the window of the exact table this batch touches: entries = representable fp32 values between min and max pressure
+        p_lo = float(min(d["p0"].min(), d["p1"].min()))
+        p_hi = float(max(d["p0"].max(), d["p1"].max()))
+        n_entries = int(np.float32(p_hi).view(np.int32)) - int(np.float32(p_lo).view(np.int32)) + 1
         if glue:
             glue["frac"] = glue["achieved_GBps"] / peak
             if "achieved_GBps" in glue.get("batch_gather", {}):
@@ -519,25 +607,35 @@ def run_ours(args):
                 "fwd_ms": float(fwd_ms), "bwd_ms": float(bwd_ms),
                 "note": ("reference-order numerics: the exact-table gathers bound both passes at the L2 sector rate "
                          "(tools/gather_probe2.cu; floor = 25 % of the HBM roofline, DESIGN.md 5.1)") if (lut and not gc) else None}
+        if closed is not None:
+            closed["alg_bytes_per_cell"] = ab
+            closed["achieved"] = closed["value_per_gpu"] * ab / 1e9
+            closed["frac"] = closed["achieved"] / peak
+            closed["forward_frac"] = one * ab_f / (closed["fwd_ms"] * 1e-3) / peak
+            closed["adjoint_frac"] = one * ab_a / (closed["bwd_ms"] * 1e-3) / peak
+            roof["closed_form"] = closed
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _, _ = cpu_oracle_throughput(args.workload, target_seconds=12.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {'gas-condensate (two-phase)' if gc else 'dry-gas'} {spec.W}x{spec.H}x{spec.D}, T={T}, K={K_total} per GPU" + (f" as {reps} chunks of K={K}" if reps > 1 else "") + f", B={B * reps}, "
                                    f"{len(spec.wells)} well connections" + (", blocking-factor integral" if spec.use_blocking_factor else ""),
                        "numerics": args.numerics, "cells_per_gpu_per_step": N * reps,
                        "pvt": ("reference-order spline tabulated per fp32 pressure over the clamp range at handle creation "
-                               "(%.2f s, outside the timed region, bit-identical to direct evaluation)" % t_create) if lut
+                               "(%.2f s, outside the timed region, bit-identical to direct evaluation); pressures of this batch span "
+                               "[%.0f, %.0f] psi = %.2f M table entries" % (t_create, p_lo, p_hi, n_entries / 1e6)) if lut
                               else "evaluated per cell",
                        "l2": "inputs+workspace per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % ((2 * N * 4 + eng.workspace(B, b.kx.shape[0]).numel()) / 1e6),
-                       "parallelism": f"sample-sharded x{world}; all-reduce of the 16-float loss-term vector only"},
+                       "parallelism": f"sample-sharded x{world} ({scaling}: K = {K_job} realisations in the job); the only collective is the all-reduce of the "
+                                      "16-float loss-term vector, queued behind the adjoint and waited on one step later"},
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * reps, "d2h_bytes_per_step": int(d2h) * reps,
                     "steps": e2e_steps, "loss": loss,
+                    "h2d_GBps_per_rank": int(h2d) * reps * e2e_steps / e2e_s / 1e9, "d2h_GBps_per_rank": int(d2h) * reps * e2e_steps / e2e_s / 1e9,
                     "api": f"srm.engine.HostPipeline.step: pinned host batch, {n_chunks_used} chunks of whole realisations, H2D / kernels / D2H on three streams; "
                            "value = full round trip (all cotangent fields back to pinned host memory)",
                     "grads_on_device": {"value": e2e_loss_only, "unit": UNIT, "d2h_bytes_per_step": int(d2h_loss_only) * reps,
@@ -559,10 +657,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--strong", action="store_true", help="shard the config's K realisations over the ranks (strong scaling) instead of K per rank")
+    ap.add_argument("--p-window", default="", help="lo:hi psi -- stretch the synthetic pressures over this window (exact-table locality check)")
     ap.add_argument("--numerics", default="reference", choices=["reference", "closed_form"])
     ap.add_argument("--K", type=int, default=0, help="override realisations per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-closed-form", action="store_true", help="skip the closed-form numerics leg reported as roofline.closed_form")
     ap.add_argument("--kernels-only", action="store_true", help="tuning: print the device-timed step only (no e2e, graph, glue, cpu legs)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="realisation chunks of the host-buffer pipeline")
     ap.add_argument("--no-pvt-lut", action="store_true", help="reference numerics: evaluate the 37-term spline per cell instead of the exact table")

@@ -795,13 +795,86 @@ def corey_krog_krgo_t(sg, cfg: OracleConfig, dtype=torch.float32):
     return krog, krgo
 
 
-def wells_gc(p_cell, sg_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConfig, dtype):
-    """WellRatesPressure.compute_rates_and_bhp, fluid_type 'GC', non-iterative control, blocking factor off
-    (well_rate_bhp_Subclassed.py:727-837, 614-724, 963-1034), at the connection cells.
+def solve_newton_sg(cost, ref, max_iters, max_value):
+    """_solve_newton (well_rate_bhp_Subclassed.py:236-269): start 0.1, Sg <- clip(Sg - f/(df + 1e-12), 0, max_value),
+    df by the inner tape; every iteration stays in the graph (tf.while_loop is differentiated through)."""
+    sg = torch.full_like(ref, 0.1)
+    if not sg.requires_grad:
+        sg.requires_grad_(True)
+    for _ in range(int(max_iters)):
+        f = cost(sg)
+        (df,) = torch.autograd.grad(f, sg, grad_outputs=torch.ones_like(f), create_graph=True)
+        sg = _tf_clip(sg - f / (df + 1e-12), torch.zeros_like(sg), torch.full_like(sg, max_value))
+    return sg
+
+
+def solve_bracket_sg(cost, ref, max_iters, tol, max_value):
+    """_solve_chandrupatla (well_rate_bhp_Subclassed.py:272-324) as written: a regula-falsi bracket update on
+    [0, max_value] (hi nudged to lo + 1e-3 when the end values do not bracket), at most max_iters steps while ANY element
+    is wider than tol, result 0.5 (lo + hi)."""
+    lo = torch.zeros_like(ref)
+    hi = torch.ones_like(ref) * max_value
+    f_lo, f_hi = cost(lo), cost(hi)
+    bad = (f_lo * f_hi) > 0.0
+    hi = torch.where(bad, lo + 1e-3, hi)
+    f_hi = torch.where(bad, cost(hi), f_hi)
+    it = 0
+    while bool(((hi - lo) > tol).any()) and it < int(max_iters):
+        d = (f_hi - f_lo) / (hi - lo + 1e-12)
+        guess = hi - f_hi / d
+        f_guess = cost(guess)
+        rep = (f_lo * f_guess) < 0.0
+        lo, f_lo, hi, f_hi = (torch.where(rep, lo, guess), torch.where(rep, f_lo, f_guess),
+                              torch.where(rep, guess, hi), torch.where(rep, f_guess, f_hi))
+        it += 1
+    return 0.5 * (lo + hi)
+
+
+def blocking_integral_gc(p, sg, pwf, tab, cfg, krog_n1, mg_n1, mo_n1, dtype, solver="newton", n_root_iter=20):
+    """compute_blocking_integral_and_factor, GC branch (well_rate_bhp_Subclassed.py:857-950): trapezoid over
+    tf.linspace(p, pwf, n+1); at every node the gas saturation solves mo(Sg) mg_n1 - mo_n1 mg(Sg) = 0 (the producing
+    gas-oil ratio of the block is kept along the path), Sg_max where krog of the block is below 1e-3 (:912).
+    Returns (Ig, Io)."""
+    n = cfg.n_intervals
+    delta = (pwf - p) / float(n)
+    grid = [p] + [p + delta * float(i) for i in range(1, n)] + [pwf]
+    sg_max = 1.0 - cfg.Swmin
+    sum_g, sum_o = torch.zeros_like(p), torch.zeros_like(p)
+    mg_prev, mo_prev = mg_n1, mo_n1
+    cond = krog_n1 < 1e-3                                                        # :897
+    for i in range(n):
+        pa, pb = grid[i], grid[i + 1]
+        v, _ = pvt_eval(pb, tab, cfg, props=(0, 1, 2, 3, 4, 5))
+        invBg1, invBo1, invug1, invuo1, Rs1, Rv1 = (v[j] for j in range(6))
+
+        def cost(s):                                                             # :899-908 (well_id == 1 at a connection)
+            krog, krgo = corey_krog_krgo_t(s, cfg, dtype)
+            mgg = krgo * invBg1 * invug1
+            mgo = krog * invBo1 * invuo1 * Rs1
+            moo = krog * invBo1 * invuo1
+            mog = krgo * invBg1 * invug1 * Rv1
+            return (moo + mog) * mg_n1 - mo_n1 * (mgg + mgo)
+
+        if solver == "newton":
+            s1 = solve_newton_sg(cost, sg, n_root_iter, sg_max)
+        else:
+            s1 = solve_bracket_sg(cost, sg, n_root_iter, 1e-6, sg_max)
+        s1 = torch.where(cond, torch.ones_like(s1) * sg_max, s1)                 # :912
+        krog1, krgo1 = corey_krog_krgo_t(s1, cfg, dtype)
+        mg1 = krgo1 * invBg1 * invug1 + krog1 * invBo1 * invuo1 * Rs1            # :926-930
+        mo1 = krog1 * invBo1 * invuo1 + krgo1 * invBg1 * invug1 * Rv1
+        dp = pa - pb
+        sum_g = sum_g + 0.5 * (mg_prev + mg1) * dp                               # :937
+        sum_o = sum_o + 0.5 * (mo_prev + mo1) * dp * 1.0                         # :938
+        mg_prev, mo_prev = mg1, mo1
+    return sum_g, sum_o
+
+
+def wells_gc(p_cell, sg_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConfig, dtype, solver="newton"):
+    """WellRatesPressure.compute_rates_and_bhp, fluid_type 'GC', non-iterative control, with or without the
+    blocking-factor integral (well_rate_bhp_Subclassed.py:727-837, 614-724, 840-960, 963-1034), at the connection cells.
 
     returns (qgg, qgo, qoo, qog) each (B,nw), pwf (B,nw)"""
-    if cfg.use_blocking_factor:
-        raise NotImplementedError("GC blocking-factor integral (Newton/Chandrupatla root find) is not restated")
     dt = dtype
     wells = cfg.wells
     nw = len(wells)
@@ -825,17 +898,27 @@ def wells_gc(p_cell, sg_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConf
     tiny = 1e-12
     one = torch.ones_like(p)
     zero = torch.zeros_like(p)
-    # ---- _non_iterative_method (:614-724), blocking off: Ig_max = Io_max = 1
+    blk = bool(cfg.use_blocking_factor)
+
+    def integrals(pwf_):
+        if blk:
+            return blocking_integral_gc(p, sg_cell, pwf_, tab, cfg, krog, mg, mo, dt, solver=solver)
+        return one, one                                                          # :955-959
+    # ---- _non_iterative_method (:614-724)
+    ig_max, _io_max = integrals(pmin.expand_as(p))
     dp_max = p - pmin + tiny                                                     # :650
-    blk_g_max = one                                                              # :657
+    blk_g_max = _dnn(ig_max, mg * dp_max) if blk else ig_max                     # :654-657
     qg_max = ck * blk_g_max * mg * dp_max                                        # :662 (well_id == 1)
     qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), zero)            # :666
     lam = _tf_clip(_dnn(qg_opt, ck * blk_g_max * mg), zero, blk_g_max)           # :699
     pwf = _tf_clip(p - lam * dp_max, pmin.expand_as(p), p)                       # :721-723
     # ---- _compute_phase_rates (:963-1007)
+    ig, io = integrals(pwf)
     dp = p - pwf + tiny                                                          # :987
-    qg_max2 = ck * one * mg * dp                                                 # :997
-    qo_max2 = ck * one * mo * dp                                                 # :998
+    blk_g = _dnn(ig, mg * dp) if blk else ig                                     # :990-995
+    blk_o = _dnn(io, mo * dp) if blk else io
+    qg_max2 = ck * blk_g * mg * dp                                               # :997
+    qo_max2 = ck * blk_o * mo * dp                                               # :998
     qg = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), zero)               # :1001
     qo_target = qg * (1.0 / (Rv + tiny))                                         # :1004
     qo = _tf_maximum(_tf_minimum(qo_target, qo_max2), zero)                      # :1005

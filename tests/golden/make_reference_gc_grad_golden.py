@@ -72,7 +72,7 @@ class GraphModelGC:
         return [p, sg, so, val[0], val[1], val[2], val[3], val[4], val[5], one, der, self.DTF[lv], one, q4, pwf]
 
 
-def run_case(seed, B, H, W, wells, R=1, sg_lo=0.2, sg_hi=0.75, small_dp=False, dts=(0.5, 2.25, 7.125, 1.0, 0.375, 9.5)):
+def run_case(seed, B, H, W, wells, R=1, sg_lo=0.2, sg_hi=0.75, small_dp=False, dts=(0.5, 2.25, 7.125, 1.0, 0.375, 9.5), blocking=False):
     cols = O.load_pvt_table(os.path.join(HERE, "pvt_table.npz"))
     tab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
     if wells == "two":
@@ -81,7 +81,7 @@ def run_case(seed, B, H, W, wells, R=1, sg_lo=0.2, sg_hi=0.75, small_dp=False, d
         wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=6, j=4, k=0, value=300.0), dict(i=3, j=2, k=0, value=2.0e5)]
     else:
         wl = []
-    cfg = O.OracleConfig(D=1, H=H, W=W, wells=[O.Well(**w) for w in wl])
+    cfg = O.OracleConfig(D=1, H=H, W=W, wells=[O.Well(**w) for w in wl], use_blocking_factor=blocking, n_intervals=8)
     rng = np.random.default_rng(seed)
     shp = (B, 1, H, W)
     d = dict(kx=rng.uniform(1, 6, (R, 1, H, W)).astype(np.float32))
@@ -117,7 +117,7 @@ def run_case(seed, B, H, W, wells, R=1, sg_lo=0.2, sg_hi=0.75, small_dp=False, d
         "Kr_gas_oil": relperm,
     }
     pvt_layer = GG.reference_pvt_layer(cols, tab, O.GC_PROPS, "GC")
-    wells_m = GG.reference_wells(cfg, 1, H, W, "GC", False, relperm) if wl else types.SimpleNamespace(well_data={"connection_index": []})
+    wells_m = GG.reference_wells(cfg, 1, H, W, "GC", blocking, relperm) if wl else types.SimpleNamespace(well_data={"connection_index": []})
     sr = torch.as_tensor(d["sample_real"].astype(np.int64))
     kxb = tt(d["kx"]).index_select(0, sr)
     model = GraphModelGC(cfg, P, SG, SO, DTF, pvt_layer, wells_m, relperm, kxb, cfd)
@@ -139,7 +139,7 @@ def run_case(seed, B, H, W, wells, R=1, sg_lo=0.2, sg_hi=0.75, small_dp=False, d
     assert model.calls == 2
     back = lambda a: a.detach().reshape(B, 1, H, W).numpy()
     out = {k: v for k, v in d.items()}
-    out.update(W=W, H=H, B=B, R=R, nwt=np.asarray(nwt, np.float32),
+    out.update(W=W, H=H, B=B, R=R, blocking=int(blocking), nwt=np.asarray(nwt, np.float32),
                wells=np.asarray([[w["i"], w["j"], w["k"], w["value"]] for w in wl], np.float32).reshape(-1, 4),
                wsse=np.asarray([float(v.detach()) if isinstance(v, torch.Tensor) else float(v) for v in wsse[:8]], np.float64))
     for name, i in (("batch", 0), ("dom", 1), ("ibc", 4), ("mbc", 6), ("cmbc", 7)):
@@ -155,7 +155,9 @@ def main():
     out = {}
     cases = {"a": dict(seed=5311, B=3, H=9, W=8, wells="two"),
              "b": dict(seed=5312, B=4, H=7, W=10, wells="three", R=2, sg_lo=0.2, sg_hi=0.35),
-             "c": dict(seed=5313, B=2, H=6, W=7, wells="none", small_dp=True, sg_lo=0.2, sg_hi=0.5)}
+             "c": dict(seed=5313, B=2, H=6, W=7, wells="none", small_dp=True, sg_lo=0.2, sg_hi=0.5),
+             # the blocking-factor integral: twenty Newton iterations per trapezoid node, all of them inside the tape
+             "d": dict(seed=5314, B=2, H=7, W=10, wells="three", sg_lo=0.3, sg_hi=0.6, blocking=True)}
     for name, kw in cases.items():
         r = run_case(**kw)
         print(name, "wsse", r["wsse"], " max|g_batch|:", {f: float(np.abs(r[f"g_batch_{f}"]).max()) for f in ("p0", "p1", "sg0", "sg1", "so0", "so1", "dt1")})

@@ -10,7 +10,8 @@ TensorFlow stand-in of this directory (TensorFlow is not installable here):
     model_PVT is the oracle's spline (pinned by make_reference_pvt_golden.py), relperm_model the oracle's Corey function,
     the de-normalisation of t and kx is the identity (physical inputs).
 
-Cases: dry gas without and with the blocking-factor integral (n_intervals = 8), gas condensate.
+Cases: dry gas without and with the blocking-factor integral (n_intervals = 8), gas condensate without it and with it
+(Newton and the bracketing solver, 20 root iterations per trapezoid node).
 Output: tests/golden/reference_wells.npz (inputs + the dense rate / BHP fields the reference code returns).
 """
 import ast
@@ -57,7 +58,7 @@ def build_class(path, cls, names, ns):
     return ns[cls]
 
 
-def run_case(fluid, blocking, seed, B=4, D=2, H=7, W=9):
+def run_case(fluid, blocking, seed, B=4, D=2, H=7, W=9, solver="newton"):
     rng = np.random.default_rng(seed)
     wl = [O.Well(i=2, j=2, k=0, value=500.0), O.Well(i=W - 2, j=H - 3, k=D - 1, value=1000.0, shutin_days=(20.0, 35.0)),
           O.Well(i=4, j=1, k=0, value=2.0e5)]                    # the third target is BHP limited
@@ -80,9 +81,9 @@ def run_case(fluid, blocking, seed, B=4, D=2, H=7, W=9):
            "slice_tensor": lambda x, idx, dim=-1: x[..., idx[0]:idx[0] + 1]}
     WRP = build_class(os.path.join(REF, "well_rate_bhp_Subclassed.py"), "WellRatesPressure",
                       ["compute_rates_and_bhp", "_non_iterative_method", "_compute_phase_rates", "compute_blocking_integral_and_factor",
-                       "_split_condensate_components", "extract_pvt_properties", "_solve_newton"], ns2)
+                       "_split_condensate_components", "extract_pvt_properties", "_solve_newton", "_solve_chandrupatla"], ns2)
     w = WRP.__new__(WRP)
-    w.fluid_type, w.use_blocking_factor, w.dtype, w.solver, w.n_intervals, w.n_root_iter = fluid, blocking, tf.float32, "newton", 8, 20
+    w.fluid_type, w.use_blocking_factor, w.dtype, w.solver, w.n_intervals, w.n_root_iter = fluid, blocking, tf.float32, solver, 8, 20
     w.max_iters, w.tol, w.use_non_iterative, w.compute_mo = 10, 1e-6, True, fluid == "GC"
     w.kx_ky = tf.constant(cfg.kx_ky, dtype=tf.float32)
     w.dx = tf.constant(cfg.length, dtype=tf.float32) / W          # :113-115
@@ -131,13 +132,13 @@ def run_case(fluid, blocking, seed, B=4, D=2, H=7, W=9):
     kc = torch.as_tensor(kx).reshape(B, -1)[:, flat]
     if fluid == "GC":
         sc = torch.as_tensor(sg).reshape(B, -1)[:, flat]
-        q4o, pwo = O.wells_gc(pc, sc, kc, t_days, tab, cfg, torch.float32)
+        q4o, pwo = O.wells_gc(pc, sc, kc, t_days, tab, cfg, torch.float32, solver=solver)
         ref = [out["q4"][c].reshape(B, -1)[:, flat] for c in range(4)]
-        d = max(ulp(q4o[c].numpy(), ref[c]) for c in range(4))
+        d = max(ulp(q4o[c].detach().numpy(), ref[c]) for c in range(4))
     else:
         qo, pwo = O.wells_dg(pc, kc, t_days, tab, cfg, torch.float32)
         d = ulp(qo.numpy(), out["q"].reshape(B, -1)[:, flat])
-    dp = ulp(pwo.numpy(), out["pwf"].reshape(B, -1)[:, flat])
+    dp = ulp(pwo.detach().numpy(), out["pwf"].reshape(B, -1)[:, flat])
     print(fluid, "blocking" if blocking else "plain", ": max ulp distance reference vs oracle at the connections: rates", d, " pwf", dp)
     return out
 
@@ -153,7 +154,10 @@ def ulp(a, b):
 def main():
     out = {}
     for name, kw in {"dg": dict(fluid="DG", blocking=False, seed=5401), "dgblk": dict(fluid="DG", blocking=True, seed=5402),
-                     "gc": dict(fluid="GC", blocking=False, seed=5403)}.items():
+                     "gc": dict(fluid="GC", blocking=False, seed=5403),
+                     # the GC blocking-factor integral with its root finders (well_rate_bhp_Subclassed.py:857-950, 236-324)
+                     "gcblk": dict(fluid="GC", blocking=True, seed=5404),
+                     "gcblk_br": dict(fluid="GC", blocking=True, seed=5405, solver="chandrupatla")}.items():
         for k, v in run_case(**kw).items():
             out[f"{name}_{k}"] = np.asarray(v)
     np.savez_compressed(os.path.join(HERE, "reference_wells.npz"), **out)

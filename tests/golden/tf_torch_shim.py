@@ -294,9 +294,10 @@ class GradientTape:
                 return [torch.zeros_like(v) for v in x]
             g = torch.autograd.grad(y, list(x), grad_outputs=torch.ones_like(y), retain_graph=True, allow_unused=True)
             return [torch.zeros_like(v) if gi is None else gi for gi, v in zip(g, x)]
-        # a watched tensor that is itself part of an enclosing graph (PVTLayer's inner tape under the loss tape): the
-        # derivative stays differentiable, as TensorFlow's nested tapes record it
-        return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True, create_graph=x.grad_fn is not None)[0]
+        # the derivative stays differentiable, as TensorFlow's nested tapes record it (PVTLayer's inner tape under the
+        # loss tape; the Newton iterations of the blocking-factor integral, whose cost depends on the enclosing graph
+        # even where the watched iterate is a fresh tensor)
+        return torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), retain_graph=True, create_graph=True)[0]
 
 
 class _Layer:

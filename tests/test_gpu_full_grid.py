@@ -1,0 +1,108 @@
+"""Oracle parity at the FULL grids of BASELINE configs 3, 4 and 5 (run with -m gpu): one sample each, the CUDA bench
+kernels (k_fwd4 / k_adj4 with the exact table; the fused gas-condensate pair; the closed-form TMA pair) against the
+oracle evaluated on the box's host cores on the same inputs.
+
+  * config 3: 128 x 128 x 32 dry gas, five default connections
+  * config 4: 128 x 128 x 32 gas condensate (two-phase)
+  * config 5: 256 x 256 x 64 dry gas, 4 x 8 lattice completed in every layer (2048 connections), blocking-factor integral
+
+Gates: residual field `dom` 0 ulp (reference numerics), loss terms 1e-5, gradients H3
+(|cuda - oracle| <= rtol |oracle| + rtol max|oracle|, rtol 1e-5 dry gas; the two-phase figure is printed un-widened and
+gated at 3e-5, the oracle's own distance to the reference-graph gradients).  Closed-form mode: against the fp64 oracle.
+The oracle takes a few seconds per 128^2 x 32 sample and ~30 s for the 256^2 x 64 one (torch-CPU autograd).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util as U
+
+srm, O = U.srm, U.O
+pytestmark = pytest.mark.gpu
+
+
+def h3_min_rtol(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    den = np.abs(b) + np.abs(b).max()
+    return float((np.abs(a - b) / np.maximum(den, 1e-300)).max()) if den.max() > 0 else float(np.abs(a).max())
+
+
+def oracle_threads():
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+def dg_case(W, H, D, wells, blocking, seed):
+    ocfg, otab, spec, ptab, batch = U.make_case(W=W, H=H, D=D, T=1, K=1, seed=seed, wells=wells, use_blocking_factor=blocking,
+                                                near_knots=True)
+    return ocfg, otab, spec, ptab, batch
+
+
+@pytest.mark.parametrize("name,W,H,D,wells,blocking", [("cfg3", 128, 128, 32, "default", False),
+                                                       ("cfg5", 256, 256, 64, "lattice", True)])
+def test_dry_gas_full_grid_against_the_oracle(name, W, H, D, wells, blocking, capsys):
+    oracle_threads()
+    ocfg, otab, spec, ptab, batch = dg_case(W, H, D, wells, blocking, seed=9300 + D)
+    assert len(spec.wells) == (2048 if wells == "lattice" else 5)
+    o = U.oracle_run(ocfg, otab, batch)
+    c = U.cuda_run(spec, ptab, batch, pvt_lut=True)
+    assert U.ulp_diff(c["dom"], o["dom"]) == 0, name
+    live = [0, 1, 2, 3]
+    assert np.allclose(c["terms"][live], o["terms"][live], rtol=1e-5)
+    assert np.array_equal(c["counts"], O.dg_counts(ocfg, 1))
+    assert np.array_equal(c["qw"] == 0, o["qw"] == 0) and np.allclose(c["qw"], o["qw"], rtol=1e-5)
+    worst = {k: h3_min_rtol(c[k], o[k]) for k in ("gp0", "gp1", "gdt1")}
+    with capsys.disabled():
+        print(f"\n[{name} full grid {W}x{H}x{D}, {len(spec.wells)} connections] dom 0 ulp; smallest passing H3 rtol: "
+              + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    for k, v in worst.items():
+        assert v <= 1e-5, (name, k, v)
+    assert np.abs(c["gdt2"]).max() <= 1e-5 * np.abs(o["gdt1"]).max()
+    # closed-form mode on the same sample, against the fp64 oracle
+    o64 = U.oracle_run(ocfg, otab, batch, dtype=torch.float64)
+    cf = U.cuda_run(spec, ptab, batch, numerics="closed_form")
+    err = {k: U.rel_to_max(cf[k], o64[k]) for k in ("dom", "gp0", "gp1", "gdt1")}
+    with capsys.disabled():
+        print(f"[{name} full grid, closed form vs fp64 oracle] rel. to max: " + ", ".join(f"{k} {v:.2e}" for k, v in err.items()))
+    assert err["dom"] <= 1e-6 and err["gp0"] <= 5e-6 and err["gp1"] <= 5e-6 and err["gdt1"] <= 5e-6, err
+
+
+def test_gas_condensate_full_grid_against_the_oracle(capsys):
+    """config 4: 128 x 128 x 32 two-phase, one sample, fused pair (table over the whole clamp range)"""
+    oracle_threads()
+    W, H, D = 128, 128, 32
+    wells = srm.config.scaled_default_wells(W, H, D)
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=wells, fluid_type="GC")
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    ocfg = O.OracleConfig(D=D, H=H, W=W, wells=[O.Well(i=w.i, j=w.j, k=w.k, value=abs(w.q_target), producer=not np.signbit(w.q_target),
+                                                       minimum_bhp=w.pwf_min, wellbore_radius=w.rw, completion_ratio=w.hc,
+                                                       shutin_days=(w.shut_start, w.shut_stop)) for w in wells])
+    b = srm.synth.make_batch(W, H, D, 1, 1, [(w.i, w.j) for w in wells], seed=9404)
+    sat = srm.synth.make_saturations(b, seed=9404)
+    d = dict(kx=b.kx.numpy(), p0=b.p0.numpy(), p1=b.p1.numpy(), sg0=sat[0].numpy(), sg1=sat[1].numpy(), so0=sat[2].numpy(),
+             so1=sat[3].numpy(), dt1=b.dt1.numpy(), dt2=b.dt2.numpy(), t1=b.t1.numpy(), sample_real=np.zeros(1, np.int32))
+    wts = [1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+    o = O.gc_forward_backward(ocfg, otab, d["kx"], d["p0"], d["p1"], d["sg0"], d["sg1"], d["so0"], d["so1"], d["dt1"], d["dt2"],
+                              d["t1"], d["sample_real"], wts)
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=True)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    fw = eng.forward_gc(want_dom=True, **dev)
+    g = eng.backward_gc(dterms=torch.tensor(wts, dtype=torch.float32, device="cuda"), **dev)
+    torch.cuda.synchronize()
+    assert U.ulp_diff(fw["dom"].cpu().numpy(), o["dom"]) == 0
+    T = srm._lib.TERM_NAMES
+    terms = fw["terms"][0].cpu().numpy()
+    for nm in ("dom", "ibc", "mbc", "cmbc"):
+        assert np.isclose(terms[T.index(nm)], o["terms"][T.index(nm)], rtol=1e-5, atol=1e-30), nm
+    worst = {}
+    for nm, t in zip(("gp0", "gp1", "gsg0", "gsg1", "gso0", "gso1", "gdt1"), g):
+        worst[nm] = h3_min_rtol(t.cpu().numpy(), o[nm])
+    with capsys.disabled():
+        print(f"\n[cfg4 full grid {W}x{H}x{D} two-phase] dom 0 ulp; smallest passing H3 rtol (un-widened): "
+              + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    for k, v in worst.items():
+        assert v <= 3e-5, (k, v)
+    eng.close()

@@ -323,7 +323,8 @@ def _wells_ref_case(g, name, blocking):
     return O.OracleConfig(D=D, H=H, W=W, wells=wl, use_blocking_factor=blocking, n_intervals=8), wl
 
 
-@pytest.mark.parametrize("name,fluid,blocking", [("dg", "DG", False), ("dgblk", "DG", True), ("gc", "GC", False)])
+@pytest.mark.parametrize("name,fluid,blocking", [("dg", "DG", False), ("dgblk", "DG", True), ("gc", "GC", False),
+                                                 ("gcblk", "GC", True), ("gcblk_br", "GC", True)])
 def test_oracle_wells_equal_the_reference_class_bit_for_bit(name, fluid, blocking):
     """PIN: tests/golden/reference_wells.npz holds the dense rate / BHP fields returned by the reference's OWN
     WellRatesPressure.compute_rates_and_bhp (non-iterative control, phase rates, the dry-gas blocking-factor integral,
@@ -342,7 +343,11 @@ def test_oracle_wells_equal_the_reference_class_bit_for_bit(name, fluid, blockin
     t_days = g[f"{name}_t_days"]
     eq = lambda a, b: np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
     if fluid == "GC":
-        q4, pwf = O.wells_gc(pc, torch.as_tensor(at(g[f"{name}_sg"])), kc, t_days, tab, cfg, torch.float32)
+        # gcblk / gcblk_br: the blocking-factor integral with the Newton / bracketing root find per trapezoid node
+        # (well_rate_bhp_Subclassed.py:857-950, 236-324)
+        q4, pwf = O.wells_gc(pc, torch.as_tensor(at(g[f"{name}_sg"])), kc, t_days, tab, cfg, torch.float32,
+                             solver="bracket" if name.endswith("_br") else "newton")
+        q4, pwf = [q.detach() for q in q4], pwf.detach()
         for c in range(4):
             assert eq(q4[c].numpy(), at(g[f"{name}_q4"][c])), c
             dense = g[f"{name}_q4"][c].reshape(B, -1).copy()
