@@ -144,6 +144,8 @@ class PhysicsSpec:
     wells: List[WellSpec] = field(default_factory=list)
     use_blocking_factor: bool = False
     n_intervals: int = 8
+    root_solver: str = "newton"           # well_rate_bhp_Subclassed.py:38 ('newton' | 'chandrupatla'), GC blocking integral
+    n_root_iter: int = 20                 # well_rate_bhp_Subclassed.py:40
     tde_in_dom: bool = True
     fluid_type: str = "DG"
     # time normalisation statistics (for normalize_diff of the predicted time step)

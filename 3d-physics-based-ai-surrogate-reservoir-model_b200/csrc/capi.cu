@@ -56,7 +56,11 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   if (cfg->fluid_type == SRM_FLUID_GC) {
     if (cfg->n_props != 7) { srm_set_error("srm_create: SRM_FLUID_GC needs the 7 GC properties (InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro), got %d", cfg->n_props); return SRM_ERR_INVALID; }
     if (cfg->numerics != SRM_NUMERICS_REFERENCE) { srm_set_error("srm_create: SRM_FLUID_GC is built for SRM_NUMERICS_REFERENCE only"); return SRM_ERR_INVALID; }
-    if (cfg->use_blocking_factor) { srm_set_error("srm_create: the GC blocking-factor integral (well_rate_bhp_Subclassed.py:897-911) is not built"); return SRM_ERR_INVALID; }
+    if (cfg->use_blocking_factor && (cfg->n_root_iter < 1 || cfg->n_root_iter > 200 ||
+                                     (cfg->root_solver != SRM_ROOT_NEWTON && cfg->root_solver != SRM_ROOT_BRACKET))) {
+      srm_set_error("srm_create: the GC blocking-factor integral needs root_solver SRM_ROOT_NEWTON|SRM_ROOT_BRACKET and 1 <= n_root_iter <= 200");
+      return SRM_ERR_INVALID;
+    }
     if (cfg->pvt_method == SRM_PVT_SPLINE && cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
   }
   const bool poly = cfg->pvt_method == SRM_PVT_POLYNOMIAL;
@@ -120,6 +124,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   P.p_min = cfg->p_min; P.p_max = cfg->p_max;
   P.tde_in_dom = cfg->tde_in_dom;
   P.use_blk = cfg->use_blocking_factor; P.n_int = cfg->n_intervals;
+  P.root_solver = cfg->root_solver; P.n_root_iter = cfg->n_root_iter;
   P.n_knots = cfg->n_knots; P.order = cfg->spline_order; P.n_props = cfg->n_props;
   // SCAL: constants formed in fp32 like relative_permeability.py:58-68
   P.fluid = cfg->fluid_type;

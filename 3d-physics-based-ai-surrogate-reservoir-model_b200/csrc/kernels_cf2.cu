@@ -21,7 +21,7 @@
 
 #include "common.cuh"
 
-#define CF2_NB 4096
+#define CF2_NB 2048
 
 // closed-form tables of the lean pair, device global memory; every CTA copies them to shared memory
 struct Cf2Tab {
@@ -63,12 +63,13 @@ int srm_build_cf2(SrmHandle* h, const SrmConfig* cfg) {
   }
   // exactly on a knot the reference's gradient mask drops the knot's own term: mean of the two slopes (kernels_cf.cu)
   for (int k = 1; k <= n; ++k) { T.e1[k].y = (float)(0.5 * (sl0[k] + sl0[k - 1])); T.e1[k].z = (float)(0.5 * (sl1[k] + sl1[k - 1])); }
-  // buckets over [lo, hi]: width 0.45 x the smallest knot spacing that touches the clamp range
+  // buckets over [lo, hi]: width 0.9 x the smallest knot spacing that touches the clamp range (a bucket window, margin
+  // included, then holds at most one knot: the lookup takes at most one step up)
   double wmin = 1e300;
   for (int i = 1; i < n; ++i)
     if (cfg->knots[i] >= cfg->p_min && cfg->knots[i - 1] <= cfg->p_max) wmin = std::fmin(wmin, (double)cfg->knots[i] - cfg->knots[i - 1]);
   if (!(wmin < 1e300) || !(cfg->p_max > cfg->p_min)) return SRM_OK;
-  const double w = 0.45 * wmin;
+  const double w = 0.9 * wmin;
   const int nb = (int)std::floor(((double)cfg->p_max - cfg->p_min) / w) + 2;
   if (nb > CF2_NB) return SRM_OK;             // the generic kernels (kernels_cf.cu) take such tables
   T.nb = nb;
@@ -106,6 +107,9 @@ namespace {
 #ifndef CF2_LXMAX
 #define CF2_LXMAX 32
 #endif
+#ifndef CF2_CPT
+#define CF2_CPT 4          // x-adjacent cells per thread: 4 (16-byte shared loads) or 2 (8-byte, half the registers)
+#endif
 #define CF2_STR2(x) #x
 #define CF2_STR(x) CF2_STR2(x)
 #ifdef CF2_UNROLL
@@ -114,6 +118,17 @@ namespace {
 #define CF2_LOOP_PRAGMA
 #endif
 constexpr int NT = CF2_NT;
+constexpr int CPT = CF2_CPT;
+#ifndef CF2_ABL
+#define CF2_ABL 0          // ablation builds (timing experiments only): 1 = forward without arithmetic, 2 = forward without the face copies
+#endif
+constexpr int ABL = CF2_ABL;
+#ifndef CF2_FREE
+#define CF2_FREE 0         // 1: warps march independently (no block barrier, no shared G plane; measured: no faster); 0: one barrier per plane
+#endif
+constexpr bool FREE = CF2_FREE != 0;
+constexpr int NGP = FREE ? 0 : 3;          // shared G planes
+static_assert(CPT == 4 || CPT == 2, "cells per thread");
 constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // TMA stages (planes in flight)
 static_assert(S_FWD >= 3 && S_ADJ >= 3, "plane k is waited for at the top of iteration k and refilled stages are issued at k-2+S: fewer than 3 stages deadlocks");
 
@@ -121,7 +136,7 @@ __host__ __device__ constexpr int al128(int b) { return (b + 127) & ~127; }
 
 template <int LX>
 struct Geo {
-  static constexpr int TX = 4 * LX;                 // cells per tile row
+  static constexpr int TX = CPT * LX;                 // cells per tile row
   static constexpr int RPW = 32 / LX;               // tile rows per warp
   static constexpr int TY = (NT / 32) * RPW;
   static constexpr int BX = TX + 8, BY = TY + 2;    // haloed box: columns x0-4 .. x0+TX+3, rows y0-1 .. y0+TY
@@ -140,7 +155,7 @@ struct Geo {
   static constexpr int RING = 2 * TX + 2 * TY;
   static constexpr int GPL = al128(P1_B);                            // one G plane (same layout as the p1 box)
   template <bool ADJ> static constexpr int total() {
-    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + 3 * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + TY * TX /*well flags*/;
+    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + NGP * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + TY * TX /*well flags*/;
   }
 };
 
@@ -177,9 +192,19 @@ __device__ __forceinline__ void tma_4d(void* dst, const CUtensorMap* map, uint64
 __device__ __forceinline__ uint64_t pol_evict_last() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t pol_evict_first() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void sts4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void a4(float (&d)[4], float4 v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+// CPT floats at once: shared loads / stores and streaming global stores
+__device__ __forceinline__ void ldv(float (&d)[CPT], const float* p) {
+  if constexpr (CPT == 4) { const float4 v = *reinterpret_cast<const float4*>(p); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+  else { const float2 v = *reinterpret_cast<const float2*>(p); d[0] = v.x; d[1] = v.y; }
+}
+__device__ __forceinline__ void stv(float* p, const float (&d)[CPT]) {
+  if constexpr (CPT == 4) *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+  else *reinterpret_cast<float2*>(p) = make_float2(d[0], d[1]);
+}
+__device__ __forceinline__ void stv_cs(float* p, const float (&d)[CPT]) {
+  if constexpr (CPT == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));
+  else __stcs(reinterpret_cast<float2*>(p), make_float2(d[0], d[1]));
+}
 
 // ---- PVT from the shared tables -------------------------------------------------------------------------------
 // interval of the clamped pressure: bucket, then at most one step up (at most one knot per bucket window)
@@ -218,6 +243,24 @@ __device__ __forceinline__ float cf2_G_cached(const Cf2Tab* __restrict__ T, cons
     return fmaf(c1.x, dx, c0.w) * fmaf(c1.z, dx, c1.y);
   }
   return cf2_G(T, p);
+}
+
+// G of CPT neighbour pressures at once (barrier-free march: a warp evaluates the face mobilities of its S / N rows itself)
+__device__ __forceinline__ void cf2_G_vec(const Cf2Tab* __restrict__ T, const float4 c0, const float4 c1, const float (&p)[CPT], float (&g)[CPT]) {
+  bool in = true;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    in = in && (p[c] > c0.x) && (p[c] < c0.y);
+    const float dx = p[c] - c0.z;
+    g[c] = fmaf(c1.x, dx, c0.w) * fmaf(c1.z, dx, c1.y);
+  }
+  if (!in) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) g[c] = cf2_G(T, p[c]);
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // first connection (sorted by cell) with cell >= c: well_lower_bound of common.cuh on the slim parameter block
@@ -272,8 +315,8 @@ __device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
   t.lx = lane % LX; t.ry = warp * G::RPW + lane / LX;
   const int tyi = blockIdx.x / tiles_x, txi = blockIdx.x - tyi * tiles_x;
   t.x0 = txi * G::TX; t.y0 = tyi * G::TY;
-  t.own = (t.ry + 1) * G::BX + 4 + 4 * t.lx;
-  t.valid = (t.x0 + 4 * t.lx < P.W) && (t.y0 + t.ry < P.H);
+  t.own = (t.ry + 1) * G::BX + 4 + CPT * t.lx;
+  t.valid = (t.x0 + CPT * t.lx < P.W) && (t.y0 + t.ry < P.H);
   auto ring = [&](int h) {
     if (h < G::TX) return 4 + h;                                               // row y0-1
     if (h < 2 * G::TX) return (G::TY + 1) * G::BX + 4 + (h - G::TX);             // row y0+TY
@@ -308,7 +351,7 @@ __device__ __forceinline__ bool thread_has_well(const Cf2Dev& P, const Place<LX>
   bool mine = false;
   if (t.valid) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) mine |= flags[t.ry * G::TX + 4 * t.lx + c] != 0;
+    for (int c = 0; c < CPT; ++c) mine |= flags[t.ry * G::TX + CPT * t.lx + c] != 0;
   }
   any = __syncthreads_or(mine ? 1 : 0) != 0;
   return mine;
@@ -327,9 +370,11 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   constexpr int S = S_FWD;
   extern __shared__ __align__(1024) unsigned char smem[];
   float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_F);
-  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_F + 3 * G::GPL);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_F + 3 * G::GPL + al128((int)sizeof(Cf2Tab)));
-  unsigned char* flags = smem + S * G::STAGE_F + 3 * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_F + NGP * G::GPL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
+  uint64_t* empty = full + S;           // barrier-free march: one arrival per warp when it has read a stage for the last time
+  static_assert(2 * S * 8 <= 128, "barrier block");
+  unsigned char* flags = smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
   __shared__ double red[4 * 32];
 
   const int tid = threadIdx.x;
@@ -342,15 +387,17 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     const int s = plane % S;
     unsigned char* st = stage(s);
     const uint64_t keep = pol_evict_last(), strm = pol_evict_first();
-    mbar_expect_tx(&full[s], G::TX_F);
+    mbar_expect_tx(&full[s], ABL == 2 ? G::P1_B + G::P0_B : G::TX_F);
     tma_4d(st + G::O_P1, &m_p1, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
     tma_4d(st + G::O_P0, &m_p0, &full[s], t.x0, t.y0, plane, b, strm);
-    tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
-    tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
-    tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
+    if (ABL != 2) {
+      tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
+      tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
+      tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
+    }
   };
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < S && k < D; ++k) issue(k);
@@ -365,8 +412,8 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   const float cA = P.dv * P.invDc / d1;
   const float cT = P.dvDc * 2e-7f / d1;
   const float mbk = P.dvSgi_phi / (P.Dc * d1);
-  float* domf = A.dom + (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
-  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+  float* domf = A.dom + (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
+  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
 
   float a_dom = 0.f, a_tde = 0.f, a_mb = 0.f;
   double d_dom = 0.0, d_tde = 0.0, d_mb = 0.0, d_ibc = 0.0;
@@ -378,9 +425,9 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   const float4 c0 = T->cur0, c1 = T->cur1;
 
   // z window in registers: plane m (cur) and the arriving plane (next); the upper z-face term of plane m-1
-  float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, fz[4] = {0.f, 0.f, 0.f, 0.f};
-  float a1c[4] = {0.f, 0.f, 0.f, 0.f}, a1lc[4] = {0.f, 0.f, 0.f, 0.f};      // invBg at level n+1 of plane m: value, anchor low part
-  float pn[4], Gn[4], a1n[4], a1ln[4];
+  float pc[CPT] = {}, Gc[CPT] = {}, fz[CPT] = {};
+  float a1c[CPT] = {}, a1lc[CPT] = {};      // invBg at level n+1 of plane m: value, anchor low part
+  float pn[CPT], Gn[CPT], a1n[CPT], a1ln[CPT];
 
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
@@ -389,10 +436,15 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       mbar_wait(&full[s], (k / S) & 1);
       const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
       float* Gb = Gs + (k % 3) * (G::GPL / 4);
-      a4(pn, lds4(sp1 + t.own));
+      ldv(pn, sp1 + t.own);
       bool in = true;
+      if (ABL == 1) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) { Gn[c] = pn[c]; a1n[c] = 0.f; a1ln[c] = 0.f; }
+        if (!FREE) stv(Gb + t.own, Gn);
+      } else {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
         in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
         const float dx = pn[c] - c0.z;
         a1n[c] = fmaf(c1.x, dx, c0.w);
@@ -401,7 +453,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
       if (!in) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float x = cf2_clamp(T, pn[c]);
           const int kk = cf2_interval(T, x);
           const float4 e = T->e0[kk];
@@ -412,17 +464,28 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           Gn[c] = a1n[c] * fmaf(f.x, dx, e.w);
         }
       }
-      sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
-      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
-      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
-      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
+      if (!FREE) {
+        stv(Gb + t.own, Gn);
+        if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
+        if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
+        if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
+      }
+      }
     } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
+      for (int c = 0; c < CPT; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
     }
-    __syncthreads();
-    // the stage of plane k-2 has been consumed by every thread: refill it
-    if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    if (FREE) {
+      // no block barrier: the stage of plane k-2 is refilled once every warp has arrived on its `empty` barrier
+      if (tid == 0 && k >= 2 && k - 2 + S < D) {
+        mbar_wait(&empty[(k - 2) % S], ((k - 2) / S) & 1);
+        issue(k - 2 + S);
+      }
+    } else {
+      __syncthreads();
+      // the stage of plane k-2 has been consumed by every thread: refill it
+      if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    }
     const int m = k - 1;
     if (m >= 0) {
       const unsigned char* st = stage(m % S);
@@ -432,30 +495,38 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
       const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
       const float* Gm = Gs + (m % 3) * (G::GPL / 4);
-      float pS[4], pN[4], gS[4], gN[4], fE[4], fS[4], fN[4], fU[4], p0[4];
-      a4(pS, lds4(sp1 + t.own - G::BX)); a4(pN, lds4(sp1 + t.own + G::BX));
-      a4(gS, lds4(Gm + t.own - G::BX)); a4(gN, lds4(Gm + t.own + G::BX));
-      a4(fE, lds4(sfe + t.ry * G::FEX + 4 + 4 * t.lx));
-      a4(fS, lds4(sfn + t.ry * G::TX + 4 * t.lx)); a4(fN, lds4(sfn + (t.ry + 1) * G::TX + 4 * t.lx));
-      a4(fU, lds4(sfu + t.ry * G::TX + 4 * t.lx));
-      a4(p0, lds4(sp0 + t.ry * G::TX + 4 * t.lx));
-      float pW = __shfl_up_sync(0xffffffffu, pc[3], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[3], 1, LX);
-      float fW = __shfl_up_sync(0xffffffffu, fE[3], 1, LX);
+      if (ABL == 1) {
+        float q0[CPT], dv_[CPT];
+        ldv(q0, sp0 + t.ry * G::TX + CPT * t.lx);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) dv_[c] = pc[c] + q0[c];
+        if (t.valid) stv_cs(domf + (int64_t)m * P.H * P.W, dv_);
+      } else {
+      float pS[CPT], pN[CPT], gS[CPT], gN[CPT], fE[CPT], fS[CPT], fN[CPT], fU[CPT], p0[CPT];
+      ldv(pS, sp1 + t.own - G::BX); ldv(pN, sp1 + t.own + G::BX);
+      if (FREE) { cf2_G_vec(T, c0, c1, pS, gS); cf2_G_vec(T, c0, c1, pN, gN); }
+      else { ldv(gS, Gm + t.own - G::BX); ldv(gN, Gm + t.own + G::BX); }
+      ldv(fE, sfe + t.ry * G::FEX + 4 + CPT * t.lx);
+      ldv(fS, sfn + t.ry * G::TX + CPT * t.lx); ldv(fN, sfn + (t.ry + 1) * G::TX + CPT * t.lx);
+      ldv(fU, sfu + t.ry * G::TX + CPT * t.lx);
+      ldv(p0, sp0 + t.ry * G::TX + CPT * t.lx);
+      float pW = __shfl_up_sync(0xffffffffu, pc[CPT - 1], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[CPT - 1], 1, LX);
+      float fW = __shfl_up_sync(0xffffffffu, fE[CPT - 1], 1, LX);
       float pE = __shfl_down_sync(0xffffffffu, pc[0], 1, LX), gE = __shfl_down_sync(0xffffffffu, Gc[0], 1, LX);
-      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = Gm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
-      if (t.lx == LX - 1) { pE = sp1[t.own + 4]; gE = Gm[t.own + 4]; }
+      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = FREE ? cf2_G_cached(T, c0, c1, pW) : Gm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
+      if (t.lx == LX - 1) { pE = sp1[t.own + CPT]; gE = FREE ? cf2_G_cached(T, c0, c1, pE) : Gm[t.own + CPT]; }
       // x faces, one evaluation per face: F_i = T_i (G_l + G_r)(p_l - p_r); cell c takes -F_c + F_{c+1}
-      float Fx[5];
+      float Fx[CPT + 1];
       Fx[0] = fW * (gW + Gc[0]) * (pW - pc[0]);
 #pragma unroll
-      for (int i = 1; i < 4; ++i) Fx[i] = fE[i - 1] * (Gc[i - 1] + Gc[i]) * (pc[i - 1] - pc[i]);
-      Fx[4] = fE[3] * (Gc[3] + gE) * (pc[3] - pE);
-      float dvf[4], rest[4], domv[4];
+      for (int i = 1; i < CPT; ++i) Fx[i] = fE[i - 1] * (Gc[i - 1] + Gc[i]) * (pc[i - 1] - pc[i]);
+      Fx[CPT] = fE[CPT - 1] * (Gc[CPT - 1] + gE) * (pc[CPT - 1] - pE);
+      float dvf[CPT], rest[CPT], domv[CPT];
       // level-n PVT of the four cells: A0 = invBg(p0), Ap = its slope, low part of the anchor value
-      float A0[4], Ap[4], A0l[4];
+      float A0[CPT], Ap[CPT], A0l[CPT];
       bool in0 = true;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
         A0[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
         Ap[c] = c1.x;
@@ -463,7 +534,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
       if (!in0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float x = cf2_clamp(T, p0[c]);
           const int kk = cf2_interval(T, x);
           const float4 e = T->e0[kk];
@@ -475,7 +546,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         float flux = Fx[c + 1] - Fx[c];
         flux = fmaf(fS[c] * (Gc[c] + gS[c]), pc[c] - pS[c], flux);
         flux = fmaf(fN[c] * (Gc[c] + gN[c]), pc[c] - pN[c], flux);
@@ -492,7 +563,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
       if (tile_wells && has_well) {     // wells in this thread's columns (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const int cell = m * P.H * P.W + cell0 + c;
           const int first = cf2_lower_bound(P, cell);
           float q = 0.f, mask = 0.f;
@@ -506,17 +577,22 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) domv[c] = dvf[c] + rest[c];
+      for (int c = 0; c < CPT; ++c) domv[c] = dvf[c] + rest[c];
       if (t.valid) {
-        __stcs(reinterpret_cast<float4*>(domf + (int64_t)m * P.H * P.W), make_float4(domv[0], domv[1], domv[2], domv[3]));
+        stv_cs(domf + (int64_t)m * P.H * P.W, domv);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
+        for (int c = 0; c < CPT; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
       } else {
         a_tde = 0.f; a_mb = 0.f;
       }
+      }
+      if (FREE) {         // this warp has read plane m's stage for the last time
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[m % S]);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
+    for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
     if ((k & 7) == 7) { d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f; }
   }
   double acc4[4] = {d_dom + (double)a_dom, d_ibc, d_tde + (double)a_tde, (d_mb + (double)a_mb) * (double)mbk};
@@ -545,9 +621,11 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   constexpr int S = S_ADJ;
   extern __shared__ __align__(1024) unsigned char smem[];
   float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_A);
-  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_A + 3 * G::GPL);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_A + 3 * G::GPL + al128((int)sizeof(Cf2Tab)));
-  unsigned char* flags = smem + S * G::STAGE_A + 3 * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_A + NGP * G::GPL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
+  uint64_t* empty = full + S;
+  static_assert(2 * S * 8 <= 128, "barrier block");
+  unsigned char* flags = smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
   __shared__ double red[32];
 
   const int tid = threadIdx.x;
@@ -569,7 +647,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
   };
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < S && k < D; ++k) issue(k);
@@ -591,8 +669,8 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   const float smbk = smb * mbk;
   const float wt2 = 2.f * w_tde;
   const float seed_tde = P.tde_in_dom ? 1.f : 0.f;
-  const int64_t fo = (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
-  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + 4 * t.lx;
+  const int64_t fo = (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
+  const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
   const float lo = T->lo, hi = T->hi;
 
   float a_g1 = 0.f;
@@ -602,10 +680,10 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   __syncthreads();
   const float4 c0 = T->cur0, c1 = T->cur1;
   // plane m (cur) in registers; (X, Y) of the lower z face handed up by plane m-1
-  float pc[4] = {0.f, 0.f, 0.f, 0.f}, Gc[4] = {0.f, 0.f, 0.f, 0.f}, dc[4] = {0.f, 0.f, 0.f, 0.f};
-  float Gpc[4] = {0.f, 0.f, 0.f, 0.f}, Apc[4] = {0.f, 0.f, 0.f, 0.f};
-  float Xz[4] = {0.f, 0.f, 0.f, 0.f}, Yz[4] = {0.f, 0.f, 0.f, 0.f};
-  float pn[4], Gn[4], dn[4], Gpn[4], Apn[4];
+  float pc[CPT] = {}, Gc[CPT] = {}, dc[CPT] = {};
+  float Gpc[CPT] = {}, Apc[CPT] = {};
+  float Xz[CPT] = {}, Yz[CPT] = {};
+  float pn[CPT], Gn[CPT], dn[CPT], Gpn[CPT], Apn[CPT];
 
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
@@ -615,11 +693,11 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
       const float* sdm = reinterpret_cast<const float*>(stage(s) + G::O_DM);
       float* Gb = Gs + (k % 3) * (G::GPL / 4);
-      a4(pn, lds4(sp1 + t.own));
-      a4(dn, lds4(sdm + t.own));
+      ldv(pn, sp1 + t.own);
+      ldv(dn, sdm + t.own);
       bool in = true;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {        // strictly inside the cached interval: inside the clamp too, off every knot
+      for (int c = 0; c < CPT; ++c) {        // strictly inside the cached interval: inside the clamp too, off every knot
         in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
         const float dx = pn[c] - c0.z;
         const float A1 = fmaf(c1.x, dx, c0.w);
@@ -630,7 +708,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       }
       if (!in) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float x = cf2_clamp(T, pn[c]);
           const int kk = cf2_interval(T, x);
           const float4 e = T->e0[kk];
@@ -646,16 +724,25 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
           Gpn[c] = pass ? fmaf(sA, M, A1 * sM) : 0.f;
         }
       }
-      sts4(Gb + t.own, make_float4(Gn[0], Gn[1], Gn[2], Gn[3]));
-      if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
-      if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
-      if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
+      if (!FREE) {
+        stv(Gb + t.own, Gn);
+        if (t.ring0 >= 0) Gb[t.ring0] = cf2_G_cached(T, c0, c1, sp1[t.ring0]);
+        if (t.ring1 >= 0) Gb[t.ring1] = cf2_G_cached(T, c0, c1, sp1[t.ring1]);
+        if (G::RING > 2 * NT && t.ring2 >= 0) Gb[t.ring2] = cf2_G_cached(T, c0, c1, sp1[t.ring2]);
+      }
     } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
+      for (int c = 0; c < CPT; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
     }
-    __syncthreads();
-    if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    if (FREE) {
+      if (tid == 0 && k >= 2 && k - 2 + S < D) {
+        mbar_wait(&empty[(k - 2) % S], ((k - 2) / S) & 1);
+        issue(k - 2 + S);
+      }
+    } else {
+      __syncthreads();
+      if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+    }
     const int m = k - 1;
     if (m >= 0) {
       const unsigned char* st = stage(m % S);
@@ -666,26 +753,27 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
       const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
       const float* Gm = Gs + (m % 3) * (G::GPL / 4);
-      float pS[4], pN[4], gS[4], gN[4], dS[4], dN[4], fE[4], fS[4], fN[4], fU[4], p0[4];
-      a4(pS, lds4(sp1 + t.own - G::BX)); a4(pN, lds4(sp1 + t.own + G::BX));
-      a4(gS, lds4(Gm + t.own - G::BX)); a4(gN, lds4(Gm + t.own + G::BX));
-      a4(dS, lds4(sdm + t.own - G::BX)); a4(dN, lds4(sdm + t.own + G::BX));
-      a4(fE, lds4(sfe + t.ry * G::FEX + 4 + 4 * t.lx));
-      a4(fS, lds4(sfn + t.ry * G::TX + 4 * t.lx)); a4(fN, lds4(sfn + (t.ry + 1) * G::TX + 4 * t.lx));
-      a4(fU, lds4(sfu + t.ry * G::TX + 4 * t.lx));
-      a4(p0, lds4(sp0 + t.ry * G::TX + 4 * t.lx));
-      float pW = __shfl_up_sync(0xffffffffu, pc[3], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[3], 1, LX);
-      float dW = __shfl_up_sync(0xffffffffu, dc[3], 1, LX), fW = __shfl_up_sync(0xffffffffu, fE[3], 1, LX);
+      float pS[CPT], pN[CPT], gS[CPT], gN[CPT], dS[CPT], dN[CPT], fE[CPT], fS[CPT], fN[CPT], fU[CPT], p0[CPT];
+      ldv(pS, sp1 + t.own - G::BX); ldv(pN, sp1 + t.own + G::BX);
+      if (FREE) { cf2_G_vec(T, c0, c1, pS, gS); cf2_G_vec(T, c0, c1, pN, gN); }
+      else { ldv(gS, Gm + t.own - G::BX); ldv(gN, Gm + t.own + G::BX); }
+      ldv(dS, sdm + t.own - G::BX); ldv(dN, sdm + t.own + G::BX);
+      ldv(fE, sfe + t.ry * G::FEX + 4 + CPT * t.lx);
+      ldv(fS, sfn + t.ry * G::TX + CPT * t.lx); ldv(fN, sfn + (t.ry + 1) * G::TX + CPT * t.lx);
+      ldv(fU, sfu + t.ry * G::TX + CPT * t.lx);
+      ldv(p0, sp0 + t.ry * G::TX + CPT * t.lx);
+      float pW = __shfl_up_sync(0xffffffffu, pc[CPT - 1], 1, LX), gW = __shfl_up_sync(0xffffffffu, Gc[CPT - 1], 1, LX);
+      float dW = __shfl_up_sync(0xffffffffu, dc[CPT - 1], 1, LX), fW = __shfl_up_sync(0xffffffffu, fE[CPT - 1], 1, LX);
       float pE = __shfl_down_sync(0xffffffffu, pc[0], 1, LX), gE = __shfl_down_sync(0xffffffffu, Gc[0], 1, LX);
       float dE = __shfl_down_sync(0xffffffffu, dc[0], 1, LX);
-      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = Gm[t.own - 1]; dW = sdm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
-      if (t.lx == LX - 1) { pE = sp1[t.own + 4]; gE = Gm[t.own + 4]; dE = sdm[t.own + 4]; }
-      float g1v[4], g0v[4];
+      if (t.lx == 0) { pW = sp1[t.own - 1]; gW = FREE ? cf2_G_cached(T, c0, c1, pW) : Gm[t.own - 1]; dW = sdm[t.own - 1]; fW = sfe[t.ry * G::FEX + 3]; }
+      if (t.lx == LX - 1) { pE = sp1[t.own + CPT]; gE = FREE ? cf2_G_cached(T, c0, c1, pE) : Gm[t.own + CPT]; dE = sdm[t.own + CPT]; }
+      float g1v[CPT], g0v[CPT];
       // level-n PVT: A0 = invBg(p0), Ap = its slope, Apm = the slope behind the clamp's gradient mask
-      float A0v[4], Apv[4], Apmv[4];
+      float A0v[CPT], Apv[CPT], Apmv[CPT];
       bool in0 = true;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
         A0v[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
         Apv[c] = c1.x;
@@ -693,7 +781,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       }
       if (!in0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const float x = cf2_clamp(T, p0[c]);
           const int kk = cf2_interval(T, x);
           const float4 e = T->e0[kk];
@@ -704,10 +792,10 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         // in-plane faces in gather form; the z faces once per face: this plane's upper face is the next one's lower
         const float plW = (c == 0) ? pW : pc[c - (c > 0)], glW = (c == 0) ? gW : Gc[c - (c > 0)], dlW = (c == 0) ? dW : dc[c - (c > 0)];
-        const float plE = (c == 3) ? pE : pc[c + (c < 3)], glE = (c == 3) ? gE : Gc[c + (c < 3)], dlE = (c == 3) ? dE : dc[c + (c < 3)];
+        const float plE = (c == CPT - 1) ? pE : pc[c + (c < CPT - 1)], glE = (c == CPT - 1) ? gE : Gc[c + (c < CPT - 1)], dlE = (c == CPT - 1) ? dE : dc[c + (c < CPT - 1)];
         const float tW = (c == 0) ? fW : fE[c - (c > 0)];
         float g1 = 0.f;
         g1 = fmaf((dc[c] - dlW) * tW, fmaf(Gpc[c], pc[c] - plW, Gc[c] + glW), g1);
@@ -735,7 +823,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       }
       if (tile_wells && has_well) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           const int cell = m * P.H * P.W + cell0 + c;
           float dq = 0.f;
           const int first = cf2_lower_bound(P, cell);
@@ -744,14 +832,18 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         }
       }
       if (t.valid) {
-        __stcs(reinterpret_cast<float4*>(A.gp0 + fo + (int64_t)m * P.H * P.W), make_float4(g0v[0], g0v[1], g0v[2], g0v[3]));
-        __stcs(reinterpret_cast<float4*>(A.gp1 + fo + (int64_t)m * P.H * P.W), make_float4(g1v[0], g1v[1], g1v[2], g1v[3]));
+        stv_cs(A.gp0 + fo + (int64_t)m * P.H * P.W, g0v);
+        stv_cs(A.gp1 + fo + (int64_t)m * P.H * P.W, g1v);
       } else {
         a_g1 = 0.f;
       }
+      if (FREE) {
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty[m % S]);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; dc[c] = dn[c]; Gpc[c] = Gpn[c]; Apc[c] = Apn[c]; }
+    for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; dc[c] = dn[c]; Gpc[c] = Gpn[c]; Apc[c] = Apn[c]; }
     if ((k & 7) == 7) { d_g1 += (double)a_g1; a_g1 = 0.f; }
   }
   double acc1[1] = {d_g1 + (double)a_g1};
@@ -806,7 +898,7 @@ Cf2Dev slim(const SrmDev& P) {
   d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells;
   return d;
 }
-int lanes_for(int W) { const int l = W >= 96 ? 32 : (W >= 48 ? 16 : 8); return l > CF2_LXMAX ? CF2_LXMAX : l; }
+int lanes_for(int W) { const int l = W >= 24 * CPT ? 32 : (W >= 12 * CPT ? 16 : 8); return l > CF2_LXMAX ? CF2_LXMAX : l; }
 
 template <int LX>
 int launch_fwd(const SrmHandle* h, const Cf2Args& A0, int32_t B, int32_t R, const float* p0, const float* p1, const float* faces, cudaStream_t s) {

@@ -239,6 +239,116 @@ __device__ __forceinline__ D2 clip2(D2 t, D2 lo, D2 hi) {                       
   return mk(fmaxf(fminf(t.v, hi.v), lo.v), g.a, g.b);
 }
 
+// Corey relative permeabilities with first AND second derivative in Sg (the Newton iterations of the blocking-factor
+// integral are differentiated through: the tangent of d cost/d Sg needs the second derivative); TF's routing as in corey()
+__device__ __forceinline__ float d2pow_pinned(float x, float n, int ni) {
+  if (ni > 0) return ni > 1 ? (float)(ni * (ni - 1)) * (ni > 2 ? powi_rt(x, ni - 2) : 1.f) : 0.f;
+  return n * (n - 1.f) * pow_general(x, n - 2.f);
+}
+struct Corey2 { float ko, kg, dko, dkg, d2ko, d2kg; };
+__device__ __forceinline__ Corey2 corey2(const SrmDev& P, float sg) {
+  Corey2 r;
+  const float so = __fsub_rn(__fsub_rn(1.0f, sg), P.swmin);
+  const float xo = __fdiv_rn(__fsub_rn(so, P.sorg), P.kr_den_o);
+  const float xg = __fdiv_rn(__fsub_rn(sg, P.sgc), P.kr_den_g);
+  const float io = 1.0f / P.kr_den_o, ig = 1.0f / P.kr_den_g;
+  r.ko = __fmul_rn(P.kro_somax, pow_pinned(xo, P.nog, P.nog_i));
+  r.kg = __fmul_rn(P.krg_sorg, pow_pinned(xg, P.ng, P.ng_i));
+  r.dko = P.kro_somax * dpow_pinned(xo, P.nog, P.nog_i) * (-io);
+  r.dkg = P.krg_sorg * dpow_pinned(xg, P.ng, P.ng_i) * ig;
+  r.d2ko = P.kro_somax * d2pow_pinned(xo, P.nog, P.nog_i) * io * io;
+  r.d2kg = P.krg_sorg * d2pow_pinned(xg, P.ng, P.ng_i) * ig * ig;
+  if (so <= P.kr_so_zero) { r.ko = 0.f; r.dko = 0.f; r.d2ko = 0.f; }
+  if (sg > P.kr_sg_full) { r.kg = P.krg_swmin; r.dkg = 0.f; r.d2kg = 0.f; }
+  if (!(r.ko <= P.kro_somax)) { r.ko = P.kro_somax; r.dko = 0.f; r.d2ko = 0.f; }
+  if (!(r.ko >= 0.f)) { r.ko = 0.f; r.dko = 0.f; r.d2ko = 0.f; }
+  if (!(r.kg <= P.krg_swmin)) { r.kg = P.krg_swmin; r.dkg = 0.f; r.d2kg = 0.f; }
+  if (!(r.kg >= 0.f)) { r.kg = 0.f; r.dkg = 0.f; r.d2kg = 0.f; }
+  return r;
+}
+
+// the six PVT properties at a (dual) pressure: values with d/dp, d/dSg carried through the clamp
+struct Pvt6 { D2 invBg, invBo, invug, invuo, Rs, Rv; };
+__device__ __forceinline__ Pvt6 pvt6_at(const SrmDev& P, D2 pb) {
+  float m;
+  const float x = srm_clamp(P, pb.v, m);
+  float v[6], d[6], d2[6];
+  srm_pvt_ref<6, true, false>(P, 0, x, v, d, d2);
+  Pvt6 o;
+  auto mkp = [&](int i) { return mk(v[i], d[i] * m * pb.a, d[i] * m * pb.b); };
+  o.invBg = mkp(0); o.invBo = mkp(1); o.invug = mkp(2); o.invuo = mkp(3); o.Rs = mkp(4); o.Rv = mkp(5);
+  return o;
+}
+// mobilities of one node at a (dual) saturation                        well_rate_bhp_Subclassed.py:900-906,926-934
+__device__ __forceinline__ void node_mob(const Pvt6& q, D2 krog, D2 krgo, D2& mg, D2& mo) {
+  const D2 mgg = krgo * q.invBg * q.invug;
+  const D2 mgo = krog * q.invBo * q.invuo * q.Rs;
+  const D2 moo = krog * q.invBo * q.invuo;
+  const D2 mog = krgo * q.invBg * q.invug * q.Rv;
+  mg = mgg + mgo;
+  mo = moo + mog;
+}
+__device__ __forceinline__ D2 with_tangent(float v, float dv, D2 s) { return mk(v, dv * s.a, dv * s.b); }
+
+// compute_blocking_integral_and_factor, GC branch                       well_rate_bhp_Subclassed.py:857-950
+// Trapezoid over tf.linspace(p, pwf, n+1); at each node the saturation solves cost(Sg) = mo(Sg) mg_n1 - mo_n1 mg(Sg) = 0
+// with the node's PVT.  Every root-finder iteration carries d/dp and d/dSg of the connection cell, as tf.while_loop's
+// gradient does.
+__device__ void blocking_integral_gc(const SrmDev& P, D2 p, D2 pwf, float krog_n1, D2 mg_n1, D2 mo_n1, D2& Ig, D2& Io) {
+  const int n = P.n_int;
+  const D2 delta = (pwf - p) / mk((float)n);
+  const float sg_max = 1.0f - P.swmin;
+  const D2 tiny = mk(1e-12f), zero = mk(0.f), smax = mk(sg_max);
+  D2 sum_g = zero, sum_o = zero, mg_prev = mg_n1, mo_prev = mo_n1, pa = p;
+  const bool cond = krog_n1 < 1e-3f;                                            // :897
+  for (int i = 0; i < n; ++i) {
+    const D2 pb = (i + 1 < n) ? p + delta * mk((float)(i + 1)) : pwf;
+    const Pvt6 q = pvt6_at(P, pb);
+    auto cost = [&](D2 s, D2* dcost) {
+      const Corey2 c = corey2(P, s.v);
+      D2 mg, mo;
+      node_mob(q, with_tangent(c.ko, c.dko, s), with_tangent(c.kg, c.dkg, s), mg, mo);
+      if (dcost) {                      // d cost / d s (the inner tape), itself a dual number
+        D2 dmg, dmo;
+        node_mob(q, with_tangent(c.dko, c.d2ko, s), with_tangent(c.dkg, c.d2kg, s), dmg, dmo);
+        *dcost = dmo * mg_n1 - mo_n1 * dmg;
+      }
+      return mo * mg_n1 - mo_n1 * mg;
+    };
+    D2 s1;
+    if (P.root_solver == SRM_ROOT_NEWTON) {                                      // _solve_newton :236-269
+      s1 = mk(0.1f);
+      for (int it = 0; it < P.n_root_iter; ++it) {
+        D2 df;
+        const D2 f = cost(s1, &df);
+        s1 = clip2(s1 - f / (df + tiny), zero, smax);
+      }
+    } else {                                                                     // _solve_chandrupatla :272-324
+      D2 lo = zero, hi = smax;
+      D2 f_lo = cost(lo, nullptr), f_hi = cost(hi, nullptr);
+      if (f_lo.v * f_hi.v > 0.f) { hi = lo + mk(1e-3f); f_hi = cost(hi, nullptr); }
+      // the reference's loop runs while ANY element of the field is wider than tol; a converged element keeps stepping
+      // with the others.  Per connection here: step while this bracket is wider than tol.
+      for (int it = 0; it < P.n_root_iter && (hi.v - lo.v) > 1e-6f; ++it) {
+        const D2 d = (f_hi - f_lo) / ((hi - lo) + tiny);
+        const D2 guess = hi - f_hi / d;
+        const D2 f_g = cost(guess, nullptr);
+        if (f_lo.v * f_g.v < 0.f) { hi = guess; f_hi = f_g; } else { lo = guess; f_lo = f_g; }
+      }
+      s1 = mk(0.5f) * (lo + hi);
+    }
+    if (cond) s1 = smax;                                                         // :912
+    const Corey2 c1 = corey2(P, s1.v);
+    D2 mg1, mo1;
+    node_mob(q, with_tangent(c1.ko, c1.dko, s1), with_tangent(c1.kg, c1.dkg, s1), mg1, mo1);
+    const D2 dp = pa - pb;
+    sum_g = sum_g + mk(0.5f) * (mg_prev + mg1) * dp;                             // :937
+    sum_o = sum_o + mk(0.5f) * (mo_prev + mo1) * dp;                             // :938
+    mg_prev = mg1; mo_prev = mo1; pa = pb;
+  }
+  Ig = sum_g; Io = sum_o;
+}
+
 __global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev P, int32_t B, int32_t R,
                                                   const float* __restrict__ kx, const int32_t* __restrict__ sample_real,
                                                   const float* __restrict__ pfield, const float* __restrict__ sgfield,
@@ -280,17 +390,24 @@ __global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev
   const D2 mog = krgo * invBg * invug * Rv;
   const D2 mg = mgg + mgo, mo = moo + mog;
   const D2 p = mk(pv, 1.f, 0.f), pmin = mk(wd.pwf_min), qt = mk(wd.q_target), zero = mk(0.f), one = mk(1.f), tiny = mk(1e-12f);
-  // ---- _non_iterative_method, blocking factor off (:614-724)
+  // ---- _non_iterative_method (:614-724); without the blocking factor Ig = Io = 1 (:955-959)
+  D2 ig_max = one, io_max = one;
+  if (P.use_blk) blocking_integral_gc(P, p, pmin, ko, mg, mo, ig_max, io_max);
   const D2 dp_max = (p - pmin) + tiny;                                           // :650
-  const D2 qg_max = Ck * one * mg * dp_max;                                      // :662
+  const D2 blk_max = P.use_blk ? dnn2(ig_max, mg * dp_max) : ig_max;             // :654-657
+  const D2 qg_max = Ck * blk_max * mg * dp_max;                                  // :662
   const D2 qg_opt = max2(min2(qt, qg_max), zero);                                // :666
-  const D2 lam = clip2(dnn2(qg_opt, Ck * one * mg), zero, one);                  // :699
+  const D2 lam = clip2(dnn2(qg_opt, Ck * blk_max * mg), zero, blk_max);          // :699
   const D2 pwf = clip2(p - lam * dp_max, pmin, p);                               // :721-723
   // ---- _compute_phase_rates (:963-1007)
+  D2 ig = one, io = one;
+  if (P.use_blk) blocking_integral_gc(P, p, pwf, ko, mg, mo, ig, io);
   const D2 dp = (p - pwf) + tiny;                                                // :987
-  const D2 qg = max2(min2(qt, Ck * one * mg * dp), zero);                        // :997,1001
+  const D2 blk_g = P.use_blk ? dnn2(ig, mg * dp) : ig;                           // :990-995
+  const D2 blk_o = P.use_blk ? dnn2(io, mo * dp) : io;
+  const D2 qg = max2(min2(qt, Ck * blk_g * mg * dp), zero);                      // :997,1001
   const D2 qo_target = qg * (one / (Rv + tiny));                                 // :1004
-  const D2 qo = max2(min2(qo_target, Ck * one * mo * dp), zero);                 // :998,1005
+  const D2 qo = max2(min2(qo_target, Ck * blk_o * mo * dp), zero);               // :998,1005
   // ---- _split_condensate_components (:1010-1034)
   const D2 dg = (mgg + mgo) + tiny, dn = (moo + mog) + tiny;
   const D2 qgg = qg * (mgg / dg), qgo = qg * (mgo / dg), qoo = qo * (moo / dn), qog = qo * (mog / dn);

@@ -31,6 +31,7 @@ struct SrmDev {
   float p_min, p_max;
   int32_t tde_in_dom;
   int32_t use_blk, n_int;
+  int32_t root_solver, n_root_iter;   // GC blocking-factor integral: SRM_ROOT_*, iterations per trapezoid node
   int32_t n_wells;
   const WellDev* wells;  // device, sorted by cell
   // spline

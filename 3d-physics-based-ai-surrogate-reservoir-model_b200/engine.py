@@ -48,7 +48,8 @@ class SrmPhysics:
             use_blocking_factor=spec.use_blocking_factor, n_intervals=spec.n_intervals,
             numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range,
             fluid_type=L.SRM_FLUID_GC if spec.fluid_type == "GC" else L.SRM_FLUID_DG,
-            end_points=spec.end_points, corey_exponents=spec.corey_exponents)
+            end_points=spec.end_points, corey_exponents=spec.corey_exponents,
+            root_solver=spec.root_solver, n_root_iter=spec.n_root_iter)
         self.pvt_lut = bool(pvt_lut) and numerics == "reference"
         h = C.c_void_p()
         L.check(self.lib, self.lib.srm_create(C.byref(cfg), C.byref(h)), "srm_create")

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SRM_ABI_VERSION 3
+#define SRM_ABI_VERSION 4
 
 typedef enum SrmStatus {
   SRM_OK = 0,
@@ -46,6 +46,7 @@ typedef enum SrmStatus {
 } SrmStatus;
 
 /* loss-term slots of terms_out / dterms (default_configurations.py:63-83 key set) */
+enum { SRM_ROOT_NEWTON = 0, SRM_ROOT_BRACKET = 1 };
 enum { SRM_TERM_DOM = 0, SRM_TERM_IBC = 1, SRM_TERM_MBC = 2, SRM_TERM_TDE = 3,
        SRM_TERM_OBC = 4, SRM_TERM_IC = 5, SRM_TERM_TD = 6, SRM_TERM_CMBC = 7, SRM_N_TERMS = 8 };
 
@@ -125,6 +126,10 @@ typedef struct SrmConfig {
    * Used by the gas-condensate path (SRM_FLUID_GC) and by srm_relperm; the dry-gas path only needs the
    * host-computed scalar krg above. */
   float Swmin, Sorg, Sgc, Socr, kro_Somax, krg_Sorg, krg_Swmin, nog, ng;
+  /* root finder of the gas-condensate blocking-factor integral (well_rate_bhp_Subclassed.py:236-324, 909-911):
+   * SRM_ROOT_NEWTON = _solve_newton (start 0.1, clip to [0, 1 - Swmin]), SRM_ROOT_BRACKET = _solve_chandrupatla
+   * (regula-falsi bracket update, tol 1e-6); n_root_iter iterations per trapezoid node (reference default 20) */
+  int32_t root_solver, n_root_iter;
 } SrmConfig;
 
 typedef struct SrmHandle SrmHandle;

@@ -324,7 +324,7 @@ def test_gc_fused_pair_repeats_bit_for_bit():
 # 2e-5 per field (the oracle itself sits at <= 1.4e-5 from these goldens), wider only where the reference's own fp32
 # autodiff is rounding noise: gp1 of `dom` in case c (cells with p1 == p0, chord slopes) 3e-4, gdt1 of the cmbc term 2e-3.
 @pytest.mark.parametrize("pvt_lut", [False, "full"])
-@pytest.mark.parametrize("case", ["a", "b", "c"])
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
 def test_cuda_gc_adjoint_equals_the_reference_graph_gradients(case, pvt_lut, capsys):
     import test_oracle_gc as TG
     g = np.load(os.path.join(U.GOLDEN, "reference_gc_grad.npz"))
@@ -332,7 +332,8 @@ def test_cuda_gc_adjoint_equals_the_reference_graph_gradients(case, pvt_lut, cap
     W, H = int(a("W")), int(a("H"))
     conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
                   wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for r in a("wells")]
-    spec = srm.PhysicsSpec(D=1, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC")
+    spec = srm.PhysicsSpec(D=1, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC",
+                           use_blocking_factor=bool(a("blocking")), n_intervals=8)      # case d: the blocking-factor integral
     cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
     otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
     ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
@@ -353,7 +354,16 @@ def test_cuda_gc_adjoint_equals_the_reference_graph_gradients(case, pvt_lut, cap
         torch.cuda.synchronize()
         for f, t in zip(("p0", "p1", "sg0", "sg1", "so0", "so1", "dt1"), out[:7]):
             ref = a(f"g_{name}_{f}")
-            m = TG.h3_min_rtol(t.cpu().numpy().reshape(ref.shape), ref)
+            got = t.cpu().numpy().reshape(ref.shape)
+            if name == "cmbc":
+                # the cumulative-balance term is a sum of truncation brackets that vanish analytically: its value (SSE ~ 1
+                # against 1e10 for the others) and its gradient are fp32 rounding noise of the reference's op order, which
+                # the hand-derived adjoint does not reproduce.  Measured on the scale of the gradient that reaches the
+                # same tensor (the batch gradient): both sides must be negligible there.
+                scale = np.abs(a(f"g_batch_{f}")).max()
+                assert np.abs(got - ref).max() <= 2e-5 * scale, (case, name, f, np.abs(got - ref).max() / scale)
+                continue
+            m = TG.h3_min_rtol(got, ref)
             gate = TG.gc_grad_gate(case, name, f)
             if gate == 2e-5:
                 worst[f] = max(worst.get(f, 0.0), m)
@@ -361,4 +371,36 @@ def test_cuda_gc_adjoint_equals_the_reference_graph_gradients(case, pvt_lut, cap
     with capsys.disabled():
         print(f"\n[reference-graph gradients, GC case {case}, pvt_lut={pvt_lut}] smallest passing H3 rtol: "
               + ", ".join(f"g{k} {v:.2e}" for k, v in worst.items()))
+    eng.close()
+
+
+@pytest.mark.parametrize("name,blocking,solver", [("gc", False, "newton"), ("gcblk", True, "newton"), ("gcblk_br", True, "chandrupatla")])
+def test_cuda_gc_wells_against_the_reference_class(name, blocking, solver):
+    """srm_forward_gc's well kernel against the dense rate / BHP fields returned by the reference's OWN
+    WellRatesPressure.compute_rates_and_bhp, gas-condensate branch (tests/golden/make_reference_wells_golden.py) --
+    without the blocking factor, and with the blocking-factor integral and its root finders (Newton; the bracketing
+    `_solve_chandrupatla`): twenty iterations per trapezoid node (well_rate_bhp_Subclassed.py:857-950, 236-324).
+    Cells, shut-ins and zeros exact; values 1e-5 (pow/log of the Peaceman factor are not bit-identical across libraries)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells.npz"))
+    D, H, W, B = (int(g[f"{name}_{k}"]) for k in ("D", "H", "W", "B"))
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[float(r[4]), float(r[5])]]) for r in g[f"{name}_wells"]]
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), use_blocking_factor=blocking, n_intervals=8,
+                           fluid_type="GC", root_solver=solver, n_root_iter=20)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    eng = srm.SrmPhysics(spec, ptab)
+    dev = eng.device
+    tt = lambda k: torch.from_numpy(g[f"{name}_{k}"]).to(dev).contiguous()
+    q4, pwf = eng.wells_gc(tt("kx"), torch.arange(B, dtype=torch.int32, device=dev), tt("p"), tt("sg"), tt("t_days"))
+    torch.cuda.synchronize()
+    rq, rp = g[f"{name}_q4"], g[f"{name}_pwf"]
+    assert np.array_equal(pwf.cpu().numpy() == 0, rp == 0)
+    assert np.allclose(pwf.cpu().numpy(), rp, rtol=RTOL, atol=0)
+    for c in range(4):
+        q = q4[c].cpu().numpy()
+        assert np.array_equal(q == 0, rq[c] == 0), c
+        assert np.allclose(q, rq[c], rtol=2e-5 if blocking else RTOL, atol=0), (c, np.abs(q - rq[c]).max() / np.abs(rq[c]).max())
+    assert (rq[0] > 0).sum() >= B
     eng.close()

@@ -120,7 +120,8 @@ def _gc_ref_case(g, case):
     import srm_oracle as O
     W, H = int(g[f"{case}_W"]), int(g[f"{case}_H"])
     wl = [O.Well(i=int(r[0]), j=int(r[1]), k=int(r[2]), value=float(r[3])) for r in g[f"{case}_wells"]]
-    return O.OracleConfig(D=1, H=H, W=W, wells=wl)
+    blocking = bool(g[f"{case}_blocking"]) if f"{case}_blocking" in g.files else False
+    return O.OracleConfig(D=1, H=H, W=W, wells=wl, use_blocking_factor=blocking, n_intervals=8)
 
 
 @pytest.mark.parametrize("case", ["a", "b", "c"])
@@ -144,7 +145,7 @@ def test_oracle_gc_residual_equals_the_reference_fragment_bit_for_bit(case):
 # ---- gradients of the reference's OWN two-phase op graph (tests/golden/make_reference_gc_grad_golden.py) ---------------
 # smallest passing H3 rtol of the oracle against them, over three cases and five term selections:
 #   gp0 1.2e-5, gp1 1.4e-5, gsg*/gso* 5.0e-6, gdt1 3.2e-6; wider only where the reference's own fp32 autodiff is noise:
-#   gp1 of `dom` in case c (p1 == p0 cells: the 1/dp^2 pieces of the chord slopes, physics_loss.py:465-466) 2.1e-4, and
+#   gp0 / gp1 of `dom` in case c (p1 == p0 cells: the 1/dp^2 pieces of the chord slopes, physics_loss.py:465-466) 2.1e-4, and
 #   gdt1 of the cmbc term (a sum of truncation brackets that vanish analytically) 1e-3.
 GC_GRAD_FIELDS = ("p0", "p1", "sg0", "sg1", "so0", "so1", "dt1")
 GC_TERMS = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
@@ -153,7 +154,7 @@ GC_TERMS = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
 def gc_grad_gate(case, name, field):
     if name == "cmbc" and field == "dt1":
         return 2e-3
-    if (case, name, field) == ("c", "dom", "p1"):
+    if case == "c" and name == "dom" and field in ("p0", "p1"):       # chord slopes at p1 == p0 cells: 1/dp^2 pieces (oracle 2.1e-4, CUDA 1.4e-4)
         return 3e-4
     return 2e-5
 
@@ -170,11 +171,12 @@ def h3_min_rtol(a, b):
     return float((np.abs(a - b) / np.maximum(den, 1e-300)).max()) if den.max() > 0 else float(np.abs(a).max())
 
 
-@pytest.mark.parametrize("case", ["a", "b", "c"])
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
 def test_oracle_gc_gradients_equal_the_reference_graph_gradients(case):
     """PIN (adjoint, two-phase): tape.gradient of every weighted SSE term taken by the reference's OWN
     pinn_batch_sse_grad over physics_error_gas_oil_2D, PVTLayer (nested tape), RelativePermeability and
-    WellRatesPressure (GC branch), network outputs as trainable variables."""
+    WellRatesPressure (GC branch; case d with the blocking-factor integral, whose twenty Newton iterations per trapezoid
+    node are all inside the tape), network outputs as trainable variables."""
     g = np.load(os.path.join(U.GOLDEN, "reference_gc_grad.npz"))
     cfg = _gc_ref_case(g, case)
     cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
@@ -186,6 +188,11 @@ def test_oracle_gc_gradients_equal_the_reference_graph_gradients(case):
                                   a("t1"), a("sample_real"), wts)
         for f in GC_GRAD_FIELDS:
             ref = a(f"g_{name}_{f}")
+            if name == "cmbc" and f == "dt1":
+                # a sum of truncation brackets that vanish analytically: rounding noise, measured on the scale of the
+                # batch gradient that reaches the same tensor
+                assert np.abs(r["g" + f] - ref).max() <= 1e-6 * np.abs(a(f"g_batch_{f}")).max()
+                continue
             assert h3_min_rtol(r["g" + f], ref) <= gc_grad_gate(case, name, f), (case, name, f, h3_min_rtol(r["g" + f], ref))
             live += int(np.abs(ref).max() > 0)
     assert live >= 20
