@@ -20,7 +20,7 @@ __all__ = ["_lib", "config", "pvt", "synth", "PhysicsSpec", "spec_from_reference
 def __getattr__(name):
     # engine / physics_loss import torch.cuda-facing code lazily
     import importlib
-    if name in ("engine", "physics_loss", "wells", "dist", "hard_layer", "batching"):
+    if name in ("engine", "physics_loss", "wells", "dist", "hard_layer", "batching", "data"):
         return importlib.import_module(f"{__name__}.{name}")
     if name == "SrmPhysics":
         return importlib.import_module(f"{__name__}.engine").SrmPhysics

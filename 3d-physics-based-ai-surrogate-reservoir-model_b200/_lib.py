@@ -30,7 +30,7 @@ EXPORTS = (
     "srm_version", "srm_last_error", "srm_create", "srm_destroy", "srm_workspace_bytes",
     "srm_pvt_eval", "srm_denormalize_log", "srm_selftest_rounding", "srm_wells", "srm_forward", "srm_backward",
     "srm_relperm", "srm_forward_gc", "srm_backward_gc", "srm_glue_workspace_bytes", "srm_glue_forward", "srm_glue_backward", "srm_gather_rows",
-    "srm_features_forward", "srm_features_backward",
+    "srm_features_forward", "srm_features_backward", "srm_weave_features",
 )
 
 
@@ -117,6 +117,8 @@ def load_library(path: Optional[str] = None):
     lib.srm_features_forward.argtypes = [i32, vp, vp, i32, i64, i32, i32, i32, fp, fp, fp, fp, vp, vp, vp]
     lib.srm_features_backward.restype = C.c_int
     lib.srm_features_backward.argtypes = [i32, vp, i32, i64, i32, i32, vp, vp]
+    lib.srm_weave_features.restype = C.c_int
+    lib.srm_weave_features.argtypes = [i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, fp, fp, vp, vp]
     if lib.srm_version() != SRM_ABI_VERSION:
         raise RuntimeError(f"libsrm_physics ABI {lib.srm_version()} != binding {SRM_ABI_VERSION}")
     if path == LIB_PATH:

@@ -392,6 +392,80 @@ extern "C" int srm_features_backward(int32_t device, const float* gx1, int32_t B
   return SRM_OK;
 }
 
+// ---- feature construction on the device -------------------------------------------------------
+// weave_tensors (data_processing_utils.py:90-223) on [permx (K, cells), time (T), x, y, z (cells)] with
+// flatten_first_axes and the channel flip, fused with DataSummary.normalize ('lnk-linear-scaling', :1031-1042):
+//   out[(k*T + t)][cell][0..4] = norm(z), norm(y), norm(x), norm(t), normlog(permx)
+// A thread owns CPT consecutive cells of one realisation: the three coordinate channels and the permeability channel are
+// normalised once and written for every time point (20 bytes per cell and sample, written as whole 16-byte vectors).
+namespace {
+struct WeaveStats { float mn[5], inv[5]; float lo, span; };      // channel order [z, y, x, t, k]; k: ln(min), 1/ln(max/min)
+__device__ __forceinline__ float norm_lin(float v, float mn, float den, float span, float lo) {
+  const float r = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(v, mn), den), span), lo);          // (((v-min)/(max-min))*(hi-lo))+lo
+  return (isnan(r) || isinf(r)) ? 0.f : r;
+}
+template <int CPT>
+__global__ void __launch_bounds__(256) k_weave(int32_t K, int32_t T, int64_t cells, const float* __restrict__ permx,
+                                               const float* __restrict__ time, const float* __restrict__ xg, const float* __restrict__ yg,
+                                               const float* __restrict__ zg, const float* __restrict__ st /* [5][2] min, max */,
+                                               float lo, float hi, float* __restrict__ out) {
+  const int64_t c0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
+  const int k = blockIdx.y;
+  if (c0 >= cells) return;
+  const float span = hi - lo;
+  float v[CPT][5];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) {
+    const int64_t c = c0 + i;
+    if (c < cells) {
+      v[i][0] = norm_lin(zg[c], st[0], __fsub_rn(st[1], st[0]), span, lo);
+      v[i][1] = norm_lin(yg[c], st[2], __fsub_rn(st[3], st[2]), span, lo);
+      v[i][2] = norm_lin(xg[c], st[4], __fsub_rn(st[5], st[4]), span, lo);
+      // ((log(k/min)/log(max/min))*(hi-lo))+lo
+      const float r = __fadd_rn(__fmul_rn(__fdiv_rn(logf(__fdiv_rn(permx[(int64_t)k * cells + c], st[8])), logf(__fdiv_rn(st[9], st[8]))), span), lo);
+      v[i][4] = (isnan(r) || isinf(r)) ? 0.f : r;
+    }
+  }
+  const float tden = __fsub_rn(st[7], st[6]);
+  for (int t = 0; t < T; ++t) {
+    const float tn = norm_lin(time[t], st[6], tden, span, lo);
+    float* o = out + (((int64_t)k * T + t) * cells + c0) * 5;
+    if (CPT == 4 && c0 + 4 <= cells) {          // 20 floats = five 16-byte stores (rows are 16-byte aligned: 4 cells x 20 B)
+      float w[20];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { w[5 * i] = v[i][0]; w[5 * i + 1] = v[i][1]; w[5 * i + 2] = v[i][2]; w[5 * i + 3] = tn; w[5 * i + 4] = v[i][4]; }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) __stcs(reinterpret_cast<float4*>(o) + q, make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i)
+        if (c0 + i < cells) { float* oc = o + 5 * i; oc[0] = v[i][0]; oc[1] = v[i][1]; oc[2] = v[i][2]; oc[3] = tn; oc[4] = v[i][4]; }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int srm_weave_features(int32_t device, int32_t K, int32_t T, int64_t cells, const float* permx, const float* time,
+                                  const float* xg, const float* yg, const float* zg, const float* stats, float lo, float hi,
+                                  float* out, void* stream) {
+  if (K < 1 || K > 65535 || T < 1 || cells < 1 || !permx || !time || !xg || !yg || !zg || !stats || !out || !(hi > lo)) {
+    srm_set_error("srm_weave_features: bad argument (1 <= K <= 65535, T >= 1, hi > lo, no NULL pointers)");
+    return SRM_ERR_INVALID;
+  }
+  SRM_CUDA_CHECK(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = cells % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  if (vec) {
+    const dim3 grid((unsigned)((cells / 4 + 255) / 256), (unsigned)K);
+    k_weave<4><<<grid, 256, 0, s>>>(K, T, cells, permx, time, xg, yg, zg, stats, lo, hi, out);
+  } else {
+    const dim3 grid((unsigned)((cells + 255) / 256), (unsigned)K);
+    k_weave<1><<<grid, 256, 0, s>>>(K, T, cells, permx, time, xg, yg, zg, stats, lo, hi, out);
+  }
+  SRM_CUDA_CHECK(cudaGetLastError());
+  return SRM_OK;
+}
+
 extern "C" int srm_gather_rows(int32_t device, const void* src, const int32_t* idx, int64_t n_idx, int64_t n_rows,
                                int64_t row_bytes, void* dst, void* stream) {
   if (n_idx < 0 || n_rows < 1 || row_bytes < 1 || (n_idx > 0 && (!src || !idx || !dst)) || n_idx > 65535) {

@@ -277,6 +277,16 @@ int srm_features_forward(int32_t device, const float* x, const float* dn, int32_
 int srm_features_backward(int32_t device, const float* gx1, int32_t B, int64_t cells, int32_t C, int32_t t_channel,
                           float* gdn, void* stream);
 
+/* Feature construction on the device: weave_tensors (data_processing/data_processing_utils.py:
+ * 90-223; call site srm_data_processing.py:363-403) over [permx (K, cells), time (T), x, y, z (cells)] with
+ * flatten_first_axes and the channel flip, fused with DataSummary.normalize ('lnk-linear-scaling',
+ * data_processing_utils.py:1031-1042).  All pointers DEVICE fp32.  stats is [5][2] = (min, max) per output channel in
+ * the order [z, y, x, t, k]; channels 0..3 are normalised linearly, the permeability channel logarithmically; NaN/Inf -> 0.
+ *   out[(k*T + t)][cell][0..4]      -- the (K*T, D, H, W, 5) tensor every training step reads, written once in HBM */
+int srm_weave_features(int32_t device, int32_t K, int32_t T, int64_t cells, const float* permx, const float* time,
+                       const float* xg, const float* yg, const float* zg, const float* stats, float lo, float hi,
+                       float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
