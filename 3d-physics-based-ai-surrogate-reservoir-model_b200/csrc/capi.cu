@@ -1,5 +1,6 @@
 // C ABI of libsrm_physics.so (see include/srm_physics.h).  Host-side validation, handle
 // construction and dispatch to the kernel launchers.  No CPU compute path exists here.
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -61,7 +62,6 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
       srm_set_error("srm_create: the GC blocking-factor integral needs root_solver SRM_ROOT_NEWTON|SRM_ROOT_BRACKET and 1 <= n_root_iter <= 200");
       return SRM_ERR_INVALID;
     }
-    if (cfg->pvt_method == SRM_PVT_SPLINE && cfg->spline_order != 1) { srm_set_error("srm_create: SRM_FLUID_GC needs spline_order 1"); return SRM_ERR_INVALID; }
   }
   const bool poly = cfg->pvt_method == SRM_PVT_POLYNOMIAL;
   if (cfg->pvt_method != SRM_PVT_SPLINE && !poly) { srm_set_error("srm_create: unknown pvt_method %d", cfg->pvt_method); return SRM_ERR_INVALID; }
@@ -108,6 +108,8 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   h->cfg.knots = h->cfg.spline_w = h->cfg.spline_v = nullptr;
   h->cfg.wells = nullptr;
   h->device = cfg->device;
+  h->st_family = -1;
+  h->no_dg4 = getenv("SRM_NO_DG4") != nullptr ? 1 : 0;      // test knob, read once here (tests compare the kernel families)
   SRM_CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
 
   SrmDev& P = h->dev;
@@ -314,16 +316,20 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
   }
   SRM_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const bool have = srm_state_is(h, B, R, workspace, kx, sample_real, p0, p1, nullptr, nullptr, nullptr, nullptr, dt1, dt2, t1);
+  bool have = srm_state_is(h, B, R, workspace, kx, sample_real, p0, p1, nullptr, nullptr, nullptr, nullptr, dt1, dt2, t1);
   const int mode = srm_ws_mode(h);
   const bool cf = mode == SRM_WS_CF;
+  // fused reference path: the adjoint's kernel family follows from the alignment of ITS pointers (gp0, gp1 included);
+  // a state saved by the other family's forward is recomputed in this one's, so the pair never mixes families
+  const int fam = mode == SRM_WS_REF_FUSED ? srm_ref2_backward_family(h, p0, p1, ws.dom, gp0, gp1) : -1;
+  if (have && fam >= 0 && h->st_family != fam) have = false;
   if (!have) {
     h->st_valid = 0;
     // recompute the forward state (PVT stage with derivatives, wells, residual field) into the workspace
     float* terms_tmp = nullptr;
     SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
     rc = cf ? srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s)
-         : mode == SRM_WS_REF_FUSED ? srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, s)
+         : mode == SRM_WS_REF_FUSED ? srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, s, fam)
             : srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
     cudaFreeAsync(terms_tmp, s);
     if (rc) return rc;

@@ -417,27 +417,24 @@ __global__ void __launch_bounds__(128) k_ibc_adj_ref2(const __grid_constant__ Sr
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+#ifdef SRM_WITH_DG5     // the warp-specialised forward experiment (kernels_dg5.cu); not part of the default build
 bool srm_dg5_applicable(const SrmHandle* h);
 cudaError_t srm_dg5_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
+#endif
 bool srm_dg4_applicable(const SrmHandle* h);
 cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
 cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, cudaStream_t s);
 cudaError_t srm_dg4_finalize_adj(const void* args, int32_t B, float* gdt1, float* gdt2, cudaStream_t s);
 
-// the lean kernels (kernels_dg4.cu) need the table over the whole clamp range and vector-aligned fields
+// the lean kernels (kernels_dg4.cu) need the table over the whole clamp range and vector-aligned fields.  The choice is
+// a function of the handle and of pointer alignment only (no environment reads on the call path); the forward records
+// its family with the saved state and a backward of the other family recomputes the forward in its own.
 static bool use_dg4(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
-  const bool off = getenv("SRM_NO_DG4") != nullptr;     // read per call: the tests compare both kernel families in one process
   auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  return !off && srm_dg4_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
+  return !h->no_dg4 && srm_dg4_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
 }
-
-// warp-specialised forward (kernels_dg5.cu): W % 4 == 0, at least two planes.  Measured SLOWER than kernels_dg4.cu on
-// B200 (0.64 vs 0.45 ms at cfg2: with one 12-warp CTA per SM the producer/consumer hand-offs and the CTA prologue are
-// not hidden); kept selectable (SRM_DG5=1) as the starting point for a two-CTA variant.
-static bool use_dg5(const SrmHandle* h, const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
-  const bool on = getenv("SRM_DG5") != nullptr && getenv("SRM_NO_DG4") == nullptr;
-  auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  return on && srm_dg5_applicable(h) && ok(a) && ok(b) && ok(c) && ok(d) && ok(e) && ok(f);
+int srm_ref2_backward_family(const SrmHandle* h, const float* p0, const float* p1, const void* dom_ws, const float* gp0, const float* gp1) {
+  return use_dg4(h, p0, p1, dom_ws, nullptr, gp0, gp1) ? 1 : 0;
 }
 
 size_t srm_ref2_face_floats(const SrmDev& P) { return (size_t)face_layout(P.D, P.H, P.W).per_real; }
@@ -456,7 +453,7 @@ static R2Args make_args(const SrmDev& P, int32_t B, int32_t R, const int32_t* sa
 
 int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
-                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s) {
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family) {
   const SrmDev& P = h->dev;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
   const FaceLay FL = face_layout(P.D, P.H, P.W);
@@ -470,9 +467,15 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   }
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dom_out = dom_out;
-  if (use_dg5(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+  const bool lean = force_family >= 0 ? (force_family == 1 && use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr))
+                                      : use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr);
+  h->st_family = lean ? 1 : 0;
+#ifdef SRM_WITH_DG5
+  if (lean && srm_dg5_applicable(h)) {
     SRM_CUDA_CHECK(srm_dg5_launch_fwd(h, &A, B, s));
-  } else if (use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr)) {
+  } else
+#endif
+  if (lean) {
     SRM_CUDA_CHECK(srm_dg4_launch_fwd(h, &A, B, s));
   } else {
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);

@@ -102,6 +102,8 @@ struct SrmHandle {
   // call that produced it (dry gas leaves the saturation slots null), so a backward on other inputs recomputes
   const void* st_ptr[13];    // ws, kx, sample_real, p0, p1, sg0, sg1, so0, so1, dt1, dt2, t1, spare
   int32_t st_B, st_R; int32_t st_valid;
+  int32_t st_family;   // fused reference path: kernel family of the forward that saved the state (1 lean kernels_dg4.cu, 0 generic)
+  int32_t no_dg4;      // test knob SRM_NO_DG4, read ONCE at srm_create: the handle runs the generic fused kernels only
 };
 static inline void srm_state_set(SrmHandle* h, int32_t B, int32_t R, const void* ws, const void* kx, const void* sr, const void* p0,
                                  const void* p1, const void* sg0, const void* sg1, const void* so0, const void* so1,
@@ -229,9 +231,10 @@ int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const i
                          float* dqdp_sorted, cudaStream_t s);
 int srm_build_pvt_lut(SrmHandle* h, float lo, float hi);
 int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi);
+int srm_ref2_backward_family(const SrmHandle* h, const float* p0, const float* p1, const void* dom_ws, const float* gp0, const float* gp1);
 int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
-                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s);
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family = -1);
 int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                       const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                       const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,

@@ -124,9 +124,11 @@ def test_gc_per_term_gradients():
 
 def test_gc_handle_rules():
     ocfg, otab, spec, ptab, d = gc_case(31)
-    spec_b = srm.PhysicsSpec(D=spec.D, H=spec.H, W=spec.W, wells=spec.wells, fluid_type="GC", use_blocking_factor=True)
+    spec_b = srm.PhysicsSpec(D=spec.D, H=spec.H, W=spec.W, wells=spec.wells, fluid_type="GC", use_blocking_factor=True, n_root_iter=0)
     with pytest.raises(srm._lib.SrmError):
-        srm.SrmPhysics(spec_b, ptab, device=0)                   # GC blocking-factor integral is not built
+        srm.SrmPhysics(spec_b, ptab, device=0)                   # the GC blocking-factor integral needs >= 1 root iteration
+    spec_b = srm.PhysicsSpec(D=spec.D, H=spec.H, W=spec.W, wells=spec.wells, fluid_type="GC", use_blocking_factor=True)
+    srm.SrmPhysics(spec_b, ptab, device=0).close()               # ... and is built (Newton, 20 iterations by default)
     eng = srm.SrmPhysics(spec, ptab, device=0)
     dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     with pytest.raises(srm._lib.SrmError):                       # a GC handle refuses the dry-gas entry point
@@ -404,3 +406,33 @@ def test_cuda_gc_wells_against_the_reference_class(name, blocking, solver):
         assert np.allclose(q, rq[c], rtol=2e-5 if blocking else RTOL, atol=0), (c, np.abs(q - rq[c]).max() / np.abs(rq[c]).max())
     assert (rq[0] > 0).sum() >= B
     eng.close()
+
+
+def test_gc_order_2_spline_on_the_fused_table_path():
+    """The reference's DEFAULT spline order is 2 (default_configurations.py:235; the example overrides to 1).  The exact
+    table tabulates whatever the per-cell code computes, so the fused pair takes order 2 as it takes order 1: its residual
+    field equals the per-cell (staged) evaluation bit for bit and the gradients agree to rounding.  Against the oracle the
+    order-2 VALUES are tolerance-checked only: 0.5 r ln r with r ~ 1e7 cancels heavily in fp32 and logf is not
+    bit-identical across libraries (5e-3 of max, as tests/test_oracle.py gates the oracle against the reference layer)."""
+    ocfg, otab1, spec, _, d = gc_case(seed=77, B=3, D=3, H=9, W=12, wells="two", R=1)
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=2, lam=0.001)
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=2, properties=srm.pvt.GC_PROPERTIES)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    wts = torch.tensor(W_ALL, dtype=torch.float32, device="cuda")
+    res = {}
+    for mode in (False, True):
+        eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=mode)
+        fw = eng.forward_gc(want_dom=True, **dev)
+        g = [t.clone() for t in eng.backward_gc(dterms=wts, **dev)]
+        res[mode] = (fw["dom"].clone(), fw["terms"].clone(), g)
+        if mode:
+            val, _ = eng.pvt_eval(dev["p1"].reshape(-1).contiguous())
+        eng.close()
+    assert torch.equal(res[False][0].view(torch.int32), res[True][0].view(torch.int32))
+    assert torch.allclose(res[False][1], res[True][1], rtol=1e-6)
+    for x, y in zip(res[False][2], res[True][2]):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-6 * max(float(x.abs().max()), 1e-30))
+    for pi in range(6):
+        ov = O.spline_eval_np(d["p1"].reshape(-1), otab, pi, np.float32, need=0)[0]
+        assert np.abs(val[pi].cpu().numpy() - ov).max() <= 5e-3 * np.abs(ov).max(), pi

@@ -11,6 +11,6 @@ for cfg in "$@"; do
   [ -n "$extra" ] && name="${name}_$(echo $extra | tr -d ' =-' )"
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --fmad=true \
     -DCF2_NT=$1 -DCF2_OCCF=$2 -DCF2_OCCA=$3 -DCF2_SF=$4 -DCF2_SA=$5 -DCF2_LXMAX=$6 $extra -c kernels_cf2.cu -o /tmp/$name.o
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/$name.so capi.o kernels_ref.o kernels_ref2.o kernels_dg4.o kernels_dg5.o kernels_gc.o kernels_cf.o /tmp/$name.o kernels_misc.o kernels_glue.o -lcudart
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/$name.so capi.o kernels_ref.o kernels_ref2.o kernels_dg4.o kernels_gc.o kernels_cf.o /tmp/$name.o kernels_misc.o kernels_glue.o -lcudart
   echo built variants/$name.so
 done
