@@ -109,6 +109,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   h->cfg.wells = nullptr;
   h->device = cfg->device;
   h->st_family = -1;
+  h->adj_packs = 0;
   h->no_dg4 = getenv("SRM_NO_DG4") != nullptr ? 1 : 0;      // test knob, read once here (tests compare the kernel families)
   SRM_CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
 
@@ -177,6 +178,12 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     int rc = cfg->fluid_type == SRM_FLUID_GC ? srm_build_pvt_lut_gc(h, lo, hi) : srm_build_pvt_lut(h, lo, hi);
     if (rc) { srm_destroy(h); return rc; }
   }
+  // Optional (SRM_ADJ_PACKS=1, read once here): the lean dry-gas forward stages the adjoint's six table values per cell
+  // through the workspace and the adjoint runs without table gathers.  Measured on B200 (cfg5, K = 8): adjoint
+  // 18.4 -> 14.7 ms, forward 15.6 -> 20.0 ms -- the 24 B per cell of extra stores cost the forward more than the
+  // adjoint gains, so it is off by default.
+  h->adj_packs = (cfg->fluid_type == SRM_FLUID_DG && srm_ws_mode(h) == SRM_WS_REF_FUSED && srm_dg4_applicable(h) && !h->no_dg4 &&
+                  getenv("SRM_ADJ_PACKS") != nullptr) ? 1 : 0;
   *out = h;
   return SRM_OK;
 }
@@ -192,7 +199,7 @@ void srm_destroy(SrmHandle* h) {
 }
 
 static SrmWs carve(const SrmHandle* h, void* base, int32_t B, int32_t R) {
-  return srm_carve(base, B, R, h->dev.N, h->dev.n_wells, srm_ws_mode(h), srm_ref2_face_floats(h->dev));
+  return srm_carve(base, B, R, h->dev.N, h->dev.n_wells, srm_ws_mode(h), srm_ref2_face_floats(h->dev), h->adj_packs != 0);
 }
 
 size_t srm_workspace_bytes(const SrmHandle* h, int32_t B, int32_t R, int32_t flags) {
@@ -287,7 +294,7 @@ int srm_forward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32
   if (mode == SRM_WS_CF)
     rc = srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
   else if (mode == SRM_WS_REF_FUSED)
-    rc = srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, s);
+    rc = srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, s, -1, save);
   else
     rc = srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_out, dom_out, ws, save, s);
   if (rc) return rc;
@@ -329,7 +336,7 @@ int srm_backward(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int3
     float* terms_tmp = nullptr;
     SRM_CUDA_CHECK(cudaMallocAsync((void**)&terms_tmp, sizeof(float) * 2 * SRM_N_TERMS, s));
     rc = cf ? srm_forward_cf(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s)
-         : mode == SRM_WS_REF_FUSED ? srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, s, fam)
+         : mode == SRM_WS_REF_FUSED ? srm_forward_ref2(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, s, fam, true)
             : srm_forward_ref(h, B, R, kx, sample_real, p0, p1, dt1, dt2, t1, terms_tmp, nullptr, ws, true, s);
     cudaFreeAsync(terms_tmp, s);
     if (rc) return rc;

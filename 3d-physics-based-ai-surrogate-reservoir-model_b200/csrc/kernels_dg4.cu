@@ -142,6 +142,10 @@ __device__ __forceinline__ bool thread_has_well4(const SrmDev& P, const Tile4& t
 // ------------------------------------------------------------------------------------------
 // forward                                                       physics_loss.py:143-193,787-807
 // ------------------------------------------------------------------------------------------
+// PK: the forward gathers the ADJOINT's 32-byte table entries (the same sectors as the forward's 16-byte ones) and
+// stages the six values the adjoint needs per cell -- cp, A0', A0'', G, A1', G' -- in the workspace, so that k_adj4<true>
+// runs without a single table gather (+24 B per cell-timestep each way through otherwise idle HBM bandwidth).
+template <bool PK>
 __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
   __shared__ __align__(16) float s_p[2 * PLANE];
   __shared__ __align__(16) float s_G[2 * PLANE];
@@ -177,8 +181,20 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
   const bool div_slow = !(by_d1.ok && by_den.ok) || c2e7 == 0.f || !P.cp_safe;
 
   const uint64_t keep = l2_evict_last(), strm = l2_evict_first();
-  const Tab TF = make_tab(P.lutf0, P, 16);
+  const Tab TF = make_tab(PK ? (const void*)P.lut0 : (const void*)P.lutf0, P, PK ? 32 : 16);
   const int own_s = (t.ty + 1) * SW + XO + CPT * t.cx;       // own cells inside a shared plane
+  float* __restrict__ pkb = PK ? A.pk + (int64_t)b * P.N : nullptr;
+  const int64_t pks = A.pk_stride;
+  // one pressure pair -> forward values {invBg, cp} / {invBg, G}; PK: plus {A0', A0''} / {A1', G'} for the adjoint pack
+  auto gat2 = [&](float p1v, float p0v, float2& e1, float2& e0, float2& x1, float2& x0) {
+    if constexpr (PK) {
+      const float4 a = GATA1(TF, p1v), c = GATA0(TF, p0v);
+      e1 = make_float2(a.x, a.y); x1 = make_float2(a.z, a.w);
+      e0 = make_float2(c.x, c.w); x0 = make_float2(c.y, c.z);
+    } else {
+      e1 = GATF1(TF, p1v); e0 = GATF0(TF, p0v);
+    }
+  };
 
   float a_dom = 0.f, a_tde = 0.f, a_mbf = 0.f;
   double a_ibc = 0.0, a_mb = 0.0;
@@ -186,7 +202,28 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
   // cell-local part of one plane: L = acc (+ tde), physics_loss.py:156,171,175; sums of tde^2 and of the
   // material-balance cells (:193) when `count`
   auto local = [&](const float (&p1)[CPT], const float (&p0)[CPT], const float2 (&e0)[CPT], const float2 (&e1)[CPT],
-                   float (&L)[CPT], bool count) {
+                   const float2 (&x0)[CPT], const float2 (&x1)[CPT], int off, float (&L)[CPT], bool count) {
+    if (PK && count) {          // the adjoint's pack of this plane: cp, A0', A0'', G, A1', G'
+      float v[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = e0[c].y;
+      stgs(pkb + off, v, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = x0[c].x;
+      stgs(pkb + pks + off, v, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = x0[c].y;
+      stgs(pkb + 2 * pks + off, v, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = e1[c].y;
+      stgs(pkb + 3 * pks + off, v, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = x1[c].x;
+      stgs(pkb + 4 * pks + off, v, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) v[c] = x1[c].y;
+      stgs(pkb + 5 * pks + off, v, strm);
+    }
     float dpv[CPT], numr[CPT], q1[CPT], q2[CPT];
     bool bad = div_slow;
 #pragma unroll
@@ -234,17 +271,17 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
       if (t.halo) { hp0 = LD_STRM(p1f + t.h_off, strm); hq = LD_STRM(p1f + (s1 + t.h_off), strm); }
       ldgs(p1f + off + s2, pq, strm);
       ldgs(p0f + off + s2, p0q, strm);
-      float2 e1a[CPT], e1b[CPT], e0a[CPT], e0b[CPT];
+      float2 e1a[CPT], e1b[CPT], e0a[CPT], e0b[CPT], x1a[CPT], x1b[CPT], x0a[CPT], x0b[CPT];
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
-        e1a[c] = GATF1(TF, pc[c]); e0a[c] = GATF0(TF, p0a[c]);
-        e1b[c] = GATF1(TF, pn[c]); e0b[c] = GATF0(TF, p0b[c]);
+        gat2(pc[c], p0a[c], e1a[c], e0a[c], x1a[c], x0a[c]);
+        gat2(pn[c], p0b[c], e1b[c], e0b[c], x1b[c], x0b[c]);
       }
-      if (t.halo) { s_p[t.h_slot] = hp0; s_G[t.h_slot] = GATF1(TF, hp0).y; }
+      if (t.halo) { s_p[t.h_slot] = hp0; s_G[t.h_slot] = PK ? GATA1G(TF, hp0).y : GATF1(TF, hp0).y; }
 #pragma unroll
       for (int c = 0; c < CPT; ++c) { Gc[c] = e1a[c].y; Gn[c] = e1b[c].y; tz[c] = -0.0f; }   // image face below plane 0: a5*(p - p) = +0
-      local(pc, p0a, e0a, e1a, Lc, t.valid);
-      local(pn, p0b, e0b, e1b, Ln, t.valid && D > 1);
+      local(pc, p0a, e0a, e1a, x0a, x1a, off, Lc, t.valid);
+      local(pn, p0b, e0b, e1b, x0b, x1b, off + s1, Ln, t.valid && D > 1);
       stsv(s_p + own_s, pc);
       stsv(s_G + own_s, Gc);
       mbar_arrive_warp(&s_bar);
@@ -273,11 +310,11 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
         if (t.halo && rem >= 2) hq = LD_STRM(p1f + (off - t.oc + 2 * HW + t.h_off), strm);
       }
       // gathers of plane k+2 (own) and k+1 (halo): in flight during the stencil of plane k
-      float2 e1nn[CPT], e0nn[CPT];
+      float2 e1nn[CPT], e0nn[CPT], x1nn[CPT], x0nn[CPT];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) { e1nn[c] = GATF1(TF, pnn[c]); e0nn[c] = GATF0(TF, p0nn[c]); }
+      for (int c = 0; c < CPT; ++c) gat2(pnn[c], p0nn[c], e1nn[c], e0nn[c], x1nn[c], x0nn[c]);
       float hG = 0.f;
-      if (t.halo && rem >= 1) hG = GATF1(TF, hp).y;
+      if (t.halo && rem >= 1) hG = PK ? GATA1G(TF, hp).y : GATF1(TF, hp).y;
       mbar_wait(&s_bar, k & 1);                          // plane k (own + halo) is in buffer sb
       float pS[CPT], pN[CPT], gS[CPT], gN[CPT];
       ldsv(sp + own_s - SW, pS);
@@ -356,7 +393,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
       mbar_arrive_warp(&s_bar);
       // cell-local part of plane k+2
       float Lnn[CPT];
-      local(pnn, p0nn, e0nn, e1nn, Lnn, t.valid && rem >= 2);
+      local(pnn, p0nn, e0nn, e1nn, x0nn, x1nn, off + 2 * HW, Lnn, t.valid && rem >= 2);
 #pragma unroll
       for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; Lc[c] = Ln[c]; pn[c] = pnn[c]; Gn[c] = e1nn[c].y; Ln[c] = Lnn[c]; }
       off += HW; offE += strE; offN += strN; offU += HW;
@@ -380,6 +417,8 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // adjoint: hand-derived, what tape.gradient delivers (physics_loss.py:849-859)
 // ------------------------------------------------------------------------------------------
+// PK: the six table values per cell come from the pack the forward staged (coalesced streams); no table gathers
+template <bool PK>
 __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant__ SrmDev P, const __grid_constant__ R2Args A) {
   __shared__ __align__(16) float s_p[2 * PLANE];
   __shared__ __align__(16) float s_G[2 * PLANE];
@@ -430,6 +469,22 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
   const Tab TA = make_tab(P.lut0, P, 32);
   const int own_s = (t.ty + 1) * SW + XO + CPT * t.cx;
   const float plo = P.p_min, phi_ = P.p_max;
+  const float* __restrict__ pkb = PK ? A.pk + (int64_t)b * P.N : nullptr;
+  const int64_t pks = A.pk_stride;
+  // the adjoint's table values of CPT cells: gathered, or (PK) streamed from the forward's pack at plane offset o
+  auto entries = [&](const float (&p1v)[CPT], const float (&p0v)[CPT], int o, float4 (&e1)[CPT], float4 (&e0)[CPT]) {
+    if constexpr (PK) {
+      float cp[CPT], a0p[CPT], a0pp[CPT], g[CPT], a1p[CPT], gp[CPT];
+      ldgs(pkb + o, cp, strm); ldgs(pkb + pks + o, a0p, strm); ldgs(pkb + 2 * pks + o, a0pp, strm);
+      ldgs(pkb + 3 * pks + o, g, strm); ldgs(pkb + 4 * pks + o, a1p, strm); ldgs(pkb + 5 * pks + o, gp, strm);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) { e1[c] = make_float4(0.f, g[c], a1p[c], gp[c]); e0[c] = make_float4(0.f, a0p[c], a0pp[c], cp[c]); }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) { e1[c] = GATA1(TA, p1v[c]); e0[c] = GATA0(TA, p0v[c]); }
+    }
+  };
+  auto halo_G = [&](float hp, int o) { return PK ? LD_STRM(pkb + 3 * pks + o, strm) : GATA1G(TA, hp).y; };
 
   float a_g1 = 0.f, a_g2 = 0.f;      // per-thread partial sums of dL/ddt1, dL/ddt2 (flushed to fp64 every 8 planes)
   double d_g1 = 0.0, d_g2 = 0.0;
@@ -501,12 +556,9 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
       ldgs(p1f + off + s2, pq, strm);
       ldgs(p0f + off + s2, p0q, strm);
       float4 e1a[CPT], e1b[CPT], e0a[CPT], e0b[CPT];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        e1a[c] = GATA1(TA, pc[c]); e0a[c] = GATA0(TA, p0a[c]);
-        e1b[c] = GATA1(TA, pn[c]); e0b[c] = GATA0(TA, p0b[c]);
-      }
-      if (t.halo) { s_p[t.h_slot] = hp0; s_G[t.h_slot] = GATA1G(TA, hp0).y; s_s[t.h_slot] = two_wd * hs0; }
+      entries(pc, p0a, off, e1a, e0a);
+      entries(pn, p0b, off + s1, e1b, e0b);
+      if (t.halo) { s_p[t.h_slot] = hp0; s_G[t.h_slot] = halo_G(hp0, t.h_off); s_s[t.h_slot] = two_wd * hs0; }
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         Gc[c] = e1a[c].y; Gn[c] = e1b[c].y; sc[c] *= two_wd; sn[c] *= two_wd;
@@ -546,10 +598,9 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
         if (t.halo && rem >= 1) hs = LD_STRM(domf + (off - t.oc + HW + t.h_off), strm);
       }
       float4 e1nn[CPT], e0nn[CPT];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) { e1nn[c] = GATA1(TA, pnn[c]); e0nn[c] = GATA0(TA, p0nn[c]); }
+      entries(pnn, p0nn, off + min(2, rem) * HW, e1nn, e0nn);
       float hG = 0.f;
-      if (t.halo && rem >= 1) hG = GATA1G(TA, hp).y;
+      if (t.halo && rem >= 1) hG = halo_G(hp, off - t.oc + HW + t.h_off);
       mbar_wait(&s_bar, k & 1);
       float pS[CPT], pN[CPT], gS[CPT], gN[CPT], sS[CPT], sN[CPT];
       ldsv(sp + own_s - SW, pS);
@@ -686,10 +737,14 @@ static cudaError_t dg4_set_carveout(int device) {
   int pct = 20;
   if (const char* e = getenv("SRM_D4_CARVEOUT")) pct = atoi(e);
   if (pct >= 0) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_fwd4, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaError_t e1 = cudaFuncSetAttribute(k_fwd4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e1 != cudaSuccess) return e1;
-    e1 = cudaFuncSetAttribute(k_adj4, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    e1 = cudaFuncSetAttribute(k_fwd4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (e1 != cudaSuccess) return e1;
+    e1 = cudaFuncSetAttribute(k_adj4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e1 != cudaSuccess) return e1;
+    // the gather-free adjoint has no table misses to keep in flight: it keeps the driver's default carve-out
+
   }
   done = true;
   return cudaSuccess;
@@ -701,7 +756,7 @@ cudaError_t srm_dg4_launch_fwd(const SrmHandle* h, const void* args, int32_t B, 
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  k_fwd4<<<grid, NT, 0, s>>>(P, A);
+  if (A.pk) k_fwd4<true><<<grid, NT, 0, s>>>(P, A); else k_fwd4<false><<<grid, NT, 0, s>>>(P, A);
   cudaError_t e = cudaGetLastError();
   // the residual field for the caller (tests, diagnostics): a copy of the adjoint's seed, off the hot path
   if (e == cudaSuccess && A.dom_out) e = cudaMemcpyAsync(A.dom_out, A.dom, sizeof(float) * (size_t)B * (size_t)P.N, cudaMemcpyDeviceToDevice, s);
@@ -714,7 +769,7 @@ cudaError_t srm_dg4_launch_adj(const SrmHandle* h, const void* args, int32_t B, 
   R2Args A = *reinterpret_cast<const R2Args*>(args);
   A.tiles_x = (P.W + TW - 1) / TW;
   const dim3 grid((unsigned)(A.tiles_x * ((P.H + TY - 1) / TY)), (unsigned)B);
-  k_adj4<<<grid, NT, 0, s>>>(P, A);
+  if (A.pk) k_adj4<true><<<grid, NT, 0, s>>>(P, A); else k_adj4<false><<<grid, NT, 0, s>>>(P, A);
   return cudaGetLastError();
 }
 

@@ -453,7 +453,7 @@ static R2Args make_args(const SrmDev& P, int32_t B, int32_t R, const int32_t* sa
 
 int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
-                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family) {
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family, bool save) {
   const SrmDev& P = h->dev;
   SRM_CUDA_CHECK(cudaMemsetAsync(ws.sse, 0, (char*)ws.mbc - (char*)ws.sse, s));   // sse, mb_sum, q_sum, gdt accs
   const FaceLay FL = face_layout(P.D, P.H, P.W);
@@ -470,6 +470,8 @@ int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const 
   const bool lean = force_family >= 0 ? (force_family == 1 && use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr))
                                       : use_dg4(h, p0, p1, ws.dom, dom_out, nullptr, nullptr);
   h->st_family = lean ? 1 : 0;
+  A.pk = (lean && save) ? ws.pk : nullptr;            // the lean forward stages the adjoint's table values
+  A.pk_stride = (int64_t)B * P.N;
 #ifdef SRM_WITH_DG5
   if (lean && srm_dg5_applicable(h)) {
     SRM_CUDA_CHECK(srm_dg5_launch_fwd(h, &A, B, s));
@@ -498,6 +500,8 @@ int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const
   R2Args A = make_args(P, B, R, sample_real, p0, p1, dt1, dt2, ws);
   A.dterms = dterms; A.gp0 = gp0; A.gp1 = gp1;
   const bool dg4 = use_dg4(h, p0, p1, ws.dom, nullptr, gp0, gp1);
+  A.pk = dg4 ? ws.pk : nullptr;                        // written by the forward that saved this state (same family)
+  A.pk_stride = (int64_t)B * P.N;
   if (dg4) {
     SRM_CUDA_CHECK(srm_dg4_launch_adj(h, &A, B, s));
   } else {

@@ -104,6 +104,8 @@ struct SrmHandle {
   int32_t st_B, st_R; int32_t st_valid;
   int32_t st_family;   // fused reference path: kernel family of the forward that saved the state (1 lean kernels_dg4.cu, 0 generic)
   int32_t no_dg4;      // test knob SRM_NO_DG4, read ONCE at srm_create: the handle runs the generic fused kernels only
+  int32_t adj_packs;   // lean family: the forward stages the adjoint's six table values per cell in the workspace (24 B per
+                       // cell-timestep through otherwise idle HBM bandwidth), so the adjoint runs without table gathers
 };
 static inline void srm_state_set(SrmHandle* h, int32_t B, int32_t R, const void* ws, const void* kx, const void* sr, const void* p0,
                                  const void* p1, const void* sg0, const void* sg1, const void* so0, const void* so1,
@@ -151,6 +153,7 @@ struct SrmWs {
   float* A0pp;
   float* G1p;
   float* A1p;
+  float* pk;          // fused reference path, lean family: adjoint packs [6][B*N] = cp, A0', A0'', G, A1', G'
   size_t bytes;
 };
 
@@ -166,7 +169,7 @@ static inline int srm_ws_mode(const SrmHandle* h) {
   return h->dev.lut_n > 0 ? SRM_WS_REF_FUSED : SRM_WS_REF_STAGED;
 }
 
-static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64_t nw, int mode, size_t face_floats) {
+static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64_t nw, int mode, size_t face_floats, bool packs = false) {
   const bool closed_form = mode == SRM_WS_CF;
   SrmWs w;
   char* p = (char*)base;
@@ -209,6 +212,8 @@ static inline SrmWs srm_carve(void* base, int64_t B, int64_t R, int64_t N, int64
     w.G1p = (float*)take(fb);
     w.A1p = (float*)take(fb);
   }
+  w.pk = nullptr;
+  if (mode == SRM_WS_REF_FUSED && packs) w.pk = (float*)take(6 * fb);
   w.bytes = off;
   return w;
 }
@@ -231,10 +236,11 @@ int srm_launch_wells_ref(const SrmHandle* h, int32_t B, const float* kx, const i
                          float* dqdp_sorted, cudaStream_t s);
 int srm_build_pvt_lut(SrmHandle* h, float lo, float hi);
 int srm_build_pvt_lut_gc(SrmHandle* h, float lo, float hi);
+bool srm_dg4_applicable(const SrmHandle* h);       // kernels_dg4.cu
 int srm_ref2_backward_family(const SrmHandle* h, const float* p0, const float* p1, const void* dom_ws, const float* gp0, const float* gp1);
 int srm_forward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                      const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
-                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family = -1);
+                     float* terms_out, float* dom_out, const SrmWs& ws, cudaStream_t s, int force_family = -1, bool save = true);
 int srm_backward_ref2(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,
                       const float* p0, const float* p1, const float* dt1, const float* dt2, const float* t1,
                       const float* dterms, float* gp0, float* gp1, float* gdt1, float* gdt2,
