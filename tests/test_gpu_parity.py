@@ -517,3 +517,21 @@ def test_adjoint_never_mixes_kernel_families():
     for a, b in zip(again[:2], ref[:2]):
         assert torch.equal(a, b)
     eng.close()
+
+
+def test_staged_adjoint_packs_are_equivalent(monkeypatch):
+    """SRM_ADJ_PACKS=1 (read at handle creation): the lean forward stages the adjoint's six table values per cell in the
+    workspace and the adjoint streams them instead of gathering.  Same table values, same arithmetic: the residual field
+    is bit-identical and the gradients equal the gathered adjoint's bit for bit."""
+    ocfg, otab, spec, ptab, batch = U.make_case(W=72, H=21, D=5, T=2, K=2, seed=2090, all_layers=True)
+    base = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    monkeypatch.setenv("SRM_ADJ_PACKS", "1")
+    eng = srm.SrmPhysics(spec, ptab, device=0, pvt_lut=True)
+    B = batch.p0.shape[0]
+    assert eng.workspace_bytes(B, 2) >= 6 * 4 * batch.p0.numel()          # the packs live in the workspace
+    eng.close()
+    pk = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    assert np.array_equal(np.asarray(pk["dom"]).view(np.uint32), np.asarray(base["dom"]).view(np.uint32))
+    for k in ("gp0", "gp1"):
+        assert np.array_equal(np.asarray(pk[k]).view(np.uint32), np.asarray(base[k]).view(np.uint32)), k
+    assert np.allclose(pk["gdt1"], base["gdt1"], rtol=1e-6) and np.allclose(pk["terms"], base["terms"], rtol=1e-6)
