@@ -164,6 +164,33 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     if (e == cudaSuccess) e = cudaMemcpy(h->d_wells, wd.data(), sizeof(WellDev) * cfg->n_wells, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { srm_set_error("srm_create: wells upload: %s", cudaGetErrorString(e)); srm_destroy(h); return SRM_ERR_CUDA; }
     P.wells = h->d_wells;
+    // column lists (well_tile.cuh): connections grouped by (j, i), layers ascending; integer work
+    {
+      const int HW = cfg->H * cfg->W, nw = cfg->n_wells;
+      std::vector<int> order(nw);
+      for (int w = 0; w < nw; ++w) order[w] = w;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return wd[a].cell % HW < wd[b].cell % HW; });   // wd is cell-sorted: layers stay ascending
+      std::vector<int32_t> rem, ptr;
+      std::vector<int32_t> ent(2 * (size_t)nw);
+      for (int t = 0; t < nw; ++t) {
+        const int w = order[t], r = wd[w].cell % HW;
+        if (rem.empty() || rem.back() != r) { rem.push_back(r); ptr.push_back(t); }
+        ent[2 * t] = wd[w].cell / HW; ent[2 * t + 1] = w;
+      }
+      ptr.push_back(nw);
+      const size_t nc = rem.size();
+      std::vector<int32_t> blob;
+      blob.insert(blob.end(), rem.begin(), rem.end());
+      blob.insert(blob.end(), ptr.begin(), ptr.end());
+      if (blob.size() & 1) blob.push_back(0);            // col_ent is read as int2
+      const size_t ent_at = blob.size();
+      blob.insert(blob.end(), ent.begin(), ent.end());
+      e = cudaMalloc((void**)&h->d_wcols, sizeof(int32_t) * blob.size());
+      if (e == cudaSuccess) e = cudaMemcpy(h->d_wcols, blob.data(), sizeof(int32_t) * blob.size(), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { srm_set_error("srm_create: well columns upload: %s", cudaGetErrorString(e)); srm_destroy(h); return SRM_ERR_CUDA; }
+      P.n_cols = (int32_t)nc;
+      P.col_rem = h->d_wcols; P.col_ptr = h->d_wcols + nc; P.col_ent = reinterpret_cast<const int2*>(h->d_wcols + ent_at);
+    }
   }
   if (!poly && cfg->spline_order == 1) {
     int rc = srm_build_closed_form(h, cfg);
@@ -192,6 +219,7 @@ void srm_destroy(SrmHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->d_wells) cudaFree(h->d_wells);
+  if (h->d_wcols) cudaFree(h->d_wcols);
   if (h->d_cf) cudaFree(h->d_cf);
   if (h->d_cf2) cudaFree(h->d_cf2);
   if (h->d_lut) cudaFree(h->d_lut);

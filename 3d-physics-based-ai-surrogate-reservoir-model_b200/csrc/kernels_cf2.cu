@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "well_tile.cuh"
 
 #define CF2_NB 2048
 
@@ -154,10 +155,17 @@ struct Geo {
   static constexpr int TX_A = TX_F + P1_B;
   static constexpr int RING = 2 * TX + 2 * TY;
   static constexpr int GPL = al128(P1_B);                            // one G plane (same layout as the p1 box)
+  using WT = WellTile<NT, TX, TY, 16, 320>;           // the tile's connections (well_tile.cuh)
   template <bool ADJ> static constexpr int total() {
-    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + NGP * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + TY * TX /*well flags*/;
+    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + NGP * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + (int)sizeof(WT);
   }
 };
+
+#if CF2_SF == 3 && CF2_SA == 3 && CF2_CPT == 4 && CF2_NT == 256 && !CF2_FREE
+// two CTAs per SM: dynamic + static (reduction scratch) + the 1 KB the system reserves per CTA, out of 228 KB
+static_assert(2 * (Geo<32>::total<true>() + 1024 + 1024) <= 233472, "the adjoint no longer fits twice into an SM's shared memory");
+static_assert(2 * (Geo<32>::total<false>() + 1024 + 1024) <= 233472, "the forward no longer fits twice into an SM's shared memory");
+#endif
 
 struct Cf2Args {
   const float* dt1; const int32_t* sample_real;
@@ -269,6 +277,7 @@ struct Cf2Dev {
   float dv, invDc, dvDc, Dc, K1, K2, dvSgi_phi;    // K1 = Sgi*phi, K2 = Sgi*phi*cf
   int32_t tde_in_dom, n_wells;
   const WellDev* wells;
+  WellColsDev wc;
 };
 __device__ __forceinline__ int cf2_lower_bound(const Cf2Dev& P, int c) {
   int lo = 0, hi = P.n_wells;
@@ -374,7 +383,8 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
   uint64_t* empty = full + S;           // barrier-free march: one arrival per warp when it has read a stage for the last time
   static_assert(2 * S * 8 <= 128, "barrier block");
-  unsigned char* flags = smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
+  unsigned char* flags = WTs.slot_of;
   __shared__ double red[4 * 32];
 
   const int tid = threadIdx.x;
@@ -403,8 +413,14 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     for (int k = 0; k < S && k < D; ++k) issue(k);
   }
   for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
-  bool tile_wells = false;
-  const bool has_well = (P.n_wells > 0) ? thread_has_well<LX>(P, t, flags, tile_wells) : false;
+  // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
+  bool tile_wells = false, wt_overflow = false, has_well = false;
+  uint32_t wslots = 0;
+  if (P.n_wells > 0) {
+    tile_wells = WTs.build(P.wc, P.W, P.D, t.x0, t.y0, A.qw + (int64_t)b * P.n_wells, wt_overflow);
+    if (wt_overflow) has_well = thread_has_well<LX>(P, t, flags, tile_wells);
+    else if (tile_wells && t.valid) { wslots = WTs.template slots_of<CPT>(t.ry * G::TX + CPT * t.lx); has_well = wslots != 0; }
+  }
   __syncthreads();
 
   // per-sample scalars                                                      physics_loss.py:156,171,193
@@ -561,7 +577,24 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         a_tde = fmaf(tde, tde, a_tde);
         a_mb += (a1c[c] - A0[c]) + (a1lc[c] - A0l[c]);
       }
-      if (tile_wells && has_well) {     // wells in this thread's columns (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
+      if (tile_wells && has_well && !wt_overflow) {     // wells in this thread's columns, from the staged lists (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const uint32_t sl = (wslots >> (8 * c)) & 255u;
+          if (sl) {
+            int first, last;
+            WTs.take((int)sl - 1, m, first, last);
+            if (last > first) {
+              float q = 0.f;
+              for (int e = first; e < last; ++e) q += WTs.val[e];
+              dvf[c] += q;                                                      // divq = dv * flux + q    physics_loss.py:174
+              for (int e = first; e < last; ++e) A.divqw[(int64_t)b * P.n_wells + WTs.w[e]] = dvf[c];
+              const float ibc = (float)(last - first) * dvf[c];                 // physics_loss.py:189
+              d_ibc += (double)ibc * (double)ibc;
+            }
+          }
+        }
+      } else if (tile_wells && has_well) {     // lists that did not fit: search the cell-sorted table
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const int cell = m * P.H * P.W + cell0 + c;
@@ -625,7 +658,8 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
   uint64_t* empty = full + S;
   static_assert(2 * S * 8 <= 128, "barrier block");
-  unsigned char* flags = smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128;
+  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
+  unsigned char* flags = WTs.slot_of;
   __shared__ double red[32];
 
   const int tid = threadIdx.x;
@@ -653,8 +687,14 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     for (int k = 0; k < S && k < D; ++k) issue(k);
   }
   for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
-  bool tile_wells = false;
-  const bool has_well = (P.n_wells > 0) ? thread_has_well<LX>(P, t, flags, tile_wells) : false;
+  // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
+  bool tile_wells = false, wt_overflow = false, has_well = false;
+  uint32_t wslots = 0;
+  if (P.n_wells > 0) {
+    tile_wells = WTs.build(P.wc, P.W, P.D, t.x0, t.y0, A.dqdp + (int64_t)b * P.n_wells, wt_overflow);
+    if (wt_overflow) has_well = thread_has_well<LX>(P, t, flags, tile_wells);
+    else if (tile_wells && t.valid) { wslots = WTs.template slots_of<CPT>(t.ry * G::TX + CPT * t.lx); has_well = wslots != 0; }
+  }
   __syncthreads();
 
   const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_tde = A.dterms[SRM_TERM_TDE];
@@ -821,7 +861,19 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         g0v[c] = sc * cA * (cpp * dp10 - cp) + stt * cT * cpp + smbk * Apm;
         a_g1 -= (sc * acc + stt * tde) * inv_d1;
       }
-      if (tile_wells && has_well) {
+      if (tile_wells && has_well && !wt_overflow) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const uint32_t sl = (wslots >> (8 * c)) & 255u;
+          if (sl) {
+            int first, last;
+            float dq = 0.f;
+            WTs.take((int)sl - 1, m, first, last);
+            for (int e = first; e < last; ++e) dq += WTs.val[e];
+            g1v[c] += (sd * dc[c] - smb) * dq;
+          }
+        }
+      } else if (tile_wells && has_well) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const int cell = m * P.H * P.W + cell0 + c;
@@ -895,7 +947,7 @@ Cf2Dev slim(const SrmDev& P) {
   d.D = P.D; d.H = P.H; d.W = P.W; d.N = P.N;
   d.dv = P.dv; d.invDc = P.invDc; d.dvDc = P.dvDc; d.Dc = P.Dc;
   d.K1 = P.Sgi * P.phi; d.K2 = P.Sgi * P.phicf; d.dvSgi_phi = P.dvSgi_phi;
-  d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells;
+  d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells; d.wc = well_cols_of(P);
   return d;
 }
 int lanes_for(int W) { const int l = W >= 24 * CPT ? 32 : (W >= 12 * CPT ? 16 : 8); return l > CF2_LXMAX ? CF2_LXMAX : l; }

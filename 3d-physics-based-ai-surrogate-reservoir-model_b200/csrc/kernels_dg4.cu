@@ -25,6 +25,7 @@
 #include <cstring>
 #include "ref_fused.cuh"
 #include "dg_lean.cuh"
+#include "well_tile.cuh"
 
 namespace {
 
@@ -119,6 +120,8 @@ __device__ __forceinline__ Tile4 make_tile4(const SrmDev& P, int tiles_x) {
   return t;
 }
 
+using WTile = WellTile<NT, TW, TY, 8, 192>;
+
 // marks the threads that own a cell column with a well connection (any layer)
 __device__ __forceinline__ bool thread_has_well4(const SrmDev& P, const Tile4& t, unsigned char (*s_flag)[TW]) {
   unsigned char* flat = &s_flag[0][0];
@@ -150,15 +153,25 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
   __shared__ __align__(16) float s_p[2 * PLANE];
   __shared__ __align__(16) float s_G[2 * PLANE];
   __shared__ double red[4 * 32];
-  __shared__ __align__(4) unsigned char s_flag[TY][TW];
+  __shared__ __align__(8) WTile s_wt;
   __shared__ __align__(8) uint64_t s_bar;
   const Tile4 t = make_tile4(P, A.tiles_x);
   const int b = blockIdx.y;
   const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   if (threadIdx.x == 0) mbar_init(&s_bar, NT / 32);
   __syncthreads();
-  const bool has_well = (P.n_wells > 0) ? thread_has_well4(P, t, s_flag) : false;
-  const bool tile_wells = (P.n_wells > 0) ? (__syncthreads_or(has_well ? 1 : 0) != 0) : false;
+  // the tile's connections: column lists staged in shared memory (well_tile.cuh); lists that do not fit keep the search
+  bool tile_wells = false, wt_overflow = false, has_well = false;
+  uint32_t wslots = 0;
+  if (P.n_wells > 0) {
+    tile_wells = s_wt.build(well_cols_of(P), P.W, P.D, t.x0, t.y0, A.qw + (int64_t)b * P.n_wells, wt_overflow);
+    if (wt_overflow) {
+      has_well = thread_has_well4(P, t, reinterpret_cast<unsigned char (*)[TW]>(s_wt.slot_of));
+      tile_wells = __syncthreads_or(has_well ? 1 : 0) != 0;
+    } else if (tile_wells && t.valid) {
+      wslots = s_wt.template slots_of<CPT>(t.ty * TW + CPT * t.cx);
+    }
+  }
   const int W = P.W, H = P.H, D = P.D, HW = H * W;
   const FaceLay FL = face_layout(D, H, W);
   const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
@@ -257,7 +270,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
   };
 
   auto march = [&](auto WT) {
-    constexpr bool WELLS = decltype(WT)::value;
+    constexpr int WELLS = decltype(WT)::value;      // 0: no connection in the tile, 1: staged lists, 2: search (lists did not fit)
     int off = t.oc, offE = yy * FL.WP + xx, offN = (int)FL.nE + t.oc, offU = (int)(FL.nE + FL.nN) + t.oc + HW;
     float pc[CPT], Gc[CPT], Lc[CPT], pn[CPT], Gn[CPT], Ln[CPT], tz[CPT], pq[CPT], p0q[CPT], hq = 0.f;
     {
@@ -349,9 +362,18 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
         tz[c] = tu;
         // wells in this cell (scatter_nd sums duplicates)                        well_rate_bhp_Subclassed.py:128-132
         float qdv = 0.f, mask = 0.f;
-        int wfirst = 0;
+        int wfirst = 0, wlast = 0;
         const int cell = off + c;
-        if (WELLS && has_well) {
+        if (WELLS == 1) {
+          const uint32_t sl = (wslots >> (8 * c)) & 255u;
+          if (sl) {
+            float q = 0.f;
+            s_wt.take((int)sl - 1, k, wfirst, wlast);
+            for (int e = wfirst; e < wlast; ++e) { q = __fadd_rn(q, s_wt.val[e]); mask += 1.f; }
+            if (mask != 0.f) qdv = __fdiv_rn(q, P.dv);
+          }
+        }
+        if (WELLS == 2 && has_well) {
           float q = 0.f;
           wfirst = well_lower_bound(P, cell);
           for (int w = wfirst; w < P.n_wells && P.wells[w].cell == cell; ++w) {
@@ -373,7 +395,8 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
         domv[c] = dom;
         dsum = fmaf(dom, dom, dsum);
         if (WELLS && mask != 0.f && t.valid) {
-          for (int w = wfirst; w < P.n_wells && P.wells[w].cell == cell; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq;
+          if (WELLS == 1) { for (int e = wfirst; e < wlast; ++e) A.divqw[(int64_t)b * P.n_wells + s_wt.w[e]] = divq; }
+          else { for (int w = wfirst; w < P.n_wells && P.wells[w].cell == cell; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq; }
           const float ibc = __fmul_rn(mask, divq);                                // physics_loss.py:189
           a_ibc += (double)ibc * (double)ibc;
         }
@@ -401,7 +424,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
       if ((k & 7) == 7) { a_mb += (double)a_mbf; a_mbf = 0.f; }
     }
   };
-  if (tile_wells) march(BoolC<true>()); else march(BoolC<false>());
+  if (!tile_wells) march(IntC<0>()); else if (!wt_overflow) march(IntC<1>()); else march(IntC<2>());
 
   double acc4[4] = {(double)a_dom, a_ibc, (double)a_tde, a_mb + (double)a_mbf};
   __syncthreads();
@@ -424,15 +447,25 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
   __shared__ __align__(16) float s_G[2 * PLANE];
   __shared__ __align__(16) float s_s[2 * PLANE];
   __shared__ double red[2 * 32];
-  __shared__ __align__(4) unsigned char s_flag[TY][TW];
+  __shared__ __align__(8) WTile s_wt;
   __shared__ __align__(8) uint64_t s_bar;
   const Tile4 t = make_tile4(P, A.tiles_x);
   const int b = blockIdx.y;
   const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   if (threadIdx.x == 0) mbar_init(&s_bar, NT / 32);
   __syncthreads();
-  const bool has_well = (P.n_wells > 0) ? thread_has_well4(P, t, s_flag) : false;
-  const bool tile_wells = (P.n_wells > 0) ? (__syncthreads_or(has_well ? 1 : 0) != 0) : false;
+  // the tile's connections: column lists staged in shared memory (well_tile.cuh); lists that do not fit keep the search
+  bool tile_wells = false, wt_overflow = false, has_well = false;
+  uint32_t wslots = 0;
+  if (P.n_wells > 0) {
+    tile_wells = s_wt.build(well_cols_of(P), P.W, P.D, t.x0, t.y0, A.dqdp + (int64_t)b * P.n_wells, wt_overflow);
+    if (wt_overflow) {
+      has_well = thread_has_well4(P, t, reinterpret_cast<unsigned char (*)[TW]>(s_wt.slot_of));
+      tile_wells = __syncthreads_or(has_well ? 1 : 0) != 0;
+    } else if (tile_wells && t.valid) {
+      wslots = s_wt.template slots_of<CPT>(t.ty * TW + CPT * t.cx);
+    }
+  }
   const int W = P.W, H = P.H, D = P.D, HW = H * W;
   const FaceLay FL = face_layout(D, H, W);
   const float* __restrict__ p0f = A.p0 + (int64_t)b * P.N;
@@ -537,7 +570,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
   };
 
   auto march = [&](auto WT) {
-    constexpr bool WELLS = decltype(WT)::value;
+    constexpr int WELLS = decltype(WT)::value;
     int off = t.oc, offE = yy * FL.WP + xx, offN = (int)FL.nE + t.oc, offU = (int)(FL.nE + FL.nN) + t.oc + HW;
     // planes k and k+1: p1, G, masked G', seed, local part of dL/dp1; carried upper-face pair of the plane below
     float pc[CPT], Gc[CPT], Gpc[CPT], sc[CPT], Lc[CPT], pn[CPT], Gn[CPT], Gpn[CPT], sn[CPT], Ln[CPT], Xz[CPT], Yz[CPT];
@@ -656,7 +689,17 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
           Xz[c] = X; Yz[c] = Y;
         }
         float g1 = fmaf(P.dv, fmaf(Gpc[c], sy[c], sx[c]), Lc[c]);
-        if (WELLS && has_well) {
+        if (WELLS == 1) {
+          const uint32_t sl = (wslots >> (8 * c)) & 255u;
+          if (sl) {
+            int first, last;
+            float dq = 0.f;
+            s_wt.take((int)sl - 1, k, first, last);
+            for (int e = first; e < last; ++e) dq += s_wt.val[e];
+            g1 = fmaf(s0 - smb, dq, g1);
+          }
+        }
+        if (WELLS == 2 && has_well) {
           const int cell = off + c;
           float dq = 0.f;
           const int first = well_lower_bound(P, cell);
@@ -691,7 +734,7 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
       if ((k & 7) == 7) { d_g1 += (double)a_g1; d_g2 += (double)a_g2; a_g1 = 0.f; a_g2 = 0.f; }
     }
   };
-  if (tile_wells) march(BoolC<true>()); else march(BoolC<false>());
+  if (!tile_wells) march(IntC<0>()); else if (!wt_overflow) march(IntC<1>()); else march(IntC<2>());
 
   double acc2[2] = {d_g1 + (double)a_g1, d_g2 + (double)a_g2};
   __syncthreads();

@@ -34,6 +34,12 @@ struct SrmDev {
   int32_t root_solver, n_root_iter;   // GC blocking-factor integral: SRM_ROOT_*, iterations per trapezoid node
   int32_t n_wells;
   const WellDev* wells;  // device, sorted by cell
+  // the same connections grouped by (j, i) column, layers ascending inside a column (well_tile.cuh): what a z-marching
+  // tile needs to find its connections without searching the cell-sorted table once per plane
+  int32_t n_cols;
+  const int32_t* col_rem;   // [n_cols]      j*W + i of the column, ascending
+  const int32_t* col_ptr;   // [n_cols + 1]  range of the column in col_ent
+  const int2* col_ent;      // [n_wells]     {layer k, position in the cell-sorted table}, sorted by (column, layer, position)
   // spline
   int32_t n_knots, order, n_props;   // polynomial fit: n_knots = number of coefficients, w[q][i] = coefficient i
   int32_t pvt_method;                // SRM_PVT_*
@@ -90,6 +96,7 @@ struct SrmHandle {
   SrmConfig cfg;       // host copy (pointers nulled)
   SrmDev dev;          // device parameter block
   WellDev* d_wells;    // device
+  int32_t* d_wcols;    // device: col_rem | col_ptr | col_ent of the parameter block (one allocation)
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
   void* d_cf2;         // device (tables of the lean closed-form pair, kernels_cf2.cu), may be null
   int cf_faces_ok, cf_grouped;   // closed form: which per-call scratch the last forward left in the workspace

@@ -25,11 +25,16 @@ CASES = [
     dict(W=16, H=16, D=4, T=2, K=2, seed=2003, all_layers=True, use_blocking_factor=True),
     dict(W=36, H=10, D=9, T=3, K=2, seed=2004),                           # two z-chunks of 8 + 1
     dict(W=33, H=7, D=2, T=1, K=1, seed=2005, wells="none"),
+    dict(W=64, H=20, D=5, T=2, K=1, seed=2006, wells=("crowded", 4)),    # staged column lists (well_tile.cuh), a duplicate connection
+    dict(W=64, H=20, D=5, T=2, K=1, seed=2007, wells=("crowded", 18)),   # more well columns in a tile than the lists hold
 ]
 
 
 @pytest.mark.parametrize("kw", CASES)
 def test_closed_form_vs_fp64_oracle(kw):
+    kw = dict(kw)
+    if isinstance(kw.get("wells"), tuple):
+        kw["wells"] = U.crowded_wells(kw["D"], kw["wells"][1])
     ocfg, otab, spec, ptab, batch = U.make_case(**kw)
     o64 = U.oracle_run(ocfg, otab, batch, dtype=torch.float64)
     o32 = U.oracle_run(ocfg, otab, batch)
