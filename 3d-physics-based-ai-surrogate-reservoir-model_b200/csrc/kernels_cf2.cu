@@ -163,8 +163,8 @@ struct Geo {
 
 #if CF2_SF == 3 && CF2_SA == 3 && CF2_CPT == 4 && CF2_NT == 256 && !CF2_FREE
 // two CTAs per SM: dynamic + static (reduction scratch) + the 1 KB the system reserves per CTA, out of 228 KB
-static_assert(2 * (Geo<32>::total<true>() + 1024 + 1024) <= 233472, "the adjoint no longer fits twice into an SM's shared memory");
-static_assert(2 * (Geo<32>::total<false>() + 1024 + 1024) <= 233472, "the forward no longer fits twice into an SM's shared memory");
+static_assert(2 * (Geo<32>::total<true>() + 1024) <= 233472, "the adjoint no longer fits twice into an SM's shared memory");
+static_assert(2 * (Geo<32>::total<false>() + 1024) <= 233472, "the forward no longer fits twice into an SM's shared memory");
 #endif
 
 struct Cf2Args {
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   static_assert(2 * S * 8 <= 128, "barrier block");
   typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
   unsigned char* flags = WTs.slot_of;
-  __shared__ double red[4 * 32];
+  double* red = reinterpret_cast<double*>(smem);      // reduction scratch: stage 0, after the last plane has been consumed
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   static_assert(2 * S * 8 <= 128, "barrier block");
   typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
   unsigned char* flags = WTs.slot_of;
-  __shared__ double red[32];
+  double* red = reinterpret_cast<double*>(smem);      // reduction scratch: stage 0, after the last plane has been consumed
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;

@@ -34,7 +34,9 @@ CASES = [
 def test_closed_form_vs_fp64_oracle(kw):
     kw = dict(kw)
     if isinstance(kw.get("wells"), tuple):
-        kw["wells"] = U.crowded_wells(kw["D"], kw["wells"][1])
+        # rate-controlled connections only: at the BHP limit the fp64 yardstick and an fp32 evaluation may sit on different
+        # sides of the switch (d rate / d p jumps there), which says nothing about the kernels
+        kw["wells"] = U.crowded_wells(kw["D"], kw["wells"][1], minimum_bhp=3000.0)
     ocfg, otab, spec, ptab, batch = U.make_case(**kw)
     o64 = U.oracle_run(ocfg, otab, batch, dtype=torch.float64)
     o32 = U.oracle_run(ocfg, otab, batch)

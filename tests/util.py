@@ -43,7 +43,7 @@ def make_case(W, H, D, T, K, seed, wells="default", all_layers=False, use_blocki
     return ocfg, otab, spec, ptab, batch
 
 
-def crowded_wells(D, n_cols, j=1, i0=2, step=2, duplicate=True):
+def crowded_wells(D, n_cols, j=1, i0=2, step=2, duplicate=True, minimum_bhp=4100.0):
     """n_cols producer columns next to each other in grid row j, completed in every layer, plus (duplicate) a second
     connection in the first column's top cell: more columns than a tile's staged lists hold (well_tile.cuh) send the
     kernels to their search path, and the duplicate exercises the summed scatter (welldata_processor.py:170-224)"""
@@ -51,7 +51,7 @@ def crowded_wells(D, n_cols, j=1, i0=2, step=2, duplicate=True):
     for t in range(n_cols):
         for k in range(D):
             conns.append({"name": f"C{t}", "i": i0 + step * t, "j": j, "k": k, "type": "producer", "control": "ORAT",
-                          "value": 400.0 + 50.0 * (t % 3), "minimum_bhp": 4100.0, "wellbore_radius": 0.09525,
+                          "value": 400.0 + 50.0 * (t % 3), "minimum_bhp": minimum_bhp, "wellbore_radius": 0.09525,
                           "completion_ratio": 0.5, "shutin_days": [[1000.0, 0.0]]})
     if duplicate:
         conns.append(dict(conns[0], name="Cdup", value=250.0))
