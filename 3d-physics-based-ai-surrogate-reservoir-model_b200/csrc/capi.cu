@@ -185,11 +185,20 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
       if (blob.size() & 1) blob.push_back(0);            // col_ent is read as int2
       const size_t ent_at = blob.size();
       blob.insert(blob.end(), ent.begin(), ent.end());
+      const size_t lay_at = blob.size();
+      {
+        int w = 0;
+        for (int k = 0; k <= cfg->D; ++k) {                // first connection with cell >= k*HW
+          while (w < nw && wd[w].cell < (int64_t)k * HW) ++w;
+          blob.push_back(w);
+        }
+      }
       e = cudaMalloc((void**)&h->d_wcols, sizeof(int32_t) * blob.size());
       if (e == cudaSuccess) e = cudaMemcpy(h->d_wcols, blob.data(), sizeof(int32_t) * blob.size(), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) { srm_set_error("srm_create: well columns upload: %s", cudaGetErrorString(e)); srm_destroy(h); return SRM_ERR_CUDA; }
       P.n_cols = (int32_t)nc;
       P.col_rem = h->d_wcols; P.col_ptr = h->d_wcols + nc; P.col_ent = reinterpret_cast<const int2*>(h->d_wcols + ent_at);
+      P.layer_ptr = h->d_wcols + lay_at;
     }
   }
   if (!poly && cfg->spline_order == 1) {

@@ -42,9 +42,10 @@ __device__ __forceinline__ float div_z(float a, float b) {
   return __fdiv_rn(a, b);
 }
 
-// first well (sorted by cell) with cell >= c
+// first well (sorted by cell) with cell >= c: binary search inside the cell's layer
 __device__ __forceinline__ int well_lower_bound(const SrmDev& P, int c) {
-  int lo = 0, hi = P.n_wells;
+  const int k = c / (P.H * P.W);
+  int lo = P.layer_ptr[k], hi = P.layer_ptr[k + 1];
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (P.wells[mid].cell < c) lo = mid + 1; else hi = mid;

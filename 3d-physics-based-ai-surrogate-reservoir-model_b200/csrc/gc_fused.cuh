@@ -21,7 +21,10 @@
 constexpr int G2X = 32, G2Y = 8, G2PX = G2X + 2, G2PL = (G2Y + 2) * G2PX;
 static_assert(G2X * G2Y == kThreads, "one column per thread");
 
+using G2Wells = WellTile<kThreads, G2X, G2Y, 8, 192>;      // the tile's connections (well_tile.cuh)
+
 struct G2Geom {
+  int tx0, ty0, lt;                 // tile origin, own cell inside the tile (row-major)
   int gi, gj, ci, cj, col, so;      // own column: global, clamped, flat, shared slot
   bool active, halo;
   int hcol, hs;                     // halo duty of this thread: clamped flat column, shared slot
@@ -31,6 +34,7 @@ __device__ __forceinline__ G2Geom g2_geom(const SrmDev& P, int tiles_x) {
   const int tile = blockIdx.x;
   const int ty0 = (tile / tiles_x) * G2Y, tx0 = (tile % tiles_x) * G2X;
   const int t = threadIdx.x, tx = t & (G2X - 1), ty = t / G2X;
+  g.tx0 = tx0; g.ty0 = ty0; g.lt = ty * G2X + tx;
   g.gi = tx0 + tx; g.gj = ty0 + ty;
   g.active = g.gi < P.W && g.gj < P.H;
   g.ci = min(g.gi, P.W - 1); g.cj = min(g.gj, P.H - 1);
@@ -106,7 +110,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
-  const bool col_wells = g.active && column_has_well_gc(P, g.col, HW);
+  // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
+  __shared__ __align__(8) G2Wells s_wt;
+  bool col_wells = false;
+  int wslot = 0;
+  if (P.n_wells > 0) {
+    bool over = false;
+    const bool any = s_wt.build(well_cols_of(P), P.W, P.D, g.tx0, g.ty0, nullptr, over);
+    if (over) col_wells = g.active && column_has_well_gc(P, g.col, HW);
+    else if (any && g.active) wslot = s_wt.slot_of[g.lt];
+  }
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
   const float idt = __fdiv_rn(1.0f, __fmul_rn(P.Dc, d1));
@@ -206,8 +219,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     }
     // wells in this cell (scatter_nd sums duplicates)
     float q4[4] = {0.f, 0.f, 0.f, 0.f}, mask = 0.f;
-    int wfirst = 0;
-    if (col_wells) {
+    int wfirst = 0, wlast = 0;
+    if (wslot) {
+      s_wt.take(wslot - 1, k, wfirst, wlast);
+      for (int e = wfirst; e < wlast; ++e) {
+        const int w = s_wt.w[e];
+#pragma unroll
+        for (int X = 0; X < 4; ++X) q4[X] = __fadd_rn(q4[X], A.W7[X * wt + (int64_t)b * P.n_wells + w]);
+        mask += 1.f;
+      }
+    } else if (col_wells) {
       wfirst = well_lower_bound(P, c);
       for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) {
 #pragma unroll
@@ -270,8 +291,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     if (g.active) {
       A.dom[base + c] = dom;
       if (A.dom_out) A.dom_out[base + c] = dom;
-      if (mask != 0.f)
-        for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq_tot;
+      if (mask != 0.f) {
+        if (wslot) { for (int e = wfirst; e < wlast; ++e) A.divqw[(int64_t)b * P.n_wells + s_wt.w[e]] = divq_tot; }
+        else { for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq_tot; }
+      }
       acc[0] += (double)dom * (double)dom;
       if (mask != 0.f) acc[1] += (double)ibc * (double)ibc;
       acc[2] += (double)trn * (double)trn;
@@ -334,7 +357,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const float* __restrict__ FN = FE + FL.nE;
   const float* __restrict__ FU = FN + FL.nN;
   int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
-  const bool col_wells = g.active && column_has_well_gc(P, g.col, HW);
+  // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
+  __shared__ __align__(8) G2Wells s_wt;
+  bool col_wells = false;
+  int wslot = 0;
+  if (P.n_wells > 0) {
+    bool over = false;
+    const bool any = s_wt.build(well_cols_of(P), P.W, P.D, g.tx0, g.ty0, nullptr, over);
+    if (over) col_wells = g.active && column_has_well_gc(P, g.col, HW);
+    else if (any && g.active) wslot = s_wt.slot_of[g.lt];
+  }
   const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_trn = A.dterms[SRM_TERM_CMBC];
   const float w2 = 2.f * w_dom;
   const float d1 = A.dt1[b], d2 = A.dt2[b];
@@ -477,7 +509,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     go1 -= smf * (r1 + b1);
     go0 += smf * (R0 + B0);
     // wells in this cell: sum of the four rates enters dom (+) and mbc (-)
-    if (col_wells) {
+    if (wslot) {
+      const int64_t wt = (int64_t)A.B * P.n_wells;
+      int first, last;
+      s_wt.take(wslot - 1, k, first, last);
+      for (int e = first; e < last; ++e) {
+        const int w = s_wt.w[e];
+        const float dqp = A.W7[4 * wt + (int64_t)b * P.n_wells + w], dqs = A.W7[5 * wt + (int64_t)b * P.n_wells + w];
+        g1 += (sc - smb) * dqp;
+        gs1 += (sc - smb) * dqs;
+      }
+    } else if (col_wells) {
       const int64_t wt = (int64_t)A.B * P.n_wells;
       const int first = well_lower_bound(P, c);
       for (int w = first; w < P.n_wells && P.wells[w].cell == c; ++w) {

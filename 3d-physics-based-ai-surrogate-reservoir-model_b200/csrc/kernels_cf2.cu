@@ -277,10 +277,12 @@ struct Cf2Dev {
   float dv, invDc, dvDc, Dc, K1, K2, dvSgi_phi;    // K1 = Sgi*phi, K2 = Sgi*phi*cf
   int32_t tde_in_dom, n_wells;
   const WellDev* wells;
+  const int32_t* layer_ptr;
   WellColsDev wc;
 };
 __device__ __forceinline__ int cf2_lower_bound(const Cf2Dev& P, int c) {
-  int lo = 0, hi = P.n_wells;
+  const int k = c / (P.H * P.W);
+  int lo = P.layer_ptr[k], hi = P.layer_ptr[k + 1];
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (P.wells[mid].cell < c) lo = mid + 1; else hi = mid;
@@ -947,7 +949,7 @@ Cf2Dev slim(const SrmDev& P) {
   d.D = P.D; d.H = P.H; d.W = P.W; d.N = P.N;
   d.dv = P.dv; d.invDc = P.invDc; d.dvDc = P.dvDc; d.Dc = P.Dc;
   d.K1 = P.Sgi * P.phi; d.K2 = P.Sgi * P.phicf; d.dvSgi_phi = P.dvSgi_phi;
-  d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells; d.wc = well_cols_of(P);
+  d.tde_in_dom = P.tde_in_dom; d.n_wells = P.n_wells; d.wells = P.wells; d.layer_ptr = P.layer_ptr; d.wc = well_cols_of(P);
   return d;
 }
 int lanes_for(int W) { const int l = W >= 24 * CPT ? 32 : (W >= 12 * CPT ? 16 : 8); return l > CF2_LXMAX ? CF2_LXMAX : l; }

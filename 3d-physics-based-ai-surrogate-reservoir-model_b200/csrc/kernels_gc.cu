@@ -20,6 +20,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "ref_fused.cuh"
+#include "well_tile.cuh"
 
 namespace {
 

@@ -40,6 +40,7 @@ struct SrmDev {
   const int32_t* col_rem;   // [n_cols]      j*W + i of the column, ascending
   const int32_t* col_ptr;   // [n_cols + 1]  range of the column in col_ent
   const int2* col_ent;      // [n_wells]     {layer k, position in the cell-sorted table}, sorted by (column, layer, position)
+  const int32_t* layer_ptr; // [D + 1]       range of layer k in the cell-sorted table (the searches that remain stay inside one layer)
   // spline
   int32_t n_knots, order, n_props;   // polynomial fit: n_knots = number of coefficients, w[q][i] = coefficient i
   int32_t pvt_method;                // SRM_PVT_*

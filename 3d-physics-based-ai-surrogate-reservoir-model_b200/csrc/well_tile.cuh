@@ -34,7 +34,7 @@ struct WellTile {
 
   // block-wide; returns true when the tile holds a connection.  `overflow` (block-uniform) says the lists did not fit.
   // Ends with a barrier: slot_of / lists are visible to every thread.
-  __device__ __forceinline__ bool build(const WellColsDev& C, int W, int D, int x0, int y0, const float* __restrict__ vals /* row of this sample */,
+  __device__ __forceinline__ bool build(const WellColsDev& C, int W, int D, int x0, int y0, const float* __restrict__ vals /* row of this sample, or null */,
                                         bool& overflow) {
     const int tid = threadIdx.x;
     for (int i = tid; i < TY * TW; i += NT) slot_of[i] = 0;
@@ -63,7 +63,7 @@ struct WellTile {
           const int2 e = C.col_ent[from + t];
           lay[b0 + t] = (uint16_t)e.x;
           w[b0 + t] = e.y;
-          val[b0 + t] = vals[e.y];
+          if (vals) val[b0 + t] = vals[e.y];
         }
       }
     }

@@ -79,6 +79,8 @@ CASES = [
     dict(seed=15, wells="none"),
     dict(seed=16, B=4, R=2),                              # two realisations
     dict(seed=17, small_dp=True, sg_lo=0.2, sg_hi=0.5),   # cells with |p1 - p0| << 1 psi and == 0
+    dict(seed=18, D=4, H=6, W=24, B=2, wells=("columns", 3), sg_lo=0.2, sg_hi=0.5),    # connections in every layer: the staged column lists (well_tile.cuh)
+    dict(seed=19, D=3, H=6, W=24, B=2, wells=("columns", 10), sg_lo=0.2, sg_hi=0.5),   # more well columns in a tile than the lists hold: search path
 ]
 
 
@@ -202,6 +204,7 @@ def test_cuda_gc_forward_equals_the_reference_fragment_bit_for_bit(case, pvt_lut
 
 
 @pytest.mark.parametrize("kw", [dict(seed=41, D=5, H=19, W=70, B=3, R=2, wells="dup", sg_lo=0.2, sg_hi=0.5),   # ragged tiles in x and y
+                                dict(seed=44, D=6, H=19, W=70, B=2, R=1, wells=("columns", 5), sg_lo=0.2, sg_hi=0.5),  # well columns through every layer
                                 dict(seed=42, D=2, H=8, W=32, B=2),                                              # exactly one tile
                                 dict(seed=43, D=1, H=17, W=33, B=2, wells="none")])
 def test_gc_fused_pair_equals_the_staged_pipeline(kw, monkeypatch):

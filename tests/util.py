@@ -109,6 +109,9 @@ def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, s
         wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=W - 2, j=H - 2, k=D - 1, value=1000.0)]
     elif wells == "dup":     # two connections in one cell + a neighbouring well cell
         wl = [dict(i=2, j=2, k=0, value=500.0), dict(i=2, j=2, k=0, value=300.0), dict(i=3, j=2, k=0, value=800.0)]
+    elif isinstance(wells, tuple) and wells[0] == "columns":     # n well columns side by side, completed in every layer, one duplicate
+        wl = [dict(i=1 + 2 * t, j=1, k=k, value=300.0 + 100.0 * (t % 3)) for t in range(wells[1]) for k in range(D)]
+        wl.append(dict(i=1, j=1, k=D - 1, value=250.0))
     else:
         wl = []
     ocfg = O.OracleConfig(D=D, H=H, W=W, wells=[O.Well(**w) for w in wl])

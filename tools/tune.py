@@ -14,12 +14,13 @@ import srm_b200 as srm  # noqa: E402
 name, numerics, K, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
 libs = sys.argv[5:]
 c, spec = bench.workload(name)
-if os.environ.get("TUNE_NOWELLS"):      # the same grid without connections: what the well code costs
+cones = [(w.i, w.j) for w in spec.wells[:8]]
+if os.environ.get("TUNE_NOWELLS"):      # the same grid and pressures without connections: what the well code costs
     import dataclasses
     spec = dataclasses.replace(spec, wells=[])
 gc = spec.fluid_type == "GC"
 tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.GC_PROPERTIES if gc else srm.pvt.DG_PROPERTIES, order=1)
-b = srm.synth.make_batch(spec.W, spec.H, spec.D, c["T"], K, [(w.i, w.j) for w in spec.wells[:8]], seed=2002, device="cuda")
+b = srm.synth.make_batch(spec.W, spec.H, spec.D, c["T"], K, cones, seed=2002, device="cuda")
 d = dict(kx=b.kx, sample_real=b.sample_real, p0=b.p0, p1=b.p1, dt1=b.dt1, dt2=b.dt2, t1=b.t1)
 if gc:
     d["sg0"], d["sg1"], d["so0"], d["so1"] = srm.synth.make_saturations(b, seed=2002)
