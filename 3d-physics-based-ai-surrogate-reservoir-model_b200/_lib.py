@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SRM_PHYSICS_LIB: kernel-tuning experiments load an alternative build of the same library
 LIB_PATH = os.environ.get("SRM_PHYSICS_LIB") or os.path.join(_HERE, "libsrm_physics.so")
 
-SRM_ABI_VERSION = 4
+SRM_ABI_VERSION = 5
 SRM_N_TERMS = 8
 TERM_NAMES = ("dom", "ibc", "mbc", "tde", "obc", "ic", "td", "cmbc")
 SRM_FLUID_DG, SRM_FLUID_GC = 0, 1
@@ -59,6 +59,7 @@ class SrmConfig(C.Structure):
         ("Swmin", C.c_float), ("Sorg", C.c_float), ("Sgc", C.c_float), ("Socr", C.c_float),
         ("kro_Somax", C.c_float), ("krg_Sorg", C.c_float), ("krg_Swmin", C.c_float), ("nog", C.c_float), ("ng", C.c_float),
         ("root_solver", C.c_int32), ("n_root_iter", C.c_int32),
+        ("bhp_iterative", C.c_int32), ("bhp_max_iters", C.c_int32), ("bhp_tol", C.c_float),
     ]
 
 
@@ -147,7 +148,8 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
                 numerics: int, tde_in_dom: bool, fluid_type: int = SRM_FLUID_DG, pvt_lut: bool = False,
                 lut_range: Optional[Sequence[float]] = None, end_points: Optional[dict] = None,
                 corey_exponents: Optional[dict] = None, pvt_method: int = SRM_PVT_SPLINE,
-                root_solver: str = "newton", n_root_iter: int = 20):
+                root_solver: str = "newton", n_root_iter: int = 20,
+                use_non_iterative: bool = True, bhp_max_iters: int = 10, bhp_tol: float = 1e-6):
     """Fill an SrmConfig; returns (cfg, keepalive) -- keepalive owns the host arrays cfg points into."""
     knots = np.ascontiguousarray(knots, dtype=np.float32)
     spline_w = np.ascontiguousarray(spline_w, dtype=np.float32)
@@ -168,7 +170,8 @@ def make_config(*, device: int, D: int, H: int, W: int, dx: float, dy: float, dz
         n_intervals=int(n_intervals), numerics=int(numerics), tde_in_dom=int(bool(tde_in_dom)),
         pvt_lut=int(bool(pvt_lut)), lut_p_lo=float(lut_range[0]) if lut_range else 0.0,
         lut_p_hi=float(lut_range[1]) if lut_range else 0.0,
-        root_solver=SRM_ROOT_NEWTON if str(root_solver).lower() == "newton" else SRM_ROOT_BRACKET, n_root_iter=int(n_root_iter))
+        root_solver=SRM_ROOT_NEWTON if str(root_solver).lower() == "newton" else SRM_ROOT_BRACKET, n_root_iter=int(n_root_iter),
+        bhp_iterative=int(not use_non_iterative), bhp_max_iters=int(bhp_max_iters), bhp_tol=float(bhp_tol))
     if end_points is not None:
         for k in ("Swmin", "Sorg", "Sgc", "Socr", "kro_Somax", "krg_Sorg", "krg_Swmin"):
             setattr(cfg, k, float(end_points[k]))

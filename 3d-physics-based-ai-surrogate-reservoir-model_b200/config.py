@@ -146,6 +146,9 @@ class PhysicsSpec:
     n_intervals: int = 8
     root_solver: str = "newton"           # well_rate_bhp_Subclassed.py:38 ('newton' | 'chandrupatla'), GC blocking integral
     n_root_iter: int = 20                 # well_rate_bhp_Subclassed.py:40
+    use_non_iterative: bool = True        # well_rate_bhp_Subclassed.py:44; False: Newton-Raphson on the BHP (_iterative_method, :515-612)
+    max_iters: int = 10                   # well_rate_bhp_Subclassed.py:41
+    tol: float = 1e-6                     # well_rate_bhp_Subclassed.py:42
     tde_in_dom: bool = True
     fluid_type: str = "DG"
     # time normalisation statistics (for normalize_diff of the predicted time step)

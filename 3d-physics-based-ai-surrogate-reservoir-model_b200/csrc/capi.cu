@@ -63,6 +63,10 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
       return SRM_ERR_INVALID;
     }
   }
+  if (cfg->bhp_iterative && (cfg->bhp_max_iters < 0 || cfg->bhp_max_iters > 1000 || !(cfg->bhp_tol >= 0.f))) {
+    srm_set_error("srm_create: iterative BHP control needs 0 <= bhp_max_iters <= 1000 and bhp_tol >= 0");
+    return SRM_ERR_INVALID;
+  }
   const bool poly = cfg->pvt_method == SRM_PVT_POLYNOMIAL;
   if (cfg->pvt_method != SRM_PVT_SPLINE && !poly) { srm_set_error("srm_create: unknown pvt_method %d", cfg->pvt_method); return SRM_ERR_INVALID; }
   if (cfg->n_knots < (poly ? 1 : 2) || cfg->n_knots > SRM_MAXK || cfg->n_props < 2 || cfg->n_props > SRM_MAXP || !cfg->spline_w ||
@@ -128,6 +132,7 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
   P.tde_in_dom = cfg->tde_in_dom;
   P.use_blk = cfg->use_blocking_factor; P.n_int = cfg->n_intervals;
   P.root_solver = cfg->root_solver; P.n_root_iter = cfg->n_root_iter;
+  P.bhp_iterative = cfg->bhp_iterative ? 1 : 0; P.bhp_max_iters = cfg->bhp_max_iters; P.bhp_tol = cfg->bhp_tol;
   P.n_knots = cfg->n_knots; P.order = cfg->spline_order; P.n_props = cfg->n_props;
   // SCAL: constants formed in fp32 like relative_permeability.py:58-68
   P.fluid = cfg->fluid_type;

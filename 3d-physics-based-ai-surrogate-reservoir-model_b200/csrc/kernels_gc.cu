@@ -391,24 +391,42 @@ __global__ void __launch_bounds__(128) k_wells_gc(const __grid_constant__ SrmDev
   const D2 mog = krgo * invBg * invug * Rv;
   const D2 mg = mgg + mgo, mo = moo + mog;
   const D2 p = mk(pv, 1.f, 0.f), pmin = mk(wd.pwf_min), qt = mk(wd.q_target), zero = mk(0.f), one = mk(1.f), tiny = mk(1e-12f);
-  // ---- _non_iterative_method (:614-724); without the blocking factor Ig = Io = 1 (:955-959)
-  D2 ig_max = one, io_max = one;
-  if (P.use_blk) blocking_integral_gc(P, p, pmin, ko, mg, mo, ig_max, io_max);
-  const D2 dp_max = (p - pmin) + tiny;                                           // :650
-  const D2 blk_max = P.use_blk ? dnn2(ig_max, mg * dp_max) : ig_max;             // :654-657
-  const D2 qg_max = Ck * blk_max * mg * dp_max;                                  // :662
-  const D2 qg_opt = max2(min2(qt, qg_max), zero);                                // :666
-  const D2 lam = clip2(dnn2(qg_opt, Ck * blk_max * mg), zero, blk_max);          // :699
-  const D2 pwf = clip2(p - lam * dp_max, pmin, p);                               // :721-723
-  // ---- _compute_phase_rates (:963-1007)
-  D2 ig = one, io = one;
-  if (P.use_blk) blocking_integral_gc(P, p, pwf, ko, mg, mo, ig, io);
-  const D2 dp = (p - pwf) + tiny;                                                // :987
-  const D2 blk_g = P.use_blk ? dnn2(ig, mg * dp) : ig;                           // :990-995
-  const D2 blk_o = P.use_blk ? dnn2(io, mo * dp) : io;
-  const D2 qg = max2(min2(qt, Ck * blk_g * mg * dp), zero);                      // :997,1001
-  const D2 qo_target = qg * (one / (Rv + tiny));                                 // :1004
-  const D2 qo = max2(min2(qo_target, Ck * blk_o * mo * dp), zero);               // :998,1005
+  // _compute_phase_rates (:963-1007); without the blocking factor Ig = Io = 1 (:955-959)
+  auto phase_rates = [&](D2 pwf_, D2& qg_, D2& qo_) {
+    D2 ig = one, io = one;
+    if (P.use_blk) blocking_integral_gc(P, p, pwf_, ko, mg, mo, ig, io);
+    const D2 dp = (p - pwf_) + tiny;                                             // :987
+    const D2 blk_g = P.use_blk ? dnn2(ig, mg * dp) : ig;                         // :990-995
+    const D2 blk_o = P.use_blk ? dnn2(io, mo * dp) : io;
+    qg_ = max2(min2(qt, Ck * blk_g * mg * dp), zero);                            // :997,1001
+    const D2 qo_target = qg_ * (one / (Rv + tiny));                              // :1004
+    qo_ = max2(min2(qo_target, Ck * blk_o * mo * dp), zero);                     // :998,1005
+  };
+  D2 pwf, qg, qo;
+  if (!P.bhp_iterative) {
+    // ---- _non_iterative_method (:614-724)
+    D2 ig_max = one, io_max = one;
+    if (P.use_blk) blocking_integral_gc(P, p, pmin, ko, mg, mo, ig_max, io_max);
+    const D2 dp_max = (p - pmin) + tiny;                                         // :650
+    const D2 blk_max = P.use_blk ? dnn2(ig_max, mg * dp_max) : ig_max;           // :654-657
+    const D2 qg_max = Ck * blk_max * mg * dp_max;                                // :662
+    const D2 qg_opt = max2(min2(qt, qg_max), zero);                              // :666
+    const D2 lam = clip2(dnn2(qg_opt, Ck * blk_max * mg), zero, blk_max);        // :699
+    pwf = clip2(p - lam * dp_max, pmin, p);                                      // :721-723
+  } else {
+    // ---- _iterative_method (:515-612): see wells.cuh for the stopping rule
+    const D2 eps = mk(14.7f);
+    pwf = pmin + mk(0.5f) * (p - pmin);                                          // :537
+    for (int it = 0; it < P.bhp_max_iters; ++it) {
+      D2 qg_it, qo_it, qg_plus, qo_plus;
+      phase_rates(pwf, qg_it, qo_it);                                            // :566-569
+      if (!(fabsf(__fsub_rn(qg_it.v, qt.v)) > P.bhp_tol)) break;
+      phase_rates(pwf + eps, qg_plus, qo_plus);                                  // :571-574
+      const D2 dq = (qg_plus - qg_it) / eps;                                     // :576
+      pwf = clip2(pwf - (qg_it - qt) / (dq + tiny), pmin, p);                    // :584-586
+    }
+  }
+  phase_rates(pwf, qg, qo);
   // ---- _split_condensate_components (:1010-1034)
   const D2 dg = (mgg + mgo) + tiny, dn = (moo + mog) + tiny;
   const D2 qgg = qg * (mgg / dg), qgo = qg * (mgo / dg), qoo = qo * (moo / dn), qog = qo * (mog / dn);

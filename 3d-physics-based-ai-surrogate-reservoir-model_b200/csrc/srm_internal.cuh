@@ -32,6 +32,8 @@ struct SrmDev {
   int32_t tde_in_dom;
   int32_t use_blk, n_int;
   int32_t root_solver, n_root_iter;   // GC blocking-factor integral: SRM_ROOT_*, iterations per trapezoid node
+  int32_t bhp_iterative, bhp_max_iters;   // _iterative_method instead of _non_iterative_method (well_rate_bhp_Subclassed.py:813-822)
+  float bhp_tol;
   int32_t n_wells;
   const WellDev* wells;  // device, sorted by cell
   // the same connections grouped by (j, i) column, layers ascending inside a column (well_tile.cuh): what a z-marching

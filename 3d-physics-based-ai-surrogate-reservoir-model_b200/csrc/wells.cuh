@@ -78,24 +78,46 @@ __global__ void __launch_bounds__(128) k_wells(const __grid_constant__ SrmDev P,
   const Dual Ck = dmk(__fmul_rn(open, ck));
   const Dual mg = mob(P, p);
   const Dual pmin = dmk(wd.pwf_min), qt = dmk(wd.q_target), zero = dmk(0.f), tiny = dmk(1e-12f);
-  // ---- _non_iterative_method                                 :614-724
-  Dual ig_max = dmk(1.f);
-  if (P.use_blk) ig_max = blocking_integral(P, mob, p, pmin, mg);
-  const Dual dp_max = (p - pmin) + tiny;                                       // :650
-  const Dual blk_max = P.use_blk ? ddnn(ig_max, mg * dp_max) : ig_max;         // :654-657
-  const Dual ckb = Ck * blk_max;                                               // well_id == 1
-  const Dual qg_max = ckb * mg * dp_max;                                       // :662
-  const Dual qg_opt = dmax(dmin(qt, qg_max), zero);                            // :666
-  const Dual lam = dclip(ddnn(qg_opt, ckb * mg), zero, blk_max);               // :699
-  const Dual dp_opt = lam * dp_max;                                            // :721
-  const Dual pwf = dclip(p - dp_opt, pmin, p);                                 // :723
-  // ---- _compute_phase_rates                                  :963-1007
-  Dual ig = dmk(1.f);
-  if (P.use_blk) ig = blocking_integral(P, mob, p, pwf, mg);
-  const Dual dp = (p - pwf) + tiny;                                            // :987
-  const Dual blk = P.use_blk ? ddnn(ig, mg * dp) : ig;                         // :991
-  const Dual qg_max2 = Ck * blk * mg * dp;                                     // :997
-  const Dual qg = dmax(dmin(qt, qg_max2), zero);                               // :1001
+  // _compute_phase_rates                                       :963-1007
+  auto phase_rates = [&](Dual pwf_) {
+    Dual ig = dmk(1.f);
+    if (P.use_blk) ig = blocking_integral(P, mob, p, pwf_, mg);
+    const Dual dp = (p - pwf_) + tiny;                                         // :987
+    const Dual blk = P.use_blk ? ddnn(ig, mg * dp) : ig;                       // :991
+    const Dual qg_max2 = Ck * blk * mg * dp;                                   // :997
+    return dmax(dmin(qt, qg_max2), zero);                                      // :1001
+  };
+  Dual pwf;
+  if (!P.bhp_iterative) {
+    // ---- _non_iterative_method                               :614-724
+    Dual ig_max = dmk(1.f);
+    if (P.use_blk) ig_max = blocking_integral(P, mob, p, pmin, mg);
+    const Dual dp_max = (p - pmin) + tiny;                                     // :650
+    const Dual blk_max = P.use_blk ? ddnn(ig_max, mg * dp_max) : ig_max;       // :654-657
+    const Dual ckb = Ck * blk_max;                                             // well_id == 1
+    const Dual qg_max = ckb * mg * dp_max;                                     // :662
+    const Dual qg_opt = dmax(dmin(qt, qg_max), zero);                          // :666
+    const Dual lam = dclip(ddnn(qg_opt, ckb * mg), zero, blk_max);             // :699
+    const Dual dp_opt = lam * dp_max;                                          // :721
+    pwf = dclip(p - dp_opt, pmin, p);                                          // :723
+  } else {
+    // ---- _iterative_method                                   :515-612
+    // Newton-Raphson on the bottom-hole pressure, d/dp carried through every step (tf.while_loop's gradient).  The
+    // reference iterates the whole batch while ANY connection misses its target; a connection with |qg - q_target| <= tol
+    // has qg == q_target (the minimum picked the target: zero gradient), so its step is the identity in value and
+    // derivative -- stopping it on its own error gives the same numbers.
+    const Dual eps = dmk(14.7f);                                               // :540
+    pwf = pmin + dmk(0.5f) * (p - pmin);                                       // :537
+    for (int it = 0; it < P.bhp_max_iters; ++it) {
+      const Dual qg_it = phase_rates(pwf);                                     // :566-569 (and the cond's evaluation, :549-553)
+      if (!(fabsf(__fsub_rn(qg_it.v, qt.v)) > P.bhp_tol)) break;
+      const Dual qg_plus = phase_rates(pwf + eps);                             // :571-574
+      const Dual dq = (qg_plus - qg_it) / eps;                                 // :576
+      const Dual pwf_new = pwf - (qg_it - qt) / (dq + tiny);                   // :584
+      pwf = dclip(pwf_new, pmin, p);                                           // :586
+    }
+  }
+  const Dual qg = phase_rates(pwf);
   qw[g] = qg.v;
   pwfw[g] = pwf.v;
   dqdp[g] = qg.d;

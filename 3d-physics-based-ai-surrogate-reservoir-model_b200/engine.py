@@ -49,7 +49,8 @@ class SrmPhysics:
             numerics=NUMERICS[numerics], tde_in_dom=spec.tde_in_dom, pvt_lut=pvt_lut, lut_range=lut_range,
             fluid_type=L.SRM_FLUID_GC if spec.fluid_type == "GC" else L.SRM_FLUID_DG,
             end_points=spec.end_points, corey_exponents=spec.corey_exponents,
-            root_solver=spec.root_solver, n_root_iter=spec.n_root_iter)
+            root_solver=spec.root_solver, n_root_iter=spec.n_root_iter,
+            use_non_iterative=spec.use_non_iterative, bhp_max_iters=spec.max_iters, bhp_tol=spec.tol)
         self.pvt_lut = bool(pvt_lut) and numerics == "reference"
         h = C.c_void_p()
         L.check(self.lib, self.lib.srm_create(C.byref(cfg), C.byref(h)), "srm_create")

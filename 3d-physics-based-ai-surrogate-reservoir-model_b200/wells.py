@@ -75,15 +75,16 @@ class WellRatesPressure:
                  general_config=None, kx_stats=(0.26, 24.0), t_range=(0.0, 365.0), norm_limits=(-1.0, 1.0)):
         if fluid_type.upper() != engine.fluid:
             raise ValueError(f"fluid_type {fluid_type!r} does not match the engine ({engine.fluid})")
-        if not use_non_iterative:
-            raise NotImplementedError("only the non-iterative BHP control (the reference default) is built")
         spec: PhysicsSpec = engine.spec
+        if bool(use_non_iterative) != bool(spec.use_non_iterative):      # the control method is fixed when the handle is made
+            raise ValueError("use_non_iterative must match the engine's PhysicsSpec (well_rate_bhp_Subclassed.py:44, 813-822)")
         if use_blocking_factor is not None and bool(use_blocking_factor) != bool(spec.use_blocking_factor):
             raise ValueError("use_blocking_factor must match the engine's PhysicsSpec")
         self.engine = engine
         self.fluid_type = engine.fluid
         self.use_blocking_factor = spec.use_blocking_factor
         self.n_intervals = spec.n_intervals
+        self.use_non_iterative, self.max_iters, self.tol = spec.use_non_iterative, spec.max_iters, spec.tol
         self.k_min, self.k_max = kx_stats
         self.t_min, self.t_max = t_range
         self.lo, self.hi = norm_limits

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SRM_ABI_VERSION 4
+#define SRM_ABI_VERSION 5
 
 typedef enum SrmStatus {
   SRM_OK = 0,
@@ -130,6 +130,15 @@ typedef struct SrmConfig {
    * SRM_ROOT_NEWTON = _solve_newton (start 0.1, clip to [0, 1 - Swmin]), SRM_ROOT_BRACKET = _solve_chandrupatla
    * (regula-falsi bracket update, tol 1e-6); n_root_iter iterations per trapezoid node (reference default 20) */
   int32_t root_solver, n_root_iter;
+  /* bottom-hole-pressure control (well_rate_bhp_Subclassed.py:41-44, 813-822): bhp_iterative = 0 is the reference's
+   * default, _non_iterative_method (:614-724); 1 selects _iterative_method (:515-612) -- Newton-Raphson on the
+   * bottom-hole pressure from min_bhp + (p - min_bhp)/2, one-sided difference quotient with eps = 14.7 psi, clip into
+   * [min_bhp, p] after every step, at most bhp_max_iters steps (reference default 10) while |qg - q_target| > bhp_tol
+   * (default 1e-6).  The reference stops the WHOLE batch together; every connection that has met its target is a fixed
+   * point of the step (value and gradient), so the kernels iterate per connection.  d rate / d p (and d / d Sg) is carried
+   * through every iteration, as tf.while_loop's gradient does. */
+  int32_t bhp_iterative, bhp_max_iters;
+  float bhp_tol;
 } SrmConfig;
 
 typedef struct SrmHandle SrmHandle;
@@ -165,7 +174,7 @@ int srm_denormalize_log(int32_t device, int64_t n, const float* x_norm, float km
 int srm_selftest_rounding(int32_t device, int64_t n, uint64_t seed, int64_t* mismatches, void* stream);
 
 /* WellRatesPressure.compute_rates_and_bhp (well_rate_bhp_Subclassed.py:727-837) incl.
- * _non_iterative_method (:614-724), _compute_phase_rates (:963-1007),
+ * _non_iterative_method (:614-724) or _iterative_method (:515-612, SrmConfig.bhp_iterative), _compute_phase_rates (:963-1007),
  * compute_blocking_integral_and_factor (:840-960), and the integer bookkeeping of
  * WellDataProcessor.scatter_y / conn_shutins_idx (welldata_processor.py:170-224,228-389),
  * evaluated sparsely at the connection cells.
@@ -210,9 +219,9 @@ int srm_relperm(const SrmHandle* h, int64_t n, const float* sg, float* krog, flo
  * created with fluid_type = SRM_FLUID_GC (n_props = 7: InvBg, InvBo, Invug, Invuo, Rs, Rv, Vro;
  * PVT_Layer_Subclassed.py:71-72).  Inputs are the networks' outputs at both time levels: pressure, gas
  * and oil saturation (physics_loss.py:330-332,372-374).  Well rates come from the GC branch of
- * WellRatesPressure (non-iterative control, _split_condensate_components;
- * well_rate_bhp_Subclassed.py:614-724,963-1034); the GC blocking-factor integral is not built (the handle
- * refuses use_blocking_factor with SRM_FLUID_GC).
+ * WellRatesPressure (non-iterative or iterative control, _split_condensate_components;
+ * well_rate_bhp_Subclassed.py:515-724,963-1034), with use_blocking_factor the blocking-factor integral and its root
+ * finders (:857-950, 236-324; SrmConfig.root_solver, n_root_iter).
  *   terms_out [2][SRM_N_TERMS]: slots DOM, IBC, MBC and CMBC (= the truncation term, physics_loss.py:680)
  *   q4w_out   [4][B][n_wells]: qgg, qgo, qoo, qog per connection (nullable);  pwfw_out [B][n_wells] */
 int srm_forward_gc(SrmHandle* h, int32_t B, int32_t R, const float* kx, const int32_t* sample_real,

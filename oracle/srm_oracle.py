@@ -125,6 +125,9 @@ class OracleConfig:
     wells: List[Well] = field(default_factory=list)
     use_blocking_factor: bool = False     # well_rate_bhp_Subclassed.py:36
     n_intervals: int = 8                  # well_rate_bhp_Subclassed.py:39
+    use_non_iterative: bool = True        # well_rate_bhp_Subclassed.py:44: False -> _iterative_method (:515-612)
+    bhp_max_iters: int = 10               # well_rate_bhp_Subclassed.py:41
+    bhp_tol: float = 1e-6                 # well_rate_bhp_Subclassed.py:42
     tde_in_dom: bool = True               # legacy DG folds trn_err into dom (physics_loss.py:175)
 
     @property
@@ -548,6 +551,28 @@ def blocking_integral_dg(p, pwf, tab, cfg, krg_p, krg_smax, n_intervals):
     return sum_g, mg_n1
 
 
+def bhp_newton(gas_rate, p, pmin, q_t, cfg: OracleConfig):
+    """WellRatesPressure._iterative_method (well_rate_bhp_Subclassed.py:515-612): Newton-Raphson on the bottom-hole
+    pressure with a one-sided difference quotient (eps = 14.7 psi) for d qg / d pwf, clipped into [min_bhp, p] after
+    every step.  The stopping test is the reference's: the WHOLE batch iterates while any connection misses its target
+    by more than tol, at most max_iters times (tf.while_loop's cond, :548-562); the loop is differentiated through, as
+    tf.while_loop's gradient does.  gas_rate(pwf) is _compute_phase_rates' qg."""
+    pwf = pmin + 0.5 * (p - pmin)                                                # :537
+    eps = 14.7                                                                   # :540
+    it = 0
+    while it < cfg.bhp_max_iters:
+        qg = gas_rate(pwf)                                                       # :566-569 (the cond evaluates the same rate, :549-553)
+        err = (qg - q_t).abs().detach()                                          # cond: evaluated, not differentiated
+        if not bool((err > cfg.bhp_tol).any()):
+            break
+        qg_plus = gas_rate(pwf + eps)                                            # :571-574
+        dq = (qg_plus - qg) / eps                                                # :576
+        pwf_new = pwf - (qg - q_t) / (dq + 1e-12)                                # :584
+        pwf = _tf_clip(pwf_new, pmin, p)                                         # :586
+        it += 1
+    return pwf
+
+
 def wells_dg(p_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConfig, dtype):
     """WellRatesPressure.compute_rates_and_bhp, DG, non-iterative control
     (well_rate_bhp_Subclassed.py:727-837, 614-724, 963-1007), evaluated at the connection cells only.
@@ -579,28 +604,33 @@ def wells_dg(p_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConfig, dtype
             return ig
         return torch.ones_like(p)                                                # :955-959
 
-    # ---- _non_iterative_method (:614-724)
-    ig_max = integral(pmin.expand_as(p))
-    dp_max = p - pmin + tiny                                                     # :650
-    if cfg.use_blocking_factor:
-        blk_max = _dnn(ig_max, mg * dp_max)                                      # :654
+    def phase_rates(pwf_):                                                       # _compute_phase_rates (:963-1007)
+        ig = integral(pwf_)
+        dp = p - pwf_ + tiny                                                     # :987
+        if cfg.use_blocking_factor:
+            blk = _dnn(ig, mg * dp)                                              # :991
+        else:
+            blk = ig
+        qg_max2 = well_id * ck * blk * mg * dp                                   # :997
+        return _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), torch.zeros_like(p))  # :1001
+
+    if cfg.use_non_iterative:
+        # ---- _non_iterative_method (:614-724)
+        ig_max = integral(pmin.expand_as(p))
+        dp_max = p - pmin + tiny                                                 # :650
+        if cfg.use_blocking_factor:
+            blk_max = _dnn(ig_max, mg * dp_max)                                  # :654
+        else:
+            blk_max = ig_max                                                     # :657
+        qg_max = well_id * ck * blk_max * mg * dp_max                            # :662
+        qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), torch.zeros_like(p))   # :666
+        lam = _tf_clip(_dnn(qg_opt, well_id * ck * blk_max * mg), torch.zeros_like(p), blk_max)  # :699
+        dp_opt = lam * dp_max                                                    # :721
+        pwf = p - dp_opt
+        pwf = well_id * _tf_clip(pwf, pmin.expand_as(p), p)                      # :723
     else:
-        blk_max = ig_max                                                         # :657
-    qg_max = well_id * ck * blk_max * mg * dp_max                                # :662
-    qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), torch.zeros_like(p))   # :666
-    lam = _tf_clip(_dnn(qg_opt, well_id * ck * blk_max * mg), torch.zeros_like(p), blk_max)  # :699
-    dp_opt = lam * dp_max                                                        # :721
-    pwf = p - dp_opt
-    pwf = well_id * _tf_clip(pwf, pmin.expand_as(p), p)                          # :723
-    # ---- _compute_phase_rates (:963-1007)
-    ig = integral(pwf)
-    dp = p - pwf + tiny                                                          # :987
-    if cfg.use_blocking_factor:
-        blk = _dnn(ig, mg * dp)                                                  # :991
-    else:
-        blk = ig
-    qg_max2 = well_id * ck * blk * mg * dp                                       # :997
-    qg = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), torch.zeros_like(p))  # :1001
+        pwf = bhp_newton(phase_rates, p, pmin.expand_as(p), q_t.expand_as(p), cfg)
+    qg = phase_rates(pwf)
     return qg, pwf
 
 
@@ -904,24 +934,29 @@ def wells_gc(p_cell, sg_cell, kx_cell, t_days, tab: SplineTable, cfg: OracleConf
         if blk:
             return blocking_integral_gc(p, sg_cell, pwf_, tab, cfg, krog, mg, mo, dt, solver=solver)
         return one, one                                                          # :955-959
-    # ---- _non_iterative_method (:614-724)
-    ig_max, _io_max = integrals(pmin.expand_as(p))
-    dp_max = p - pmin + tiny                                                     # :650
-    blk_g_max = _dnn(ig_max, mg * dp_max) if blk else ig_max                     # :654-657
-    qg_max = ck * blk_g_max * mg * dp_max                                        # :662 (well_id == 1)
-    qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), zero)            # :666
-    lam = _tf_clip(_dnn(qg_opt, ck * blk_g_max * mg), zero, blk_g_max)           # :699
-    pwf = _tf_clip(p - lam * dp_max, pmin.expand_as(p), p)                       # :721-723
-    # ---- _compute_phase_rates (:963-1007)
-    ig, io = integrals(pwf)
-    dp = p - pwf + tiny                                                          # :987
-    blk_g = _dnn(ig, mg * dp) if blk else ig                                     # :990-995
-    blk_o = _dnn(io, mo * dp) if blk else io
-    qg_max2 = ck * blk_g * mg * dp                                               # :997
-    qo_max2 = ck * blk_o * mo * dp                                               # :998
-    qg = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), zero)               # :1001
-    qo_target = qg * (1.0 / (Rv + tiny))                                         # :1004
-    qo = _tf_maximum(_tf_minimum(qo_target, qo_max2), zero)                      # :1005
+    def phase_rates(pwf_):                                                       # _compute_phase_rates (:963-1007)
+        ig, io = integrals(pwf_)
+        dp = p - pwf_ + tiny                                                     # :987
+        blk_g = _dnn(ig, mg * dp) if blk else ig                                 # :990-995
+        blk_o = _dnn(io, mo * dp) if blk else io
+        qg_max2 = ck * blk_g * mg * dp                                           # :997
+        qo_max2 = ck * blk_o * mo * dp                                           # :998
+        qg_ = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max2), zero)          # :1001
+        qo_target = qg_ * (1.0 / (Rv + tiny))                                    # :1004
+        return qg_, _tf_maximum(_tf_minimum(qo_target, qo_max2), zero)           # :1005
+
+    if cfg.use_non_iterative:
+        # ---- _non_iterative_method (:614-724)
+        ig_max, _io_max = integrals(pmin.expand_as(p))
+        dp_max = p - pmin + tiny                                                 # :650
+        blk_g_max = _dnn(ig_max, mg * dp_max) if blk else ig_max                 # :654-657
+        qg_max = ck * blk_g_max * mg * dp_max                                    # :662 (well_id == 1)
+        qg_opt = _tf_maximum(_tf_minimum(q_t.expand_as(p), qg_max), zero)        # :666
+        lam = _tf_clip(_dnn(qg_opt, ck * blk_g_max * mg), zero, blk_g_max)       # :699
+        pwf = _tf_clip(p - lam * dp_max, pmin.expand_as(p), p)                   # :721-723
+    else:
+        pwf = bhp_newton(lambda pw: phase_rates(pw)[0], p, pmin.expand_as(p), q_t.expand_as(p), cfg)
+    qg, qo = phase_rates(pwf)
     # ---- _split_condensate_components (:1010-1034)
     denom_g = mgg + mgo + tiny
     denom_o = moo + mog + tiny

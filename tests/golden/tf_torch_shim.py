@@ -424,6 +424,18 @@ debugging = types.SimpleNamespace(assert_shapes=lambda *a, **k: None, assert_equ
 bool = torch.bool
 
 
+def reduce_max(x, axis=None, keepdims=False):
+    x = _t(x)
+    return x.max() if axis is None else x.amax(dim=axis, keepdim=keepdims)
+
+
+def abs(x):                # noqa: A001
+    return torch.abs(_t(x))
+
+
+strings = types.SimpleNamespace(format=lambda template, inputs=(), **k: str(template))      # log lines: never compared
+
+
 def while_loop(cond, body, loop_vars, shape_invariants=None, **k):
     v = list(loop_vars)
     while _b.bool(cond(*v)):

@@ -411,6 +411,36 @@ def test_cuda_gc_wells_against_the_reference_class(name, blocking, solver):
     eng.close()
 
 
+@pytest.mark.parametrize("name,blocking", [("gc", False), ("gcblk", True)])
+def test_cuda_gc_iterative_bhp_control_against_the_reference_class(name, blocking):
+    """Two-phase branch of WellRatesPressure._iterative_method (well_rate_bhp_Subclassed.py:515-612; with the blocking
+    factor every Newton step on the BHP evaluates the trapezoid integral and its root finds twice) against the reference's
+    own loop (tests/golden/reference_wells_iter.npz): component rates 2e-5, BHP 1e-5, zeros exact."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells_iter.npz"))
+    D, H, W, B = (int(g[f"{name}_{k}"]) for k in ("D", "H", "W", "B"))
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[float(r[4]), float(r[5])]]) for r in g[f"{name}_wells"]]
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), use_blocking_factor=blocking, n_intervals=8,
+                           fluid_type="GC", root_solver="newton", n_root_iter=20, use_non_iterative=False,
+                           max_iters=int(g[f"{name}_max_iters"]))
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
+    ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
+    eng = srm.SrmPhysics(spec, ptab)
+    dev = eng.device
+    tt = lambda k: torch.from_numpy(g[f"{name}_{k}"]).to(dev).contiguous()
+    q4, pwf = eng.wells_gc(tt("kx"), torch.arange(B, dtype=torch.int32, device=dev), tt("p"), tt("sg"), tt("t_days"))
+    torch.cuda.synchronize()
+    rq, rp = g[f"{name}_q4"], g[f"{name}_pwf"]
+    cells = [(w.k * H + w.j) * W + w.i for w in spec.wells]
+    assert np.allclose(pwf.cpu().numpy().reshape(B, -1)[:, cells], rp.reshape(B, -1)[:, cells], rtol=RTOL, atol=0)
+    for c in range(4):
+        q = q4[c].cpu().numpy()
+        assert np.array_equal(q == 0, rq[c] == 0), c
+        assert np.allclose(q, rq[c], rtol=2e-5, atol=0), (c, np.abs(q - rq[c]).max() / np.abs(rq[c]).max())
+    eng.close()
+
+
 def test_gc_order_2_spline_on_the_fused_table_path():
     """The reference's DEFAULT spline order is 2 (default_configurations.py:235; the example overrides to 1).  The exact
     table tabulates whatever the per-cell code computes, so the fused pair takes order 2 as it takes order 1: its residual

@@ -417,6 +417,57 @@ def test_cuda_wells_against_the_reference_class(name, blocking):
     eng.close()
 
 
+@pytest.mark.parametrize("name,blocking", [("dg", False), ("dgblk", True)])
+def test_cuda_iterative_bhp_control_against_the_reference_class(name, blocking):
+    """SrmConfig.bhp_iterative (PhysicsSpec(use_non_iterative=False)): WellRatesPressure._iterative_method
+    (well_rate_bhp_Subclassed.py:515-612), the reference's own loop executed through the TF stand-in
+    (tests/golden/reference_wells_iter.npz).  Rates and BHP 1e-5, cells and zeros exact; d rate / d p carried through
+    the Newton iterations against the gradient of the reference graph through its tf.while_loop."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells_iter.npz"))
+    D, H, W, B = (int(g[f"{name}_{k}"]) for k in ("D", "H", "W", "B"))
+    conns = [dict(i=int(r[0]), j=int(r[1]), k=int(r[2]), type="producer", control="ORAT", value=float(r[3]), minimum_bhp=4100.0,
+                  wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[float(r[4]), float(r[5])]]) for r in g[f"{name}_wells"]]
+    spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), use_blocking_factor=blocking, n_intervals=8,
+                           use_non_iterative=False, max_iters=int(g[f"{name}_max_iters"]), tol=1e-6)
+    tabs = srm.build_spline_tables(srm.load_default_pvt_table(), srm.pvt.DG_PROPERTIES)
+    eng = srm.SrmPhysics(spec, tabs)
+    dev = eng.device
+    out = eng.wells(torch.from_numpy(g[f"{name}_kx"]).to(dev), torch.arange(B, dtype=torch.int32, device=dev),
+                    torch.from_numpy(g[f"{name}_p"]).to(dev), torch.from_numpy(g[f"{name}_t_days"]).to(dev), dense=True)
+    torch.cuda.synchronize()
+    q, pwf = out["q"].cpu().numpy(), out["pwf"].cpu().numpy()
+    rq, rp = g[f"{name}_q"], g[f"{name}_pwf"]
+    assert np.array_equal(q == 0, rq == 0)
+    assert np.allclose(q, rq, rtol=RTOL, atol=0)
+    cells = [(w.k * H + w.j) * W + w.i for w in spec.wells]
+    assert np.allclose(pwf.reshape(B, -1)[:, cells], rp.reshape(B, -1)[:, cells], rtol=RTOL, atol=0)
+    ref_g = g[f"{name}_dq_dp"].reshape(B, -1)[:, cells]
+    # per-connection tables come back in the handle's cell-sorted order: compare as multisets per sample
+    got = np.sort(out["dqdp"].cpu().numpy(), axis=1)
+    assert np.abs(got - np.sort(ref_g, axis=1)).max() <= 2e-5 * np.abs(ref_g).max()
+    assert np.abs(ref_g).max() > 0
+    eng.close()
+
+
+def test_residual_and_adjoint_with_iterative_bhp_control():
+    """the whole path with PhysicsSpec(use_non_iterative=False): the rates of the Newton loop enter the residual and
+    d rate / d p through the loop enters the adjoint (oracle: torch autograd through its batch-coupled loop)."""
+    import dataclasses
+    ocfg, otab, spec, ptab, batch = U.make_case(W=12, H=9, D=2, T=2, K=2, seed=2101, all_layers=True, use_blocking_factor=True)
+    ocfg.use_non_iterative = False
+    spec = dataclasses.replace(spec, use_non_iterative=False)
+    o = U.oracle_run(ocfg, otab, batch)
+    c = U.cuda_run(spec, ptab, batch, pvt_lut=True, want_dom=True)
+    assert U.rel_to_max(c["dom"], o["dom"]) <= 1e-6
+    assert np.allclose(c["qw"], o["qw"], rtol=RTOL) and np.allclose(c["pwfw"], o["pwfw"], rtol=RTOL)
+    assert np.allclose(c["terms"], o["terms"], rtol=RTOL, atol=0)
+    for k in ("gp0", "gp1", "gdt1"):
+        assert h3_close(c[k], o[k]), (k, U.rel_to_max(c[k], o[k]))
+    # the loop changes the answer: the non-iterative control gives other BHPs on the same inputs
+    c0 = U.cuda_run(dataclasses.replace(spec, use_non_iterative=True), ptab, batch, pvt_lut=True)
+    assert not np.allclose(c0["pwfw"], c["pwfw"], rtol=1e-4)
+
+
 @pytest.mark.parametrize("pvt_lut", LUT_MODES)
 def test_cuda_terms_and_counts_against_the_reference_pinn_batch_sse_grad(pvt_lut):
     """srm_forward's SSE terms and error counts against the reference's OWN pinn_batch_sse_grad (executed with its own

@@ -323,6 +323,45 @@ def _wells_ref_case(g, name, blocking):
     return O.OracleConfig(D=D, H=H, W=W, wells=wl, use_blocking_factor=blocking, n_intervals=8), wl
 
 
+@pytest.mark.parametrize("name,fluid,blocking", [("dg", "DG", False), ("dgblk", "DG", True), ("gc", "GC", False), ("gcblk", "GC", True)])
+def test_oracle_iterative_bhp_control_equals_the_reference_class(name, fluid, blocking):
+    """PIN: WellRatesPressure._iterative_method (use_non_iterative=False, well_rate_bhp_Subclassed.py:515-612) executed
+    from the reference's own source through the TF stand-in (tests/golden/reference_wells_iter.npz): Newton-Raphson on the
+    bottom-hole pressure inside tf.while_loop, batch-coupled stopping test.  The oracle's rates and BHP equal the
+    reference's bit for bit; the gradient of the summed rates THROUGH the loop (w.r.t. pressure, and gas saturation for the
+    two-phase branch) agrees with the reference graph's to 1e-5 of its maximum."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_wells_iter.npz"))
+    cfg, wl = _wells_ref_case(g, name, blocking)
+    cfg.use_non_iterative = False
+    cols = O.load_pvt_table(os.path.join(U.GOLDEN, "pvt_table.npz"))
+    tab = O.build_spline_table(cols, O.GC_PROPS if fluid == "GC" else O.DG_PROPS, order=1, lam=0.001)
+    B = int(g[f"{name}_B"])
+    nb = B
+    cfg.bhp_max_iters = int(g[f"{name}_max_iters"])      # the blocking two-phase case runs three steps: each costs two integrals of eight root finds
+    flat = O.well_flat_index(wl, cfg.D, cfg.H, cfg.W).astype(np.int64)
+    at = lambda a: np.asarray(a).reshape(B, -1)[:nb, flat]
+    pc, kc = torch.as_tensor(at(g[f"{name}_p"])).requires_grad_(True), torch.as_tensor(at(g[f"{name}_kx"]))
+    eq = lambda a, b: np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+    close = lambda a, b: np.abs(np.asarray(a, np.float64) - b).max() <= 1e-5 * np.abs(b).max()
+    t_days = g[f"{name}_t_days"][:nb]
+    if fluid == "GC":
+        sc = torch.as_tensor(at(g[f"{name}_sg"])).requires_grad_(True)
+        q4, pwf = O.wells_gc(pc, sc, kc, t_days, tab, cfg, torch.float32)
+        for c in range(4):
+            assert eq(q4[c].detach().numpy(), at(g[f"{name}_q4"][c])), c
+        gp, gs = torch.autograd.grad(sum(q.sum() for q in q4), [pc, sc])
+        assert close(gp.numpy(), at(g[f"{name}_dq_dp"])) and close(gs.numpy(), at(g[f"{name}_dq_dsg"]))
+    else:
+        q, pwf = O.wells_dg(pc, kc, t_days, tab, cfg, torch.float32)
+        assert eq(q.detach().numpy(), at(g[f"{name}_q"]))
+        (gp,) = torch.autograd.grad(q.sum(), [pc])
+        assert close(gp.numpy(), at(g[f"{name}_dq_dp"]))
+    assert eq(pwf.detach().numpy(), at(g[f"{name}_pwf"]))
+    # the loop did run: the initial guess min_bhp + (p - min_bhp)/2 is not the answer everywhere
+    p0 = 4100.0 + 0.5 * (at(g[f"{name}_p"]) - 4100.0)
+    assert (np.abs(pwf.detach().numpy() - p0) > 1.0).any()
+
+
 @pytest.mark.parametrize("name,fluid,blocking", [("dg", "DG", False), ("dgblk", "DG", True), ("gc", "GC", False),
                                                  ("gcblk", "GC", True), ("gcblk_br", "GC", True)])
 def test_oracle_wells_equal_the_reference_class_bit_for_bit(name, fluid, blocking):
