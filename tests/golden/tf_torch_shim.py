@@ -479,4 +479,23 @@ constant_initializer = lambda value=0.0: (lambda shape: torch.full(tuple(int(s) 
 keras.constraints = types.SimpleNamespace(MinMaxNorm=lambda **k: None, UnitNorm=lambda **k: None)
 keras.initializers.get = lambda name: None
 nn = types.SimpleNamespace(sigmoid=torch.sigmoid, relu=torch.relu, tanh=torch.tanh)
+
+
+class _Dense(_Layer):
+    """tf.keras.layers.Dense on the last axis: activation(x @ kernel + bias); the generator sets kernel / bias"""
+
+    def __init__(self, units, activation=None, kernel_initializer=None, kernel_constraint=None, name=None, **k):
+        super().__init__(name=name)
+        self.units, self.activation = int(units), activation
+        self.kernel = self.bias = None
+
+    def call(self, x):
+        if self.kernel is None:
+            self.kernel = torch.ones(x.shape[-1], self.units).requires_grad_(True)
+            self.bias = torch.zeros(self.units).requires_grad_(True)
+        y = matmul(x, self.kernel) + self.bias
+        return self.activation(y) if self.activation is not None else y
+
+
+keras.layers.Dense = _Dense
 math.reduce_sum = reduce_sum

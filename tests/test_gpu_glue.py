@@ -190,6 +190,37 @@ def test_glue_against_the_reference_hard_layer_class():
     eng.close()
 
 
+def test_hard_layer_options_against_the_reference_class():
+    """The mirror's HardLayer with every non-default option on -- use_rbf (Dense(1, sigmoid) on the property channel),
+    the gas-condensate rectifier on a third input, activations on the kernel exponent and on the network output --
+    against values and cotangents of the reference's OWN class with the same options (Hard_Layer_Subclassed.py:41-45,
+    168-187, 219-246; tests/golden/make_reference_hardlayer_golden.py: reference_hardlayer_opts.npz)."""
+    g = np.load(os.path.join(U.GOLDEN, "reference_hardlayer_opts.npz"))
+    B, D, H, W = g["y"].shape
+    ocfg, otab, spec, ptab, _ = U.make_case(W=W, H=H, D=D, T=1, K=1, seed=1)
+    eng = srm.SrmPhysics(spec, ptab, device=0)
+    dev = eng.device
+    hl = srm.HardLayer(eng, norm_limits=[-1, 1], init_value=float(g["init_value"]),
+                       kernel_exponent_config={"initial_value": (0.5,), "trainable": True, "min_value": 0.1, "max_value": 1.0},
+                       use_rbf=True, rbf_config={"output_dim": 25, "activation": "sigmoid"}, rectifier=torch.relu,
+                       kernel_activation=[torch.sigmoid], input_activation=torch.tanh, pdew=float(g["pdew"]), pmin=float(g["pmin"]))
+    with torch.no_grad():
+        hl.kernel_exponent.copy_(torch.as_tensor(g["expo"]).to(dev))
+        hl.rbf_dense.weight.fill_(float(g["kernel"]))
+        hl.rbf_dense.bias.fill_(float(g["bias"]))
+    t5 = lambda k: torch.as_tensor(g[k]).to(dev).unsqueeze(-1)
+    tn = torch.as_tensor(g["tn"]).to(dev).requires_grad_(True)
+    time = tn.view(B, 1, 1, 1, 1).expand(B, D, H, W, 1)
+    y, rect = t5("y").requires_grad_(True), t5("rect").requires_grad_(True)
+    out = hl([[time, t5("prop")], y, rect])
+    assert np.allclose(out.detach().cpu().numpy()[..., 0], g["out"], rtol=2e-6, atol=0)
+    gy, ge, gt, gk, gb, gr = torch.autograd.grad((out * t5("wgt")).sum(), [y, hl.kernel_exponent, tn, hl.rbf_dense.weight, hl.rbf_dense.bias, rect])
+    for got, key in ((gy[..., 0], "gy"), (ge, "gexpo"), (gt, "gtn"), (gk.reshape(1, 1), "gkernel"), (gb, "gbias"), (gr[..., 0], "grect")):
+        assert U.rel_to_max(got.cpu().numpy(), g[key]) < 1e-5, key
+    assert (g["rect"] < float(g["pdew"])).any() and (g["rect"] > float(g["pdew"])).any()      # both sides of the dew point
+    eng.close()
+
+
 def test_fused_two_level_carries_the_time_cotangent_to_the_time_step_model():
     """d p1 / d tn1 = -e alpha_t^(e-1) y1 / (t_hi - t_lo) must reach the time-step model through x1's time
     channel.  fused_two_level (one CUDA pass) against the same graph in plain torch ops on the same device."""
