@@ -10,6 +10,9 @@
 #include <vector>
 
 #include "srm_internal.cuh"
+#ifndef SRM_L2_PERSIST_DEFAULT_MB
+#define SRM_L2_PERSIST_DEFAULT_MB 0
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -218,6 +221,22 @@ int srm_create(const SrmConfig* cfg, SrmHandle** out) {
     h->lut_full = (lo <= cfg->p_min && hi >= cfg->p_max) ? 1 : 0;
     int rc = cfg->fluid_type == SRM_FLUID_GC ? srm_build_pvt_lut_gc(h, lo, hi) : srm_build_pvt_lut(h, lo, hi);
     if (rc) { srm_destroy(h); return rc; }
+    // The table gathers carry an L2::evict_last policy; that priority only has a region of the L2 to live in when the
+    // device's persisting set-aside is non-zero (cudaLimitPersistingL2CacheSize, 0 by default).  SRM_L2_PERSIST_MB
+    // (read once, here) overrides the size; 0 leaves the device limit alone.
+    {
+      int max_persist = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+      long mb = SRM_L2_PERSIST_DEFAULT_MB;
+      if (const char* e = getenv("SRM_L2_PERSIST_MB")) mb = atol(e);
+      if (mb > 0 && max_persist > 0) {
+        size_t want = (size_t)mb << 20;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        cudaError_t ce = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        if (ce != cudaSuccess) (void)cudaGetLastError();      // not fatal: the hints fall back to ordinary replacement
+        h->l2_persist_bytes = (ce == cudaSuccess) ? (int64_t)want : 0;
+      }
+    }
   }
   // Optional (SRM_ADJ_PACKS=1, read once here): the lean dry-gas forward stages the adjoint's six table values per cell
   // through the workspace and the adjoint runs without table gathers.  Measured on B200 (cfg5, K = 8): adjoint

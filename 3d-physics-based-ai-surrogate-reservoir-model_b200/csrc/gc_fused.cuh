@@ -91,6 +91,9 @@ __device__ __forceinline__ VisF g2_vis_fwd(const SrmDev& P, const float4* __rest
   return v;
 }
 
+// LISTS: the tile's connections come from the staged column lists (well_tile.cuh; lattices of many connections);
+// otherwise the few-connection path: exact column flags, a search inside the cell's layer
+template <bool LISTS>
 __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
   __shared__ float4 s_m[2][G2PL];
   __shared__ float4 s_q[2][G2PL];                  // {p1, krg, kro, -}
@@ -111,14 +114,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   const float* __restrict__ FU = FN + FL.nN;
   int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
   // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
-  __shared__ __align__(8) G2Wells s_wt;
+  __shared__ __align__(8) unsigned char s_wt_raw[LISTS ? sizeof(G2Wells) : 8];
+  G2Wells& s_wt = *reinterpret_cast<G2Wells*>(s_wt_raw);
   bool col_wells = false;
   int wslot = 0;
-  if (P.n_wells > 0) {
+  if constexpr (LISTS) {
     bool over = false;
     const bool any = s_wt.build(well_cols_of(P), P.W, P.D, g.tx0, g.ty0, nullptr, over);
     if (over) col_wells = g.active && column_has_well_gc(P, g.col, HW);
     else if (any && g.active) wslot = s_wt.slot_of[g.lt];
+  } else {
+    col_wells = g.active && column_has_well_gc(P, g.col, HW);
   }
   const float d1 = A.dt1[b], d2 = A.dt2[b];
   const float idl[6] = {P.idx, P.idx, P.idy, P.idy, P.idz, P.idz};
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     // wells in this cell (scatter_nd sums duplicates)
     float q4[4] = {0.f, 0.f, 0.f, 0.f}, mask = 0.f;
     int wfirst = 0, wlast = 0;
-    if (wslot) {
+    if (LISTS && wslot) {
       s_wt.take(wslot - 1, k, wfirst, wlast);
       for (int e = wfirst; e < wlast; ++e) {
         const int w = s_wt.w[e];
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
       A.dom[base + c] = dom;
       if (A.dom_out) A.dom_out[base + c] = dom;
       if (mask != 0.f) {
-        if (wslot) { for (int e = wfirst; e < wlast; ++e) A.divqw[(int64_t)b * P.n_wells + s_wt.w[e]] = divq_tot; }
+        if (LISTS && wslot) { for (int e = wfirst; e < wlast; ++e) A.divqw[(int64_t)b * P.n_wells + s_wt.w[e]] = divq_tot; }
         else { for (int w = wfirst; w < P.n_wells && P.wells[w].cell == c; ++w) A.divqw[(int64_t)b * P.n_wells + w] = divq_tot; }
       }
       acc[0] += (double)dom * (double)dom;
@@ -339,6 +345,7 @@ __device__ __forceinline__ VisA g2_vis_adj(const SrmDev& P, float p1, float sg1,
   return v;
 }
 
+template <bool LISTS>
 __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
   __shared__ float4 s_v[2][G2PL];                  // {p1, 2 w_dom dom, krg, kro}
   __shared__ float2 s_k[2][G2PL];                  // {Mg, Mo}
@@ -358,14 +365,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const float* __restrict__ FU = FN + FL.nN;
   int fe = g.cj * FL.WP + g.ci, fn = g.col, fu = g.col;      // face offsets of plane 0 (per-realisation arrays: < 2^31 floats)
   // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
-  __shared__ __align__(8) G2Wells s_wt;
+  __shared__ __align__(8) unsigned char s_wt_raw[LISTS ? sizeof(G2Wells) : 8];
+  G2Wells& s_wt = *reinterpret_cast<G2Wells*>(s_wt_raw);
   bool col_wells = false;
   int wslot = 0;
-  if (P.n_wells > 0) {
+  if constexpr (LISTS) {
     bool over = false;
     const bool any = s_wt.build(well_cols_of(P), P.W, P.D, g.tx0, g.ty0, nullptr, over);
     if (over) col_wells = g.active && column_has_well_gc(P, g.col, HW);
     else if (any && g.active) wslot = s_wt.slot_of[g.lt];
+  } else {
+    col_wells = g.active && column_has_well_gc(P, g.col, HW);
   }
   const float w_dom = A.dterms[SRM_TERM_DOM], w_mbc = A.dterms[SRM_TERM_MBC], w_trn = A.dterms[SRM_TERM_CMBC];
   const float w2 = 2.f * w_dom;
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     go1 -= smf * (r1 + b1);
     go0 += smf * (R0 + B0);
     // wells in this cell: sum of the four rates enters dom (+) and mbc (-)
-    if (wslot) {
+    if (LISTS && wslot) {
       const int64_t wt = (int64_t)A.B * P.n_wells;
       int first, last;
       s_wt.take(wslot - 1, k, first, last);

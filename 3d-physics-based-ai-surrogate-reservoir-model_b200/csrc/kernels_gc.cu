@@ -997,7 +997,7 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
   if (fused) {
     A.tiles_x = (P.W + G2X - 1) / G2X;
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
-    k_fwd_gc2<<<grid, kThreads, 0, s>>>(P, A);
+    if (P.n_wells > 64) k_fwd_gc2<true><<<grid, kThreads, 0, s>>>(P, A); else k_fwd_gc2<false><<<grid, kThreads, 0, s>>>(P, A);
   } else {
     const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
     k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
@@ -1027,7 +1027,7 @@ int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, co
   if (fused) {
     A.tiles_x = (P.W + G2X - 1) / G2X;
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
-    k_adj_gc2<<<grid, kThreads, 0, s>>>(P, A);
+    if (P.n_wells > 64) k_adj_gc2<true><<<grid, kThreads, 0, s>>>(P, A); else k_adj_gc2<false><<<grid, kThreads, 0, s>>>(P, A);
   } else {
     const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
     k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);

@@ -100,6 +100,7 @@ struct SrmHandle {
   SrmDev dev;          // device parameter block
   WellDev* d_wells;    // device
   int32_t* d_wcols;    // device: col_rem | col_ptr | col_ent of the parameter block (one allocation)
+  int64_t l2_persist_bytes;   // persisting L2 set-aside requested for the table gathers' evict_last policy (0: none)
   SrmClosedForm* d_cf; // device (closed-form tables), may be null
   void* d_cf2;         // device (tables of the lean closed-form pair, kernels_cf2.cu), may be null
   int cf_faces_ok, cf_grouped;   // closed form: which per-call scratch the last forward left in the workspace

@@ -15,6 +15,10 @@ name, numerics, K, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.a
 libs = sys.argv[5:]
 c, spec = bench.workload(name)
 cones = [(w.i, w.j) for w in spec.wells[:8]]
+if os.environ.get("TUNE_LATTICE"):      # a 4 x 8 lattice completed in every layer instead of the config's connections
+    import dataclasses
+    spec = dataclasses.replace(spec, wells=srm.config.lattice_wells(spec.W, spec.H, spec.D))
+    cones = [(w.i, w.j) for w in spec.wells[::spec.D][:8]]
 if os.environ.get("TUNE_NOWELLS"):      # the same grid and pressures without connections: what the well code costs
     import dataclasses
     spec = dataclasses.replace(spec, wells=[])
