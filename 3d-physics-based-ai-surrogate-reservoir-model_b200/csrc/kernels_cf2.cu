@@ -336,7 +336,7 @@ __device__ __forceinline__ Place<LX> make_place(const Cf2Dev& P, int tiles_x) {
     return -1;
   };
   t.ring0 = ring(tid);
-#ifdef CF2_RING_LAST
+#ifndef CF2_RING_FIRST
   t.ring1 = ring(NT + (NT - 1 - tid));      // the second halo cell goes to the LAST warp: warp 0 already issues the TMA copies
 #else
   t.ring1 = ring(tid + NT);
@@ -447,13 +447,17 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   float a1c[CPT] = {}, a1lc[CPT] = {};      // invBg at level n+1 of plane m: value, anchor low part
   float pn[CPT], Gn[CPT], a1n[CPT], a1ln[CPT];
 
+  // running indices of the march (no division in the plane loop): stage / parity / G buffer of the arriving plane k,
+  // stage and G buffer of the plane m = k - 1 under the stencil, store pointer of plane m
+  int sk = 0, phk = 0, gk = 0, sm = 0, gm = 0;
+  float* domp = domf;
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
     if (k < D) {
-      const int s = k % S;
-      mbar_wait(&full[s], (k / S) & 1);
+      const int s = sk;
+      mbar_wait(&full[s], phk);
       const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
-      float* Gb = Gs + (k % 3) * (G::GPL / 4);
+      float* Gb = Gs + gk * (G::GPL / 4);
       ldv(pn, sp1 + t.own);
       bool in = true;
       if (ABL == 1) {
@@ -506,19 +510,19 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     }
     const int m = k - 1;
     if (m >= 0) {
-      const unsigned char* st = stage(m % S);
+      const unsigned char* st = stage(sm);
       const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
       const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
       const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
       const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
       const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
-      const float* Gm = Gs + (m % 3) * (G::GPL / 4);
+      const float* Gm = Gs + gm * (G::GPL / 4);
       if (ABL == 1) {
         float q0[CPT], dv_[CPT];
         ldv(q0, sp0 + t.ry * G::TX + CPT * t.lx);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) dv_[c] = pc[c] + q0[c];
-        if (t.valid) stv_cs(domf + (int64_t)m * P.H * P.W, dv_);
+        if (t.valid) stv_cs(domp, dv_);
       } else {
       float pS[CPT], pN[CPT], gS[CPT], gN[CPT], fE[CPT], fS[CPT], fN[CPT], fU[CPT], p0[CPT];
       ldv(pS, sp1 + t.own - G::BX); ldv(pN, sp1 + t.own + G::BX);
@@ -614,7 +618,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CPT; ++c) domv[c] = dvf[c] + rest[c];
       if (t.valid) {
-        stv_cs(domf + (int64_t)m * P.H * P.W, domv);
+        stv_cs(domp, domv);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
       } else {
@@ -623,9 +627,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
       if (FREE) {         // this warp has read plane m's stage for the last time
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[m % S]);
+        if ((tid & 31) == 0) mbar_arrive(&empty[sm]);
       }
+      domp += P.H * P.W;
     }
+    sm = sk; gm = gk;
+    if (++sk == S) { sk = 0; phk ^= 1; }
+    if (++gk == 3) gk = 0;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
     if ((k & 7) == 7) { d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f; }
@@ -727,14 +735,16 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   float Xz[CPT] = {}, Yz[CPT] = {};
   float pn[CPT], Gn[CPT], dn[CPT], Gpn[CPT], Apn[CPT];
 
+  int sk = 0, phk = 0, gk = 0, sm = 0, gm = 0;      // running indices, as in the forward
+  int64_t go = fo;                                  // store offset of plane m
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
     if (k < D) {
-      const int s = k % S;
-      mbar_wait(&full[s], (k / S) & 1);
+      const int s = sk;
+      mbar_wait(&full[s], phk);
       const float* sp1 = reinterpret_cast<const float*>(stage(s) + G::O_P1);
       const float* sdm = reinterpret_cast<const float*>(stage(s) + G::O_DM);
-      float* Gb = Gs + (k % 3) * (G::GPL / 4);
+      float* Gb = Gs + gk * (G::GPL / 4);
       ldv(pn, sp1 + t.own);
       ldv(dn, sdm + t.own);
       bool in = true;
@@ -787,14 +797,14 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     }
     const int m = k - 1;
     if (m >= 0) {
-      const unsigned char* st = stage(m % S);
+      const unsigned char* st = stage(sm);
       const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
       const float* sdm = reinterpret_cast<const float*>(st + G::O_DM);
       const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
       const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
       const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
       const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
-      const float* Gm = Gs + (m % 3) * (G::GPL / 4);
+      const float* Gm = Gs + gm * (G::GPL / 4);
       float pS[CPT], pN[CPT], gS[CPT], gN[CPT], dS[CPT], dN[CPT], fE[CPT], fS[CPT], fN[CPT], fU[CPT], p0[CPT];
       ldv(pS, sp1 + t.own - G::BX); ldv(pN, sp1 + t.own + G::BX);
       if (FREE) { cf2_G_vec(T, c0, c1, pS, gS); cf2_G_vec(T, c0, c1, pN, gN); }
@@ -886,16 +896,20 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         }
       }
       if (t.valid) {
-        stv_cs(A.gp0 + fo + (int64_t)m * P.H * P.W, g0v);
-        stv_cs(A.gp1 + fo + (int64_t)m * P.H * P.W, g1v);
+        stv_cs(A.gp0 + go, g0v);
+        stv_cs(A.gp1 + go, g1v);
       } else {
         a_g1 = 0.f;
       }
       if (FREE) {
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty[m % S]);
+        if ((tid & 31) == 0) mbar_arrive(&empty[sm]);
       }
+      go += P.H * P.W;
     }
+    sm = sk; gm = gk;
+    if (++sk == S) { sk = 0; phk ^= 1; }
+    if (++gk == 3) gk = 0;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; dc[c] = dn[c]; Gpc[c] = Gpn[c]; Apc[c] = Apn[c]; }
     if ((k & 7) == 7) { d_g1 += (double)a_g1; a_g1 = 0.f; }
