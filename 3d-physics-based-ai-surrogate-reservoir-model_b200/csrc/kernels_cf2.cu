@@ -200,6 +200,27 @@ __device__ __forceinline__ void tma_4d(void* dst, const CUtensorMap* map, uint64
 __device__ __forceinline__ uint64_t pol_evict_last() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t pol_evict_first() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 
+// ---- packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2) -----------------------------------------------------------
+// Two x-adjacent cells per instruction: the packed forms issue at half the warp-instruction rate of the scalar ones
+// and move the same 128 lanes per cycle and SM (tools/ffma2_probe.cu), so a packed operation costs one issue slot for
+// two cells.  Pairs that sit in adjacent registers (the halves of a 16-byte shared load, unrolled arrays) pack and unpack
+// for free; a scalar operand {s, s} is a broadcast form of the instruction, not a second register.
+#ifndef CF2_PACK
+#define CF2_PACK 1
+#endif
+constexpr bool PACK = (CF2_PACK != 0) && CPT == 4;
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float x, float y) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ f2 bc(float s) { return pk(s, s); }
+__device__ __forceinline__ void upk(f2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float hsum(f2 v) { float x, y; upk(v, x, y); return x + y; }
+#define PK2(a, h) pk((a)[2 * (h)], (a)[2 * (h) + 1])
+#define UPK2(v, a, h) upk((v), (a)[2 * (h)], (a)[2 * (h) + 1])
+
 // CPT floats at once: shared loads / stores and streaming global stores
 __device__ __forceinline__ void ldv(float (&d)[CPT], const float* p) {
   if constexpr (CPT == 4) { const float4 v = *reinterpret_cast<const float4*>(p); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
@@ -434,6 +455,8 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
 
   float a_dom = 0.f, a_tde = 0.f, a_mb = 0.f;
+  f2 a_dom2 = 0ull, a_tde2 = 0ull, a_mb2 = 0ull;      // the same partial sums, one lane per cell of a pair (PACK)
+  f2 fz2[CPT / 2] = {};                               // upper z-face term of the plane below, packed
   double d_dom = 0.0, d_tde = 0.0, d_mb = 0.0, d_ibc = 0.0;
 
   // the cached interval: that of the tile's first pressure of plane 0
@@ -465,6 +488,17 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         for (int c = 0; c < CPT; ++c) { Gn[c] = pn[c]; a1n[c] = 0.f; a1ln[c] = 0.f; }
         if (!FREE) stv(Gb + t.own, Gn);
       } else {
+      if constexpr (PACK) {
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) {
+          in = in && (pn[2 * h] > c0.x) && (pn[2 * h] < c0.y) && (pn[2 * h + 1] > c0.x) && (pn[2 * h + 1] < c0.y);
+          const f2 dx = sub2(PK2(pn, h), bc(c0.z));
+          const f2 a1 = fma2(bc(c1.x), dx, bc(c0.w));
+          UPK2(a1, a1n, h);
+          UPK2(mul2(a1, fma2(bc(c1.z), dx, bc(c1.y))), Gn, h);
+          a1ln[2 * h] = c1.w; a1ln[2 * h + 1] = c1.w;
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
@@ -472,6 +506,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         a1n[c] = fmaf(c1.x, dx, c0.w);
         a1ln[c] = c1.w;
         Gn[c] = a1n[c] * fmaf(c1.z, dx, c1.y);
+      }
       }
       if (!in) {
 #pragma unroll
@@ -550,9 +585,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
-        A0[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
+        if constexpr (!PACK) A0[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
         Ap[c] = c1.x;
         A0l[c] = c1.w;
+      }
+      if constexpr (PACK) {
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) UPK2(fma2(bc(c1.x), sub2(PK2(p0, h), bc(c0.z)), bc(c0.w)), A0, h);
       }
       if (!in0) {
 #pragma unroll
@@ -567,6 +606,28 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           A0l[c] = f.w;
         }
       }
+      if constexpr (PACK) {
+        // y and z faces, the cell-local part: two cells per instruction (the x faces above stay scalar: a cell's W
+        // neighbour sits in the other half of its pair)
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) {
+          const f2 Gc2 = PK2(Gc, h), pc2 = PK2(pc, h);
+          f2 flux = pk(Fx[2 * h + 1] - Fx[2 * h], Fx[2 * h + 2] - Fx[2 * h + 1]);
+          flux = fma2(mul2(PK2(fS, h), add2(Gc2, PK2(gS, h))), sub2(pc2, PK2(pS, h)), flux);
+          flux = fma2(mul2(PK2(fN, h), add2(Gc2, PK2(gN, h))), sub2(pc2, PK2(pN, h)), flux);
+          const f2 fu = mul2(mul2(PK2(fU, h), add2(Gc2, PK2(Gn, h))), sub2(pc2, PK2(pn, h)));     // upper z face; the plane above takes -fu
+          flux = add2(flux, sub2(fu, fz2[h]));
+          fz2[h] = fu;
+          const f2 A02 = PK2(A0, h);
+          const f2 cp = fma2(bc(P.K1), PK2(Ap, h), mul2(bc(P.K2), A02));
+          const f2 tde = mul2(bc(cT), cp);
+          const f2 cacp = mul2(bc(cA), cp), dp10 = sub2(pc2, PK2(p0, h));
+          UPK2(mul2(bc(P.dv), flux), dvf, h);
+          UPK2(P.tde_in_dom ? fma2(cacp, dp10, tde) : mul2(cacp, dp10), rest, h);
+          a_tde2 = fma2(tde, tde, a_tde2);
+          a_mb2 = add2(a_mb2, add2(sub2(PK2(a1c, h), A02), sub2(PK2(a1lc, h), PK2(A0l, h))));
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         float flux = Fx[c + 1] - Fx[c];
@@ -582,6 +643,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         rest[c] = P.tde_in_dom ? fmaf(cA * cp, pc[c] - p0[c], tde) : cA * cp * (pc[c] - p0[c]);
         a_tde = fmaf(tde, tde, a_tde);
         a_mb += (a1c[c] - A0[c]) + (a1lc[c] - A0l[c]);
+      }
       }
       if (tile_wells && has_well && !wt_overflow) {     // wells in this thread's columns, from the staged lists (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
 #pragma unroll
@@ -615,6 +677,16 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           }
         }
       }
+      if constexpr (PACK) {
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) {
+          const f2 dm = add2(PK2(dvf, h), PK2(rest, h));
+          UPK2(dm, domv, h);
+          if (t.valid) a_dom2 = fma2(dm, dm, a_dom2);
+        }
+        if (t.valid) stv_cs(domp, domv);
+        else { a_tde2 = 0ull; a_mb2 = 0ull; }
+      } else {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) domv[c] = dvf[c] + rest[c];
       if (t.valid) {
@@ -623,6 +695,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         for (int c = 0; c < CPT; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
       } else {
         a_tde = 0.f; a_mb = 0.f;
+      }
       }
       }
       if (FREE) {         // this warp has read plane m's stage for the last time
@@ -636,8 +709,12 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     if (++gk == 3) gk = 0;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
-    if ((k & 7) == 7) { d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f; }
+    if ((k & 7) == 7) {
+      if constexpr (PACK) { a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2); a_dom2 = a_tde2 = a_mb2 = 0ull; }
+      d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f;
+    }
   }
+  if constexpr (PACK) { a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2); }
   double acc4[4] = {d_dom + (double)a_dom, d_ibc, d_tde + (double)a_tde, (d_mb + (double)a_mb) * (double)mbk};
   __syncthreads();
   block_reduce<4>(acc4, red);
@@ -724,6 +801,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   const float lo = T->lo, hi = T->hi;
 
   float a_g1 = 0.f;
+  f2 a_g1_2 = 0ull;      // the same partial sum, one lane per cell of a pair (PACK)
   double d_g1 = 0.0;
   mbar_wait(&full[0], 0);
   if (tid == 0) cf2_cache_interval(T, reinterpret_cast<const float*>(stage(0) + G::O_P1)[G::BX + 4]);
@@ -748,6 +826,18 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       ldv(pn, sp1 + t.own);
       ldv(dn, sdm + t.own);
       bool in = true;
+      if constexpr (PACK) {
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) {        // strictly inside the cached interval: inside the clamp too, off every knot
+          in = in && (pn[2 * h] > c0.x) && (pn[2 * h] < c0.y) && (pn[2 * h + 1] > c0.x) && (pn[2 * h + 1] < c0.y);
+          const f2 dx = sub2(PK2(pn, h), bc(c0.z));
+          const f2 A1 = fma2(bc(c1.x), dx, bc(c0.w));
+          const f2 M = fma2(bc(c1.z), dx, bc(c1.y));
+          UPK2(mul2(A1, M), Gn, h);
+          UPK2(fma2(bc(c1.x), M, mul2(A1, bc(c1.z))), Gpn, h);
+          Apn[2 * h] = c1.x; Apn[2 * h + 1] = c1.x;
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {        // strictly inside the cached interval: inside the clamp too, off every knot
         in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
@@ -757,6 +847,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         Gn[c] = A1 * M;
         Apn[c] = c1.x;
         Gpn[c] = fmaf(c1.x, M, A1 * c1.z);
+      }
       }
       if (!in) {
 #pragma unroll
@@ -827,9 +918,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
-        A0v[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
+        if constexpr (!PACK) A0v[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
         Apv[c] = c1.x;
         Apmv[c] = c1.x;
+      }
+      if constexpr (PACK) {
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) UPK2(fma2(bc(c1.x), sub2(PK2(p0, h), bc(c0.z)), bc(c0.w)), A0v, h);
       }
       if (!in0) {
 #pragma unroll
@@ -843,6 +938,46 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
           Apmv[c] = (p0[c] >= lo && p0[c] <= hi) ? Apv[c] : 0.f;
         }
       }
+      if constexpr (PACK) {
+        // x faces per cell (the W / E neighbour sits in the other half of a pair), y and z faces and the cell-local part
+        // two cells per instruction
+        float gx[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const float plW = (c == 0) ? pW : pc[c - (c > 0)], glW = (c == 0) ? gW : Gc[c - (c > 0)], dlW = (c == 0) ? dW : dc[c - (c > 0)];
+          const float plE = (c == CPT - 1) ? pE : pc[c + (c < CPT - 1)], glE = (c == CPT - 1) ? gE : Gc[c + (c < CPT - 1)], dlE = (c == CPT - 1) ? dE : dc[c + (c < CPT - 1)];
+          const float tW = (c == 0) ? fW : fE[c - (c > 0)];
+          float g1 = (dc[c] - dlW) * tW * fmaf(Gpc[c], pc[c] - plW, Gc[c] + glW);
+          gx[c] = fmaf((dc[c] - dlE) * fE[c], fmaf(Gpc[c], pc[c] - plE, Gc[c] + glE), g1);
+        }
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) {
+          const f2 dc2 = PK2(dc, h), pc2 = PK2(pc, h), Gc2 = PK2(Gc, h), Gp2 = PK2(Gpc, h);
+          f2 g1 = PK2(gx, h);
+          g1 = fma2(mul2(sub2(dc2, PK2(dS, h)), PK2(fS, h)), fma2(Gp2, sub2(pc2, PK2(pS, h)), add2(Gc2, PK2(gS, h))), g1);
+          g1 = fma2(mul2(sub2(dc2, PK2(dN, h)), PK2(fN, h)), fma2(Gp2, sub2(pc2, PK2(pN, h)), add2(Gc2, PK2(gN, h))), g1);
+          const f2 u = mul2(sub2(dc2, PK2(dn, h)), PK2(fU, h));
+          const f2 X = mul2(u, add2(Gc2, PK2(Gn, h))), Y = mul2(u, sub2(pc2, PK2(pn, h)));
+          g1 = add2(g1, fma2(Gp2, add2(Y, PK2(Yz, h)), sub2(X, PK2(Xz, h))));
+          UPK2(X, Xz, h); UPK2(Y, Yz, h);
+          g1 = mul2(g1, bc(sddv));
+          // cell-local part
+          const f2 sc = mul2(bc(sd), dc2);
+          const f2 Apm = PK2(Apmv, h);
+          const f2 cp = fma2(bc(P.K1), PK2(Apv, h), mul2(bc(P.K2), PK2(A0v, h)));
+          const f2 cpp = mul2(bc(P.K2), Apm);
+          const f2 dp10 = sub2(pc2, PK2(p0, h));
+          const f2 cacp = mul2(bc(cA), cp);
+          const f2 acc = mul2(cacp, dp10);
+          const f2 tde = mul2(bc(cT), cp);
+          const f2 stt = fma2(bc(seed_tde), sc, mul2(bc(wt2), tde));
+          g1 = add2(g1, sub2(mul2(sc, cacp), mul2(bc(smbk), PK2(Apc, h))));
+          UPK2(g1, g1v, h);
+          const f2 g0 = fma2(mul2(sc, bc(cA)), sub2(mul2(cpp, dp10), cp), fma2(mul2(stt, bc(cT)), cpp, mul2(bc(smbk), Apm)));
+          UPK2(g0, g0v, h);
+          a_g1_2 = sub2(a_g1_2, mul2(fma2(sc, acc, mul2(stt, tde)), bc(inv_d1)));
+        }
+      } else {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         // in-plane faces in gather form; the z faces once per face: this plane's upper face is the next one's lower
@@ -873,6 +1008,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         g0v[c] = sc * cA * (cpp * dp10 - cp) + stt * cT * cpp + smbk * Apm;
         a_g1 -= (sc * acc + stt * tde) * inv_d1;
       }
+      }
       if (tile_wells && has_well && !wt_overflow) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
@@ -899,7 +1035,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         stv_cs(A.gp0 + go, g0v);
         stv_cs(A.gp1 + go, g1v);
       } else {
-        a_g1 = 0.f;
+        a_g1 = 0.f; a_g1_2 = 0ull;
       }
       if (FREE) {
         __syncwarp();
@@ -912,8 +1048,12 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     if (++gk == 3) gk = 0;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; dc[c] = dn[c]; Gpc[c] = Gpn[c]; Apc[c] = Apn[c]; }
-    if ((k & 7) == 7) { d_g1 += (double)a_g1; a_g1 = 0.f; }
+    if ((k & 7) == 7) {
+      if constexpr (PACK) { a_g1 = hsum(a_g1_2); a_g1_2 = 0ull; }
+      d_g1 += (double)a_g1; a_g1 = 0.f;
+    }
   }
+  if constexpr (PACK) a_g1 = hsum(a_g1_2);
   double acc1[1] = {d_g1 + (double)a_g1};
   __syncthreads();
   block_reduce<1>(acc1, red);
