@@ -208,7 +208,7 @@ __device__ __forceinline__ uint64_t pol_evict_first() { uint64_t p; asm("createp
 #ifndef CF2_PACK
 #define CF2_PACK 1
 #endif
-constexpr bool PACK = (CF2_PACK != 0) && CPT == 4;
+constexpr bool PACK = (CF2_PACK != 0);
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 pk(float x, float y) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
 __device__ __forceinline__ f2 bc(float s) { return pk(s, s); }
