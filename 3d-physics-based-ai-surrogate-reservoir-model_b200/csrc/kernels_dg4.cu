@@ -78,6 +78,10 @@ __device__ __forceinline__ void stgs(float* p, const float (&v)[CPT], uint64_t p
 }
 // static face coefficients: shared by the T samples of a realisation, default caching
 __device__ __forceinline__ void ldgc(const float* p, float* v) {
+#if defined(SRM_D4_ABL) && SRM_D4_ABL == 3     // timing ablation: no face-coefficient loads at all (results are wrong)
+  for (int c = 0; c < CPT; ++c) v[c] = 1e-3f + 1e-9f * (float)(reinterpret_cast<uintptr_t>(p) & 1023u);
+  return;
+#endif
   if constexpr (CPT == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   else { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[0] = t.x; v[1] = t.y; }
 }
@@ -308,7 +312,11 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCF) k_fwd4(const __grid_constant_
       // static face coefficients of plane k first: they are not queued behind the gathers
       float fx[CPT + 1], fS[CPT], fN[CPT], fU[CPT];
       ldgc(FB + offE, fx);
+#if defined(SRM_D4_ABL) && SRM_D4_ABL == 3
+      fx[CPT] = 1e-3f;
+#else
       fx[CPT] = __ldg(FB + offE + CPT);
+#endif
       ldgc(FB + offN, fS);
       ldgc(FB + offN + W, fN);
       ldgc(FB + offU, fU);
@@ -613,7 +621,11 @@ __global__ void __launch_bounds__(NT, SRM_D4_OCCA) k_adj4(const __grid_constant_
       const int rem = D - 1 - k;
       float fx[CPT + 1], fS[CPT], fN[CPT], fU[CPT];
       ldgc(FB + offE, fx);
+#if defined(SRM_D4_ABL) && SRM_D4_ABL == 3
+      fx[CPT] = 1e-3f;
+#else
       fx[CPT] = __ldg(FB + offE + CPT);
+#endif
       ldgc(FB + offN, fS);
       ldgc(FB + offN + W, fN);
       ldgc(FB + offU, fU);

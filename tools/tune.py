@@ -15,6 +15,9 @@ name, numerics, K, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.a
 libs = sys.argv[5:]
 c, spec = bench.workload(name)
 cones = [(w.i, w.j) for w in spec.wells[:8]]
+if os.environ.get("TUNE_D"):            # the same x-y grid with another depth (per-CTA fixed costs against the column length)
+    import dataclasses
+    spec = dataclasses.replace(spec, D=int(os.environ["TUNE_D"]), wells=[w for w in spec.wells if w.k < int(os.environ["TUNE_D"])])
 if os.environ.get("TUNE_LATTICE"):      # a 4 x 8 lattice completed in every layer instead of the config's connections
     import dataclasses
     spec = dataclasses.replace(spec, wells=srm.config.lattice_wells(spec.W, spec.H, spec.D))
