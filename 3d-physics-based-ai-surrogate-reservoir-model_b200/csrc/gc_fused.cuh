@@ -80,20 +80,21 @@ __device__ __forceinline__ uint32_t g2_entry(const SrmDev& P, float p, float& m)
 
 // ---- forward -------------------------------------------------------------------------------------
 struct VisF { float4 m; float p1, krg, kro; };     // m = {Mgg, Mgo, Moo, Mog}
-__device__ __forceinline__ VisF g2_vis_fwd(const SrmDev& P, const float4* __restrict__ t1, float p1, float sg1) {
+template <int NOG = 0, int NG = 0>
+__device__ __forceinline__ VisF g2_vis_fwd(const SrmDev& P, const DivC* den, const float4* __restrict__ t1, float p1, float sg1) {
   float m1;
   const uint32_t e = g2_entry(P, p1, m1);
   VisF v;
   v.m = __ldg(t1 + 2 * (size_t)e);                  // {Mgg, Mgo, Moo, Mog}: the forward view is stored in component order
   float dko, dkg;
-  corey(P, sg1, v.kro, v.krg, dko, dkg);
+  corey<NOG, NG>(P, sg1, v.kro, v.krg, dko, dkg, den);
   v.p1 = p1;
   return v;
 }
 
 // LISTS: the tile's connections come from the staged column lists (well_tile.cuh; lattices of many connections);
 // otherwise the few-connection path: exact column flags, a search inside the cell's layer
-template <bool LISTS>
+template <bool LISTS, int NOG, int NG>
 __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__ SrmDev P, const __grid_constant__ GcFwd A) {
   __shared__ float4 s_m[2][G2PL];
   __shared__ float4 s_q[2][G2PL];                  // {p1, krg, kro, -}
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   const int b = blockIdx.y;
   const int HW = P.H * P.W;
   const G2Geom g = g2_geom(P, A.tiles_x);
+  const DivC* kr_den = nullptr;      // forward: the IEEE intrinsic (the hoisted-reciprocal form costs this kernel registers: measured slower)
   const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   const float4* __restrict__ T0 = reinterpret_cast<const float4*>(P.lutf0);
   const float4* __restrict__ T1 = reinterpret_cast<const float4*>(P.lutf1);
@@ -139,11 +141,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
 
   // plane 0 into buffer 0; raw p1 / sg1 of the next plane travel one plane ahead of their gather
   float sg1c = SG1[g.col];
-  VisF vC = g2_vis_fwd(P, T1, P1[g.col], sg1c);
+  VisF vC = g2_vis_fwd<NOG, NG>(P, nullptr, T1, P1[g.col], sg1c);
   s_m[0][g.so] = vC.m;
   s_q[0][g.so] = make_float4(vC.p1, vC.krg, vC.kro, 0.f);
   if (g.halo) {
-    const VisF h = g2_vis_fwd(P, T1, P1[g.hcol], SG1[g.hcol]);
+    const VisF h = g2_vis_fwd<NOG, NG>(P, nullptr, T1, P1[g.hcol], SG1[g.hcol]);
     s_m[0][g.hs] = h.m;
     s_q[0][g.hs] = make_float4(h.p1, h.krg, h.kro, 0.f);
   }
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
     float sg1nn = sg1c;
     const float p0 = p0c;
     if (k + 1 < P.D) {
-      vN = g2_vis_fwd(P, T1, p1n, sg1n);
+      vN = g2_vis_fwd<NOG, NG>(P, nullptr, T1, p1n, sg1n);
       sg1nn = sg1n;
       {   // level-n pack of plane k+1
         float mm;
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
       if (g.halo) {     // raw values arrived a plane ago: the gather goes straight to shared memory, asynchronously
         float hm, hko, hkg, hdko, hdkg;
         cp_async16(&s_m[buf ^ 1][g.hs], T1 + 2 * (size_t)g2_entry(P, hp1, hm));
-        corey(P, hsg1, hko, hkg, hdko, hdkg);
+        corey<NOG, NG>(P, hsg1, hko, hkg, hdko, hdkg, kr_den);
         s_q[buf ^ 1][g.hs] = make_float4(hp1, hkg, hko, 0.f);
         if (k + 2 < P.D) { hp1 = P1[(k + 2) * HW + g.hcol]; hsg1 = SG1[(k + 2) * HW + g.hcol]; }
       }
@@ -332,12 +334,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
 
 // ---- adjoint -------------------------------------------------------------------------------------
 struct VisA { float p1, sn, Mg, Mo, krg, kro, dkrg, dkro; };    // dkrg, dkro: own cell only (not published)
-__device__ __forceinline__ VisA g2_vis_adj(const SrmDev& P, float p1, float sg1, float dom, float w2) {
+template <int NOG = 0, int NG = 0>
+__device__ __forceinline__ VisA g2_vis_adj(const SrmDev& P, const DivC* den, float p1, float sg1, float dom, float w2) {
   float m1;
   const uint32_t e = g2_entry(P, p1, m1);
   const float2 t = __ldg(P.gcv + e);                // {Mgg + Mog, Mgo + Moo}
   VisA v;
-  corey(P, sg1, v.kro, v.krg, v.dkro, v.dkrg);
+  corey<NOG, NG>(P, sg1, v.kro, v.krg, v.dkro, v.dkrg, den);
   v.p1 = p1;
   v.sn = w2 * dom;
   v.Mg = t.x;
@@ -345,7 +348,7 @@ __device__ __forceinline__ VisA g2_vis_adj(const SrmDev& P, float p1, float sg1,
   return v;
 }
 
-template <bool LISTS>
+template <bool LISTS, int NOG, int NG>
 __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__ SrmDev P, const __grid_constant__ GcAdj A) {
   __shared__ float4 s_v[2][G2PL];                  // {p1, 2 w_dom dom, krg, kro}
   __shared__ float2 s_k[2][G2PL];                  // {Mg, Mo}
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const int b = blockIdx.y;
   const int HW = P.H * P.W;
   const G2Geom g = g2_geom(P, A.tiles_x);
+  const DivC kr_den[2] = {make_divc(P.kr_den_o), make_divc(P.kr_den_g)};      // Corey saturations: division by two per-handle constants
   const int r = srm_real_of(A.sample_real, b, A.B, A.R);
   double acc2[2] = {0.0, 0.0};
   const int64_t base = (int64_t)b * P.N;
@@ -396,11 +400,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   const float dE1c = -2.f * 2.5e-8f / (d1 * d1);
 
   float sg1c = SG1[g.col];
-  VisA vC = g2_vis_adj(P, P1[g.col], sg1c, DOM[g.col], w2);
+  VisA vC = g2_vis_adj<NOG, NG>(P, kr_den, P1[g.col], sg1c, DOM[g.col], w2);
   s_v[0][g.so] = make_float4(vC.p1, vC.sn, vC.krg, vC.kro);
   s_k[0][g.so] = make_float2(vC.Mg, vC.Mo);
   if (g.halo) {
-    const VisA h = g2_vis_adj(P, P1[g.hcol], SG1[g.hcol], DOM[g.hcol], w2);
+    const VisA h = g2_vis_adj<NOG, NG>(P, kr_den, P1[g.hcol], SG1[g.hcol], DOM[g.hcol], w2);
     s_v[0][g.hs] = make_float4(h.p1, h.sn, h.krg, h.kro);
     s_k[0][g.hs] = make_float2(h.Mg, h.Mo);
   }
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
     float sg1nn = sg1c;
     const float p0 = p0c;
     if (k + 1 < P.D) {
-      vN = g2_vis_adj(P, p1n, sg1n, domn, w2);
+      vN = g2_vis_adj<NOG, NG>(P, kr_den, p1n, sg1n, domn, w2);
       sg1nn = sg1n;
       {   // own-cell packs of plane k+1: 48 bytes at p0 (two sectors at most), 32 at p1
         float mm;
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
       if (g.halo) {
         float hm, hko, hkg, hdko, hdkg;
         cp_async8(&s_k[buf ^ 1][g.hs], P.gcv + g2_entry(P, hp1, hm));
-        corey(P, hsg1, hko, hkg, hdko, hdkg);
+        corey<NOG, NG>(P, hsg1, hko, hkg, hdko, hdkg, kr_den);
         s_v[buf ^ 1][g.hs] = make_float4(hp1, w2 * hdom, hkg, hko);
         if (k + 2 < P.D) { const int hc = (k + 2) * HW + g.hcol; hp1 = P1[hc]; hsg1 = SG1[hc]; hdom = DOM[hc]; }
       }

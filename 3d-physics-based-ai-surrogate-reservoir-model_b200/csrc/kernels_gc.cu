@@ -72,14 +72,25 @@ __device__ __forceinline__ float dpow_pinned(float x, float n, int ni) {
 }
 // relative_permeability.py:58-73; derivatives follow TF's routing: tf.where picks a branch, tf.minimum /
 // tf.maximum pass the gradient to the first argument on ties.
-__device__ __forceinline__ void corey(const SrmDev& P, float sg, float& krog, float& krgo, float& dkrog, float& dkrgo) {
+// NOG / NG > 0: the integer Corey exponents as compile-time constants (the fused kernels are instantiated for the
+// reference's defaults, nog = 3 and ng = 6: the left-to-right products are then straight-line code instead of a switch
+// per call); 0: the handle's run-time exponents
+// den: the two saturation denominators as DivC (ref_fused.cuh: div.rn's own arithmetic with the reciprocal hoisted out of
+// the cell loop, same bits), or null for the IEEE intrinsic
+template <int NOG = 0, int NG = 0>
+__device__ __forceinline__ void corey(const SrmDev& P, float sg, float& krog, float& krgo, float& dkrog, float& dkrgo,
+                                      const DivC* den = nullptr) {
   const float so = __fsub_rn(__fsub_rn(1.0f, sg), P.swmin);                              // :58
-  const float xo = __fdiv_rn(__fsub_rn(so, P.sorg), P.kr_den_o);
-  const float xg = __fdiv_rn(__fsub_rn(sg, P.sgc), P.kr_den_g);
-  float ko = __fmul_rn(P.kro_somax, pow_pinned(xo, P.nog, P.nog_i));                     // :59
-  float kg = __fmul_rn(P.krg_sorg, pow_pinned(xg, P.ng, P.ng_i));                        // :60
-  float dko = P.kro_somax * dpow_pinned(xo, P.nog, P.nog_i) * (-1.0f / P.kr_den_o);
-  float dkg = P.krg_sorg * dpow_pinned(xg, P.ng, P.ng_i) * (1.0f / P.kr_den_g);
+  const float xo = den ? div_c(__fsub_rn(so, P.sorg), den[0]) : __fdiv_rn(__fsub_rn(so, P.sorg), P.kr_den_o);
+  const float xg = den ? div_c(__fsub_rn(sg, P.sgc), den[1]) : __fdiv_rn(__fsub_rn(sg, P.sgc), P.kr_den_g);
+  const float po = NOG > 0 ? powi<NOG ? NOG : 1>(xo) : pow_pinned(xo, P.nog, P.nog_i);
+  const float pg = NG > 0 ? powi<NG ? NG : 1>(xg) : pow_pinned(xg, P.ng, P.ng_i);
+  float ko = __fmul_rn(P.kro_somax, po);                                                 // :59
+  float kg = __fmul_rn(P.krg_sorg, pg);                                                  // :60
+  const float dpo = NOG > 0 ? (float)NOG * (NOG > 1 ? powi<(NOG > 1) ? NOG - 1 : 1>(xo) : 1.f) : dpow_pinned(xo, P.nog, P.nog_i);
+  const float dpg = NG > 0 ? (float)NG * (NG > 1 ? powi<(NG > 1) ? NG - 1 : 1>(xg) : 1.f) : dpow_pinned(xg, P.ng, P.ng_i);
+  float dko = P.kro_somax * dpo * (-1.0f / P.kr_den_o);
+  float dkg = P.krg_sorg * dpg * (1.0f / P.kr_den_g);
   if (so <= P.kr_so_zero) { ko = 0.f; dko = 0.f; }                                       // :67
   if (sg > P.kr_sg_full) { kg = P.krg_swmin; dkg = 0.f; }                                // :68
   if (!(ko <= P.kro_somax)) { ko = P.kro_somax; dko = 0.f; }                             // :71 tf.minimum
@@ -997,7 +1008,9 @@ int srm_forward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, con
   if (fused) {
     A.tiles_x = (P.W + G2X - 1) / G2X;
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
-    if (P.n_wells > 64) k_fwd_gc2<true><<<grid, kThreads, 0, s>>>(P, A); else k_fwd_gc2<false><<<grid, kThreads, 0, s>>>(P, A);
+    const bool dflt = P.nog_i == 3 && P.ng_i == 6;      // the reference's Corey exponents (default_configurations.py:266)
+    if (P.n_wells > 64) { if (dflt) k_fwd_gc2<true, 3, 6><<<grid, kThreads, 0, s>>>(P, A); else k_fwd_gc2<true, 0, 0><<<grid, kThreads, 0, s>>>(P, A); }
+    else { if (dflt) k_fwd_gc2<false, 3, 6><<<grid, kThreads, 0, s>>>(P, A); else k_fwd_gc2<false, 0, 0><<<grid, kThreads, 0, s>>>(P, A); }
   } else {
     const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
     k_resid_fwd_gc<<<grid, kThreads, 0, s>>>(P, A);
@@ -1027,7 +1040,9 @@ int srm_backward_gc_impl(SrmHandle* h, int32_t B, int32_t R, const float* kx, co
   if (fused) {
     A.tiles_x = (P.W + G2X - 1) / G2X;
     const dim3 grid((unsigned)(A.tiles_x * ((P.H + G2Y - 1) / G2Y)), (unsigned)B);
-    if (P.n_wells > 64) k_adj_gc2<true><<<grid, kThreads, 0, s>>>(P, A); else k_adj_gc2<false><<<grid, kThreads, 0, s>>>(P, A);
+    const bool dflt = P.nog_i == 3 && P.ng_i == 6;
+    if (P.n_wells > 64) { if (dflt) k_adj_gc2<true, 3, 6><<<grid, kThreads, 0, s>>>(P, A); else k_adj_gc2<true, 0, 0><<<grid, kThreads, 0, s>>>(P, A); }
+    else { if (dflt) k_adj_gc2<false, 3, 6><<<grid, kThreads, 0, s>>>(P, A); else k_adj_gc2<false, 0, 0><<<grid, kThreads, 0, s>>>(P, A); }
   } else {
     const dim3 grid((unsigned)((P.H * P.W + kThreads - 1) / kThreads), (unsigned)B);
     k_resid_adj_gc<<<grid, kThreads, 0, s>>>(P, A);

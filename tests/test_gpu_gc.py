@@ -79,6 +79,7 @@ CASES = [
     dict(seed=15, wells="none"),
     dict(seed=16, B=4, R=2),                              # two realisations
     dict(seed=17, small_dp=True, sg_lo=0.2, sg_hi=0.5),   # cells with |p1 - p0| << 1 psi and == 0
+    dict(seed=20, D=2, H=6, W=9, B=2, nog=2, ng=4, sg_lo=0.2, sg_hi=0.5),              # Corey exponents other than the defaults the fused kernels are specialised for
     dict(seed=18, D=4, H=6, W=24, B=2, wells=("columns", 3), sg_lo=0.2, sg_hi=0.5),    # connections in every layer: the staged column lists (well_tile.cuh)
     dict(seed=19, D=3, H=6, W=24, B=2, wells=("columns", 10), sg_lo=0.2, sg_hi=0.5),   # more well columns in a tile than the lists hold: search path
 ]

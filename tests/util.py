@@ -102,7 +102,7 @@ def ulp_diff(a, b):
     return int(np.abs(ai - bi).max())
 
 
-def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, small_dp=False):
+def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, small_dp=False, nog=None, ng=None):
     cols = O.load_pvt_table(os.path.join(GOLDEN, "pvt_table.npz"))
     otab = O.build_spline_table(cols, O.GC_PROPS, order=1, lam=0.001)
     if wells == "two":
@@ -118,6 +118,9 @@ def gc_case(seed, B=2, D=2, H=5, W=6, sg_lo=0.2, sg_hi=0.75, wells="two", R=1, s
     conns = [dict(i=w["i"], j=w["j"], k=w["k"], type="producer", control="ORAT", value=w["value"], minimum_bhp=4100.0,
                   wellbore_radius=0.09525, completion_ratio=0.5, shutin_days=[[1000.0, 0.0]]) for w in wl]
     spec = srm.PhysicsSpec(D=D, H=H, W=W, wells=srm.config.wells_from_connections(conns), fluid_type="GC")
+    if nog is not None:          # other Corey exponents than the reference's defaults (3, 6): the kernels' run-time exponent path
+        ocfg.nog, ocfg.ng = float(nog), float(ng)
+        spec.corey_exponents = {"nog": float(nog), "ng": float(ng)}
     ptab = srm.pvt.SplineTables(knots=otab.c, w=otab.w, v=otab.v, order=1, properties=srm.pvt.GC_PROPERTIES)
     rng = np.random.default_rng(seed)
     shp = (B, D, H, W)
