@@ -87,3 +87,57 @@ def test_device_weave_feeds_the_batch_generator_order():
     assert torch.equal(f5[0, :, ..., 3], f5[K - 1, :, ..., 3])            # time is realisation independent
     tn = f5[0, :, 0, 0, 0, 3].cpu().numpy()
     assert np.allclose(tn, np.linspace(-1, 1, T), atol=1e-6)
+
+
+def _simfiles():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_simfiles.npz"))
+
+
+def test_restart_keywords_equal_the_reference_parser(tmp_path):
+    """formatted restart file: blocks per keyword and report step, bit for bit what parse_continuous_file returns
+    (simulation_data_process_pipeline.py:247-292), from the text and from a file on disk"""
+    from srm_b200 import data
+    g = _simfiles()
+    text = str(g["restart_text"])
+    keys = ["PRESSURE", "SGAS", "SOIL", "SWAT"]
+    p = tmp_path / "CASE.FUNRST"
+    p.write_text(text)
+    for src in (text, str(p)):
+        got = data.read_restart_keywords(src, keys)
+        for k in keys:
+            n = int(g[f"restart_{k}_n"])
+            assert len(got[k]) == n, k
+            for i in range(n):
+                assert got[k][i].dtype == np.float32 and np.array_equal(got[k][i], g[f"restart_{k}_{i}"]), (k, i)
+    assert got["SWAT"] == []
+    grid = data.restart_to_grid(got["PRESSURE"], 2, 3, 5)
+    assert grid.shape == (3, 2, 3, 5) and grid[1, 1, 2, 4] == got["PRESSURE"][1][-1] and grid[2, 0, 1, 0] == got["PRESSURE"][2][5]
+    with pytest.raises(ValueError):
+        data.restart_to_grid(got["PRESSURE"], 2, 3, 4)
+    assert data.restart_to_grid([], 2, 3, 5).shape == (0, 2, 3, 5)
+
+
+def test_rsm_columns_equal_the_reference_parser():
+    """run summary: segmented tab-separated tables, merged multi-line titles, compound (name, qualifier) columns, NaN for a
+    cell that is not a number, empty cells skipped, None for what is not there (parse_tabular_file_from_string, :148-245)"""
+    from srm_b200 import data
+    g = _simfiles()
+    spec = [["TIME"], ["WOPR", "15 15 1"], ["WOPR", "20  20 1"], "WGPR", "WWPR", "WBHP", "FPR"]
+    got = data.read_rsm_columns(str(g["rsm_text"]), spec)
+
+    def same(a, key):
+        if bool(g[key + "_none"]):
+            assert a is None, key
+        else:
+            assert a is not None and a.dtype == np.float32 and np.array_equal(a, g[key], equal_nan=True), key
+
+    for k in ("TIME", "WGPR", "WWPR", "WBHP", "FPR"):
+        same(got[k], "rsm_" + k)
+    for s in ("15 15 1", "20  20 1"):
+        same(got["WOPR"][s], f"rsm_WOPR|{s}")
+    assert got["TIME"].size == 12 and np.isnan(got["WOPR"]["15 15 1"][2]) and got["WGPR"].size == 5
+    # dictionary form of the spec, and page-break lines of a real file (a numeric line with no header above it) are skipped
+    paged = "1\n" + str(g["rsm_text"]).replace("\n\n\n", "\n\n1\n")
+    again = data.read_rsm_columns(paged, {"FPR": ["FPR"], "WBHP": ["WBHP"]})
+    assert np.array_equal(again["FPR"], got["FPR"]) and np.array_equal(again["WBHP"], got["WBHP"])
+    assert data.read_rsm_columns("", ["TIME"]) == {"TIME": None}
