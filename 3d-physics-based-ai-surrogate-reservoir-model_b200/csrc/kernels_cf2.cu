@@ -5,6 +5,7 @@
 //   * one CTA = one (128 x 8 | 64 x 16 | 32 x 32) column tile of ONE sample, marching over z; 256 threads, FOUR
 //     x-adjacent cells per thread (16-byte shared loads and global stores);
 //   * every global read is a TMA box copy (cp.async.bulk.tensor.4d, mbarrier complete_tx) into a ring of stages:
+//     (two rings: pressures / residual S planes ahead, the L2-resident face planes CF2_FS ahead)
 //     p1 and dom with their halo, p0, and the three static face-transmissibility planes (k_faces_cf2: zero on the
 //     grid boundary, so the zero fill of out-of-bounds box elements IS the reference's edge-replicating pad) --
 //     no address arithmetic, no boundary branches and no global loads in the instruction stream;
@@ -100,10 +101,10 @@ namespace {
 #define CF2_OCCA 2
 #endif
 #ifndef CF2_SF
-#define CF2_SF 3
+#define CF2_SF 4
 #endif
 #ifndef CF2_SA
-#define CF2_SA 3
+#define CF2_SA 4
 #endif
 #ifndef CF2_LXMAX
 #define CF2_LXMAX 32
@@ -130,8 +131,30 @@ constexpr int ABL = CF2_ABL;
 constexpr bool FREE = CF2_FREE != 0;
 constexpr int NGP = FREE ? 0 : 3;          // shared G planes
 static_assert(CPT == 4 || CPT == 2, "cells per thread");
-constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // TMA stages (planes in flight)
+#ifndef CF2_FS
+#define CF2_FS 2           // stages of the face ring (static, L2-resident planes: needed one iteration after their copy is issued)
+#endif
+// Two TMA rings.  The streamed fields (p1, p0, dom: HBM) and the static face planes (L2) have different latencies and
+// different first uses -- a plane's pressures are read when it ARRIVES (iteration k), its faces one iteration later under
+// the stencil -- so they complete on different mbarriers and are staged at different depths: the pressure ring runs S
+// planes ahead, the face ring CF2_FS.  One ring of three whole stages (the round-2 layout) left the copies of plane k+1
+// one stencil phase of lead (measured: 7-9 % of the stall samples at the stage wait, 11-14 % at the plane barrier behind
+// it); a fourth whole stage does not fit twice into an SM.
+constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // pressure-ring stages (planes in flight)
+constexpr int S_FACE = CF2_FS;
+#ifndef CF2_JOINT_F
+#define CF2_JOINT_F 1      // forward: faces and pressures of a plane in ONE stage on one mbarrier (four whole stages fit twice per SM)
+#endif
+// Measured on B200, config 5, K = 4 (tools/tune.py; forward / adjoint ms): one ring of 3 stages 2.99 / 3.28; forward with
+// one ring of 4 stages 2.89; forward with two rings 4 + 2 or 4 + 3: 2.98 (the second wait and the longer issue path cost
+// what the depth gains); forward with the faces of plane k-1 on the mbarrier of p(k): 3.01; adjoint with two rings
+// 4 + 2: 3.19 (four whole adjoint stages do not fit twice into an SM).  Hence: forward joint, adjoint split.
+constexpr bool JOINT_F = CF2_JOINT_F != 0;
+constexpr int FACE_STAGES_F = JOINT_F ? S_FWD : S_FACE;
+template <bool ADJ> __host__ __device__ constexpr int bar_bytes() { return ((ADJ || !JOINT_F) ? 128 : 64); }      // full[S], empty[S] (, fullf[S_FACE])
 static_assert(S_FWD >= 3 && S_ADJ >= 3, "plane k is waited for at the top of iteration k and refilled stages are issued at k-2+S: fewer than 3 stages deadlocks");
+static_assert(S_FACE >= 2, "the faces of plane k are issued in iteration k (stage of plane k-2 free) and read in iteration k+1");
+static_assert((2 * S_FWD + (JOINT_F ? 0 : S_FACE)) * 8 <= bar_bytes<false>() && (2 * S_ADJ + S_FACE) * 8 <= bar_bytes<true>(), "barrier block");
 
 __host__ __device__ constexpr int al128(int b) { return (b + 127) & ~127; }
 
@@ -143,25 +166,32 @@ struct Geo {
   static constexpr int BX = TX + 8, BY = TY + 2;    // haloed box: columns x0-4 .. x0+TX+3, rows y0-1 .. y0+TY
   static constexpr int FEX = TX + 4;                // east-face box: columns x0-4 .. x0+TX-1 (column 3 = W face of the tile's first cell)
   static constexpr int P1_B = BX * BY * 4, P0_B = TX * TY * 4, FE_B = FEX * TY * 4, FN_B = TX * (TY + 1) * 4, FU_B = TX * TY * 4;
+  // pressure stage: [p1 box | p0 box] (adjoint: [... | dom box]); face stage: [E | N | U]
   static constexpr int O_P1 = 0;
   static constexpr int O_P0 = O_P1 + al128(P1_B);
-  static constexpr int O_FE = O_P0 + al128(P0_B);
+  static constexpr int STAGE_F = O_P0 + al128(P0_B);                 // forward pressure stage
+  static constexpr int O_DM = STAGE_F;
+  static constexpr int STAGE_A = O_DM + al128(P1_B);                 // adjoint pressure stage (+ dom box)
+  static constexpr int O_FE = 0;
   static constexpr int O_FN = O_FE + al128(FE_B);
   static constexpr int O_FU = O_FN + al128(FN_B);
-  static constexpr int STAGE_F = O_FU + al128(FU_B);                 // forward stage
-  static constexpr int O_DM = STAGE_F;
-  static constexpr int STAGE_A = O_DM + al128(P1_B);                 // adjoint stage (+ dom box)
-  static constexpr int TX_F = P1_B + P0_B + FE_B + FN_B + FU_B;      // bytes a stage's mbarrier expects
+  static constexpr int STAGE_X = O_FU + al128(FU_B);                 // face stage
+  static constexpr int TX_F = P1_B + P0_B;                           // bytes a pressure stage's mbarrier expects
   static constexpr int TX_A = TX_F + P1_B;
+  static constexpr int TX_X = FE_B + FN_B + FU_B;                    // bytes a face stage's mbarrier expects
   static constexpr int RING = 2 * TX + 2 * TY;
   static constexpr int GPL = al128(P1_B);                            // one G plane (same layout as the p1 box)
   using WT = WellTile<NT, TX, TY, 16, 320>;           // the tile's connections (well_tile.cuh)
-  template <bool ADJ> static constexpr int total() {
-    return (ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F) + NGP * GPL + al128((int)sizeof(Cf2Tab)) + 128 /*barriers*/ + (int)sizeof(WT);
-  }
+  // shared-memory map: pressure ring | face ring | G planes | tables | mbarriers | well lists
+  template <bool ADJ> __host__ __device__ static constexpr int off_face() { return ADJ ? S_ADJ * STAGE_A : S_FWD * STAGE_F; }
+  template <bool ADJ> __host__ __device__ static constexpr int off_G() { return off_face<ADJ>() + (ADJ ? S_FACE : FACE_STAGES_F) * STAGE_X; }
+  template <bool ADJ> __host__ __device__ static constexpr int off_tab() { return off_G<ADJ>() + NGP * GPL; }
+  template <bool ADJ> __host__ __device__ static constexpr int off_bar() { return off_tab<ADJ>() + al128((int)sizeof(Cf2Tab)); }
+  template <bool ADJ> __host__ __device__ static constexpr int off_wells() { return off_bar<ADJ>() + bar_bytes<ADJ>(); }
+  template <bool ADJ> __host__ __device__ static constexpr int total() { return off_wells<ADJ>() + (int)sizeof(WT); }
 };
 
-#if CF2_SF == 3 && CF2_SA == 3 && CF2_CPT == 4 && CF2_NT == 256 && !CF2_FREE
+#if CF2_OCCF == 2 && CF2_OCCA == 2 && CF2_CPT == 4 && CF2_NT == 256 && !CF2_FREE
 // two CTAs per SM: dynamic + static (reduction scratch) + the 1 KB the system reserves per CTA, out of 228 KB
 static_assert(2 * (Geo<32>::total<true>() + 1024) <= 233472, "the adjoint no longer fits twice into an SM's shared memory");
 static_assert(2 * (Geo<32>::total<false>() + 1024) <= 233472, "the forward no longer fits twice into an SM's shared memory");
@@ -401,12 +431,12 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   using G = Geo<LX>;
   constexpr int S = S_FWD;
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_F);
-  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_F + NGP * G::GPL);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
+  float* Gs = reinterpret_cast<float*>(smem + G::template off_G<false>());
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + G::template off_tab<false>());
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::template off_bar<false>());
   uint64_t* empty = full + S;           // barrier-free march: one arrival per warp when it has read a stage for the last time
-  static_assert(2 * S * 8 <= 128, "barrier block");
-  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_F + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
+  uint64_t* fullf = empty + S;          // face ring (two-ring build only)
+  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + G::template off_wells<false>());
   unsigned char* flags = WTs.slot_of;
   double* red = reinterpret_cast<double*>(smem);      // reduction scratch: stage 0, after the last plane has been consumed
 
@@ -416,24 +446,37 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   const Place<LX> t = make_place<LX>(P, A.tiles_x);
   const int D = P.D;
   auto stage = [&](int s) { return smem + s * G::STAGE_F; };
-  auto issue = [&](int plane) {      // one thread
+  auto fstage = [&](int s) { return smem + G::template off_face<false>() + s * G::STAGE_X; };
+  auto issue_faces_on = [&](int plane, int slot, uint64_t* bar) {      // the static face planes of `plane`
+    unsigned char* st = fstage(slot);
+    const uint64_t keep = pol_evict_last();
+    tma_4d(st + G::O_FE, &m_fe, bar, t.x0 - 4, t.y0, plane, r, keep);
+    tma_4d(st + G::O_FN, &m_fn, bar, t.x0, t.y0 - 1, plane, r, keep);
+    tma_4d(st + G::O_FU, &m_fu, bar, t.x0, t.y0, plane, r, keep);
+  };
+  auto issue = [&](int plane) {      // one thread: the pressures of a plane; joint ring: and its faces, on the same mbarrier
     const int s = plane % S;
     unsigned char* st = stage(s);
-    const uint64_t keep = pol_evict_last(), strm = pol_evict_first();
-    mbar_expect_tx(&full[s], ABL == 2 ? G::P1_B + G::P0_B : G::TX_F);
+    const uint64_t strm = pol_evict_first();
+    const bool with_faces = JOINT_F && ABL != 2;
+    mbar_expect_tx(&full[s], G::TX_F + (with_faces ? G::TX_X : 0));
     tma_4d(st + G::O_P1, &m_p1, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
     tma_4d(st + G::O_P0, &m_p0, &full[s], t.x0, t.y0, plane, b, strm);
-    if (ABL != 2) {
-      tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
-      tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
-      tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
-    }
+    if (with_faces) issue_faces_on(plane, s, &full[s]);
+  };
+  auto issue_faces = [&](int plane) {      // one thread, face ring on its own mbarriers (two-ring build)
+    if (ABL == 2 || JOINT_F) return;
+    const int s = plane % S_FACE;
+    mbar_expect_tx(&fullf[s], G::TX_X);
+    issue_faces_on(plane, s, &fullf[s]);
   };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
+    if (!JOINT_F) for (int s = 0; s < S_FACE; ++s) mbar_init(&fullf[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < S && k < D; ++k) issue(k);
+    if (!JOINT_F) for (int k = 0; k < S_FACE && k < D; ++k) issue_faces(k);
   }
   for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
   // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
@@ -473,6 +516,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   // running indices of the march (no division in the plane loop): stage / parity / G buffer of the arriving plane k,
   // stage and G buffer of the plane m = k - 1 under the stencil, store pointer of plane m
   int sk = 0, phk = 0, gk = 0, sm = 0, gm = 0;
+  int fm = 0, phf = 0;      // face stage and parity of plane m
   float* domp = domf;
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
@@ -534,23 +578,29 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     }
     if (FREE) {
       // no block barrier: the stage of plane k-2 is refilled once every warp has arrived on its `empty` barrier
-      if (tid == 0 && k >= 2 && k - 2 + S < D) {
+      if (tid == 0 && k >= 2 && (k - 2 + S < D || (!JOINT_F && k - 2 + S_FACE < D))) {
         mbar_wait(&empty[(k - 2) % S], ((k - 2) / S) & 1);
-        issue(k - 2 + S);
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
     } else {
       __syncthreads();
-      // the stage of plane k-2 has been consumed by every thread: refill it
-      if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+      // the stages of plane k-2 have been consumed by every thread: refill them
+      if (tid == 0 && k >= 2) {
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
+      }
     }
     const int m = k - 1;
     if (m >= 0) {
       const unsigned char* st = stage(sm);
+      const unsigned char* sx = fstage(fm);
       const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
       const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
-      const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
-      const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
-      const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
+      const float* sfe = reinterpret_cast<const float*>(sx + G::O_FE);
+      const float* sfn = reinterpret_cast<const float*>(sx + G::O_FN);
+      const float* sfu = reinterpret_cast<const float*>(sx + G::O_FU);
+      if (!JOINT_F && ABL != 2) mbar_wait(&fullf[fm], phf);
       const float* Gm = Gs + gm * (G::GPL / 4);
       if (ABL == 1) {
         float q0[CPT], dv_[CPT];
@@ -703,6 +753,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         if ((tid & 31) == 0) mbar_arrive(&empty[sm]);
       }
       domp += P.H * P.W;
+      if (++fm == FACE_STAGES_F) { fm = 0; phf ^= 1; }
     }
     sm = sk; gm = gk;
     if (++sk == S) { sk = 0; phk ^= 1; }
@@ -740,12 +791,12 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   using G = Geo<LX>;
   constexpr int S = S_ADJ;
   extern __shared__ __align__(1024) unsigned char smem[];
-  float* Gs = reinterpret_cast<float*>(smem + S * G::STAGE_A);
-  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + S * G::STAGE_A + NGP * G::GPL);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)));
+  float* Gs = reinterpret_cast<float*>(smem + G::template off_G<true>());
+  Cf2Tab* T = reinterpret_cast<Cf2Tab*>(smem + G::template off_tab<true>());
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::template off_bar<true>());
   uint64_t* empty = full + S;
-  static_assert(2 * S * 8 <= 128, "barrier block");
-  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + S * G::STAGE_A + NGP * G::GPL + al128((int)sizeof(Cf2Tab)) + 128);
+  uint64_t* fullf = empty + S;          // face ring
+  typename G::WT& WTs = *reinterpret_cast<typename G::WT*>(smem + G::template off_wells<true>());
   unsigned char* flags = WTs.slot_of;
   double* red = reinterpret_cast<double*>(smem);      // reduction scratch: stage 0, after the last plane has been consumed
 
@@ -755,23 +806,32 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   const Place<LX> t = make_place<LX>(P, A.tiles_x);
   const int D = P.D;
   auto stage = [&](int s) { return smem + s * G::STAGE_A; };
-  auto issue = [&](int plane) {
+  auto fstage = [&](int s) { return smem + G::template off_face<true>() + s * G::STAGE_X; };
+  auto issue = [&](int plane) {      // one thread: pressures and residual of a plane
     const int s = plane % S;
     unsigned char* st = stage(s);
-    const uint64_t keep = pol_evict_last(), strm = pol_evict_first();
+    const uint64_t strm = pol_evict_first();
     mbar_expect_tx(&full[s], G::TX_A);
     tma_4d(st + G::O_P1, &m_p1, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
     tma_4d(st + G::O_DM, &m_dm, &full[s], t.x0 - 4, t.y0 - 1, plane, b, strm);
     tma_4d(st + G::O_P0, &m_p0, &full[s], t.x0, t.y0, plane, b, strm);
-    tma_4d(st + G::O_FE, &m_fe, &full[s], t.x0 - 4, t.y0, plane, r, keep);
-    tma_4d(st + G::O_FN, &m_fn, &full[s], t.x0, t.y0 - 1, plane, r, keep);
-    tma_4d(st + G::O_FU, &m_fu, &full[s], t.x0, t.y0, plane, r, keep);
+  };
+  auto issue_faces = [&](int plane) {      // one thread: the static face planes of a plane
+    const int s = plane % S_FACE;
+    unsigned char* st = fstage(s);
+    const uint64_t keep = pol_evict_last();
+    mbar_expect_tx(&fullf[s], G::TX_X);
+    tma_4d(st + G::O_FE, &m_fe, &fullf[s], t.x0 - 4, t.y0, plane, r, keep);
+    tma_4d(st + G::O_FN, &m_fn, &fullf[s], t.x0, t.y0 - 1, plane, r, keep);
+    tma_4d(st + G::O_FU, &m_fu, &fullf[s], t.x0, t.y0, plane, r, keep);
   };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
+    for (int s = 0; s < S_FACE; ++s) mbar_init(&fullf[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < S && k < D; ++k) issue(k);
+    for (int k = 0; k < S_FACE && k < D; ++k) issue_faces(k);
   }
   for (int e = tid; e < (int)(sizeof(Cf2Tab) / 4); e += NT) reinterpret_cast<uint32_t*>(T)[e] = reinterpret_cast<const uint32_t*>(A.T)[e];
   // the tile's connections: column lists staged in shared memory; lists that do not fit keep the per-plane search
@@ -814,6 +874,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
   float pn[CPT], Gn[CPT], dn[CPT], Gpn[CPT], Apn[CPT];
 
   int sk = 0, phk = 0, gk = 0, sm = 0, gm = 0;      // running indices, as in the forward
+  int fm = 0, phf = 0;
   int64_t go = fo;                                  // store offset of plane m
   CF2_LOOP_PRAGMA
   for (int k = 0; k <= D; ++k) {
@@ -878,23 +939,29 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       for (int c = 0; c < CPT; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; dn[c] = dc[c]; Gpn[c] = 0.f; Apn[c] = 0.f; }
     }
     if (FREE) {
-      if (tid == 0 && k >= 2 && k - 2 + S < D) {
+      if (tid == 0 && k >= 2 && (k - 2 + S < D || k - 2 + S_FACE < D)) {
         mbar_wait(&empty[(k - 2) % S], ((k - 2) / S) & 1);
-        issue(k - 2 + S);
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
     } else {
       __syncthreads();
-      if (tid == 0 && k >= 2 && k - 2 + S < D) issue(k - 2 + S);
+      if (tid == 0 && k >= 2) {
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
+      }
     }
     const int m = k - 1;
     if (m >= 0) {
       const unsigned char* st = stage(sm);
+      const unsigned char* sx = fstage(fm);
       const float* sp1 = reinterpret_cast<const float*>(st + G::O_P1);
       const float* sdm = reinterpret_cast<const float*>(st + G::O_DM);
       const float* sp0 = reinterpret_cast<const float*>(st + G::O_P0);
-      const float* sfe = reinterpret_cast<const float*>(st + G::O_FE);
-      const float* sfn = reinterpret_cast<const float*>(st + G::O_FN);
-      const float* sfu = reinterpret_cast<const float*>(st + G::O_FU);
+      const float* sfe = reinterpret_cast<const float*>(sx + G::O_FE);
+      const float* sfn = reinterpret_cast<const float*>(sx + G::O_FN);
+      const float* sfu = reinterpret_cast<const float*>(sx + G::O_FU);
+      mbar_wait(&fullf[fm], phf);
       const float* Gm = Gs + gm * (G::GPL / 4);
       float pS[CPT], pN[CPT], gS[CPT], gN[CPT], dS[CPT], dN[CPT], fE[CPT], fS[CPT], fN[CPT], fU[CPT], p0[CPT];
       ldv(pS, sp1 + t.own - G::BX); ldv(pN, sp1 + t.own + G::BX);
@@ -1042,6 +1109,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         if ((tid & 31) == 0) mbar_arrive(&empty[sm]);
       }
       go += P.H * P.W;
+      if (++fm == S_FACE) { fm = 0; phf ^= 1; }
     }
     sm = sk; gm = gk;
     if (++sk == S) { sk = 0; phk ^= 1; }
