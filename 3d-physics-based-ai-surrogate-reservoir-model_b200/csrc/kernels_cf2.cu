@@ -497,8 +497,12 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   float* domf = A.dom + (int64_t)b * P.N + (int64_t)(t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
   const int cell0 = (t.y0 + t.ry) * P.W + t.x0 + CPT * t.lx;
 
+  static_assert(PACK, "the forward is written for the packed f32x2 forms");
   float a_dom = 0.f, a_tde = 0.f, a_mb = 0.f;
-  f2 a_dom2 = 0ull, a_tde2 = 0ull, a_mb2 = 0ull;      // the same partial sums, one lane per cell of a pair (PACK)
+  f2 a_dom2 = 0ull, a_tde2 = 0ull, a_mb2 = 0ull;      // partial sums, one lane per cell of a pair
+  // invBg is anchor + slope * dx with the anchor split into a float and its low part; inside the cached interval both
+  // levels share the anchor, so the low parts cancel in A1 - A0 -- only cells on the table path contribute theirs
+  float a_mbl = 0.f;
   f2 fz2[CPT / 2] = {};                               // upper z-face term of the plane below, packed
   double d_dom = 0.0, d_tde = 0.0, d_mb = 0.0, d_ibc = 0.0;
 
@@ -509,9 +513,9 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
   const float4 c0 = T->cur0, c1 = T->cur1;
 
   // z window in registers: plane m (cur) and the arriving plane (next); the upper z-face term of plane m-1
-  float pc[CPT] = {}, Gc[CPT] = {}, fz[CPT] = {};
-  float a1c[CPT] = {}, a1lc[CPT] = {};      // invBg at level n+1 of plane m: value, anchor low part
-  float pn[CPT], Gn[CPT], a1n[CPT], a1ln[CPT];
+  float pc[CPT] = {}, Gc[CPT] = {};
+  float a1c[CPT] = {};      // invBg at level n+1 of plane m
+  float pn[CPT], Gn[CPT], a1n[CPT];
 
   // running indices of the march (no division in the plane loop): stage / parity / G buffer of the arriving plane k,
   // stage and G buffer of the plane m = k - 1 under the stencil, store pointer of plane m
@@ -529,28 +533,16 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       bool in = true;
       if (ABL == 1) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) { Gn[c] = pn[c]; a1n[c] = 0.f; a1ln[c] = 0.f; }
+        for (int c = 0; c < CPT; ++c) { Gn[c] = pn[c]; a1n[c] = 0.f; }
         if (!FREE) stv(Gb + t.own, Gn);
       } else {
-      if constexpr (PACK) {
 #pragma unroll
-        for (int h = 0; h < CPT / 2; ++h) {
-          in = in && (pn[2 * h] > c0.x) && (pn[2 * h] < c0.y) && (pn[2 * h + 1] > c0.x) && (pn[2 * h + 1] < c0.y);
-          const f2 dx = sub2(PK2(pn, h), bc(c0.z));
-          const f2 a1 = fma2(bc(c1.x), dx, bc(c0.w));
-          UPK2(a1, a1n, h);
-          UPK2(mul2(a1, fma2(bc(c1.z), dx, bc(c1.y))), Gn, h);
-          a1ln[2 * h] = c1.w; a1ln[2 * h + 1] = c1.w;
-        }
-      } else {
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        in = in && (pn[c] > c0.x) && (pn[c] < c0.y);
-        const float dx = pn[c] - c0.z;
-        a1n[c] = fmaf(c1.x, dx, c0.w);
-        a1ln[c] = c1.w;
-        Gn[c] = a1n[c] * fmaf(c1.z, dx, c1.y);
-      }
+      for (int h = 0; h < CPT / 2; ++h) {
+        in = in && (pn[2 * h] > c0.x) && (pn[2 * h] < c0.y) && (pn[2 * h + 1] > c0.x) && (pn[2 * h + 1] < c0.y);
+        const f2 dx = sub2(PK2(pn, h), bc(c0.z));
+        const f2 a1 = fma2(bc(c1.x), dx, bc(c0.w));
+        UPK2(a1, a1n, h);
+        UPK2(mul2(a1, fma2(bc(c1.z), dx, bc(c1.y))), Gn, h);
       }
       if (!in) {
 #pragma unroll
@@ -561,7 +553,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           const float4 f = T->e1[kk];
           const float dx = x - e.x;
           a1n[c] = fmaf(e.z, dx, e.y);
-          a1ln[c] = f.w;
+          a_mbl += f.w - c1.w;
           Gn[c] = a1n[c] * fmaf(f.x, dx, e.w);
         }
       }
@@ -574,7 +566,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; a1ln[c] = a1lc[c]; }
+      for (int c = 0; c < CPT; ++c) { pn[c] = pc[c]; Gn[c] = Gc[c]; a1n[c] = a1c[c]; }
     }
     if (FREE) {
       // no block barrier: the stage of plane k-2 is refilled once every warp has arrived on its `empty` barrier
@@ -629,21 +621,19 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       for (int i = 1; i < CPT; ++i) Fx[i] = fE[i - 1] * (Gc[i - 1] + Gc[i]) * (pc[i - 1] - pc[i]);
       Fx[CPT] = fE[CPT - 1] * (Gc[CPT - 1] + gE) * (pc[CPT - 1] - pE);
       float dvf[CPT], rest[CPT], domv[CPT];
-      // level-n PVT of the four cells: A0 = invBg(p0), Ap = its slope, low part of the anchor value
-      float A0[CPT], Ap[CPT], A0l[CPT];
+      // level-n PVT of the four cells: A0 = invBg(p0) and cp = K1 A0' + K2 A0; inside the cached interval the slope is the
+      // interval's (a broadcast operand, no per-cell copy), anything else takes the table path
+      f2 A02[CPT / 2], cp2[CPT / 2];
       bool in0 = true;
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
-        if constexpr (!PACK) A0[c] = fmaf(c1.x, p0[c] - c0.z, c0.w);
-        Ap[c] = c1.x;
-        A0l[c] = c1.w;
-      }
-      if constexpr (PACK) {
+      for (int c = 0; c < CPT; ++c) in0 = in0 && (p0[c] > c0.x) && (p0[c] < c0.y);
 #pragma unroll
-        for (int h = 0; h < CPT / 2; ++h) UPK2(fma2(bc(c1.x), sub2(PK2(p0, h), bc(c0.z)), bc(c0.w)), A0, h);
+      for (int h = 0; h < CPT / 2; ++h) {
+        A02[h] = fma2(bc(c1.x), sub2(PK2(p0, h), bc(c0.z)), bc(c0.w));
+        cp2[h] = fma2(bc(P.K1), bc(c1.x), mul2(bc(P.K2), A02[h]));
       }
       if (!in0) {
+        float A0[CPT], cpv[CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const float x = cf2_clamp(T, p0[c]);
@@ -652,11 +642,14 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           const float4 f = T->e1[kk];
           const float dx = x - e.x;
           A0[c] = fmaf(e.z, dx, e.y);
-          Ap[c] = (dx < 1e-5f) ? f.y : e.z;          // on a knot: mean of the two slopes
-          A0l[c] = f.w;
+          const float Ap = (dx < 1e-5f) ? f.y : e.z;          // on a knot: mean of the two slopes
+          cpv[c] = fmaf(P.K1, Ap, P.K2 * A0[c]);
+          a_mbl -= f.w - c1.w;
         }
+#pragma unroll
+        for (int h = 0; h < CPT / 2; ++h) { A02[h] = PK2(A0, h); cp2[h] = PK2(cpv, h); }
       }
-      if constexpr (PACK) {
+      {
         // y and z faces, the cell-local part: two cells per instruction (the x faces above stay scalar: a cell's W
         // neighbour sits in the other half of its pair)
 #pragma unroll
@@ -668,32 +661,14 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           const f2 fu = mul2(mul2(PK2(fU, h), add2(Gc2, PK2(Gn, h))), sub2(pc2, PK2(pn, h)));     // upper z face; the plane above takes -fu
           flux = add2(flux, sub2(fu, fz2[h]));
           fz2[h] = fu;
-          const f2 A02 = PK2(A0, h);
-          const f2 cp = fma2(bc(P.K1), PK2(Ap, h), mul2(bc(P.K2), A02));
+          const f2 cp = cp2[h];
           const f2 tde = mul2(bc(cT), cp);
           const f2 cacp = mul2(bc(cA), cp), dp10 = sub2(pc2, PK2(p0, h));
           UPK2(mul2(bc(P.dv), flux), dvf, h);
           UPK2(P.tde_in_dom ? fma2(cacp, dp10, tde) : mul2(cacp, dp10), rest, h);
           a_tde2 = fma2(tde, tde, a_tde2);
-          a_mb2 = add2(a_mb2, add2(sub2(PK2(a1c, h), A02), sub2(PK2(a1lc, h), PK2(A0l, h))));
+          a_mb2 = add2(a_mb2, sub2(PK2(a1c, h), A02[h]));
         }
-      } else {
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        float flux = Fx[c + 1] - Fx[c];
-        flux = fmaf(fS[c] * (Gc[c] + gS[c]), pc[c] - pS[c], flux);
-        flux = fmaf(fN[c] * (Gc[c] + gN[c]), pc[c] - pN[c], flux);
-        const float fu = fU[c] * (Gc[c] + Gn[c]) * (pc[c] - pn[c]);     // upper z face; the plane above takes -fu
-        flux += fu - fz[c];
-        fz[c] = fu;
-        // cell-local part: accumulation, truncation term, material balance
-        const float cp = fmaf(P.K1, Ap[c], P.K2 * A0[c]);
-        const float tde = cT * cp;
-        dvf[c] = P.dv * flux;
-        rest[c] = P.tde_in_dom ? fmaf(cA * cp, pc[c] - p0[c], tde) : cA * cp * (pc[c] - p0[c]);
-        a_tde = fmaf(tde, tde, a_tde);
-        a_mb += (a1c[c] - A0[c]) + (a1lc[c] - A0l[c]);
-      }
       }
       if (tile_wells && has_well && !wt_overflow) {     // wells in this thread's columns, from the staged lists (scatter_nd sums duplicates)   well_rate_bhp_Subclassed.py:128-132
 #pragma unroll
@@ -727,26 +702,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
           }
         }
       }
-      if constexpr (PACK) {
 #pragma unroll
-        for (int h = 0; h < CPT / 2; ++h) {
-          const f2 dm = add2(PK2(dvf, h), PK2(rest, h));
-          UPK2(dm, domv, h);
-          if (t.valid) a_dom2 = fma2(dm, dm, a_dom2);
-        }
-        if (t.valid) stv_cs(domp, domv);
-        else { a_tde2 = 0ull; a_mb2 = 0ull; }
-      } else {
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) domv[c] = dvf[c] + rest[c];
-      if (t.valid) {
-        stv_cs(domp, domv);
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) a_dom = fmaf(domv[c], domv[c], a_dom);
-      } else {
-        a_tde = 0.f; a_mb = 0.f;
+      for (int h = 0; h < CPT / 2; ++h) {
+        const f2 dm = add2(PK2(dvf, h), PK2(rest, h));
+        UPK2(dm, domv, h);
+        a_dom2 = fma2(dm, dm, a_dom2);
       }
-      }
+      if (t.valid) stv_cs(domp, domv);      // threads outside the grid (zero-filled boxes) drop their sums after the march
       }
       if (FREE) {         // this warp has read plane m's stage for the last time
         __syncwarp();
@@ -759,14 +721,15 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     if (++sk == S) { sk = 0; phk ^= 1; }
     if (++gk == 3) gk = 0;
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; a1lc[c] = a1ln[c]; }
+    for (int c = 0; c < CPT; ++c) { pc[c] = pn[c]; Gc[c] = Gn[c]; a1c[c] = a1n[c]; }
     if ((k & 7) == 7) {
-      if constexpr (PACK) { a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2); a_dom2 = a_tde2 = a_mb2 = 0ull; }
+      a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2) + a_mbl; a_dom2 = a_tde2 = a_mb2 = 0ull; a_mbl = 0.f;
       d_dom += (double)a_dom; d_tde += (double)a_tde; d_mb += (double)a_mb; a_dom = a_tde = a_mb = 0.f;
     }
   }
-  if constexpr (PACK) { a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2); }
+  a_dom = hsum(a_dom2); a_tde = hsum(a_tde2); a_mb = hsum(a_mb2) + a_mbl;
   double acc4[4] = {d_dom + (double)a_dom, d_ibc, d_tde + (double)a_tde, (d_mb + (double)a_mb) * (double)mbk};
+  if (!t.valid) { acc4[0] = 0.0; acc4[2] = 0.0; acc4[3] = 0.0; }
   __syncthreads();
   block_reduce<4>(acc4, red);
   if (tid == 0) {
