@@ -1061,11 +1061,9 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
           g1v[c] += (sd * dc[c] - smb) * dq;
         }
       }
-      if (t.valid) {
+      if (t.valid) {      // threads outside the grid (zero-filled boxes) drop their sum after the march
         stv_cs(A.gp0 + go, g0v);
         stv_cs(A.gp1 + go, g1v);
-      } else {
-        a_g1 = 0.f; a_g1_2 = 0ull;
       }
       if (FREE) {
         __syncwarp();
@@ -1085,7 +1083,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     }
   }
   if constexpr (PACK) a_g1 = hsum(a_g1_2);
-  double acc1[1] = {d_g1 + (double)a_g1};
+  double acc1[1] = {t.valid ? d_g1 + (double)a_g1 : 0.0};
   __syncthreads();
   block_reduce<1>(acc1, red);
   if (tid == 0) atomicAdd(&A.gdt1_acc[b], acc1[0]);
