@@ -107,18 +107,17 @@ namespace {
 #define CF2_SA 4
 #endif
 #ifndef CF2_LXMAX
-#define CF2_LXMAX 32
+#define CF2_LXMAX 16         // lanes along x: 16 = a 64 x 16 tile (a warp owns 64 x 2 cells) -- measured against 128 x 8 and 32 x 32 below
 #endif
 #ifndef CF2_CPT
 #define CF2_CPT 4          // x-adjacent cells per thread: 4 (16-byte shared loads) or 2 (8-byte, half the registers)
 #endif
 #define CF2_STR2(x) #x
 #define CF2_STR(x) CF2_STR2(x)
-#ifdef CF2_UNROLL
-#define CF2_LOOP_PRAGMA _Pragma(CF2_STR(unroll CF2_UNROLL))
-#else
-#define CF2_LOOP_PRAGMA
+#ifndef CF2_UNROLL
+#define CF2_UNROLL 2       // two planes per trip: the plane-to-plane register rotation (cur <- next) becomes renaming
 #endif
+#define CF2_LOOP_PRAGMA _Pragma(CF2_STR(unroll CF2_UNROLL))
 constexpr int NT = CF2_NT;
 constexpr int CPT = CF2_CPT;
 #ifndef CF2_ABL
@@ -195,6 +194,7 @@ struct Geo {
 // two CTAs per SM: dynamic + static (reduction scratch) + the 1 KB the system reserves per CTA, out of 228 KB
 static_assert(2 * (Geo<32>::total<true>() + 1024) <= 233472, "the adjoint no longer fits twice into an SM's shared memory");
 static_assert(2 * (Geo<32>::total<false>() + 1024) <= 233472, "the forward no longer fits twice into an SM's shared memory");
+static_assert(2 * (Geo<16>::total<true>() + 1024) <= 233472 && 2 * (Geo<16>::total<false>() + 1024) <= 233472, "64 x 16 tiles no longer fit twice");
 #endif
 
 struct Cf2Args {
