@@ -128,6 +128,21 @@ constexpr int ABL = CF2_ABL;
 #define CF2_FREE 0         // 1: warps march independently (no block barrier, no shared G plane; measured: no faster); 0: one barrier per plane
 #endif
 constexpr bool FREE = CF2_FREE != 0;
+#ifndef CF2_SPLITBAR
+#define CF2_SPLITBAR 1     // the plane barrier as an mbarrier: arrive after the G plane is written, wait at the END of the iteration
+#endif
+// What the plane barrier of iteration k orders is (i) G(k) written before stencil(k) reads it in iteration k+1, (ii) every
+// warp done with stencil(k-2) before the stages of plane k-2 are refilled and before G buffer (k+1) % 3 is overwritten.
+// stencil(k-1), which follows it in program order, needs none of that: with the arrival right after the G stores and the
+// wait behind the stencil the warps of a CTA may drift apart by a whole stencil phase (table-path warps, the warp that
+// issues the copies, halo duty) before anyone stalls.  One arrival per warp (empty[0] is free when !CF2_FREE).
+// Measured (config 5, K = 4): forward 2.62 -> 2.57 ms.  The price is that the refills are issued one stencil phase later;
+// the adjoint's two-deep face ring cannot pay it (3.03 -> 3.68 ms), so the adjoint keeps __syncthreads (CF2_SPLITBAR_A).
+#ifndef CF2_SPLITBAR_A
+#define CF2_SPLITBAR_A 0
+#endif
+constexpr bool SPLITBAR = CF2_SPLITBAR != 0 && !FREE;
+constexpr bool SPLITBAR_A = CF2_SPLITBAR_A != 0 && !FREE;
 constexpr int NGP = FREE ? 0 : 3;          // shared G planes
 static_assert(CPT == 4 || CPT == 2, "cells per thread");
 #ifndef CF2_FS
@@ -575,6 +590,9 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
         if (k - 2 + S < D) issue(k - 2 + S);
         if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
+    } else if (SPLITBAR) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[0]);
     } else {
       __syncthreads();
       // the stages of plane k-2 have been consumed by every thread: refill them
@@ -716,6 +734,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
       }
       domp += P.H * P.W;
       if (++fm == FACE_STAGES_F) { fm = 0; phf ^= 1; }
+    }
+    if (SPLITBAR) {
+      mbar_wait(&empty[0], k & 1);
+      if (tid == 0 && k >= 2) {
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
+      }
     }
     sm = sk; gm = gk;
     if (++sk == S) { sk = 0; phk ^= 1; }
@@ -907,6 +932,9 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
         if (k - 2 + S < D) issue(k - 2 + S);
         if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
+    } else if (SPLITBAR_A) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[0]);
     } else {
       __syncthreads();
       if (tid == 0 && k >= 2) {
@@ -1071,6 +1099,13 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       }
       go += P.H * P.W;
       if (++fm == S_FACE) { fm = 0; phf ^= 1; }
+    }
+    if (SPLITBAR_A) {
+      mbar_wait(&empty[0], k & 1);
+      if (tid == 0 && k >= 2) {
+        if (k - 2 + S < D) issue(k - 2 + S);
+        if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
+      }
     }
     sm = sk; gm = gk;
     if (++sk == S) { sk = 0; phk ^= 1; }
