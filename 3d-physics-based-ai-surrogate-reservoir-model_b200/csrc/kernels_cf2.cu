@@ -141,6 +141,18 @@ constexpr bool FREE = CF2_FREE != 0;
 #ifndef CF2_SPLITBAR_A
 #define CF2_SPLITBAR_A 0
 #endif
+#ifndef CF2_ISSUER_F
+#define CF2_ISSUER_F 1     // which thread issues the refills: 0 = thread 0, 1 = the first lane of the LAST warp
+#endif
+#ifndef CF2_ISSUER_A
+#define CF2_ISSUER_A 0
+#endif
+// The refill of a stage is ~75 instructions on ONE lane (five or six tensor copies: descriptor address, coordinates, elect
+// loop each), i.e. a quarter of a warp's plane.  With 64 x 16 tiles the halo-ring duty sits on warps 0..4, so the forward's
+// copies go to a warp without it (config 5, K = 4: 2.57 -> 2.49 ms; the last three warps in turn: 2.51); the adjoint, whose
+// warps meet at a block barrier every plane, measured the same either way (3.03 / 3.04 ms) and keeps thread 0.
+template <bool ADJ>
+__device__ __forceinline__ bool is_issuer(int tid) { return tid == (((ADJ ? CF2_ISSUER_A : CF2_ISSUER_F) != 0) ? NT - 32 : 0); }
 constexpr bool SPLITBAR = CF2_SPLITBAR != 0 && !FREE;
 constexpr bool SPLITBAR_A = CF2_SPLITBAR_A != 0 && !FREE;
 constexpr int NGP = FREE ? 0 : 3;          // shared G planes
@@ -596,7 +608,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     } else {
       __syncthreads();
       // the stages of plane k-2 have been consumed by every thread: refill them
-      if (tid == 0 && k >= 2) {
+      if (k >= 2 && is_issuer<false>(tid)) {
         if (k - 2 + S < D) issue(k - 2 + S);
         if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCF) k_fwd_cf2(const __grid_constant_
     }
     if (SPLITBAR) {
       mbar_wait(&empty[0], k & 1);
-      if (tid == 0 && k >= 2) {
+      if (k >= 2 && is_issuer<false>(tid)) {
         if (k - 2 + S < D) issue(k - 2 + S);
         if (!JOINT_F && k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
@@ -937,7 +949,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
       if ((tid & 31) == 0) mbar_arrive(&empty[0]);
     } else {
       __syncthreads();
-      if (tid == 0 && k >= 2) {
+      if (k >= 2 && is_issuer<true>(tid)) {
         if (k - 2 + S < D) issue(k - 2 + S);
         if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
@@ -1102,7 +1114,7 @@ __global__ void __launch_bounds__(NT, CF2_OCCA) k_adj_cf2(const __grid_constant_
     }
     if (SPLITBAR_A) {
       mbar_wait(&empty[0], k & 1);
-      if (tid == 0 && k >= 2) {
+      if (k >= 2 && is_issuer<true>(tid)) {
         if (k - 2 + S < D) issue(k - 2 + S);
         if (k - 2 + S_FACE < D) issue_faces(k - 2 + S_FACE);
       }
