@@ -474,7 +474,8 @@ def run_ours(args):
         cf_f = float(np.mean([ec[2 * i].elapsed_time(ec[2 * i + 1]) for i in range(args.steps)]))
         cf_a = float(np.mean([ec[2 * i + 1].elapsed_time(ec[2 * i + 2]) for i in range(args.steps)]))
         closed = {"ms_per_step": cf_ms, "fwd_ms": cf_f, "bwd_ms": cf_a, "value_per_gpu": N / (cf_ms * 1e-3),
-                  "kernels": "k_fwd_cf2 / k_adj_cf2 (kernels_cf2.cu: every global read a TMA box copy, cp.async.bulk.tensor.4d)",
+                  "kernels": "k_fwd_cf2 / k_adj_cf2 (kernels_cf2.cu: 64 x 16 column tiles marching over z, every global read a TMA box copy "
+                             "-- cp.async.bulk.tensor.4d -- into mbarrier rings four planes deep)",
                   "error_vs_fp64_oracle": "dom <= 1.9e-7, gp0 <= 2.5e-6, gp1 <= 8e-7 of max (gate of tests/test_gpu_closed_form.py); on the full "
                                           "cfg5 grid dom 1.8e-7, gp1 2.9e-7, gdt1 4e-8, gp0 1.6e-5 (tests/test_gpu_full_grid.py)",
                   "distance_to_fp32_reference_order": dist_cf}
@@ -615,6 +616,9 @@ def run_ours(args):
             closed["frac"] = closed["achieved"] / peak
             closed["forward_frac"] = one * ab_f / (closed["fwd_ms"] * 1e-3) / peak
             closed["adjoint_frac"] = one * ab_a / (closed["bwd_ms"] * 1e-3) / peak
+            tr_cf = measured_traffic(args.workload, "closed_form")      # DRAM bytes of one forward + one adjoint launch at this batch
+            closed["traffic"] = tr_cf.get("bytes_per_step") if tr_cf else None
+            closed["traffic_source"] = tr_cf.get("source") if tr_cf else None
             roof["closed_form"] = closed
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
