@@ -27,6 +27,13 @@ CASES = [
     dict(W=33, H=7, D=2, T=1, K=1, seed=2005, wells="none"),
     dict(W=64, H=20, D=5, T=2, K=1, seed=2006, wells=("crowded", 4)),    # staged column lists (well_tile.cuh), a duplicate connection
     dict(W=64, H=20, D=5, T=2, K=1, seed=2007, wells=("crowded", 18)),   # more well columns in a tile than the lists hold
+    # the lean TMA pair's rings: columns shorter than the four-plane pressure ring / the two-plane face ring, tiles cut by the
+    # grid on both axes (64 x 16 tiles above 47 cells of width, 32 x 32 below), several tiles across
+    dict(W=8, H=5, D=1, T=2, K=1, seed=2021),
+    dict(W=72, H=33, D=2, T=2, K=1, seed=2022, all_layers=True),
+    dict(W=128, H=17, D=3, T=1, K=2, seed=2023, all_layers=True),
+    dict(W=200, H=16, D=7, T=1, K=1, seed=2024),
+    dict(W=48, H=40, D=4, T=1, K=1, seed=2025),
 ]
 
 
