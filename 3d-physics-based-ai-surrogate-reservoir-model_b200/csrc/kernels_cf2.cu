@@ -2,15 +2,15 @@
 //
 // Same formulas as kernels_cf.cu (order-1 polyharmonic interpolant in its exact piecewise-linear form, flux in
 // difference form, truncation bracket == 0); what changes is how a cell-timestep is paid for:
-//   * one CTA = one (128 x 8 | 64 x 16 | 32 x 32) column tile of ONE sample, marching over z; 256 threads, FOUR
-//     x-adjacent cells per thread (16-byte shared loads and global stores);
-//   * every global read is a TMA box copy (cp.async.bulk.tensor.4d, mbarrier complete_tx) into a ring of stages:
-//     (two rings: pressures / residual S planes ahead, the L2-resident face planes CF2_FS ahead)
-//     p1 and dom with their halo, p0, and the three static face-transmissibility planes (k_faces_cf2: zero on the
-//     grid boundary, so the zero fill of out-of-bounds box elements IS the reference's edge-replicating pad) --
-//     no address arithmetic, no boundary branches and no global loads in the instruction stream;
+//   * one CTA = one 64 x 16 column tile (32 x 32 on narrow grids; 128 x 8 with -DCF2_LXMAX=32) of ONE sample, marching
+//     over z; 256 threads, FOUR x-adjacent cells per thread (16-byte shared loads and global stores), a warp = 64 x 2 cells;
+//   * every global read is a TMA box copy (cp.async.bulk.tensor.4d, mbarrier complete_tx) into rings of stages four planes
+//     deep (forward: one ring of whole stages; adjoint: pressures / residual four planes ahead, the L2-resident face planes
+//     two, on their own mbarriers): p1 and dom with their halo, p0, and the three static face-transmissibility planes
+//     (k_faces_cf2: zero on the grid boundary, so the zero fill of out-of-bounds box elements IS the reference's
+//     edge-replicating pad) -- no address arithmetic, no boundary branches and no global loads in the instruction stream;
 //   * G = invBg*invug is evaluated once per cell and plane (tile + halo ring) and shared through a triple-buffered
-//     shared plane, one barrier per plane; x neighbours travel by warp shuffles, z neighbours in registers, and the
+//     shared plane, one barrier per plane (forward: an mbarrier, arrival and wait a stencil phase apart); x neighbours travel by warp shuffles, z neighbours in registers, and the
 //     z-face terms are formed once and handed to the plane above;
 //   * PVT: bucket -> interval -> one 16-byte coefficient load per pressure, all from shared memory.
 // Algorithmic bytes per cell-timestep: forward 12 + 12/T, adjoint 20 + 12/T.
@@ -165,7 +165,7 @@ static_assert(CPT == 4 || CPT == 2, "cells per thread");
 // the stencil -- so they complete on different mbarriers and are staged at different depths: the pressure ring runs S
 // planes ahead, the face ring CF2_FS.  One ring of three whole stages (the round-2 layout) left the copies of plane k+1
 // one stencil phase of lead (measured: 7-9 % of the stall samples at the stage wait, 11-14 % at the plane barrier behind
-// it); a fourth whole stage does not fit twice into an SM.
+// it); a fourth whole ADJOINT stage does not fit twice into an SM (the forward's does: CF2_JOINT_F).
 constexpr int S_FWD = CF2_SF, S_ADJ = CF2_SA;      // pressure-ring stages (planes in flight)
 constexpr int S_FACE = CF2_FS;
 #ifndef CF2_JOINT_F
