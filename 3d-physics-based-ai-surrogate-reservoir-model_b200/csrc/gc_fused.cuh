@@ -61,6 +61,16 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* g) {
 // Experiment switch: ask for the own-cell packs of the NEXT plane one plane ahead with prefetch.global (1: L2, 2: L1).
 // Measured slower on B200 (cfg4: forward 16.6 -> 17.2 ms, adjoint 20.8 -> 25.3 ms): the prefetches are extra L2
 // requests on a path that is already bound by the gather request rate.  Off by default.
+#ifndef G2_UNROLL_F
+#define G2_UNROLL_F 1
+#endif
+#ifndef G2_UNROLL_A
+#define G2_UNROLL_A 2      // measured on config 4: adjoint 4.11 -> 4.07 ms at K = 8 (the forward loses 3.6 % with two planes per trip: 1)
+#endif
+#define G2_STR2(x) #x
+#define G2_STR(x) G2_STR2(x)
+#define G2_LOOP_F _Pragma(G2_STR(unroll G2_UNROLL_F))
+#define G2_LOOP_A _Pragma(G2_STR(unroll G2_UNROLL_A))
 #ifndef G2_PF
 #define G2_PF 0
 #endif
@@ -158,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_fwd_gc2(const __grid_constant__
   VisF vP = vC;
   __syncthreads();
 
+  G2_LOOP_F
   for (int k = 0; k < P.D; ++k) {
     const int c = k * HW + g.col;
     const int buf = k & 1;
@@ -417,6 +428,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_adj_gc2(const __grid_constant__
   VisA vP = vC;
   __syncthreads();
 
+  G2_LOOP_A
   for (int k = 0; k < P.D; ++k) {
     const int c = k * HW + g.col;
     const int buf = k & 1;
