@@ -149,3 +149,35 @@ def test_well_data_processor_integer_bookkeeping():
     t = torch.tensor([5.0, 15.0, 25.0]).view(3, 1, 1, 1).expand(3, 1, 4, 4)
     s = wdp.conn_shutins_idx(t, [[0, 1, 1], [0, 2, 3]], [[[10.0, 20.0]], [[1000.0, 0.0]]])
     assert s[:, 0, 1, 1].tolist() == [1, 0, 1] and s[:, 0, 2, 3].tolist() == [1, 1, 1] and int(s.sum()) == 5
+
+
+def test_committed_bench_line_meets_the_contract():
+    """the bench line of the final build (profiles/r5_bench_cfg5.json, written by `python bench.py` on a B200) carries every key
+    the contract names, and its roofline numbers follow from its own timings"""
+    import json
+    import math
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r5_bench_cfg5.json")
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "cell-timesteps/s" and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["dtype"] == "f32"
+    assert d["warmup"] >= 3 and "cfg5" in d["config"]["workload"] and "model" not in d["config"]
+    cells = d["config"]["cells_per_gpu_per_step"]
+    assert cells == 256 * 256 * 64 * 32 * 8
+    assert math.isclose(d["value"], cells / (d["ms_per_step"] * 1e-3), rel_tol=1e-6)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and math.isclose(r["frac"], r["achieved"] / r["peak"], rel_tol=1e-9)
+    assert math.isclose(r["achieved"], cells * r["alg_bytes_per_cell"] / (r["ms"] * 1e-3) / 1e9, rel_tol=1e-6)
+    assert r["traffic"] and r["traffic"] >= cells * r["alg_bytes_per_cell"]          # measured DRAM bytes are not below the compulsory ones
+    assert math.isclose(r["step"]["ms"], d["ms_per_step"], rel_tol=1e-9) and r["step"]["alg_bytes_per_cell"] == 28.25
+    cf = r["closed_form"]
+    assert math.isclose(cf["frac"], cells * 28.25 / (cf["ms_per_step"] * 1e-3) / 1e9 / r["peak"], rel_tol=1e-6)
+    assert "k_fwd_cf2" in cf["kernels"] and cf["distance_to_fp32_reference_order"]["gp1_rel_to_max"] < 1e-3
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] >= 2 * 4 * cells and e["d2h_bytes_per_step"] >= 2 * 4 * cells
+    assert 0 < e["value"] < d["value"]                     # host buffers in the timed region: never faster than resident inputs
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
