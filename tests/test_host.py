@@ -181,3 +181,15 @@ def test_committed_bench_line_meets_the_contract():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["unit"] == d["unit"] and c["sample"]
     assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_cpu_baseline_leg_of_the_bench_runs_the_oracle():
+    """bench.py's cpu_baseline / --impl reference leg: the oracle port on host threads, a bounded sample of the named grid
+    (config 1 in full; config 5 as 16-layer z-slabs of the same x-y extent)"""
+    import bench
+    info, done, el = bench.cpu_oracle_throughput("cfg1", target_seconds=0.2, max_samples=2)
+    assert info["kind"] == "port" and info["unit"] == "cell-timesteps/s" and info["cores"] >= 1
+    assert done >= 39 * 39 and info["value"] > 0 and "39x39x1" in info["sample"]
+    c, spec = bench.workload("cfg5")
+    assert (spec.W, spec.H, spec.D, c["T"], c["K"]) == (256, 256, 64, 32, 8) and len(spec.wells) == 2048 and spec.use_blocking_factor
+    assert bench.alg_bytes_per_cell(32, False) == 28.25 and bench.alg_bytes_per_cell(24, True) == 80.0 + 8.0 / 24
